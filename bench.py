@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — 256^3 volume-pair flow + interpolation throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A "step" = one pass of the hot path (Model.inference: 3-scale 3-D IFNet + warps + blend) over one batch of
+synthetic droplet-shaped volume pairs per GPU.  Pairs are batch-sharded over ranks, no data-path collective
+("scaling": "weak").  One JSON line is printed by rank 0; see DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nd, spatial, pairs per GPU per step, BASELINE.json config it stands for)
+    "flow3d_droplet256": (3, (256, 256, 256), 1, "Flow-3D droplet-shaped 256^3 byte volume pairs, ensemble batch-sharded"),
+    "flow3d_rect128": (3, (128, 128, 128), 4, "Flow-3D IFNet on synthetic 3D textured rectangle 128^3, batch 4"),
+    "flow2d_droplet": (2, (160, 224), 64, "Flow-2D droplet-shaped 160x224 monochrome, batch 64"),
+}
+
+
+def ifnet_macs(nd, sp):
+    """Algorithmic multiply-accumulates of one IFNet inference on one pair (logical channels)."""
+    widths = {2: (128, 96, 64), 3: (128, 64, 64)}[nd]
+    k0 = 3 if nd == 2 else 4
+    nf = 2 * nd
+    vox = 1
+    for s in sp:
+        vox *= s
+    total = 0
+    for (c, cin, scale) in zip(widths, (2, 5 + nf, 5 + nf), (4, 2, 1)):
+        v_in = vox // scale ** nd
+        v1, v2 = v_in // 2 ** nd, v_in // 4 ** nd
+        total += v1 * cin * (c // 2) * k0 ** nd + v2 * (c // 2) * c * k0 ** nd          # conv0
+        total += 8 * v2 * c * c * 3 ** nd                                                 # convblock0..3
+        total += 2 * v2 * c * (c // 2) * 4 ** nd                                          # conv1.0, conv2.0 (ConvT: in positions)
+        total += v1 * (c // 2) * (nf + 1) * 4 ** nd                                       # conv1.2, conv2.2
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_rate(nd, sp, pairs, steps, warmup):
+    """The reference's CPU path for the same workload: oracle/ifnet_ref.py (bit-identical restatement of the reference
+    modules, pinned in tests/golden) with all host threads.  Returns (pairs_per_s, seconds_per_step, threads)."""
+    import torch
+    from oracle.ifnet_ref import ModelRef
+    from opticalflowscivis_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    m = ModelRef(nd).eval()
+    if nd == 3:
+        a, _, b = synth.droplet3d_u8(pairs, sp[0])
+        img0, img1 = torch.from_numpy(a).float() / 255.0, torch.from_numpy(b).float() / 255.0
+    else:
+        a, _, b = synth.droplet2d(pairs, *sp)
+        img0, img1 = torch.from_numpy(a), torch.from_numpy(b)
+    for _ in range(warmup):
+        m.inference(img0, img1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.inference(img0, img1)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return pairs / dt, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    nd, sp, pairs, desc = WORKLOADS[args.workload]
+    full_vox = 1
+    for s in sp:
+        full_vox *= s
+    # bounded sample per step: a 128^3 sub-volume pair (1/8 of a 256^3 pair) for the 3-D headline workload
+    if args.workload == "flow3d_droplet256":
+        s_sp, s_pairs, frac, sample = (128, 128, 128), 1, 1.0 / 8.0, "one 128^3 sub-volume pair per step = 1/8 of a 256^3 pair"
+    elif args.workload == "flow3d_rect128":
+        s_sp, s_pairs, frac, sample = (64, 64, 64), 1, 1.0 / 8.0, "one 64^3 sub-volume pair per step = 1/8 of a 128^3 pair"
+    else:
+        s_sp, s_pairs, frac, sample = sp, 8, 8.0, "8 pairs of 160x224 per step"
+    rate, dt, threads = cpu_reference_rate(nd, s_sp, s_pairs, args.steps, min(args.warmup, 1))
+    value = frac / dt if nd == 3 else rate
+    unit = "pairs/s"
+    line = {
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "describes": desc, "spatial": list(sp), "pairs_per_gpu_per_step": pairs},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(workload):
+    return {"flow3d_droplet256": "256^3 volume-pair interps/sec", "flow3d_rect128": "128^3 volume-pair interps/sec",
+            "flow2d_droplet": "160x224 frame-pair interps/sec"}[workload]
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from opticalflowscivis_b200 import ops, synth
+    from opticalflowscivis_b200.rife import Model2D, Model3D
+
+    nd, sp, pairs, desc = WORKLOADS[args.workload]
+    if args.pairs:
+        pairs = args.pairs
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(1234)
+    model = (Model3D if nd == 3 else Model2D)(local_rank=local_rank, precision=args.precision, engine=args.engine)
+    model.eval()
+
+    # synthetic inputs: member seed = 1234 + global pair index (SURVEY.md §8d cfg 4)
+    if nd == 3:
+        a, _, b = synth.droplet3d_u8(pairs, sp[0], seed=1234 + rank * pairs)
+        h0, h1 = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()          # uint8 host volumes
+    else:
+        a, _, b = synth.droplet2d(pairs, *sp, seed=1234 + rank * pairs)
+        h0, h1 = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    as_f32 = (lambda t: t.float().div_(255.0)) if nd == 3 else (lambda t: t)
+    d0, d1 = as_f32(h0.to(dev)), as_f32(h1.to(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model.inference(d0, d1)
+
+    out_host = torch.empty((pairs, 1) + tuple(sp), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        x0, x1 = as_f32(h0.to(dev, non_blocking=True)), as_f32(h1.to(dev, non_blocking=True))
+        res = model.inference(x0, x1)
+        merged = res[0] if nd == 3 else res[0][2]
+        out_host.copy_(merged, non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM (`value`) with per-class CUDA-event timers
+    timer = ops.LaunchTimer()
+    ops.TIMER = timer
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+    ops.TIMER = None
+    launches = ops.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    classes = timer.totals()
+
+    # ---- timed region 2: end to end through Model.inference with pinned-host inputs and a D2H read of the result
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    total_pairs = pairs * world * args.steps
+    value = total_pairs / (ms / 1e3)
+    e2e_value = total_pairs / (ms_e2e / 1e3)
+    vox = 1
+    for s in sp:
+        vox *= s
+    flops_pair = 2.0 * ifnet_macs(nd, sp)
+    conv_cls = [k for k in classes if k.startswith("conv_")]
+    conv_ms = sum(classes[k][1] for k in conv_cls)
+    conv_n = sum(classes[k][0] for k in conv_cls)
+    share = {k: round(v[1] / ms, 4) for k, v in classes.items()}
+    dominant = max(classes, key=lambda k: classes[k][1]) if classes else None
+    # tensor roofline of the conv engine: algorithmic FLOPs of all conv launches of the timed region / their summed time
+    conv_tf = flops_pair * pairs * args.steps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+    roofline = {"kernel": "+".join(sorted(conv_cls)), "bound": "tensor", "achieved": conv_tf, "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s", "frac": (conv_tf / peaks["tf_sustained"]) if conv_tf else None, "traffic": None,
+                "peak_source": peaks["src"] + " (sustained bf16)", "launches": conv_n, "share_of_step": round(conv_ms / ms, 4),
+                "algorithmic_flops_per_pair": flops_pair}
+    # HBM roofline of the fused warp+blend kernel (the "warp HBM GB/s vs peak" half of the metric)
+    wb = classes.get("warp_blend")
+    roofline_warp = None
+    if wb:
+        nfl = 2 * nd
+        # bytes per voxel and launch: 2 img + 2nd flow + 2 warped always; + mask read, merged + sigmoid writes when requested
+        per_step = []
+        for i in range(3):
+            full = (nd == 2) or i == 2
+            per_step.append((2 + nfl + 2 + (3 if full else 0)) * 4 * vox * pairs)
+        bytes_total = sum(per_step) * args.steps
+        gbs = bytes_total / (wb[1] / 1e3) / 1e9
+        roofline_warp = {"kernel": "warp_blend_%dd_kernel" % nd, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
+                         "launches": wb[0], "share_of_step": round(wb[1] / ms, 4)}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        with contextlib.redirect_stdout(io.StringIO()):
+            if args.workload == "flow3d_droplet256":
+                rate, dt, thr = cpu_reference_rate(3, (256, 256, 256), 1, 1, 0)
+                sample = "one full 256^3 pair, single cold call"
+            elif args.workload == "flow3d_rect128":
+                rate, dt, thr = cpu_reference_rate(3, (128, 128, 128), 1, 2, 1)
+                sample = "one 128^3 pair x 2 calls after 1 warm-up"
+            else:
+                rate, dt, thr = cpu_reference_rate(2, sp, 64, 3, 1)
+                sample = "64 pairs of 160x224 x 3 calls after 1 warm-up"
+        cpu_baseline = {"value": rate, "unit": "pairs/s", "cores": thr, "kind": "port", "sample": sample}
+
+    in_bytes = int(h0.numel() * h0.element_size() * 2)
+    line = {
+        "metric": metric_name(args.workload), "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "describes": desc, "spatial": list(sp), "pairs_per_gpu_per_step": pairs,
+                   "precision": args.precision, "conv_engine": model.flownet._engine(),
+                   "l2": "working set per step (>1 GB) exceeds the 126 MB L2; no explicit flush",
+                   "weights": "random init, seed 1234"},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_warp": roofline_warp, "kernel_time_share": share, "dominant_kernel_class": dominant,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        with contextlib.redirect_stdout(sys.stderr):
+            pass
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+/* ofsv.h — C ABI of libofsv.so, the B200 (sm_100a) implementation of the OpticalFlowSciVis hot path.
+ *
+ * This is the drop-in boundary.  The reference is pure Python; its only native FFI on this path
+ * is the un-vendored pybind module `correlation_cuda` (UPFlow/model/correlation_package/correlation.py:26-27,42-43),
+ * everything else bottoms out in ATen calls (F.grid_sample, F.interpolate, nn.Conv*, nn.ConvTranspose*, nn.PReLU).
+ * Each entry point below names the reference call site it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller (PyTorch allocates it); the
+ *     library never allocates or frees caller-visible memory;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); work is enqueued, not
+ *     synchronised; the library is stateless apart from a thread-local error string;
+ *   - every function returns 0 on success, a negative OFSV_E* code otherwise (nothing is launched on a
+ *     validation error); `ofsv_last_error()` returns the message for the calling thread;
+ *   - fp32 tensors are contiguous NCHW / NCDHW exactly as the reference passes them; the conv engine uses
+ *     channels-last activations (NHWC / NDHWC) that only ever live inside the library's callers.
+ */
+#ifndef OFSV_H_
+#define OFSV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFSV_OK 0
+#define OFSV_EINVAL (-1)  /* bad shape / null pointer / misalignment */
+#define OFSV_ECUDA (-2)   /* CUDA runtime or driver error (message has the cudaError string) */
+#define OFSV_ENOSUP (-3)  /* configuration outside what the kernels implement */
+
+/* Which ATen build the fp32 warp arithmetic reproduces bit-for-bit:
+ *   OFSV_REF_CPU  : flow / float((S-1)/2) true division, trilinear sum without FMA (ATen CPU kernels)
+ *   OFSV_REF_CUDA : flow * float(1.0/((S-1)/2)) (ATen div_true_kernel_cuda fast path), FMA-contracted sums */
+#define OFSV_REF_CPU 0
+#define OFSV_REF_CUDA 1
+
+const char* ofsv_version(void);
+const char* ofsv_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t ofsv_launch_count(void);
+
+/* ---- a1: warp(tenInput, tenFlow), 2-D — Flow-2D/model/warplayer.py:7-26 (F.grid_sample bilinear/border/align_corners).
+ * src,out (N,C,H,W); flow (N,2,H,W); lin_x = torch.linspace(-1,1,W), lin_y = torch.linspace(-1,1,H) (device). */
+int ofsv_warp2d_f32(const float* src, const float* flow, const float* lin_x, const float* lin_y, float* out,
+                    int N, int C, int H, int W, int ref_mode, void* stream);
+
+/* ---- a2: warp, 3-D — Flow-3D/model/warplayer.py:9-41.  Axis-rotating:
+ * src,out (N,C,D,H,W); flow (N,3,D,H,W); lin_h/lin_d/lin_w = torch.linspace(-1,1,H|D|W).
+ * out[n,c,d,h,w] = trilinear(src[n,c]; x = u(lin_h[h]+f0/((H-1)/2), W), y = u(lin_d[d]+f1/((D-1)/2), H),
+ *                                      z = u(lin_w[w]+f2/((W-1)/2), D)),  u(g,S) = clip(((g+1)/2)*(S-1), 0, S-1). */
+int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
+                    float* out, int N, int C, int D, int H, int W, int ref_mode, void* stream);
+
+/* ---- a6 (+a1/a2 fused): sigmoid(mask) ; warp(img0, flow[:, :nd]) ; warp(img1, flow[:, nd:2nd]) ; blend.
+ * Flow-2D/model/IFNet.py:189-192,240 ; Flow-3D/model/IFNet.py:186-191,242.
+ * img0,img1,mask_logit (N,1,·); flow (N,2*nd,·).  Any of warped0/warped1/merged/mask_sig may be NULL (not written). */
+int ofsv_warp_blend_2d_f32(const float* img0, const float* img1, const float* flow, const float* mask_logit,
+                           const float* lin_x, const float* lin_y, float* warped0, float* warped1, float* merged,
+                           float* mask_sig, int N, int H, int W, int ref_mode, void* stream);
+int ofsv_warp_blend_3d_f32(const float* img0, const float* img1, const float* flow, const float* mask_logit,
+                           const float* lin_h, const float* lin_d, const float* lin_w, float* warped0, float* warped1,
+                           float* merged, float* mask_sig, int N, int D, int H, int W, int ref_mode, void* stream);
+/* plain blend of already-warped frames: merged = w0*sigmoid(m) + w1*(1-sigmoid(m)) */
+int ofsv_blend_f32(const float* w0, const float* w1, const float* mask_logit, float* merged, int64_t n, void* stream);
+
+/* ---- a8: correlation_cuda.forward / .backward — UPFlow/model/correlation_package/correlation.py:26-27,42-43,
+ * call sites UPFlow/model/upflow.py:649,652 with (pad 4, kernel 1, max_disp 4, stride1 1, stride2 1, mult 1) only.
+ * f1,f2 (B,C,H,W); out (B,81,H,W) written at out + b*out_batch_stride (elements) so the caller can point it into the
+ * channel-concatenated estimator input (upflow.py:657).  apply_leaky fuses LeakyReLU(leaky_slope) (upflow.py:655-656). */
+int ofsv_corr81_fwd_f32(const float* f1, const float* f2, float* out, int B, int C, int H, int W, float leaky_slope,
+                        int apply_leaky, int64_t out_batch_stride, void* stream);
+int ofsv_corr81_bwd_f32(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B, int C, int H,
+                        int W, void* stream);
+
+/* ---- a10: upsample2d_flow_as(inputs, target_as, "bilinear", if_rate) — UPFlow/model/pwc_modules.py:77-90. */
+int ofsv_upsample_flow_ac_f32(const float* in, float* out, int B, int h_in, int w_in, int h_out, int w_out, int if_rate,
+                              void* stream);
+
+/* ---- a11: WarpingLayer_no_div.forward — UPFlow/model/pwc_modules.py:184-207 (zeros padding, default
+ * align_corners=False, times the grid_sample(ones) >= 1 validity mask). */
+int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode,
+                            void* stream);
+
+/* =====================================================================================================
+ * IFBlock / IFNet engine (a3, a4, a5) — Flow-2D/model/IFNet.py:16-27,34-122,144-276 ; Flow-3D/model/IFNet.py.
+ * Activations are channels-last: [N][D][H][W][Cs] with Cs the channel count rounded up to a multiple of 16
+ * (2-D tensors use D = 1).  `act_dtype`: OFSV_F32 (exact-arithmetic validation path) or OFSV_BF16 (tensor cores).
+ * ===================================================================================================== */
+#define OFSV_F32 0
+#define OFSV_BF16 1
+
+/* IFBlock input builder: F.interpolate(x, 1/scale) ‖ F.interpolate(flow, 1/scale)*(1/scale) ‖ torch.cat
+ * (IFNet.py:84-93 2-D, :82-90 3-D; the cat of IFNet.py:174 / :166).  Sources are the fp32 NC(D)HW tensors of the
+ * reference (any of warped0/warped1/mask/flow may be NULL for block0: then only img0,img1 are packed).
+ * nd = 2|3, scale ∈ {1,2,4}; dst [N][D/s][H/s][W/s][Cs], channel order img0,img1,warped0,warped1,mask,flow[0..2nd). */
+int ofsv_pack_block_input(const float* img0, const float* img1, const float* warped0, const float* warped1,
+                          const float* mask, const float* flow, void* dst, int act_dtype, int nd, int N, int D, int H,
+                          int W, int scale, int Cs, void* stream);
+
+#define OFSV_MAX_TAPS 64
+/* One convolution layer in "tap" form.  For every phase ph, every virtual output position o = (oz,oy,ox) in
+ * [0,Do)x[0,Ho)x[0,Wo):
+ *   y[n, o*out_stride + parity(ph), co] = act( bias[co] + sum_t sum_ci x[n, o*in_stride + tap_off[ph*ntaps+t], ci]
+ *                                                                   * w[ph][t][ci][co] ) (+ residual)
+ * with x read as zero outside [0,Di)x[0,Hi)x[0,Wi).
+ *   Conv(k,s,p):            nphase = 1, ntaps = k^nd, tap_off = k_idx - p, in_stride = s, out_stride = 1.
+ *   ConvTranspose(4,2,1):   nphase = 2^nd (one per output parity; parity bits of ph = (z,y,x), x lowest), ntaps = 2^nd,
+ *                           in_stride = 1, out_stride = 2; per axis parity 0 uses kernel taps {1 @ 0, 3 @ -1},
+ *                           parity 1 uses {2 @ 0, 0 @ +1}. */
+typedef struct ofsv_conv_desc {
+  int32_t nd;                         /* 2 or 3 (2-D uses D = 1 and tap_off[.][0] = 0) */
+  int32_t N, Di, Hi, Wi, Cin_s;       /* input  [N][Di][Hi][Wi][Cin_s], Cin_s % 16 == 0 */
+  int32_t Do, Ho, Wo;                 /* virtual output grid (per phase) */
+  int32_t Dy, Hy, Wy, Cout_s;         /* physical output tensor [N][Dy][Hy][Wy][Cout_s], Cout_s % 8 == 0 */
+  int32_t Cout_w;                     /* padded Cout of w / bias / prelu, Cout_w % 16 == 0, Cout_s <= Cout_w */
+  int32_t in_stride, out_stride;
+  int32_t nphase, ntaps;              /* nphase * ntaps <= OFSV_MAX_TAPS */
+  int8_t tap_off[OFSV_MAX_TAPS][4];   /* (z,y,x,unused) input offset of tap [ph*ntaps + t] */
+  int32_t has_prelu, has_residual;
+  int32_t in_dtype, out_dtype;        /* OFSV_F32 | OFSV_BF16 */
+} ofsv_conv_desc;
+
+/* SIMT (CUDA-core, fp32 accumulate) engine: exact-order validation path and small-channel layers.
+ * w: fp32 [nphase][ntaps][Cin_s][Cout_w]; bias, prelu: fp32 [Cout_w]; residual: same layout/dtype as y (or NULL). */
+int ofsv_conv_simt(const ofsv_conv_desc* d, const void* x, const float* w, const float* bias, const float* prelu,
+                   const void* residual, void* y, void* stream);
+
+/* tcgen05/TMEM implicit-GEMM engine (bf16 operands, fp32 accumulate in tensor memory).
+ * w: bf16 [nphase][ntaps][Cin_s/KC][Cout_w][KC] (K-major B tiles, KC = largest of 64/32/16 dividing Cin_s). */
+int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                 const void* residual, void* y, void* stream);
+
+/* IFBlock output stage: flow/mask deltas at block resolution -> full resolution (IFNet.py:115-116 / :118-119,
+ * F.interpolate(.., scale) and flow*scale), then flow += flow_d ; mask += mask_d (IFNet.py:177-178 / :169-170).
+ * head [N][D/s][H/s][W/s][Cs] channels-last fp32 (channels 0..2nd-1 flow, 2nd mask); flow_prev/mask_prev may be NULL
+ * (block0).  flow_out (N,2nd,·), mask_out (N,1,·) fp32 NC(D)HW. */
+int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, const float* mask_prev, float* flow_out,
+                           float* mask_out, int nd, int N, int D, int H, int W, int scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFSV_H_ */

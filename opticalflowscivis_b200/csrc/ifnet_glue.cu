@@ -1,0 +1,194 @@
+// Memory-bound stages around the IFBlock convolutions (a4, a5): the block-input builder (down-resize + flow rescale +
+// concat -> channels-last) and the block-output stage (up-resize + flow*scale + residual add -> fp32 NC(D)HW).
+// Both follow ATen's upsample_{bi,tri}linear (align_corners=False) index/weight arithmetic:
+//   src = rscale*(dst+0.5)-0.5 (clamped at 0), i0 = min(floor(src), n-1), i1 = i0 + (i0 < n-1), l1 = src-i0, l0 = 1-l1,
+//   value = nested  t0*l0 + t1*l1  with W innermost (SURVEY.md Appendix A "Resize identities").
+#include "ofsv_common.cuh"
+
+namespace ofsv {
+
+template <typename T>
+__device__ __forceinline__ T cvt(float v);
+template <>
+__device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// mean of the 2^nd samples {s*o + s/2 - 1, s*o + s/2} per axis == F.interpolate(1/s) for s in {2,4}; s = 1 reads directly.
+template <int ND>
+__device__ __forceinline__ float down_sample(const float* __restrict__ vol, int H, int W, int oz, int oy, int ox, int s) {
+  if (s == 1) return __ldg(vol + ((int64_t)oz * H + oy) * W + ox);
+  const int o = s / 2 - 1;
+  const int x = ox * s + o, y = oy * s + o, z = ND == 3 ? oz * s + o : 0;
+  float r[2];
+#pragma unroll
+  for (int dz = 0; dz < (ND == 3 ? 2 : 1); ++dz) {
+    float rows[2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const float* p = vol + ((int64_t)(z + dz) * H + (y + dy)) * W + x;
+      rows[dy] = __fadd_rn(__fmul_rn(__ldg(p), 0.5f), __fmul_rn(__ldg(p + 1), 0.5f));
+    }
+    r[dz] = __fadd_rn(__fmul_rn(rows[0], 0.5f), __fmul_rn(rows[1], 0.5f));
+  }
+  if (ND == 3) return __fadd_rn(__fmul_rn(r[0], 0.5f), __fmul_rn(r[1], 0.5f));
+  return r[0];
+}
+
+template <int ND, typename T>
+__global__ void __launch_bounds__(256)
+    pack_block_input_kernel(const float* __restrict__ img0, const float* __restrict__ img1,
+                            const float* __restrict__ warped0, const float* __restrict__ warped1,
+                            const float* __restrict__ mask, const float* __restrict__ flow, T* __restrict__ dst, int N,
+                            int D, int H, int W, int s, int Cs) {
+  const int Do = ND == 3 ? D / s : 1, Ho = H / s, Wo = W / s;
+  const int64_t V = (int64_t)D * H * W, Vo = (int64_t)Do * Ho * Wo, total = (int64_t)N * Vo;
+  const float inv_s = 1.0f / (float)s;
+  constexpr int NF = 2 * ND;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Vo);
+    int r = (int)(i - (int64_t)n * Vo);
+    const int ox = r % Wo; r /= Wo;
+    const int oy = r % Ho;
+    const int oz = r / Ho;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.0f;
+    v[0] = down_sample<ND>(img0 + (int64_t)n * V, H, W, oz, oy, ox, s);
+    v[1] = down_sample<ND>(img1 + (int64_t)n * V, H, W, oz, oy, ox, s);
+    if (flow != nullptr) {
+      v[2] = down_sample<ND>(warped0 + (int64_t)n * V, H, W, oz, oy, ox, s);
+      v[3] = down_sample<ND>(warped1 + (int64_t)n * V, H, W, oz, oy, ox, s);
+      v[4] = down_sample<ND>(mask + (int64_t)n * V, H, W, oz, oy, ox, s);
+#pragma unroll
+      for (int c = 0; c < NF; ++c)  // F.interpolate(flow, 1/scale) * 1. / scale   (IFNet.py:92 / :88)
+        v[5 + c] = __fmul_rn(down_sample<ND>(flow + ((int64_t)n * NF + c) * V, H, W, oz, oy, ox, s), inv_s);
+    }
+    T* o = dst + i * Cs;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = cvt<T>(v[c]);
+    for (int c = 16; c < Cs; ++c) o[c] = cvt<T>(0.0f);
+  }
+}
+
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp up_index(int dst, int n_in, float rscale) {
+  float src = __fsub_rn(__fmul_rn(rscale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.0f ? 0.0f : src;
+  Lerp L;
+  L.i0 = min((int)src, n_in - 1);
+  L.i1 = L.i0 + (L.i0 < n_in - 1 ? 1 : 0);
+  L.l1 = fminf(fmaxf(__fsub_rn(src, (float)L.i0), 0.0f), 1.0f);
+  L.l0 = __fsub_rn(1.0f, L.l1);
+  return L;
+}
+
+// head: [N][Dh][Hh][Wh][Cs] fp32 channels-last, channels 0..NF-1 flow delta, NF mask delta.
+template <int ND>
+__global__ void __launch_bounds__(256)
+    head_upsample_add_kernel(const float* __restrict__ head, int Cs, const float* __restrict__ flow_prev,
+                             const float* __restrict__ mask_prev, float* __restrict__ flow_out,
+                             float* __restrict__ mask_out, int N, int D, int H, int W, int s) {
+  constexpr int NF = 2 * ND, NC = NF + 1;
+  const int Dh = ND == 3 ? D / s : 1, Hh = H / s, Wh = W / s;
+  const int64_t V = (int64_t)D * H * W, total = (int64_t)N * V;
+  const float rscale = 1.0f / (float)s, fs = (float)s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const int64_t r = i - (int64_t)n * V;
+    const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((int64_t)W * H));
+    float v[NC];
+    const float* hb = head + (int64_t)n * Dh * Hh * Wh * Cs;
+    if (s == 1) {
+      const float* p = hb + r * Cs;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[c] = __ldg(p + c);
+    } else {
+      const Lerp lx = up_index(x, Wh, rscale), ly = up_index(y, Hh, rscale);
+      Lerp lz; lz.i0 = lz.i1 = 0; lz.l0 = 1.0f; lz.l1 = 0.0f;
+      if (ND == 3) lz = up_index(z, Dh, rscale);
+      float acc_z[2][NC];
+#pragma unroll
+      for (int dz = 0; dz < (ND == 3 ? 2 : 1); ++dz) {
+        const int zz = dz ? lz.i1 : lz.i0;
+        float acc_y[2][NC];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int yy = dy ? ly.i1 : ly.i0;
+          const float* p0 = hb + (((int64_t)zz * Hh + yy) * Wh + lx.i0) * Cs;
+          const float* p1 = hb + (((int64_t)zz * Hh + yy) * Wh + lx.i1) * Cs;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc_y[dy][c] = __fadd_rn(__fmul_rn(__ldg(p0 + c), lx.l0), __fmul_rn(__ldg(p1 + c), lx.l1));
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc_z[dz][c] = __fadd_rn(__fmul_rn(acc_y[0][c], ly.l0), __fmul_rn(acc_y[1][c], ly.l1));
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        v[c] = ND == 3 ? __fadd_rn(__fmul_rn(acc_z[0][c], lz.l0), __fmul_rn(acc_z[1][c], lz.l1)) : acc_z[0][c];
+    }
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      float f = __fmul_rn(v[c], fs);  // F.interpolate(flow, scale) * scale
+      if (flow_prev) f = __fadd_rn(ldg_stream(flow_prev + ((int64_t)n * NF + c) * V + r), f);  // flow = flow + flow_d
+      flow_out[((int64_t)n * NF + c) * V + r] = f;
+    }
+    float m = v[NF];
+    if (mask_prev) m = __fadd_rn(ldg_stream(mask_prev + i), m);
+    mask_out[i] = m;
+  }
+}
+
+static inline int grid_1d(int64_t total) {
+  int64_t b = cdiv(total, 256);
+  const int64_t cap = 148 * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace ofsv
+
+using namespace ofsv;
+
+extern "C" int ofsv_pack_block_input(const float* img0, const float* img1, const float* warped0, const float* warped1,
+                                     const float* mask, const float* flow, void* dst, int act_dtype, int nd, int N,
+                                     int D, int H, int W, int scale, int Cs, void* stream) {
+  OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_pack_block_input: nd must be 2 or 3");
+  OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_pack_block_input: scale %d not in {1,2,4}", scale);
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1, "ofsv_pack_block_input: bad shape");
+  OFSV_REQUIRE((nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
+               "ofsv_pack_block_input: spatial dims must be multiples of scale");
+  OFSV_REQUIRE(Cs >= 16 && Cs % 16 == 0, "ofsv_pack_block_input: Cs must be a multiple of 16");
+  if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(img0 && img1 && dst, "ofsv_pack_block_input: null pointer");
+  OFSV_REQUIRE(flow == nullptr || (warped0 && warped1 && mask), "ofsv_pack_block_input: flow needs warped0/1 and mask");
+  const int64_t total = (int64_t)N * (nd == 3 ? D / scale : 1) * (H / scale) * (W / scale);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_1d(total);
+#define GO(ND, T) pack_block_input_kernel<ND, T><<<g, 256, 0, st>>>(img0, img1, warped0, warped1, mask, flow, (T*)dst, N, D, H, W, scale, Cs)
+  if (act_dtype == OFSV_F32) { if (nd == 2) GO(2, float); else GO(3, float); }
+  else if (act_dtype == OFSV_BF16) { if (nd == 2) GO(2, __nv_bfloat16); else GO(3, __nv_bfloat16); }
+  else { set_error("ofsv_pack_block_input: bad act_dtype %d", act_dtype); return OFSV_EINVAL; }
+#undef GO
+  return check_launch("pack_block_input_kernel");
+}
+
+extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, const float* mask_prev,
+                                      float* flow_out, float* mask_out, int nd, int N, int D, int H, int W, int scale,
+                                      void* stream) {
+  OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_head_upsample_add: nd must be 2 or 3");
+  OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_head_upsample_add: scale %d not in {1,2,4}", scale);
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && Cs >= 2 * nd + 1, "ofsv_head_upsample_add: bad shape");
+  OFSV_REQUIRE((nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
+               "ofsv_head_upsample_add: spatial dims must be multiples of scale");
+  OFSV_REQUIRE((flow_prev == nullptr) == (mask_prev == nullptr), "ofsv_head_upsample_add: flow_prev and mask_prev go together");
+  if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(head && flow_out && mask_out, "ofsv_head_upsample_add: null pointer");
+  const int g = grid_1d((int64_t)N * D * H * W);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nd == 2) head_upsample_add_kernel<2><<<g, 256, 0, st>>>(head, Cs, flow_prev, mask_prev, flow_out, mask_out, N, D, H, W, scale);
+  else head_upsample_add_kernel<3><<<g, 256, 0, st>>>(head, Cs, flow_prev, mask_prev, flow_out, mask_out, N, D, H, W, scale);
+  return check_launch("head_upsample_add_kernel");
+}

@@ -1,0 +1,71 @@
+// Shared host/device helpers of libofsv.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ofsv.h"
+
+namespace ofsv {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return OFSV_ECUDA;
+  }
+  return OFSV_OK;
+}
+
+#define OFSV_REQUIRE(cond, ...)   \
+  do {                            \
+    if (!(cond)) {                \
+      ofsv::set_error(__VA_ARGS__); \
+      return OFSV_EINVAL;         \
+    }                             \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------------
+// Normalised-coordinate arithmetic of warplayer.py + ATen grid_sampler, every op individually rounded
+// (__f*_rn intrinsics are never contracted into FMAs by nvcc).  SURVEY.md Appendix A.
+__device__ __forceinline__ float norm_flow(float f, float half_extent, float rcp_half_extent, int ref_mode) {
+  return ref_mode == OFSV_REF_CUDA ? __fmul_rn(f, rcp_half_extent) : __fdiv_rn(f, half_extent);
+}
+// grid_sampler_unnormalize(align_corners=True) + clip_coordinates (border)
+__device__ __forceinline__ float unnorm_clip_ac(float g, float size_m1) {
+  float p = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), size_m1);  // ((g+1)/2)*(S-1); /2 == *0.5 exactly
+  p = fmaxf(p, 0.0f);                                                 // NaN -> 0, like ATen's clamp order
+  return fminf(size_m1, p);
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace ofsv

@@ -1,0 +1,227 @@
+// UPFlow L1 operators for sm_100a: 9x9 local correlation cost volume (a8) fwd/bwd, flow up-sampling (a10),
+// feature warping with validity mask (a11).
+#include "ofsv_common.cuh"
+
+namespace ofsv {
+
+// ----------------------------------------------------------------------------------------------------
+// correlation-81 forward.
+//   out[b,(dy+4)*9+(dx+4),y,x] = (1/C) sum_c f1[b,c,y,x] * f2[b,c,y+dy,x+dx]   (zero outside), optional LeakyReLU.
+// CTA = 32x8 output pixels of one sample.  Channel chunks of CC are staged in shared memory with their 4-pixel halo
+// ((8+8) x (32+8) per channel); each thread owns one pixel and keeps the 81 displacement sums in registers, so every
+// f2 element fetched from HBM is used 81 times and f1 once per displacement from a register.
+// ----------------------------------------------------------------------------------------------------
+constexpr int CTW = 32, CTH = 8, CMD = 4, CC = 8;
+constexpr int CHW = CTW + 2 * CMD, CHH = CTH + 2 * CMD;
+
+__global__ void __launch_bounds__(CTW* CTH)
+    corr81_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int C, int H,
+                      int W, float inv_c_unused, float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
+  __shared__ float s2[CC][CHH][CHW];
+  __shared__ float s1[CC][CTH][CTW];
+  const int b = blockIdx.z, x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * CTW + tx;
+  const int64_t HW = (int64_t)H * W;
+  const float* p1 = f1 + (int64_t)b * C * HW;
+  const float* p2 = f2 + (int64_t)b * C * HW;
+  float acc[81];
+#pragma unroll
+  for (int k = 0; k < 81; ++k) acc[k] = 0.0f;
+
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    const int cc = min(CC, C - c0);
+    for (int i = tid; i < CC * CHH * CHW; i += CTW * CTH) {
+      const int c = i / (CHH * CHW), r = i - c * (CHH * CHW), yy = r / CHW, xx = r - yy * CHW;
+      const int y = y0 + yy - CMD, x = x0 + xx - CMD;
+      float v = 0.0f;
+      if (c < cc && y >= 0 && y < H && x >= 0 && x < W) v = __ldg(p2 + (int64_t)(c0 + c) * HW + (int64_t)y * W + x);
+      s2[c][yy][xx] = v;
+    }
+    for (int i = tid; i < CC * CTH * CTW; i += CTW * CTH) {
+      const int c = i / (CTH * CTW), r = i - c * (CTH * CTW), yy = r / CTW, xx = r - yy * CTW;
+      const int y = y0 + yy, x = x0 + xx;
+      float v = 0.0f;
+      if (c < cc && y < H && x < W) v = __ldg(p1 + (int64_t)(c0 + c) * HW + (int64_t)y * W + x);
+      s1[c][yy][xx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CC; ++c) {
+      const float a = s1[c][ty][tx];
+#pragma unroll
+      for (int dy = 0; dy < 9; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 9; ++dx) acc[dy * 9 + dx] = fmaf(a, s2[c][ty + dy][tx + dx], acc[dy * 9 + dx]);
+    }
+    __syncthreads();
+  }
+  const int x = x0 + tx, y = y0 + ty;
+  if (x < W && y < H) {
+    float* o = out + (int64_t)b * out_batch_stride + (int64_t)y * W + x;
+    const float cf = (float)C;
+#pragma unroll
+    for (int k = 0; k < 81; ++k) {
+      float v = acc[k] / cf;  // torch.mean = sum / C
+      if (apply_leaky && v < 0.0f) v *= leaky_slope;
+      o[(int64_t)k * HW] = v;
+    }
+  }
+}
+
+// backward: one thread per (b,c,y,x) computes both input gradients (what autograd derives through Corr_pyTorch).
+//   g1[b,c,y,x] = (1/C) sum_k gout[b,k,y,x]       * f2[b,c,y+dy,x+dx]
+//   g2[b,c,y,x] = (1/C) sum_k gout[b,k,y-dy,x-dx] * f1[b,c,y-dy,x-dx]
+__global__ void __launch_bounds__(256)
+    corr81_bwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ gout,
+                      float* __restrict__ g1, float* __restrict__ g2, int B, int C, int H, int W) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)B * C * HW;
+  const float cf = (float)C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t bc = i / HW;
+    const int b = (int)(bc / C);
+    const float* a1 = f1 + bc * HW;
+    const float* a2 = f2 + bc * HW;
+    const float* g = gout + (int64_t)b * 81 * HW;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int dy = -CMD; dy <= CMD; ++dy)
+      for (int dx = -CMD; dx <= CMD; ++dx) {
+        const int k = (dy + CMD) * 9 + (dx + CMD);
+        const int yp = y + dy, xp = x + dx, ym = y - dy, xm = x - dx;
+        if (yp >= 0 && yp < H && xp >= 0 && xp < W)
+          s1 = fmaf(__ldg(g + (int64_t)k * HW + (int64_t)y * W + x) / cf, __ldg(a2 + (int64_t)yp * W + xp), s1);
+        if (ym >= 0 && ym < H && xm >= 0 && xm < W)
+          s2 = fmaf(__ldg(g + (int64_t)k * HW + (int64_t)ym * W + xm) / cf, __ldg(a1 + (int64_t)ym * W + xm), s2);
+      }
+    g1[i] = s1;
+    g2[i] = s2;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// upsample2d_flow_as: bilinear, align_corners=True; u *= w/w_, v *= h/h_ (pwc_modules.py:77-90).
+// ATen: ratio = (in-1)/(out-1) in fp32; src = ratio*dst; i0 = (int)src; lambda1 = src - i0.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    upsample_flow_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int h_, int w_, int h, int w,
+                            float ry, float rx, float us, float vs, int if_rate) {
+  const int64_t total = (int64_t)B * 2 * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h);
+    const int64_t bc = i / ((int64_t)h * w);
+    const int c = (int)(bc & 1);
+    const float* p = in + bc * h_ * w_;
+    const float sy = __fmul_rn(ry, (float)y), sx = __fmul_rn(rx, (float)x);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h_ - 1 ? 1 : 0), x1 = x0 + (x0 < w_ - 1 ? 1 : 0);
+    const float ly1 = __fsub_rn(sy, (float)y0), ly0 = __fsub_rn(1.0f, ly1);
+    const float lx1 = __fsub_rn(sx, (float)x0), lx0 = __fsub_rn(1.0f, lx1);
+    const float top = __fadd_rn(__fmul_rn(lx0, __ldg(p + y0 * w_ + x0)), __fmul_rn(lx1, __ldg(p + y0 * w_ + x1)));
+    const float bot = __fadd_rn(__fmul_rn(lx0, __ldg(p + y1 * w_ + x0)), __fmul_rn(lx1, __ldg(p + y1 * w_ + x1)));
+    float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    if (if_rate) v = __fmul_rn(v, c == 0 ? us : vs);
+    out[i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// WarpingLayer_no_div (pwc_modules.py:184-207): zeros padding, align_corners=False, validity mask (sum of in-bounds
+// corner weights >= 1).  The >= 1 test is decided by the last bit of fp32 arithmetic, so the op order (including the
+// one contracted FMA in ATen's unnormalize) is replicated exactly — see oracle/ofsv_oracle.c.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    warping_no_div_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out, int B,
+                          int C, int H, int W, float dw, float dh, float rdw, float rdh, int ref_mode) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int r = (int)(i - (int64_t)b * HW);
+    const int y = r / W, x = r - y * W;
+    const float vx = __fadd_rn((float)x, ldg_stream(flow + ((int64_t)b * 2 + 0) * HW + r));
+    const float vy = __fadd_rn((float)y, ldg_stream(flow + ((int64_t)b * 2 + 1) * HW + r));
+    float gx, gy;
+    if (ref_mode == OFSV_REF_CUDA) {
+      gx = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vx), rdw), 1.0f);
+      gy = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vy), rdh), 1.0f);
+    } else {
+      gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vx), dw), 1.0f);
+      gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vy), dh), 1.0f);
+    }
+    const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), (float)W, -1.0f), 0.5f);
+    const float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), (float)H, -1.0f), 0.5f);
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.0f, w), n = __fsub_rn(iy, yn), s = __fsub_rn(1.0f, n);
+    const float nw = __fmul_rn(s, e), ne = __fmul_rn(s, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
+    const float xc = fminf(fmaxf(xw, -2.0f), (float)W + 1.0f), yc = fminf(fmaxf(yn, -2.0f), (float)H + 1.0f);
+    const int x0 = (int)xc, y0 = (int)yc, x1 = x0 + 1, y1 = y0 + 1;
+    const bool ix0 = x0 >= 0 && x0 < W, ix1 = x1 >= 0 && x1 < W, iy0 = y0 >= 0 && y0 < H, iy1 = y1 >= 0 && y1 < H;
+    const bool in00 = ix0 && iy0, in01 = ix1 && iy0, in10 = ix0 && iy1, in11 = ix1 && iy1;
+    const float msum = __fadd_rn(__fadd_rn(__fadd_rn(in00 ? nw : 0.0f, in01 ? ne : 0.0f), in10 ? sw : 0.0f), in11 ? se : 0.0f);
+    const float valid = msum >= 1.0f ? 1.0f : 0.0f;
+    for (int c = 0; c < C; ++c) {
+      const float* p = src + ((int64_t)b * C + c) * HW;
+      const float p00 = in00 ? __ldg(p + (int64_t)y0 * W + x0) : 0.0f, p01 = in01 ? __ldg(p + (int64_t)y0 * W + x1) : 0.0f;
+      const float p10 = in10 ? __ldg(p + (int64_t)y1 * W + x0) : 0.0f, p11 = in11 ? __ldg(p + (int64_t)y1 * W + x1) : 0.0f;
+      const float v = __fmaf_rn(p11, se, __fmaf_rn(p10, sw, __fmaf_rn(p01, ne, __fmul_rn(p00, nw))));
+      out[((int64_t)b * C + c) * HW + r] = __fmul_rn(v, valid);
+    }
+  }
+}
+
+static inline int grid_1d(int64_t total) {
+  int64_t b = cdiv(total, 256);
+  const int64_t cap = 148 * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace ofsv
+
+using namespace ofsv;
+
+extern "C" int ofsv_corr81_fwd_f32(const float* f1, const float* f2, float* out, int B, int C, int H, int W,
+                                   float leaky_slope, int apply_leaky, int64_t out_batch_stride, void* stream) {
+  OFSV_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "ofsv_corr81_fwd_f32: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (B == 0) return OFSV_OK;
+  OFSV_REQUIRE(f1 && f2 && out, "ofsv_corr81_fwd_f32: null pointer");
+  OFSV_REQUIRE(out_batch_stride >= (int64_t)81 * H * W, "ofsv_corr81_fwd_f32: out_batch_stride %lld < 81*H*W",
+               (long long)out_batch_stride);
+  OFSV_REQUIRE(B <= 65535, "ofsv_corr81_fwd_f32: batch %d exceeds grid.z", B);
+  const dim3 grid((unsigned)cdiv(W, CTW), (unsigned)cdiv(H, CTH), (unsigned)B), block(CTW, CTH);
+  corr81_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, 0.0f, leaky_slope, apply_leaky,
+                                                              out_batch_stride);
+  return check_launch("corr81_fwd_kernel");
+}
+
+extern "C" int ofsv_corr81_bwd_f32(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B,
+                                   int C, int H, int W, void* stream) {
+  OFSV_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "ofsv_corr81_bwd_f32: bad shape");
+  if (B == 0) return OFSV_OK;
+  OFSV_REQUIRE(f1 && f2 && gout && g1 && g2, "ofsv_corr81_bwd_f32: null pointer");
+  corr81_bwd_kernel<<<grid_1d((int64_t)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(f1, f2, gout, g1, g2, B, C, H, W);
+  return check_launch("corr81_bwd_kernel");
+}
+
+extern "C" int ofsv_upsample_flow_ac_f32(const float* in, float* out, int B, int h_in, int w_in, int h_out, int w_out,
+                                         int if_rate, void* stream) {
+  OFSV_REQUIRE(B >= 0 && h_in >= 1 && w_in >= 1 && h_out >= 1 && w_out >= 1, "ofsv_upsample_flow_ac_f32: bad shape");
+  if (B == 0) return OFSV_OK;
+  OFSV_REQUIRE(in && out, "ofsv_upsample_flow_ac_f32: null pointer");
+  const float ry = h_out > 1 ? (float)(h_in - 1) / (float)(h_out - 1) : 0.0f;
+  const float rx = w_out > 1 ? (float)(w_in - 1) / (float)(w_out - 1) : 0.0f;
+  const float us = (float)((double)w_out / (double)w_in), vs = (float)((double)h_out / (double)h_in);
+  upsample_flow_ac_kernel<<<grid_1d((int64_t)B * 2 * h_out * w_out), 256, 0, (cudaStream_t)stream>>>(
+      in, out, B, h_in, w_in, h_out, w_out, ry, rx, us, vs, if_rate);
+  return check_launch("upsample_flow_ac_kernel");
+}
+
+extern "C" int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W,
+                                       int ref_mode, void* stream) {
+  OFSV_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && (int64_t)H * W < (1ll << 31), "ofsv_warping_no_div_f32: bad shape");
+  OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warping_no_div_f32: bad ref_mode");
+  if ((int64_t)B * C == 0) return OFSV_OK;
+  OFSV_REQUIRE(src && flow && out, "ofsv_warping_no_div_f32: null pointer");
+  const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
+  warping_no_div_kernel<<<grid_1d((int64_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+      src, flow, out, B, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode);
+  return check_launch("warping_no_div_kernel");
+}

@@ -1,0 +1,275 @@
+"""Dimension-generic IFBlock / IFNet running on libofsv kernels.
+
+Mirrors  Flow-2D/model/IFNet.py:34-122 (IFBlock), :124-276 (IFNet)  and  Flow-3D/model/IFNet.py:31-120, :122-280.
+The modules below are PARAMETER CONTAINERS with the reference's `state_dict()` key names
+(`block0.conv0.0.0.weight` ... `block_tea.conv2.2.bias`) and the reference's default initialisation; all arithmetic
+runs in CUDA kernels behind the C ABI (no nn.Conv forward, no F.grid_sample, no F.interpolate).
+
+Per block the launch sequence is
+    pack_block_input   F.interpolate(x,1/s) ‖ F.interpolate(flow,1/s)/s ‖ cat  -> channels-last [.,16]
+    12 conv layers     conv0.{0,1}, convblock{0..3}.{0,1} (+residual), conv1.0‖conv2.0 merged ConvT, conv1.2⊕conv2.2 heads
+    head_upsample_add  F.interpolate(.,s), flow*s, flow += flow_d, mask += mask_d
+    warp_blend         sigmoid(mask), warp x2, merged
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _C, ops
+
+
+TC_READY = False   # flipped once the tcgen05 engine (csrc/conv_tc.cu) passes parity on hardware
+
+
+# ----------------------------------------------------------------------------------------------- parameter holders
+class _ConvParams(nn.Module):
+    """weight/bias of nn.Conv{2,3}d or nn.ConvTranspose{2,3}d with torch's default reset_parameters()."""
+
+    def __init__(self, nd, cin, cout, k, stride, pad, transposed=False):
+        super().__init__()
+        self.nd, self.cin, self.cout, self.k, self.stride, self.pad, self.transposed = nd, cin, cout, k, stride, pad, transposed
+        shape = ((cin, cout) if transposed else (cout, cin)) + (k,) * nd
+        self.weight = nn.Parameter(torch.empty(shape))
+        self.bias = nn.Parameter(torch.empty(cout))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        fan_in = self.weight.shape[1] * k ** nd
+        bound = 1 / math.sqrt(fan_in)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, *_):
+        raise RuntimeError("parameter container: the convolution runs inside libofsv (ofsv_conv_*)")
+
+
+class _PReLUParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.full((c,), 0.25))
+
+    def forward(self, *_):
+        raise RuntimeError("parameter container: PReLU is fused into the conv epilogue")
+
+
+def _conv(nd, cin, cout, k=3, s=1, p=1):
+    return nn.Sequential(_ConvParams(nd, cin, cout, k, s, p), _PReLUParams(cout))
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------------------------- layer packing
+class _Layer:
+    """One conv layer in tap form + its packed device weights."""
+
+    def __init__(self, nd, in_stride, out_stride, nphase, taps, w_tap, bias, prelu, cout_s, out_f32=False, residual=False):
+        # taps: list (len nphase*ntaps) of (z,y,x) offsets; w_tap: fp32 [nphase*ntaps][Cin][Cout]
+        self.nd, self.in_stride, self.out_stride, self.nphase = nd, in_stride, out_stride, nphase
+        self.ntaps = len(taps) // nphase
+        self.taps = taps
+        cin, cout = w_tap.shape[1], w_tap.shape[2]
+        self.cin_s, self.cout_w, self.cout_s = _rup(cin, 16), _rup(cout, 16), cout_s
+        dev = w_tap.device
+        w = torch.zeros(len(taps), self.cin_s, self.cout_w, device=dev, dtype=torch.float32)
+        w[:, :cin, :cout] = w_tap
+        self.w_simt = w.contiguous()
+        kc = 64 if self.cin_s % 64 == 0 else (32 if self.cin_s % 32 == 0 else 16)
+        self.kc = kc
+        self.w_tc = (w.view(len(taps), self.cin_s // kc, kc, self.cout_w).permute(0, 1, 3, 2)
+                     .contiguous().to(torch.bfloat16))
+        self.bias = torch.zeros(self.cout_w, device=dev, dtype=torch.float32)
+        self.bias[:cout] = bias
+        self.prelu = None
+        if prelu is not None:
+            self.prelu = torch.ones(self.cout_w, device=dev, dtype=torch.float32)
+            self.prelu[:cout] = prelu
+        self.out_f32, self.residual = out_f32, residual
+
+    def desc(self, n, in_sp, act_dtype):
+        """in_sp = (D,H,W) of the input; returns (ConvDesc, out_sp)."""
+        d = _C.ConvDesc()
+        d.nd = self.nd
+        d.N, (d.Di, d.Hi, d.Wi), d.Cin_s = n, in_sp, self.cin_s
+        if self.nphase == 1:
+            osp = tuple(max(1, s // self.in_stride) if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
+            vsp = osp
+        else:
+            vsp = in_sp
+            osp = tuple(s * 2 if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
+        d.Do, d.Ho, d.Wo = vsp
+        d.Dy, d.Hy, d.Wy = osp
+        d.Cout_s, d.Cout_w = self.cout_s, self.cout_w
+        d.in_stride, d.out_stride = self.in_stride, self.out_stride
+        d.nphase, d.ntaps = self.nphase, self.ntaps
+        for i, t in enumerate(self.taps):
+            d.tap_off[i][0], d.tap_off[i][1], d.tap_off[i][2], d.tap_off[i][3] = t[0], t[1], t[2], 0
+        d.has_prelu, d.has_residual = int(self.prelu is not None), int(self.residual)
+        d.in_dtype = act_dtype
+        d.out_dtype = _C.F32 if self.out_f32 else act_dtype
+        return d, osp
+
+
+def _conv_taps(nd, k, p):
+    rng = [range(k)] * nd
+    idx = list(itertools.product(*rng))
+    offs = [((0,) if nd == 2 else ()) + tuple(i - p for i in ix) for ix in idx]
+    return idx, offs
+
+
+def _pack_conv(m: _ConvParams, prelu, residual=False):
+    idx, offs = _conv_taps(m.nd, m.k, m.pad)
+    w = m.weight.detach().float()                                    # [Cout][Cin][k..]
+    w_tap = torch.stack([w[(slice(None), slice(None)) + ix].t() for ix in idx])   # [T][Cin][Cout]
+    return _Layer(m.nd, m.stride, 1, 1, offs, w_tap, m.bias.detach().float(),
+                  None if prelu is None else prelu.weight.detach().float(), _rup(m.cout, 16), residual=residual)
+
+
+_CT_TAPS = {0: ((1, 0), (3, -1)), 1: ((2, 0), (0, 1))}   # ConvTranspose(4,2,1): parity -> ((kernel idx, input offset), ...)
+
+
+def _pack_convT(nd, w, bias, prelu, cout_s, out_f32):
+    """w [Cin][Cout][4..] (already merged / block-diagonal).  2^nd output parities x 2^nd taps."""
+    taps, w_tap = [], []
+    for par in itertools.product((0, 1), repeat=nd):                 # (z,y,x) parity; x lowest bit
+        for choice in itertools.product((0, 1), repeat=nd):
+            kk = tuple(_CT_TAPS[par[a]][choice[a]][0] for a in range(nd))
+            off = tuple(_CT_TAPS[par[a]][choice[a]][1] for a in range(nd))
+            taps.append(((0,) if nd == 2 else ()) + off)
+            w_tap.append(w[(slice(None), slice(None)) + kk])         # [Cin][Cout]
+    return _Layer(nd, 1, 2, 2 ** nd, taps, torch.stack(w_tap), bias, prelu, cout_s, out_f32=out_f32)
+
+
+class IFBlock(nn.Module):
+    """Flow-2D/model/IFNet.py:34-122 / Flow-3D/model/IFNet.py:31-120, `version == 2` branch."""
+
+    def __init__(self, nd, in_planes, c=64):
+        super().__init__()
+        self.nd, self.in_planes, self.c = nd, in_planes, c
+        k0 = 3 if nd == 2 else 4
+        self.conv0 = nn.Sequential(_conv(nd, in_planes, c // 2, k0, 2, 1), _conv(nd, c // 2, c, k0, 2, 1))
+        for i in range(4):
+            setattr(self, f"convblock{i}", nn.Sequential(_conv(nd, c, c), _conv(nd, c, c)))
+        self.conv1 = nn.Sequential(_ConvParams(nd, c, c // 2, 4, 2, 1, True), _PReLUParams(c // 2),
+                                   _ConvParams(nd, c // 2, 2 * nd, 4, 2, 1, True))
+        self.conv2 = nn.Sequential(_ConvParams(nd, c, c // 2, 4, 2, 1, True), _PReLUParams(c // 2),
+                                   _ConvParams(nd, c // 2, 1, 4, 2, 1, True))
+        self._packed = None
+        self._packed_key = None
+
+    # -- weights -> tap form (re-done whenever a parameter changed or moved)
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def layers(self):
+        key = self._key()
+        if self._packed is None or self._packed_key != key:
+            nd, c = self.nd, self.c
+            L = [_pack_conv(self.conv0[0][0], self.conv0[0][1]), _pack_conv(self.conv0[1][0], self.conv0[1][1])]
+            for i in range(4):
+                cb = getattr(self, f"convblock{i}")
+                L.append(_pack_conv(cb[0][0], cb[0][1]))
+                L.append(_pack_conv(cb[1][0], cb[1][1], residual=True))
+            # conv1.0 ‖ conv2.0: one ConvT c -> c (channels [0,c/2) feed the flow head, [c/2,c) the mask head)
+            w10, w20 = self.conv1[0].weight.detach().float(), self.conv2[0].weight.detach().float()
+            L.append(_pack_convT(nd, torch.cat([w10, w20], 1),
+                                 torch.cat([self.conv1[0].bias, self.conv2[0].bias]).detach().float(),
+                                 torch.cat([self.conv1[1].weight, self.conv2[1].weight]).detach().float(), c, False))
+            # conv1.2 ⊕ conv2.2: block-diagonal ConvT c -> 2nd+1 (fp32 output, 8 stored channels)
+            w12, w22 = self.conv1[2].weight.detach().float(), self.conv2[2].weight.detach().float()
+            nf = 2 * nd
+            wh = torch.zeros((c, nf + 1) + (4,) * nd, device=w12.device)
+            wh[: c // 2, :nf] = w12
+            wh[c // 2:, nf:] = w22
+            L.append(_pack_convT(nd, wh, torch.cat([self.conv1[2].bias, self.conv2[2].bias]).detach().float(), None, 8, True))
+            self._packed, self._packed_key = L, key
+        return self._packed
+
+    def run(self, xin, n, in_sp, act_dtype, engine):
+        """xin: packed channels-last block input [N][in_sp][16].  Returns head [N][in_sp][8] fp32."""
+        L = self.layers()
+        tdt = torch.float32 if act_dtype == _C.F32 else torch.bfloat16
+        x, sp, skip = xin, in_sp, None
+        for li, lay in enumerate(L):
+            d, osp = lay.desc(n, sp, act_dtype)
+            odt = torch.float32 if lay.out_f32 else tdt
+            y = torch.empty([n] + ([osp[0]] if self.nd == 3 else []) + [osp[1], osp[2], lay.cout_s], device=x.device, dtype=odt)
+            eng = engine(li, lay) if callable(engine) else engine
+            ops.conv(d, x, lay.w_tc if eng == "tc" else lay.w_simt, lay.bias, lay.prelu,
+                     skip if lay.residual else None, y, eng)
+            if 2 <= li <= 9 and (li % 2 == 0):
+                skip = x                       # input of the residual pair
+            x, sp = y, osp
+        return x
+
+    def forward(self, *_a, **_k):
+        raise RuntimeError("IFBlock is driven by IFNet.forward (block input is built by ofsv_pack_block_input)")
+
+
+class IFNet(nn.Module):
+    """Flow-2D/model/IFNet.py:124-276 / Flow-3D/model/IFNet.py:122-280, inference branch (gt with 0 channels)."""
+
+    WIDTHS = {2: (128, 96, 64), 3: (128, 64, 64)}
+
+    def __init__(self, nd: int, precision: str = "bf16", engine: str = "auto"):
+        super().__init__()
+        self.nd = nd
+        c0, c1, c2 = self.WIDTHS[nd]
+        nf = 2 * nd
+        self.block0 = IFBlock(nd, 2, c=c0)
+        self.block1 = IFBlock(nd, 5 + nf, c=c1)
+        self.block2 = IFBlock(nd, 5 + nf, c=c2)
+        self.block_tea = IFBlock(nd, 6 + nf, c=64)      # teacher: training only (§8f), kept for state_dict parity
+        self.set_precision(precision, engine)
+        self.only_last = False
+
+    def set_precision(self, precision: str, engine: str = "auto"):
+        """precision 'bf16' (tensor-core operands, fp32 accumulate; flow/mask accumulators and heads in fp32) or
+        'fp32' (CUDA-core exact-order path).  engine 'tc' | 'simt' | 'auto' (tc wherever precision is bf16)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if engine not in ("auto", "tc", "simt"):
+            raise ValueError("engine must be 'auto', 'tc' or 'simt'")
+        if engine == "tc" and precision != "bf16":
+            raise ValueError("the tensor-core engine computes in bf16")
+        self.precision, self.engine = precision, engine
+
+    def _engine(self):
+        if self.engine == "auto":
+            return "tc" if (self.precision == "bf16" and TC_READY) else "simt"
+        return self.engine
+
+    @torch.no_grad()
+    def forward(self, x, scale=(4, 2, 1), timestep=0.5):
+        """x = cat(img0, img1) (N,2,·) fp32 CUDA.  `timestep` is accepted and ignored exactly like the reference
+        (SURVEY.md fact 5).  Returns (flow_list, mask_list | mask_list[2], merged, None, None, 0)."""
+        nd = self.nd
+        if x.dim() != nd + 2 or x.shape[1] < 2:
+            raise ValueError(f"IFNet{nd}D: expected (N,2,{'D,' if nd == 3 else ''}H,W), got {tuple(x.shape)}")
+        if x.shape[1] > 2:
+            raise NotImplementedError("teacher/distillation branch (gt channel) is the training path, SURVEY.md §8f")
+        sp = tuple(x.shape[2:])
+        if any(s % 16 for s in sp):
+            raise NotImplementedError(f"spatial dims must be multiples of 16 (got {sp}); the reference's shape-repair "
+                                      "slicing (Flow-2D/model/IFNet.py:164-188) is not reproduced")
+        img0, img1 = x[:, 0:1].contiguous(), x[:, 1:2].contiguous()
+        n = x.shape[0]
+        act = _C.F32 if self.precision == "fp32" else _C.BF16
+        eng = self._engine()
+        flow_list, mask_list, merged = [], [], []
+        w0 = w1 = flow = mask = None
+        for i, blk in enumerate((self.block0, self.block1, self.block2)):
+            s = int(scale[i])
+            xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act)
+            in_sp = tuple(v // s for v in sp)
+            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng)
+            flow, mask = ops.head_upsample_add(head, flow, mask, nd, n, sp, s)
+            last = i == 2
+            want_out = last or not self.only_last
+            w0, w1, mg, ms = ops.warp_blend(img0, img1, flow, mask, want_warped=True, want_merged=want_out, want_mask=want_out)
+            flow_list.append(flow)
+            mask_list.append(ms)
+            merged.append(mg)
+        return flow_list, (mask_list if nd == 2 else mask_list[2]), merged, None, None, 0

@@ -1,0 +1,270 @@
+"""Tensor-level wrappers over the libofsv C ABI.  PyTorch is plumbing only: it owns device memory and the stream.
+
+Every function takes CUDA tensors, allocates outputs with torch.empty and enqueues the kernel on the current
+stream.  CPU tensors raise TypeError — there is deliberately no CPU or ATen fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _C
+
+_FLAVOR = {"mode": _C.REF_CPU}
+_LIN = {}
+
+
+class LaunchTimer:
+    """CUDA-event stopwatch per kernel class, recorded on the launching stream (bench.py's roofline numbers).
+    Install with `ops.TIMER = LaunchTimer()`; every wrapper below brackets its launch with two events."""
+
+    def __init__(self):
+        self.spans = {}
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.o, self.name = owner, name
+
+        def __enter__(self):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            self.b.record()
+            self.o.spans.setdefault(self.name, []).append((self.a, self.b))
+            return False
+
+    def span(self, name):
+        return LaunchTimer._Span(self, name)
+
+    def totals(self):
+        """{class: (launches, total_ms)} — synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+
+
+class _NoSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+TIMER = None
+_NOSPAN = _NoSpan()
+
+
+def _span(name):
+    return TIMER.span(name) if TIMER is not None else _NOSPAN
+
+
+def set_reference_flavor(flavor: str) -> None:
+    """Which build of the reference the fp32 warp arithmetic reproduces bit-for-bit.
+
+    'cpu'  (default): the reference run on CPU — the oracle of this repo (true division, CPU torch.linspace table).
+    'cuda': the reference run in CUDA eager (ATen's reciprocal-multiply division, CUDA torch.linspace table).
+    The two differ by ~1e-5 max-abs in warped intensities."""
+    if flavor not in ("cpu", "cuda"):
+        raise ValueError("flavor must be 'cpu' or 'cuda'")
+    _FLAVOR["mode"] = _C.REF_CPU if flavor == "cpu" else _C.REF_CUDA
+
+
+def reference_flavor() -> str:
+    return "cpu" if _FLAVOR["mode"] == _C.REF_CPU else "cuda"
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor, got {t.device} (this package has no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def linspace_table(n: int, device: torch.device) -> torch.Tensor:
+    """torch.linspace(-1, 1, n) produced on the device class the selected reference flavour would use
+    (its bits differ between ATen's CPU and CUDA kernels), cached on `device`."""
+    key = (n, str(device), _FLAVOR["mode"])
+    t = _LIN.get(key)
+    if t is None:
+        src = "cpu" if _FLAVOR["mode"] == _C.REF_CPU else device
+        t = torch.linspace(-1.0, 1.0, n, device=src).to(device)
+        _LIN[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ warp
+def warp2d(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
+    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
+    if x.dim() != 4 or f.dim() != 4 or f.shape[1] != 2 or f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
+        raise ValueError(f"warp2d: bad shapes {tuple(x.shape)} / {tuple(f.shape)}")
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().ofsv_warp2d_f32(_p(x), _p(f), _p(linspace_table(w, x.device)), _p(linspace_table(h, x.device)),
+                                          _p(out), n, c, h, w, _FLAVOR["mode"], _stream()))
+    return out
+
+
+def warp3d(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
+    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
+    if x.dim() != 5 or f.dim() != 5 or f.shape[1] != 3 or f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
+        raise ValueError(f"warp3d: bad shapes {tuple(x.shape)} / {tuple(f.shape)}")
+    n, c, d, h, w = x.shape
+    out = torch.empty_like(x)
+    dev = x.device
+    with torch.cuda.device(dev), _span("warp3d"):
+        _C.check(_C.lib().ofsv_warp3d_f32(_p(x), _p(f), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
+                                          _p(linspace_table(w, dev)), _p(out), n, c, d, h, w, _FLAVOR["mode"], _stream()))
+    return out
+
+
+def warp_blend(img0, img1, flow, mask_logit, want_warped=True, want_merged=True, want_mask=True):
+    """sigmoid(mask); warp(img0, flow[:, :nd]); warp(img1, flow[:, nd:]); merged = w0*m + w1*(1-m) in one pass.
+    Returns (warped0, warped1, merged, mask_sigmoid); entries not asked for are None."""
+    img0, img1, flow = _cuda_f32(img0, "img0"), _cuda_f32(img1, "img1"), _cuda_f32(flow, "flow")
+    nd = img0.dim() - 2
+    if nd not in (2, 3) or img0.shape[1] != 1 or img1.shape != img0.shape or flow.shape[1] != 2 * nd \
+            or flow.shape[2:] != img0.shape[2:] or flow.shape[0] != img0.shape[0]:
+        raise ValueError("warp_blend: bad shapes")
+    need_m = want_merged or want_mask
+    if need_m:
+        mask_logit = _cuda_f32(mask_logit, "mask_logit")
+        if mask_logit.shape != img0.shape:
+            raise ValueError("warp_blend: mask shape")
+    w0 = torch.empty_like(img0) if want_warped else None
+    w1 = torch.empty_like(img0) if want_warped else None
+    mg = torch.empty_like(img0) if want_merged else None
+    ms = torch.empty_like(img0) if want_mask else None
+    dev = img0.device
+    L = _C.lib()
+    with torch.cuda.device(dev), _span("warp_blend"):
+        if nd == 2:
+            n, _, h, w = img0.shape
+            _C.check(L.ofsv_warp_blend_2d_f32(_p(img0), _p(img1), _p(flow), _p(mask_logit if need_m else None),
+                                              _p(linspace_table(w, dev)), _p(linspace_table(h, dev)), _p(w0), _p(w1), _p(mg),
+                                              _p(ms), n, h, w, _FLAVOR["mode"], _stream()))
+        else:
+            n, _, d, h, w = img0.shape
+            _C.check(L.ofsv_warp_blend_3d_f32(_p(img0), _p(img1), _p(flow), _p(mask_logit if need_m else None),
+                                              _p(linspace_table(h, dev)), _p(linspace_table(d, dev)), _p(linspace_table(w, dev)),
+                                              _p(w0), _p(w1), _p(mg), _p(ms), n, d, h, w, _FLAVOR["mode"], _stream()))
+    return w0, w1, mg, ms
+
+
+def blend(w0, w1, mask_logit):
+    w0, w1, m = _cuda_f32(w0, "w0"), _cuda_f32(w1, "w1"), _cuda_f32(mask_logit, "mask_logit")
+    if not (w0.shape == w1.shape == m.shape):
+        raise ValueError("blend: shapes differ")
+    out = torch.empty_like(w0)
+    with torch.cuda.device(w0.device):
+        _C.check(_C.lib().ofsv_blend_f32(_p(w0), _p(w1), _p(m), _p(out), w0.numel(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ UPFlow ops
+def corr81_fwd(f1, f2, leaky_slope=None, out=None):
+    """(B,C,H,W) x2 -> (B,81,H,W).  `out` may be a (B,>=81,H,W) channel-slice view of a larger contiguous buffer
+    (the estimator's concat input): only out[:, :81] is written."""
+    f1, f2 = _cuda_f32(f1, "input1"), _cuda_f32(f2, "input2")
+    if f1.dim() != 4 or f1.shape != f2.shape:
+        raise ValueError(f"corr81: bad shapes {tuple(f1.shape)} / {tuple(f2.shape)}")
+    b, c, h, w = f1.shape
+    if out is None:
+        out = torch.empty(b, 81, h, w, device=f1.device, dtype=torch.float32)
+    else:
+        if (not out.is_cuda or out.dtype != torch.float32 or out.dim() != 4 or out.shape[0] != b or out.shape[1] < 81
+                or out.shape[2:] != f1.shape[2:] or out.stride()[1:] != (h * w, w, 1)):
+            raise ValueError("corr81: `out` must be a float32 CUDA (B,>=81,H,W) tensor with dense (C,H,W) strides")
+    bstride = out.stride(0) if b > 1 else 81 * h * w
+    with torch.cuda.device(f1.device):
+        _C.check(_C.lib().ofsv_corr81_fwd_f32(_p(f1), _p(f2), _p(out), b, c, h, w,
+                                              float(leaky_slope or 0.0), int(leaky_slope is not None),
+                                              max(bstride, 81 * h * w), _stream()))
+    return out
+
+
+def corr81_bwd(f1, f2, gout):
+    f1, f2, gout = _cuda_f32(f1, "input1"), _cuda_f32(f2, "input2"), _cuda_f32(gout, "grad_output")
+    b, c, h, w = f1.shape
+    if gout.shape != (b, 81, h, w):
+        raise ValueError("corr81_bwd: grad_output shape")
+    g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+    with torch.cuda.device(f1.device):
+        _C.check(_C.lib().ofsv_corr81_bwd_f32(_p(f1), _p(f2), _p(gout), _p(g1), _p(g2), b, c, h, w, _stream()))
+    return g1, g2
+
+
+def upsample_flow_ac(flow, h, w, if_rate=True):
+    flow = _cuda_f32(flow, "inputs")
+    if flow.dim() != 4 or flow.shape[1] != 2:
+        raise ValueError("upsample_flow_ac: expected (B,2,h,w)")
+    b, _, h_, w_ = flow.shape
+    out = torch.empty(b, 2, h, w, device=flow.device, dtype=torch.float32)
+    with torch.cuda.device(flow.device):
+        _C.check(_C.lib().ofsv_upsample_flow_ac_f32(_p(flow), _p(out), b, h_, w_, h, w, int(if_rate), _stream()))
+    return out
+
+
+def warping_no_div(x, flow):
+    x, flow = _cuda_f32(x, "x"), _cuda_f32(flow, "flow")
+    if x.dim() != 4 or flow.shape != (x.shape[0], 2, x.shape[2], x.shape[3]):
+        raise ValueError("warping_no_div: bad shapes")
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().ofsv_warping_no_div_f32(_p(x), _p(flow), _p(out), b, c, h, w, _FLAVOR["mode"], _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ IFNet engine pieces
+_TDT = {_C.F32: torch.float32, _C.BF16: torch.bfloat16}
+
+
+def pack_block_input(img0, img1, warped0, warped1, mask, flow, scale, act_dtype, cs=16):
+    nd = img0.dim() - 2
+    n = img0.shape[0]
+    sp = list(img0.shape[2:])
+    d, h, w = ([1] + sp) if nd == 2 else sp
+    osp = [s // scale for s in sp]
+    dst = torch.empty([n] + osp + [cs], device=img0.device, dtype=_TDT[act_dtype])
+    with torch.cuda.device(img0.device), _span("pack_block_input"):
+        _C.check(_C.lib().ofsv_pack_block_input(_p(img0), _p(img1), _p(warped0), _p(warped1), _p(mask), _p(flow), _p(dst),
+                                                act_dtype, nd, n, d, h, w, scale, cs, _stream()))
+    return dst
+
+
+def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
+    """head [N][sp/scale...][Cs] fp32 -> (flow (N,2nd,*sp), mask (N,1,*sp))."""
+    d, h, w = ([1] + list(sp)) if nd == 2 else list(sp)
+    flow = torch.empty([n, 2 * nd] + list(sp), device=head.device, dtype=torch.float32)
+    mask = torch.empty([n, 1] + list(sp), device=head.device, dtype=torch.float32)
+    with torch.cuda.device(head.device), _span("head_upsample_add"):
+        _C.check(_C.lib().ofsv_head_upsample_add(_p(head), head.shape[-1], _p(flow_prev), _p(mask_prev), _p(flow), _p(mask),
+                                                 nd, n, d, h, w, scale, _stream()))
+    return flow, mask
+
+
+def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
+    fn = _C.lib().ofsv_conv_tc if engine == "tc" else _C.lib().ofsv_conv_simt
+    with torch.cuda.device(x.device), _span("conv_" + engine):
+        _C.check(fn(ctypes.byref(desc), _p(x), _p(w), _p(bias), _p(prelu), _p(residual), _p(y), _stream()))
+    return y
+
+
+def launch_count() -> int:
+    return int(_C.lib().ofsv_launch_count())

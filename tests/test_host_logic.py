@@ -1,0 +1,138 @@
+"""CPU tests of the host-side logic: weight packing into tap form, ConvTranspose phase decomposition, merged heads,
+state_dict interchange with the oracle, C-ABI export list, argument validation (no kernels are launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from opticalflowscivis_b200 import _C, ifnet
+from oracle.ifnet_ref import IFNetRef
+from tap_eval import run_layer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cl(x):      # NC(D)HW -> [N][D][H][W][C] (D = 1 for 2-D)
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _pad_c(x, c):
+    return F.pad(x, (0, c - x.shape[-1]))
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_conv_tap_form_matches_torch(nd):
+    torch.manual_seed(0)
+    for (cin, cout, k, s, p) in ((5, 16, 3, 1, 1), (9 if nd == 2 else 11, 32, 3 if nd == 2 else 4, 2, 1)):
+        m = ifnet._ConvParams(nd, cin, cout, k, s, p)
+        pr = ifnet._PReLUParams(cout)
+        pr.weight.data.uniform_(0.1, 0.4)
+        lay = ifnet._pack_conv(m, pr)
+        x = torch.randn((2, cin) + ((8,) * nd))
+        ref = (F.conv2d if nd == 2 else F.conv3d)(x, m.weight, m.bias, stride=s, padding=p)
+        ref = F.prelu(ref, pr.weight)
+        got = run_layer(lay, _pad_c(_cl(x), lay.cin_s))
+        assert torch.allclose(got[..., :cout], _cl(ref), atol=1e-4), (nd, cin, cout)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_conv_transpose_phase_form_matches_torch(nd):
+    torch.manual_seed(1)
+    cin, cout = 6, 5
+    m = ifnet._ConvParams(nd, cin, cout, 4, 2, 1, transposed=True)
+    lay = ifnet._pack_convT(nd, m.weight.detach(), m.bias.detach(), None, 8, True)
+    x = torch.randn((2, cin) + ((5,) * nd))
+    ref = (F.conv_transpose2d if nd == 2 else F.conv_transpose3d)(x, m.weight, m.bias, stride=2, padding=1)
+    got = run_layer(lay, _pad_c(_cl(x), lay.cin_s))
+    assert got.shape[1:4] == _cl(ref).shape[1:4]
+    assert torch.allclose(got[..., :cout], _cl(ref), atol=1e-4)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_block_layers_match_oracle_block(nd):
+    """The 12 packed layers (merged conv1.0‖conv2.0, block-diagonal heads, residual pairs) evaluated in tap form on CPU
+    reproduce the oracle IFBlock's flow/mask head outputs."""
+    torch.manual_seed(2)
+    c, cin = 32, 5 + 2 * nd
+    blk = ifnet.IFBlock(nd, cin, c)
+    from oracle.ifnet_ref import IFBlockRef
+    ref = IFBlockRef(nd, cin, c)
+    ref.load_state_dict(blk.state_dict())
+    x = torch.randn((1, cin) + ((16,) * nd))
+    with torch.no_grad():
+        h = ref.conv0(x)
+        for i in range(4):
+            h = getattr(ref, f"convblock{i}")(h) + h
+        rflow, rmask = ref.conv1(h), ref.conv2(h)
+        L = blk.layers()
+        y, skip = _pad_c(_cl(x), 16), None
+        for li, lay in enumerate(L):
+            inp = y
+            y = run_layer(lay, inp, skip if lay.residual else None)
+            if 2 <= li <= 9 and li % 2 == 0:
+                skip = inp
+    nf = 2 * nd
+    assert torch.allclose(y[..., :nf], _cl(rflow), atol=2e-4)
+    assert torch.allclose(y[..., nf:nf + 1], _cl(rmask), atol=2e-4)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_state_dict_interchange_and_seeded_init(nd):
+    torch.manual_seed(1234)
+    mine = ifnet.IFNet(nd)
+    torch.manual_seed(1234)
+    ref = IFNetRef(nd)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)          # same default init as the reference under the same seed
+    ref.load_state_dict(a)                                   # and the keys load both ways
+    mine.load_state_dict(b)
+    assert sum(p.numel() for p in mine.parameters()) == {2: 3157764, 3: 9101916}[nd]
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ofsv.h")).read()
+    declared = set(re.findall(r"\b(ofsv_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ofsv_conv_desc"}
+    L = _C.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/ofsv.h but not exported by libofsv.so"
+    assert declared == set(_C.EXPORTS), declared ^ set(_C.EXPORTS)
+    assert L.ofsv_version().startswith(b"ofsv")
+    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 4
+
+
+def test_validation_errors_launch_nothing():
+    L = _C.lib()
+    null = ctypes.c_void_p(0)
+    n0 = L.ofsv_launch_count()
+    assert L.ofsv_warp3d_f32(null, null, null, null, null, null, 1, 1, 4, 4, 4, 0, null) == _C.EINVAL
+    assert b"null" in L.ofsv_last_error()
+    assert L.ofsv_corr81_fwd_f32(null, null, null, 1, 0, 4, 4, 0.1, 0, 0, null) == _C.EINVAL
+    assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, null) == _C.EINVAL
+    d = _C.ConvDesc()
+    assert L.ofsv_conv_simt(ctypes.byref(d), null, null, null, null, null, null, null) == _C.EINVAL
+    with pytest.raises(RuntimeError):
+        _C.check(_C.EINVAL)
+    assert L.ofsv_launch_count() == n0
+    # empty batches are accepted and are no-ops
+    assert L.ofsv_warp2d_f32(null, null, null, null, null, 0, 1, 4, 4, 0, null) == _C.EINVAL   # null pointers first
+    assert L.ofsv_blend_f32(null, null, null, null, 0, null) == _C.OK
+
+
+def test_cpu_tensors_are_rejected():
+    from opticalflowscivis_b200 import ops
+    from opticalflowscivis_b200.upflow import CorrelationFunction
+    with pytest.raises(TypeError):
+        ops.warp2d(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(TypeError):
+        ops.warp3d(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4))
+    with pytest.raises(TypeError):
+        CorrelationFunction.apply(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 4, 1, 4, 1, 1, 1)
+    with pytest.raises(NotImplementedError):
+        CorrelationFunction.apply(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 3, 3, 20, 1, 2, 1)

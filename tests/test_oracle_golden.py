@@ -1,0 +1,99 @@
+"""CPU: the oracle (torch restatement + plain-C restatement) replays the golden fixtures that
+tests/golden/make_golden.py generated from the imported reference."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from oracle import ops_ref
+from oracle.ifnet_ref import IFNetRef, ModelRef
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cases(npz, suffixes):
+    keys = sorted({k.rsplit("_", 1)[0] for k in npz.files})
+    for k in keys:
+        if all(f"{k}_{s}" in npz.files for s in suffixes):
+            yield k, [npz[f"{k}_{s}"] for s in suffixes]
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_warp_golden(nd):
+    z = np.load(os.path.join(G, f"warp{nd}d.npz"))
+    n = 0
+    for name, (src, flow, out) in _cases(z, ("src", "flow", "out")):
+        t = (ops_ref.warp2d_ref if nd == 2 else ops_ref.warp3d_ref)(torch.from_numpy(src), torch.from_numpy(flow)).numpy()
+        c = (co.warp2d if nd == 2 else co.warp3d)(src, flow)
+        assert np.abs(t - out).max() <= 1e-6, name          # same torch build -> normally bit-exact
+        assert np.abs(c - out).max() <= 1e-6, name
+        # reciprocal-multiply flavour (CUDA eager) stays within ~1e-4 of the true-division reference, never equal by construction
+        c2 = (co.warp2d if nd == 2 else co.warp3d)(src, flow, co.DIV_RCP)
+        assert np.abs(c2 - out).max() <= 2e-4, name
+        n += 1
+    assert n >= 10
+
+
+def test_warp3d_zero_flow_rotates_axes():
+    """zero flow on a cube returns x.permute(0,1,3,4,2), not x."""
+    x = np.random.default_rng(0).random((1, 1, 8, 8, 8), dtype=np.float32)
+    out = co.warp3d(x, np.zeros((1, 3, 8, 8, 8), np.float32))
+    assert np.abs(out - x.transpose(0, 1, 3, 4, 2)).max() < 1e-6
+    assert np.abs(out - x).max() > 0.5
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_ifnet_golden(nd):
+    z = np.load(os.path.join(G, f"ifnet{nd}d.npz"))
+    torch.manual_seed(int(z["seed"]))
+    m = ModelRef(nd).eval()
+    wsum = float(sum(v.double().abs().sum() for v in m.flownet.state_dict().values()))
+    assert abs(wsum - float(z["weight_abs_sum"])) < 1e-6 * wsum, "seeded init drifted (different torch build?)"
+    img0, img1 = torch.from_numpy(z["img0"]), torch.from_numpy(z["img1"])
+    with torch.no_grad():
+        fl, mk, mg = m.flownet(torch.cat((img0, img1), 1), (4, 2, 1))
+    for i in range(3):
+        # conv kernels may pick a different ISA path on another host: allow 1e-4
+        assert np.abs(fl[i].numpy() - z[f"flow{i}"]).max() < 1e-4
+        assert np.abs(mk[i].numpy() - z[f"mask{i}"]).max() < 1e-4
+        assert np.abs(mg[i].numpy() - z[f"merged{i}"]).max() < 1e-4
+    out = m.inference(img0, img1)
+    if nd == 3:
+        assert out[0].shape == img0.shape and len(out[1]) == 3 and out[2].shape == img0.shape
+    else:
+        assert len(out[0]) == 3 and len(out[1]) == 3 and len(out[2]) == 3
+
+
+def test_upflow_ops_golden():
+    warnings.simplefilter("ignore")
+    z = np.load(os.path.join(G, "upflow_ops.npz"))
+    for i in range(3):
+        f1, f2, out = z[f"corr{i}_f1"], z[f"corr{i}_f2"], z[f"corr{i}_out"]
+        assert np.abs(ops_ref.corr81_ref(torch.from_numpy(f1), torch.from_numpy(f2)).numpy() - out).max() < 2e-6
+        assert np.abs(co.corr81(f1, f2) - out).max() < 2e-6
+        g1, g2 = co.corr81_bwd(f1, f2, z[f"corr{i}_gout"])
+        assert np.abs(g1 - z[f"corr{i}_g1"]).max() < 2e-5 and np.abs(g2 - z[f"corr{i}_g2"]).max() < 2e-5
+        lk = co.corr81(f1, f2, leaky_slope=0.1)
+        assert np.allclose(lk, np.where(out > 0, out, 0.1 * out), atol=2e-6)
+        fin, fout = z[f"ups{i}_in"], z[f"ups{i}_out"]
+        h, w = fout.shape[2:]
+        assert np.abs(ops_ref.upsample2d_flow_as_ref(torch.from_numpy(fin), h, w).numpy() - fout).max() < 1e-6
+        assert np.abs(co.upsample_flow_ac(fin, h, w) - fout).max() < 4e-6
+        x, fl, wo = z[f"wnd{i}_x"], z[f"wnd{i}_flow"], z[f"wnd{i}_out"]
+        assert np.array_equal(co.warping_no_div(x, fl), wo)
+        assert np.abs(ops_ref.warping_layer_no_div_ref(torch.from_numpy(x), torch.from_numpy(fl)).numpy() - wo).max() < 1e-6
+
+
+def test_resize_identities():
+    """x1/2 == avg-pool 2^d, x1/4 == mean of samples {4i+1, 4i+2} per axis."""
+    x = torch.rand(1, 2, 16, 16, 16)
+    half = ops_ref.resize_ref(x, 0.5)
+    assert torch.allclose(half, torch.nn.functional.avg_pool3d(x, 2), atol=1e-6)
+    quarter = ops_ref.resize_ref(x, 0.25)
+    sel = (x[:, :, 1::4] + x[:, :, 2::4]) / 2
+    sel = (sel[:, :, :, 1::4] + sel[:, :, :, 2::4]) / 2
+    sel = (sel[..., 1::4] + sel[..., 2::4]) / 2
+    assert torch.allclose(quarter, sel, atol=1e-6)
