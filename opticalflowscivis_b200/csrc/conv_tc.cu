@@ -1,7 +1,346 @@
-// tcgen05/TMEM implicit-GEMM convolution engine — placeholder until the kernel lands.
+// tcgen05 / TMEM implicit-GEMM convolution engine for sm_100a (ofsv.h: ofsv_conv_tc).
+//
+// GEMM view of one layer in tap form:  D[m, co] = sum_{tap} sum_{ci} X[pos(m) * in_stride + off(tap), ci] * W[tap][ci][co]
+//   M tile  = 128 virtual output positions = a (TW x TH x TD) box (8x4x4 in 3-D, 16x8x1 in 2-D)
+//   N       = Cout_w (16..128, one UMMA N), K loop = taps x (Cin_s / KC) chunks of KC in {64,32,16} channels
+//   A tile  = the input box shifted by the tap offset, fetched by ONE 5-D TMA box load per (tap, chunk) from the
+//             channels-last activation tensor [N][D][H][W][C]: out-of-range coordinates are zero-filled by TMA, which
+//             is exactly the convolution's zero padding; stride-2 layers use the tensor map's element strides.
+//             The box lands in shared memory as 128 rows x KC channels = the K-major SWIZZLE_{128,64,32}B UMMA layout.
+//   B tile  = W[tap][chunk] stored [Cout_w][KC] (K-major), one 2-D TMA load.
+//   D       = fp32 accumulator in tensor memory (128 lanes x N columns), read back with tcgen05.ld by 4 epilogue warps
+//             that fuse bias + PReLU + residual + dtype conversion and write channels-last output rows.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "ofsv_common.cuh"
-extern "C" int ofsv_conv_tc(const ofsv_conv_desc*, const void*, const void*, const float*, const float*, const void*,
-                            void*, void*) {
-  ofsv::set_error("ofsv_conv_tc: not built yet");
-  return OFSV_ENOSUP;
+
+namespace ofsv {
+
+int validate_conv_desc(const ofsv_conv_desc* d, const char* who);  // conv_simt.cu
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_M = 128;
+
+struct TcParams {
+  int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
+  int in_stride, out_stride, ntaps, nkc;
+  int tw, th, td, tiles_w, tiles_h, tiles_d;
+  int has_prelu, has_residual, out_f32;
+  int8_t tap_off[OFSV_MAX_TAPS][4];
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a trap (cudaErrorLaunchFailure), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46
+// | layout type @61 (SWIZZLE_128B = 2, 64B = 4, 32B = 6).  Rows are KC*2 bytes; 8-row groups are SBO = 8*row bytes apart.
+template <int KC>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+  constexpr uint64_t sbo = (8 * KC * 2) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int KC>
+__global__ void __launch_bounds__(192, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                   const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
+                   void* __restrict__ y) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = TC_M * KC * 2;
+  const int b_bytes = (p.Cout_w * KC * 2 + 1023) & ~1023;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* accum_full = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ph = blockIdx.z;
+  // tile -> (n, tz, ty, tx)
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_w; tile /= p.tiles_w;
+  const int ty = tile % p.tiles_h; tile /= p.tiles_h;
+  const int tz = tile % p.tiles_d;
+  const int n = tile / p.tiles_d;
+  const int ox0 = tx * p.tw, oy0 = ty * p.th, oz0 = tz * p.td;
+  const int kiters = p.ntaps * p.nkc;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.Cout_w) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (one lane) =================
+    if (lane == 0) {
+      const uint32_t tx_bytes = A_BYTES + p.Cout_w * KC * 2;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % TC_STAGES;
+        if (it >= TC_STAGES) mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+        const int t = it / p.nkc, kc = it - t * p.nkc;
+        const int8_t* off = p.tap_off[ph * p.ntaps + t];
+        mbar_expect_tx(&full[s], tx_bytes);
+        tma_load_5d(&tmA, &full[s], sA + s * A_BYTES, kc * KC, ox0 * p.in_stride + off[2], oy0 * p.in_stride + off[1],
+                    oz0 * p.in_stride + off[0], n);
+        tma_load_2d(&tmB, &full[s], sB + s * b_bytes, 0, ((ph * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one lane) =================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * b_bytes);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          umma_bf16(tmem_base, make_kmajor_desc<KC>(a0 + k * 32), make_kmajor_desc<KC>(b0 + k * 32), idesc,
+                    (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(&empty[s]);          // frees the smem slot when these MMAs have read it
+      }
+      tcgen05_commit(accum_full);           // accumulator complete
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rx = row % p.tw, ry = (row / p.tw) % p.th, rz = row / (p.tw * p.th);
+    const int ox = ox0 + rx, oy = oy0 + ry, oz = oz0 + rz;
+    const bool valid = ox < p.Wo && oy < p.Ho && oz < p.Do;
+    const int yz = oz * p.out_stride + ((ph >> 2) & 1), yy = oy * p.out_stride + ((ph >> 1) & 1), yx = ox * p.out_stride + (ph & 1);
+    const int64_t yo = ((((int64_t)n * p.Dy + yz) * p.Hy + yy) * p.Wy + yx) * p.Cout_s;
+    mbar_wait(accum_full, 0);
+    tcgen05_fence_after();
+    for (int c0 = 0; c0 < p.Cout_w; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = v[j] + __ldg(bias + c0 + j);
+        if (p.has_prelu) a = a > 0.0f ? a : a * __ldg(prelu + c0 + j);
+        v[j] = a;
+      }
+      const int nstore = min(16, p.Cout_s - c0);   // 16, or 8 for the 8-channel head tensor
+      if (nstore <= 0) continue;
+      if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(y) + yo + c0;
+        if (p.has_residual) {
+          const float* r = reinterpret_cast<const float*>(residual) + yo + c0;
+          for (int j = 0; j < nstore; ++j) v[j] += __ldg(r + j);
+        }
+        for (int j = 0; j < nstore; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + yo + c0;
+        if (p.has_residual) {
+          const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(residual) + yo + c0;
+          for (int j = 0; j < nstore; j += 8) {
+            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(r + j));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[j + 2 * e] += __low2float(h[e]); v[j + 2 * e + 1] += __high2float(h[e]); }
+          }
+        }
+        for (int j = 0; j < nstore; j += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+template <int KC>
+static int launch_tc(const TcParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* prelu,
+                     const void* residual, void* y, dim3 grid, cudaStream_t st) {
+  const int b_bytes = (P.Cout_w * KC * 2 + 1023) & ~1023;
+  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_M * KC * 2 + b_bytes) + (2 * TC_STAGES + 1) * 8 + 16;
+  static bool attr_done = false;   // per-template-instance
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error("ofsv_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
+    attr_done = true;
+  }
+  conv_tc_kernel<KC><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
+  return check_launch("conv_tc_kernel");
+}
+
+}  // namespace ofsv
+
+using namespace ofsv;
+
+extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                            const void* residual, void* y, void* stream) {
+  if (int e = validate_conv_desc(d, "ofsv_conv_tc")) return e;
+  if (d->N == 0) return OFSV_OK;
+  OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_tc: null pointer");
+  OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_tc: has_prelu without prelu slopes");
+  OFSV_REQUIRE(!d->has_residual || residual, "ofsv_conv_tc: has_residual without residual");
+  OFSV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!residual || aligned16(residual)),
+               "ofsv_conv_tc: pointers must be 16-byte aligned");
+  if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_tc: activations must be bf16"); return OFSV_ENOSUP; }
+  if (d->Cout_w > 128) { set_error("ofsv_conv_tc: Cout_w=%d > 128 not supported", d->Cout_w); return OFSV_ENOSUP; }
+  PFN_encodeTiled encode = get_encode();
+  if (!encode) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled unavailable (driver too old?)"); return OFSV_ECUDA; }
+
+  const int KC = d->Cin_s % 64 == 0 ? 64 : (d->Cin_s % 32 == 0 ? 32 : 16);
+  TcParams P;
+  P.N = d->N; P.Do = d->Do; P.Ho = d->Ho; P.Wo = d->Wo; P.Dy = d->Dy; P.Hy = d->Hy; P.Wy = d->Wy;
+  P.Cout_s = d->Cout_s; P.Cout_w = d->Cout_w; P.in_stride = d->in_stride; P.out_stride = d->out_stride;
+  P.ntaps = d->ntaps; P.nkc = d->Cin_s / KC;
+  if (d->nd == 3) { P.tw = 8; P.th = 4; P.td = 4; } else { P.tw = 16; P.th = 8; P.td = 1; }
+  P.tiles_w = (int)cdiv(d->Wo, P.tw); P.tiles_h = (int)cdiv(d->Ho, P.th); P.tiles_d = (int)cdiv(d->Do, P.td);
+  P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
+  memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
+  const int64_t ntiles = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
+  OFSV_REQUIRE(ntiles < (1ll << 31), "ofsv_conv_tc: too many tiles");
+
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t gdim[5] = {(cuuint64_t)d->Cin_s, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->Di, (cuuint64_t)d->N};
+    const cuuint64_t es = 2;
+    const cuuint64_t gstr[4] = {d->Cin_s * es, (cuuint64_t)d->Wi * d->Cin_s * es, (cuuint64_t)d->Hi * d->Wi * d->Cin_s * es,
+                                (cuuint64_t)d->Di * d->Hi * d->Wi * d->Cin_s * es};
+    const cuuint32_t s = (cuuint32_t)d->in_stride, sd = d->nd == 3 ? s : 1;   // 2-D: the D axis has extent 1
+    const cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)P.tw * s, (cuuint32_t)P.th * s, (cuuint32_t)P.td * sd, 1};
+    const cuuint32_t estr[5] = {1, s, s, sd, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return OFSV_ECUDA; }
+  }
+  {
+    const cuuint64_t rows = (cuuint64_t)d->nphase * d->ntaps * P.nkc * d->Cout_w;
+    const cuuint64_t gdim[2] = {(cuuint64_t)KC, rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KC * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)d->Cout_w};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
+  }
+  const dim3 grid((unsigned)ntiles, 1, (unsigned)d->nphase);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (KC == 64) return launch_tc<64>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  if (KC == 32) return launch_tc<32>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  return launch_tc<16>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
 }

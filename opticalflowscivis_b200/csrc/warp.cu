@@ -306,11 +306,11 @@ using namespace ofsv;
 
 extern "C" int ofsv_warp2d_f32(const float* src, const float* flow, const float* lin_x, const float* lin_y, float* out,
                                int N, int C, int H, int W, int ref_mode, void* stream) {
-  OFSV_REQUIRE(src && flow && lin_x && lin_y && out, "ofsv_warp2d_f32: null pointer");
   OFSV_REQUIRE(N >= 0 && C >= 0 && H >= 1 && W >= 1, "ofsv_warp2d_f32: bad shape N=%d C=%d H=%d W=%d", N, C, H, W);
+  if ((int64_t)N * C == 0) return OFSV_OK;   // empty batch: nothing to do (pointers may be null)
+  OFSV_REQUIRE(src && flow && lin_x && lin_y && out, "ofsv_warp2d_f32: null pointer");
   OFSV_REQUIRE((int64_t)H * W < (1ll << 31), "ofsv_warp2d_f32: plane too large");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp2d_f32: bad ref_mode %d", ref_mode);
-  if ((int64_t)N * C * H * W == 0) return OFSV_OK;
   warp2d_kernel<<<grid_1d((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(src, flow, lin_x, lin_y, out, N, C, H, W,
                                                                                 ref_mode);
   return check_launch("warp2d_kernel");
@@ -319,11 +319,11 @@ extern "C" int ofsv_warp2d_f32(const float* src, const float* flow, const float*
 extern "C" int ofsv_warp_blend_2d_f32(const float* img0, const float* img1, const float* flow, const float* mask_logit,
                                       const float* lin_x, const float* lin_y, float* warped0, float* warped1,
                                       float* merged, float* mask_sig, int N, int H, int W, int ref_mode, void* stream) {
-  OFSV_REQUIRE(img0 && img1 && flow && lin_x && lin_y, "ofsv_warp_blend_2d_f32: null pointer");
-  OFSV_REQUIRE(mask_logit || (!merged && !mask_sig), "ofsv_warp_blend_2d_f32: merged/mask_sig need mask_logit");
   OFSV_REQUIRE(N >= 0 && H >= 1 && W >= 1 && (int64_t)H * W < (1ll << 31), "ofsv_warp_blend_2d_f32: bad shape");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp_blend_2d_f32: bad ref_mode");
   if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(img0 && img1 && flow && lin_x && lin_y, "ofsv_warp_blend_2d_f32: null pointer");
+  OFSV_REQUIRE(mask_logit || (!merged && !mask_sig), "ofsv_warp_blend_2d_f32: merged/mask_sig need mask_logit");
   warp_blend_2d_kernel<<<grid_1d((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(
       img0, img1, flow, mask_logit, lin_x, lin_y, warped0, warped1, merged, mask_sig, N, H, W, ref_mode);
   return check_launch("warp_blend_2d_kernel");
@@ -332,15 +332,14 @@ extern "C" int ofsv_warp_blend_2d_f32(const float* img0, const float* img1, cons
 extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d,
                                const float* lin_w, float* out, int N, int C, int D, int H, int W, int ref_mode,
                                void* stream) {
-  OFSV_REQUIRE(src && flow && lin_h && lin_d && lin_w && out, "ofsv_warp3d_f32: null pointer");
   OFSV_REQUIRE(N >= 0 && C >= 0 && D >= 1 && H >= 1 && W >= 1, "ofsv_warp3d_f32: bad shape");
+  if ((int64_t)N * C == 0) return OFSV_OK;   // empty batch
+  OFSV_REQUIRE(src && flow && lin_h && lin_d && lin_w && out, "ofsv_warp3d_f32: null pointer");
   OFSV_REQUIRE((int64_t)D * H * W < (1ll << 31), "ofsv_warp3d_f32: volume too large for 32-bit voxel offsets");
   OFSV_REQUIRE((int64_t)N * D <= 65535 * 1ll * 65535, "ofsv_warp3d_f32: N*D too large");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp3d_f32: bad ref_mode %d", ref_mode);
-  if ((int64_t)N * C == 0) return OFSV_OK;
   const Warp3dParams P = make_params(N, C, D, H, W, ref_mode);
   const dim3 grid((unsigned)cdiv(W, T3), (unsigned)cdiv(H, T3), (unsigned)(N * D));
-  OFSV_REQUIRE(grid.z <= 65535u || true, "unreachable");
   const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
   cudaStream_t st = (cudaStream_t)stream;
   if (grid.z > 65535u) { set_error("ofsv_warp3d_f32: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
@@ -355,11 +354,11 @@ extern "C" int ofsv_warp_blend_3d_f32(const float* img0, const float* img1, cons
                                       const float* lin_h, const float* lin_d, const float* lin_w, float* warped0,
                                       float* warped1, float* merged, float* mask_sig, int N, int D, int H, int W,
                                       int ref_mode, void* stream) {
-  OFSV_REQUIRE(img0 && img1 && flow && lin_h && lin_d && lin_w, "ofsv_warp_blend_3d_f32: null pointer");
-  OFSV_REQUIRE(mask_logit || (!merged && !mask_sig), "ofsv_warp_blend_3d_f32: merged/mask_sig need mask_logit");
   OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < (1ll << 31), "ofsv_warp_blend_3d_f32: bad shape");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp_blend_3d_f32: bad ref_mode");
   if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(img0 && img1 && flow && lin_h && lin_d && lin_w, "ofsv_warp_blend_3d_f32: null pointer");
+  OFSV_REQUIRE(mask_logit || (!merged && !mask_sig), "ofsv_warp_blend_3d_f32: merged/mask_sig need mask_logit");
   const Warp3dParams P = make_params(N, 1, D, H, W, ref_mode);
   const dim3 grid((unsigned)cdiv(W, T3), (unsigned)cdiv(H, T3), (unsigned)(N * D));
   if (grid.z > 65535u) { set_error("ofsv_warp_blend_3d_f32: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }

@@ -101,13 +101,15 @@ def test_warp3d_full_size_properties():
     src = (torch.rand((1, 1, S, S, S), generator=g) > 0.5).float().to(_dev())     # binary volume: steepest gradients
     zero = torch.zeros((1, 3, S, S, S), device=_dev())
     out = ops.warp3d(src, zero)
-    assert float((out - src.permute(0, 1, 3, 4, 2)).abs().max()) <= 1e-6
+    # the reference's normalise/unnormalise round trip is not exact at S=256: ~5e-5 on a binary volume
+    assert float((out - src.permute(0, 1, 3, 4, 2)).abs().max()) <= 2e-4
+    assert float((out - src).abs().max()) > 0.5
     shift = torch.zeros_like(zero)
     shift[:, 0], shift[:, 1], shift[:, 2] = 3.0, -2.0, 5.0
     out = ops.warp3d(src, shift)
     # out[d,h,w] = src[w+5, d-2, h+3] in the interior
     ref = src.permute(0, 1, 3, 4, 2).roll(shifts=(2, -3, -5), dims=(2, 3, 4))
-    assert float((out - ref)[:, :, 4:-4, 4:-4, 8:-8].abs().max()) <= 2e-5
+    assert float((out - ref)[:, :, 4:-4, 4:-4, 8:-8].abs().max()) <= 2e-4
     o.set_reference_flavor("cuda")
     flow = (torch.randn((1, 3, S, S, S), generator=g) * 2).to(_dev())
     d = float((ops.warp3d(src, flow) - warp3d_ref(src, flow)).abs().max())
