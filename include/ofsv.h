@@ -138,6 +138,16 @@ int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const fl
 int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, const float* mask_prev, float* flow_out,
                            float* mask_out, int nd, int N, int D, int H, int W, int scale, void* stream);
 
+/* Fused 3-D IFBlock output stage: ofsv_head_upsample_add + ofsv_warp_blend_3d_f32 (+ the next block's
+ * ofsv_pack_block_input) in one pass over the full-resolution voxels — Flow-3D/model/IFNet.py:118-119 (resize, *scale),
+ * :169-170 (flow/mask accumulate), :186-191 (sigmoid, warp x2), :242 (blend), :82-90,166 (next block's resized concat).
+ * head [N][D/sh][H/sh][W/sh][Cs] fp32; flow_prev/mask_prev NULL for block0; merged/mask_sig optional;
+ * scale_next in {0: no packed output, 1, 2}: pack_out [N][D/sn][H/sn][W/sn][16] bf16 = the next block's conv0 input. */
+int ofsv_block_finish_3d(const float* head, int Cs, const float* flow_prev, const float* mask_prev, const float* img0,
+                         const float* img1, const float* lin_h, const float* lin_d, const float* lin_w, float* flow_out,
+                         float* mask_out, float* merged, float* mask_sig, void* pack_out, int N, int D, int H, int W,
+                         int scale_head, int scale_next, int ref_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,21 @@ __device__ __forceinline__ float cvt<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ void store16(float* o, const float* v) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* o, const float* v) {
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // mean of the 2^nd samples {s*o + s/2 - 1, s*o + s/2} per axis == F.interpolate(1/s) for s in {2,4}; s = 1 reads directly.
 template <int ND>
 __device__ __forceinline__ float down_sample(const float* __restrict__ vol, int H, int W, int oz, int oy, int ox, int s) {
@@ -65,10 +80,14 @@ __global__ void __launch_bounds__(256)
         v[5 + c] = __fmul_rn(down_sample<ND>(flow + ((int64_t)n * NF + c) * V, H, W, oz, oy, ox, s), inv_s);
     }
     T* o = dst + i * Cs;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = cvt<T>(v[c]);
+    store16(o, v);                                  // one 32 B (bf16) / 64 B (fp32) vector row per position
     for (int c = 16; c < Cs; ++c) o[c] = cvt<T>(0.0f);
   }
+}
+
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 struct Lerp {
@@ -103,9 +122,10 @@ __global__ void __launch_bounds__(256)
     float v[NC];
     const float* hb = head + (int64_t)n * Dh * Hh * Wh * Cs;
     if (s == 1) {
-      const float* p = hb + r * Cs;
+      float t8[8];
+      ld8(hb + r * Cs, t8);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) v[c] = __ldg(p + c);
+      for (int c = 0; c < NC; ++c) v[c] = t8[c];
     } else {
       const Lerp lx = up_index(x, Wh, rscale), ly = up_index(y, Hh, rscale);
       Lerp lz; lz.i0 = lz.i1 = 0; lz.l0 = 1.0f; lz.l1 = 0.0f;
@@ -118,10 +138,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const int yy = dy ? ly.i1 : ly.i0;
-          const float* p0 = hb + (((int64_t)zz * Hh + yy) * Wh + lx.i0) * Cs;
-          const float* p1 = hb + (((int64_t)zz * Hh + yy) * Wh + lx.i1) * Cs;
+          float c0[8], c1[8];
+          ld8(hb + (((int64_t)zz * Hh + yy) * Wh + lx.i0) * Cs, c0);
+          ld8(hb + (((int64_t)zz * Hh + yy) * Wh + lx.i1) * Cs, c1);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) acc_y[dy][c] = __fadd_rn(__fmul_rn(__ldg(p0 + c), lx.l0), __fmul_rn(__ldg(p1 + c), lx.l1));
+          for (int c = 0; c < NC; ++c) acc_y[dy][c] = __fadd_rn(__fmul_rn(c0[c], lx.l0), __fmul_rn(c1[c], lx.l1));
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc_z[dz][c] = __fadd_rn(__fmul_rn(acc_y[0][c], ly.l0), __fmul_rn(acc_y[1][c], ly.l1));
@@ -163,6 +184,7 @@ extern "C" int ofsv_pack_block_input(const float* img0, const float* img1, const
   OFSV_REQUIRE(Cs >= 16 && Cs % 16 == 0, "ofsv_pack_block_input: Cs must be a multiple of 16");
   if (N == 0) return OFSV_OK;
   OFSV_REQUIRE(img0 && img1 && dst, "ofsv_pack_block_input: null pointer");
+  OFSV_REQUIRE(aligned16(dst), "ofsv_pack_block_input: dst must be 16-byte aligned");
   OFSV_REQUIRE(flow == nullptr || (warped0 && warped1 && mask), "ofsv_pack_block_input: flow needs warped0/1 and mask");
   const int64_t total = (int64_t)N * (nd == 3 ? D / scale : 1) * (H / scale) * (W / scale);
   cudaStream_t st = (cudaStream_t)stream;
@@ -180,12 +202,13 @@ extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* fl
                                       void* stream) {
   OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_head_upsample_add: nd must be 2 or 3");
   OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_head_upsample_add: scale %d not in {1,2,4}", scale);
-  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && Cs >= 2 * nd + 1, "ofsv_head_upsample_add: bad shape");
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && Cs >= 8 && Cs % 4 == 0, "ofsv_head_upsample_add: bad shape (Cs must be >= 8, multiple of 4)");
   OFSV_REQUIRE((nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
                "ofsv_head_upsample_add: spatial dims must be multiples of scale");
   OFSV_REQUIRE((flow_prev == nullptr) == (mask_prev == nullptr), "ofsv_head_upsample_add: flow_prev and mask_prev go together");
   if (N == 0) return OFSV_OK;
   OFSV_REQUIRE(head && flow_out && mask_out, "ofsv_head_upsample_add: null pointer");
+  OFSV_REQUIRE(aligned16(head), "ofsv_head_upsample_add: head must be 16-byte aligned");
   const int g = grid_1d((int64_t)N * D * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   if (nd == 2) head_upsample_add_kernel<2><<<g, 256, 0, st>>>(head, Cs, flow_prev, mask_prev, flow_out, mask_out, N, D, H, W, scale);

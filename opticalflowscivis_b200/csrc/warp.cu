@@ -10,6 +10,7 @@
 //    results go back through shared memory so the stores are again float4 along w.
 //  * All coordinate arithmetic replicates the reference op-for-op (ofsv_common.cuh); 1e-5 parity needs it.
 #include "ofsv_common.cuh"
+#include "warp_device.cuh"
 
 namespace ofsv {
 
@@ -98,129 +99,31 @@ __global__ void __launch_bounds__(256)
 // ----------------------------------------------------------------------------------------------------
 // 3-D
 // ----------------------------------------------------------------------------------------------------
-struct Trilin {
-  int base;            // z0*HW + y0*W + x0
-  bool okx, oky, okz;  // +1 neighbour inside the volume
-  float ex, wx, ey, wy, ez, wz;
-};
-
-// (f0,f1,f2) = flow channels; lh/ld/lw = linspace entries of THIS output voxel's (h,d,w).
-__device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
-                                               int W, const float* hs, int ref_mode) {
-  const float g0 = __fadd_rn(lh, norm_flow(f0, hs[0], hs[3], ref_mode));  // sampled along the W axis
-  const float g1 = __fadd_rn(ld, norm_flow(f1, hs[1], hs[4], ref_mode));  // along H
-  const float g2 = __fadd_rn(lw, norm_flow(f2, hs[2], hs[5], ref_mode));  // along D
-  const float ix = unnorm_clip_ac(g0, (float)(W - 1)), iy = unnorm_clip_ac(g1, (float)(H - 1)),
-              iz = unnorm_clip_ac(g2, (float)(D - 1));
-  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-  Trilin t;
-  t.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix); t.wx = __fsub_rn(ix, fx);
-  t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy); t.wy = __fsub_rn(iy, fy);
-  t.ez = __fsub_rn(__fadd_rn(fz, 1.0f), iz); t.wz = __fsub_rn(iz, fz);
-  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-  t.okx = x0 + 1 <= W - 1; t.oky = y0 + 1 <= H - 1; t.okz = z0 + 1 <= D - 1;
-  t.base = (z0 * H + y0) * W + x0;
-  return t;
-}
-
-template <bool FMA>
-__device__ __forceinline__ float acc_tap(float acc, float v, float w) {
-  return FMA ? __fmaf_rn(v, w, acc) : __fadd_rn(acc, __fmul_rn(v, w));
-}
-
-// ATen grid_sampler_3d corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse; weights = product of 3 distances, left to right.
-template <bool FMA>
-__device__ __forceinline__ float trilin_sample(const float* __restrict__ p, const Trilin& t, int W, int HW) {
-  const float* q = p + t.base;
-  const float xy00 = __fmul_rn(t.ex, t.ey), xy10 = __fmul_rn(t.wx, t.ey), xy01 = __fmul_rn(t.ex, t.wy),
-              xy11 = __fmul_rn(t.wx, t.wy);
-  float acc = 0.0f;
-  acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.ez));
-  if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.ez));
-  if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.ez));
-  if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.ez));
-  if (t.okz) {
-    q += HW;
-    acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.wz));
-    if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.wz));
-    if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.wz));
-    if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.wz));
-  }
-  return acc;
-}
-
-constexpr int T3 = 32;       // tile edge (h and w)
-constexpr int T3P = T3 + 1;  // padded smem pitch (bank-conflict-free column access)
-
-// coalesced tile load: 256 threads, thread -> (row = tid/8, 4 consecutive w)
-template <bool VEC>
-__device__ __forceinline__ void load_tile(float (*s)[T3P], const float* __restrict__ plane, int h0, int w0, int H, int W) {
-  const int row = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-  const int h = h0 + row, w = w0 + c4;
-  if (h < H) {
-    const float* g = plane + (int64_t)h * W + w;
-    if (VEC && w + 3 < W) {
-      const float4 v = ldg_stream4(g);
-      s[row][c4] = v.x; s[row][c4 + 1] = v.y; s[row][c4 + 2] = v.z; s[row][c4 + 3] = v.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s[row][c4 + i] = (w + i < W) ? ldg_stream(g + i) : 0.0f;
-    }
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void store_tile(const float (*s)[T3P], float* __restrict__ plane, int h0, int w0, int H, int W) {
-  const int row = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-  const int h = h0 + row, w = w0 + c4;
-  if (h < H) {
-    float* g = plane + (int64_t)h * W + w;
-    if (VEC && w + 3 < W) {
-      stg_stream4(g, make_float4(s[row][c4], s[row][c4 + 1], s[row][c4 + 2], s[row][c4 + 3]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (w + i < W) g[i] = s[row][c4 + i];
-    }
-  }
-}
-
-struct Warp3dParams {
-  int N, C, D, H, W, ref_mode;
-  float hs[6];  // (H-1)/2, (D-1)/2, (W-1)/2 and their fp32 reciprocals (computed in double like ATen)
-};
-
 template <bool VEC, bool FMA>
 __global__ void __launch_bounds__(256)
     warp3d_kernel(const float* __restrict__ src, const float* __restrict__ flow, const float* __restrict__ lin_h,
                   const float* __restrict__ lin_d, const float* __restrict__ lin_w, float* __restrict__ out,
                   const Warp3dParams P) {
-  __shared__ float sf[3][T3][T3P];
-  __shared__ float so[T3][T3P];
+  __shared__ float sf[3][T3H][T3P];
+  __shared__ float so[1][T3H][T3P];
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int64_t V = (int64_t)D * HW;
   const int n = blockIdx.z / D, d = blockIdx.z - n * D;
-  const int h0 = blockIdx.y * T3, w0 = blockIdx.x * T3;
+  const int h0 = blockIdx.y * T3H, w0 = blockIdx.x * T3W;
   const float* fl = flow + (int64_t)n * 3 * V + (int64_t)d * HW;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) load_tile<VEC>(sf[c], fl + (int64_t)c * V, h0, w0, H, W);
+  load_planes<3, VEC>(sf, [&](int k) { return fl + (int64_t)k * V; }, h0, w0, H, W);
   __syncthreads();
-  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const int h = h0 + lane;
-  const bool hv = h < H;
-  const float lh = hv ? __ldg(lin_h + h) : 0.0f, ld = __ldg(lin_d + d);
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int h = h0 + lane, w = w0 + wl;
+  const bool ok = h < H && w < W;
+  Trilin t;
+  if (ok) t = trilin_setup(sf[0][lane][wl], sf[1][lane][wl], sf[2][lane][wl], __ldg(lin_h + h), __ldg(lin_d + d),
+                           __ldg(lin_w + w), D, H, W, P.hs, P.ref_mode);
   for (int c = 0; c < P.C; ++c) {
-    const float* sv = src + ((int64_t)n * P.C + c) * V;
-#pragma unroll
-    for (int j = 0; j < T3 / 8; ++j) {
-      const int wl = wq + j * 8, w = w0 + wl;
-      if (hv && w < W) {
-        const Trilin t = trilin_setup(sf[0][lane][wl], sf[1][lane][wl], sf[2][lane][wl], lh, ld, __ldg(lin_w + w), D, H,
-                                      W, P.hs, P.ref_mode);
-        so[lane][wl] = trilin_sample<FMA>(sv, t, W, HW);
-      }
-    }
+    if (ok) so[0][lane][wl] = trilin_sample<FMA>(src + ((int64_t)n * P.C + c) * V, t, W, HW);
     __syncthreads();
-    store_tile<VEC>(so, out + ((int64_t)n * P.C + c) * V + (int64_t)d * HW, h0, w0, H, W);
+    float* o = out + ((int64_t)n * P.C + c) * V + (int64_t)d * HW;
+    store_planes<1, VEC>(so, [&](int) { return o; }, h0, w0, H, W);
     __syncthreads();
   }
 }
@@ -233,47 +136,37 @@ __global__ void __launch_bounds__(256)
                          const float* __restrict__ lin_d, const float* __restrict__ lin_w, float* __restrict__ warped0,
                          float* __restrict__ warped1, float* __restrict__ merged, float* __restrict__ mask_sig,
                          const Warp3dParams P) {
-  __shared__ float s[7][T3][T3P];  // flow0..5, mask; slots 0..3 are re-used for the outputs
+  __shared__ float si[7][T3H][T3P];  // flow0..5, mask logit
+  __shared__ float so[4][T3H][T3P];  // warped0, warped1, merged, sigmoid(mask)
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int64_t V = (int64_t)D * HW;
   const int n = blockIdx.z / D, d = blockIdx.z - n * D;
-  const int h0 = blockIdx.y * T3, w0 = blockIdx.x * T3;
+  const int h0 = blockIdx.y * T3H, w0 = blockIdx.x * T3W;
   const int64_t plane = (int64_t)n * V + (int64_t)d * HW;
   const float* fl = flow + (int64_t)n * 6 * V + (int64_t)d * HW;
-#pragma unroll
-  for (int c = 0; c < 6; ++c) load_tile<VEC>(s[c], fl + (int64_t)c * V, h0, w0, H, W);
   const bool need_m = (merged != nullptr) || (mask_sig != nullptr);
-  if (need_m) load_tile<VEC>(s[6], mask_logit + plane, h0, w0, H, W);
+  load_planes<7, VEC>(si, [&](int k) -> const float* {
+    return k < 6 ? fl + (int64_t)k * V : (need_m ? mask_logit + plane : nullptr); }, h0, w0, H, W);
   __syncthreads();
-  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const int h = h0 + lane;
-  const bool hv = h < H;
-  const float lh = hv ? __ldg(lin_h + h) : 0.0f, ld = __ldg(lin_d + d);
-  const float* v0 = img0 + (int64_t)n * V;
-  const float* v1 = img1 + (int64_t)n * V;
-#pragma unroll
-  for (int j = 0; j < T3 / 8; ++j) {
-    const int wl = wq + j * 8, w = w0 + wl;
-    if (hv && w < W) {
-      const float lw = __ldg(lin_w + w);
-      const Trilin t0 = trilin_setup(s[0][lane][wl], s[1][lane][wl], s[2][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-      const Trilin t1 = trilin_setup(s[3][lane][wl], s[4][lane][wl], s[5][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-      const float a = trilin_sample<FMA>(v0, t0, W, HW);
-      const float b = trilin_sample<FMA>(v1, t1, W, HW);
-      float m = 0.0f, mg = 0.0f;
-      if (need_m) {
-        m = sigmoidf_ref(s[6][lane][wl]);
-        mg = __fadd_rn(__fmul_rn(a, m), __fmul_rn(b, __fsub_rn(1.0f, m)));
-      }
-      // same thread, same slot: no hazard with other threads' pending reads
-      s[0][lane][wl] = a; s[1][lane][wl] = b; s[2][lane][wl] = mg; s[3][lane][wl] = m;
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int h = h0 + lane, w = w0 + wl;
+  if (h < H && w < W) {
+    const float lh = __ldg(lin_h + h), ld = __ldg(lin_d + d), lw = __ldg(lin_w + w);
+    const Trilin t0 = trilin_setup(si[0][lane][wl], si[1][lane][wl], si[2][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+    const Trilin t1 = trilin_setup(si[3][lane][wl], si[4][lane][wl], si[5][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+    const float a = trilin_sample<FMA>(img0 + (int64_t)n * V, t0, W, HW);
+    const float b = trilin_sample<FMA>(img1 + (int64_t)n * V, t1, W, HW);
+    float m = 0.0f, mg = 0.0f;
+    if (need_m) {
+      m = sigmoidf_ref(si[6][lane][wl]);
+      mg = __fadd_rn(__fmul_rn(a, m), __fmul_rn(b, __fsub_rn(1.0f, m)));
     }
+    so[0][lane][wl] = a; so[1][lane][wl] = b; so[2][lane][wl] = mg; so[3][lane][wl] = m;
   }
   __syncthreads();
-  if (warped0) store_tile<VEC>(s[0], warped0 + plane, h0, w0, H, W);
-  if (warped1) store_tile<VEC>(s[1], warped1 + plane, h0, w0, H, W);
-  if (merged) store_tile<VEC>(s[2], merged + plane, h0, w0, H, W);
-  if (mask_sig) store_tile<VEC>(s[3], mask_sig + plane, h0, w0, H, W);
+  store_planes<4, VEC>(so, [&](int k) -> float* {
+    float* b = k == 0 ? warped0 : (k == 1 ? warped1 : (k == 2 ? merged : mask_sig));
+    return b ? b + plane : nullptr; }, h0, w0, H, W);
 }
 
 __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
@@ -283,15 +176,6 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ w0
     const float m = sigmoidf_ref(ldg_stream(mask_logit + i));
     merged[i] = __fadd_rn(__fmul_rn(ldg_stream(w0 + i), m), __fmul_rn(ldg_stream(w1 + i), __fsub_rn(1.0f, m)));
   }
-}
-
-static Warp3dParams make_params(int N, int C, int D, int H, int W, int ref_mode) {
-  Warp3dParams P;
-  P.N = N; P.C = C; P.D = D; P.H = H; P.W = W; P.ref_mode = ref_mode;
-  const double h0 = (H - 1.0) / 2.0, h1 = (D - 1.0) / 2.0, h2 = (W - 1.0) / 2.0;  // Flow-3D/model/warplayer.py:24-26
-  P.hs[0] = (float)h0; P.hs[1] = (float)h1; P.hs[2] = (float)h2;
-  P.hs[3] = (float)(1.0 / h0); P.hs[4] = (float)(1.0 / h1); P.hs[5] = (float)(1.0 / h2);
-  return P;
 }
 
 static inline int grid_1d(int64_t total) {
@@ -338,8 +222,8 @@ extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float*
   OFSV_REQUIRE((int64_t)D * H * W < (1ll << 31), "ofsv_warp3d_f32: volume too large for 32-bit voxel offsets");
   OFSV_REQUIRE((int64_t)N * D <= 65535 * 1ll * 65535, "ofsv_warp3d_f32: N*D too large");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp3d_f32: bad ref_mode %d", ref_mode);
-  const Warp3dParams P = make_params(N, C, D, H, W, ref_mode);
-  const dim3 grid((unsigned)cdiv(W, T3), (unsigned)cdiv(H, T3), (unsigned)(N * D));
+  const Warp3dParams P = make_warp3d_params(N, C, D, H, W, ref_mode);
+  const dim3 grid((unsigned)cdiv(W, T3W), (unsigned)cdiv(H, T3H), (unsigned)(N * D));
   const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
   cudaStream_t st = (cudaStream_t)stream;
   if (grid.z > 65535u) { set_error("ofsv_warp3d_f32: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
@@ -359,8 +243,8 @@ extern "C" int ofsv_warp_blend_3d_f32(const float* img0, const float* img1, cons
   if (N == 0) return OFSV_OK;
   OFSV_REQUIRE(img0 && img1 && flow && lin_h && lin_d && lin_w, "ofsv_warp_blend_3d_f32: null pointer");
   OFSV_REQUIRE(mask_logit || (!merged && !mask_sig), "ofsv_warp_blend_3d_f32: merged/mask_sig need mask_logit");
-  const Warp3dParams P = make_params(N, 1, D, H, W, ref_mode);
-  const dim3 grid((unsigned)cdiv(W, T3), (unsigned)cdiv(H, T3), (unsigned)(N * D));
+  const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
+  const dim3 grid((unsigned)cdiv(W, T3W), (unsigned)cdiv(H, T3H), (unsigned)(N * D));
   if (grid.z > 65535u) { set_error("ofsv_warp_blend_3d_f32: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
   bool vec = (W % 4 == 0) && aligned16(flow);
   const void* ptrs[] = {mask_logit, warped0, warped1, merged, mask_sig};

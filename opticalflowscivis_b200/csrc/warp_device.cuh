@@ -1,0 +1,128 @@
+// Device helpers shared by the 3-D warp kernels (warp.cu) and the fused IFBlock output stage (block_finish.cu).
+#pragma once
+#include "ofsv_common.cuh"
+
+namespace ofsv {
+
+struct Trilin {
+  int base;            // z0*HW + y0*W + x0
+  bool okx, oky, okz;  // +1 neighbour inside the volume
+  float ex, wx, ey, wy, ez, wz;
+};
+
+// (f0,f1,f2) = flow channels; lh/ld/lw = linspace entries of THIS output voxel's (h,d,w).
+__device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
+                                               int W, const float* hs, int ref_mode) {
+  const float g0 = __fadd_rn(lh, norm_flow(f0, hs[0], hs[3], ref_mode));  // sampled along the W axis
+  const float g1 = __fadd_rn(ld, norm_flow(f1, hs[1], hs[4], ref_mode));  // along H
+  const float g2 = __fadd_rn(lw, norm_flow(f2, hs[2], hs[5], ref_mode));  // along D
+  const float ix = unnorm_clip_ac(g0, (float)(W - 1)), iy = unnorm_clip_ac(g1, (float)(H - 1)),
+              iz = unnorm_clip_ac(g2, (float)(D - 1));
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  Trilin t;
+  t.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix); t.wx = __fsub_rn(ix, fx);
+  t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy); t.wy = __fsub_rn(iy, fy);
+  t.ez = __fsub_rn(__fadd_rn(fz, 1.0f), iz); t.wz = __fsub_rn(iz, fz);
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  t.okx = x0 + 1 <= W - 1; t.oky = y0 + 1 <= H - 1; t.okz = z0 + 1 <= D - 1;
+  t.base = (z0 * H + y0) * W + x0;
+  return t;
+}
+
+template <bool FMA>
+__device__ __forceinline__ float acc_tap(float acc, float v, float w) {
+  return FMA ? __fmaf_rn(v, w, acc) : __fadd_rn(acc, __fmul_rn(v, w));
+}
+
+// ATen grid_sampler_3d corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse; weights = product of 3 distances, left to right.
+template <bool FMA>
+__device__ __forceinline__ float trilin_sample(const float* __restrict__ p, const Trilin& t, int W, int HW) {
+  const float* q = p + t.base;
+  const float xy00 = __fmul_rn(t.ex, t.ey), xy10 = __fmul_rn(t.wx, t.ey), xy01 = __fmul_rn(t.ex, t.wy),
+              xy11 = __fmul_rn(t.wx, t.wy);
+  float acc = 0.0f;
+  acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.ez));
+  if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.ez));
+  if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.ez));
+  if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.ez));
+  if (t.okz) {
+    q += HW;
+    acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.wz));
+    if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.wz));
+    if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.wz));
+    if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.wz));
+  }
+  return acc;
+}
+
+// CTA tile of the 3-D kernels: 32 (h) x 8 (w) voxels at fixed (n, d); 256 threads = one voxel each, warp q owns the
+// w column q with its lanes along h (coalesced 128 B source gathers).  Global I/O of the tile is 32 rows x 32 B (one
+// full sector per row and plane) moved as float4 by the first P*64 threads; shared planes are padded to 9 floats.
+constexpr int T3H = 32, T3W = 8, T3P = T3W + 1;
+
+// planes[k] (k < NP) -> s[k][32][9]; a null plane pointer zero-fills.  `poff` = offset of the tile's (n,d) plane.
+// `plane_ptr(k)` returns the global pointer of plane k's (n,d) slice, or nullptr to zero-fill / skip.
+template <int NP, bool VEC, typename F>
+__device__ __forceinline__ void load_planes(float (*s)[T3H][T3P], F plane_ptr, int h0, int w0, int H, int W) {
+#pragma unroll
+  for (int k = 0; k < (NP * 64 + 255) / 256; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    if (idx < NP * 64) {
+      const int pl = idx >> 6, row = (idx & 63) >> 1, c4 = (idx & 1) * 4;
+      const int h = h0 + row, w = w0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* base = plane_ptr(pl);
+      if (base != nullptr && h < H) {
+        const float* g = base + (int64_t)h * W + w;
+        if (VEC && w + 3 < W) {
+          v = ldg_stream4(g);
+        } else {
+          if (w < W) v.x = ldg_stream(g);
+          if (w + 1 < W) v.y = ldg_stream(g + 1);
+          if (w + 2 < W) v.z = ldg_stream(g + 2);
+          if (w + 3 < W) v.w = ldg_stream(g + 3);
+        }
+      }
+      s[pl][row][c4] = v.x; s[pl][row][c4 + 1] = v.y; s[pl][row][c4 + 2] = v.z; s[pl][row][c4 + 3] = v.w;
+    }
+  }
+}
+template <int NP, bool VEC, typename F>
+__device__ __forceinline__ void store_planes(const float (*s)[T3H][T3P], F plane_ptr, int h0, int w0, int H, int W) {
+#pragma unroll
+  for (int k = 0; k < (NP * 64 + 255) / 256; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    if (idx < NP * 64) {
+      const int pl = idx >> 6, row = (idx & 63) >> 1, c4 = (idx & 1) * 4;
+      const int h = h0 + row, w = w0 + c4;
+      float* base = plane_ptr(pl);
+      if (base != nullptr && h < H) {
+        float* g = base + (int64_t)h * W + w;
+        if (VEC && w + 3 < W) {
+          stg_stream4(g, make_float4(s[pl][row][c4], s[pl][row][c4 + 1], s[pl][row][c4 + 2], s[pl][row][c4 + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (w + i < W) g[i] = s[pl][row][c4 + i];
+        }
+      }
+    }
+  }
+}
+
+struct Warp3dParams {
+  int N, C, D, H, W, ref_mode;
+  float hs[6];  // (H-1)/2, (D-1)/2, (W-1)/2 and their fp32 reciprocals (computed in double like ATen)
+};
+
+
+static inline Warp3dParams make_warp3d_params(int N, int C, int D, int H, int W, int ref_mode) {
+  Warp3dParams P;
+  P.N = N; P.C = C; P.D = D; P.H = H; P.W = W; P.ref_mode = ref_mode;
+  const double h0 = (H - 1.0) / 2.0, h1 = (D - 1.0) / 2.0, h2 = (W - 1.0) / 2.0;  // Flow-3D/model/warplayer.py:24-26
+  P.hs[0] = (float)h0; P.hs[1] = (float)h1; P.hs[2] = (float)h2;
+  P.hs[3] = (float)(1.0 / h0); P.hs[4] = (float)(1.0 / h1); P.hs[5] = (float)(1.0 / h2);
+  return P;
+}
+
+}  // namespace ofsv

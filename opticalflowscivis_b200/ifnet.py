@@ -224,6 +224,7 @@ class IFNet(nn.Module):
         self.block_tea = IFBlock(nd, 6 + nf, c=64)      # teacher: training only (§8f), kept for state_dict parity
         self.set_precision(precision, engine)
         self.only_last = False
+        self.fuse_output_stage = True     # 3-D bf16: ofsv_block_finish_3d instead of head_upsample_add + warp_blend + pack
 
     def set_precision(self, precision: str, engine: str = "auto"):
         """precision 'bf16' (tensor-core operands, fp32 accumulate; flow/mask accumulators and heads in fp32) or
@@ -260,15 +261,28 @@ class IFNet(nn.Module):
         eng = self._engine()
         flow_list, mask_list, merged = [], [], []
         w0 = w1 = flow = mask = None
-        for i, blk in enumerate((self.block0, self.block1, self.block2)):
-            s = int(scale[i])
-            xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act)
-            in_sp = tuple(v // s for v in sp)
-            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng)
-            flow, mask = ops.head_upsample_add(head, flow, mask, nd, n, sp, s)
+        blocks = (self.block0, self.block1, self.block2)
+        scales = [int(v) for v in scale]
+        fused = nd == 3 and act == _C.BF16 and self.fuse_output_stage
+        xin = None
+        for i, blk in enumerate(blocks):
+            s = scales[i]
             last = i == 2
             want_out = last or not self.only_last
-            w0, w1, mg, ms = ops.warp_blend(img0, img1, flow, mask, want_warped=True, want_merged=want_out, want_mask=want_out)
+            if xin is None:
+                xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act)
+            in_sp = tuple(v // s for v in sp)
+            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng)
+            xin = None
+            if fused:
+                # one pass: resize + accumulate + warp x2 (+ blend) (+ the next block's resized concat)
+                s_next = 0 if last else (scales[i + 1] if scales[i + 1] in (1, 2) else 0)
+                flow, mask, mg, ms, xin = ops.block_finish_3d(head, flow, mask, img0, img1, s, s_next, want_out, want_out)
+                if not last and xin is None:          # next scale not fusable (4): fall back to the separate builder
+                    w0, w1, _, _ = ops.warp_blend(img0, img1, flow, None, want_merged=False, want_mask=False)
+            else:
+                flow, mask = ops.head_upsample_add(head, flow, mask, nd, n, sp, s)
+                w0, w1, mg, ms = ops.warp_blend(img0, img1, flow, mask, want_warped=True, want_merged=want_out, want_mask=want_out)
             flow_list.append(flow)
             mask_list.append(ms)
             merged.append(mg)

@@ -259,6 +259,26 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
     return flow, mask
 
 
+def block_finish_3d(head, flow_prev, mask_prev, img0, img1, scale_head, scale_next, want_merged, want_mask):
+    """Fused 3-D block output stage (ofsv_block_finish_3d).  Returns (flow, mask_logit, merged|None, mask_sig|None,
+    next_block_input|None) with next_block_input [N][D/sn][H/sn][W/sn][16] bf16 when scale_next in (1, 2)."""
+    n, _, d, h, w = img0.shape
+    dev = img0.device
+    flow = torch.empty((n, 6, d, h, w), device=dev, dtype=torch.float32)
+    mask = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32)
+    mg = torch.empty_like(mask) if want_merged else None
+    ms = torch.empty_like(mask) if want_mask else None
+    pk = None
+    if scale_next:
+        pk = torch.empty((n, d // scale_next, h // scale_next, w // scale_next, 16), device=dev, dtype=torch.bfloat16)
+    with torch.cuda.device(dev), _span("block_finish"):
+        _C.check(_C.lib().ofsv_block_finish_3d(_p(head), head.shape[-1], _p(flow_prev), _p(mask_prev), _p(img0), _p(img1),
+                                               _p(linspace_table(h, dev)), _p(linspace_table(d, dev)), _p(linspace_table(w, dev)),
+                                               _p(flow), _p(mask), _p(mg), _p(ms), _p(pk), n, d, h, w, scale_head, scale_next,
+                                               _FLAVOR["mode"], _stream()))
+    return flow, mask, mg, ms, pk
+
+
 def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
     fn = _C.lib().ofsv_conv_tc if engine == "tc" else _C.lib().ofsv_conv_simt
     with torch.cuda.device(x.device), _span("conv_" + engine):

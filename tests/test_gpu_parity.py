@@ -397,3 +397,51 @@ def test_model_surface():
         m3b.load_model("flownet.pkl", td)
         a, b = m3.flownet.state_dict(), m3b.flownet.state_dict()
         assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("sh,sn,has_prev", [(4, 2, False), (2, 1, True), (1, 0, True), (1, 1, True), (2, 2, True), (4, 0, False)])
+def test_block_finish_fused_equals_unfused(sh, sn, has_prev):
+    """ofsv_block_finish_3d == head_upsample_add -> warp_blend -> pack_block_input (the unfused, individually verified path)."""
+    from opticalflowscivis_b200 import _C, ops
+    g = torch.Generator().manual_seed(20 + sh * 3 + sn)
+    n, sp = 2, (16, 48, 40)          # H not a multiple of 32, W a multiple of 8: partial tiles in h
+    dev = _dev()
+    img0, img1 = torch.rand((n, 1) + sp, generator=g).to(dev), torch.rand((n, 1) + sp, generator=g).to(dev)
+    head = (torch.randn((n,) + tuple(s // sh for s in sp) + (8,), generator=g)).to(dev)
+    fprev = (torch.randn((n, 6) + sp, generator=g) * 2).to(dev) if has_prev else None
+    mprev = torch.randn((n, 1) + sp, generator=g).to(dev) if has_prev else None
+    flow, mask, mg, ms, pk = ops.block_finish_3d(head, fprev, mprev, img0, img1, sh, sn, True, True)
+    rflow, rmask = ops.head_upsample_add(head, fprev, mprev, 3, n, sp, sh)
+    w0, w1, rmg, rms = ops.warp_blend(img0, img1, rflow, rmask)
+    assert torch.equal(flow, rflow) and torch.equal(mask, rmask)
+    assert float((mg - rmg).abs().max()) <= 1e-6 and float((ms - rms).abs().max()) <= 1e-6
+    if sn:
+        rpk = ops.pack_block_input(img0, img1, w0, w1, rmask, rflow, sn, _C.BF16)
+        assert pk.shape == rpk.shape
+        assert float((pk.float() - rpk.float()).abs().max()) <= 1e-2 * float(rpk.float().abs().max())
+        assert float((pk.float() - rpk.float()).abs().mean()) <= 1e-5
+    else:
+        assert pk is None
+    # outputs that are not requested are not produced
+    f2, m2, a, b, _ = ops.block_finish_3d(head, fprev, mprev, img0, img1, sh, sn, False, False)
+    assert a is None and b is None and torch.equal(f2, flow) and torch.equal(m2, mask)
+
+
+def test_model3d_fused_equals_unfused():
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    m = Model(precision="bf16")
+    m.eval()
+    img0, _, img1 = _synthetic_pair(3, 1, (64, 64, 64))
+    a = m.inference(img0.to(_dev()), img1.to(_dev()))
+    m.flownet.fuse_output_stage = False
+    b = m.inference(img0.to(_dev()), img1.to(_dev()))
+    assert float((a[0] - b[0]).abs().max()) <= 1e-5
+    for i in range(3):
+        assert float((a[1][i] - b[1][i]).abs().max()) <= 1e-4
+    # scale lists other than [4,2,1] (SURVEY.md: `scale=[1,1,1]` is the reference's commented alternative)
+    m.flownet.fuse_output_stage = True
+    c = m.inference(img0.to(_dev()), img1.to(_dev()), scale_list=[2, 4, 1])
+    m.flownet.fuse_output_stage = False
+    d = m.inference(img0.to(_dev()), img1.to(_dev()), scale_list=[2, 4, 1])
+    assert float((c[0] - d[0]).abs().max()) <= 1e-5
