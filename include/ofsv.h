@@ -131,6 +131,12 @@ int ofsv_conv_simt(const ofsv_conv_desc* d, const void* x, const float* w, const
 int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
                  const void* residual, void* y, void* stream);
 
+/* Same contract as ofsv_conv_tc for the stride-1 layers (3^d convs, ConvTranspose phases: every tap offset in {-1,0,1}):
+ * each input halo plane is loaded into shared memory once per super-tile and every tap is a shifted UMMA descriptor;
+ * persistent CTAs, double-buffered TMEM accumulators.  Returns OFSV_ENOSUP (nothing launched) for other layers. */
+int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                   const void* residual, void* y, void* stream);
+
 /* IFBlock output stage: flow/mask deltas at block resolution -> full resolution (IFNet.py:115-116 / :118-119,
  * F.interpolate(.., scale) and flow*scale), then flow += flow_d ; mask += mask_d (IFNet.py:177-178 / :169-170).
  * head [N][D/s][H/s][W/s][Cs] channels-last fp32 (channels 0..2nd-1 flow, 2nd mask); flow_prev/mask_prev may be NULL

@@ -46,6 +46,7 @@ _SIGS = {
     "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 8 + [_P]),
     "ofsv_conv_simt": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "ofsv_conv_halo": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_block_finish_3d": (_I, [_P, _I] + [_P] * 12 + [_I] * 7 + [_P]),
 }

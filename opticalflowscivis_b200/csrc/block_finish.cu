@@ -56,7 +56,7 @@ struct FinishPtrs {
 };
 
 template <int SH, int SN, bool VEC, bool FMA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     block_finish_3d_kernel(const FinishPtrs q, const Warp3dParams P, const int Cs) {
   constexpr int TDZ = SN == 2 ? 2 : 1;
   __shared__ float s[9][T3H][T3P];                          // in: flow_prev 0..5, mask_prev, img0, img1 ; out: flow 0..5, mask, merged, sigmoid
@@ -78,16 +78,10 @@ __global__ void __launch_bounds__(256)
   for (int dz = 0; dz < TDZ; ++dz) {
     const int d = d0 + dz;
     const int64_t plane = (int64_t)n * V + (int64_t)d * HW;
-    if (dz > 0) __syncthreads();
-    load_planes<9, VEC>(s, [&](int k) -> const float* {
-      if (k < 6) return has_prev ? q.flow_prev + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW : nullptr;
-      if (k == 6) return has_prev ? q.mask_prev + plane : nullptr;
-      if (SN == 0) return nullptr;
-      return (k == 7 ? q.img0 : q.img1) + plane; }, h0, w0, H, W);
-    __syncthreads();
+    // ---- up-sampled head (flow delta x6, mask delta): independent of the shared tile, issued first so its latency
+    //      overlaps the plane loads below
+    float v[8];
     if (ok) {
-      // ---- up-sampled head (flow delta x6, mask delta)
-      float v[8];
       if (SH == 1) {
         ld8(hb + (((int64_t)d * H + h) * W + w) * Cs, v);
       } else {
@@ -113,6 +107,15 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int c = 0; c < 7; ++c) v[c] = __fadd_rn(__fmul_rn(az[0][c], lz.l0), __fmul_rn(az[1][c], lz.l1));
       }
+    }
+    if (dz > 0) __syncthreads();
+    load_planes<9, VEC>(s, [&](int k) -> const float* {
+      if (k < 6) return has_prev ? q.flow_prev + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW : nullptr;
+      if (k == 6) return has_prev ? q.mask_prev + plane : nullptr;
+      if (SN == 0) return nullptr;
+      return (k == 7 ? q.img0 : q.img1) + plane; }, h0, w0, H, W);
+    __syncthreads();
+    if (ok) {
       // ---- flow / mask accumulation (fp32)
       float f[6];
 #pragma unroll

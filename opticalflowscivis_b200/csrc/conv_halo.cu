@@ -1,0 +1,328 @@
+// tcgen05 implicit-GEMM convolution with shared-memory HALO REUSE for the stride-1 layers of an IFBlock
+// (3^d convs of convblock0..3, and the 2^d-phase form of ConvTranspose(4,2,1): every tap offset is in {-1,0,+1}^d).
+//
+// conv_tc.cu re-loads the 128 x KC activation tile from L2 for every filter tap (27x re-read, ~650 KB of L2->SM traffic
+// per 128 output positions): it is L2/latency bound at ~25 % tensor-pipe utilisation (profiles/r01_*).  Here each input
+// plane of a super-tile is loaded ONCE and every tap is just a shifted UMMA shared-memory descriptor:
+//
+//   super-tile  = 16(h) x 8(w) x TD(d) output positions of one sample (TD in {1,2,4} accumulators of 128 rows)
+//   halo plane  = the (16+2) x (8+2) x KC input box of one input depth slice, ONE 5-D TMA load (OOB zero-fill = conv
+//                 padding), SWIZZLE_128B/64B/32B, laid out [18][10] rows of KC*2 bytes
+//   tap (dz,dy,dx) for output slice j  ->  A descriptor start = plane[j+dz-dzmin] + ((dy+1)*10 + (dx+1)) * rowbytes,
+//                 8-row-group stride SBO = 10 rows.  tests/umma_probe.cu verified on B200 that UMMA K-major swizzled
+//                 descriptors address shared memory by absolute address bits (base_offset = 0), so neither the start nor
+//                 SBO has to be a multiple of the 1024 B swizzle atom.
+//   B tile      = W[pass][tap][chunk] ([Cout_w][KC], K-major) streamed once per super-tile through a small TMA ring and
+//                 shared by the TD accumulators.
+//   passes      = 1 (conv) or 2^d (ConvTranspose output parities): the planes stay resident across all passes.
+//   TMEM        = TD x Cout_w fp32 columns per pass, double-buffered when it fits so the epilogue of pass i overlaps
+//                 the MMAs of pass i+1; CTAs are persistent over super-tiles (grid = #SMs).
+// L2->SM traffic per 128 outputs drops from ~650 KB to ~(23 KB x (TD+2)/TD + 216 KB/TD).
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace ofsv {
+
+constexpr int HT_H = 16, HT_W = 8, HP_H = HT_H + 2, HP_W = HT_W + 2, HP_ROWS = HP_H * HP_W;  // 180 halo rows
+constexpr int H_MAX_PLANES = 8;
+constexpr int H_MAX_BSTAGES = 8;
+
+struct HaloParams {
+  int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
+  int out_stride, nphase, ntaps, nkc;
+  int td, np, dzmin;                 // output slices per super-tile, input planes per super-tile, min dz over taps
+  int tiles_w, tiles_h, tiles_d;     // super-tile grid per sample
+  int nb, plane_stride, b_stride;    // B ring depth, smem strides (bytes, multiples of 1024)
+  int nbuf, acc_stride;              // TMEM accumulator double buffering
+  int has_prelu, has_residual, out_f32;
+  int8_t tap_off[OFSV_MAX_TAPS][4];
+};
+
+template <int KC>
+__global__ void __launch_bounds__(192, 1)
+    conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
+                     const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
+                     void* __restrict__ y) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int ROWB = KC * 2;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nplanes = p.np * p.nkc;
+  uint8_t* sP = smem;
+  uint8_t* sB = smem + nplanes * p.plane_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nb * p.b_stride);
+  uint64_t* plane_full = bars;                            // [H_MAX_PLANES]
+  uint64_t* planes_empty = bars + H_MAX_PLANES;           // [1]
+  uint64_t* b_full = planes_empty + 1;                    // [H_MAX_BSTAGES]
+  uint64_t* b_empty = b_full + H_MAX_BSTAGES;             // [H_MAX_BSTAGES]
+  uint64_t* acc_full = b_empty + H_MAX_BSTAGES;           // [2]
+  uint64_t* acc_empty = acc_full + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
+  const int total = per_sample * p.N;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int i = 0; i < H_MAX_PLANES; ++i) mbar_init(&plane_full[i], 1);
+    mbar_init(planes_empty, 1);
+    for (int i = 0; i < H_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t bcount = 0;
+      int iter = 0;
+      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
+        int r = st;
+        const int tx = r % p.tiles_w; r /= p.tiles_w;
+        const int ty = r % p.tiles_h; r /= p.tiles_h;
+        const int tz = r % p.tiles_d;
+        const int n = r / p.tiles_d;
+        if (iter > 0) mbar_wait(planes_empty, (iter - 1) & 1);     // previous super-tile's MMAs have read the planes
+        for (int pl = 0; pl < p.np; ++pl)
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            uint64_t* bar = &plane_full[pl * p.nkc + kc];
+            mbar_expect_tx(bar, HP_ROWS * ROWB);
+            tma_load_5d(&tmA, bar, sP + (pl * p.nkc + kc) * p.plane_stride, kc * KC, tx * HT_W - 1, ty * HT_H - 1,
+                        tz * p.td + p.dzmin + pl, n);
+          }
+        for (int pass = 0; pass < p.nphase; ++pass)
+          for (int t = 0; t < p.ntaps; ++t)
+            for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
+              const int s = bcount % p.nb;
+              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[s], ((bcount / p.nb) - 1) & 1);
+              mbar_expect_tx(&b_full[s], p.Cout_w * ROWB);
+              tma_load_2d(&tmB, &b_full[s], sB + s * p.b_stride, 0, ((pass * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+      const uint64_t a_hi = (1ull << 16) | ((uint64_t)((HP_W * ROWB) >> 4) << 32) | (1ull << 46) | (layout << 61);   // SBO = 10 halo rows
+      uint32_t bcount = 0, acc_it = 0;
+      int iter = 0;
+      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
+        const int tz = (st / (p.tiles_w * p.tiles_h)) % p.tiles_d;
+        const int d0 = tz * p.td;
+        uint32_t waited = 0;
+        for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
+          const int buf = acc_it % p.nbuf;
+          if (acc_it >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_it / p.nbuf) - 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t acc0 = tmem_base + buf * p.acc_stride;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const int8_t* off = p.tap_off[pass * p.ntaps + t];
+            const uint32_t tap_byte = ((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB;
+            for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
+              const int s = bcount % p.nb;
+              mbar_wait(&b_full[s], (bcount / p.nb) & 1);
+              tcgen05_fence_after();
+              const uint32_t b0 = smem_u32(sB + s * p.b_stride);
+              for (int j = 0; j < p.td; ++j) {
+                if (d0 + j >= p.Do) break;
+                const int pl = (j + off[0] - p.dzmin) * p.nkc + kc;
+                if (!((waited >> pl) & 1u)) {
+                  mbar_wait(&plane_full[pl], iter & 1);
+                  tcgen05_fence_after();
+                  waited |= 1u << pl;
+                }
+                const uint32_t a0 = smem_u32(sP + pl * p.plane_stride) + tap_byte;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  const uint64_t da = (uint64_t)(((a0 + k * 32) & 0x3FFFF) >> 4) | a_hi;
+                  umma_bf16(acc0 + j * p.Cout_w, da, make_kmajor_desc<KC>(b0 + k * 32), idesc, (t | kc | k) ? 1u : 0u);
+                }
+              }
+              tcgen05_commit(&b_empty[s]);
+            }
+          }
+          tcgen05_commit(&acc_full[buf]);
+        }
+        tcgen05_commit(planes_empty);
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rx = row & 7, ry = row >> 3;
+    uint32_t acc_it = 0;
+    for (int st = blockIdx.x; st < total; st += gridDim.x) {
+      int r = st;
+      const int tx = r % p.tiles_w; r /= p.tiles_w;
+      const int ty = r % p.tiles_h; r /= p.tiles_h;
+      const int tz = r % p.tiles_d;
+      const int n = r / p.tiles_d;
+      const int ox = tx * HT_W + rx, oy = ty * HT_H + ry;
+      const bool valid_xy = ox < p.Wo && oy < p.Ho;
+      for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
+        const int buf = acc_it % p.nbuf;
+        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1);
+        tcgen05_fence_after();
+        const int pz = (pass >> 2) & 1, py = (pass >> 1) & 1, px = pass & 1;
+        for (int j = 0; j < p.td; ++j) {
+          const int oz = tz * p.td + j;
+          if (oz >= p.Do) break;
+          const int64_t yo = ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy +
+                              ox * p.out_stride + px) * p.Cout_s;
+          const uint32_t t0 = tmem_base + buf * p.acc_stride + j * p.Cout_w + ((uint32_t)(q * 32) << 16);
+          for (int c0 = 0; c0 < p.Cout_w; c0 += 16) {
+            float v[16];
+            tmem_ld16(t0 + c0, v);
+            if (valid_xy) epilogue_store16(v, c0, yo, p.Cout_s, p.has_prelu, p.has_residual, p.out_f32, bias, prelu, residual, y);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+template <int KC>
+static int launch_halo(const HaloParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+                       const float* prelu, const void* residual, void* y, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("ofsv_conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
+    attr_done = true;
+  }
+  conv_halo_kernel<KC><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
+  return check_launch("conv_halo_kernel");
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace ofsv
+
+using namespace ofsv;
+
+// Same contract as ofsv_conv_tc; returns OFSV_ENOSUP (nothing launched) for layers outside this kernel's domain
+// (strided input, tap offsets outside {-1,0,1}, Cout_w > 128, planes that do not fit shared memory).
+extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                              const void* residual, void* y, void* stream) {
+  if (int e = validate_conv_desc(d, "ofsv_conv_halo")) return e;
+  if (d->N == 0) return OFSV_OK;
+  OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_halo: null pointer");
+  OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_halo: has_prelu without prelu slopes");
+  OFSV_REQUIRE(!d->has_residual || residual, "ofsv_conv_halo: has_residual without residual");
+  OFSV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!residual || aligned16(residual)),
+               "ofsv_conv_halo: pointers must be 16-byte aligned");
+  if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: activations must be bf16"); return OFSV_ENOSUP; }
+  if (d->in_stride != 1) { set_error("ofsv_conv_halo: in_stride must be 1"); return OFSV_ENOSUP; }
+  if (d->Cout_w > 128) { set_error("ofsv_conv_halo: Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
+  int dzmin = 1, dzmax = -1;
+  for (int i = 0; i < d->nphase * d->ntaps; ++i) {
+    const int8_t* o = d->tap_off[i];
+    if (o[0] < -1 || o[0] > 1 || o[1] < -1 || o[1] > 1 || o[2] < -1 || o[2] > 1) {
+      set_error("ofsv_conv_halo: tap offset outside {-1,0,1}");
+      return OFSV_ENOSUP;
+    }
+    dzmin = o[0] < dzmin ? o[0] : dzmin;
+    dzmax = o[0] > dzmax ? o[0] : dzmax;
+  }
+  PFN_encodeTiled encode = get_tensor_map_encoder();
+  if (!encode) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
+
+  const int KC = d->Cin_s % 64 == 0 ? 64 : (d->Cin_s % 32 == 0 ? 32 : 16);
+  HaloParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = d->N; P.Do = d->Do; P.Ho = d->Ho; P.Wo = d->Wo; P.Dy = d->Dy; P.Hy = d->Hy; P.Wy = d->Wy;
+  P.Cout_s = d->Cout_s; P.Cout_w = d->Cout_w; P.out_stride = d->out_stride; P.nphase = d->nphase; P.ntaps = d->ntaps;
+  P.nkc = d->Cin_s / KC; P.dzmin = dzmin;
+  P.plane_stride = (HP_ROWS * KC * 2 + 1023) & ~1023;
+  P.b_stride = (d->Cout_w * KC * 2 + 1023) & ~1023;
+  P.tiles_w = (int)cdiv(d->Wo, HT_W); P.tiles_h = (int)cdiv(d->Ho, HT_H);
+  P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
+  memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
+  const int sms = num_sms();
+  const size_t smem_cap = 227 * 1024 - 2048;
+  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16;
+  // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
+  int td = 0;
+  const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits
+  const int forced = force ? atoi(force) : 0;
+  for (int cand = 4; cand >= 1; cand >>= 1) {
+    if (forced && cand != forced && cand > 1) continue;
+    if (cand > d->Do && cand > 1) continue;
+    const int np = cand + (dzmax - dzmin);
+    if (np * P.nkc > H_MAX_PLANES) continue;
+    if (cand * d->Cout_w > 512) continue;
+    if ((size_t)np * P.nkc * P.plane_stride + 3 * (size_t)P.b_stride + bar_bytes + 1024 > smem_cap) continue;
+    const int64_t nst = (int64_t)P.tiles_w * P.tiles_h * cdiv(d->Do, cand) * d->N;
+    if (cand > 1 && nst < 2 * sms && !forced) continue;
+    td = cand;
+    break;
+  }
+  if (td == 0) { set_error("ofsv_conv_halo: layer does not fit (Cin_s=%d Cout_w=%d)", d->Cin_s, d->Cout_w); return OFSV_ENOSUP; }
+  P.td = td; P.np = td + (dzmax - dzmin);
+  P.tiles_d = (int)cdiv(d->Do, td);
+  const size_t fixed = (size_t)P.np * P.nkc * P.plane_stride + bar_bytes + 1024;
+  int nb = (int)((smem_cap - fixed) / P.b_stride);
+  nb = nb > H_MAX_BSTAGES ? H_MAX_BSTAGES : nb;
+  P.nb = nb;
+  P.nbuf = (2 * td * d->Cout_w <= 512) ? 2 : 1;
+  P.acc_stride = 256;
+  const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
+  OFSV_REQUIRE(total < (1ll << 31), "ofsv_conv_halo: too many super-tiles");
+  const size_t smem = fixed + (size_t)nb * P.b_stride;
+
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t gdim[5] = {(cuuint64_t)d->Cin_s, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->Di, (cuuint64_t)d->N};
+    const cuuint64_t es = 2;
+    const cuuint64_t gstr[4] = {d->Cin_s * es, (cuuint64_t)d->Wi * d->Cin_s * es, (cuuint64_t)d->Hi * d->Wi * d->Cin_s * es,
+                                (cuuint64_t)d->Di * d->Hi * d->Wi * d->Cin_s * es};
+    const cuuint32_t box[5] = {(cuuint32_t)KC, HP_W, HP_H, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return OFSV_ECUDA; }
+  }
+  {
+    const cuuint64_t rows = (cuuint64_t)d->nphase * d->ntaps * P.nkc * d->Cout_w;
+    const cuuint64_t gdim[2] = {(cuuint64_t)KC, rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KC * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)d->Cout_w};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
+  }
+  const int grid = (int)(total < sms ? total : sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (KC == 64) return launch_halo<64>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+  if (KC == 32) return launch_halo<32>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+  return launch_halo<16>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+}

@@ -11,15 +11,11 @@
 //   D       = fp32 accumulator in tensor memory (128 lanes x N columns), read back with tcgen05.ld by 4 epilogue warps
 //             that fuse bias + PReLU + residual + dtype conversion and write channels-last output rows.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-#include <cuda.h>
-
 #include <mutex>
 
-#include "ofsv_common.cuh"
+#include "tc_common.cuh"
 
 namespace ofsv {
-
-int validate_conv_desc(const ofsv_conv_desc* d, const char* who);  // conv_simt.cu
 
 constexpr int TC_STAGES = 4;
 constexpr int TC_M = 128;
@@ -31,86 +27,6 @@ struct TcParams {
   int has_prelu, has_residual, out_f32;
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a pipeline bug must surface as a trap (cudaErrorLaunchFailure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
-  }
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46
-// | layout type @61 (SWIZZLE_128B = 2, 64B = 4, 32B = 6).  Rows are KC*2 bytes; 8-row groups are SBO = 8*row bytes apart.
-template <int KC>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
-  constexpr uint64_t sbo = (8 * KC * 2) >> 4;
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
 
 template <int KC>
 __global__ void __launch_bounds__(192, 1)
@@ -207,42 +123,7 @@ __global__ void __launch_bounds__(192, 1)
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       if (!valid) continue;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = v[j] + __ldg(bias + c0 + j);
-        if (p.has_prelu) a = a > 0.0f ? a : a * __ldg(prelu + c0 + j);
-        v[j] = a;
-      }
-      const int nstore = min(16, p.Cout_s - c0);   // 16, or 8 for the 8-channel head tensor
-      if (nstore <= 0) continue;
-      if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(y) + yo + c0;
-        if (p.has_residual) {
-          const float* r = reinterpret_cast<const float*>(residual) + yo + c0;
-          for (int j = 0; j < nstore; ++j) v[j] += __ldg(r + j);
-        }
-        for (int j = 0; j < nstore; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + yo + c0;
-        if (p.has_residual) {
-          const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(residual) + yo + c0;
-          for (int j = 0; j < nstore; j += 8) {
-            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(r + j));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { v[j + 2 * e] += __low2float(h[e]); v[j + 2 * e + 1] += __high2float(h[e]); }
-          }
-        }
-        for (int j = 0; j < nstore; j += 8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
+      epilogue_store16(v, c0, yo, p.Cout_s, p.has_prelu, p.has_residual, p.out_f32, bias, prelu, residual, y);
     }
   }
   tcgen05_fence_before();
@@ -253,11 +134,7 @@ __global__ void __launch_bounds__(192, 1)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled get_tensor_map_encoder() {
   static PFN_encodeTiled fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -299,7 +176,7 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
                "ofsv_conv_tc: pointers must be 16-byte aligned");
   if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_tc: activations must be bf16"); return OFSV_ENOSUP; }
   if (d->Cout_w > 128) { set_error("ofsv_conv_tc: Cout_w=%d > 128 not supported", d->Cout_w); return OFSV_ENOSUP; }
-  PFN_encodeTiled encode = get_encode();
+  PFN_encodeTiled encode = get_tensor_map_encoder();
   if (!encode) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled unavailable (driver too old?)"); return OFSV_ECUDA; }
 
   const int KC = d->Cin_s % 64 == 0 ? 64 : (d->Cin_s % 32 == 0 ? 32 : 16);

@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _C, ops
 
 
+USE_HALO = True    # stride-1 layers on the halo-reuse tcgen05 kernel (csrc/conv_halo.cu)
 TC_READY = True    # the tcgen05 engine (csrc/conv_tc.cu) passed parity on B200 (tests/tc_probe.py, profiles/)
 
 
@@ -197,8 +198,16 @@ class IFBlock(nn.Module):
             odt = torch.float32 if lay.out_f32 else tdt
             y = torch.empty([n] + ([osp[0]] if self.nd == 3 else []) + [osp[1], osp[2], lay.cout_s], device=x.device, dtype=odt)
             eng = engine(li, lay) if callable(engine) else engine
-            ops.conv(d, x, lay.w_tc if eng == "tc" else lay.w_simt, lay.bias, lay.prelu,
-                     skip if lay.residual else None, y, eng)
+            res = skip if lay.residual else None
+            if eng == "tc" and USE_HALO and lay.in_stride == 1 and not getattr(lay, "no_halo", False):
+                # stride-1 layers: halo-reuse kernel; layers it cannot hold in shared memory use the per-tap kernel
+                try:
+                    ops.conv(d, x, lay.w_tc, lay.bias, lay.prelu, res, y, "halo")
+                    eng = None
+                except NotImplementedError:
+                    lay.no_halo = True
+            if eng is not None:
+                ops.conv(d, x, lay.w_simt if eng == "simt" else lay.w_tc, lay.bias, lay.prelu, res, y, eng)
             if 2 <= li <= 9 and (li % 2 == 0):
                 skip = x                       # input of the residual pair
             x, sp = y, osp

@@ -280,7 +280,8 @@ def block_finish_3d(head, flow_prev, mask_prev, img0, img1, scale_head, scale_ne
 
 
 def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
-    fn = _C.lib().ofsv_conv_tc if engine == "tc" else _C.lib().ofsv_conv_simt
+    L = _C.lib()
+    fn = {"tc": L.ofsv_conv_tc, "halo": L.ofsv_conv_halo, "simt": L.ofsv_conv_simt}[engine]
     with torch.cuda.device(x.device), _span("conv_" + engine):
         _C.check(fn(ctypes.byref(desc), _p(x), _p(w), _p(bias), _p(prelu), _p(residual), _p(y), _stream()))
     return y

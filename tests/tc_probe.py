@@ -15,7 +15,11 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     bad = 0
-    only = sys.argv[1:] or None
+    engine = "tc"
+    args = sys.argv[1:]
+    if args and args[0] in ("tc", "halo"):
+        engine, args = args[0], args[1:]
+    only = args or None
     for nd in (3, 2):
         for c in (64, 32, 128):
             cin = 5 + 2 * nd
@@ -26,8 +30,8 @@ def main():
             blk_dev = ifnet.IFBlock(nd, cin, c).to(dev)
             blk_dev.load_state_dict(blk.state_dict())
             Lc, Ld = blk.layers(), blk_dev.layers()
-            sp = (1, 24, 40) if nd == 2 else (12, 8, 16)
-            for li in (2, 3, 1, 0, 10, 11):
+            sp = (1, 24, 40) if nd == 2 else ((12, 8, 16) if engine == "tc" else (10, 24, 20))
+            for li in ((2, 3, 10, 11) if engine == "halo" else (2, 3, 1, 0, 10, 11)):
                 tag = f"nd{nd}_c{c}_L{li}"
                 if only and tag not in only:
                     continue
@@ -40,7 +44,7 @@ def main():
                                dtype=torch.float32 if lc.out_f32 else torch.bfloat16)
                 try:
                     ops.conv(d, xin.to(dev).bfloat16(), ld.w_tc, ld.bias, ld.prelu,
-                             None if res is None else res.to(dev).bfloat16(), y, "tc")
+                             None if res is None else res.to(dev).bfloat16(), y, engine)
                     torch.cuda.synchronize()
                 except Exception as e:  # noqa: BLE001
                     print(f"{tag}: EXCEPTION {e}", flush=True)
