@@ -119,6 +119,10 @@ typedef struct ofsv_conv_desc {
   int8_t tap_off[OFSV_MAX_TAPS][4];   /* (z,y,x,unused) input offset of tap [ph*ntaps + t] */
   int32_t has_prelu, has_residual;
   int32_t in_dtype, out_dtype;        /* OFSV_F32 | OFSV_BF16 */
+  int32_t out_shuffle;                /* 0, or 8: depth-to-space heads (ofsv_conv_halo only) — nphase = 1, the Cout_w = 2^nd * 8
+                                       * columns are [output parity (z,y,x)][8 channels], row o is written to the 2^nd positions
+                                       * 2*o + parity of a [N][2Do][2Ho][2Wo][8] tensor (ConvTranspose(4,2,1) with all parities
+                                       * evaluated as ONE 3^nd-tap conv whose weights are zero where a parity does not use a tap) */
 } ofsv_conv_desc;
 
 /* SIMT (CUDA-core, fp32 accumulate) engine: exact-order validation path and small-channel layers.

@@ -26,6 +26,7 @@ class ConvDesc(ctypes.Structure):
         ("tap_off", (ctypes.c_int8 * 4) * MAX_TAPS),
         ("has_prelu", ctypes.c_int32), ("has_residual", ctypes.c_int32),
         ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
+        ("out_shuffle", ctypes.c_int32),
     ]
 
 

@@ -24,9 +24,15 @@
 
 namespace ofsv {
 
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 constexpr int HT_H = 16, HT_W = 8, HP_H = HT_H + 2, HP_W = HT_W + 2, HP_ROWS = HP_H * HP_W;  // 180 halo rows
 constexpr int H_MAX_PLANES = 8;
 constexpr int H_MAX_BSTAGES = 8;
+constexpr int H_EPI_WARPS = 8, H_THREADS = 64 + 32 * H_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct HaloParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
@@ -35,12 +41,12 @@ struct HaloParams {
   int tiles_w, tiles_h, tiles_d;     // super-tile grid per sample
   int nb, plane_stride, b_stride;    // B ring depth, smem strides (bytes, multiples of 1024)
   int nbuf, acc_stride;              // TMEM accumulator double buffering
-  int has_prelu, has_residual, out_f32;
+  int has_prelu, has_residual, out_f32, shuffle;
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
 template <int KC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(H_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
                      const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
                      void* __restrict__ y) {
@@ -58,6 +64,8 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* acc_full = b_empty + H_MAX_BSTAGES;           // [2]
   uint64_t* acc_empty = acc_full + 2;                     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sBias = reinterpret_cast<float*>(tmem_slot + 4);   // [128]
+  float* sPrelu = sBias + 128;                              // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(192, 1)
     for (int i = 0; i < H_MAX_PLANES; ++i) mbar_init(&plane_full[i], 1);
     mbar_init(planes_empty, 1);
     for (int i = 0; i < H_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -111,58 +119,69 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
-      const uint64_t a_hi = (1ull << 16) | ((uint64_t)((HP_W * ROWB) >> 4) << 32) | (1ull << 46) | (layout << 61);   // SBO = 10 halo rows
-      uint32_t bcount = 0, acc_it = 0;
-      int iter = 0;
-      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
-        const int tz = (st / (p.tiles_w * p.tiles_h)) % p.tiles_d;
-        const int d0 = tz * p.td;
-        uint32_t waited = 0;
-        for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
-          const int buf = acc_it % p.nbuf;
-          if (acc_it >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_it / p.nbuf) - 1) & 1);
-          tcgen05_fence_after();
-          const uint32_t acc0 = tmem_base + buf * p.acc_stride;
-          for (int t = 0; t < p.ntaps; ++t) {
-            const int8_t* off = p.tap_off[pass * p.ntaps + t];
-            const uint32_t tap_byte = ((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB;
-            for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
-              const int s = bcount % p.nb;
-              mbar_wait(&b_full[s], (bcount / p.nb) & 1);
-              tcgen05_fence_after();
-              const uint32_t b0 = smem_u32(sB + s * p.b_stride);
-              for (int j = 0; j < p.td; ++j) {
-                if (d0 + j >= p.Do) break;
-                const int pl = (j + off[0] - p.dzmin) * p.nkc + kc;
-                if (!((waited >> pl) & 1u)) {
-                  mbar_wait(&plane_full[pl], iter & 1);
-                  tcgen05_fence_after();
-                  waited |= 1u << pl;
-                }
-                const uint32_t a0 = smem_u32(sP + pl * p.plane_stride) + tap_byte;
+    // ================= MMA issuer: the whole warp walks the (warp-uniform) loops, one elected lane issues =================
+    const uint32_t leader = elect_one_sync();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = kmajor_desc_hi<KC>(HP_W * ROWB);      // SBO = 10 halo rows
+    const uint32_t b_hi = kmajor_desc_hi<KC>(8 * ROWB);
+    const uint32_t plane_lo0 = kmajor_desc_lo(smem_u32(sP)), plane_step = (uint32_t)p.plane_stride >> 4;
+    const uint32_t b_lo0 = kmajor_desc_lo(smem_u32(sB)), b_step = (uint32_t)p.b_stride >> 4;
+    uint32_t bcount = 0, acc_it = 0;
+    int iter = 0;
+    for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
+      const int tz = (st / (p.tiles_w * p.tiles_h)) % p.tiles_d;
+      const int nj = min(p.td, p.Do - tz * p.td);
+      uint32_t waited = 0;
+      for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
+        const int buf = acc_it % p.nbuf;
+        if (acc_it >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_it / p.nbuf) - 1) & 1);
+        const uint32_t acc0 = tmem_base + buf * p.acc_stride;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int8_t* off = p.tap_off[pass * p.ntaps + t];
+          const int dzr = off[0] - p.dzmin;
+          const uint32_t tap16 = (uint32_t)(((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB) >> 4;
+          for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
+            // planes this (tap, chunk) touches for the first time in this super-tile
+            for (int j = 0; j < nj; ++j) {
+              const int pl = (j + dzr) * p.nkc + kc;
+              if (!((waited >> pl) & 1u)) { mbar_wait(&plane_full[pl], iter & 1); waited |= 1u << pl; }
+            }
+            const int s = bcount % p.nb;
+            mbar_wait(&b_full[s], (bcount / p.nb) & 1);
+            tcgen05_fence_after();
+            if (leader) {
+              const uint32_t b_lo = b_lo0 + s * b_step;
+              const uint32_t a_lo = plane_lo0 + (uint32_t)(dzr * p.nkc + kc) * plane_step + tap16;
+              const uint32_t first = (t | kc) ? 1u : 0u;
+              for (int j = 0; j < nj; ++j) {
+                const uint32_t aj = a_lo + (uint32_t)(j * p.nkc) * plane_step, dj = acc0 + j * p.Cout_w;
+                umma_bf16_lohi(dj, aj, a_hi, b_lo, b_hi, idesc, first);
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  const uint64_t da = (uint64_t)(((a0 + k * 32) & 0x3FFFF) >> 4) | a_hi;
-                  umma_bf16(acc0 + j * p.Cout_w, da, make_kmajor_desc<KC>(b0 + k * 32), idesc, (t | kc | k) ? 1u : 0u);
-                }
+                for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dj, aj + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);
               }
               tcgen05_commit(&b_empty[s]);
             }
+            __syncwarp();
           }
-          tcgen05_commit(&acc_full[buf]);
         }
-        tcgen05_commit(planes_empty);
+        if (leader) tcgen05_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (leader) tcgen05_commit(planes_empty);
+      __syncwarp();
     }
   } else {
-    // ================= epilogue =================
-    const int q = warp & 3;
+    // ================= epilogue: 8 warps, two per TMEM lane quarter, splitting the (slice, 16-column chunk) list ==========
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int rx = row & 7, ry = row >> 3;
+    for (int i = threadIdx.x - 64; i < p.Cout_w; i += 32 * H_EPI_WARPS) {
+      sBias[i] = __ldg(bias + i);
+      sPrelu[i] = p.has_prelu ? __ldg(prelu + i) : 1.0f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * H_EPI_WARPS) : "memory");
+    const int nch = p.Cout_w >> 4;
+    const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
     uint32_t acc_it = 0;
     for (int st = blockIdx.x; st < total; st += gridDim.x) {
       int r = st;
@@ -172,21 +191,81 @@ __global__ void __launch_bounds__(192, 1)
       const int n = r / p.tiles_d;
       const int ox = tx * HT_W + rx, oy = ty * HT_H + ry;
       const bool valid_xy = ox < p.Wo && oy < p.Ho;
+      const int nitems = min(p.td, p.Do - tz * p.td) * nch;
       for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
         const int buf = acc_it % p.nbuf;
+        const int pz = (pass >> 2) & 1, py = (pass >> 1) & 1, px = pass & 1;
+        // row offset of output slice j (non-shuffled layers)
+        auto row_off = [&](int j) -> int64_t {
+          const int oz = tz * p.td + j;
+          return ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy + ox * p.out_stride + px) * p.Cout_s;
+        };
+        uint4 rnext[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (p.has_residual && valid_xy && half < nitems) {
+          const __nv_bfloat16* rp = resb + row_off(half / nch) + (half % nch) * 16;
+          rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        }
         mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1);
         tcgen05_fence_after();
-        const int pz = (pass >> 2) & 1, py = (pass >> 1) & 1, px = pass & 1;
-        for (int j = 0; j < p.td; ++j) {
-          const int oz = tz * p.td + j;
-          if (oz >= p.Do) break;
-          const int64_t yo = ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy +
-                              ox * p.out_stride + px) * p.Cout_s;
-          const uint32_t t0 = tmem_base + buf * p.acc_stride + j * p.Cout_w + ((uint32_t)(q * 32) << 16);
-          for (int c0 = 0; c0 < p.Cout_w; c0 += 16) {
-            float v[16];
-            tmem_ld16(t0 + c0, v);
-            if (valid_xy) epilogue_store16(v, c0, yo, p.Cout_s, p.has_prelu, p.has_residual, p.out_f32, bias, prelu, residual, y);
+        for (int it = half; it < nitems; it += 2) {
+          const int j = it / nch, c0 = (it - j * nch) << 4;
+          const uint4 rcur0 = rnext[0], rcur1 = rnext[1];
+          if (p.has_residual && valid_xy && it + 2 < nitems) {       // prefetch the next chunk's residual row
+            const int jn = (it + 2) / nch;
+            const __nv_bfloat16* rp = resb + row_off(jn) + ((it + 2) - jn * nch) * 16;
+            rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+          }
+          float v[16];
+          tmem_ld16(tmem_base + buf * p.acc_stride + j * p.Cout_w + c0 + ((uint32_t)(q * 32) << 16), v);
+          if (!valid_xy) continue;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float a = v[e] + sBias[c0 + e];
+            v[e] = a > 0.0f ? a : a * sPrelu[c0 + e];
+          }
+          if (p.has_residual) {
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&rcur0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&rcur1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
+              v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+            }
+          }
+          if (p.shuffle) {
+            // depth-to-space heads: columns = [output parity (z,y,x)][8 channels]; this chunk holds parities c0/8 and c0/8+1
+            const int oz = tz * p.td + j;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ph = (c0 >> 3) + e;
+              const int64_t yo = ((((int64_t)n * p.Dy + oz * 2 + ((ph >> 2) & 1)) * p.Hy + oy * 2 + ((ph >> 1) & 1)) * p.Wy +
+                                  ox * 2 + (ph & 1)) * p.Cout_s;
+              if (p.out_f32) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + yo);
+                o[0] = make_float4(v[8 * e], v[8 * e + 1], v[8 * e + 2], v[8 * e + 3]);
+                o[1] = make_float4(v[8 * e + 4], v[8 * e + 5], v[8 * e + 6], v[8 * e + 7]);
+              } else {
+                uint4 w;
+                w.x = pack2_bf16(v[8 * e], v[8 * e + 1]); w.y = pack2_bf16(v[8 * e + 2], v[8 * e + 3]);
+                w.z = pack2_bf16(v[8 * e + 4], v[8 * e + 5]); w.w = pack2_bf16(v[8 * e + 6], v[8 * e + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + yo) = w;
+              }
+            }
+          } else {
+            const int64_t yo = row_off(j) + c0;
+            const int nstore = min(16, p.Cout_s - c0);
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(y) + yo;
+              for (int e = 0; e < nstore; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + yo;
+              for (int e = 0; e < nstore; e += 8) {
+                uint4 w;
+                w.x = pack2_bf16(v[e], v[e + 1]); w.y = pack2_bf16(v[e + 2], v[e + 3]);
+                w.z = pack2_bf16(v[e + 4], v[e + 5]); w.w = pack2_bf16(v[e + 6], v[e + 7]);
+                *reinterpret_cast<uint4*>(o + e) = w;
+              }
+            }
           }
         }
         tcgen05_fence_before();
@@ -209,7 +288,7 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& tmA, const CUtens
     if (e != cudaSuccess) { set_error("ofsv_conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
     attr_done = true;
   }
-  conv_halo_kernel<KC><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
+  conv_halo_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
   return check_launch("conv_halo_kernel");
 }
 
@@ -241,6 +320,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: activations must be bf16"); return OFSV_ENOSUP; }
   if (d->in_stride != 1) { set_error("ofsv_conv_halo: in_stride must be 1"); return OFSV_ENOSUP; }
   if (d->Cout_w > 128) { set_error("ofsv_conv_halo: Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
+  if (d->has_residual && d->out_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: residual needs a bf16 output"); return OFSV_ENOSUP; }
+  if (d->out_shuffle && (d->out_shuffle != 8 || d->nphase != 1 || d->Cout_w != 8 * (1 << d->nd) || d->Cout_s != 8 || d->has_residual)) {
+    set_error("ofsv_conv_halo: bad depth-to-space configuration");
+    return OFSV_EINVAL;
+  }
   int dzmin = 1, dzmax = -1;
   for (int i = 0; i < d->nphase * d->ntaps; ++i) {
     const int8_t* o = d->tap_off[i];
@@ -264,10 +348,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   P.b_stride = (d->Cout_w * KC * 2 + 1023) & ~1023;
   P.tiles_w = (int)cdiv(d->Wo, HT_W); P.tiles_h = (int)cdiv(d->Ho, HT_H);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
+  P.shuffle = d->out_shuffle;
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
   const int sms = num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
-  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16;
+  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4;
   // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
   int td = 0;
   const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits

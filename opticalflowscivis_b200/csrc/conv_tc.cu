@@ -17,14 +17,14 @@
 
 namespace ofsv {
 
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 16;   // pipeline depth is chosen per layer: small K chunks need more loads in flight
 constexpr int TC_M = 128;
 
 struct TcParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
   int in_stride, out_stride, ntaps, nkc;
   int tw, th, td, tiles_w, tiles_h, tiles_d;
-  int has_prelu, has_residual, out_f32;
+  int has_prelu, has_residual, out_f32, stages;
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
@@ -38,12 +38,13 @@ __global__ void __launch_bounds__(192, 1)
   const int b_bytes = (p.Cout_w * KC * 2 + 1023) & ~1023;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_bytes);
+  const int S = p.stages;
+  uint8_t* sB = smem + S * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * b_bytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + TC_STAGES;
-  uint64_t* accum_full = bars + 2 * TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+  uint64_t* empty = bars + TC_MAX_STAGES;
+  uint64_t* accum_full = bars + 2 * TC_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ph = blockIdx.z;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(192, 1)
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(accum_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(192, 1)
     if (lane == 0) {
       const uint32_t tx_bytes = A_BYTES + p.Cout_w * KC * 2;
       for (int it = 0; it < kiters; ++it) {
-        const int s = it % TC_STAGES;
-        if (it >= TC_STAGES) mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+        const int s = it % S;
+        if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
         const int t = it / p.nkc, kc = it - t * p.nkc;
         const int8_t* off = p.tap_off[ph * p.ntaps + t];
         mbar_expect_tx(&full[s], tx_bytes);
@@ -90,24 +91,27 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one lane) =================
-    if (lane == 0) {
-      // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % TC_STAGES;
-        mbar_wait(&full[s], (it / TC_STAGES) & 1);
-        tcgen05_fence_after();
-        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * b_bytes);
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    const uint32_t leader = elect_one_sync();
+    // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t d_hi = kmajor_desc_hi<KC>(8 * KC * 2);
+    const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(sA)), b_lo0 = kmajor_desc_lo(smem_u32(sB));
+    for (int it = 0; it < kiters; ++it) {
+      const int s = it % S;
+      mbar_wait(&full[s], (it / S) & 1);
+      tcgen05_fence_after();
+      if (leader) {
+        const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4), b_lo = b_lo0 + s * (b_bytes >> 4);
+        umma_bf16_lohi(tmem_base, a_lo, d_hi, b_lo, d_hi, idesc, it > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          umma_bf16(tmem_base, make_kmajor_desc<KC>(a0 + k * 32), make_kmajor_desc<KC>(b0 + k * 32), idesc,
-                    (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, 1u);
         tcgen05_commit(&empty[s]);          // frees the smem slot when these MMAs have read it
       }
-      tcgen05_commit(accum_full);           // accumulator complete
+      __syncwarp();
     }
+    if (leader) tcgen05_commit(accum_full);   // accumulator complete
+    __syncwarp();
   } else {
     // ================= epilogue: TMEM -> registers -> global =================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -150,7 +154,7 @@ template <int KC>
 static int launch_tc(const TcParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* prelu,
                      const void* residual, void* y, dim3 grid, cudaStream_t st) {
   const int b_bytes = (P.Cout_w * KC * 2 + 1023) & ~1023;
-  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_M * KC * 2 + b_bytes) + (2 * TC_STAGES + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)P.stages * (TC_M * KC * 2 + b_bytes) + (2 * TC_MAX_STAGES + 1) * 8 + 16;
   static bool attr_done = false;   // per-template-instance
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -168,6 +172,7 @@ using namespace ofsv;
 extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
                             const void* residual, void* y, void* stream) {
   if (int e = validate_conv_desc(d, "ofsv_conv_tc")) return e;
+  if (d->out_shuffle) { set_error("ofsv_conv_tc: depth-to-space heads are only implemented by ofsv_conv_halo"); return OFSV_ENOSUP; }
   if (d->N == 0) return OFSV_OK;
   OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_tc: null pointer");
   OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_tc: has_prelu without prelu slopes");
@@ -188,6 +193,10 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
   P.tiles_w = (int)cdiv(d->Wo, P.tw); P.tiles_h = (int)cdiv(d->Ho, P.th); P.tiles_d = (int)cdiv(d->Do, P.td);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
+  {  // 4 stages: small-K layers hide TMA latency through CTA occupancy (up to ~10 CTAs/SM), measured faster than deep rings
+    const int kiters = d->ntaps * P.nkc;
+    P.stages = kiters < 4 ? kiters : 4;
+  }
   const int64_t ntiles = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
   OFSV_REQUIRE(ntiles < (1ll << 31), "ofsv_conv_tc: too many tiles");
 

@@ -65,6 +65,42 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two shared-memory descriptors passed as (lo, hi) 32-bit halves: advancing along K or to another tap is
+// then ONE 32-bit add on `lo` (start address >> 4) — the single issuing thread is instruction-latency bound otherwise.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+// upper 32 bits of a K-major descriptor: SBO>>4 @[0,14), version 1 @14, layout type @29
+template <int KC>
+__device__ __forceinline__ uint32_t kmajor_desc_hi(uint32_t sbo_bytes) {
+  constexpr uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+  return (sbo_bytes >> 4) | (1u << 14) | (layout << 29);
+}
+// lower 32 bits: start address >> 4 @[0,14), LBO (unused for swizzled K-major, 1 like CUTLASS) @16
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(

@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _C, ops
 
 
+USE_SHUFFLE_HEADS = True   # final ConvTranspose heads as one 3^d-tap depth-to-space conv (N = 2^d * 8) on the halo engine
 USE_HALO = True    # stride-1 layers on the halo-reuse tcgen05 kernel (csrc/conv_halo.cu)
 TC_READY = True    # the tcgen05 engine (csrc/conv_tc.cu) passed parity on B200 (tests/tc_probe.py, profiles/)
 
@@ -66,7 +67,8 @@ def _rup(x, m):
 class _Layer:
     """One conv layer in tap form + its packed device weights."""
 
-    def __init__(self, nd, in_stride, out_stride, nphase, taps, w_tap, bias, prelu, cout_s, out_f32=False, residual=False):
+    def __init__(self, nd, in_stride, out_stride, nphase, taps, w_tap, bias, prelu, cout_s, out_f32=False, residual=False,
+                 shuffle=0):
         # taps: list (len nphase*ntaps) of (z,y,x) offsets; w_tap: fp32 [nphase*ntaps][Cin][Cout]
         self.nd, self.in_stride, self.out_stride, self.nphase = nd, in_stride, out_stride, nphase
         self.ntaps = len(taps) // nphase
@@ -87,14 +89,17 @@ class _Layer:
         if prelu is not None:
             self.prelu = torch.ones(self.cout_w, device=dev, dtype=torch.float32)
             self.prelu[:cout] = prelu
-        self.out_f32, self.residual = out_f32, residual
+        self.out_f32, self.residual, self.shuffle = out_f32, residual, shuffle
 
     def desc(self, n, in_sp, act_dtype):
         """in_sp = (D,H,W) of the input; returns (ConvDesc, out_sp)."""
         d = _C.ConvDesc()
         d.nd = self.nd
         d.N, (d.Di, d.Hi, d.Wi), d.Cin_s = n, in_sp, self.cin_s
-        if self.nphase == 1:
+        if self.shuffle:
+            vsp = in_sp
+            osp = tuple(s * 2 if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
+        elif self.nphase == 1:
             osp = tuple(max(1, s // self.in_stride) if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
             vsp = osp
         else:
@@ -110,6 +115,7 @@ class _Layer:
         d.has_prelu, d.has_residual = int(self.prelu is not None), int(self.residual)
         d.in_dtype = act_dtype
         d.out_dtype = _C.F32 if self.out_f32 else act_dtype
+        d.out_shuffle = self.shuffle
         return d, osp
 
 
@@ -141,6 +147,28 @@ def _pack_convT(nd, w, bias, prelu, cout_s, out_f32):
             taps.append(((0,) if nd == 2 else ()) + off)
             w_tap.append(w[(slice(None), slice(None)) + kk])         # [Cin][Cout]
     return _Layer(nd, 1, 2, 2 ** nd, taps, torch.stack(w_tap), bias, prelu, cout_s, out_f32=out_f32)
+
+
+def _pack_heads_shuffle(nd, w, bias):
+    """Depth-to-space form of the final ConvTranspose(4,2,1) heads (ofsv_conv_desc.out_shuffle = 8): ONE 3^nd-tap conv with
+    2^nd * 8 output columns [output parity][8 channels]; a (parity, offset) pair that the transposed conv does not use
+    gets zero weights.  w [Cin][Cout<=8][4..], bias [Cout]."""
+    cin, cout = w.shape[0], w.shape[1]
+    kidx = {(0, 0): 1, (0, -1): 3, (1, 0): 2, (1, 1): 0}            # (parity, input offset) -> kernel index, per axis
+    taps, w_tap = [], []
+    pars = list(itertools.product((0, 1), repeat=nd))
+    for off in itertools.product((-1, 0, 1), repeat=nd):
+        wt = torch.zeros(cin, 8 * len(pars), device=w.device)
+        for pi, par in enumerate(pars):
+            ks = [kidx.get((par[a], off[a])) for a in range(nd)]
+            if all(k is not None for k in ks):
+                wt[:, pi * 8: pi * 8 + cout] = w[(slice(None), slice(None)) + tuple(ks)]
+        taps.append(((0,) if nd == 2 else ()) + off)
+        w_tap.append(wt)
+    b = torch.zeros(8 * len(pars), device=w.device)
+    for pi in range(len(pars)):
+        b[pi * 8: pi * 8 + cout] = bias
+    return _Layer(nd, 1, 2, 1, taps, torch.stack(w_tap), b, None, 8, out_f32=True, shuffle=8)
 
 
 class IFBlock(nn.Module):
@@ -184,7 +212,9 @@ class IFBlock(nn.Module):
             wh = torch.zeros((c, nf + 1) + (4,) * nd, device=w12.device)
             wh[: c // 2, :nf] = w12
             wh[c // 2:, nf:] = w22
-            L.append(_pack_convT(nd, wh, torch.cat([self.conv1[2].bias, self.conv2[2].bias]).detach().float(), None, 8, True))
+            bh = torch.cat([self.conv1[2].bias, self.conv2[2].bias]).detach().float()
+            L.append(_pack_convT(nd, wh, bh, None, 8, True))
+            self._heads_shuffle = _pack_heads_shuffle(nd, wh, bh)     # same layer, depth-to-space form (halo engine)
             self._packed, self._packed_key = L, key
         return self._packed
 
@@ -194,6 +224,9 @@ class IFBlock(nn.Module):
         tdt = torch.float32 if act_dtype == _C.F32 else torch.bfloat16
         x, sp, skip = xin, in_sp, None
         for li, lay in enumerate(L):
+            eng0 = engine(li, lay) if callable(engine) else engine
+            if li == 11 and eng0 == "tc" and USE_HALO and USE_SHUFFLE_HEADS:
+                lay = self._heads_shuffle
             d, osp = lay.desc(n, sp, act_dtype)
             odt = torch.float32 if lay.out_f32 else tdt
             y = torch.empty([n] + ([osp[0]] if self.nd == 3 else []) + [osp[1], osp[2], lay.cout_s], device=x.device, dtype=odt)

@@ -25,6 +25,12 @@ def run_layer(lay, x, residual=None):
         if lay.prelu is not None:
             a = lay.prelu.cpu().view(1, 1, 1, 1, -1)
             acc = torch.where(acc > 0, acc, acc * a)
+        if getattr(lay, "shuffle", 0):
+            npar = lay.cout_w // lay.shuffle
+            for q in range(npar):           # columns [output parity][8 channels] -> depth-to-space
+                qz, qy, qx = ((q >> 2) & 1, (q >> 1) & 1, q & 1) if lay.nd == 3 else (0, (q >> 1) & 1, q & 1)
+                y[:, qz::(2 if lay.nd == 3 else 1), qy::2, qx::2] = acc[..., q * 8:(q + 1) * 8]
+            continue
         pz, py, px = (ph >> 2) & 1, (ph >> 1) & 1, ph & 1
         y[:, pz::lay.out_stride, py::lay.out_stride, px::lay.out_stride] = acc[..., : lay.cout_s]
     if residual is not None:

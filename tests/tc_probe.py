@@ -36,6 +36,8 @@ def main():
                 if only and tag not in only:
                     continue
                 lc, ld = Lc[li], Ld[li]
+                if engine == "halo" and li == 11:
+                    lc, ld = blk._heads_shuffle, blk_dev._heads_shuffle
                 xin = (torch.randn((2,) + sp + (lc.cin_s,)) * 0.5).bfloat16().float()
                 d, osp = lc.desc(2, sp, _C.BF16)
                 res = (torch.randn((2,) + osp + (lc.cout_s,)) * 0.5).bfloat16().float() if lc.residual else None

@@ -54,6 +54,18 @@ def test_conv_transpose_phase_form_matches_torch(nd):
 
 
 @pytest.mark.parametrize("nd", [2, 3])
+def test_depth_to_space_heads_equal_phase_form(nd):
+    """The one-conv depth-to-space packing of the final ConvTranspose heads equals the 2^nd-phase packing."""
+    torch.manual_seed(3)
+    blk = ifnet.IFBlock(nd, 5 + 2 * nd, 32)
+    L = blk.layers()
+    x = torch.randn((2,) + ((1, 6, 7) if nd == 2 else (4, 6, 7)) + (32,))
+    a = run_layer(L[11], x)
+    b = run_layer(blk._heads_shuffle, x)
+    assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
 def test_block_layers_match_oracle_block(nd):
     """The 12 packed layers (merged conv1.0‖conv2.0, block-diagonal heads, residual pairs) evaluated in tap form on CPU
     reproduce the oracle IFBlock's flow/mask head outputs."""
@@ -104,7 +116,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/ofsv.h but not exported by libofsv.so"
     assert declared == set(_C.EXPORTS), declared ^ set(_C.EXPORTS)
     assert L.ofsv_version().startswith(b"ofsv")
-    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 4
+    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 5
 
 
 def test_validation_errors_launch_nothing():
