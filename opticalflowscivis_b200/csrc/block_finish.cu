@@ -49,6 +49,34 @@ __device__ __forceinline__ void store_pack_row(__nv_bfloat16* dst, const float* 
   reinterpret_cast<uint4*>(dst)[1] = hi;
 }
 
+
+// Lean tile I/O for the vectorised path: thread t owns tile row (t & 63) >> 1, columns ((t & 1) * 4 .. +3) of planes
+// g, g+4, g+8 with g = t >> 6 — the row/column arithmetic is done once per CTA, each plane costs one 16 B access.
+struct TileIO {
+  int row, c4, goff;   // tile-local row / first column, element offset of (h0+row, w0+c4) inside a (H, W) plane
+  bool in;             // inside the volume (W % 4 == 0 on this path)
+};
+__device__ __forceinline__ TileIO make_tile_io(int h0, int w0, int H, int W) {
+  TileIO t;
+  const int r = threadIdx.x & 63;
+  t.row = r >> 1; t.c4 = (r & 1) * 4;
+  t.in = (h0 + t.row) < H && (w0 + t.c4) < W;
+  t.goff = (h0 + t.row) * W + w0 + t.c4;
+  return t;
+}
+__device__ __forceinline__ void tile_load(float (*s)[T3P], const float* __restrict__ plane, const TileIO& t) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (plane != nullptr && t.in) v = ldg_stream4(plane + t.goff);
+  float* d = &s[t.row][t.c4];
+  d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+}
+__device__ __forceinline__ void tile_store(const float (*s)[T3P], float* __restrict__ plane, const TileIO& t) {
+  if (plane != nullptr && t.in) {
+    const float* d = &s[t.row][t.c4];
+    stg_stream4(plane + t.goff, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
 struct FinishPtrs {
   const float* head; const float* flow_prev; const float* mask_prev; const float* img0; const float* img1;
   const float* lin_h; const float* lin_d; const float* lin_w;
@@ -73,6 +101,7 @@ __global__ void __launch_bounds__(256, 4)
   const float* hb = q.head + (int64_t)n * Dh * Hh * Wh * Cs;
   const bool has_prev = q.flow_prev != nullptr;
   const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+  const TileIO tio = make_tile_io(h0, w0, H, W);
 
 #pragma unroll
   for (int dz = 0; dz < TDZ; ++dz) {
@@ -109,11 +138,22 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
     if (dz > 0) __syncthreads();
-    load_planes<9, VEC>(s, [&](int k) -> const float* {
-      if (k < 6) return has_prev ? q.flow_prev + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW : nullptr;
-      if (k == 6) return has_prev ? q.mask_prev + plane : nullptr;
-      if (SN == 0) return nullptr;
-      return (k == 7 ? q.img0 : q.img1) + plane; }, h0, w0, H, W);
+    if (VEC) {
+      const int g = threadIdx.x >> 6;
+      const float* fp = has_prev ? q.flow_prev + (int64_t)n * 6 * V + (int64_t)d * HW : nullptr;
+      // planes g, g+4, g+8 of {flow_prev 0..5, mask_prev, img0, img1}
+      tile_load(s[g], fp ? fp + (int64_t)g * V : nullptr, tio);
+      const int k1 = g + 4;
+      tile_load(s[k1], k1 < 6 ? (fp ? fp + (int64_t)k1 * V : nullptr)
+                              : (k1 == 6 ? (has_prev ? q.mask_prev + plane : nullptr) : (SN == 0 ? nullptr : q.img0 + plane)), tio);
+      if (g == 0) tile_load(s[8], SN == 0 ? nullptr : q.img1 + plane, tio);
+    } else {
+      load_planes<9, false>(s, [&](int k) -> const float* {
+        if (k < 6) return has_prev ? q.flow_prev + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW : nullptr;
+        if (k == 6) return has_prev ? q.mask_prev + plane : nullptr;
+        if (SN == 0) return nullptr;
+        return (k == 7 ? q.img0 : q.img1) + plane; }, h0, w0, H, W);
+    }
     __syncthreads();
     if (ok) {
       // ---- flow / mask accumulation (fp32)
@@ -149,10 +189,19 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
     __syncthreads();
-    store_planes<9, VEC>(s, [&](int k) -> float* {
-      if (k < 6) return q.flow_out + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW;
-      float* b = k == 6 ? q.mask_out : (k == 7 ? q.merged : q.mask_sig);
-      return b ? b + plane : nullptr; }, h0, w0, H, W);
+    if (VEC) {
+      const int g = threadIdx.x >> 6;
+      float* fo = q.flow_out + (int64_t)n * 6 * V + (int64_t)d * HW;
+      tile_store(s[g], fo + (int64_t)g * V, tio);
+      const int k1 = g + 4;
+      tile_store(s[k1], k1 < 6 ? fo + (int64_t)k1 * V : (k1 == 6 ? q.mask_out + plane : (q.merged ? q.merged + plane : nullptr)), tio);
+      if (g == 0) tile_store(s[8], q.mask_sig ? q.mask_sig + plane : nullptr, tio);
+    } else {
+      store_planes<9, false>(s, [&](int k) -> float* {
+        if (k < 6) return q.flow_out + (int64_t)n * 6 * V + (int64_t)k * V + (int64_t)d * HW;
+        float* b = k == 6 ? q.mask_out : (k == 7 ? q.merged : q.mask_sig);
+        return b ? b + plane : nullptr; }, h0, w0, H, W);
+    }
   }
   if (SN == 2) {
     // 2x2x2 mean == F.interpolate(., 0.5): nested W, H, D like ATen; flow channels additionally * 0.5

@@ -18,6 +18,7 @@
 //   TMEM        = TD x Cout_w fp32 columns per pass, double-buffered when it fits so the epilogue of pass i overlaps
 //                 the MMAs of pass i+1; CTAs are persistent over super-tiles (grid = #SMs).
 // L2->SM traffic per 128 outputs drops from ~650 KB to ~(23 KB x (TD+2)/TD + 216 KB/TD).
+#include <cstdio>
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -32,7 +33,8 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 constexpr int HT_H = 16, HT_W = 8, HP_H = HT_H + 2, HP_W = HT_W + 2, HP_ROWS = HP_H * HP_W;  // 180 halo rows
 constexpr int H_MAX_PLANES = 8;
 constexpr int H_MAX_BSTAGES = 8;
-constexpr int H_EPI_WARPS = 8, H_THREADS = 64 + 32 * H_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int H_MMA_WARPS = 4, H_EPI_WARPS = 8, H_EPI_W0 = 1 + H_MMA_WARPS;
+constexpr int H_THREADS = 32 * (H_EPI_W0 + H_EPI_WARPS);   // warp 0 TMA, warps 1..2 MMA issuers (output slices split by parity), warps 3..10 epilogue
 
 struct HaloParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
@@ -41,7 +43,7 @@ struct HaloParams {
   int tiles_w, tiles_h, tiles_d;     // super-tile grid per sample
   int nb, plane_stride, b_stride;    // B ring depth, smem strides (bytes, multiples of 1024)
   int nbuf, acc_stride;              // TMEM accumulator double buffering
-  int has_prelu, has_residual, out_f32, shuffle;
+  int has_prelu, has_residual, out_f32, shuffle, dbg_flags;
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
@@ -49,9 +51,10 @@ template <int KC>
 __global__ void __launch_bounds__(H_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
                      const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
-                     void* __restrict__ y) {
+                     void* __restrict__ y, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROWB = KC * 2;
+  const bool trace = dbg != nullptr && blockIdx.x == 0;   // OFSV_HALO_TRACE: per-super-tile clock64 timeline of CTA 0
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nplanes = p.np * p.nkc;
   uint8_t* sP = smem;
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sBias = reinterpret_cast<float*>(tmem_slot + 4);   // [128]
   float* sPrelu = sBias + 128;                              // [128]
+  uint32_t* sTap = reinterpret_cast<uint32_t*>(sPrelu + 128); // [OFSV_MAX_TAPS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
@@ -75,9 +79,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < H_MAX_PLANES; ++i) mbar_init(&plane_full[i], 1);
-    mbar_init(planes_empty, 1);
-    for (int i = 0; i < H_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], H_EPI_WARPS); }
+    mbar_init(planes_empty, H_MMA_WARPS);
+    for (int i = 0; i < H_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], H_MMA_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], H_MMA_WARPS); mbar_init(&acc_empty[i], H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t bcount = 0;
+      uint32_t bcount = 0, bs = 0, bphase = 0;
       int iter = 0;
       for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
         int r = st;
@@ -100,7 +104,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         const int ty = r % p.tiles_h; r /= p.tiles_h;
         const int tz = r % p.tiles_d;
         const int n = r / p.tiles_d;
-        if (iter > 0) mbar_wait(planes_empty, (iter - 1) & 1);     // previous super-tile's MMAs have read the planes
+        if (trace && iter < 16) dbg[iter * 16 + 0] = clock64();
+        if (iter > 0) mbar_wait(planes_empty, (iter - 1) & 1, 200);     // previous super-tile's MMAs have read the planes
+        if (trace && iter < 16) dbg[iter * 16 + 1] = clock64();
         for (int pl = 0; pl < p.np; ++pl)
           for (int kc = 0; kc < p.nkc; ++kc) {
             uint64_t* bar = &plane_full[pl * p.nkc + kc];
@@ -111,71 +117,92 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         for (int pass = 0; pass < p.nphase; ++pass)
           for (int t = 0; t < p.ntaps; ++t)
             for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
-              const int s = bcount % p.nb;
-              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[s], ((bcount / p.nb) - 1) & 1);
-              mbar_expect_tx(&b_full[s], p.Cout_w * ROWB);
-              tma_load_2d(&tmB, &b_full[s], sB + s * p.b_stride, 0, ((pass * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
+              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[bs], bphase ^ 1u, 100);
+              mbar_expect_tx(&b_full[bs], p.Cout_w * ROWB);
+              tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stride, 0, ((pass * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
+              if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; }
             }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp < H_EPI_W0) {
+    const int iss = warp - 1;   // issuer index: owns output slices j with j % H_MMA_WARPS == iss
     // ================= MMA issuer: the whole warp walks the (warp-uniform) loops, one elected lane issues =================
+    // The issuing thread is latency-bound on its own scalar code, so everything per operand tile is table-driven:
+    // sTap[pass*ntaps + t] = (descriptor offset of the tap inside a plane) | (dz - dzmin) << 16, ring indices are counters.
+    for (int i = lane; iss == 0 && i < p.nphase * p.ntaps; i += 32) {
+      const int8_t* off = p.tap_off[i];
+      sTap[i] = ((uint32_t)(((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB) >> 4) | ((uint32_t)(off[0] - p.dzmin) << 16);
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * H_MMA_WARPS) : "memory");
     const uint32_t leader = elect_one_sync();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout_w >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a_hi = kmajor_desc_hi<KC>(HP_W * ROWB);      // SBO = 10 halo rows
     const uint32_t b_hi = kmajor_desc_hi<KC>(8 * ROWB);
     const uint32_t plane_lo0 = kmajor_desc_lo(smem_u32(sP)), plane_step = (uint32_t)p.plane_stride >> 4;
     const uint32_t b_lo0 = kmajor_desc_lo(smem_u32(sB)), b_step = (uint32_t)p.b_stride >> 4;
-    uint32_t bcount = 0, acc_it = 0;
+    const uint32_t jstep = (uint32_t)p.nkc * plane_step;
+    const int ntap_total = p.ntaps;
+    uint32_t bs = 0, bphase = 0;             // B ring slot / parity
+    uint32_t buf = 0, acc_use = 0;           // accumulator buffer, number of uses so far
     int iter = 0;
     for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
       const int tz = (st / (p.tiles_w * p.tiles_h)) % p.tiles_d;
       const int nj = min(p.td, p.Do - tz * p.td);
-      uint32_t waited = 0;
-      for (int pass = 0; pass < p.nphase; ++pass, ++acc_it) {
-        const int buf = acc_it % p.nbuf;
-        if (acc_it >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_it / p.nbuf) - 1) & 1);
+      const uint32_t jmask = (1u << nj) - 1u;
+      uint32_t waited = 0;                   // bit (slice plane * nkc + kc)
+      const long long t_in = trace ? clock64() : 0;
+      for (int pass = 0; pass < p.nphase; ++pass) {
+        if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1);
         const uint32_t acc0 = tmem_base + buf * p.acc_stride;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int8_t* off = p.tap_off[pass * p.ntaps + t];
-          const int dzr = off[0] - p.dzmin;
-          const uint32_t tap16 = (uint32_t)(((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB) >> 4;
-          for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
-            // planes this (tap, chunk) touches for the first time in this super-tile
-            for (int j = 0; j < nj; ++j) {
-              const int pl = (j + dzr) * p.nkc + kc;
-              if (!((waited >> pl) & 1u)) { mbar_wait(&plane_full[pl], iter & 1); waited |= 1u << pl; }
+        const uint32_t* taps = sTap + pass * ntap_total;
+        for (int t = 0; t < ntap_total; ++t) {
+          const uint32_t te = taps[t];
+          const uint32_t tap16 = te & 0xFFFFu, dzr = te >> 16;
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            // planes this (tap, chunk) touches for the first time in this super-tile (nkc == 1: planes dzr .. dzr+nj-1)
+            if (p.nkc == 1) {
+              uint32_t need = (jmask << dzr) & ~waited;
+              while (need) { const int pl = __ffs(need) - 1; mbar_wait(&plane_full[pl], iter & 1); need &= need - 1; }
+              waited |= jmask << dzr;
+            } else {
+              for (int j = 0; j < nj; ++j) {
+                const int pl = (j + dzr) * p.nkc + kc;
+                if (!((waited >> pl) & 1u)) { mbar_wait(&plane_full[pl], iter & 1); waited |= 1u << pl; }
+              }
             }
-            const int s = bcount % p.nb;
-            mbar_wait(&b_full[s], (bcount / p.nb) & 1);
+            mbar_wait(&b_full[bs], bphase);
             tcgen05_fence_after();
             if (leader) {
-              const uint32_t b_lo = b_lo0 + s * b_step;
-              const uint32_t a_lo = plane_lo0 + (uint32_t)(dzr * p.nkc + kc) * plane_step + tap16;
+              const uint32_t b_lo = b_lo0 + bs * b_step;
+              const uint32_t a_lo = plane_lo0 + (dzr * p.nkc + kc) * plane_step + tap16;
               const uint32_t first = (t | kc) ? 1u : 0u;
-              for (int j = 0; j < nj; ++j) {
-                const uint32_t aj = a_lo + (uint32_t)(j * p.nkc) * plane_step, dj = acc0 + j * p.Cout_w;
+              for (int j = iss; j < nj; j += H_MMA_WARPS) {
+                const uint32_t aj = a_lo + j * jstep, dj = acc0 + j * p.Cout_w;
                 umma_bf16_lohi(dj, aj, a_hi, b_lo, b_hi, idesc, first);
 #pragma unroll
                 for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dj, aj + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);
               }
-              tcgen05_commit(&b_empty[s]);
+              tcgen05_commit(&b_empty[bs]);
             }
             __syncwarp();
+            if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; }
           }
         }
         if (leader) tcgen05_commit(&acc_full[buf]);
         __syncwarp();
+        ++acc_use;
+        if (++buf == (uint32_t)p.nbuf) buf = 0;
       }
       if (leader) tcgen05_commit(planes_empty);
       __syncwarp();
+      if (trace && iter < 16 && lane == 0 && iss == 0) { dbg[iter * 16 + 2] = t_in; dbg[iter * 16 + 3] = clock64(); }
     }
   } else {
     // ================= epilogue: 8 warps, two per TMEM lane quarter, splitting the (slice, 16-column chunk) list ==========
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - H_EPI_W0) >> 2;
     const int row = q * 32 + lane;
     const int rx = row & 7, ry = row >> 3;
-    for (int i = threadIdx.x - 64; i < p.Cout_w; i += 32 * H_EPI_WARPS) {
+    for (int i = threadIdx.x - 32 * H_EPI_W0; i < p.Cout_w; i += 32 * H_EPI_WARPS) {
       sBias[i] = __ldg(bias + i);
       sPrelu[i] = p.has_prelu ? __ldg(prelu + i) : 1.0f;
     }
@@ -205,9 +232,11 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           const __nv_bfloat16* rp = resb + row_off(half / nch) + (half % nch) * 16;
           rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
         }
-        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1);
+        const long long te0 = clock64();
+        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 400);   // long waits: sleep, do not poll
         tcgen05_fence_after();
-        for (int it = half; it < nitems; it += 2) {
+        const long long te1 = clock64();
+        for (int it = half; it < ((p.dbg_flags & 1) ? 0 : nitems); it += 2) {
           const int j = it / nch, c0 = (it - j * nch) << 4;
           const uint4 rcur0 = rnext[0], rcur1 = rnext[1];
           if (p.has_residual && valid_xy && it + 2 < nitems) {       // prefetch the next chunk's residual row
@@ -271,6 +300,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+        if (trace && warp == H_EPI_W0 && lane == 0 && acc_it < 16) { dbg[acc_it * 16 + 8] = te0; dbg[acc_it * 16 + 9] = te1; dbg[acc_it * 16 + 10] = clock64(); }
       }
     }
   }
@@ -282,14 +312,31 @@ __global__ void __launch_bounds__(H_THREADS, 1)
 template <int KC>
 static int launch_halo(const HaloParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
                        const float* prelu, const void* residual, void* y, int grid, size_t smem, cudaStream_t st) {
+  long long* dbg = nullptr;
+  const char* trace_path = getenv("OFSV_HALO_TRACE");
+  if (trace_path) { cudaMalloc(&dbg, 16 * 16 * 8); cudaMemset(dbg, 0, 16 * 16 * 8); }
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("ofsv_conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
     attr_done = true;
   }
-  conv_halo_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
-  return check_launch("conv_halo_kernel");
+  conv_halo_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y, dbg);
+  const int rc = check_launch("conv_halo_kernel");
+  if (trace_path) {   // debug only: synchronous dump of CTA 0's timeline
+    static long long h[256];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "launch N=%d Cout_w=%d td=%d nphase=%d ntaps=%d tiles=%dx%dx%d grid=%d nb=%d nbuf=%d\n", P.N, P.Cout_w, P.td, P.nphase, P.ntaps, P.tiles_w, P.tiles_h, P.tiles_d, grid, P.nb, P.nbuf);
+      const long long t0 = h[0];
+      for (int i = 0; i < 16 && h[i * 16 + 3]; ++i)
+        fprintf(f, "  st %2d: prod wait_planes_empty [%lld..%lld]  mma [%lld..%lld] wait plane %lld b %lld acc %lld | epi(pass %d) wait_full [%lld..%lld] done %lld\n", i, h[i * 16] - t0, h[i * 16 + 1] - t0, h[i * 16 + 2] - t0, h[i * 16 + 3] - t0, h[i * 16 + 4], h[i * 16 + 5], h[i * 16 + 6], i, h[i * 16 + 8] - t0, h[i * 16 + 9] - t0, h[i * 16 + 10] - t0);
+      fclose(f);
+    }
+  }
+  return rc;
 }
 
 static int num_sms() {
@@ -349,10 +396,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   P.tiles_w = (int)cdiv(d->Wo, HT_W); P.tiles_h = (int)cdiv(d->Ho, HT_H);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
   P.shuffle = d->out_shuffle;
+  { const char* f = getenv("OFSV_HALO_DBGFLAGS"); P.dbg_flags = f ? atoi(f) : 0; }   // bring-up switches (1 = skip epilogue work)
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
   const int sms = num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
-  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4;
+  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
   // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
   int td = 0;
   const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits

@@ -139,7 +139,7 @@ int validate_conv_desc(const ofsv_conv_desc* d, const char* who) {
                "%s: bad spatial shape", who);
   OFSV_REQUIRE(d->Cin_s >= 16 && d->Cin_s % 16 == 0, "%s: Cin_s=%d must be a multiple of 16", who, d->Cin_s);
   OFSV_REQUIRE(d->Cout_s >= 8 && d->Cout_s % 8 == 0 && d->Cout_w >= 16 && d->Cout_w % 16 == 0 && d->Cout_s <= d->Cout_w &&
-                   d->Cout_w - d->Cout_s < 16,
+                   (d->Cout_w - d->Cout_s < 16 || d->out_shuffle == d->Cout_s),
                "%s: bad output channels (Cout_s=%d Cout_w=%d)", who, d->Cout_s, d->Cout_w);
   OFSV_REQUIRE(d->nphase >= 1 && d->ntaps >= 1 && d->nphase * d->ntaps <= OFSV_MAX_TAPS, "%s: nphase*ntaps out of range", who);
   OFSV_REQUIRE(d->nphase == 1 || d->nphase == (1 << d->nd), "%s: nphase must be 1 or 2^nd", who);

@@ -15,24 +15,33 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a pipeline bug must surface as a trap (cudaErrorLaunchFailure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+// Bounded wait: a pipeline bug must surface as a trap (cudaErrorLaunchFailure), never as a hung GPU.  The fast path (barrier
+// already complete) is a single try_wait: the MMA-issuing thread calls this once per operand tile.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done;
+}
+// Waiting warps back off with nanosleep: at N = 64 the tensor core's operand fetch needs ~95 % of the shared-memory
+// cycles, so nine warps hammering mbarrier words in shared memory measurably slow the MMAs down.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t sleep_ns) {
   const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
+  while (!mbar_try(addr, parity)) {
+    __nanosleep(sleep_ns);
     if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 32) {
+  const uint32_t addr = smem_u32(bar);
+  if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity, sleep_ns);
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3, int c4) {

@@ -1,4 +1,5 @@
-"""Tiny driver for ncu captures: a few Model.inference calls on one synthetic 256^3 (or given size) pair."""
+"""Tiny driver for ncu captures: warm-up inferences, then ONE Model.inference inside a cudaProfilerStart/Stop range
+(run ncu with --profile-from-start off) on one synthetic pair.  usage: prof_step.py [size=256] [warmup=3] [2d]"""
 import os
 import sys
 
@@ -6,16 +7,26 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opticalflowscivis_b200 import synth  # noqa: E402
-from opticalflowscivis_b200.flow3d.model.RIFE import Model  # noqa: E402
 
 s = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+warm = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+two_d = len(sys.argv) > 3 and sys.argv[3] == "2d"
 torch.manual_seed(1234)
+if two_d:
+    from opticalflowscivis_b200.flow2d.model.RIFE import Model
+    a, _, b = synth.droplet2d(64)
+    d0, d1 = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+else:
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    a, _, b = synth.droplet3d_u8(1, s)
+    d0, d1 = torch.from_numpy(a).cuda().float() / 255, torch.from_numpy(b).cuda().float() / 255
 m = Model()
 m.eval()
-a, _, b = synth.droplet3d_u8(1, s)
-d0, d1 = torch.from_numpy(a).cuda().float() / 255, torch.from_numpy(b).cuda().float() / 255
-for _ in range(iters):
+for _ in range(warm):
     out = m.inference(d0, d1)
 torch.cuda.synchronize()
-print("ok", float(out[0].mean()))
+torch.cuda.profiler.start()
+out = m.inference(d0, d1)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("ok")
