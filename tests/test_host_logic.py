@@ -148,3 +148,53 @@ def test_cpu_tensors_are_rejected():
         CorrelationFunction.apply(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 4, 1, 4, 1, 1, 1)
     with pytest.raises(NotImplementedError):
         CorrelationFunction.apply(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 3, 3, 20, 1, 2, 1)
+
+
+# ------------------------------------------------------------------------------------------------- multi-GPU host logic
+def test_shard_range_partitions_every_item_once():
+    from opticalflowscivis_b200.shard import shard_range, shard_sizes
+    for n in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            owned = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                owned += list(range(lo, hi))
+            assert owned == list(range(n))
+            assert max(shard_sizes(n, world)) - min(shard_sizes(n, world)) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, n_items, q):
+    import torch.distributed as dist
+    from opticalflowscivis_b200.shard import gather_counts, shard_range
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_items, rank, world)
+        total, t = gather_counts(hi - lo, 10.0 + rank)          # rank r "took" 10+r ms
+        q.put((rank, lo, hi, total, t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_sharding_world2_gloo():
+    """N>1 path on CPU: two gloo ranks shard 5 pairs with no data-path collective; the only reduction is
+    (sum of processed items, max of device times), exactly what bench.py does over NCCL."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
+    assert all(r[3] == 5 and r[4] == 11.0 for r in res)
