@@ -96,7 +96,9 @@ int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int
  * nd = 2|3, scale ∈ {1,2,4}; dst [N][D/s][H/s][W/s][Cs], channel order img0,img1,warped0,warped1,mask,flow[0..2nd). */
 int ofsv_pack_block_input(const float* img0, const float* img1, const float* warped0, const float* warped1,
                           const float* mask, const float* flow, void* dst, int act_dtype, int nd, int N, int D, int H,
-                          int W, int scale, int Cs, void* stream);
+                          int W, int scale, int Cs, int s2d, void* stream);
+/* s2d = 1: dst is the shifted space-to-depth tensor [N][Dn/2+1][Hn/2+1][Wn/2+1][2^nd][Cs] of the resized grid
+ * (Dn,Hn,Wn) = (D,H,W)/scale (see ofsv_conv_desc.out_s2d); only interior sub-cells are written. */
 
 #define OFSV_MAX_TAPS 64
 /* One convolution layer in "tap" form.  For every phase ph, every virtual output position o = (oz,oy,ox) in
@@ -123,6 +125,12 @@ typedef struct ofsv_conv_desc {
                                        * columns are [output parity (z,y,x)][8 channels], row o is written to the 2^nd positions
                                        * 2*o + parity of a [N][2Do][2Ho][2Wo][8] tensor (ConvTranspose(4,2,1) with all parities
                                        * evaluated as ONE 3^nd-tap conv whose weights are zero where a parity does not use a tap) */
+  int32_t out_s2d;                    /* 1: y is written in the SHIFTED SPACE-TO-DEPTH layout (ofsv_conv_halo only, nphase = 1,
+                                       * out_stride = 1, no residual): logical output (z,y,x) of the [Dy][Hy][Wy] grid goes to cell
+                                       * ((i+1)>>1) / sub-cell ((i+1)&1) per axis of a [N][Dy/2+1][Hy/2+1][Wy/2+1][2^nd][Cout_s]
+                                       * tensor whose border sub-cells the caller keeps zero.  A Conv(k<=4, s=2, p=1) over the
+                                       * logical tensor is then a stride-1 conv with tap offsets in {0,1}^nd over 2^nd*Cout_s
+                                       * channels: kernel index k = 2*offset + sub-cell. */
 } ofsv_conv_desc;
 
 /* SIMT (CUDA-core, fp32 accumulate) engine: exact-order validation path and small-channel layers.
@@ -151,12 +159,16 @@ int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, co
 /* Fused 3-D IFBlock output stage: ofsv_head_upsample_add + ofsv_warp_blend_3d_f32 (+ the next block's
  * ofsv_pack_block_input) in one pass over the full-resolution voxels — Flow-3D/model/IFNet.py:118-119 (resize, *scale),
  * :169-170 (flow/mask accumulate), :186-191 (sigmoid, warp x2), :242 (blend), :82-90,166 (next block's resized concat).
- * head [N][D/sh][H/sh][W/sh][Cs] fp32; flow_prev/mask_prev NULL for block0; merged/mask_sig optional;
- * scale_next in {0: no packed output, 1, 2}: pack_out [N][D/sn][H/sn][W/sn][16] bf16 = the next block's conv0 input. */
-int ofsv_block_finish_3d(const float* head, int Cs, const float* flow_prev, const float* mask_prev, const float* img0,
-                         const float* img1, const float* lin_h, const float* lin_d, const float* lin_w, float* flow_out,
-                         float* mask_out, float* merged, float* mask_sig, void* pack_out, int N, int D, int H, int W,
-                         int scale_head, int scale_next, int ref_mode, void* stream);
+ * It works on the CHANNELS-LAST flow/mask state fm[N][D][H][W][8] fp32 = (flow 0..5, mask logit, 0): one 32 B sector
+ * per voxel, read and written with coalesced 16 B accesses; it is also the layout the depth-to-space head conv produces.
+ * head [N][D/sh][H/sh][W/sh][8] fp32; fm_prev NULL for block0; merged / mask_sig (N,1,D,H,W) optional;
+ * scale_next in {0: no packed output, 1, 2}: pack_out = the next block's conv0 input, bf16 [N][D/sn][H/sn][W/sn][16], or with
+ * pack_s2d = 1 its shifted space-to-depth form (ofsv_conv_desc.out_s2d) so that conv0 (k=4,s=2,p=1) runs as a stride-1
+ * conv on ofsv_conv_halo. */
+int ofsv_block_stage_3d(const float* head, const float* fm_prev, const float* img0, const float* img1, const float* lin_h,
+                        const float* lin_d, const float* lin_w, float* fm_out, float* merged, float* mask_sig,
+                        void* pack_out, int N, int D, int H, int W, int scale_head, int scale_next, int pack_s2d,
+                        int ref_mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ class ConvDesc(ctypes.Structure):
         ("has_prelu", ctypes.c_int32), ("has_residual", ctypes.c_int32),
         ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
         ("out_shuffle", ctypes.c_int32),
+        ("out_s2d", ctypes.c_int32),
     ]
 
 
@@ -44,12 +45,12 @@ _SIGS = {
     "ofsv_corr81_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ofsv_upsample_flow_ac_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warping_no_div_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 8 + [_P]),
+    "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 9 + [_P]),
     "ofsv_conv_simt": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_halo": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "ofsv_block_finish_3d": (_I, [_P, _I] + [_P] * 12 + [_I] * 7 + [_P]),
+    "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 8 + [_P]),
 }
 EXPORTS = tuple(_SIGS)
 

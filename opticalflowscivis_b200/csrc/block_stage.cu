@@ -1,0 +1,285 @@
+// Fused IFBlock output stage for 3-D volumes on a CHANNELS-LAST flow/mask state (a4/a5/a6 glue, one pass per scale):
+//
+//   flow_d, mask_d = F.interpolate(head, scale) (flow_d *= scale)                 Flow-3D/model/IFNet.py:118-119
+//   flow = flow + flow_d ; mask = mask + mask_d                                    :169-170
+//   warped0 = warp(img0, flow[:, :3]) ; warped1 = warp(img1, flow[:, 3:6])         :190-191
+//   mask_sig = sigmoid(mask) ; merged = warped0*mask_sig + warped1*(1-mask_sig)    :186,242      (optional)
+//   next block's input = cat(img0,img1,warped0,warped1,mask,flow) resized by 1/s_next, flow/s_next   :82-90,166
+//
+// State layout: fm[N][D][H][W][8] fp32 = (flow 0..5, mask logit, 0).  One voxel = one 32 B sector, so the state is read
+// and written with fully coalesced 16 B accesses (two threads per voxel) instead of seven strided 4 B planes, and the
+// depth-to-space epilogue of the head conv produces exactly this layout.  The user-facing (N,6,D,H,W) flow tensors are
+// permuted views of it (ops.py).
+//
+// CTA = 32(h) x 8(w) voxels at fixed (n, d) (two d planes when the next block's input is pooled 2x):
+//   phase A  (voxel, half) threads: prev (+) up-sampled head -> fm_out (global, streaming) and a padded shared tile
+//   phase B  one voxel per thread, LANES ALONG h: the reference warp rotates axes, output h is the
+//            contiguous source axis, so the 16 trilinear taps of a warp are 128 B-coalesced; sigmoid / blend; the 11
+//            block-input channels go to shared memory (bf16 rows, or fp32 planes for the 2x2x2 mean)
+//   phase C  coalesced stores of merged / sigmoid(mask) / the packed bf16 rows.
+// The packed output is either plain channels-last [N][D/s][H/s][W/s][16] or the SHIFTED SPACE-TO-DEPTH form
+// [N][Dn/2+1][Hn/2+1][Wn/2+1][2x2x2][16] (cell = (i+1)>>1, sub = (i+1)&1 per axis; border sub-cells stay zero) that turns
+// the next conv0 (k=4, s=2, p=1) into a stride-1 2^3-tap conv over 128 channels for the halo tcgen05 kernel.
+#include "warp_device.cuh"
+
+namespace ofsv {
+
+constexpr int BS_H = 32, BS_W = 8;
+constexpr int BS_ROW = BS_W * 8 + 4;   // floats per tile row of the state tile: +16 B so lanes along h hit distinct banks
+constexpr int BS_PKROW = BS_W * 2 + 1; // uint4 per tile row of the packed tile (32 B per voxel + 16 B pad)
+
+struct Lerp1s {
+  int i0, i1;
+  float l0, l1;
+};
+// ATen area_pixel_compute_source_index (align_corners=False) + guard_index_and_lambda
+__device__ __forceinline__ Lerp1s up_index1s(int dst, int n_in, float rscale) {
+  float src = __fsub_rn(__fmul_rn(rscale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.0f ? 0.0f : src;
+  Lerp1s L;
+  L.i0 = min((int)src, n_in - 1);
+  L.i1 = L.i0 + (L.i0 < n_in - 1 ? 1 : 0);
+  L.l1 = fminf(fmaxf(__fsub_rn(src, (float)L.i0), 0.0f), 1.0f);
+  L.l0 = __fsub_rn(1.0f, L.l1);
+  return L;
+}
+
+__device__ __forceinline__ float4 lerp4(float4 a, float la, float4 b, float lb) {
+  return make_float4(__fadd_rn(__fmul_rn(a.x, la), __fmul_rn(b.x, lb)), __fadd_rn(__fmul_rn(a.y, la), __fmul_rn(b.y, lb)),
+                     __fadd_rn(__fmul_rn(a.z, la), __fmul_rn(b.z, lb)), __fadd_rn(__fmul_rn(a.w, la), __fmul_rn(b.w, lb)));
+}
+
+__device__ __forceinline__ uint32_t bs_pack2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// element (bf16) offset of the 16-channel row of position (z,y,x) of sample n in the packed tensor of logical size (Dn,Hn,Wn)
+template <bool S2D>
+__device__ __forceinline__ int64_t pack_row_off(int n, int z, int y, int x, int Dn, int Hn, int Wn) {
+  if (!S2D) return ((((int64_t)n * Dn + z) * Hn + y) * Wn + x) * 16;
+  return s2d_row(3, n, z, y, x, Dn, Hn, Wn) * 16;
+}
+
+struct StagePtrs {
+  const float* head; const float* fm_prev; const float* img0; const float* img1;
+  const float* lin_h; const float* lin_d; const float* lin_w;
+  float* fm_out; float* merged; float* mask_sig; __nv_bfloat16* pack_out;
+};
+
+template <int SH, int SN, bool S2D, bool FMA>
+__global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
+  constexpr int TDZ = SN == 2 ? 2 : 1;
+  __shared__ __align__(16) float s_fm[BS_H * BS_ROW];
+  __shared__ float s_img[2][BS_H][BS_W + 1];
+  __shared__ float s_out[2][BS_H][BS_W + 1];
+  __shared__ __align__(16) uint4 s_pk[SN == 1 ? BS_H * BS_PKROW : 1];
+  __shared__ float s_pool[SN == 2 ? 2 * 11 : 1][BS_H][BS_W + 1];
+
+  const int H = P.H, W = P.W, D = P.D, HW = H * W;
+  const int64_t V = (int64_t)D * HW;
+  const int nzb = D / TDZ;
+  const int n = blockIdx.z / nzb, d0 = (blockIdx.z - n * nzb) * TDZ;
+  const int h0 = blockIdx.y * BS_H, w0 = blockIdx.x * BS_W;
+  const int tid = threadIdx.x;
+  // phase B mapping: lanes along h
+  const int lane = tid & 31, wl = tid >> 5;
+  const int hB = h0 + lane, wB = w0 + wl;
+  const bool okB = hB < H && wB < W;
+  // phase A/C mapping of the planar tiles: 8 consecutive threads = one 32 B row segment
+  const int rP = tid >> 3, cP = tid & 7;
+  const bool okP = (h0 + rP) < H && (w0 + cP) < W;
+  const int Dh = D / SH, Hh = H / SH, Wh = W / SH;
+  const float* hb = q.head + (int64_t)n * Dh * Hh * Wh * 8;
+  const bool has_prev = q.fm_prev != nullptr;
+  const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+
+#pragma unroll
+  for (int dz = 0; dz < TDZ; ++dz) {
+    const int d = d0 + dz;
+    const int64_t plane = (int64_t)n * V + (int64_t)d * HW;
+    if (dz > 0) __syncthreads();
+    // ---------------- phase A: state update, two threads per voxel, 16 B each
+    if (SN != 0) {
+      const int64_t g = plane + (int64_t)(h0 + rP) * W + w0 + cP;
+      s_img[0][rP][cP] = okP ? ldg_stream(q.img0 + g) : 0.0f;
+      s_img[1][rP][cP] = okP ? ldg_stream(q.img1 + g) : 0.0f;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int i = it * 256 + tid;
+      const int half = i & 1, vox = i >> 1;
+      const int wl_a = vox & 7, hl_a = vox >> 3;
+      const int h = h0 + hl_a, w = w0 + wl_a;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (h < H && w < W) {
+        const int64_t g = ((plane + (int64_t)h * W + w) << 3) + half * 4;
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_prev) pv = ldg_stream4(q.fm_prev + g);
+        float4 v;
+        if (SH == 1) {
+          v = ldg_stream4(hb + ((((int64_t)d * H + h) * W + w) << 3) + half * 4);
+        } else {
+          const float rs = 1.0f / (float)SH;
+          const Lerp1s lx = up_index1s(w, Wh, rs), ly = up_index1s(h, Hh, rs), lz = up_index1s(d, Dh, rs);
+          float4 az[2];
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int zz = a ? lz.i1 : lz.i0;
+            float4 ay[2];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int yy = b ? ly.i1 : ly.i0;
+              const float* r = hb + (((int64_t)zz * Hh + yy) * Wh) * 8 + half * 4;
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(r + lx.i0 * 8));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(r + lx.i1 * 8));
+              ay[b] = lerp4(c0, lx.l0, c1, lx.l1);
+            }
+            az[a] = lerp4(ay[0], ly.l0, ay[1], ly.l1);
+          }
+          v = lerp4(az[0], lz.l0, az[1], lz.l1);
+        }
+        const float sh = (float)SH;
+        if (half == 0) {
+          o.x = __fadd_rn(pv.x, __fmul_rn(v.x, sh)); o.y = __fadd_rn(pv.y, __fmul_rn(v.y, sh));
+          o.z = __fadd_rn(pv.z, __fmul_rn(v.z, sh)); o.w = __fadd_rn(pv.w, __fmul_rn(v.w, sh));
+        } else {
+          o.x = __fadd_rn(pv.x, __fmul_rn(v.x, sh)); o.y = __fadd_rn(pv.y, __fmul_rn(v.y, sh));
+          o.z = __fadd_rn(pv.z, v.z); o.w = 0.0f;
+        }
+        if (!has_prev) {   // block 0: flow = flow_d exactly (no "+ 0" so -0.0 / rounding match the unfused path)
+          if (half == 0) o = make_float4(__fmul_rn(v.x, sh), __fmul_rn(v.y, sh), __fmul_rn(v.z, sh), __fmul_rn(v.w, sh));
+          else o = make_float4(__fmul_rn(v.x, sh), __fmul_rn(v.y, sh), v.z, 0.0f);
+        }
+        stg_stream4(q.fm_out + g, o);
+      }
+      *reinterpret_cast<float4*>(&s_fm[hl_a * BS_ROW + wl_a * 8 + half * 4]) = o;
+    }
+    __syncthreads();
+    // ---------------- phase B: warps / blend, one voxel per thread, lanes along h
+    if (okB) {
+      const float4 fa = *reinterpret_cast<const float4*>(&s_fm[lane * BS_ROW + wl * 8]);
+      const float4 fb = *reinterpret_cast<const float4*>(&s_fm[lane * BS_ROW + wl * 8 + 4]);
+      const float m = fb.z;
+      const float lh = __ldg(q.lin_h + hB), ld = __ldg(q.lin_d + d), lw = __ldg(q.lin_w + wB);
+      const Trilin t0 = trilin_setup(fa.x, fa.y, fa.z, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+      const Trilin t1 = trilin_setup(fa.w, fb.x, fb.y, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+      const float a = trilin_sample<FMA>(q.img0 + (int64_t)n * V, t0, W, HW);
+      const float b = trilin_sample<FMA>(q.img1 + (int64_t)n * V, t1, W, HW);
+      float ms = 0.0f, mg = 0.0f;
+      if (need_m) {
+        ms = sigmoidf_ref(m);
+        mg = __fadd_rn(__fmul_rn(a, ms), __fmul_rn(b, __fsub_rn(1.0f, ms)));
+      }
+      s_out[0][lane][wl] = mg; s_out[1][lane][wl] = ms;
+      if (SN == 1) {
+        const float i0v = s_img[0][lane][wl], i1v = s_img[1][lane][wl];
+        uint4 lo, hi;
+        lo.x = bs_pack2(i0v, i1v); lo.y = bs_pack2(a, b); lo.z = bs_pack2(m, fa.x); lo.w = bs_pack2(fa.y, fa.z);
+        hi.x = bs_pack2(fa.w, fb.x); hi.y = bs_pack2(fb.y, 0.0f); hi.z = 0u; hi.w = 0u;
+        s_pk[lane * BS_PKROW + wl * 2] = lo;
+        s_pk[lane * BS_PKROW + wl * 2 + 1] = hi;
+      } else if (SN == 2) {
+        const float c11[11] = {s_img[0][lane][wl], s_img[1][lane][wl], a, b, m, fa.x, fa.y, fa.z, fa.w, fb.x, fb.y};
+#pragma unroll
+        for (int c = 0; c < 11; ++c) s_pool[dz * 11 + c][lane][wl] = c11[c];
+      }
+    }
+    __syncthreads();
+    // ---------------- phase C: coalesced stores
+    if (okP) {
+      const int64_t g = plane + (int64_t)(h0 + rP) * W + w0 + cP;
+      if (q.merged) q.merged[g] = s_out[0][rP][cP];
+      if (q.mask_sig) q.mask_sig[g] = s_out[1][rP][cP];
+    }
+    if (SN == 1) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int i = it * 256 + tid;
+        const int half = i & 1, vox = i >> 1;
+        const int wl_a = vox & 7, hl_a = vox >> 3;
+        const int h = h0 + hl_a, w = w0 + wl_a;
+        if (h < H && w < W) {
+          const int64_t off = pack_row_off<S2D>(n, d, h, w, D, H, W) + half * 8;
+          *reinterpret_cast<uint4*>(q.pack_out + off) = s_pk[hl_a * BS_PKROW + wl_a * 2 + half];
+        }
+      }
+    }
+  }
+  if (SN == 2) {
+    // 2x2x2 mean == F.interpolate(., 0.5): nested W, H, D like ATen; flow channels additionally * 0.5
+    __syncthreads();
+    if (tid < 64) {
+      const int ph = tid >> 2, pw = tid & 3;
+      const int oh = h0 / 2 + ph, ow = w0 / 2 + pw;
+      if (oh < H / 2 && ow < W / 2) {
+        float c11[11];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+          float rz[2];
+#pragma unroll
+          for (int dz = 0; dz < 2; ++dz) {
+            const float (*pl)[BS_W + 1] = s_pool[dz * 11 + c];
+            const float r0 = __fadd_rn(__fmul_rn(pl[2 * ph][2 * pw], 0.5f), __fmul_rn(pl[2 * ph][2 * pw + 1], 0.5f));
+            const float r1 = __fadd_rn(__fmul_rn(pl[2 * ph + 1][2 * pw], 0.5f), __fmul_rn(pl[2 * ph + 1][2 * pw + 1], 0.5f));
+            rz[dz] = __fadd_rn(__fmul_rn(r0, 0.5f), __fmul_rn(r1, 0.5f));
+          }
+          float r = __fadd_rn(__fmul_rn(rz[0], 0.5f), __fmul_rn(rz[1], 0.5f));
+          if (c >= 5) r = __fmul_rn(r, 0.5f);
+          c11[c] = r;
+        }
+        uint4 lo, hi;
+        lo.x = bs_pack2(c11[0], c11[1]); lo.y = bs_pack2(c11[2], c11[3]); lo.z = bs_pack2(c11[4], c11[5]); lo.w = bs_pack2(c11[6], c11[7]);
+        hi.x = bs_pack2(c11[8], c11[9]); hi.y = bs_pack2(c11[10], 0.0f); hi.z = 0u; hi.w = 0u;
+        uint4* o = reinterpret_cast<uint4*>(q.pack_out + pack_row_off<S2D>(n, d0 / 2, oh, ow, D / 2, H / 2, W / 2));
+        o[0] = lo; o[1] = hi;
+      }
+    }
+  }
+}
+
+}  // namespace ofsv
+
+using namespace ofsv;
+
+extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, const float* img0, const float* img1,
+                                   const float* lin_h, const float* lin_d, const float* lin_w, float* fm_out, float* merged,
+                                   float* mask_sig, void* pack_out, int N, int D, int H, int W, int scale_head,
+                                   int scale_next, int pack_s2d, int ref_mode, void* stream) {
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < (1ll << 31), "ofsv_block_stage_3d: bad shape");
+  OFSV_REQUIRE(scale_head == 1 || scale_head == 2 || scale_head == 4, "ofsv_block_stage_3d: scale_head %d not in {1,2,4}", scale_head);
+  OFSV_REQUIRE(scale_next == 0 || scale_next == 1 || scale_next == 2, "ofsv_block_stage_3d: scale_next %d not in {0,1,2}", scale_next);
+  OFSV_REQUIRE(D % scale_head == 0 && H % scale_head == 0 && W % scale_head == 0, "ofsv_block_stage_3d: dims must be multiples of scale_head");
+  OFSV_REQUIRE(scale_next != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ofsv_block_stage_3d: dims must be even for scale_next = 2");
+  OFSV_REQUIRE(!pack_s2d || (scale_next != 0 && D % (2 * scale_next) == 0 && H % (2 * scale_next) == 0 && W % (2 * scale_next) == 0),
+               "ofsv_block_stage_3d: space-to-depth packing needs dims that are multiples of 2*scale_next");
+  OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_block_stage_3d: bad ref_mode");
+  if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(head && img0 && img1 && lin_h && lin_d && lin_w && fm_out, "ofsv_block_stage_3d: null pointer");
+  OFSV_REQUIRE((scale_next == 0) == (pack_out == nullptr), "ofsv_block_stage_3d: pack_out must be given iff scale_next != 0");
+  OFSV_REQUIRE(aligned16(head) && aligned16(fm_out) && (!fm_prev || aligned16(fm_prev)) && (!pack_out || aligned16(pack_out)),
+               "ofsv_block_stage_3d: head / fm / pack_out must be 16-byte aligned");
+  const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
+  const int tdz = scale_next == 2 ? 2 : 1;
+  const dim3 grid((unsigned)cdiv(W, BS_W), (unsigned)cdiv(H, BS_H), (unsigned)(N * (D / tdz)));
+  if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
+  StagePtrs q{head, fm_prev, img0, img1, lin_h, lin_d, lin_w, fm_out, merged, mask_sig, reinterpret_cast<__nv_bfloat16*>(pack_out)};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fma = ref_mode == OFSV_REF_CUDA;
+  const bool s2d = pack_s2d != 0;
+#define GO3(SH, SN, S2)                                                                                \
+  do {                                                                                                 \
+    if (fma) block_stage_3d_kernel<SH, SN, S2, true><<<grid, 256, 0, st>>>(q, P);                      \
+    else block_stage_3d_kernel<SH, SN, S2, false><<<grid, 256, 0, st>>>(q, P);                         \
+  } while (0)
+#define GO(SH)                                                                                         \
+  do {                                                                                                 \
+    if (scale_next == 0) GO3(SH, 0, false);                                                            \
+    else if (scale_next == 1) { if (s2d) GO3(SH, 1, true); else GO3(SH, 1, false); }                   \
+    else { if (s2d) GO3(SH, 2, true); else GO3(SH, 2, false); }                                        \
+  } while (0)
+  if (scale_head == 1) GO(1); else if (scale_head == 2) GO(2); else GO(4);
+#undef GO
+#undef GO3
+  return check_launch("block_stage_3d_kernel");
+}

@@ -44,6 +44,7 @@ struct HaloParams {
   int nb, plane_stride, b_stride;    // B ring depth, smem strides (bytes, multiples of 1024)
   int nbuf, acc_stride;              // TMEM accumulator double buffering
   int has_prelu, has_residual, out_f32, shuffle, dbg_flags;
+  int nd, out_s2d;
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         // row offset of output slice j (non-shuffled layers)
         auto row_off = [&](int j) -> int64_t {
           const int oz = tz * p.td + j;
+          if (p.out_s2d) return s2d_row(p.nd, n, oz, oy, ox, p.Dy, p.Hy, p.Wy) * p.Cout_s;
           return ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy + ox * p.out_stride + px) * p.Cout_s;
         };
         uint4 rnext[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
@@ -372,6 +374,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     set_error("ofsv_conv_halo: bad depth-to-space configuration");
     return OFSV_EINVAL;
   }
+  if (d->out_s2d && (d->nphase != 1 || d->out_stride != 1 || d->has_residual || d->out_shuffle || d->Hy % 2 || d->Wy % 2 ||
+                     (d->nd == 3 && d->Dy % 2))) {
+    set_error("ofsv_conv_halo: bad space-to-depth output configuration");
+    return OFSV_EINVAL;
+  }
   int dzmin = 1, dzmax = -1;
   for (int i = 0; i < d->nphase * d->ntaps; ++i) {
     const int8_t* o = d->tap_off[i];
@@ -395,7 +402,7 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   P.b_stride = (d->Cout_w * KC * 2 + 1023) & ~1023;
   P.tiles_w = (int)cdiv(d->Wo, HT_W); P.tiles_h = (int)cdiv(d->Ho, HT_H);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
-  P.shuffle = d->out_shuffle;
+  P.shuffle = d->out_shuffle; P.nd = d->nd; P.out_s2d = d->out_s2d;
   { const char* f = getenv("OFSV_HALO_DBGFLAGS"); P.dbg_flags = f ? atoi(f) : 0; }   // bring-up switches (1 = skip epilogue work)
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
   const int sms = num_sms();

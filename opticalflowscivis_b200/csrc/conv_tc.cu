@@ -173,6 +173,7 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
                             const void* residual, void* y, void* stream) {
   if (int e = validate_conv_desc(d, "ofsv_conv_tc")) return e;
   if (d->out_shuffle) { set_error("ofsv_conv_tc: depth-to-space heads are only implemented by ofsv_conv_halo"); return OFSV_ENOSUP; }
+  if (d->out_s2d) { set_error("ofsv_conv_tc: space-to-depth outputs are only implemented by ofsv_conv_halo"); return OFSV_ENOSUP; }
   if (d->N == 0) return OFSV_OK;
   OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_tc: null pointer");
   OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_tc: has_prelu without prelu slopes");

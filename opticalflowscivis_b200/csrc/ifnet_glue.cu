@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256)
     pack_block_input_kernel(const float* __restrict__ img0, const float* __restrict__ img1,
                             const float* __restrict__ warped0, const float* __restrict__ warped1,
                             const float* __restrict__ mask, const float* __restrict__ flow, T* __restrict__ dst, int N,
-                            int D, int H, int W, int s, int Cs) {
+                            int D, int H, int W, int s, int Cs, int s2d) {
   const int Do = ND == 3 ? D / s : 1, Ho = H / s, Wo = W / s;
   const int64_t V = (int64_t)D * H * W, Vo = (int64_t)Do * Ho * Wo, total = (int64_t)N * Vo;
   const float inv_s = 1.0f / (float)s;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256)
       for (int c = 0; c < NF; ++c)  // F.interpolate(flow, 1/scale) * 1. / scale   (IFNet.py:92 / :88)
         v[5 + c] = __fmul_rn(down_sample<ND>(flow + ((int64_t)n * NF + c) * V, H, W, oz, oy, ox, s), inv_s);
     }
-    T* o = dst + i * Cs;
+    T* o = dst + (s2d ? s2d_row(ND, n, oz, oy, ox, Do, Ho, Wo) : i) * Cs;
     store16(o, v);                                  // one 32 B (bf16) / 64 B (fp32) vector row per position
     for (int c = 16; c < Cs; ++c) o[c] = cvt<T>(0.0f);
   }
@@ -175,8 +175,10 @@ using namespace ofsv;
 
 extern "C" int ofsv_pack_block_input(const float* img0, const float* img1, const float* warped0, const float* warped1,
                                      const float* mask, const float* flow, void* dst, int act_dtype, int nd, int N,
-                                     int D, int H, int W, int scale, int Cs, void* stream) {
+                                     int D, int H, int W, int scale, int Cs, int s2d, void* stream) {
   OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_pack_block_input: nd must be 2 or 3");
+  OFSV_REQUIRE(!s2d || ((nd == 2 || D % (2 * scale) == 0) && H % (2 * scale) == 0 && W % (2 * scale) == 0),
+               "ofsv_pack_block_input: space-to-depth packing needs dims that are multiples of 2*scale");
   OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_pack_block_input: scale %d not in {1,2,4}", scale);
   OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1, "ofsv_pack_block_input: bad shape");
   OFSV_REQUIRE((nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
@@ -189,7 +191,7 @@ extern "C" int ofsv_pack_block_input(const float* img0, const float* img1, const
   const int64_t total = (int64_t)N * (nd == 3 ? D / scale : 1) * (H / scale) * (W / scale);
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_1d(total);
-#define GO(ND, T) pack_block_input_kernel<ND, T><<<g, 256, 0, st>>>(img0, img1, warped0, warped1, mask, flow, (T*)dst, N, D, H, W, scale, Cs)
+#define GO(ND, T) pack_block_input_kernel<ND, T><<<g, 256, 0, st>>>(img0, img1, warped0, warped1, mask, flow, (T*)dst, N, D, H, W, scale, Cs, s2d)
   if (act_dtype == OFSV_F32) { if (nd == 2) GO(2, float); else GO(3, float); }
   else if (act_dtype == OFSV_BF16) { if (nd == 2) GO(2, __nv_bfloat16); else GO(3, __nv_bfloat16); }
   else { set_error("ofsv_pack_block_input: bad act_dtype %d", act_dtype); return OFSV_EINVAL; }

@@ -33,6 +33,18 @@ inline int check_launch(const char* what) {
     }                             \
   } while (0)
 
+// Shifted space-to-depth addressing (block_stage.cu, ifnet_glue.cu, conv_halo.cu): position (z,y,x) of a logical
+// [Dn][Hn][Wn] grid lives in cell ((i+1)>>1) with sub-index ((i+1)&1) per axis, cells stored [N][Dn/2+1][Hn/2+1][Wn/2+1]
+// [2^nd sub-cells] rows (2-D: the D axis has extent 1 and is not split).  Returns the ROW index; the sub-cells that
+// correspond to i = -1 and i = n (the conv padding) are never written and must stay zero.
+__host__ __device__ inline int64_t s2d_row(int nd, int n, int z, int y, int x, int Dn, int Hn, int Wn) {
+  const int Hc = Hn / 2 + 1, Wc = Wn / 2 + 1;
+  const int y1 = y + 1, x1 = x + 1;
+  if (nd == 2) return (((int64_t)n * Hc + (y1 >> 1)) * Wc + (x1 >> 1)) * 4 + (((y1 & 1) << 1) | (x1 & 1));
+  const int Dc = Dn / 2 + 1, z1 = z + 1;
+  return ((((int64_t)n * Dc + (z1 >> 1)) * Hc + (y1 >> 1)) * Wc + (x1 >> 1)) * 8 + (((z1 & 1) << 2) | ((y1 & 1) << 1) | (x1 & 1));
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

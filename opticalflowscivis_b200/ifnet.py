@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _C, ops
 
 
+USE_S2D = True     # stride-2 conv0 layers as stride-1 convs over the shifted space-to-depth input (halo engine)
 USE_SHUFFLE_HEADS = True   # final ConvTranspose heads as one 3^d-tap depth-to-space conv (N = 2^d * 8) on the halo engine
 USE_HALO = True    # stride-1 layers on the halo-reuse tcgen05 kernel (csrc/conv_halo.cu)
 TC_READY = True    # the tcgen05 engine (csrc/conv_tc.cu) passed parity on B200 (tests/tc_probe.py, profiles/)
@@ -90,13 +91,27 @@ class _Layer:
             self.prelu = torch.ones(self.cout_w, device=dev, dtype=torch.float32)
             self.prelu[:cout] = prelu
         self.out_f32, self.residual, self.shuffle = out_f32, residual, shuffle
+        self.in_s2d = self.out_s2d = False
+
+    def out_shape(self, n, osp):
+        """Physical shape of the output tensor for logical output dims osp = (D,H,W)."""
+        sp = osp if self.nd == 3 else osp[1:]
+        if self.out_s2d:
+            shp = [n] + [v // 2 + 1 for v in sp] + [(2 ** self.nd) * self.cout_s]
+        else:
+            shp = [n] + list(sp) + [self.cout_s]
+        return shp
 
     def desc(self, n, in_sp, act_dtype):
-        """in_sp = (D,H,W) of the input; returns (ConvDesc, out_sp)."""
+        """in_sp = LOGICAL (D,H,W) of the input (before space-to-depth); returns (ConvDesc, logical out_sp)."""
         d = _C.ConvDesc()
         d.nd = self.nd
         d.N, (d.Di, d.Hi, d.Wi), d.Cin_s = n, in_sp, self.cin_s
-        if self.shuffle:
+        if self.in_s2d:
+            d.Di, d.Hi, d.Wi = tuple((s // 2 + 1) if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
+            osp = tuple(max(1, s // 2) if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
+            vsp = osp
+        elif self.shuffle:
             vsp = in_sp
             osp = tuple(s * 2 if (self.nd == 3 or i > 0) else 1 for i, s in enumerate(in_sp))
         elif self.nphase == 1:
@@ -116,6 +131,7 @@ class _Layer:
         d.in_dtype = act_dtype
         d.out_dtype = _C.F32 if self.out_f32 else act_dtype
         d.out_shuffle = self.shuffle
+        d.out_s2d = int(self.out_s2d)
         return d, osp
 
 
@@ -132,6 +148,47 @@ def _pack_conv(m: _ConvParams, prelu, residual=False):
     w_tap = torch.stack([w[(slice(None), slice(None)) + ix].t() for ix in idx])   # [T][Cin][Cout]
     return _Layer(m.nd, m.stride, 1, 1, offs, w_tap, m.bias.detach().float(),
                   None if prelu is None else prelu.weight.detach().float(), _rup(m.cout, 16), residual=residual)
+
+
+def _pack_conv_s2d(m: _ConvParams, prelu, cs_in, out_s2d):
+    """Conv(k in {3,4}, stride 2, pad 1) as a stride-1 conv with tap offsets {0,1}^nd over the SHIFTED space-to-depth
+    input (cell = (i+1)>>1, sub-cell = (i+1)&1 per axis; include/ofsv.h `out_s2d`): input i = 2o - 1 + k lives in cell
+    o + (k>>1), sub-cell k&1, so kernel index k = 2*offset + sub.  cs_in = channel stride of one sub-cell."""
+    nd, k = m.nd, m.k
+    assert m.stride == 2 and m.pad == 1 and k in (3, 4) and not m.transposed
+    nsub = 2 ** nd
+    w = m.weight.detach().float()                                    # [Cout][Cin][k..]
+    cout, cin = w.shape[0], w.shape[1]
+    taps, w_tap = [], []
+    for off in itertools.product((0, 1), repeat=nd):
+        wt = torch.zeros(nsub * cs_in, cout, device=w.device)
+        for sub in itertools.product((0, 1), repeat=nd):
+            kk = tuple(2 * off[a] + sub[a] for a in range(nd))
+            if all(v < k for v in kk):
+                si = 0
+                for a in range(nd):
+                    si = (si << 1) | sub[a]                          # (z,y,x), x lowest bit — s2d_row() in ofsv_common.cuh
+                wt[si * cs_in: si * cs_in + cin] = w[(slice(None), slice(None)) + kk].t()
+        taps.append(((0,) if nd == 2 else ()) + off)
+        w_tap.append(wt)
+    lay = _Layer(nd, 1, 1, 1, taps, torch.stack(w_tap), m.bias.detach().float(),
+                 None if prelu is None else prelu.weight.detach().float(), _rup(cout, 16))
+    lay.in_s2d, lay.out_s2d = True, bool(out_s2d)
+    return lay
+
+
+def s2d_shift_pack(x, nd):
+    """Channels-last [N][D][H][W][C] (D = 1 in 2-D) -> shifted space-to-depth [N][D/2+1][H/2+1][W/2+1][2^nd * C]
+    (torch restatement of s2d_row(); used by the CPU tests)."""
+    import torch.nn.functional as F
+    n, d, h, w, c = x.shape
+    if nd == 3:
+        xp = F.pad(x, (0, 0, 1, 1, 1, 1, 1, 1))
+        xp = xp.view(n, d // 2 + 1, 2, h // 2 + 1, 2, w // 2 + 1, 2, c).permute(0, 1, 3, 5, 2, 4, 6, 7)
+        return xp.reshape(n, d // 2 + 1, h // 2 + 1, w // 2 + 1, 8 * c).contiguous()
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    xp = xp.view(n, 1, h // 2 + 1, 2, w // 2 + 1, 2, c).permute(0, 1, 2, 4, 3, 5, 6)
+    return xp.reshape(n, 1, h // 2 + 1, w // 2 + 1, 4 * c).contiguous()
 
 
 _CT_TAPS = {0: ((1, 0), (3, -1)), 1: ((2, 0), (0, 1))}   # ConvTranspose(4,2,1): parity -> ((kernel idx, input offset), ...)
@@ -215,22 +272,35 @@ class IFBlock(nn.Module):
             bh = torch.cat([self.conv1[2].bias, self.conv2[2].bias]).detach().float()
             L.append(_pack_convT(nd, wh, bh, None, 8, True))
             self._heads_shuffle = _pack_heads_shuffle(nd, wh, bh)     # same layer, depth-to-space form (halo engine)
+            # conv0.{0,1} in space-to-depth form (halo engine).  conv0.1's planes must fit shared memory: 2^nd*Cs0 channels
+            # x (1 + dz range) planes <= 8 chunks of 64 channels -> always in 2-D, Cs0 <= 32 in 3-D
+            cs0 = _rup(c // 2, 16)
+            self._s2d1_ok = nd == 2 or cs0 <= 32
+            self._s2d0 = _pack_conv_s2d(self.conv0[0][0], self.conv0[0][1], 16, out_s2d=self._s2d1_ok)
+            self._s2d1 = _pack_conv_s2d(self.conv0[1][0], self.conv0[1][1], cs0, out_s2d=False) if self._s2d1_ok else None
             self._packed, self._packed_key = L, key
         return self._packed
 
-    def run(self, xin, n, in_sp, act_dtype, engine):
-        """xin: packed channels-last block input [N][in_sp][16].  Returns head [N][in_sp][8] fp32."""
+    def run(self, xin, n, in_sp, act_dtype, engine, s2d_in=False):
+        """xin: packed channels-last block input [N][in_sp][16] (or its shifted space-to-depth form when s2d_in).
+        Returns head [N][in_sp][8] fp32."""
         L = self.layers()
         tdt = torch.float32 if act_dtype == _C.F32 else torch.bfloat16
         x, sp, skip = xin, in_sp, None
         for li, lay in enumerate(L):
-            eng0 = engine(li, lay) if callable(engine) else engine
-            if li == 11 and eng0 == "tc" and USE_HALO and USE_SHUFFLE_HEADS:
+            eng = engine(li, lay) if callable(engine) else engine
+            if li == 11 and eng == "tc" and USE_HALO and USE_SHUFFLE_HEADS:
                 lay = self._heads_shuffle
+            if s2d_in and li == 0:
+                lay = self._s2d0
+            elif s2d_in and li == 1 and self._s2d1_ok:
+                lay = self._s2d1
             d, osp = lay.desc(n, sp, act_dtype)
             odt = torch.float32 if lay.out_f32 else tdt
-            y = torch.empty([n] + ([osp[0]] if self.nd == 3 else []) + [osp[1], osp[2], lay.cout_s], device=x.device, dtype=odt)
-            eng = engine(li, lay) if callable(engine) else engine
+            if lay.out_s2d:
+                y = ops.workspace(("conv0", id(self)), lay.out_shape(n, osp), odt, x.device)
+            else:
+                y = torch.empty(lay.out_shape(n, osp), device=x.device, dtype=odt)
             res = skip if lay.residual else None
             if eng == "tc" and USE_HALO and lay.in_stride == 1 and not getattr(lay, "no_halo", False):
                 # stride-1 layers: halo-reuse kernel; layers it cannot hold in shared memory use the per-tap kernel
@@ -238,6 +308,8 @@ class IFBlock(nn.Module):
                     ops.conv(d, x, lay.w_tc, lay.bias, lay.prelu, res, y, "halo")
                     eng = None
                 except NotImplementedError:
+                    if lay.in_s2d:
+                        raise
                     lay.no_halo = True
             if eng is not None:
                 ops.conv(d, x, lay.w_simt if eng == "simt" else lay.w_tc, lay.bias, lay.prelu, res, y, eng)
@@ -266,7 +338,7 @@ class IFNet(nn.Module):
         self.block_tea = IFBlock(nd, 6 + nf, c=64)      # teacher: training only (§8f), kept for state_dict parity
         self.set_precision(precision, engine)
         self.only_last = False
-        self.fuse_output_stage = True     # 3-D bf16: ofsv_block_finish_3d instead of head_upsample_add + warp_blend + pack
+        self.fuse_output_stage = True     # 3-D bf16: ofsv_block_stage_3d instead of head_upsample_add + warp_blend + pack
 
     def set_precision(self, precision: str, engine: str = "auto"):
         """precision 'bf16' (tensor-core operands, fp32 accumulate; flow/mask accumulators and heads in fp32) or
@@ -306,21 +378,24 @@ class IFNet(nn.Module):
         blocks = (self.block0, self.block1, self.block2)
         scales = [int(v) for v in scale]
         fused = nd == 3 and act == _C.BF16 and self.fuse_output_stage
-        xin = None
+        s2d = eng == "tc" and USE_S2D and USE_HALO and all((v // sc) % 4 == 0 for v in sp for sc in scales)
+        xin = fm = None
         for i, blk in enumerate(blocks):
             s = scales[i]
             last = i == 2
             want_out = last or not self.only_last
             if xin is None:
-                xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act)
+                xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act, s2d=s2d)
             in_sp = tuple(v // s for v in sp)
-            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng)
+            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng, s2d_in=s2d)
             xin = None
             if fused:
-                # one pass: resize + accumulate + warp x2 (+ blend) (+ the next block's resized concat)
+                # one pass over the channels-last state: resize + accumulate + warp x2 (+ blend) (+ the next block's input)
                 s_next = 0 if last else (scales[i + 1] if scales[i + 1] in (1, 2) else 0)
-                flow, mask, mg, ms, xin = ops.block_finish_3d(head, flow, mask, img0, img1, s, s_next, want_out, want_out)
+                fm, mg, ms, xin = ops.block_stage_3d(head, fm, img0, img1, s, s_next, want_out, want_out, pack_s2d=s2d)
+                flow, mask = ops.state_views(fm)
                 if not last and xin is None:          # next scale not fusable (4): fall back to the separate builder
+                    flow, mask = flow.contiguous(), mask.contiguous()
                     w0, w1, _, _ = ops.warp_blend(img0, img1, flow, None, want_merged=False, want_mask=False)
             else:
                 flow, mask = ops.head_upsample_add(head, flow, mask, nd, n, sp, s)

@@ -235,16 +235,43 @@ def warping_no_div(x, flow):
 _TDT = {_C.F32: torch.float32, _C.BF16: torch.bfloat16}
 
 
-def pack_block_input(img0, img1, warped0, warped1, mask, flow, scale, act_dtype, cs=16):
+_WS = {}
+
+
+def workspace(key, shape, dtype, device):
+    """Persistent ZERO-initialised buffer per (key, shape, dtype, device).  Used for the shifted space-to-depth tensors whose
+    border sub-cells (the conv padding) must stay zero: producers only ever write the interior, so the buffer is zeroed
+    once and reused by every later call on the same stream."""
+    k = (key, tuple(shape), dtype, str(device))
+    t = _WS.get(k)
+    if t is None:
+        t = torch.zeros(shape, dtype=dtype, device=device)
+        _WS[k] = t
+    return t
+
+
+def clear_workspaces():
+    _WS.clear()
+
+
+def s2d_shape(n, sp, c):
+    """Shape of the shifted space-to-depth tensor of a logical [n][*sp][c] channels-last tensor (sp = (D,H,W) or (H,W))."""
+    return [n] + [v // 2 + 1 for v in sp] + [(2 ** len(sp)) * c]
+
+
+def pack_block_input(img0, img1, warped0, warped1, mask, flow, scale, act_dtype, cs=16, s2d=False, key="xin"):
     nd = img0.dim() - 2
     n = img0.shape[0]
     sp = list(img0.shape[2:])
     d, h, w = ([1] + sp) if nd == 2 else sp
     osp = [s // scale for s in sp]
-    dst = torch.empty([n] + osp + [cs], device=img0.device, dtype=_TDT[act_dtype])
+    if s2d:
+        dst = workspace((key, scale), s2d_shape(n, osp, cs), _TDT[act_dtype], img0.device)
+    else:
+        dst = torch.empty([n] + osp + [cs], device=img0.device, dtype=_TDT[act_dtype])
     with torch.cuda.device(img0.device), _span("pack_block_input"):
         _C.check(_C.lib().ofsv_pack_block_input(_p(img0), _p(img1), _p(warped0), _p(warped1), _p(mask), _p(flow), _p(dst),
-                                                act_dtype, nd, n, d, h, w, scale, cs, _stream()))
+                                                act_dtype, nd, n, d, h, w, scale, cs, int(s2d), _stream()))
     return dst
 
 
@@ -259,24 +286,36 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
     return flow, mask
 
 
-def block_finish_3d(head, flow_prev, mask_prev, img0, img1, scale_head, scale_next, want_merged, want_mask):
-    """Fused 3-D block output stage (ofsv_block_finish_3d).  Returns (flow, mask_logit, merged|None, mask_sig|None,
-    next_block_input|None) with next_block_input [N][D/sn][H/sn][W/sn][16] bf16 when scale_next in (1, 2)."""
+def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merged, want_mask, pack_s2d=False, key="xin"):
+    """Fused 3-D block output stage on the channels-last state (ofsv_block_stage_3d).  head [N][D/sh][H/sh][W/sh][8] fp32,
+    fm_prev [N][D][H][W][8] fp32 or None.  Returns (fm, merged|None, mask_sig|None, next_block_input|None)."""
     n, _, d, h, w = img0.shape
     dev = img0.device
-    flow = torch.empty((n, 6, d, h, w), device=dev, dtype=torch.float32)
-    mask = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32)
-    mg = torch.empty_like(mask) if want_merged else None
-    ms = torch.empty_like(mask) if want_mask else None
+    if head.dtype != torch.float32 or head.shape[-1] != 8 or not head.is_contiguous():
+        raise ValueError("block_stage_3d: head must be a contiguous fp32 [...,8] tensor")
+    if fm_prev is not None and (fm_prev.shape != (n, d, h, w, 8) or fm_prev.dtype != torch.float32 or not fm_prev.is_contiguous()):
+        raise ValueError("block_stage_3d: fm_prev must be a contiguous fp32 [N,D,H,W,8] tensor")
+    fm = torch.empty((n, d, h, w, 8), device=dev, dtype=torch.float32)
+    mg = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_merged else None
+    ms = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_mask else None
     pk = None
     if scale_next:
-        pk = torch.empty((n, d // scale_next, h // scale_next, w // scale_next, 16), device=dev, dtype=torch.bfloat16)
-    with torch.cuda.device(dev), _span("block_finish"):
-        _C.check(_C.lib().ofsv_block_finish_3d(_p(head), head.shape[-1], _p(flow_prev), _p(mask_prev), _p(img0), _p(img1),
-                                               _p(linspace_table(h, dev)), _p(linspace_table(d, dev)), _p(linspace_table(w, dev)),
-                                               _p(flow), _p(mask), _p(mg), _p(ms), _p(pk), n, d, h, w, scale_head, scale_next,
-                                               _FLAVOR["mode"], _stream()))
-    return flow, mask, mg, ms, pk
+        osp = [d // scale_next, h // scale_next, w // scale_next]
+        if pack_s2d:
+            pk = workspace((key, scale_next), s2d_shape(n, osp, 16), torch.bfloat16, dev)
+        else:
+            pk = torch.empty([n] + osp + [16], device=dev, dtype=torch.bfloat16)
+    with torch.cuda.device(dev), _span("block_stage"):
+        _C.check(_C.lib().ofsv_block_stage_3d(_p(head), _p(fm_prev), _p(img0), _p(img1), _p(linspace_table(h, dev)),
+                                              _p(linspace_table(d, dev)), _p(linspace_table(w, dev)), _p(fm), _p(mg), _p(ms),
+                                              _p(pk), n, d, h, w, scale_head, scale_next, int(bool(pack_s2d) and scale_next != 0), _FLAVOR["mode"],
+                                              _stream()))
+    return fm, mg, ms, pk
+
+
+def state_views(fm):
+    """(flow (N,6,D,H,W), mask_logit (N,1,D,H,W)) as permuted VIEWS of the channels-last state [N,D,H,W,8]."""
+    return fm[..., :6].permute(0, 4, 1, 2, 3), fm[..., 6:7].permute(0, 4, 1, 2, 3)
 
 
 def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):

@@ -7,9 +7,13 @@ import torch
 
 
 def run_layer(lay, x, residual=None):
-    """lay: ifnet._Layer ; x: [N][D][H][W][Cin_s] fp32 (D = 1 for 2-D) -> y [N][Dy][Hy][Wy][Cout_s]."""
+    """lay: ifnet._Layer ; x: [N][D][H][W][Cin_s] fp32 (D = 1 for 2-D) -> y [N][Dy][Hy][Wy][Cout_s]
+    (always the plain logical layout, also for `out_s2d` layers)."""
     n, di, hi, wi, _ = x.shape
-    d, osp = lay.desc(n, (di, hi, wi), 0)
+    if getattr(lay, "in_s2d", False):       # x is the shifted space-to-depth tensor: desc() wants the logical dims
+        d, osp = lay.desc(n, ((di - 1) * 2 if lay.nd == 3 else 1, (hi - 1) * 2, (wi - 1) * 2), 0)
+    else:
+        d, osp = lay.desc(n, (di, hi, wi), 0)
     y = torch.zeros(n, osp[0], osp[1], osp[2], lay.cout_s)
     w = lay.w_simt.cpu()
     zs, ys, xs = torch.arange(d.Do), torch.arange(d.Ho), torch.arange(d.Wo)

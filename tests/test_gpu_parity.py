@@ -246,6 +246,11 @@ def test_pack_and_head_stages(nd, scale):
     assert float(got[..., 5 + nf:].abs().max()) == 0.0
     gb = ops.pack_block_input(d["img0"], d["img1"], None, None, None, None, scale, _C.BF16)
     assert gb.dtype == torch.bfloat16 and float(gb[..., 2:].float().abs().max()) == 0.0
+    # shifted space-to-depth form of the same tensor (input layout of the stride-2 conv0 on the halo engine)
+    from opticalflowscivis_b200.ifnet import s2d_shift_pack
+    gs = ops.pack_block_input(d["img0"], d["img1"], d["w0"], d["w1"], d["mask"], d["flow"], scale, _C.F32, s2d=True, key="t")
+    want = s2d_shift_pack(got.cpu().unsqueeze(1) if nd == 2 else got.cpu(), nd)
+    assert torch.equal(gs.cpu().view(want.shape), want)
     # head stage
     hs = tuple(s // scale for s in sp)
     head = torch.randn((n,) + hs + (8,), generator=g)
@@ -400,9 +405,13 @@ def test_model_surface():
 
 
 @pytest.mark.parametrize("sh,sn,has_prev", [(4, 2, False), (2, 1, True), (1, 0, True), (1, 1, True), (2, 2, True), (4, 0, False)])
-def test_block_finish_fused_equals_unfused(sh, sn, has_prev):
-    """ofsv_block_finish_3d == head_upsample_add -> warp_blend -> pack_block_input (the unfused, individually verified path)."""
+@pytest.mark.parametrize("s2d", [False, True])
+def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d):
+    """ofsv_block_stage_3d (channels-last state) == head_upsample_add -> warp_blend -> pack_block_input (the unfused,
+    individually verified chain on planar tensors)."""
     from opticalflowscivis_b200 import _C, ops
+    if s2d and sn == 0:
+        pytest.skip("no packed output")
     g = torch.Generator().manual_seed(20 + sh * 3 + sn)
     n, sp = 2, (16, 48, 40)          # H not a multiple of 32, W a multiple of 8: partial tiles in h
     dev = _dev()
@@ -410,21 +419,59 @@ def test_block_finish_fused_equals_unfused(sh, sn, has_prev):
     head = (torch.randn((n,) + tuple(s // sh for s in sp) + (8,), generator=g)).to(dev)
     fprev = (torch.randn((n, 6) + sp, generator=g) * 2).to(dev) if has_prev else None
     mprev = torch.randn((n, 1) + sp, generator=g).to(dev) if has_prev else None
-    flow, mask, mg, ms, pk = ops.block_finish_3d(head, fprev, mprev, img0, img1, sh, sn, True, True)
+    fm_prev = None
+    if has_prev:
+        fm_prev = torch.cat((fprev, mprev, torch.zeros_like(mprev)), 1).permute(0, 2, 3, 4, 1).contiguous()
+    fm, mg, ms, pk = ops.block_stage_3d(head, fm_prev, img0, img1, sh, sn, True, True, pack_s2d=s2d, key="t")
+    flow, mask = ops.state_views(fm)
+    assert flow.shape == (n, 6) + sp and mask.shape == (n, 1) + sp
     rflow, rmask = ops.head_upsample_add(head, fprev, mprev, 3, n, sp, sh)
     w0, w1, rmg, rms = ops.warp_blend(img0, img1, rflow, rmask)
-    assert torch.equal(flow, rflow) and torch.equal(mask, rmask)
+    assert torch.equal(flow, rflow) and torch.equal(mask, rmask) and float(fm[..., 7].abs().max()) == 0.0
     assert float((mg - rmg).abs().max()) <= 1e-6 and float((ms - rms).abs().max()) <= 1e-6
     if sn:
-        rpk = ops.pack_block_input(img0, img1, w0, w1, rmask, rflow, sn, _C.BF16)
+        rpk = ops.pack_block_input(img0, img1, w0, w1, rmask, rflow, sn, _C.BF16, s2d=s2d, key="r")
         assert pk.shape == rpk.shape
         assert float((pk.float() - rpk.float()).abs().max()) <= 1e-2 * float(rpk.float().abs().max())
         assert float((pk.float() - rpk.float()).abs().mean()) <= 1e-5
     else:
         assert pk is None
     # outputs that are not requested are not produced
-    f2, m2, a, b, _ = ops.block_finish_3d(head, fprev, mprev, img0, img1, sh, sn, False, False)
-    assert a is None and b is None and torch.equal(f2, flow) and torch.equal(m2, mask)
+    f2, a, b, _ = ops.block_stage_3d(head, fm_prev, img0, img1, sh, sn, False, False, pack_s2d=s2d, key="t")
+    assert a is None and b is None and torch.equal(f2, fm)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_conv0_space_to_depth_on_halo_engine(nd):
+    """conv0.0 -> conv0.1 of a block in space-to-depth form on ofsv_conv_halo (out_s2d chaining) vs the tap evaluator."""
+    from opticalflowscivis_b200 import _C, ifnet, ops
+    from tap_eval import run_layer
+    torch.manual_seed(17)
+    c, cin = 64, 5 + 2 * nd
+    blk = ifnet.IFBlock(nd, cin, c)
+    blk_dev = ifnet.IFBlock(nd, cin, c).to(_dev())
+    blk_dev.load_state_dict(blk.state_dict())
+    blk.layers(), blk_dev.layers()
+    assert blk._s2d1_ok
+    sp = (1, 48, 40) if nd == 2 else (24, 32, 40)
+    x = (torch.randn((2,) + sp + (16,)) * 0.5).to(torch.bfloat16).float()
+    x[..., cin:] = 0
+    xs = ifnet.s2d_shift_pack(x, nd)
+    r0 = run_layer(blk._s2d0, xs)
+    d0, osp0 = blk_dev._s2d0.desc(2, sp, _C.BF16)
+    y0 = torch.zeros(blk_dev._s2d0.out_shape(2, osp0), device=_dev(), dtype=torch.bfloat16)
+    ops.conv(d0, xs.to(_dev()).to(torch.bfloat16), blk_dev._s2d0.w_tc, blk_dev._s2d0.bias, blk_dev._s2d0.prelu, None, y0, "halo")
+    want0 = ifnet.s2d_shift_pack(r0, nd)
+    got0 = y0.float().cpu().view(want0.shape)
+    assert float((got0 - want0).abs().max()) <= 3e-2 * max(1.0, float(want0.abs().max()))
+    border = want0 == 0
+    assert float(got0[border].abs().max()) <= 3e-2          # padding sub-cells untouched (zero)
+    d1, osp1 = blk_dev._s2d1.desc(2, osp0, _C.BF16)
+    y1 = torch.empty(blk_dev._s2d1.out_shape(2, osp1), device=_dev(), dtype=torch.bfloat16)
+    ops.conv(d1, y0, blk_dev._s2d1.w_tc, blk_dev._s2d1.bias, blk_dev._s2d1.prelu, None, y1, "halo")
+    r1 = run_layer(blk._s2d1, got0)
+    got1 = y1.float().cpu().view(r1.shape)
+    assert float((got1 - r1).abs().max()) <= 3e-2 * max(1.0, float(r1.abs().max()))
 
 
 def test_model3d_fused_equals_unfused():

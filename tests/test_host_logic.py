@@ -41,6 +41,30 @@ def test_conv_tap_form_matches_torch(nd):
 
 
 @pytest.mark.parametrize("nd", [2, 3])
+def test_strided_conv_space_to_depth_form_matches_torch(nd):
+    """Conv(k=3|4, s=2, p=1) == stride-1 {0,1}^nd-tap conv over the shifted space-to-depth input (ifnet._pack_conv_s2d)."""
+    torch.manual_seed(5)
+    cin, cout, k = (9 if nd == 2 else 11), 32, (3 if nd == 2 else 4)
+    m = ifnet._ConvParams(nd, cin, cout, k, 2, 1)
+    pr = ifnet._PReLUParams(cout)
+    pr.weight.data.uniform_(0.1, 0.4)
+    lay = ifnet._pack_conv_s2d(m, pr, 16, out_s2d=False)
+    assert lay.ntaps == 2 ** nd and lay.cin_s == 16 * 2 ** nd and lay.in_stride == 1
+    x = torch.randn((2, cin) + ((12,) * nd))
+    ref = F.prelu((F.conv2d if nd == 2 else F.conv3d)(x, m.weight, m.bias, stride=2, padding=1), pr.weight)
+    xs = ifnet.s2d_shift_pack(_pad_c(_cl(x), 16), nd)
+    assert list(xs.shape[1:]) == ([1] if nd == 2 else [7]) + [7, 7, 16 * 2 ** nd]
+    got = run_layer(lay, xs)
+    assert torch.allclose(got[..., :cout], _cl(ref), atol=1e-4)
+    # chained: conv0.0 (s2d out) -> conv0.1 (s2d in) as in IFBlock
+    m1 = ifnet._ConvParams(nd, cout, 2 * cout, k, 2, 1)
+    lay1 = ifnet._pack_conv_s2d(m1, None, lay.cout_s, out_s2d=False)
+    ref1 = (F.conv2d if nd == 2 else F.conv3d)(ref, m1.weight, m1.bias, stride=2, padding=1)
+    got1 = run_layer(lay1, ifnet.s2d_shift_pack(got, nd))
+    assert torch.allclose(got1[..., :2 * cout], _cl(ref1), atol=2e-4)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
 def test_conv_transpose_phase_form_matches_torch(nd):
     torch.manual_seed(1)
     cin, cout = 6, 5
@@ -116,7 +140,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/ofsv.h but not exported by libofsv.so"
     assert declared == set(_C.EXPORTS), declared ^ set(_C.EXPORTS)
     assert L.ofsv_version().startswith(b"ofsv")
-    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 5
+    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 6
 
 
 def test_validation_errors_launch_nothing():
@@ -126,7 +150,8 @@ def test_validation_errors_launch_nothing():
     assert L.ofsv_warp3d_f32(null, null, null, null, null, null, 1, 1, 4, 4, 4, 0, null) == _C.EINVAL
     assert b"null" in L.ofsv_last_error()
     assert L.ofsv_corr81_fwd_f32(null, null, null, 1, 0, 4, 4, 0.1, 0, 0, null) == _C.EINVAL
-    assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, null) == _C.EINVAL
+    assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, 0, null) == _C.EINVAL
+    assert L.ofsv_block_stage_3d(*([null] * 11), 1, 16, 16, 16, 3, 0, 0, 0, null) == _C.EINVAL
     d = _C.ConvDesc()
     assert L.ofsv_conv_simt(ctypes.byref(d), null, null, null, null, null, null, null) == _C.EINVAL
     with pytest.raises(RuntimeError):
