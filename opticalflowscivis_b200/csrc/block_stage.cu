@@ -25,7 +25,6 @@
 namespace ofsv {
 
 constexpr int BS_H = 32, BS_W = 8;
-constexpr int BS_ROW = BS_W * 8 + 4;   // floats per tile row of the state tile: +16 B so lanes along h hit distinct banks
 constexpr int BS_PKROW = BS_W * 2 + 1; // uint4 per tile row of the packed tile (32 B per voxel + 16 B pad)
 
 struct Lerp1s {
@@ -42,11 +41,6 @@ __device__ __forceinline__ Lerp1s up_index1s(int dst, int n_in, float rscale) {
   L.l1 = fminf(fmaxf(__fsub_rn(src, (float)L.i0), 0.0f), 1.0f);
   L.l0 = __fsub_rn(1.0f, L.l1);
   return L;
-}
-
-__device__ __forceinline__ float4 lerp4(float4 a, float la, float4 b, float lb) {
-  return make_float4(__fadd_rn(__fmul_rn(a.x, la), __fmul_rn(b.x, lb)), __fadd_rn(__fmul_rn(a.y, la), __fmul_rn(b.y, lb)),
-                     __fadd_rn(__fmul_rn(a.z, la), __fmul_rn(b.z, lb)), __fadd_rn(__fmul_rn(a.w, la), __fmul_rn(b.w, lb)));
 }
 
 __device__ __forceinline__ uint32_t bs_pack2(float a, float b) {
@@ -67,17 +61,29 @@ struct StagePtrs {
   float* fm_out; float* merged; float* mask_sig; __nv_bfloat16* pack_out;
 };
 
+// c0*l0 + c1*l1 per component (the product c0*l0 rounded, then one FMA — the same expression in head_upsample_add_kernel)
+__device__ __forceinline__ float4 lerp4(float4 a, float la, float4 b, float lb) {
+  return make_float4(__fmaf_rn(b.x, lb, __fmul_rn(a.x, la)), __fmaf_rn(b.y, lb, __fmul_rn(a.y, la)),
+                     __fmaf_rn(b.z, lb, __fmul_rn(a.z, la)), __fmaf_rn(b.w, lb, __fmul_rn(a.w, la)));
+}
+
+// SH: scale of the head (1, 2, 4), or 0 = the state is already accumulated (fm_prev holds flow/mask, nothing is added and
+// fm_out is not written: the warp/blend-only pass after a head conv whose epilogue did `fm = fm_prev + head`).
 template <int SH, int SN, bool S2D, bool FMA>
 __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
   constexpr int TDZ = SN == 2 ? 2 : 1;
-  __shared__ __align__(16) float s_fm[BS_H * BS_ROW];
+  constexpr int FROW = BS_W * 4 + 4;                       // floats per tile row of each half-state tile (+16 B pad)
+  __shared__ __align__(16) float s_fa[BS_H * FROW];        // flow 0..3
+  __shared__ __align__(16) float s_fb[BS_H * FROW];        // flow 4,5, mask, 0
   __shared__ float s_img[2][BS_H][BS_W + 1];
   __shared__ float s_out[2][BS_H][BS_W + 1];
   __shared__ __align__(16) uint4 s_pk[SN == 1 ? BS_H * BS_PKROW : 1];
   __shared__ float s_pool[SN == 2 ? 2 * 11 : 1][BS_H][BS_W + 1];
+  __shared__ int s_li[SH > 1 ? 2 * (BS_H + BS_W + TDZ) : 1];      // i0, i1 element offsets of the head taps per tile row / col / plane
+  __shared__ float s_ll[SH > 1 ? 2 * (BS_H + BS_W + TDZ) : 1];    // l0, l1
 
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
-  const int64_t V = (int64_t)D * HW;
+  const int V = D * HW;                                     // < 2^28 (host check): 32-bit offsets inside one sample
   const int nzb = D / TDZ;
   const int n = blockIdx.z / nzb, d0 = (blockIdx.z - n * nzb) * TDZ;
   const int h0 = blockIdx.y * BS_H, w0 = blockIdx.x * BS_W;
@@ -86,92 +92,107 @@ __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs 
   const int lane = tid & 31, wl = tid >> 5;
   const int hB = h0 + lane, wB = w0 + wl;
   const bool okB = hB < H && wB < W;
-  // phase A/C mapping of the planar tiles: 8 consecutive threads = one 32 B row segment
+  // phase A/C mapping: 8 consecutive threads = one tile row (8 voxels = 256 B of state, 32 B of a planar volume)
   const int rP = tid >> 3, cP = tid & 7;
   const bool okP = (h0 + rP) < H && (w0 + cP) < W;
-  const int Dh = D / SH, Hh = H / SH, Wh = W / SH;
+  constexpr int SHD = SH > 1 ? SH : 1;
+  const int Dh = D / SHD, Hh = H / SHD, Wh = W / SHD;
   const float* hb = q.head + (int64_t)n * Dh * Hh * Wh * 8;
-  const bool has_prev = q.fm_prev != nullptr;
+  const float* fprev = q.fm_prev ? q.fm_prev + (int64_t)n * V * 8 : nullptr;
+  float* fout = q.fm_out + (int64_t)n * V * 8;
+  const float* i0p = q.img0 + (int64_t)n * V;
+  const float* i1p = q.img1 + (int64_t)n * V;
+  const bool has_prev = fprev != nullptr;
   const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+
+  if (SH > 1) {
+    // per-axis tap tables of F.interpolate(scale_factor = SH, align_corners = False) for this tile
+    constexpr int NT = BS_H + BS_W + TDZ;
+    if (tid < NT) {
+      int dst, n_in, stride;
+      if (tid < BS_H) { dst = h0 + tid; n_in = Hh; stride = Wh * 8; }
+      else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 8; }
+      else { dst = d0 + tid - BS_H - BS_W; n_in = Dh; stride = Hh * Wh * 8; }
+      const Lerp1s L = up_index1s(dst, n_in, 1.0f / (float)SHD);
+      s_li[2 * tid] = L.i0 * stride; s_li[2 * tid + 1] = L.i1 * stride;
+      s_ll[2 * tid] = L.l0; s_ll[2 * tid + 1] = L.l1;
+    }
+    __syncthreads();
+  }
 
 #pragma unroll
   for (int dz = 0; dz < TDZ; ++dz) {
     const int d = d0 + dz;
-    const int64_t plane = (int64_t)n * V + (int64_t)d * HW;
+    const int plane = d * HW;
+    const int gP = plane + (h0 + rP) * W + w0 + cP;        // voxel offset of this thread's phase A/C voxel
     if (dz > 0) __syncthreads();
-    // ---------------- phase A: state update, two threads per voxel, 16 B each
+    // ---------------- phase A: state update, one voxel (32 B) per thread
     if (SN != 0) {
-      const int64_t g = plane + (int64_t)(h0 + rP) * W + w0 + cP;
-      s_img[0][rP][cP] = okP ? ldg_stream(q.img0 + g) : 0.0f;
-      s_img[1][rP][cP] = okP ? ldg_stream(q.img1 + g) : 0.0f;
+      s_img[0][rP][cP] = okP ? ldg_stream(i0p + gP) : 0.0f;
+      s_img[1][rP][cP] = okP ? ldg_stream(i1p + gP) : 0.0f;
     }
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int i = it * 256 + tid;
-      const int half = i & 1, vox = i >> 1;
-      const int wl_a = vox & 7, hl_a = vox >> 3;
-      const int h = h0 + hl_a, w = w0 + wl_a;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (h < H && w < W) {
-        const int64_t g = ((plane + (int64_t)h * W + w) << 3) + half * 4;
-        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_prev) pv = ldg_stream4(q.fm_prev + g);
-        float4 v;
-        if (SH == 1) {
-          v = ldg_stream4(hb + ((((int64_t)d * H + h) * W + w) << 3) + half * 4);
+    {
+      float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+      if (okP) {
+        float4 pa = oa, pb = oa;
+        if (has_prev) { pa = ldg_stream4(fprev + gP * 8); pb = ldg_stream4(fprev + gP * 8 + 4); }
+        if (SH == 0) {
+          oa = pa; ob = pb;
         } else {
-          const float rs = 1.0f / (float)SH;
-          const Lerp1s lx = up_index1s(w, Wh, rs), ly = up_index1s(h, Hh, rs), lz = up_index1s(d, Dh, rs);
-          float4 az[2];
+          float4 va, vb;
+          if (SH == 1) {
+            va = ldg_stream4(hb + gP * 8); vb = ldg_stream4(hb + gP * 8 + 4);
+          } else {
+            const int ty = rP, tx = BS_H + cP, tz = BS_H + BS_W + dz;
+            const int y0 = s_li[2 * ty], y1 = s_li[2 * ty + 1], x0 = s_li[2 * tx], x1 = s_li[2 * tx + 1];
+            const int z0 = s_li[2 * tz], z1 = s_li[2 * tz + 1];
+            const float ly0 = s_ll[2 * ty], ly1 = s_ll[2 * ty + 1], lx0 = s_ll[2 * tx], lx1 = s_ll[2 * tx + 1];
+            const float lz0 = s_ll[2 * tz], lz1 = s_ll[2 * tz + 1];
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const int zz = a ? lz.i1 : lz.i0;
-            float4 ay[2];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const int yy = b ? ly.i1 : ly.i0;
-              const float* r = hb + (((int64_t)zz * Hh + yy) * Wh) * 8 + half * 4;
-              const float4 c0 = __ldg(reinterpret_cast<const float4*>(r + lx.i0 * 8));
-              const float4 c1 = __ldg(reinterpret_cast<const float4*>(r + lx.i1 * 8));
-              ay[b] = lerp4(c0, lx.l0, c1, lx.l1);
+            for (int half = 0; half < 2; ++half) {
+              const float* r = hb + half * 4;
+              auto L4 = [&](int o) { return __ldg(reinterpret_cast<const float4*>(r + o)); };
+              const float4 a00 = lerp4(L4(z0 + y0 + x0), lx0, L4(z0 + y0 + x1), lx1);
+              const float4 a01 = lerp4(L4(z0 + y1 + x0), lx0, L4(z0 + y1 + x1), lx1);
+              const float4 a10 = lerp4(L4(z1 + y0 + x0), lx0, L4(z1 + y0 + x1), lx1);
+              const float4 a11 = lerp4(L4(z1 + y1 + x0), lx0, L4(z1 + y1 + x1), lx1);
+              const float4 v = lerp4(lerp4(a00, ly0, a01, ly1), lz0, lerp4(a10, ly0, a11, ly1), lz1);
+              if (half == 0) va = v; else vb = v;
             }
-            az[a] = lerp4(ay[0], ly.l0, ay[1], ly.l1);
           }
-          v = lerp4(az[0], lz.l0, az[1], lz.l1);
+          const float sh = (float)SHD;
+          if (has_prev) {
+            oa = make_float4(__fadd_rn(pa.x, __fmul_rn(va.x, sh)), __fadd_rn(pa.y, __fmul_rn(va.y, sh)),
+                             __fadd_rn(pa.z, __fmul_rn(va.z, sh)), __fadd_rn(pa.w, __fmul_rn(va.w, sh)));
+            ob = make_float4(__fadd_rn(pb.x, __fmul_rn(vb.x, sh)), __fadd_rn(pb.y, __fmul_rn(vb.y, sh)), __fadd_rn(pb.z, vb.z), 0.0f);
+          } else {   // block 0: flow = flow_d exactly
+            oa = make_float4(__fmul_rn(va.x, sh), __fmul_rn(va.y, sh), __fmul_rn(va.z, sh), __fmul_rn(va.w, sh));
+            ob = make_float4(__fmul_rn(vb.x, sh), __fmul_rn(vb.y, sh), vb.z, 0.0f);
+          }
+          stg_stream4(fout + gP * 8, oa);
+          stg_stream4(fout + gP * 8 + 4, ob);
         }
-        const float sh = (float)SH;
-        if (half == 0) {
-          o.x = __fadd_rn(pv.x, __fmul_rn(v.x, sh)); o.y = __fadd_rn(pv.y, __fmul_rn(v.y, sh));
-          o.z = __fadd_rn(pv.z, __fmul_rn(v.z, sh)); o.w = __fadd_rn(pv.w, __fmul_rn(v.w, sh));
-        } else {
-          o.x = __fadd_rn(pv.x, __fmul_rn(v.x, sh)); o.y = __fadd_rn(pv.y, __fmul_rn(v.y, sh));
-          o.z = __fadd_rn(pv.z, v.z); o.w = 0.0f;
-        }
-        if (!has_prev) {   // block 0: flow = flow_d exactly (no "+ 0" so -0.0 / rounding match the unfused path)
-          if (half == 0) o = make_float4(__fmul_rn(v.x, sh), __fmul_rn(v.y, sh), __fmul_rn(v.z, sh), __fmul_rn(v.w, sh));
-          else o = make_float4(__fmul_rn(v.x, sh), __fmul_rn(v.y, sh), v.z, 0.0f);
-        }
-        stg_stream4(q.fm_out + g, o);
       }
-      *reinterpret_cast<float4*>(&s_fm[hl_a * BS_ROW + wl_a * 8 + half * 4]) = o;
+      *reinterpret_cast<float4*>(&s_fa[rP * FROW + cP * 4]) = oa;
+      *reinterpret_cast<float4*>(&s_fb[rP * FROW + cP * 4]) = ob;
     }
     __syncthreads();
     // ---------------- phase B: warps / blend, one voxel per thread, lanes along h
     if (okB) {
-      const float4 fa = *reinterpret_cast<const float4*>(&s_fm[lane * BS_ROW + wl * 8]);
-      const float4 fb = *reinterpret_cast<const float4*>(&s_fm[lane * BS_ROW + wl * 8 + 4]);
+      const float4 fa = *reinterpret_cast<const float4*>(&s_fa[lane * FROW + wl * 4]);
+      const float4 fb = *reinterpret_cast<const float4*>(&s_fb[lane * FROW + wl * 4]);
       const float m = fb.z;
       const float lh = __ldg(q.lin_h + hB), ld = __ldg(q.lin_d + d), lw = __ldg(q.lin_w + wB);
       const Trilin t0 = trilin_setup(fa.x, fa.y, fa.z, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
       const Trilin t1 = trilin_setup(fa.w, fb.x, fb.y, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-      const float a = trilin_sample<FMA>(q.img0 + (int64_t)n * V, t0, W, HW);
-      const float b = trilin_sample<FMA>(q.img1 + (int64_t)n * V, t1, W, HW);
+      const float a = trilin_sample<FMA>(i0p, t0, W, HW);
+      const float b = trilin_sample<FMA>(i1p, t1, W, HW);
       float ms = 0.0f, mg = 0.0f;
       if (need_m) {
         ms = sigmoidf_ref(m);
         mg = __fadd_rn(__fmul_rn(a, ms), __fmul_rn(b, __fsub_rn(1.0f, ms)));
+        s_out[0][lane][wl] = mg; s_out[1][lane][wl] = ms;
       }
-      s_out[0][lane][wl] = mg; s_out[1][lane][wl] = ms;
       if (SN == 1) {
         const float i0v = s_img[0][lane][wl], i1v = s_img[1][lane][wl];
         uint4 lo, hi;
@@ -185,24 +206,16 @@ __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs 
         for (int c = 0; c < 11; ++c) s_pool[dz * 11 + c][lane][wl] = c11[c];
       }
     }
-    __syncthreads();
+    if (need_m || SN == 1) __syncthreads();
     // ---------------- phase C: coalesced stores
     if (okP) {
-      const int64_t g = plane + (int64_t)(h0 + rP) * W + w0 + cP;
+      const int64_t g = (int64_t)n * V + gP;
       if (q.merged) q.merged[g] = s_out[0][rP][cP];
       if (q.mask_sig) q.mask_sig[g] = s_out[1][rP][cP];
-    }
-    if (SN == 1) {
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int i = it * 256 + tid;
-        const int half = i & 1, vox = i >> 1;
-        const int wl_a = vox & 7, hl_a = vox >> 3;
-        const int h = h0 + hl_a, w = w0 + wl_a;
-        if (h < H && w < W) {
-          const int64_t off = pack_row_off<S2D>(n, d, h, w, D, H, W) + half * 8;
-          *reinterpret_cast<uint4*>(q.pack_out + off) = s_pk[hl_a * BS_PKROW + wl_a * 2 + half];
-        }
+      if (SN == 1) {
+        uint4* o = reinterpret_cast<uint4*>(q.pack_out + pack_row_off<S2D>(n, d, h0 + rP, w0 + cP, D, H, W));
+        o[0] = s_pk[rP * BS_PKROW + cP * 2];
+        o[1] = s_pk[rP * BS_PKROW + cP * 2 + 1];
       }
     }
   }
@@ -246,18 +259,20 @@ extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, cons
                                    const float* lin_h, const float* lin_d, const float* lin_w, float* fm_out, float* merged,
                                    float* mask_sig, void* pack_out, int N, int D, int H, int W, int scale_head,
                                    int scale_next, int pack_s2d, int ref_mode, void* stream) {
-  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < (1ll << 31), "ofsv_block_stage_3d: bad shape");
-  OFSV_REQUIRE(scale_head == 1 || scale_head == 2 || scale_head == 4, "ofsv_block_stage_3d: scale_head %d not in {1,2,4}", scale_head);
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < (1ll << 28), "ofsv_block_stage_3d: bad shape (D*H*W must be < 2^28)");
+  OFSV_REQUIRE(scale_head == 0 || scale_head == 1 || scale_head == 2 || scale_head == 4, "ofsv_block_stage_3d: scale_head %d not in {0,1,2,4}", scale_head);
   OFSV_REQUIRE(scale_next == 0 || scale_next == 1 || scale_next == 2, "ofsv_block_stage_3d: scale_next %d not in {0,1,2}", scale_next);
-  OFSV_REQUIRE(D % scale_head == 0 && H % scale_head == 0 && W % scale_head == 0, "ofsv_block_stage_3d: dims must be multiples of scale_head");
+  OFSV_REQUIRE(scale_head == 0 || (D % scale_head == 0 && H % scale_head == 0 && W % scale_head == 0), "ofsv_block_stage_3d: dims must be multiples of scale_head");
   OFSV_REQUIRE(scale_next != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ofsv_block_stage_3d: dims must be even for scale_next = 2");
   OFSV_REQUIRE(!pack_s2d || (scale_next != 0 && D % (2 * scale_next) == 0 && H % (2 * scale_next) == 0 && W % (2 * scale_next) == 0),
                "ofsv_block_stage_3d: space-to-depth packing needs dims that are multiples of 2*scale_next");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_block_stage_3d: bad ref_mode");
   if (N == 0) return OFSV_OK;
-  OFSV_REQUIRE(head && img0 && img1 && lin_h && lin_d && lin_w && fm_out, "ofsv_block_stage_3d: null pointer");
+  OFSV_REQUIRE(img0 && img1 && lin_h && lin_d && lin_w, "ofsv_block_stage_3d: null pointer");
+  if (scale_head == 0) OFSV_REQUIRE(fm_prev && !head && !fm_out, "ofsv_block_stage_3d: scale_head = 0 takes the accumulated state in fm_prev (head and fm_out must be NULL)");
+  else OFSV_REQUIRE(head && fm_out, "ofsv_block_stage_3d: null pointer");
   OFSV_REQUIRE((scale_next == 0) == (pack_out == nullptr), "ofsv_block_stage_3d: pack_out must be given iff scale_next != 0");
-  OFSV_REQUIRE(aligned16(head) && aligned16(fm_out) && (!fm_prev || aligned16(fm_prev)) && (!pack_out || aligned16(pack_out)),
+  OFSV_REQUIRE((!head || aligned16(head)) && (!fm_out || aligned16(fm_out)) && (!fm_prev || aligned16(fm_prev)) && (!pack_out || aligned16(pack_out)),
                "ofsv_block_stage_3d: head / fm / pack_out must be 16-byte aligned");
   const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
   const int tdz = scale_next == 2 ? 2 : 1;
@@ -278,7 +293,7 @@ extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, cons
     else if (scale_next == 1) { if (s2d) GO3(SH, 1, true); else GO3(SH, 1, false); }                   \
     else { if (s2d) GO3(SH, 2, true); else GO3(SH, 2, false); }                                        \
   } while (0)
-  if (scale_head == 1) GO(1); else if (scale_head == 2) GO(2); else GO(4);
+  if (scale_head == 0) GO(0); else if (scale_head == 1) GO(1); else if (scale_head == 2) GO(2); else GO(4);
 #undef GO
 #undef GO3
   return check_launch("block_stage_3d_kernel");

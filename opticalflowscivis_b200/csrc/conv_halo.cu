@@ -230,7 +230,24 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           return ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy + ox * p.out_stride + px) * p.Cout_s;
         };
         uint4 rnext[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.has_residual && valid_xy && half < nitems) {
+        const bool res_bf16 = p.has_residual && !p.shuffle, res_f32 = p.has_residual && p.shuffle;
+        // depth-to-space heads: element offset of output parity ph (z,y,x bits) of slice j, row (oy, ox)
+        auto shuf_off = [&](int j, int ph) -> int64_t {
+          const int oz = tz * p.td + j;
+          return ((((int64_t)n * p.Dy + oz * 2 + ((ph >> 2) & 1)) * p.Hy + oy * 2 + ((ph >> 1) & 1)) * p.Wy + ox * 2 + (ph & 1)) * p.Cout_s;
+        };
+        const float* resf = reinterpret_cast<const float*>(residual);
+        float4 fnext[4];
+        auto load_state = [&](int it) {       // fp32 state rows (fm_prev) of the two parities of chunk `it`
+          const int j = it / nch, c0 = (it - j * nch) << 4;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float4* r = reinterpret_cast<const float4*>(resf + shuf_off(j, (c0 >> 3) + e));
+            fnext[2 * e] = __ldg(r); fnext[2 * e + 1] = __ldg(r + 1);
+          }
+        };
+        if (res_f32 && valid_xy && half < nitems) load_state(half);
+        if (res_bf16 && valid_xy && half < nitems) {
           const __nv_bfloat16* rp = resb + row_off(half / nch) + (half % nch) * 16;
           rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
         }
@@ -241,7 +258,13 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         for (int it = half; it < ((p.dbg_flags & 1) ? 0 : nitems); it += 2) {
           const int j = it / nch, c0 = (it - j * nch) << 4;
           const uint4 rcur0 = rnext[0], rcur1 = rnext[1];
-          if (p.has_residual && valid_xy && it + 2 < nitems) {       // prefetch the next chunk's residual row
+          float4 fcur[4];
+          if (res_f32) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) fcur[e] = fnext[e];
+            if (valid_xy && it + 2 < nitems) load_state(it + 2);
+          }
+          if (res_bf16 && valid_xy && it + 2 < nitems) {       // prefetch the next chunk's residual row
             const int jn = (it + 2) / nch;
             const __nv_bfloat16* rp = resb + row_off(jn) + ((it + 2) - jn * nch) * 16;
             rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
@@ -254,7 +277,14 @@ __global__ void __launch_bounds__(H_THREADS, 1)
             const float a = v[e] + sBias[c0 + e];
             v[e] = a > 0.0f ? a : a * sPrelu[c0 + e];
           }
-          if (p.has_residual) {
+          if (res_f32) {            // flow/mask state accumulation: fm = fm_prev + head (Flow-3D/model/IFNet.py:169-170)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[4 * e] = __fadd_rn(fcur[e].x, v[4 * e]); v[4 * e + 1] = __fadd_rn(fcur[e].y, v[4 * e + 1]);
+              v[4 * e + 2] = __fadd_rn(fcur[e].z, v[4 * e + 2]); v[4 * e + 3] = __fadd_rn(fcur[e].w, v[4 * e + 3]);
+            }
+          }
+          if (res_bf16) {
             const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&rcur0);
             const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&rcur1);
 #pragma unroll
@@ -265,12 +295,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           }
           if (p.shuffle) {
             // depth-to-space heads: columns = [output parity (z,y,x)][8 channels]; this chunk holds parities c0/8 and c0/8+1
-            const int oz = tz * p.td + j;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int ph = (c0 >> 3) + e;
-              const int64_t yo = ((((int64_t)n * p.Dy + oz * 2 + ((ph >> 2) & 1)) * p.Hy + oy * 2 + ((ph >> 1) & 1)) * p.Wy +
-                                  ox * 2 + (ph & 1)) * p.Cout_s;
+              const int64_t yo = shuf_off(j, (c0 >> 3) + e);
               if (p.out_f32) {
                 float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + yo);
                 o[0] = make_float4(v[8 * e], v[8 * e + 1], v[8 * e + 2], v[8 * e + 3]);
@@ -369,8 +396,9 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: activations must be bf16"); return OFSV_ENOSUP; }
   if (d->in_stride != 1) { set_error("ofsv_conv_halo: in_stride must be 1"); return OFSV_ENOSUP; }
   if (d->Cout_w > 128) { set_error("ofsv_conv_halo: Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
-  if (d->has_residual && d->out_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: residual needs a bf16 output"); return OFSV_ENOSUP; }
-  if (d->out_shuffle && (d->out_shuffle != 8 || d->nphase != 1 || d->Cout_w != 8 * (1 << d->nd) || d->Cout_s != 8 || d->has_residual)) {
+  if (d->has_residual && d->out_dtype != OFSV_BF16 && !d->out_shuffle) { set_error("ofsv_conv_halo: residual needs a bf16 output"); return OFSV_ENOSUP; }
+  if (d->has_residual && d->out_shuffle && d->out_dtype != OFSV_F32) { set_error("ofsv_conv_halo: depth-to-space residual (flow/mask state) is fp32"); return OFSV_ENOSUP; }
+  if (d->out_shuffle && (d->out_shuffle != 8 || d->nphase != 1 || d->Cout_w != 8 * (1 << d->nd) || d->Cout_s != 8)) {
     set_error("ofsv_conv_halo: bad depth-to-space configuration");
     return OFSV_EINVAL;
   }

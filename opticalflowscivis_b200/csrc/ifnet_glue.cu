@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(256)
           ld8(hb + (((int64_t)zz * Hh + yy) * Wh + lx.i0) * Cs, c0);
           ld8(hb + (((int64_t)zz * Hh + yy) * Wh + lx.i1) * Cs, c1);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) acc_y[dy][c] = __fadd_rn(__fmul_rn(c0[c], lx.l0), __fmul_rn(c1[c], lx.l1));
+          for (int c = 0; c < NC; ++c) acc_y[dy][c] = __fmaf_rn(c1[c], lx.l1, __fmul_rn(c0[c], lx.l0));
         }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc_z[dz][c] = __fadd_rn(__fmul_rn(acc_y[0][c], ly.l0), __fmul_rn(acc_y[1][c], ly.l1));
+        for (int c = 0; c < NC; ++c) acc_z[dz][c] = __fmaf_rn(acc_y[1][c], ly.l1, __fmul_rn(acc_y[0][c], ly.l0));
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c)
-        v[c] = ND == 3 ? __fadd_rn(__fmul_rn(acc_z[0][c], lz.l0), __fmul_rn(acc_z[1][c], lz.l1)) : acc_z[0][c];
+        v[c] = ND == 3 ? __fmaf_rn(acc_z[1][c], lz.l1, __fmul_rn(acc_z[0][c], lz.l0)) : acc_z[0][c];
     }
 #pragma unroll
     for (int c = 0; c < NF; ++c) {

@@ -281,9 +281,14 @@ class IFBlock(nn.Module):
             self._packed, self._packed_key = L, key
         return self._packed
 
-    def run(self, xin, n, in_sp, act_dtype, engine, s2d_in=False):
+    def can_accumulate_state(self, engine):
+        """True when the final heads run as the depth-to-space conv whose epilogue can do `fm = fm_prev + head`."""
+        return engine == "tc" and USE_HALO and USE_SHUFFLE_HEADS
+
+    def run(self, xin, n, in_sp, act_dtype, engine, s2d_in=False, state_prev=None):
         """xin: packed channels-last block input [N][in_sp][16] (or its shifted space-to-depth form when s2d_in).
-        Returns head [N][in_sp][8] fp32."""
+        Returns head [N][in_sp][8] fp32 — or, with `state_prev` ([N][in_sp][8] fp32 flow/mask state, scale-1 block only),
+        the accumulated state state_prev + head written by the head conv's epilogue."""
         L = self.layers()
         tdt = torch.float32 if act_dtype == _C.F32 else torch.bfloat16
         x, sp, skip = xin, in_sp, None
@@ -296,12 +301,16 @@ class IFBlock(nn.Module):
             elif s2d_in and li == 1 and self._s2d1_ok:
                 lay = self._s2d1
             d, osp = lay.desc(n, sp, act_dtype)
+            if li == 11 and state_prev is not None:
+                if not lay.shuffle:
+                    raise RuntimeError("state accumulation needs the depth-to-space head conv")
+                d.has_residual = 1
             odt = torch.float32 if lay.out_f32 else tdt
             if lay.out_s2d:
                 y = ops.workspace(("conv0", id(self)), lay.out_shape(n, osp), odt, x.device)
             else:
                 y = torch.empty(lay.out_shape(n, osp), device=x.device, dtype=odt)
-            res = skip if lay.residual else None
+            res = skip if lay.residual else (state_prev if (li == 11 and state_prev is not None) else None)
             if eng == "tc" and USE_HALO and lay.in_stride == 1 and not getattr(lay, "no_halo", False):
                 # stride-1 layers: halo-reuse kernel; layers it cannot hold in shared memory use the per-tap kernel
                 try:
@@ -338,6 +347,7 @@ class IFNet(nn.Module):
         self.block_tea = IFBlock(nd, 6 + nf, c=64)      # teacher: training only (§8f), kept for state_dict parity
         self.set_precision(precision, engine)
         self.only_last = False
+        self.fuse_state_accumulate = True # scale-1 block: `flow += flow_d, mask += mask_d` inside the head conv's epilogue
         self.fuse_output_stage = True     # 3-D bf16: ofsv_block_stage_3d instead of head_upsample_add + warp_blend + pack
 
     def set_precision(self, precision: str, engine: str = "auto"):
@@ -387,12 +397,18 @@ class IFNet(nn.Module):
             if xin is None:
                 xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, s, act, s2d=s2d)
             in_sp = tuple(v // s for v in sp)
-            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng, s2d_in=s2d)
+            # scale-1 block on the halo engine: the head conv's epilogue accumulates the state (fm = fm_prev + head)
+            acc_state = fused and s == 1 and fm is not None and self.fuse_state_accumulate and blk.can_accumulate_state(eng)
+            head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng, s2d_in=s2d,
+                           state_prev=fm if acc_state else None)
             xin = None
             if fused:
                 # one pass over the channels-last state: resize + accumulate + warp x2 (+ blend) (+ the next block's input)
                 s_next = 0 if last else (scales[i + 1] if scales[i + 1] in (1, 2) else 0)
-                fm, mg, ms, xin = ops.block_stage_3d(head, fm, img0, img1, s, s_next, want_out, want_out, pack_s2d=s2d)
+                if acc_state:
+                    fm, mg, ms, xin = ops.block_stage_3d(None, head, img0, img1, 0, s_next, want_out, want_out, pack_s2d=s2d)
+                else:
+                    fm, mg, ms, xin = ops.block_stage_3d(head, fm, img0, img1, s, s_next, want_out, want_out, pack_s2d=s2d)
                 flow, mask = ops.state_views(fm)
                 if not last and xin is None:          # next scale not fusable (4): fall back to the separate builder
                     flow, mask = flow.contiguous(), mask.contiguous()

@@ -288,14 +288,18 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
 
 def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merged, want_mask, pack_s2d=False, key="xin"):
     """Fused 3-D block output stage on the channels-last state (ofsv_block_stage_3d).  head [N][D/sh][H/sh][W/sh][8] fp32,
-    fm_prev [N][D][H][W][8] fp32 or None.  Returns (fm, merged|None, mask_sig|None, next_block_input|None)."""
+    fm_prev [N][D][H][W][8] fp32 or None.  scale_head = 0: fm_prev already holds the accumulated state (the head conv's
+    epilogue added the head), only warp / blend / pack run.  Returns (fm, merged|None, mask_sig|None, next_block_input|None)."""
     n, _, d, h, w = img0.shape
     dev = img0.device
-    if head.dtype != torch.float32 or head.shape[-1] != 8 or not head.is_contiguous():
+    if scale_head == 0:
+        if head is not None or fm_prev is None:
+            raise ValueError("block_stage_3d: scale_head = 0 takes the already accumulated state in fm_prev and no head")
+    elif head.dtype != torch.float32 or head.shape[-1] != 8 or not head.is_contiguous():
         raise ValueError("block_stage_3d: head must be a contiguous fp32 [...,8] tensor")
     if fm_prev is not None and (fm_prev.shape != (n, d, h, w, 8) or fm_prev.dtype != torch.float32 or not fm_prev.is_contiguous()):
         raise ValueError("block_stage_3d: fm_prev must be a contiguous fp32 [N,D,H,W,8] tensor")
-    fm = torch.empty((n, d, h, w, 8), device=dev, dtype=torch.float32)
+    fm = torch.empty((n, d, h, w, 8), device=dev, dtype=torch.float32) if scale_head else None
     mg = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_merged else None
     ms = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_mask else None
     pk = None
@@ -310,7 +314,7 @@ def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merge
                                               _p(linspace_table(d, dev)), _p(linspace_table(w, dev)), _p(fm), _p(mg), _p(ms),
                                               _p(pk), n, d, h, w, scale_head, scale_next, int(bool(pack_s2d) and scale_next != 0), _FLAVOR["mode"],
                                               _stream()))
-    return fm, mg, ms, pk
+    return (fm if scale_head else fm_prev), mg, ms, pk
 
 
 def state_views(fm):

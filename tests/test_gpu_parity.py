@@ -71,6 +71,20 @@ def test_warp3d_vs_c_oracle(shape):
     assert d <= WARP_TOL, d
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 64, 64, 64), (1, 2, 20, 36, 52), (1, 1, 33, 31, 35), (1, 1, 16, 24, 32)])
+def test_warp3d_bit_exact_vs_c_oracle(shape):
+    """The CPU-flavour arithmetic (incl. the Markstein constant division of norm_flow) is BIT-identical to the reference's."""
+    from opticalflowscivis_b200 import ops
+    from oracle import c_oracle as co
+    g = torch.Generator().manual_seed(66)
+    src = torch.rand(shape, generator=g)
+    flow = torch.randn((shape[0], 3) + shape[2:], generator=g) * 5
+    flow[0, :, 0, 0, :4] = torch.tensor([0.0, 1e-30, 3e6, -2.5])[None, :]      # slow-path operands
+    got = _np(ops.warp3d(src.to(_dev()), flow.to(_dev())))
+    ref = co.warp3d(src.numpy(), flow.numpy())
+    assert np.array_equal(got, ref), float(np.abs(got - ref).max())
+
+
 def test_warp3d_cuda_flavor_matches_reference_cuda_eager():
     """ref_mode CUDA reproduces the reference's own CUDA-eager arithmetic (ATen's reciprocal-multiply division)."""
     import opticalflowscivis_b200 as o
@@ -439,6 +453,9 @@ def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d):
     # outputs that are not requested are not produced
     f2, a, b, _ = ops.block_stage_3d(head, fm_prev, img0, img1, sh, sn, False, False, pack_s2d=s2d, key="t")
     assert a is None and b is None and torch.equal(f2, fm)
+    # scale_head = 0: the state is already accumulated (head-conv epilogue did fm_prev + head); same warps / blend / pack
+    f3, mg3, ms3, pk3 = ops.block_stage_3d(None, fm, img0, img1, 0, sn, True, True, pack_s2d=s2d, key="t3")
+    assert f3 is fm and torch.equal(mg3, mg) and torch.equal(ms3, ms) and (pk is None or torch.equal(pk3, pk))
 
 
 @pytest.mark.parametrize("nd", [2, 3])
@@ -486,6 +503,10 @@ def test_model3d_fused_equals_unfused():
     assert float((a[0] - b[0]).abs().max()) <= 1e-5
     for i in range(3):
         assert float((a[1][i] - b[1][i]).abs().max()) <= 1e-4
+    m.flownet.fuse_output_stage, m.flownet.fuse_state_accumulate = True, False      # state accumulated by block_stage instead
+    e = m.inference(img0.to(_dev()), img1.to(_dev()))
+    assert torch.equal(a[0], e[0]) and all(torch.equal(a[1][i], e[1][i]) for i in range(3))
+    m.flownet.fuse_state_accumulate = True
     # scale lists other than [4,2,1] (`scale=[1,1,1]` is the reference's commented alternative)
     m.flownet.fuse_output_stage = True
     c = m.inference(img0.to(_dev()), img1.to(_dev()), scale_list=[2, 4, 1])
