@@ -67,25 +67,57 @@ __device__ __forceinline__ float4 lerp4(float4 a, float la, float4 b, float lb) 
                      __fmaf_rn(b.z, lb, __fmul_rn(a.z, la)), __fmaf_rn(b.w, lb, __fmul_rn(a.w, la)));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int BS_NST = 3;                    // cp.async stages (planes in flight per CTA)
+constexpr int BS_DZ = 8;                     // d planes walked by one CTA
+constexpr int BS_FROW = BS_W * 4 + 4;        // floats per tile row of a half-state tile (+16 B pad: lanes along h hit distinct banks)
+constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile
+
+// shared-memory carve-up (bytes) — must match the kernel
+__host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
+  return BS_NST * 2 * BS_HALF * 4                       // s_fa, s_fb   (prev state, updated in place)
+         + (SH == 1 ? BS_NST * 2 * BS_HALF * 4 : 0)     // s_ha, s_hb   (full-resolution head tiles)
+         + BS_NST * 2 * BS_H * (BS_W + 1) * 4           // s_img
+         + 2 * BS_H * (BS_W + 1) * 4                    // s_out
+         + (SN == 1 ? BS_H * BS_PKROW * 16 : 0)         // s_pk
+         + (SN == 2 ? 22 * BS_H * (BS_W + 1) * 4 : 0)   // s_pool
+         + 4 * (BS_H + BS_W + BS_DZ) * 4;               // tap tables
+}
+
 // SH: scale of the head (1, 2, 4), or 0 = the state is already accumulated (fm_prev holds flow/mask, nothing is added and
 // fm_out is not written: the warp/blend-only pass after a head conv whose epilogue did `fm = fm_prev + head`).
+//
+// One CTA walks BS_DZ consecutive d planes of its 32(h) x 8(w) tile.  The streaming inputs of plane p+2 (previous state,
+// full-resolution head, the voxel's own img0/img1 values) are in flight as cp.async copies while plane p is processed, so
+// the only exposed latencies are the data-dependent gathers of phase B (hidden by the other resident CTAs).
 template <int SH, int SN, bool S2D, bool FMA>
-__global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
-  constexpr int TDZ = SN == 2 ? 2 : 1;
-  constexpr int FROW = BS_W * 4 + 4;                       // floats per tile row of each half-state tile (+16 B pad)
-  __shared__ __align__(16) float s_fa[BS_H * FROW];        // flow 0..3
-  __shared__ __align__(16) float s_fb[BS_H * FROW];        // flow 4,5, mask, 0
-  __shared__ float s_img[2][BS_H][BS_W + 1];
-  __shared__ float s_out[2][BS_H][BS_W + 1];
-  __shared__ __align__(16) uint4 s_pk[SN == 1 ? BS_H * BS_PKROW : 1];
-  __shared__ float s_pool[SN == 2 ? 2 * 11 : 1][BS_H][BS_W + 1];
-  __shared__ int s_li[SH > 1 ? 2 * (BS_H + BS_W + TDZ) : 1];      // i0, i1 element offsets of the head taps per tile row / col / plane
-  __shared__ float s_ll[SH > 1 ? 2 * (BS_H + BS_W + TDZ) : 1];    // l0, l1
+__global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
+  extern __shared__ __align__(16) uint8_t bs_smem[];
+  float* s_fa = reinterpret_cast<float*>(bs_smem);                 // [NST][BS_HALF] flow 0..3
+  float* s_fb = s_fa + BS_NST * BS_HALF;                           // [NST][BS_HALF] flow 4,5, mask, 0
+  float* s_ha = s_fb + BS_NST * BS_HALF;                           // [NST][BS_HALF] (SH == 1)
+  float* s_hb = s_ha + (SH == 1 ? BS_NST * BS_HALF : 0);
+  float (*s_img)[2][BS_H][BS_W + 1] = reinterpret_cast<float (*)[2][BS_H][BS_W + 1]>(s_hb + (SH == 1 ? BS_NST * BS_HALF : 0));
+  float (*s_out)[BS_H][BS_W + 1] = reinterpret_cast<float (*)[BS_H][BS_W + 1]>(&s_img[BS_NST][0][0][0]);
+  uint4* s_pk = reinterpret_cast<uint4*>(&s_out[2][0][0]);
+  float (*s_pool)[BS_H][BS_W + 1] = reinterpret_cast<float (*)[BS_H][BS_W + 1]>(s_pk + (SN == 1 ? BS_H * BS_PKROW : 0));
+  int* s_li = reinterpret_cast<int*>(&s_pool[SN == 2 ? 22 : 0][0][0]);   // i0, i1 element offsets of the head taps per tile row / col / plane
+  float* s_ll = reinterpret_cast<float*>(s_li + 2 * (BS_H + BS_W + BS_DZ));
 
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int V = D * HW;                                     // < 2^28 (host check): 32-bit offsets inside one sample
-  const int nzb = D / TDZ;
-  const int n = blockIdx.z / nzb, d0 = (blockIdx.z - n * nzb) * TDZ;
+  const int nzb = (D + BS_DZ - 1) / BS_DZ;
+  const int n = blockIdx.z / nzb, dbeg = (blockIdx.z - n * nzb) * BS_DZ;
+  const int nplanes = min(BS_DZ, D - dbeg);
   const int h0 = blockIdx.y * BS_H, w0 = blockIdx.x * BS_W;
   const int tid = threadIdx.x;
   // phase B mapping: lanes along h
@@ -95,118 +127,124 @@ __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs 
   // phase A/C mapping: 8 consecutive threads = one tile row (8 voxels = 256 B of state, 32 B of a planar volume)
   const int rP = tid >> 3, cP = tid & 7;
   const bool okP = (h0 + rP) < H && (w0 + cP) < W;
+  const int sP = rP * BS_FROW + cP * 4;                     // this thread's slot in a half-state tile
   constexpr int SHD = SH > 1 ? SH : 1;
   const int Dh = D / SHD, Hh = H / SHD, Wh = W / SHD;
-  const float* hb = q.head + (int64_t)n * Dh * Hh * Wh * 8;
+  const float* hb = SH ? q.head + (int64_t)n * Dh * Hh * Wh * 8 : nullptr;
   const float* fprev = q.fm_prev ? q.fm_prev + (int64_t)n * V * 8 : nullptr;
-  float* fout = q.fm_out + (int64_t)n * V * 8;
+  float* fout = SH ? q.fm_out + (int64_t)n * V * 8 : nullptr;
   const float* i0p = q.img0 + (int64_t)n * V;
   const float* i1p = q.img1 + (int64_t)n * V;
   const bool has_prev = fprev != nullptr;
   const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+  const int gP0 = (h0 + rP) * W + w0 + cP;                  // in-plane voxel offset of this thread's phase A/C voxel
+
+  auto issue = [&](int it) {            // async copies of plane dbeg + it into stage it % NST (always commits a group)
+    if (it < nplanes && okP) {
+      const int st = it % BS_NST, g = (dbeg + it) * HW + gP0;
+      if (has_prev) { cp_async16(s_fa + st * BS_HALF + sP, fprev + g * 8); cp_async16(s_fb + st * BS_HALF + sP, fprev + g * 8 + 4); }
+      if (SH == 1) { cp_async16(s_ha + st * BS_HALF + sP, hb + g * 8); cp_async16(s_hb + st * BS_HALF + sP, hb + g * 8 + 4); }
+      if (SN != 0) { cp_async4(&s_img[st][0][rP][cP], i0p + g); cp_async4(&s_img[st][1][rP][cP], i1p + g); }
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
 
   if (SH > 1) {
-    // per-axis tap tables of F.interpolate(scale_factor = SH, align_corners = False) for this tile
-    constexpr int NT = BS_H + BS_W + TDZ;
+    // per-axis tap tables of F.interpolate(scale_factor = SH, align_corners = False) for this tile column
+    constexpr int NT = BS_H + BS_W + BS_DZ;
     if (tid < NT) {
       int dst, n_in, stride;
       if (tid < BS_H) { dst = h0 + tid; n_in = Hh; stride = Wh * 8; }
       else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 8; }
-      else { dst = d0 + tid - BS_H - BS_W; n_in = Dh; stride = Hh * Wh * 8; }
+      else { dst = dbeg + tid - BS_H - BS_W; n_in = Dh; stride = Hh * Wh * 8; }
       const Lerp1s L = up_index1s(dst, n_in, 1.0f / (float)SHD);
       s_li[2 * tid] = L.i0 * stride; s_li[2 * tid + 1] = L.i1 * stride;
       s_ll[2 * tid] = L.l0; s_ll[2 * tid + 1] = L.l1;
     }
-    __syncthreads();
   }
 
-#pragma unroll
-  for (int dz = 0; dz < TDZ; ++dz) {
-    const int d = d0 + dz;
-    const int plane = d * HW;
-    const int gP = plane + (h0 + rP) * W + w0 + cP;        // voxel offset of this thread's phase A/C voxel
-    if (dz > 0) __syncthreads();
-    // ---------------- phase A: state update, one voxel (32 B) per thread
-    if (SN != 0) {
-      s_img[0][rP][cP] = okP ? ldg_stream(i0p + gP) : 0.0f;
-      s_img[1][rP][cP] = okP ? ldg_stream(i1p + gP) : 0.0f;
-    }
-    {
+  for (int it = 0; it < nplanes; ++it) {
+    const int d = dbeg + it, st = it % BS_NST;
+    const int gP = d * HW + gP0;
+    float* fa = s_fa + st * BS_HALF;
+    float* fb = s_fb + st * BS_HALF;
+    issue(it + 2);
+    cp_async_wait<2>();
+    __syncthreads();
+    // ---------------- phase A: state update in place, one voxel (32 B) per thread
+    if (SH != 0) {
       float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
       if (okP) {
-        float4 pa = oa, pb = oa;
-        if (has_prev) { pa = ldg_stream4(fprev + gP * 8); pb = ldg_stream4(fprev + gP * 8 + 4); }
-        if (SH == 0) {
-          oa = pa; ob = pb;
+        float4 va, vb;
+        if (SH == 1) {
+          va = *reinterpret_cast<const float4*>(s_ha + st * BS_HALF + sP);
+          vb = *reinterpret_cast<const float4*>(s_hb + st * BS_HALF + sP);
         } else {
-          float4 va, vb;
-          if (SH == 1) {
-            va = ldg_stream4(hb + gP * 8); vb = ldg_stream4(hb + gP * 8 + 4);
-          } else {
-            const int ty = rP, tx = BS_H + cP, tz = BS_H + BS_W + dz;
-            const int y0 = s_li[2 * ty], y1 = s_li[2 * ty + 1], x0 = s_li[2 * tx], x1 = s_li[2 * tx + 1];
-            const int z0 = s_li[2 * tz], z1 = s_li[2 * tz + 1];
-            const float ly0 = s_ll[2 * ty], ly1 = s_ll[2 * ty + 1], lx0 = s_ll[2 * tx], lx1 = s_ll[2 * tx + 1];
-            const float lz0 = s_ll[2 * tz], lz1 = s_ll[2 * tz + 1];
+          const int ty = rP, tx = BS_H + cP, tz = BS_H + BS_W + it;
+          const int y0 = s_li[2 * ty], y1 = s_li[2 * ty + 1], x0 = s_li[2 * tx], x1 = s_li[2 * tx + 1];
+          const int z0 = s_li[2 * tz], z1 = s_li[2 * tz + 1];
+          const float ly0 = s_ll[2 * ty], ly1 = s_ll[2 * ty + 1], lx0 = s_ll[2 * tx], lx1 = s_ll[2 * tx + 1];
+          const float lz0 = s_ll[2 * tz], lz1 = s_ll[2 * tz + 1];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const float* r = hb + half * 4;
-              auto L4 = [&](int o) { return __ldg(reinterpret_cast<const float4*>(r + o)); };
-              const float4 a00 = lerp4(L4(z0 + y0 + x0), lx0, L4(z0 + y0 + x1), lx1);
-              const float4 a01 = lerp4(L4(z0 + y1 + x0), lx0, L4(z0 + y1 + x1), lx1);
-              const float4 a10 = lerp4(L4(z1 + y0 + x0), lx0, L4(z1 + y0 + x1), lx1);
-              const float4 a11 = lerp4(L4(z1 + y1 + x0), lx0, L4(z1 + y1 + x1), lx1);
-              const float4 v = lerp4(lerp4(a00, ly0, a01, ly1), lz0, lerp4(a10, ly0, a11, ly1), lz1);
-              if (half == 0) va = v; else vb = v;
-            }
+          for (int half = 0; half < 2; ++half) {
+            const float* r = hb + half * 4;
+            auto L4 = [&](int o) { return __ldg(reinterpret_cast<const float4*>(r + o)); };
+            const float4 a00 = lerp4(L4(z0 + y0 + x0), lx0, L4(z0 + y0 + x1), lx1);
+            const float4 a01 = lerp4(L4(z0 + y1 + x0), lx0, L4(z0 + y1 + x1), lx1);
+            const float4 a10 = lerp4(L4(z1 + y0 + x0), lx0, L4(z1 + y0 + x1), lx1);
+            const float4 a11 = lerp4(L4(z1 + y1 + x0), lx0, L4(z1 + y1 + x1), lx1);
+            const float4 v = lerp4(lerp4(a00, ly0, a01, ly1), lz0, lerp4(a10, ly0, a11, ly1), lz1);
+            if (half == 0) va = v; else vb = v;
           }
-          const float sh = (float)SHD;
-          if (has_prev) {
-            oa = make_float4(__fadd_rn(pa.x, __fmul_rn(va.x, sh)), __fadd_rn(pa.y, __fmul_rn(va.y, sh)),
-                             __fadd_rn(pa.z, __fmul_rn(va.z, sh)), __fadd_rn(pa.w, __fmul_rn(va.w, sh)));
-            ob = make_float4(__fadd_rn(pb.x, __fmul_rn(vb.x, sh)), __fadd_rn(pb.y, __fmul_rn(vb.y, sh)), __fadd_rn(pb.z, vb.z), 0.0f);
-          } else {   // block 0: flow = flow_d exactly
-            oa = make_float4(__fmul_rn(va.x, sh), __fmul_rn(va.y, sh), __fmul_rn(va.z, sh), __fmul_rn(va.w, sh));
-            ob = make_float4(__fmul_rn(vb.x, sh), __fmul_rn(vb.y, sh), vb.z, 0.0f);
-          }
-          stg_stream4(fout + gP * 8, oa);
-          stg_stream4(fout + gP * 8 + 4, ob);
         }
+        const float sh = (float)SHD;
+        if (has_prev) {
+          const float4 pa = *reinterpret_cast<const float4*>(fa + sP), pb = *reinterpret_cast<const float4*>(fb + sP);
+          oa = make_float4(__fadd_rn(pa.x, __fmul_rn(va.x, sh)), __fadd_rn(pa.y, __fmul_rn(va.y, sh)),
+                           __fadd_rn(pa.z, __fmul_rn(va.z, sh)), __fadd_rn(pa.w, __fmul_rn(va.w, sh)));
+          ob = make_float4(__fadd_rn(pb.x, __fmul_rn(vb.x, sh)), __fadd_rn(pb.y, __fmul_rn(vb.y, sh)), __fadd_rn(pb.z, vb.z), 0.0f);
+        } else {   // block 0: flow = flow_d exactly
+          oa = make_float4(__fmul_rn(va.x, sh), __fmul_rn(va.y, sh), __fmul_rn(va.z, sh), __fmul_rn(va.w, sh));
+          ob = make_float4(__fmul_rn(vb.x, sh), __fmul_rn(vb.y, sh), vb.z, 0.0f);
+        }
+        stg_stream4(fout + gP * 8, oa);
+        stg_stream4(fout + gP * 8 + 4, ob);
       }
-      *reinterpret_cast<float4*>(&s_fa[rP * FROW + cP * 4]) = oa;
-      *reinterpret_cast<float4*>(&s_fb[rP * FROW + cP * 4]) = ob;
+      *reinterpret_cast<float4*>(fa + sP) = oa;
+      *reinterpret_cast<float4*>(fb + sP) = ob;
+      __syncthreads();
     }
-    __syncthreads();
     // ---------------- phase B: warps / blend, one voxel per thread, lanes along h
     if (okB) {
-      const float4 fa = *reinterpret_cast<const float4*>(&s_fa[lane * FROW + wl * 4]);
-      const float4 fb = *reinterpret_cast<const float4*>(&s_fb[lane * FROW + wl * 4]);
-      const float m = fb.z;
+      const float4 va = *reinterpret_cast<const float4*>(fa + lane * BS_FROW + wl * 4);
+      const float4 vb = *reinterpret_cast<const float4*>(fb + lane * BS_FROW + wl * 4);
+      const float m = vb.z;
       const float lh = __ldg(q.lin_h + hB), ld = __ldg(q.lin_d + d), lw = __ldg(q.lin_w + wB);
-      const Trilin t0 = trilin_setup(fa.x, fa.y, fa.z, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-      const Trilin t1 = trilin_setup(fa.w, fb.x, fb.y, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-      const float a = trilin_sample<FMA>(i0p, t0, W, HW);
-      const float b = trilin_sample<FMA>(i1p, t1, W, HW);
-      float ms = 0.0f, mg = 0.0f;
+      const Trilin t0 = trilin_setup(va.x, va.y, va.z, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+      const Trilin t1 = trilin_setup(va.w, vb.x, vb.y, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+      const Taps8 g0 = trilin_gather(i0p, t0), g1 = trilin_gather(i1p, t1);     // 16 independent loads in flight
+      const float a = trilin_reduce<FMA>(g0, t0), b = trilin_reduce<FMA>(g1, t1);
       if (need_m) {
-        ms = sigmoidf_ref(m);
-        mg = __fadd_rn(__fmul_rn(a, ms), __fmul_rn(b, __fsub_rn(1.0f, ms)));
-        s_out[0][lane][wl] = mg; s_out[1][lane][wl] = ms;
+        const float ms = sigmoidf_ref(m);
+        s_out[0][lane][wl] = __fadd_rn(__fmul_rn(a, ms), __fmul_rn(b, __fsub_rn(1.0f, ms)));
+        s_out[1][lane][wl] = ms;
       }
       if (SN == 1) {
-        const float i0v = s_img[0][lane][wl], i1v = s_img[1][lane][wl];
+        const float i0v = s_img[st][0][lane][wl], i1v = s_img[st][1][lane][wl];
         uint4 lo, hi;
-        lo.x = bs_pack2(i0v, i1v); lo.y = bs_pack2(a, b); lo.z = bs_pack2(m, fa.x); lo.w = bs_pack2(fa.y, fa.z);
-        hi.x = bs_pack2(fa.w, fb.x); hi.y = bs_pack2(fb.y, 0.0f); hi.z = 0u; hi.w = 0u;
+        lo.x = bs_pack2(i0v, i1v); lo.y = bs_pack2(a, b); lo.z = bs_pack2(m, va.x); lo.w = bs_pack2(va.y, va.z);
+        hi.x = bs_pack2(va.w, vb.x); hi.y = bs_pack2(vb.y, 0.0f); hi.z = 0u; hi.w = 0u;
         s_pk[lane * BS_PKROW + wl * 2] = lo;
         s_pk[lane * BS_PKROW + wl * 2 + 1] = hi;
       } else if (SN == 2) {
-        const float c11[11] = {s_img[0][lane][wl], s_img[1][lane][wl], a, b, m, fa.x, fa.y, fa.z, fa.w, fb.x, fb.y};
+        const float c11[11] = {s_img[st][0][lane][wl], s_img[st][1][lane][wl], a, b, m, va.x, va.y, va.z, va.w, vb.x, vb.y};
 #pragma unroll
-        for (int c = 0; c < 11; ++c) s_pool[dz * 11 + c][lane][wl] = c11[c];
+        for (int c = 0; c < 11; ++c) s_pool[(it & 1) * 11 + c][lane][wl] = c11[c];
       }
     }
-    if (need_m || SN == 1) __syncthreads();
+    __syncthreads();
     // ---------------- phase C: coalesced stores
     if (okP) {
       const int64_t g = (int64_t)n * V + gP;
@@ -218,11 +256,8 @@ __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs 
         o[1] = s_pk[rP * BS_PKROW + cP * 2 + 1];
       }
     }
-  }
-  if (SN == 2) {
-    // 2x2x2 mean == F.interpolate(., 0.5): nested W, H, D like ATen; flow channels additionally * 0.5
-    __syncthreads();
-    if (tid < 64) {
+    if (SN == 2 && (it & 1) && tid < 64) {
+      // 2x2x2 mean == F.interpolate(., 0.5): nested W, H, D like ATen; flow channels additionally * 0.5
       const int ph = tid >> 2, pw = tid & 3;
       const int oh = h0 / 2 + ph, ow = w0 / 2 + pw;
       if (oh < H / 2 && ow < W / 2) {
@@ -244,11 +279,25 @@ __global__ void __launch_bounds__(256, 4) block_stage_3d_kernel(const StagePtrs 
         uint4 lo, hi;
         lo.x = bs_pack2(c11[0], c11[1]); lo.y = bs_pack2(c11[2], c11[3]); lo.z = bs_pack2(c11[4], c11[5]); lo.w = bs_pack2(c11[6], c11[7]);
         hi.x = bs_pack2(c11[8], c11[9]); hi.y = bs_pack2(c11[10], 0.0f); hi.z = 0u; hi.w = 0u;
-        uint4* o = reinterpret_cast<uint4*>(q.pack_out + pack_row_off<S2D>(n, d0 / 2, oh, ow, D / 2, H / 2, W / 2));
+        uint4* o = reinterpret_cast<uint4*>(q.pack_out + pack_row_off<S2D>(n, d / 2, oh, ow, D / 2, H / 2, W / 2));
         o[0] = lo; o[1] = hi;
       }
     }
   }
+  cp_async_wait<0>();
+}
+
+template <int SH, int SN, bool S2D, bool FMA>
+static int launch_stage(const StagePtrs& q, const Warp3dParams& P, dim3 grid, cudaStream_t st) {
+  constexpr int smem = bs_smem_bytes(SH, SN);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(block_stage_3d_kernel<SH, SN, S2D, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("ofsv_block_stage_3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
+    attr_done = true;
+  }
+  block_stage_3d_kernel<SH, SN, S2D, FMA><<<grid, 256, smem, st>>>(q, P);
+  return OFSV_OK;
 }
 
 }  // namespace ofsv
@@ -275,17 +324,16 @@ extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, cons
   OFSV_REQUIRE((!head || aligned16(head)) && (!fm_out || aligned16(fm_out)) && (!fm_prev || aligned16(fm_prev)) && (!pack_out || aligned16(pack_out)),
                "ofsv_block_stage_3d: head / fm / pack_out must be 16-byte aligned");
   const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
-  const int tdz = scale_next == 2 ? 2 : 1;
-  const dim3 grid((unsigned)cdiv(W, BS_W), (unsigned)cdiv(H, BS_H), (unsigned)(N * (D / tdz)));
+  const dim3 grid((unsigned)cdiv(W, BS_W), (unsigned)cdiv(H, BS_H), (unsigned)(N * cdiv(D, BS_DZ)));
   if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
   StagePtrs q{head, fm_prev, img0, img1, lin_h, lin_d, lin_w, fm_out, merged, mask_sig, reinterpret_cast<__nv_bfloat16*>(pack_out)};
   cudaStream_t st = (cudaStream_t)stream;
   const bool fma = ref_mode == OFSV_REF_CUDA;
   const bool s2d = pack_s2d != 0;
+  int rc = OFSV_OK;
 #define GO3(SH, SN, S2)                                                                                \
   do {                                                                                                 \
-    if (fma) block_stage_3d_kernel<SH, SN, S2, true><<<grid, 256, 0, st>>>(q, P);                      \
-    else block_stage_3d_kernel<SH, SN, S2, false><<<grid, 256, 0, st>>>(q, P);                         \
+    rc = fma ? launch_stage<SH, SN, S2, true>(q, P, grid, st) : launch_stage<SH, SN, S2, false>(q, P, grid, st);  \
   } while (0)
 #define GO(SH)                                                                                         \
   do {                                                                                                 \
@@ -296,5 +344,6 @@ extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, cons
   if (scale_head == 0) GO(0); else if (scale_head == 1) GO(1); else if (scale_head == 2) GO(2); else GO(4);
 #undef GO
 #undef GO3
+  if (rc != OFSV_OK) return rc;
   return check_launch("block_stage_3d_kernel");
 }

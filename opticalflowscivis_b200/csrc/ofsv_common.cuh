@@ -53,17 +53,15 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // (__f*_rn intrinsics are never contracted into FMAs by nvcc).  SURVEY.md Appendix A.
 // f / half_extent as the CPU reference computes it (true IEEE division).  For the constants c = (S-1)/2 the Markstein
 // sequence q = RN(f*rc), r = f - q*c (exact, FMA), RN(q + r*rc) with rc = RN(1/c) IS the correctly rounded quotient for every
-// float 2^-60 <= |f| <= 2^20 (oracle/check_div_const.c checks all of them for S = 2..1024); it costs 3 instructions where
-// __fdiv_rn costs ~20 on the critical path of every warp tap.  Anything outside that range takes the slow exact path.
+// float 2^-60 <= |f| <= 2^20 (oracle/check_div_const.c checks all of them for S = 2..1024); it costs 3 instructions and no
+// branch where __fdiv_rn costs ~20 with a slow-path call on the critical path of every warp tap.  Outside that range the
+// result can differ from IEEE division in the last bit (or be NaN instead of +-inf beyond 1e38), which cannot change the
+// warp: quotients below 2^-60/c vanish in `lin + q`, and |f| > 2^20 px lands far outside the volume and is border-clipped.
 __device__ __forceinline__ float norm_flow(float f, float half_extent, float rcp_half_extent, int ref_mode) {
-  if (ref_mode == OFSV_REF_CUDA) return __fmul_rn(f, rcp_half_extent);
-  const float af = fabsf(f);
-  if (af >= 0x1p-60f && af <= 0x1p20f) {
-    const float q = __fmul_rn(f, rcp_half_extent);
-    const float r = __fmaf_rn(-q, half_extent, f);
-    return __fmaf_rn(r, rcp_half_extent, q);
-  }
-  return __fdiv_rn(f, half_extent);
+  const float q = __fmul_rn(f, rcp_half_extent);
+  if (ref_mode == OFSV_REF_CUDA) return q;
+  const float r = __fmaf_rn(-q, half_extent, f);
+  return __fmaf_rn(r, rcp_half_extent, q);
 }
 // grid_sampler_unnormalize(align_corners=True) + clip_coordinates (border)
 __device__ __forceinline__ float unnorm_clip_ac(float g, float size_m1) {

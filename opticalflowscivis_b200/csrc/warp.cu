@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256)
     const float lh = __ldg(lin_h + h), ld = __ldg(lin_d + d), lw = __ldg(lin_w + w);
     const Trilin t0 = trilin_setup(si[0][lane][wl], si[1][lane][wl], si[2][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
     const Trilin t1 = trilin_setup(si[3][lane][wl], si[4][lane][wl], si[5][lane][wl], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-    const float a = trilin_sample<FMA>(img0 + (int64_t)n * V, t0, W, HW);
-    const float b = trilin_sample<FMA>(img1 + (int64_t)n * V, t1, W, HW);
+    const Taps8 g0 = trilin_gather(img0 + (int64_t)n * V, t0), g1 = trilin_gather(img1 + (int64_t)n * V, t1);
+    const float a = trilin_reduce<FMA>(g0, t0), b = trilin_reduce<FMA>(g1, t1);
     float m = 0.0f, mg = 0.0f;
     if (need_m) {
       m = sigmoidf_ref(si[6][lane][wl]);

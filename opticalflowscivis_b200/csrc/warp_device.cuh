@@ -6,7 +6,7 @@ namespace ofsv {
 
 struct Trilin {
   int base;            // z0*HW + y0*W + x0
-  bool okx, oky, okz;  // +1 neighbour inside the volume
+  int dx, dy, dz;      // element offset of the +1 neighbour along each source axis, 0 when it lies outside the volume
   float ex, wx, ey, wy, ez, wz;
 };
 
@@ -24,7 +24,12 @@ __device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, flo
   t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy); t.wy = __fsub_rn(iy, fy);
   t.ez = __fsub_rn(__fadd_rn(fz, 1.0f), iz); t.wz = __fsub_rn(iz, fz);
   const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-  t.okx = x0 + 1 <= W - 1; t.oky = y0 + 1 <= H - 1; t.okz = z0 + 1 <= D - 1;
+  // A +1 neighbour outside the volume only occurs when the clipped coordinate sits exactly on the last sample, where its
+  // weight (wx / wy / wz) is exactly 0: ATen skips the tap, here it re-reads the in-range sample with weight 0.  That keeps
+  // the 8 taps branch-free so that all gathers of a voxel are in flight together (one memory round trip, not four).
+  t.dx = x0 + 1 <= W - 1 ? 1 : 0;
+  t.dy = y0 + 1 <= H - 1 ? W : 0;
+  t.dz = z0 + 1 <= D - 1 ? H * W : 0;
   t.base = (z0 * H + y0) * W + x0;
   return t;
 }
@@ -34,25 +39,38 @@ __device__ __forceinline__ float acc_tap(float acc, float v, float w) {
   return FMA ? __fmaf_rn(v, w, acc) : __fadd_rn(acc, __fmul_rn(v, w));
 }
 
+struct Taps8 {
+  float v[8];
+};
+__device__ __forceinline__ Taps8 trilin_gather(const float* __restrict__ p, const Trilin& t) {
+  const float* q = p + t.base;
+  Taps8 r;
+  r.v[0] = __ldg(q); r.v[1] = __ldg(q + t.dx); r.v[2] = __ldg(q + t.dy); r.v[3] = __ldg(q + t.dy + t.dx);
+  q += t.dz;
+  r.v[4] = __ldg(q); r.v[5] = __ldg(q + t.dx); r.v[6] = __ldg(q + t.dy); r.v[7] = __ldg(q + t.dy + t.dx);
+  return r;
+}
 // ATen grid_sampler_3d corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse; weights = product of 3 distances, left to right.
 template <bool FMA>
-__device__ __forceinline__ float trilin_sample(const float* __restrict__ p, const Trilin& t, int W, int HW) {
-  const float* q = p + t.base;
+__device__ __forceinline__ float trilin_reduce(const Taps8& r, const Trilin& t) {
   const float xy00 = __fmul_rn(t.ex, t.ey), xy10 = __fmul_rn(t.wx, t.ey), xy01 = __fmul_rn(t.ex, t.wy),
               xy11 = __fmul_rn(t.wx, t.wy);
   float acc = 0.0f;
-  acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.ez));
-  if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.ez));
-  if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.ez));
-  if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.ez));
-  if (t.okz) {
-    q += HW;
-    acc = acc_tap<FMA>(acc, __ldg(q), __fmul_rn(xy00, t.wz));
-    if (t.okx) acc = acc_tap<FMA>(acc, __ldg(q + 1), __fmul_rn(xy10, t.wz));
-    if (t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W), __fmul_rn(xy01, t.wz));
-    if (t.okx && t.oky) acc = acc_tap<FMA>(acc, __ldg(q + W + 1), __fmul_rn(xy11, t.wz));
-  }
+  acc = acc_tap<FMA>(acc, r.v[0], __fmul_rn(xy00, t.ez));
+  acc = acc_tap<FMA>(acc, r.v[1], __fmul_rn(xy10, t.ez));
+  acc = acc_tap<FMA>(acc, r.v[2], __fmul_rn(xy01, t.ez));
+  acc = acc_tap<FMA>(acc, r.v[3], __fmul_rn(xy11, t.ez));
+  acc = acc_tap<FMA>(acc, r.v[4], __fmul_rn(xy00, t.wz));
+  acc = acc_tap<FMA>(acc, r.v[5], __fmul_rn(xy10, t.wz));
+  acc = acc_tap<FMA>(acc, r.v[6], __fmul_rn(xy01, t.wz));
+  acc = acc_tap<FMA>(acc, r.v[7], __fmul_rn(xy11, t.wz));
   return acc;
+}
+template <bool FMA>
+__device__ __forceinline__ float trilin_sample(const float* __restrict__ p, const Trilin& t, int W, int HW) {
+  (void)W; (void)HW;
+  const Taps8 r = trilin_gather(p, t);
+  return trilin_reduce<FMA>(r, t);
 }
 
 // CTA tile of the 3-D kernels: 32 (h) x 8 (w) voxels at fixed (n, d); 256 threads = one voxel each, warp q owns the
