@@ -99,33 +99,127 @@ __global__ void __launch_bounds__(256)
 // ----------------------------------------------------------------------------------------------------
 // 3-D
 // ----------------------------------------------------------------------------------------------------
+// Warp-autonomous 3-D warp: no block-level barrier anywhere.  A task = (n, d, 32 consecutive h, W3_WT consecutive w), owned
+// by one WARP; tasks are numbered with the w tile fastest so that warps running at the same time read neighbouring pieces of
+// the same flow rows (DRAM page hits) and gather from the same few source planes (L2 hits).  Per task
+//   * the three flow planes (32 rows x 64 B) arrive by cp.async into the warp's private, double-buffered shared tile — the
+//     tile of the warp's NEXT task is in flight while the current one is processed, so streaming reads never stall the warp;
+//   * lane = row h: it reads its flow vectors with 16 B shared loads and processes 4 voxels at a time (32 independent
+//     gathers in flight per lane, 12 warps per SM); lanes along h make every tap a 128 B-coalesced read of the rotated
+//     source, and walking along w steps through consecutive source z planes (the z+1 taps of one voxel are the z taps of
+//     the next: L1 hits);
+//   * each lane stores its 16 results as four 16 B vectors (64 contiguous bytes of its output row).
+constexpr int W3_WT = 16;                 // voxels along w per tile
+constexpr int W3_ROW = W3_WT + 4;         // floats per tile row in shared memory (80 B: 16 B-aligned, conflict-free for LDS.128)
+constexpr int W3_WARPS = 4;
+constexpr int W3_PLANE = 32 * W3_ROW;     // floats per (plane, tile)
+constexpr int W3_SMEM_PER_WARP = 2 * 3 * W3_PLANE * 4;
+
+__device__ __forceinline__ void w3_cp16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void w3_cp4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 template <bool VEC, bool FMA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * W3_WARPS, 3)
     warp3d_kernel(const float* __restrict__ src, const float* __restrict__ flow, const float* __restrict__ lin_h,
                   const float* __restrict__ lin_d, const float* __restrict__ lin_w, float* __restrict__ out,
-                  const Warp3dParams P) {
-  __shared__ float sf[3][T3H][T3P];
-  __shared__ float so[1][T3H][T3P];
+                  const Warp3dParams P, const long long ntasks) {
+  extern __shared__ __align__(16) float w3_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sf = w3_smem + wid * (W3_SMEM_PER_WARP / 4);     // [2][3][32][W3_ROW]
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int64_t V = (int64_t)D * HW;
-  const int n = blockIdx.z / D, d = blockIdx.z - n * D;
-  const int h0 = blockIdx.y * T3H, w0 = blockIdx.x * T3W;
-  const float* fl = flow + (int64_t)n * 3 * V + (int64_t)d * HW;
-  load_planes<3, VEC>(sf, [&](int k) { return fl + (int64_t)k * V; }, h0, w0, H, W);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int h = h0 + lane, w = w0 + wl;
-  const bool ok = h < H && w < W;
-  Trilin t;
-  if (ok) t = trilin_setup(sf[0][lane][wl], sf[1][lane][wl], sf[2][lane][wl], __ldg(lin_h + h), __ldg(lin_d + d),
-                           __ldg(lin_w + w), D, H, W, P.hs, P.ref_mode);
-  for (int c = 0; c < P.C; ++c) {
-    if (ok) so[0][lane][wl] = trilin_sample<FMA>(src + ((int64_t)n * P.C + c) * V, t, W, HW);
-    __syncthreads();
-    float* o = out + ((int64_t)n * P.C + c) * V + (int64_t)d * HW;
-    store_planes<1, VEC>(so, [&](int) { return o; }, h0, w0, H, W);
-    __syncthreads();
+  const int hblocks = (H + 31) >> 5;
+  const int ntw = (W + W3_WT - 1) / W3_WT;
+  const long long stride = (long long)gridDim.x * W3_WARPS;
+  struct Task { int n, d, h0, w0; };
+  auto decode = [&](long long id) {
+    Task k;
+    k.w0 = (int)(id % ntw) * W3_WT; id /= ntw;
+    k.h0 = (int)(id % hblocks) << 5; id /= hblocks;
+    k.d = (int)(id % D);
+    k.n = (int)(id / D);
+    return k;
+  };
+  // async copy of the flow tile of task `id` (3 planes x 32 rows x 16 floats) into stage st: row = i*8 + lane/4, chunk = lane%4
+  auto issue = [&](long long id, int st) {
+    if (id < ntasks) {
+      const Task k = decode(id);
+      const float* fl = flow + (int64_t)k.n * 3 * V + (int64_t)k.d * HW;
+      float* dst = sf + st * 3 * W3_PLANE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 8 + (lane >> 2), c4 = (lane & 3) * 4;
+        if (k.h0 + row < H) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* g = fl + (int64_t)c * V + (int64_t)(k.h0 + row) * W + k.w0 + c4;
+            float* s = dst + c * W3_PLANE + row * W3_ROW + c4;
+            if (VEC && k.w0 + c4 + 3 < W) {
+              w3_cp16(s, g);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (k.w0 + c4 + e < W) w3_cp4(s + e, g + e);
+            }
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  long long task = (long long)blockIdx.x * W3_WARPS + wid;
+  issue(task, 0);
+  for (int it = 0; task < ntasks; task += stride, ++it) {
+    const int st = it & 1;
+    issue(task + stride, st ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const Task k = decode(task);
+    const int h = k.h0 + lane, w0 = k.w0;
+    const bool okh = h < H;
+    const float lh = okh ? __ldg(lin_h + h) : 0.0f, ld = __ldg(lin_d + k.d);
+    const float* f0 = sf + st * 3 * W3_PLANE + lane * W3_ROW;
+    for (int c = 0; c < P.C; ++c) {
+      const float* sp = src + ((int64_t)k.n * P.C + c) * V;
+      if (okh) {
+        float* o = out + ((int64_t)k.n * P.C + c) * V + (int64_t)k.d * HW + (int64_t)h * W + w0;
+#pragma unroll
+        for (int q4 = 0; q4 < W3_WT / 4; ++q4) {
+          const float4 a = *reinterpret_cast<const float4*>(f0 + q4 * 4);
+          const float4 b = *reinterpret_cast<const float4*>(f0 + W3_PLANE + q4 * 4);
+          const float4 e = *reinterpret_cast<const float4*>(f0 + 2 * W3_PLANE + q4 * 4);
+          const float fa[4] = {a.x, a.y, a.z, a.w}, fb[4] = {b.x, b.y, b.z, b.w}, fe[4] = {e.x, e.y, e.z, e.w};
+          float r[4];
+          {
+            Trilin tr[4];
+            Taps8 tp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int w = min(w0 + q4 * 4 + j, W - 1);        // columns past W reuse the last one (never stored)
+              tr[j] = trilin_setup(fa[j], fb[j], fe[j], lh, ld, __ldg(lin_w + w), D, H, W, P.hs, P.ref_mode);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tp[j] = trilin_gather(sp, tr[j]);     // 32 independent gathers in flight
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = trilin_reduce<FMA>(tp[j], tr[j]);
+          }
+          if (VEC && w0 + q4 * 4 + 3 < W) {
+            stg_stream4(o + q4 * 4, make_float4(r[0], r[1], r[2], r[3]));
+          } else {
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2)
+              if (w0 + q4 * 4 + e2 < W) o[q4 * 4 + e2] = r[e2];
+          }
+        }
+      }
+    }
+    __syncwarp();            // every lane has read stage st before the next iteration's copies overwrite it
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // fused: sigmoid(mask), warp(img0, flow[:, :3]), warp(img1, flow[:, 3:6]), merged.  7 input planes -> up to 4 output planes.
@@ -220,14 +314,23 @@ extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float*
   if ((int64_t)N * C == 0) return OFSV_OK;   // empty batch
   OFSV_REQUIRE(src && flow && lin_h && lin_d && lin_w && out, "ofsv_warp3d_f32: null pointer");
   OFSV_REQUIRE((int64_t)D * H * W < (1ll << 31), "ofsv_warp3d_f32: volume too large for 32-bit voxel offsets");
-  OFSV_REQUIRE((int64_t)N * D <= 65535 * 1ll * 65535, "ofsv_warp3d_f32: N*D too large");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp3d_f32: bad ref_mode %d", ref_mode);
   const Warp3dParams P = make_warp3d_params(N, C, D, H, W, ref_mode);
-  const dim3 grid((unsigned)cdiv(W, T3W), (unsigned)cdiv(H, T3H), (unsigned)(N * D));
   const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (grid.z > 65535u) { set_error("ofsv_warp3d_f32: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
-#define LAUNCH(V, F) warp3d_kernel<V, F><<<grid, 256, 0, st>>>(src, flow, lin_h, lin_d, lin_w, out, P)
+  const long long ntasks = (long long)N * D * cdiv(H, 32) * cdiv(W, W3_WT);
+  const int64_t ctas = cdiv(ntasks, W3_WARPS);
+  const int grid = (int)(ctas < 148 * 3 ? ctas : 148 * 3);      // 3 CTAs (12 warps) resident per SM, persistent over the task list
+  const int smem = W3_WARPS * W3_SMEM_PER_WARP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(warp3d_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(warp3d_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(warp3d_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(warp3d_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_done = true;
+  }
+#define LAUNCH(V, F) warp3d_kernel<V, F><<<grid, 32 * W3_WARPS, smem, st>>>(src, flow, lin_h, lin_d, lin_w, out, P, ntasks)
   if (vec) { if (ref_mode == OFSV_REF_CUDA) LAUNCH(true, true); else LAUNCH(true, false); }
   else     { if (ref_mode == OFSV_REF_CUDA) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
