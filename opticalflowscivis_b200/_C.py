@@ -70,6 +70,7 @@ def lib() -> ctypes.CDLL:
                     "libofsv.so is missing and could not be built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                     "this package has no CPU or PyTorch fallback") from e
             so = _SO
+        so = os.environ.get("OFSV_LIB", so)       # A/B testing of an alternative build of the same C ABI (tests/ab_build.sh)
         L = ctypes.CDLL(so)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch

@@ -1,3 +1,5 @@
+// PLANE-RING variant of the halo-reuse tcgen05 convolution (conv_halo.cu), used for the layers with few taps per super-tile
+// (the space-to-depth conv0 layers): z-fastest tile runs that share boundary planes, per-plane release, resident weights.
 // tcgen05 implicit-GEMM convolution with shared-memory HALO REUSE for the stride-1 layers of an IFBlock
 // (3^d convs of convblock0..3, and the 2^d-phase form of ConvTranspose(4,2,1): every tap offset is in {-1,0,+1}^d).
 //
@@ -17,6 +19,11 @@
 //   passes      = 1 (conv) or 2^d (ConvTranspose output parities): the planes stay resident across all passes.
 //   TMEM        = TD x Cout_w fp32 columns per pass, double-buffered when it fits so the epilogue of pass i overlaps
 //                 the MMAs of pass i+1; CTAs are persistent over super-tiles (grid = #SMs).
+//   plane ring  = every CTA walks a contiguous run of super-tiles in z-FASTEST order, so consecutive super-tiles of a column
+//                 share their (dzmax - dzmin) boundary planes: the np = TD + dz-span plane slots form a ring indexed by the
+//                 input depth, only TD new planes are loaded per super-tile, and (single-pass layers, taps sorted by dz) a
+//                 plane's slot is handed back to the TMA producer right after the last tap that reads it — the next
+//                 super-tile's planes stream in underneath the current super-tile's MMAs instead of after them.
 // L2->SM traffic per 128 outputs drops from ~650 KB to ~(23 KB x (TD+2)/TD + 216 KB/TD).
 #include <cstdio>
 #include <cstdlib>
@@ -25,18 +32,18 @@
 
 namespace ofsv {
 
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+__device__ __forceinline__ uint32_t ring_pack2_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 constexpr int HT_H = 16, HT_W = 8, HP_H = HT_H + 2, HP_W = HT_W + 2, HP_ROWS = HP_H * HP_W;  // 180 halo rows
 constexpr int H_MAX_PLANES = 8;
-constexpr int H_MAX_BSTAGES = 8;
+constexpr int H_MAX_BSTAGES = 32;
 constexpr int H_MMA_WARPS = 4, H_EPI_WARPS = 8, H_EPI_W0 = 1 + H_MMA_WARPS;
 constexpr int H_THREADS = 32 * (H_EPI_W0 + H_EPI_WARPS);   // warp 0 TMA, warps 1..2 MMA issuers (output slices split by parity), warps 3..10 epilogue
 
-struct HaloParams {
+struct RingParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
   int out_stride, nphase, ntaps, nkc;
   int td, np, dzmin;                 // output slices per super-tile, input planes per super-tile, min dz over taps
@@ -45,12 +52,17 @@ struct HaloParams {
   int nbuf, acc_stride;              // TMEM accumulator double buffering
   int has_prelu, has_residual, out_f32, shuffle, dbg_flags;
   int nd, out_s2d;
+  int dzspan;                        // dzmax - dzmin
+  int sliding;                       // 1: z-fastest contiguous tile runs with shared boundary planes and early plane release
+  int b_resident;                    // all weight tiles fit the ring: loaded once per CTA, never recycled
+  uint8_t tap_order[OFSV_MAX_TAPS];   // per pass: taps in ascending dz (position -> original tap index)
+  uint8_t rel_after[OFSV_MAX_TAPS];   // last pass only: bitmask of non-shared plane indices q < td whose last reader is this position
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
 template <int KC>
 __global__ void __launch_bounds__(H_THREADS, 1)
-    conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p,
+    conv_halo_ring_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RingParams p,
                      const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
                      void* __restrict__ y, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -61,9 +73,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
   uint8_t* sP = smem;
   uint8_t* sB = smem + nplanes * p.plane_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nb * p.b_stride);
-  uint64_t* plane_full = bars;                            // [H_MAX_PLANES]
-  uint64_t* planes_empty = bars + H_MAX_PLANES;           // [1]
-  uint64_t* b_full = planes_empty + 1;                    // [H_MAX_BSTAGES]
+  uint64_t* plane_full = bars;                            // [H_MAX_PLANES]  (indexed by ring position)
+  uint64_t* plane_empty = bars + H_MAX_PLANES;            // [H_MAX_PLANES]
+  uint64_t* b_full = plane_empty + H_MAX_PLANES;          // [H_MAX_BSTAGES]
   uint64_t* b_empty = b_full + H_MAX_BSTAGES;             // [H_MAX_BSTAGES]
   uint64_t* acc_full = b_empty + H_MAX_BSTAGES;           // [2]
   uint64_t* acc_empty = acc_full + 2;                     // [2]
@@ -73,14 +85,35 @@ __global__ void __launch_bounds__(H_THREADS, 1)
   uint32_t* sTap = reinterpret_cast<uint32_t*>(sPrelu + 128); // [OFSV_MAX_TAPS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
-  const int total = per_sample * p.N;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  // sliding: contiguous run of super-tiles of this CTA in z-fastest order, L = ((n * tiles_h + ty) * tiles_w + tx) * tiles_d + tz.
+  // otherwise: tiles blockIdx.x + k * gridDim.x of the x-fastest order (neighbouring CTAs work on neighbouring tiles), every
+  // tile loads all of its planes.  Both are expressed as a run [L_begin, L_end) of per-CTA sequence numbers.
+  const int L_begin = p.sliding ? (int)(((long long)blockIdx.x * total) / gridDim.x) : 0;
+  const int L_end = p.sliding ? (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x)
+                              : (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  struct TileC { int tx, ty, tz, n; };
+  auto decode = [&](int L) {
+    TileC c;
+    if (p.sliding) {
+      c.tz = L % p.tiles_d; L /= p.tiles_d;
+      c.tx = L % p.tiles_w; L /= p.tiles_w;
+      c.ty = L % p.tiles_h;
+      c.n = L / p.tiles_h;
+    } else {
+      int r = (int)blockIdx.x + L * (int)gridDim.x;
+      c.tx = r % p.tiles_w; r /= p.tiles_w;
+      c.ty = r % p.tiles_h; r /= p.tiles_h;
+      c.tz = r % p.tiles_d;
+      c.n = r / p.tiles_d;
+    }
+    return c;
+  };
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int i = 0; i < H_MAX_PLANES; ++i) mbar_init(&plane_full[i], 1);
-    mbar_init(planes_empty, H_MMA_WARPS);
+    for (int i = 0; i < H_MAX_PLANES; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], H_MMA_WARPS); }
     for (int i = 0; i < H_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], H_MMA_WARPS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], H_MMA_WARPS); mbar_init(&acc_empty[i], H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -98,31 +131,62 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t bcount = 0, bs = 0, bphase = 0;
-      int iter = 0;
-      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
-        int r = st;
-        const int tx = r % p.tiles_w; r /= p.tiles_w;
-        const int ty = r % p.tiles_h; r /= p.tiles_h;
-        const int tz = r % p.tiles_d;
-        const int n = r / p.tiles_d;
-        if (trace && iter < 16) dbg[iter * 16 + 0] = clock64();
-        if (iter > 0) mbar_wait(planes_empty, (iter - 1) & 1, 200);     // previous super-tile's MMAs have read the planes
-        if (trace && iter < 16) dbg[iter * 16 + 1] = clock64();
-        for (int pl = 0; pl < p.np; ++pl)
-          for (int kc = 0; kc < p.nkc; ++kc) {
-            uint64_t* bar = &plane_full[pl * p.nkc + kc];
-            mbar_expect_tx(bar, HP_ROWS * ROWB);
-            tma_load_5d(&tmA, bar, sP + (pl * p.nkc + kc) * p.plane_stride, kc * KC, tx * HT_W - 1, ty * HT_H - 1,
-                        tz * p.td + p.dzmin + pl, n);
-          }
+      // plane cursor: planes are issued strictly in (tile, plane index) order; it may run at most one tile ahead of the B cursor
+      int cL = L_begin, cq = 0, c_ring0 = 0;               // tile / plane index of the next plane to issue, ring position of its plane 0
+      uint32_t used = 0, eph = 0;                           // per ring slot: loaded before? / parity of the next empty-wait
+      auto tile_is_start = [&](int L) { return !p.sliding || L == L_begin || (L % p.tiles_d) == 0; };
+      auto cursor_norm = [&]() {                            // skip the planes the tile shares with its predecessor
+        if (cL < L_end && cq == 0 && !tile_is_start(cL)) cq = p.dzspan;
+      };
+      auto cursor_try = [&](bool block) -> bool {           // issue the plane under the cursor if its slot is free
+        int r = c_ring0 + cq; if (r >= p.np) r -= p.np;
+        if ((used >> r) & 1u) {
+          if (block) mbar_wait(&plane_empty[r], (eph >> r) & 1u, 64);
+          else if (!mbar_try(smem_u32(&plane_empty[r]), (eph >> r) & 1u)) return false;
+          eph ^= 1u << r;
+        }
+        used |= 1u << r;
+        const TileC c = decode(cL);
+        mbar_expect_tx(&plane_full[r], p.nkc * HP_ROWS * ROWB);
+        for (int kc = 0; kc < p.nkc; ++kc)
+          tma_load_5d(&tmA, &plane_full[r], sP + (r * p.nkc + kc) * p.plane_stride, kc * KC, c.tx * HT_W - 1, c.ty * HT_H - 1,
+                      c.tz * p.td + p.dzmin + cq, c.n);
+        if (++cq == p.np) {                                  // next tile: its plane 0 sits td ring positions further
+          cq = 0; ++cL;
+          if (cL < L_end) { if (tile_is_start(cL)) c_ring0 = 0; else { c_ring0 += p.td; if (c_ring0 >= p.np) c_ring0 -= p.np; } }
+          cursor_norm();
+        }
+        return true;
+      };
+      for (int L = L_begin; L < L_end; ++L) {
         for (int pass = 0; pass < p.nphase; ++pass)
-          for (int t = 0; t < p.ntaps; ++t)
+          for (int tp = 0; tp < p.ntaps; ++tp) {
+            const int t = p.tap_order[pass * p.ntaps + tp];
+            // planes this tap needs must have been issued before its weights (else the MMA warps could wait on a plane that
+            // is never requested while this thread blocks on the weight ring)
+            const int q_need = ((p.nphase == 1 && p.sliding) ? (p.tap_off[t][0] - p.dzmin) : p.dzspan) + p.td - 1;
+            while (cL == L && cq <= q_need) cursor_try(true);
             for (int kc = 0; kc < p.nkc; ++kc, ++bcount) {
-              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[bs], bphase ^ 1u, 100);
+              if (p.b_resident && L > L_begin) {               // weights already in shared memory: only keep planes streaming
+                while (cL < L_end && cL <= L + 1 && cursor_try(false)) {}
+                continue;
+              }
+              if (bcount >= (uint32_t)p.nb) {
+                if (!p.sliding) {
+                  mbar_wait(&b_empty[bs], bphase ^ 1u, 100);
+                } else {
+                  const uint32_t addr = smem_u32(&b_empty[bs]);
+                  while (!mbar_try(addr, bphase ^ 1u)) {     // while the ring is full: stream planes of this / the next tile
+                    if (!(cL < L_end && cL <= L + 1 && cursor_try(false))) __nanosleep(64);
+                  }
+                }
+              }
               mbar_expect_tx(&b_full[bs], p.Cout_w * ROWB);
               tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stride, 0, ((pass * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
               if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; }
+              if (p.sliding) while (cL < L_end && cL <= L + 1 && cursor_try(false)) {}
             }
+          }
       }
     }
   } else if (warp < H_EPI_W0) {
@@ -131,7 +195,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     // The issuing thread is latency-bound on its own scalar code, so everything per operand tile is table-driven:
     // sTap[pass*ntaps + t] = (descriptor offset of the tap inside a plane) | (dz - dzmin) << 16, ring indices are counters.
     for (int i = lane; iss == 0 && i < p.nphase * p.ntaps; i += 32) {
-      const int8_t* off = p.tap_off[i];
+      const int8_t* off = p.tap_off[(i / p.ntaps) * p.ntaps + p.tap_order[i]];
       sTap[i] = ((uint32_t)(((off[1] + 1) * HP_W + (off[2] + 1)) * ROWB) >> 4) | ((uint32_t)(off[0] - p.dzmin) << 16);
     }
     asm volatile("bar.sync 2, %0;" ::"n"(32 * H_MMA_WARPS) : "memory");
@@ -141,52 +205,75 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     const uint32_t b_hi = kmajor_desc_hi<KC>(8 * ROWB);
     const uint32_t plane_lo0 = kmajor_desc_lo(smem_u32(sP)), plane_step = (uint32_t)p.plane_stride >> 4;
     const uint32_t b_lo0 = kmajor_desc_lo(smem_u32(sB)), b_step = (uint32_t)p.b_stride >> 4;
-    const uint32_t jstep = (uint32_t)p.nkc * plane_step;
     const int ntap_total = p.ntaps;
+    const int nj = p.td;                     // Do % td == 0 (host)
+    const uint32_t jmask = (1u << nj) - 1u;
     uint32_t bs = 0, bphase = 0;             // B ring slot / parity
     uint32_t buf = 0, acc_use = 0;           // accumulator buffer, number of uses so far
+    uint32_t fph = 0;                        // per ring slot: parity of the next full-wait
+    int ring0 = 0;
     int iter = 0;
-    for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
-      const int tz = (st / (p.tiles_w * p.tiles_h)) % p.tiles_d;
-      const int nj = min(p.td, p.Do - tz * p.td);
-      const uint32_t jmask = (1u << nj) - 1u;
-      uint32_t waited = 0;                   // bit (slice plane * nkc + kc)
+    for (int L = L_begin; L < L_end; ++L, ++iter) {
+      const int tz = L % p.tiles_d;      // (only meaningful when sliding)
+      const bool col_start = !p.sliding || L == L_begin || tz == 0, col_end = !p.sliding || tz == p.tiles_d - 1;
+      if (col_start) ring0 = 0; else { ring0 += p.td; if (ring0 >= p.np) ring0 -= p.np; }
+      uint32_t waited = col_start ? 0u : ((1u << p.dzspan) - 1u);   // plane indices q already resident (shared with the previous tile)
       const long long t_in = trace ? clock64() : 0;
+      long long tw_plane = 0, tw_b = 0, tw_acc = 0;
       for (int pass = 0; pass < p.nphase; ++pass) {
-        if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1);
+        { const long long t0 = trace ? clock64() : 0;
+          if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1);
+          if (trace) tw_acc += clock64() - t0; }
         const uint32_t acc0 = tmem_base + buf * p.acc_stride;
         const uint32_t* taps = sTap + pass * ntap_total;
+        const bool last_pass = pass == p.nphase - 1;
         for (int t = 0; t < ntap_total; ++t) {
           const uint32_t te = taps[t];
           const uint32_t tap16 = te & 0xFFFFu, dzr = te >> 16;
+          // planes this tap touches for the first time in this super-tile: q = dzr .. dzr + nj - 1
+          const long long tp0 = trace ? clock64() : 0;
+          uint32_t need = (jmask << dzr) & ~waited;
+          while (need) {
+            const int q = __ffs(need) - 1;
+            int r = ring0 + q; if (r >= p.np) r -= p.np;
+            mbar_wait(&plane_full[r], (fph >> r) & 1u);
+            fph ^= 1u << r;
+            need &= need - 1;
+          }
+          waited |= jmask << dzr;
+          if (trace) tw_plane += clock64() - tp0;
           for (int kc = 0; kc < p.nkc; ++kc) {
-            // planes this (tap, chunk) touches for the first time in this super-tile (nkc == 1: planes dzr .. dzr+nj-1)
-            if (p.nkc == 1) {
-              uint32_t need = (jmask << dzr) & ~waited;
-              while (need) { const int pl = __ffs(need) - 1; mbar_wait(&plane_full[pl], iter & 1); need &= need - 1; }
-              waited |= jmask << dzr;
-            } else {
-              for (int j = 0; j < nj; ++j) {
-                const int pl = (j + dzr) * p.nkc + kc;
-                if (!((waited >> pl) & 1u)) { mbar_wait(&plane_full[pl], iter & 1); waited |= 1u << pl; }
-              }
-            }
-            mbar_wait(&b_full[bs], bphase);
+            const long long tb0 = trace ? clock64() : 0;
+            mbar_wait(&b_full[bs], p.b_resident ? 0u : bphase);
+            if (trace) tw_b += clock64() - tb0;
             tcgen05_fence_after();
             if (leader) {
               const uint32_t b_lo = b_lo0 + bs * b_step;
-              const uint32_t a_lo = plane_lo0 + (dzr * p.nkc + kc) * plane_step + tap16;
               const uint32_t first = (t | kc) ? 1u : 0u;
               for (int j = iss; j < nj; j += H_MMA_WARPS) {
-                const uint32_t aj = a_lo + j * jstep, dj = acc0 + j * p.Cout_w;
+                int r = ring0 + j + (int)dzr; if (r >= p.np) r -= p.np;
+                const uint32_t aj = plane_lo0 + (uint32_t)(r * p.nkc + kc) * plane_step + tap16, dj = acc0 + j * p.Cout_w;
                 umma_bf16_lohi(dj, aj, a_hi, b_lo, b_hi, idesc, first);
 #pragma unroll
                 for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dj, aj + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);
               }
-              tcgen05_commit(&b_empty[bs]);
+              if (!p.b_resident) tcgen05_commit(&b_empty[bs]);
             }
             __syncwarp();
             if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; }
+          }
+          if (last_pass) {
+            // hand plane slots back to the producer: planes whose last reader was this tap; at the end of a column also the
+            // planes that would otherwise be kept for the next super-tile
+            uint32_t rel = p.rel_after[t];
+            if (t == ntap_total - 1 && col_end) rel |= ((1u << p.np) - 1u) & ~((1u << p.td) - 1u);
+            while (rel) {
+              const int q = __ffs(rel) - 1;
+              int r = ring0 + q; if (r >= p.np) r -= p.np;
+              if (leader) tcgen05_commit(&plane_empty[r]);
+              rel &= rel - 1;
+            }
+            __syncwarp();
           }
         }
         if (leader) tcgen05_commit(&acc_full[buf]);
@@ -194,9 +281,10 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         ++acc_use;
         if (++buf == (uint32_t)p.nbuf) buf = 0;
       }
-      if (leader) tcgen05_commit(planes_empty);
-      __syncwarp();
-      if (trace && iter < 16 && lane == 0 && iss == 0) { dbg[iter * 16 + 2] = t_in; dbg[iter * 16 + 3] = clock64(); }
+      if (trace && iter < 16 && lane == 0 && iss == 0) {
+        dbg[iter * 16 + 2] = t_in; dbg[iter * 16 + 3] = clock64();
+        dbg[iter * 16 + 4] = tw_plane; dbg[iter * 16 + 5] = tw_b; dbg[iter * 16 + 6] = tw_acc;
+      }
     }
   } else {
     // ================= epilogue: 8 warps, two per TMEM lane quarter, splitting the (slice, 16-column chunk) list ==========
@@ -211,12 +299,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     const int nch = p.Cout_w >> 4;
     const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
     uint32_t acc_it = 0;
-    for (int st = blockIdx.x; st < total; st += gridDim.x) {
-      int r = st;
-      const int tx = r % p.tiles_w; r /= p.tiles_w;
-      const int ty = r % p.tiles_h; r /= p.tiles_h;
-      const int tz = r % p.tiles_d;
-      const int n = r / p.tiles_d;
+    for (int L = L_begin; L < L_end; ++L) {
+      const TileC tc = decode(L);
+      const int tx = tc.tx, ty = tc.ty, tz = tc.tz, n = tc.n;
       const int ox = tx * HT_W + rx, oy = ty * HT_H + ry;
       const bool valid_xy = ox < p.Wo && oy < p.Ho;
       const int nitems = min(p.td, p.Do - tz * p.td) * nch;
@@ -304,8 +389,8 @@ __global__ void __launch_bounds__(H_THREADS, 1)
                 o[1] = make_float4(v[8 * e + 4], v[8 * e + 5], v[8 * e + 6], v[8 * e + 7]);
               } else {
                 uint4 w;
-                w.x = pack2_bf16(v[8 * e], v[8 * e + 1]); w.y = pack2_bf16(v[8 * e + 2], v[8 * e + 3]);
-                w.z = pack2_bf16(v[8 * e + 4], v[8 * e + 5]); w.w = pack2_bf16(v[8 * e + 6], v[8 * e + 7]);
+                w.x = ring_pack2_bf16(v[8 * e], v[8 * e + 1]); w.y = ring_pack2_bf16(v[8 * e + 2], v[8 * e + 3]);
+                w.z = ring_pack2_bf16(v[8 * e + 4], v[8 * e + 5]); w.w = ring_pack2_bf16(v[8 * e + 6], v[8 * e + 7]);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + yo) = w;
               }
             }
@@ -319,8 +404,8 @@ __global__ void __launch_bounds__(H_THREADS, 1)
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + yo;
               for (int e = 0; e < nstore; e += 8) {
                 uint4 w;
-                w.x = pack2_bf16(v[e], v[e + 1]); w.y = pack2_bf16(v[e + 2], v[e + 3]);
-                w.z = pack2_bf16(v[e + 4], v[e + 5]); w.w = pack2_bf16(v[e + 6], v[e + 7]);
+                w.x = ring_pack2_bf16(v[e], v[e + 1]); w.y = ring_pack2_bf16(v[e + 2], v[e + 3]);
+                w.z = ring_pack2_bf16(v[e + 4], v[e + 5]); w.w = ring_pack2_bf16(v[e + 6], v[e + 7]);
                 *reinterpret_cast<uint4*>(o + e) = w;
               }
             }
@@ -339,19 +424,19 @@ __global__ void __launch_bounds__(H_THREADS, 1)
 }
 
 template <int KC>
-static int launch_halo(const HaloParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+static int launch_halo_ring(const RingParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
                        const float* prelu, const void* residual, void* y, int grid, size_t smem, cudaStream_t st) {
   long long* dbg = nullptr;
   const char* trace_path = getenv("OFSV_HALO_TRACE");
   if (trace_path) { cudaMalloc(&dbg, 16 * 16 * 8); cudaMemset(dbg, 0, 16 * 16 * 8); }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("ofsv_conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_ring_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("ofsv_conv_halo(ring): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
     attr_done = true;
   }
-  conv_halo_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y, dbg);
-  const int rc = check_launch("conv_halo_kernel");
+  conv_halo_ring_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y, dbg);
+  const int rc = check_launch("conv_halo_ring_kernel");
   if (trace_path) {   // debug only: synchronous dump of CTA 0's timeline
     static long long h[256];
     cudaStreamSynchronize(st);
@@ -368,7 +453,7 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& tmA, const CUtens
   return rc;
 }
 
-static int num_sms() {
+static int ring_num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -384,49 +469,44 @@ using namespace ofsv;
 
 // Same contract as ofsv_conv_tc; returns OFSV_ENOSUP (nothing launched) for layers outside this kernel's domain
 // (strided input, tap offsets outside {-1,0,1}, Cout_w > 128, planes that do not fit shared memory).
-extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
-                              const void* residual, void* y, void* stream) {
+int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                         const void* residual, void* y, void* stream) {
   if (int e = validate_conv_desc(d, "ofsv_conv_halo")) return e;
   if (d->N == 0) return OFSV_OK;
-  OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_halo: null pointer");
-  OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_halo: has_prelu without prelu slopes");
-  OFSV_REQUIRE(!d->has_residual || residual, "ofsv_conv_halo: has_residual without residual");
+  OFSV_REQUIRE(x && w && bias && y, "ofsv_conv_halo(ring): null pointer");
+  OFSV_REQUIRE(!d->has_prelu || prelu, "ofsv_conv_halo(ring): has_prelu without prelu slopes");
+  OFSV_REQUIRE(!d->has_residual || residual, "ofsv_conv_halo(ring): has_residual without residual");
   OFSV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!residual || aligned16(residual)),
-               "ofsv_conv_halo: pointers must be 16-byte aligned");
-  if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo: activations must be bf16"); return OFSV_ENOSUP; }
-  if (d->in_stride != 1) { set_error("ofsv_conv_halo: in_stride must be 1"); return OFSV_ENOSUP; }
-  if (d->Cout_w > 128) { set_error("ofsv_conv_halo: Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
-  if (d->has_residual && d->out_dtype != OFSV_BF16 && !d->out_shuffle) { set_error("ofsv_conv_halo: residual needs a bf16 output"); return OFSV_ENOSUP; }
-  if (d->has_residual && d->out_shuffle && d->out_dtype != OFSV_F32) { set_error("ofsv_conv_halo: depth-to-space residual (flow/mask state) is fp32"); return OFSV_ENOSUP; }
+               "ofsv_conv_halo(ring): pointers must be 16-byte aligned");
+  if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo(ring): activations must be bf16"); return OFSV_ENOSUP; }
+  if (d->in_stride != 1) { set_error("ofsv_conv_halo(ring): in_stride must be 1"); return OFSV_ENOSUP; }
+  if (d->Cout_w > 128) { set_error("ofsv_conv_halo(ring): Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
+  if (d->has_residual && d->out_dtype != OFSV_BF16 && !d->out_shuffle) { set_error("ofsv_conv_halo(ring): residual needs a bf16 output"); return OFSV_ENOSUP; }
+  if (d->has_residual && d->out_shuffle && d->out_dtype != OFSV_F32) { set_error("ofsv_conv_halo(ring): depth-to-space residual (flow/mask state) is fp32"); return OFSV_ENOSUP; }
   if (d->out_shuffle && (d->out_shuffle != 8 || d->nphase != 1 || d->Cout_w != 8 * (1 << d->nd) || d->Cout_s != 8)) {
-    set_error("ofsv_conv_halo: bad depth-to-space configuration");
+    set_error("ofsv_conv_halo(ring): bad depth-to-space configuration");
     return OFSV_EINVAL;
   }
   if (d->out_s2d && (d->nphase != 1 || d->out_stride != 1 || d->has_residual || d->out_shuffle || d->Hy % 2 || d->Wy % 2 ||
                      (d->nd == 3 && d->Dy % 2))) {
-    set_error("ofsv_conv_halo: bad space-to-depth output configuration");
+    set_error("ofsv_conv_halo(ring): bad space-to-depth output configuration");
     return OFSV_EINVAL;
   }
   int dzmin = 1, dzmax = -1;
   for (int i = 0; i < d->nphase * d->ntaps; ++i) {
     const int8_t* o = d->tap_off[i];
     if (o[0] < -1 || o[0] > 1 || o[1] < -1 || o[1] > 1 || o[2] < -1 || o[2] > 1) {
-      set_error("ofsv_conv_halo: tap offset outside {-1,0,1}");
+      set_error("ofsv_conv_halo(ring): tap offset outside {-1,0,1}");
       return OFSV_ENOSUP;
     }
     dzmin = o[0] < dzmin ? o[0] : dzmin;
     dzmax = o[0] > dzmax ? o[0] : dzmax;
   }
-  {  // layers with little tensor work per loaded plane (the 2^d-tap space-to-depth conv0 layers): plane-ring kernel
-    const char* f = getenv("OFSV_HALO_RING");
-    const bool ring = f ? atoi(f) != 0 : (d->nphase == 1 && d->ntaps <= 8);
-    if (ring) return conv_halo_ring(d, x, w, bias, prelu, residual, y, stream);
-  }
   PFN_encodeTiled encode = get_tensor_map_encoder();
-  if (!encode) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
+  if (!encode) { set_error("ofsv_conv_halo(ring): cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
 
   const int KC = d->Cin_s % 64 == 0 ? 64 : (d->Cin_s % 32 == 0 ? 32 : 16);
-  HaloParams P;
+  RingParams P;
   memset(&P, 0, sizeof(P));
   P.N = d->N; P.Do = d->Do; P.Ho = d->Ho; P.Wo = d->Wo; P.Dy = d->Dy; P.Hy = d->Hy; P.Wy = d->Wy;
   P.Cout_s = d->Cout_s; P.Cout_w = d->Cout_w; P.out_stride = d->out_stride; P.nphase = d->nphase; P.ntaps = d->ntaps;
@@ -438,16 +518,16 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   P.shuffle = d->out_shuffle; P.nd = d->nd; P.out_s2d = d->out_s2d;
   { const char* f = getenv("OFSV_HALO_DBGFLAGS"); P.dbg_flags = f ? atoi(f) : 0; }   // bring-up switches (1 = skip epilogue work)
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
-  const int sms = num_sms();
+  const int sms = ring_num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
-  const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
+  const size_t bar_bytes = (2 * H_MAX_PLANES + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
   // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
   int td = 0;
   const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits
   const int forced = force ? atoi(force) : 0;
   for (int cand = 4; cand >= 1; cand >>= 1) {
     if (forced && cand != forced && cand > 1) continue;
-    if (cand > d->Do && cand > 1) continue;
+    if (d->Do % cand) continue;                       // the plane ring assumes full super-tiles along z
     const int np = cand + (dzmax - dzmin);
     if (np * P.nkc > H_MAX_PLANES) continue;
     if (cand * d->Cout_w > 512) continue;
@@ -457,17 +537,46 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     td = cand;
     break;
   }
-  if (td == 0) { set_error("ofsv_conv_halo: layer does not fit (Cin_s=%d Cout_w=%d)", d->Cin_s, d->Cout_w); return OFSV_ENOSUP; }
-  P.td = td; P.np = td + (dzmax - dzmin);
-  P.tiles_d = (int)cdiv(d->Do, td);
+  if (td == 0) { set_error("ofsv_conv_halo(ring): layer does not fit (Cin_s=%d Cout_w=%d)", d->Cin_s, d->Cout_w); return OFSV_ENOSUP; }
+  P.td = td; P.np = td + (dzmax - dzmin); P.dzspan = dzmax - dzmin;
+  P.tiles_d = d->Do / td;
+  // tap order per pass: ascending dz (stable), so that the lowest planes of a super-tile are finished first; single-pass
+  // layers release plane q < td right after the last tap that reads it (dz = dzmin + min(q, dzspan))
+  for (int ph = 0; ph < d->nphase; ++ph) {
+    int pos = 0;
+    for (int dz = dzmin; dz <= dzmax; ++dz)
+      for (int t = 0; t < d->ntaps; ++t)
+        if (d->tap_off[ph * d->ntaps + t][0] == dz) P.tap_order[ph * d->ntaps + pos++] = (uint8_t)t;
+  }
+  {  // the plane ring pays off where a super-tile has little tensor work per loaded plane (few taps, several channel chunks);
+     // layers with a long tap loop hide their plane loads anyway and measured ~10 % slower with it on B200
+    const int mmas = d->nphase * d->ntaps * P.nkc * (KC / 16) * td;
+    const char* f = getenv("OFSV_HALO_SLIDING");
+    P.sliding = f ? atoi(f) : (mmas <= 256 ? 1 : 0);
+  }
+  if (d->nphase == 1 && P.sliding) {
+    for (int q = 0; q < td; ++q) {
+      const int last_dz = dzmin + (q < P.dzspan ? q : P.dzspan);
+      int pos = -1;
+      for (int t = 0; t < d->ntaps; ++t)
+        if (d->tap_off[P.tap_order[t]][0] == last_dz) pos = t;
+      if (pos < 0) pos = d->ntaps - 1;
+      P.rel_after[pos] |= (uint8_t)(1u << q);
+    }
+  } else {
+    P.rel_after[d->ntaps - 1] = (uint8_t)((1u << td) - 1u);
+  }
   const size_t fixed = (size_t)P.np * P.nkc * P.plane_stride + bar_bytes + 1024;
   int nb = (int)((smem_cap - fixed) / P.b_stride);
   nb = nb > H_MAX_BSTAGES ? H_MAX_BSTAGES : nb;
+  const int nbt = d->nphase * d->ntaps * P.nkc;       // weight tiles of the layer
+  if (nb >= nbt) { nb = nbt; P.b_resident = 1; }
+  else if (nb > 8) nb = 8;
   P.nb = nb;
   P.nbuf = (2 * td * d->Cout_w <= 512) ? 2 : 1;
   P.acc_stride = 256;
   const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
-  OFSV_REQUIRE(total < (1ll << 31), "ofsv_conv_halo: too many super-tiles");
+  OFSV_REQUIRE(total < (1ll << 31), "ofsv_conv_halo(ring): too many super-tiles");
   const size_t smem = fixed + (size_t)nb * P.b_stride;
 
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -481,7 +590,7 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return OFSV_ECUDA; }
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo(ring): cuTensorMapEncodeTiled(A) failed with %d", (int)r); return OFSV_ECUDA; }
   }
   {
     const cuuint64_t rows = (cuuint64_t)d->nphase * d->ntaps * P.nkc * d->Cout_w;
@@ -491,11 +600,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
+    if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo(ring): cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
   }
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = (cudaStream_t)stream;
-  if (KC == 64) return launch_halo<64>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
-  if (KC == 32) return launch_halo<32>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
-  return launch_halo<16>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+  if (KC == 64) return launch_halo_ring<64>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+  if (KC == 32) return launch_halo_ring<32>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
+  return launch_halo_ring<16>(P, tmA, tmB, bias, prelu, residual, y, grid, smem, st);
 }

@@ -180,5 +180,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_tensor_map_encoder();   // conv_tc.cu
 int validate_conv_desc(const ofsv_conv_desc* d, const char* who);  // conv_simt.cu
+// conv_halo_ring.cu: same contract as ofsv_conv_halo (called by it for the layers the plane ring is faster on)
+int conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
+                   const void* residual, void* y, void* stream);
 
 }  // namespace ofsv

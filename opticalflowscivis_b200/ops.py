@@ -21,6 +21,7 @@ class LaunchTimer:
 
     def __init__(self):
         self.spans = {}
+        self.seq = []          # (class, start event, stop event) in launch order
 
     class _Span:
         def __init__(self, owner, name):
@@ -35,6 +36,7 @@ class LaunchTimer:
         def __exit__(self, *exc):
             self.b.record()
             self.o.spans.setdefault(self.name, []).append((self.a, self.b))
+            self.o.seq.append((self.name, self.a, self.b))
             return False
 
     def span(self, name):
