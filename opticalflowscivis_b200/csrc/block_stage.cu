@@ -82,6 +82,12 @@ constexpr int BS_DZ = 8;                     // d planes walked by one CTA
 constexpr int BS_FROW = BS_W * 4 + 4;        // floats per tile row of a half-state tile (+16 B pad: lanes along h hit distinct banks)
 constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile
 
+// head tile of one (tile, plane) for SH > 1: the 2 x (32/SH + 2) x (8/SH + 2) coarse voxels all trilinear taps fall into
+__host__ __device__ constexpr int bs_head_rows(int SH) { return SH > 1 ? BS_H / SH + 2 : 0; }
+__host__ __device__ constexpr int bs_head_cols(int SH) { return SH > 1 ? BS_W / SH + 2 : 0; }
+__host__ __device__ constexpr int bs_head_rowf(int SH) { return SH > 1 ? bs_head_cols(SH) * 8 + 4 : 0; }   // floats per row (+16 B pad)
+__host__ __device__ constexpr int bs_head_tile(int SH) { return 2 * bs_head_rows(SH) * bs_head_rowf(SH); }
+
 // shared-memory carve-up (bytes) — must match the kernel
 __host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
   return BS_NST * 2 * BS_HALF * 4                       // s_fa, s_fb   (prev state, updated in place)
@@ -90,7 +96,8 @@ __host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
          + 2 * BS_H * (BS_W + 1) * 4                    // s_out
          + (SN == 1 ? BS_H * BS_PKROW * 16 : 0)         // s_pk
          + (SN == 2 ? 22 * BS_H * (BS_W + 1) * 4 : 0)   // s_pool
-         + 4 * (BS_H + BS_W + BS_DZ) * 4;               // tap tables
+         + 4 * (BS_H + BS_W + BS_DZ) * 4                // tap tables
+         + BS_NST * bs_head_tile(SH) * 4;               // coarse head voxels of the plane's taps (SH > 1)
 }
 
 // SH: scale of the head (1, 2, 4), or 0 = the state is already accumulated (fm_prev holds flow/mask, nothing is added and
@@ -112,6 +119,8 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
   float (*s_pool)[BS_H][BS_W + 1] = reinterpret_cast<float (*)[BS_H][BS_W + 1]>(s_pk + (SN == 1 ? BS_H * BS_PKROW : 0));
   int* s_li = reinterpret_cast<int*>(&s_pool[SN == 2 ? 22 : 0][0][0]);   // i0, i1 element offsets of the head taps per tile row / col / plane
   float* s_ll = reinterpret_cast<float*>(s_li + 2 * (BS_H + BS_W + BS_DZ));
+  float* s_head = s_ll + 2 * (BS_H + BS_W + BS_DZ);                // [NST][2 z taps][HNR][HRF]
+  constexpr int HNR = bs_head_rows(SH), HNC = bs_head_cols(SH), HRF = bs_head_rowf(SH), HTILE = bs_head_tile(SH);
 
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int V = D * HW;                                     // < 2^28 (host check): 32-bit offsets inside one sample
@@ -146,6 +155,18 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
       if (SH == 1) { cp_async16(s_ha + st * BS_HALF + sP, hb + g * 8); cp_async16(s_hb + st * BS_HALF + sP, hb + g * 8 + 4); }
       if (SN != 0) { cp_async4(&s_img[st][0][rP][cP], i0p + g); cp_async4(&s_img[st][1][rP][cP], i1p + g); }
     }
+    if (SH > 1 && it < nplanes) {
+      // the coarse head voxels this plane's taps need, so that phase A interpolates from shared memory
+      const int st = it % BS_NST;
+      const float rs = 1.0f / (float)SHD;
+      const Lerp1s lz = up_index1s(dbeg + it, Dh, rs);
+      const int yb = up_index1s(h0, Hh, rs).i0, xb = up_index1s(w0, Wh, rs).i0;
+      for (int idx = tid; idx < 2 * HNR * HNC * 2; idx += 256) {
+        const int half = idx & 1, c = (idx >> 1) % HNC, r = ((idx >> 1) / HNC) % HNR, z = (idx >> 1) / (HNC * HNR);
+        const int zz = z ? lz.i1 : lz.i0, yy = min(yb + r, Hh - 1), xx = min(xb + c, Wh - 1);
+        cp_async16(s_head + st * HTILE + (z * HNR + r) * HRF + c * 8 + half * 4, hb + (((int64_t)zz * Hh + yy) * Wh + xx) * 8 + half * 4);
+      }
+    }
     cp_async_commit();
   };
   issue(0);
@@ -155,12 +176,14 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
     // per-axis tap tables of F.interpolate(scale_factor = SH, align_corners = False) for this tile column
     constexpr int NT = BS_H + BS_W + BS_DZ;
     if (tid < NT) {
-      int dst, n_in, stride;
-      if (tid < BS_H) { dst = h0 + tid; n_in = Hh; stride = Wh * 8; }
-      else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 8; }
-      else { dst = dbeg + tid - BS_H - BS_W; n_in = Dh; stride = Hh * Wh * 8; }
-      const Lerp1s L = up_index1s(dst, n_in, 1.0f / (float)SHD);
-      s_li[2 * tid] = L.i0 * stride; s_li[2 * tid + 1] = L.i1 * stride;
+      // offsets inside the plane's head tile [z tap][row - yb][col - xb][8]
+      int dst, n_in, stride, base;
+      const float rs = 1.0f / (float)SHD;
+      if (tid < BS_H) { dst = h0 + tid; n_in = Hh; stride = HRF; base = up_index1s(h0, Hh, rs).i0; }
+      else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 8; base = up_index1s(w0, Wh, rs).i0; }
+      else { dst = dbeg + tid - BS_H - BS_W; n_in = Dh; stride = 0; base = 0; }
+      const Lerp1s L = up_index1s(dst, n_in, rs);
+      s_li[2 * tid] = (L.i0 - base) * stride; s_li[2 * tid + 1] = (L.i1 - base) * stride;
       s_ll[2 * tid] = L.l0; s_ll[2 * tid + 1] = L.l1;
     }
   }
@@ -184,13 +207,13 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
         } else {
           const int ty = rP, tx = BS_H + cP, tz = BS_H + BS_W + it;
           const int y0 = s_li[2 * ty], y1 = s_li[2 * ty + 1], x0 = s_li[2 * tx], x1 = s_li[2 * tx + 1];
-          const int z0 = s_li[2 * tz], z1 = s_li[2 * tz + 1];
+          const int z0 = 0, z1 = HNR * HRF;
           const float ly0 = s_ll[2 * ty], ly1 = s_ll[2 * ty + 1], lx0 = s_ll[2 * tx], lx1 = s_ll[2 * tx + 1];
           const float lz0 = s_ll[2 * tz], lz1 = s_ll[2 * tz + 1];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const float* r = hb + half * 4;
-            auto L4 = [&](int o) { return __ldg(reinterpret_cast<const float4*>(r + o)); };
+            const float* r = s_head + st * HTILE + half * 4;
+            auto L4 = [&](int o) { return *reinterpret_cast<const float4*>(r + o); };
             const float4 a00 = lerp4(L4(z0 + y0 + x0), lx0, L4(z0 + y0 + x1), lx1);
             const float4 a01 = lerp4(L4(z0 + y1 + x0), lx0, L4(z0 + y1 + x1), lx1);
             const float4 a10 = lerp4(L4(z1 + y0 + x0), lx0, L4(z1 + y0 + x1), lx1);
