@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (nd, spatial, pairs per GPU per step, BASELINE.json config it stands for)
-    "flow3d_droplet256": (3, (256, 256, 256), 1, "Flow-3D droplet-shaped 256^3 byte volume pairs, ensemble batch-sharded"),
+    "flow3d_droplet256": (3, (256, 256, 256), 4, "Flow-3D droplet-shaped 256^3 byte volume pairs, ensemble batch-sharded"),
     "flow3d_rect128": (3, (128, 128, 128), 4, "Flow-3D IFNet on synthetic 3D textured rectangle 128^3, batch 4"),
     "flow2d_droplet": (2, (160, 224), 64, "Flow-2D droplet-shaped 160x224 monochrome, batch 64"),
 }
