@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
   uint64_t* acc_full = b_empty + H_MAX_BSTAGES;           // [2]
   uint64_t* acc_empty = acc_full + 2;                     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* sBias = reinterpret_cast<float*>(tmem_slot + 4);   // [128]
+  float* sBias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [128], 16 B aligned
   float* sPrelu = sBias + 128;                              // [128]
   uint32_t* sTap = reinterpret_cast<uint32_t*>(sPrelu + 128); // [OFSV_MAX_TAPS]
 
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           rnext[0] = __ldg(reinterpret_cast<const uint4*>(rp)); rnext[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
         }
         const long long te0 = clock64();
-        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 400);   // long waits: sleep, do not poll
+        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 128);   // long waits: sleep between polls
         tcgen05_fence_after();
         const long long te1 = clock64();
         for (int it = half; it < ((p.dbg_flags & 1) ? 0 : nitems); it += 2) {
@@ -358,9 +358,15 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           tmem_ld16(tmem_base + buf * p.acc_stride + j * p.Cout_w + c0 + ((uint32_t)(q * 32) << 16), v);
           if (!valid_xy) continue;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float a = v[e] + sBias[c0 + e];
-            v[e] = a > 0.0f ? a : a * sPrelu[c0 + e];
+          for (int e4 = 0; e4 < 4; ++e4) {          // 16 B shared loads: the epilogue competes with the UMMA operand fetch
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + e4 * 4);
+            const float4 p4 = *reinterpret_cast<const float4*>(sPrelu + c0 + e4 * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = v[e4 * 4 + e] + bb[e];
+              v[e4 * 4 + e] = fmaxf(a, 0.0f) + pp[e] * fminf(a, 0.0f);
+            }
           }
           if (res_f32) {            // flow/mask state accumulation: fm = fm_prev + head (Flow-3D/model/IFNet.py:169-170)
 #pragma unroll
@@ -520,7 +526,7 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
   const int sms = ring_num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
-  const size_t bar_bytes = (2 * H_MAX_PLANES + 2 * H_MAX_BSTAGES + 4) * 8 + 16 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
+  const size_t bar_bytes = (2 * H_MAX_PLANES + 2 * H_MAX_BSTAGES + 4) * 8 + 32 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
   // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
   int td = 0;
   const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits
