@@ -7,63 +7,110 @@ namespace ofsv {
 // ----------------------------------------------------------------------------------------------------
 // correlation-81 forward.
 //   out[b,(dy+4)*9+(dx+4),y,x] = (1/C) sum_c f1[b,c,y,x] * f2[b,c,y+dy,x+dx]   (zero outside), optional LeakyReLU.
-// CTA = 32x8 output pixels of one sample.  Channel chunks of CC are staged in shared memory with their 4-pixel halo
-// ((8+8) x (32+8) per channel); each thread owns one pixel and keeps the 81 displacement sums in registers, so every
-// f2 element fetched from HBM is used 81 times and f1 once per displacement from a register.
+// CTA = 32(x) x 8(y) output pixels of one sample, 288 threads = 9 warps: warp = displacement row dy, lane = (pair of pixel
+// rows, quad of 4 consecutive x).  Channel chunks of CC are staged in shared memory with their 4-pixel halo (16 B global
+// loads, one fixed tile position per thread, channels walked by pointer increment); per channel a thread reads its 8 f1
+// values and the 2 x 12 f2 values its 8 pixels x 9 dx need with eight 16 B shared loads and does 72 FMAs into registers
+// (9 FMAs per shared load instead of 1), so the kernel is FMA-bound rather than shared-memory-bound.
 // ----------------------------------------------------------------------------------------------------
 constexpr int CTW = 32, CTH = 8, CMD = 4, CC = 8;
 constexpr int CHW = CTW + 2 * CMD, CHH = CTH + 2 * CMD;
 
-__global__ void __launch_bounds__(CTW* CTH)
+template <bool VEC>
+__global__ void __launch_bounds__(288)
     corr81_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int C, int H,
-                      int W, float inv_c_unused, float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
-  __shared__ float s2[CC][CHH][CHW];
-  __shared__ float s1[CC][CTH][CTW];
+                      int W, float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
+  __shared__ __align__(16) float s2[CC][CHH][CHW];
+  __shared__ __align__(16) float s1[CC][CTH][CTW];
   const int b = blockIdx.z, x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * CTW + tx;
+  const int tid = threadIdx.x;
+  const int q = tid & 7, rp = (tid >> 3) & 3, dy = tid >> 5;       // quad, pixel-row pair, displacement row (warp-uniform)
   const int64_t HW = (int64_t)H * W;
   const float* p1 = f1 + (int64_t)b * C * HW;
   const float* p2 = f2 + (int64_t)b * C * HW;
-  float acc[81];
+  // loader role: threads 0..159 own one 16 B column of the f2 halo tile (16 rows x 10 quads), threads 160..223 one of the f1
+  // tile (8 rows x 8 quads); the position (and its bounds check) is fixed, only the channel pointer moves
+  const bool ld2 = tid < CHH * (CHW / 4), ld1 = tid >= 160 && tid < 160 + CTH * (CTW / 4);
+  int lyy = 0, lxx = 0;
+  bool lin = false;
+  const float* lsrc = nullptr;
+  if (ld2) { lyy = tid / (CHW / 4); lxx = (tid % (CHW / 4)) * 4; const int y = y0 + lyy - CMD, x = x0 + lxx - CMD;
+             lin = y >= 0 && y < H && x >= 0 && x < W; lsrc = p2 + (int64_t)y * W + x; }
+  if (ld1) { const int t = tid - 160; lyy = t / (CTW / 4); lxx = (t % (CTW / 4)) * 4; const int y = y0 + lyy, x = x0 + lxx;
+             lin = y < H && x < W; lsrc = p1 + (int64_t)y * W + x; }
+  const int lx_glob = ld2 ? x0 + lxx - CMD : x0 + lxx;
+  float acc[2][4][9];
 #pragma unroll
-  for (int k = 0; k < 81; ++k) acc[k] = 0.0f;
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[j][i][k] = 0.0f;
 
   for (int c0 = 0; c0 < C; c0 += CC) {
     const int cc = min(CC, C - c0);
-    for (int i = tid; i < CC * CHH * CHW; i += CTW * CTH) {
-      const int c = i / (CHH * CHW), r = i - c * (CHH * CHW), yy = r / CHW, xx = r - yy * CHW;
-      const int y = y0 + yy - CMD, x = x0 + xx - CMD;
-      float v = 0.0f;
-      if (c < cc && y >= 0 && y < H && x >= 0 && x < W) v = __ldg(p2 + (int64_t)(c0 + c) * HW + (int64_t)y * W + x);
-      s2[c][yy][xx] = v;
-    }
-    for (int i = tid; i < CC * CTH * CTW; i += CTW * CTH) {
-      const int c = i / (CTH * CTW), r = i - c * (CTH * CTW), yy = r / CTW, xx = r - yy * CTW;
-      const int y = y0 + yy, x = x0 + xx;
-      float v = 0.0f;
-      if (c < cc && y < H && x < W) v = __ldg(p1 + (int64_t)(c0 + c) * HW + (int64_t)y * W + x);
-      s1[c][yy][xx] = v;
+    if (ld1 || ld2) {
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < cc && lin) {
+          const float* g = lsrc + (int64_t)(c0 + c) * HW;
+          if (VEC) {
+            v = __ldg(reinterpret_cast<const float4*>(g));
+          } else {                      // rows not 16 B aligned (W % 4 != 0) or ragged right edge
+            v.x = __ldg(g);
+            if (lx_glob + 1 >= 0 && lx_glob + 1 < W) v.y = __ldg(g + 1);
+            if (lx_glob + 2 >= 0 && lx_glob + 2 < W) v.z = __ldg(g + 2);
+            if (lx_glob + 3 >= 0 && lx_glob + 3 < W) v.w = __ldg(g + 3);
+          }
+        }
+        if (ld2) *reinterpret_cast<float4*>(&s2[c][lyy][lxx]) = v; else *reinterpret_cast<float4*>(&s1[c][lyy][lxx]) = v;
+      }
     }
     __syncthreads();
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < CC; ++c) {
-      const float a = s1[c][ty][tx];
 #pragma unroll
-      for (int dy = 0; dy < 9; ++dy)
+      for (int j = 0; j < 2; ++j) {
+        const int r = 2 * rp + j;
+        const float4 a4 = *reinterpret_cast<const float4*>(&s1[c][r][4 * q]);
+        const float4 r0 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q]);
+        const float4 r1 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q + 4]);
+        const float4 r2 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q + 8]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float row[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-        for (int dx = 0; dx < 9; ++dx) acc[dy * 9 + dx] = fmaf(a, s2[c][ty + dy][tx + dx], acc[dy * 9 + dx]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc[j][i][k] = fmaf(a[i], row[i + k], acc[j][i][k]);
+      }
     }
     __syncthreads();
   }
-  const int x = x0 + tx, y = y0 + ty;
-  if (x < W && y < H) {
-    float* o = out + (int64_t)b * out_batch_stride + (int64_t)y * W + x;
-    const float cf = (float)C;
+  const float cf = (float)C;
 #pragma unroll
-    for (int k = 0; k < 81; ++k) {
-      float v = acc[k] / cf;  // torch.mean = sum / C
-      if (apply_leaky && v < 0.0f) v *= leaky_slope;
-      o[(int64_t)k * HW] = v;
+  for (int j = 0; j < 2; ++j) {
+    const int x = x0 + 4 * q, y = y0 + 2 * rp + j;
+    if (y < H && x < W) {
+      float* o = out + (int64_t)b * out_batch_stride + (int64_t)(dy * 9) * HW + (int64_t)y * W + x;
+      const bool vec = VEC && (x + 3 < W) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) && ((HW & 3) == 0);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = acc[j][i][k] / cf;  // torch.mean = sum / C
+          if (apply_leaky && v[i] < 0.0f) v[i] *= leaky_slope;
+        }
+        float* ok = o + (int64_t)k * HW;
+        if (vec) {
+          *reinterpret_cast<float4*>(ok) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (x + i < W) ok[i] = v[i];
+        }
+      }
     }
   }
 }
@@ -186,9 +233,11 @@ extern "C" int ofsv_corr81_fwd_f32(const float* f1, const float* f2, float* out,
   OFSV_REQUIRE(out_batch_stride >= (int64_t)81 * H * W, "ofsv_corr81_fwd_f32: out_batch_stride %lld < 81*H*W",
                (long long)out_batch_stride);
   OFSV_REQUIRE(B <= 65535, "ofsv_corr81_fwd_f32: batch %d exceeds grid.z", B);
-  const dim3 grid((unsigned)cdiv(W, CTW), (unsigned)cdiv(H, CTH), (unsigned)B), block(CTW, CTH);
-  corr81_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, 0.0f, leaky_slope, apply_leaky,
-                                                              out_batch_stride);
+  OFSV_REQUIRE(cdiv(H, CTH) <= 65535, "ofsv_corr81_fwd_f32: H too large");
+  const dim3 grid((unsigned)cdiv(W, CTW), (unsigned)cdiv(H, CTH), (unsigned)B);
+  const bool vec = (W % 4 == 0) && aligned16(f1) && aligned16(f2);
+  if (vec) corr81_fwd_kernel<true><<<grid, 288, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, leaky_slope, apply_leaky, out_batch_stride);
+  else corr81_fwd_kernel<false><<<grid, 288, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, leaky_slope, apply_leaky, out_batch_stride);
   return check_launch("corr81_fwd_kernel");
 }
 
