@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
   float (*s_pool)[BS_H][BS_W + 1] = reinterpret_cast<float (*)[BS_H][BS_W + 1]>(s_pk + (SN == 1 ? BS_H * BS_PKROW : 0));
   int* s_li = reinterpret_cast<int*>(&s_pool[SN == 2 ? 22 : 0][0][0]);   // i0, i1 element offsets of the head taps per tile row / col / plane
   float* s_ll = reinterpret_cast<float*>(s_li + 2 * (BS_H + BS_W + BS_DZ));
-  float* s_head = s_ll + 2 * (BS_H + BS_W + BS_DZ);                // [NST][2 z taps][HNR][HRF]
+  float* s_head = s_ll + 2 * (BS_H + BS_W + BS_DZ);                // [NST][2 z taps][HNR][2 halves][HNC][4] (+16 B row pad)
   constexpr int HNR = bs_head_rows(SH), HNC = bs_head_cols(SH), HRF = bs_head_rowf(SH), HTILE = bs_head_tile(SH);
 
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
       for (int idx = tid; idx < 2 * HNR * HNC * 2; idx += 256) {
         const int half = idx & 1, c = (idx >> 1) % HNC, r = ((idx >> 1) / HNC) % HNR, z = (idx >> 1) / (HNC * HNR);
         const int zz = z ? lz.i1 : lz.i0, yy = min(yb + r, Hh - 1), xx = min(xb + c, Wh - 1);
-        cp_async16(s_head + st * HTILE + (z * HNR + r) * HRF + c * 8 + half * 4, hb + (((int64_t)zz * Hh + yy) * Wh + xx) * 8 + half * 4);
+        cp_async16(s_head + st * HTILE + (z * HNR + r) * HRF + half * (HNC * 4) + c * 4, hb + (((int64_t)zz * Hh + yy) * Wh + xx) * 8 + half * 4);
       }
     }
     cp_async_commit();
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
       int dst, n_in, stride, base;
       const float rs = 1.0f / (float)SHD;
       if (tid < BS_H) { dst = h0 + tid; n_in = Hh; stride = HRF; base = up_index1s(h0, Hh, rs).i0; }
-      else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 8; base = up_index1s(w0, Wh, rs).i0; }
+      else if (tid < BS_H + BS_W) { dst = w0 + tid - BS_H; n_in = Wh; stride = 4; base = up_index1s(w0, Wh, rs).i0; }
       else { dst = dbeg + tid - BS_H - BS_W; n_in = Dh; stride = 0; base = 0; }
       const Lerp1s L = up_index1s(dst, n_in, rs);
       s_li[2 * tid] = (L.i0 - base) * stride; s_li[2 * tid + 1] = (L.i1 - base) * stride;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
           const float lz0 = s_ll[2 * tz], lz1 = s_ll[2 * tz + 1];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const float* r = s_head + st * HTILE + half * 4;
+            const float* r = s_head + st * HTILE + half * (HNC * 4);     // [z tap][row][half][col][4]: the 16 B taps of a tile row are contiguous
             auto L4 = [&](int o) { return *reinterpret_cast<const float4*>(r + o); };
             const float4 a00 = lerp4(L4(z0 + y0 + x0), lx0, L4(z0 + y0 + x1), lx1);
             const float4 a01 = lerp4(L4(z0 + y1 + x0), lx0, L4(z0 + y1 + x1), lx1);
