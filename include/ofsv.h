@@ -100,6 +100,10 @@ int ofsv_pack_block_input(const float* img0, const float* img1, const float* war
 /* s2d = 1: dst is the shifted space-to-depth tensor [N][Dn/2+1][Hn/2+1][Wn/2+1][2^nd][Cs] of the resized grid
  * (Dn,Hn,Wn) = (D,H,W)/scale (see ofsv_conv_desc.out_s2d); only interior sub-cells are written. */
 
+/* Data edge: uint8 volume -> fp32, dst[i] = (float)src[i] / div with IEEE division (div = 255 reproduces
+ * the reference loaders' `/ 255.`: Datasets/read_data.py, Flow-3D/load_datasets.py), so only bytes cross PCIe. */
+int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream);
+
 #define OFSV_MAX_TAPS 64
 /* One convolution layer in "tap" form.  For every phase ph, every virtual output position o = (oz,oy,ox) in
  * [0,Do)x[0,Ho)x[0,Wo):

@@ -163,6 +163,25 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// uint8 volume -> fp32 in [0,1]: float(x) / 255.0f (true division, what the reference loaders compute on the host:
+// Datasets/read_data.py, Flow-3D/load_datasets.py).  16 voxels per thread: one 16 B load, four 16 B stores.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n, float div) {
+  const int64_t nv = n >> 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float4* o = reinterpret_cast<float4*>(dst) + i * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = make_float4(__fdiv_rn((float)(w[k] & 0xFFu), div), __fdiv_rn((float)((w[k] >> 8) & 0xFFu), div),
+                         __fdiv_rn((float)((w[k] >> 16) & 0xFFu), div), __fdiv_rn((float)(w[k] >> 24), div));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 15)) {
+    const int64_t i = (nv << 4) + threadIdx.x;
+    dst[i] = __fdiv_rn((float)src[i], div);
+  }
+}
+
 static inline int grid_1d(int64_t total) {
   int64_t b = cdiv(total, 256);
   const int64_t cap = 148 * 32;
@@ -216,4 +235,13 @@ extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* fl
   if (nd == 2) head_upsample_add_kernel<2><<<g, 256, 0, st>>>(head, Cs, flow_prev, mask_prev, flow_out, mask_out, N, D, H, W, scale);
   else head_upsample_add_kernel<3><<<g, 256, 0, st>>>(head, Cs, flow_prev, mask_prev, flow_out, mask_out, N, D, H, W, scale);
   return check_launch("head_upsample_add_kernel");
+}
+
+extern "C" int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream) {
+  OFSV_REQUIRE(n >= 0 && div != 0.0f, "ofsv_u8_to_f32: bad arguments");
+  if (n == 0) return OFSV_OK;
+  OFSV_REQUIRE(src && dst, "ofsv_u8_to_f32: null pointer");
+  OFSV_REQUIRE(aligned16(src) && aligned16(dst), "ofsv_u8_to_f32: pointers must be 16-byte aligned");
+  u8_to_f32_kernel<<<grid_1d(cdiv(n, 16)), 256, 0, (cudaStream_t)stream>>>(src, dst, n, div);
+  return check_launch("u8_to_f32_kernel");
 }

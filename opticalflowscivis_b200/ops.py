@@ -332,5 +332,16 @@ def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
     return y
 
 
+def u8_to_f32(src: torch.Tensor, div: float = 255.0) -> torch.Tensor:
+    """uint8 CUDA tensor -> fp32 `src / div` (IEEE division, bit-identical to `src.float() / div`) in one pass."""
+    if not isinstance(src, torch.Tensor) or not src.is_cuda or src.dtype != torch.uint8:
+        raise TypeError("u8_to_f32: expected a uint8 CUDA tensor")
+    src = src.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _C.check(_C.lib().ofsv_u8_to_f32(_p(src), _p(dst), src.numel(), float(div), _stream()))
+    return dst
+
+
 def launch_count() -> int:
     return int(_C.lib().ofsv_launch_count())

@@ -30,7 +30,8 @@ class StreamedInterpolator:
                  select: Optional[Callable] = None, depth: int = 2):
         self.model = model
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.to_float = to_float or (lambda t: t.float().div_(255.0) if t.dtype == torch.uint8 else t)
+        from . import ops
+        self.to_float = to_float or (lambda t: ops.u8_to_f32(t, 255.0) if t.dtype == torch.uint8 else t)
         self.select = select or (lambda out: out[0] if torch.is_tensor(out[0]) else out[0][2])
         self.depth = max(2, depth)
         self.s_in = torch.cuda.Stream(self.dev)

@@ -391,6 +391,29 @@ def test_model_inference_vs_oracle(nd, precision):
         assert abs(p_ref - p_mine) <= 0.05                 # frames within 0.05 dB PSNR
 
 
+def test_u8_to_f32_and_streamed_interpolator():
+    """The data edge: ofsv_u8_to_f32 == x.float()/255 bit for bit; StreamedInterpolator == plain inference on each pair."""
+    from opticalflowscivis_b200 import ops, synth
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    from opticalflowscivis_b200.pipeline import StreamedInterpolator
+    x = torch.randint(0, 256, (3, 1, 7, 9, 11), dtype=torch.uint8)          # ragged tail (2079 elements)
+    assert torch.equal(ops.u8_to_f32(x.to(_dev())).cpu(), x.float() / 255.0)
+    with pytest.raises(TypeError):
+        ops.u8_to_f32(x)
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    pairs = []
+    for i in range(3):
+        a, _, b = synth.droplet3d_u8(1, 32, seed=1234 + i)
+        pairs.append((torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()))
+    outs = [o.clone() for o in StreamedInterpolator(m, _dev()).run(iter(pairs))]
+    assert len(outs) == 3
+    for (a, b), o in zip(pairs, outs):
+        ref = m.inference(a.to(_dev()).float() / 255.0, b.to(_dev()).float() / 255.0)[0]
+        assert torch.equal(o, ref.cpu())
+
+
 def test_model_surface():
     from opticalflowscivis_b200.flow2d.model.RIFE import Model as M2
     from opticalflowscivis_b200.flow3d.model.RIFE import Model as M3
