@@ -67,7 +67,12 @@ __global__ void __launch_bounds__(H_THREADS, 1)
                      void* __restrict__ y, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROWB = KC * 2;
+#ifdef OFSV_RING_TRACE   // compile-time: clock reads inside the MMA issue loop cost ~10 % on the 27-tap layers
   const bool trace = dbg != nullptr && blockIdx.x == 0;   // OFSV_HALO_TRACE: per-super-tile clock64 timeline of CTA 0
+#else
+  constexpr bool trace = false;
+  (void)dbg;
+#endif
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nplanes = p.np * p.nkc;
   uint8_t* sP = smem;
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
       auto cursor_norm = [&]() {                            // skip the planes the tile shares with its predecessor
         if (cL < L_end && cq == 0 && !tile_is_start(cL)) cq = p.dzspan;
       };
+      TileC cc = decode(cL < L_end ? cL : L_begin);         // coordinates of the cursor's tile (decoded once per tile)
       auto cursor_try = [&](bool block) -> bool {           // issue the plane under the cursor if its slot is free
         int r = c_ring0 + cq; if (r >= p.np) r -= p.np;
         if ((used >> r) & 1u) {
@@ -146,14 +152,17 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           eph ^= 1u << r;
         }
         used |= 1u << r;
-        const TileC c = decode(cL);
+        const TileC c = cc;
         mbar_expect_tx(&plane_full[r], p.nkc * HP_ROWS * ROWB);
         for (int kc = 0; kc < p.nkc; ++kc)
           tma_load_5d(&tmA, &plane_full[r], sP + (r * p.nkc + kc) * p.plane_stride, kc * KC, c.tx * HT_W - 1, c.ty * HT_H - 1,
                       c.tz * p.td + p.dzmin + cq, c.n);
         if (++cq == p.np) {                                  // next tile: its plane 0 sits td ring positions further
           cq = 0; ++cL;
-          if (cL < L_end) { if (tile_is_start(cL)) c_ring0 = 0; else { c_ring0 += p.td; if (c_ring0 >= p.np) c_ring0 -= p.np; } }
+          if (cL < L_end) {
+            cc = decode(cL);
+            if (tile_is_start(cL)) c_ring0 = 0; else { c_ring0 += p.td; if (c_ring0 >= p.np) c_ring0 -= p.np; }
+          }
           cursor_norm();
         }
         return true;
