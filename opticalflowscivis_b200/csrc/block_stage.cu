@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
       const Lerp1s lz = up_index1s(dbeg + it, Dh, rs);
       const int yb = up_index1s(h0, Hh, rs).i0, xb = up_index1s(w0, Wh, rs).i0;
       for (int idx = tid; idx < 2 * HNR * HNC * 2; idx += 256) {
-        const int half = idx & 1, c = (idx >> 1) % HNC, r = ((idx >> 1) / HNC) % HNR, z = (idx >> 1) / (HNC * HNR);
+        constexpr int NCd = HNC > 0 ? HNC : 1, NRd = HNR > 0 ? HNR : 1;      // (dead code when SH <= 1)
+        const int half = idx & 1, c = (idx >> 1) % NCd, r = ((idx >> 1) / NCd) % NRd, z = (idx >> 1) / (NCd * NRd);
         const int zz = z ? lz.i1 : lz.i0, yy = min(yb + r, Hh - 1), xx = min(xb + c, Wh - 1);
         cp_async16(s_head + st * HTILE + (z * HNR + r) * HRF + half * (HNC * 4) + c * 4, hb + (((int64_t)zz * Hh + yy) * Wh + xx) * 8 + half * 4);
       }
