@@ -148,6 +148,27 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
   const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
   const int gP0 = (h0 + rP) * W + w0 + cP;                  // in-plane voxel offset of this thread's phase A/C voxel
 
+  // head tile copies (SH > 1): every thread owns at most two fixed 16 B pieces of the tile; their position inside the tile
+  // and inside a coarse plane never changes, only the two coarse z planes do — decode once, not per plane
+  constexpr int HPIECES = 2 * bs_head_rows(SH) * bs_head_cols(SH) * 2;      // (z tap, row, col, half)
+  int hsm[2] = {-1, -1}, hgl[2] = {0, 0}, hz[2] = {0, 0};
+  if (SH > 1) {
+    const float rs = 1.0f / (float)SHD;
+    const int yb = up_index1s(h0, Hh, rs).i0, xb = up_index1s(w0, Wh, rs).i0;
+    constexpr int NCd = HNC > 0 ? HNC : 1, NRd = HNR > 0 ? HNR : 1;          // (dead code when SH <= 1)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = tid + k * 256;
+      if (idx < HPIECES) {
+        const int half = idx & 1, c = (idx >> 1) % NCd, r = ((idx >> 1) / NCd) % NRd, z = (idx >> 1) / (NCd * NRd);
+        const int yy = min(yb + r, Hh - 1), xx = min(xb + c, Wh - 1);
+        hsm[k] = (z * HNR + r) * HRF + half * (HNC * 4) + c * 4;
+        hgl[k] = (yy * Wh + xx) * 8 + half * 4;
+        hz[k] = z;
+      }
+    }
+  }
+  static_assert(HPIECES <= 512, "head tile pieces per thread");
   auto issue = [&](int it) {            // async copies of plane dbeg + it into stage it % NST (always commits a group)
     if (it < nplanes && okP) {
       const int st = it % BS_NST, g = (dbeg + it) * HW + gP0;
@@ -158,15 +179,11 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
     if (SH > 1 && it < nplanes) {
       // the coarse head voxels this plane's taps need, so that phase A interpolates from shared memory
       const int st = it % BS_NST;
-      const float rs = 1.0f / (float)SHD;
-      const Lerp1s lz = up_index1s(dbeg + it, Dh, rs);
-      const int yb = up_index1s(h0, Hh, rs).i0, xb = up_index1s(w0, Wh, rs).i0;
-      for (int idx = tid; idx < 2 * HNR * HNC * 2; idx += 256) {
-        constexpr int NCd = HNC > 0 ? HNC : 1, NRd = HNR > 0 ? HNR : 1;      // (dead code when SH <= 1)
-        const int half = idx & 1, c = (idx >> 1) % NCd, r = ((idx >> 1) / NCd) % NRd, z = (idx >> 1) / (NCd * NRd);
-        const int zz = z ? lz.i1 : lz.i0, yy = min(yb + r, Hh - 1), xx = min(xb + c, Wh - 1);
-        cp_async16(s_head + st * HTILE + (z * HNR + r) * HRF + half * (HNC * 4) + c * 4, hb + (((int64_t)zz * Hh + yy) * Wh + xx) * 8 + half * 4);
-      }
+      const Lerp1s lz = up_index1s(dbeg + it, Dh, 1.0f / (float)SHD);
+      const int64_t zo0 = (int64_t)lz.i0 * Hh * Wh * 8, zo1 = (int64_t)lz.i1 * Hh * Wh * 8;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (hsm[k] >= 0) cp_async16(s_head + st * HTILE + hsm[k], hb + (hz[k] ? zo1 : zo0) + hgl[k]);
     }
     cp_async_commit();
   };
