@@ -295,8 +295,11 @@ def run_ours(args, rank, world, local_rank):
     # HBM roofline of the standalone warp kernel: (nd flow + 1 src + 1 out) * 4 B = 20 B/voxel in 3-D, 16 B/px in 2-D
     warp_bytes = (nd + 2) * 4 * vox * pairs
     warp_gbs = warp_bytes / (warp_ms / 1e3) / 1e9
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/r01n_ncu_full_warp3d_256.csv:
+    # dram__bytes_read 268.5 MB + write 50.7 MB per 256^3 volume), scaled to this launch's volume count
+    warp_traffic = (268.5e6 + 50.7e6) * pairs if (nd == 3 and tuple(sp) == (256, 256, 256)) else None
     roofline_warp = {"kernel": "warp%dd_kernel" % nd, "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": warp_traffic, "peak_source": peaks["src"],
                      "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": warp_ms, "timed": "standalone, 10 launches"}
     # HBM roofline of the fused block output stage (3-D): state read/write, img gathers, merged/mask, next block's input
     roofline_stage = None
@@ -307,8 +310,12 @@ def run_ours(args, rank, world, local_rank):
                    32 + 8 + 8]                         # final: read the state (accumulated by the head conv), imgs, write merged + mask
         stage_bytes = sum(per_vox) * vox * pairs * args.steps
         sg = stage_bytes / (bs[1] / 1e3) / 1e9
+        # ncu --set full (profiles/r01n_ncu_full_block2_flow3d_256.csv, r01n_launches_flow3d_256.csv): the three stage launches of
+        # one 256^3 pair move 1.77 GB of DRAM reads + 1.68 GB of writes (algorithmic: 3.36 GB)
+        stage_traffic = 3.45e9 * pairs if tuple(sp) == (256, 256, 256) else None
         roofline_stage = {"kernel": "block_stage_3d_kernel", "bound": "hbm", "achieved": sg, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": sg / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"], "launches": bs[0],
+                          "frac": sg / peaks["hbm_gbs"], "traffic": stage_traffic, "traffic_unit": "bytes per step (3 launches)",
+                          "peak_source": peaks["src"], "launches": bs[0],
                           "share_of_step": round(bs[1] / ms_prof, 4), "algorithmic_bytes_per_voxel_per_scale": per_vox}
 
     cpu_baseline = None
