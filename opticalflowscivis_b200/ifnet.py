@@ -375,11 +375,22 @@ class IFNet(nn.Module):
             raise ValueError(f"IFNet{nd}D: expected (N,2,{'D,' if nd == 3 else ''}H,W), got {tuple(x.shape)}")
         if x.shape[1] > 2:
             raise NotImplementedError("teacher/distillation branch (gt channel) is the training path, SURVEY.md §8f")
+        return self.forward_pair(x[:, 0:1].contiguous(), x[:, 1:2].contiguous(), scale, timestep)
+
+    @torch.no_grad()
+    def forward_pair(self, img0, img1, scale=(4, 2, 1), timestep=0.5):
+        """`forward` on the two frames/volumes given separately ((N,1,·) each): what `Model.inference` calls, so that the
+        reference's `torch.cat((img0, img1), 1)` (RIFE.py:67 / :68) and the channel slicing that undoes it (IFNet.py:146-147)
+        never touch HBM (1 GB of copies per 256^3 pair)."""
+        nd = self.nd
+        if img0.dim() != nd + 2 or img0.shape[1] != 1 or img1.shape != img0.shape:
+            raise ValueError(f"IFNet{nd}D: expected two (N,1,{'D,' if nd == 3 else ''}H,W) tensors, got {tuple(img0.shape)} / {tuple(img1.shape)}")
+        x = img0
         sp = tuple(x.shape[2:])
         if any(s % 16 for s in sp):
             raise NotImplementedError(f"spatial dims must be multiples of 16 (got {sp}); the reference's shape-repair "
                                       "slicing (Flow-2D/model/IFNet.py:164-188) is not reproduced")
-        img0, img1 = x[:, 0:1].contiguous(), x[:, 1:2].contiguous()
+        img0, img1 = ops._cuda_f32(img0, "img0"), ops._cuda_f32(img1, "img1")
         n = x.shape[0]
         act = _C.F32 if self.precision == "fp32" else _C.BF16
         eng = self._engine()

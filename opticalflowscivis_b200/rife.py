@@ -52,10 +52,9 @@ class _ModelBase:
         for t, name in ((img0, "img0"), (img1, "img1")):
             if not t.is_cuda:
                 raise TypeError(f"{name}: expected a CUDA tensor (no CPU path)")
-        imgs = torch.cat((img0, img1), 1)
         self.flownet.only_last = only_last
         try:
-            return self.flownet(imgs, scale_list, timestep=timestep)
+            return self.flownet.forward_pair(img0, img1, scale_list, timestep=timestep)
         finally:
             self.flownet.only_last = False
 
