@@ -391,6 +391,34 @@ def test_model_inference_vs_oracle(nd, precision):
         assert abs(p_ref - p_mine) <= 0.05                 # frames within 0.05 dB PSNR
 
 
+@pytest.mark.parametrize("sp,n", [((32, 48, 64), 2), ((16, 16, 16), 3), ((48, 32, 80), 1)])
+def test_model3d_noncubic_and_small_volumes(sp, n):
+    """Ragged tiles everywhere: H not a multiple of the 32-row stage tile, conv grids smaller than one 16x8 halo tile, batch > 1."""
+    from oracle.ifnet_ref import ModelRef
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    ref = ModelRef(3).eval()
+    m = Model(precision="bf16")
+    m.flownet.load_state_dict(ref.flownet.state_dict())
+    m.eval()
+    g = torch.Generator().manual_seed(99)
+    img0 = torch.rand((n, 1) + sp, generator=g)
+    img1 = torch.roll(img0, shifts=(1, 2, 1), dims=(2, 3, 4))
+    r_merged, r_flow, r_mask = ref.inference(img0, img1)
+    merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
+    torch.cuda.synchronize()
+    assert merged.shape == img0.shape and mask.shape == img0.shape and all(f.shape == (n, 6) + sp for f in flow)
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).view(n, 2, 3, -1).sum(2).sqrt().mean()) for i in range(3)]
+    assert max(epe) <= 1e-2, epe
+    assert float((merged.cpu() - r_merged).abs().max()) <= 3e-2
+    # the fp32 validation engine on the same shape
+    m32 = Model(precision="fp32")
+    m32.flownet.load_state_dict(ref.flownet.state_dict())
+    m32.eval()
+    mg32, fl32, _ = m32.inference(img0.to(_dev()), img1.to(_dev()))
+    assert float((fl32[2].cpu() - r_flow[2]).abs().max()) <= 1e-4 and float((mg32.cpu() - r_merged).abs().max()) <= 1e-4
+
+
 def test_u8_to_f32_and_streamed_interpolator():
     """The data edge: ofsv_u8_to_f32 == x.float()/255 bit for bit; StreamedInterpolator == plain inference on each pair."""
     from opticalflowscivis_b200 import ops, synth
