@@ -77,7 +77,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int BS_NST = 3;                    // cp.async stages (planes in flight per CTA)
+#ifndef OFSV_BS_MINB
+#define OFSV_BS_MINB 4
+#endif
+#ifndef OFSV_BS_NST
+#define OFSV_BS_NST 2
+#endif
+constexpr int BS_NST = OFSV_BS_NST;          // cp.async stages (planes in flight per CTA)
 constexpr int BS_DZ = 8;                     // d planes walked by one CTA
 constexpr int BS_FROW = BS_W * 4 + 4;        // floats per tile row of a half-state tile (+16 B pad: lanes along h hit distinct banks)
 constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile
@@ -107,7 +113,7 @@ __host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
 // full-resolution head, the voxel's own img0/img1 values) are in flight as cp.async copies while plane p is processed, so
 // the only exposed latencies are the data-dependent gathers of phase B (hidden by the other resident CTAs).
 template <int SH, int SN, bool S2D, bool FMA>
-__global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
+__global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
   extern __shared__ __align__(16) uint8_t bs_smem[];
   float* s_fa = reinterpret_cast<float*>(bs_smem);                 // [NST][BS_HALF] flow 0..3
   float* s_fb = s_fa + BS_NST * BS_HALF;                           // [NST][BS_HALF] flow 4,5, mask, 0
@@ -187,8 +193,7 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
     }
     cp_async_commit();
   };
-  issue(0);
-  issue(1);
+  for (int i = 0; i < BS_NST - 1; ++i) issue(i);
 
   if (SH > 1) {
     // per-axis tap tables of F.interpolate(scale_factor = SH, align_corners = False) for this tile column
@@ -211,8 +216,8 @@ __global__ void __launch_bounds__(256, 3) block_stage_3d_kernel(const StagePtrs 
     const int gP = d * HW + gP0;
     float* fa = s_fa + st * BS_HALF;
     float* fb = s_fb + st * BS_HALF;
-    issue(it + 2);
-    cp_async_wait<2>();
+    issue(it + BS_NST - 1);
+    cp_async_wait<BS_NST - 1>();
     __syncthreads();
     // ---------------- phase A: state update in place, one voxel (32 B) per thread
     if (SH != 0) {
