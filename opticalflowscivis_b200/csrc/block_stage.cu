@@ -84,7 +84,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define OFSV_BS_NST 2
 #endif
 constexpr int BS_NST = OFSV_BS_NST;          // cp.async stages (planes in flight per CTA)
-constexpr int BS_DZ = 8;                     // d planes walked by one CTA
+#ifndef OFSV_BS_DZ
+#define OFSV_BS_DZ 8
+#endif
+constexpr int BS_DZ = OFSV_BS_DZ;            // d planes walked by one CTA
 constexpr int BS_FROW = BS_W * 4 + 4;        // floats per tile row of a half-state tile (+16 B pad: lanes along h hit distinct banks)
 constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile
 

@@ -122,8 +122,11 @@ __device__ __forceinline__ void w3_cp4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+#ifndef OFSV_W3_MINB
+#define OFSV_W3_MINB 3
+#endif
 template <bool VEC, bool FMA>
-__global__ void __launch_bounds__(32 * W3_WARPS, 3)
+__global__ void __launch_bounds__(32 * W3_WARPS, OFSV_W3_MINB)
     warp3d_kernel(const float* __restrict__ src, const float* __restrict__ flow, const float* __restrict__ lin_h,
                   const float* __restrict__ lin_d, const float* __restrict__ lin_w, float* __restrict__ out,
                   const Warp3dParams P, const long long ntasks) {
@@ -320,7 +323,7 @@ extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const long long ntasks = (long long)N * D * cdiv(H, 32) * cdiv(W, W3_WT);
   const int64_t ctas = cdiv(ntasks, W3_WARPS);
-  const int grid = (int)(ctas < 148 * 3 ? ctas : 148 * 3);      // 3 CTAs (12 warps) resident per SM, persistent over the task list
+  const int grid = (int)(ctas < 148 * OFSV_W3_MINB ? ctas : 148 * OFSV_W3_MINB);      // OFSV_W3_MINB CTAs of 4 warps resident per SM, persistent over the task list
   const int smem = W3_WARPS * W3_SMEM_PER_WARP;
   static bool attr_done = false;
   if (!attr_done) {

@@ -419,6 +419,30 @@ def test_model3d_noncubic_and_small_volumes(sp, n):
     assert float((fl32[2].cpu() - r_flow[2]).abs().max()) <= 1e-4 and float((mg32.cpu() - r_merged).abs().max()) <= 1e-4
 
 
+def test_model3d_full_size_batch_invariance():
+    """BASELINE size (256^3 byte volumes): size-independent properties instead of an oracle run (the CPU reference needs ~25 s
+    and 5 GB per pair).  Every op on the path is per-sample, so (a) a pair gives bit-identical results alone and inside a
+    batch (this is what makes batch-sharding over GPUs exact), (b) repeated runs are bit-identical (no atomics / races),
+    (c) the interpolated volume of a {0,1}-valued pair stays inside [0,1] up to rounding and the mask is a probability."""
+    from opticalflowscivis_b200 import synth
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    a, _, b = synth.droplet3d_u8(2, 256, seed=1234)
+    d0, d1 = torch.from_numpy(a).to(_dev()).float() / 255.0, torch.from_numpy(b).to(_dev()).float() / 255.0
+    mg2, fl2, mk2 = m.inference(d0, d1)
+    mg2, fl2, mk2 = mg2.clone(), [f.clone() for f in fl2], mk2.clone()
+    for i in range(2):
+        mg1, fl1, mk1 = m.inference(d0[i:i + 1], d1[i:i + 1])
+        assert torch.equal(mg1[0], mg2[i]) and torch.equal(mk1[0], mk2[i])
+        assert all(torch.equal(fl1[k][0], fl2[k][i]) for k in range(3))
+    mg3, fl3, _ = m.inference(d0, d1)
+    assert torch.equal(mg3, mg2) and all(torch.equal(x, y) for x, y in zip(fl3, fl2))
+    assert float(mg2.min()) >= -1e-3 and float(mg2.max()) <= 1.0 + 1e-3
+    assert float(mk2.min()) >= 0.0 and float(mk2.max()) <= 1.0 and bool(torch.isfinite(fl2[2]).all())
+
+
 def test_u8_to_f32_and_streamed_interpolator():
     """The data edge: ofsv_u8_to_f32 == x.float()/255 bit for bit; StreamedInterpolator == plain inference on each pair."""
     from opticalflowscivis_b200 import ops, synth
