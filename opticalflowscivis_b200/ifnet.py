@@ -5,11 +5,14 @@ The modules below are PARAMETER CONTAINERS with the reference's `state_dict()` k
 (`block0.conv0.0.0.weight` ... `block_tea.conv2.2.bias`) and the reference's default initialisation; all arithmetic
 runs in CUDA kernels behind the C ABI (no nn.Conv forward, no F.grid_sample, no F.interpolate).
 
-Per block the launch sequence is
-    pack_block_input   F.interpolate(x,1/s) ‖ F.interpolate(flow,1/s)/s ‖ cat  -> channels-last [.,16]
-    12 conv layers     conv0.{0,1}, convblock{0..3}.{0,1} (+residual), conv1.0‖conv2.0 merged ConvT, conv1.2⊕conv2.2 heads
-    head_upsample_add  F.interpolate(.,s), flow*s, flow += flow_d, mask += mask_d
-    warp_blend         sigmoid(mask), warp x2, merged
+Per block the launch sequence is (3-D, bf16 tensor-core engine)
+    12 conv layers     conv0.{0,1} as stride-1 convs over the shifted space-to-depth input, convblock{0..3}.{0,1} (+residual),
+                       conv1.0‖conv2.0 merged ConvT, conv1.2⊕conv2.2 as one depth-to-space conv whose epilogue accumulates the
+                       flow/mask state when the block runs at scale 1
+    block_stage_3d     F.interpolate(head, s)*s, flow += , mask += , sigmoid, warp x2, blend, and the NEXT block's resized concat
+                       (bf16, space-to-depth) in one pass over the channels-last fp32 state
+(block 0 starts from pack_block_input).  2-D and the fp32 validation engine use the unfused planar chain
+    pack_block_input -> 12 conv layers -> head_upsample_add -> warp_blend.
 """
 from __future__ import annotations
 
