@@ -451,10 +451,14 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   const int sms = num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
   const size_t bar_bytes = (H_MAX_PLANES + 1 + 2 * H_MAX_BSTAGES + 4) * 8 + 32 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
-  // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
+  // TD (output slices per super-tile, all sharing one pass over the weight tiles): pick the feasible candidate with the
+  // smallest modelled time = rounds of super-tiles per SM x (max(tensor time, weight-stream time) + exposed plane loads).
+  // Constants measured on B200: an SS-mode M128.N.K16 MMA takes 44 + 0.49 N cycles (tests/umma_rate_probe.cu); weight tiles
+  // arrive from L2 at ~10 B/clk per SM when every CTA streams the same tensor, halo planes at ~30 B/clk (tests/halo_trace.py).
   int td = 0;
   const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits
   const int forced = force ? atoi(force) : 0;
+  double best = 0.0;
   for (int cand = 4; cand >= 1; cand >>= 1) {
     if (forced && cand != forced && cand > 1) continue;
     if (cand > d->Do && cand > 1) continue;
@@ -463,9 +467,13 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     if (cand * d->Cout_w > 512) continue;
     if ((size_t)np * P.nkc * P.plane_stride + 3 * (size_t)P.b_stride + bar_bytes + 1024 > smem_cap) continue;
     const int64_t nst = (int64_t)P.tiles_w * P.tiles_h * cdiv(d->Do, cand) * d->N;
-    if (cand > 1 && nst < 2 * sms && !forced) continue;
-    td = cand;
-    break;
+    const double ntiles_b = (double)d->nphase * d->ntaps * P.nkc;
+    const double mma = ntiles_b * (KC / 16) * (44.0 + 0.49 * d->Cout_w) * cand;
+    const double wstream = ntiles_b * P.b_stride / 10.0;
+    const double planes = (double)np * P.nkc * P.plane_stride / 30.0;
+    const double cost = (double)cdiv(nst, sms) * ((mma > wstream ? mma : wstream) + planes);
+    if (td == 0 || cost < best) { td = cand; best = cost; }
+    if (forced && cand == forced) break;
   }
   if (td == 0) { set_error("ofsv_conv_halo: layer does not fit (Cin_s=%d Cout_w=%d)", d->Cin_s, d->Cout_w); return OFSV_ENOSUP; }
   P.td = td; P.np = td + (dzmax - dzmin);
