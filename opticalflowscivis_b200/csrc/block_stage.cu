@@ -12,7 +12,7 @@
 // permuted views of it (ops.py).
 //
 // CTA = 32(h) x 8(w) voxels at fixed (n, d) (two d planes when the next block's input is pooled 2x):
-//   phase A  (voxel, half) threads: prev (+) up-sampled head -> fm_out (global, streaming) and a padded shared tile
+//   phase A  one voxel per thread: prev (+) up-sampled head -> fm_out (global, streaming) and, in place, the shared state tile
 //   phase B  one voxel per thread, LANES ALONG h: the reference warp rotates axes, output h is the
 //            contiguous source axis, so the 16 trilinear taps of a warp are 128 B-coalesced; sigmoid / blend; the 11
 //            block-input channels go to shared memory (bf16 rows, or fp32 planes for the 2x2x2 mean)
@@ -89,7 +89,9 @@ constexpr int BS_NST = OFSV_BS_NST;          // cp.async stages (planes in fligh
 #endif
 constexpr int BS_DZ = OFSV_BS_DZ;            // d planes walked by one CTA
 constexpr int BS_FROW = BS_W * 4 + 4;        // floats per tile row of a half-state tile (+16 B pad: lanes along h hit distinct banks)
-constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile
+constexpr int BS_HALF = BS_H * BS_FROW;      // floats per half-state tile (full-resolution head, SH == 1)
+constexpr int BS_SROW = BS_W * 8 + 4;        // floats per row of the state tile: 8 voxels x 32 B as they lie in memory + 16 B pad
+constexpr int BS_STATE = BS_H * BS_SROW;     // floats per state tile
 
 // head tile of one (tile, plane) for SH > 1: the 2 x (32/SH + 2) x (8/SH + 2) coarse voxels all trilinear taps fall into
 __host__ __device__ constexpr int bs_head_rows(int SH) { return SH > 1 ? BS_H / SH + 2 : 0; }
@@ -99,7 +101,7 @@ __host__ __device__ constexpr int bs_head_tile(int SH) { return 2 * bs_head_rows
 
 // shared-memory carve-up (bytes) — must match the kernel
 __host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
-  return BS_NST * 2 * BS_HALF * 4                       // s_fa, s_fb   (prev state, updated in place)
+  return BS_NST * BS_STATE * 4                          // s_f          (prev state, updated in place)
          + (SH == 1 ? BS_NST * 2 * BS_HALF * 4 : 0)     // s_ha, s_hb   (full-resolution head tiles)
          + BS_NST * 2 * BS_H * (BS_W + 1) * 4           // s_img
          + 2 * BS_H * (BS_W + 1) * 4                    // s_out
@@ -118,9 +120,8 @@ __host__ __device__ constexpr int bs_smem_bytes(int SH, int SN) {
 template <int SH, int SN, bool S2D, bool FMA>
 __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) block_stage_3d_kernel(const StagePtrs q, const Warp3dParams P) {
   extern __shared__ __align__(16) uint8_t bs_smem[];
-  float* s_fa = reinterpret_cast<float*>(bs_smem);                 // [NST][BS_HALF] flow 0..3
-  float* s_fb = s_fa + BS_NST * BS_HALF;                           // [NST][BS_HALF] flow 4,5, mask, 0
-  float* s_ha = s_fb + BS_NST * BS_HALF;                           // [NST][BS_HALF] (SH == 1)
+  float* s_f = reinterpret_cast<float*>(bs_smem);                  // [NST][BS_H][BS_SROW]: rows of 8 voxels x (flow 0..5, mask, 0)
+  float* s_ha = s_f + BS_NST * BS_STATE;                           // [NST][BS_HALF] (SH == 1)
   float* s_hb = s_ha + (SH == 1 ? BS_NST * BS_HALF : 0);
   float (*s_img)[2][BS_H][BS_W + 1] = reinterpret_cast<float (*)[2][BS_H][BS_W + 1]>(s_hb + (SH == 1 ? BS_NST * BS_HALF : 0));
   float (*s_out)[BS_H][BS_W + 1] = reinterpret_cast<float (*)[BS_H][BS_W + 1]>(&s_img[BS_NST][0][0][0]);
@@ -178,10 +179,23 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
     }
   }
   static_assert(HPIECES <= 512, "head tile pieces per thread");
+  // previous state: a tile row is 8 voxels x 32 B = 256 contiguous bytes, copied as it lies in memory.  One cp.async
+  // instruction covers two whole rows (512 contiguous bytes = 16 sectors): LDGSTS costs one shared-memory wavefront per
+  // global sector it touches, so the voxel-per-thread mapping (every thread one half sector, 32 sectors per instruction)
+  // spent a third of the kernel's L1 data-pipe cycles on these copies.  (One bulk copy per row measured slower.)
+  const int rows_valid = min(BS_H, H - h0), row_bytes = min(BS_W, W - w0) * 32;
   auto issue = [&](int it) {            // async copies of plane dbeg + it into stage it % NST (always commits a group)
+    if (has_prev && it < nplanes) {
+      const int st = it % BS_NST;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pc = k * 256 + tid, row = pc >> 4, c = pc & 15;
+        if (row < rows_valid && c * 16 < row_bytes)
+          cp_async16(s_f + (st * BS_H + row) * BS_SROW + c * 4, fprev + ((int64_t)(dbeg + it) * HW + (int64_t)(h0 + row) * W + w0) * 8 + c * 4);
+      }
+    }
     if (it < nplanes && okP) {
       const int st = it % BS_NST, g = (dbeg + it) * HW + gP0;
-      if (has_prev) { cp_async16(s_fa + st * BS_HALF + sP, fprev + g * 8); cp_async16(s_fb + st * BS_HALF + sP, fprev + g * 8 + 4); }
       if (SH == 1) { cp_async16(s_ha + st * BS_HALF + sP, hb + g * 8); cp_async16(s_hb + st * BS_HALF + sP, hb + g * 8 + 4); }
       if (SN != 0) { cp_async4(&s_img[st][0][rP][cP], i0p + g); cp_async4(&s_img[st][1][rP][cP], i1p + g); }
     }
@@ -217,8 +231,11 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
   for (int it = 0; it < nplanes; ++it) {
     const int d = dbeg + it, st = it % BS_NST;
     const int gP = d * HW + gP0;
-    float* fa = s_fa + st * BS_HALF;
-    float* fb = s_fb + st * BS_HALF;
+    float* sf = s_f + st * BS_STATE;
+    // a voxel's two 16 B halves are read / written in opposite order by lanes 0-3 and 4-7 of a quarter warp: with the rows
+    // stored as they lie in memory (32 B per voxel) this is what keeps the 16 B accesses of phase A / C bank-conflict-free
+    const int sw = (cP >> 2) & 1;
+    float* myv = sf + rP * BS_SROW + cP * 8;
     issue(it + BS_NST - 1);
     cp_async_wait<BS_NST - 1>();
     __syncthreads();
@@ -250,7 +267,8 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
         }
         const float sh = (float)SHD;
         if (has_prev) {
-          const float4 pa = *reinterpret_cast<const float4*>(fa + sP), pb = *reinterpret_cast<const float4*>(fb + sP);
+          const float4 p0 = *reinterpret_cast<const float4*>(myv + sw * 4), p1 = *reinterpret_cast<const float4*>(myv + (sw ^ 1) * 4);
+          const float4 pa = sw ? p1 : p0, pb = sw ? p0 : p1;
           oa = make_float4(__fadd_rn(pa.x, __fmul_rn(va.x, sh)), __fadd_rn(pa.y, __fmul_rn(va.y, sh)),
                            __fadd_rn(pa.z, __fmul_rn(va.z, sh)), __fadd_rn(pa.w, __fmul_rn(va.w, sh)));
           ob = make_float4(__fadd_rn(pb.x, __fmul_rn(vb.x, sh)), __fadd_rn(pb.y, __fmul_rn(vb.y, sh)), __fadd_rn(pb.z, vb.z), 0.0f);
@@ -261,14 +279,14 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
         stg_stream4(fout + gP * 8, oa);
         stg_stream4(fout + gP * 8 + 4, ob);
       }
-      *reinterpret_cast<float4*>(fa + sP) = oa;
-      *reinterpret_cast<float4*>(fb + sP) = ob;
+      *reinterpret_cast<float4*>(myv + sw * 4) = sw ? ob : oa;
+      *reinterpret_cast<float4*>(myv + (sw ^ 1) * 4) = sw ? oa : ob;
       __syncthreads();
     }
     // ---------------- phase B: warps / blend, one voxel per thread, lanes along h
     if (okB) {
-      const float4 va = *reinterpret_cast<const float4*>(fa + lane * BS_FROW + wl * 4);
-      const float4 vb = *reinterpret_cast<const float4*>(fb + lane * BS_FROW + wl * 4);
+      const float4 va = *reinterpret_cast<const float4*>(sf + lane * BS_SROW + wl * 8);
+      const float4 vb = *reinterpret_cast<const float4*>(sf + lane * BS_SROW + wl * 8 + 4);
       const float m = vb.z;
       const float lh = __ldg(q.lin_h + hB), ld = __ldg(q.lin_d + d), lw = __ldg(q.lin_w + wB);
       const Trilin t0 = trilin_setup(va.x, va.y, va.z, lh, ld, lw, D, H, W, P.hs, P.ref_mode);
@@ -301,8 +319,8 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
       if (q.mask_sig) q.mask_sig[g] = s_out[1][rP][cP];
       if (SN == 1) {
         uint4* o = reinterpret_cast<uint4*>(q.pack_out + pack_row_off<S2D>(n, d, h0 + rP, w0 + cP, D, H, W));
-        o[0] = s_pk[rP * BS_PKROW + cP * 2];
-        o[1] = s_pk[rP * BS_PKROW + cP * 2 + 1];
+        o[sw] = s_pk[rP * BS_PKROW + cP * 2 + sw];
+        o[sw ^ 1] = s_pk[rP * BS_PKROW + cP * 2 + (sw ^ 1)];
       }
     }
     if (SN == 2 && (it & 1) && tid < 64) {

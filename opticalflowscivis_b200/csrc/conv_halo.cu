@@ -152,8 +152,11 @@ __global__ void __launch_bounds__(H_THREADS, 1)
       const uint32_t jmask = (1u << nj) - 1u;
       uint32_t waited = 0;                   // bit (slice plane * nkc + kc)
       const long long t_in = trace ? clock64() : 0;
+      long long w_plane = 0, w_b = 0, w_acc = 0, tw = 0;
       for (int pass = 0; pass < p.nphase; ++pass) {
+        if (trace) tw = clock64();
         if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1);
+        if (trace) w_acc += clock64() - tw;
         const uint32_t acc0 = tmem_base + buf * p.acc_stride;
         const uint32_t* taps = sTap + pass * ntap_total;
         for (int t = 0; t < ntap_total; ++t) {
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           const uint32_t tap16 = te & 0xFFFFu, dzr = te >> 16;
           for (int kc = 0; kc < p.nkc; ++kc) {
             // planes this (tap, chunk) touches for the first time in this super-tile (nkc == 1: planes dzr .. dzr+nj-1)
+            if (trace) tw = clock64();
             if (p.nkc == 1) {
               uint32_t need = (jmask << dzr) & ~waited;
               while (need) { const int pl = __ffs(need) - 1; mbar_wait(&plane_full[pl], iter & 1); need &= need - 1; }
@@ -171,7 +175,9 @@ __global__ void __launch_bounds__(H_THREADS, 1)
                 if (!((waited >> pl) & 1u)) { mbar_wait(&plane_full[pl], iter & 1); waited |= 1u << pl; }
               }
             }
+            if (trace) { const long long t1 = clock64(); w_plane += t1 - tw; tw = t1; }
             mbar_wait(&b_full[bs], bphase);
+            if (trace) w_b += clock64() - tw;
             tcgen05_fence_after();
             if (leader) {
               const uint32_t b_lo = b_lo0 + bs * b_step;
@@ -196,7 +202,10 @@ __global__ void __launch_bounds__(H_THREADS, 1)
       }
       if (leader) tcgen05_commit(planes_empty);
       __syncwarp();
-      if (trace && iter < 16 && lane == 0 && iss == 0) { dbg[iter * 16 + 2] = t_in; dbg[iter * 16 + 3] = clock64(); }
+      if (trace && iter < 16 && lane == 0 && iss == 0) {
+        dbg[iter * 16 + 2] = t_in; dbg[iter * 16 + 3] = clock64();
+        dbg[iter * 16 + 4] = w_plane; dbg[iter * 16 + 5] = w_b; dbg[iter * 16 + 6] = w_acc;
+      }
     }
   } else {
     // ================= epilogue: 8 warps, two per TMEM lane quarter, splitting the (slice, 16-column chunk) list ==========
