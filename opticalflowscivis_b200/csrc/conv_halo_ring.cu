@@ -40,8 +40,11 @@ __device__ __forceinline__ uint32_t ring_pack2_bf16(float a, float b) {
 constexpr int HT_H = 16, HT_W = 8, HP_H = HT_H + 2, HP_W = HT_W + 2, HP_ROWS = HP_H * HP_W;  // 180 halo rows
 constexpr int H_MAX_PLANES = 8;
 constexpr int H_MAX_BSTAGES = 32;
-constexpr int H_MMA_WARPS = 4, H_EPI_WARPS = 8, H_EPI_W0 = 1 + H_MMA_WARPS;
-constexpr int H_THREADS = 32 * (H_EPI_W0 + H_EPI_WARPS);   // warp 0 TMA, warps 1..2 MMA issuers (output slices split by parity), warps 3..10 epilogue
+#ifndef OFSV_RING_MMA_WARPS
+#define OFSV_RING_MMA_WARPS 8
+#endif
+constexpr int H_MMA_WARPS = OFSV_RING_MMA_WARPS, H_EPI_WARPS = 8, H_EPI_W0 = 1 + H_MMA_WARPS;
+constexpr int H_THREADS = 32 * (H_EPI_W0 + H_EPI_WARPS);   // warp 0 TMA, then the MMA issuer warps (slices x tap groups), then 8 epilogue warps
 
 struct RingParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
@@ -55,6 +58,8 @@ struct RingParams {
   int dzspan;                        // dzmax - dzmin
   int sliding;                       // 1: z-fastest contiguous tile runs with shared boundary planes and early plane release
   int b_resident;                    // all weight tiles fit the ring: loaded once per CTA, never recycled
+  int ng;                            // tap groups (resident weights only): the taps of a super-tile are split over ng issuer
+                                     // warps per slice, each with its own partial accumulator, summed by the epilogue
   uint8_t tap_order[OFSV_MAX_TAPS];   // per pass: taps in ascending dz (position -> original tap index)
   uint8_t rel_after[OFSV_MAX_TAPS];   // last pass only: bitmask of non-shared plane indices q < td whose last reader is this position
   int8_t tap_off[OFSV_MAX_TAPS][4];
@@ -216,6 +221,12 @@ __global__ void __launch_bounds__(H_THREADS, 1)
     const uint32_t b_lo0 = kmajor_desc_lo(smem_u32(sB)), b_step = (uint32_t)p.b_stride >> 4;
     const int ntap_total = p.ntaps;
     const int nj = p.td;                     // Do % td == 0 (host)
+    // tap groups: the single issuing thread needs ~600 cycles of scalar work per (tap, chunk) whatever the MMA sizes, so a
+    // short super-tile (few slices, small N) is issue-bound; with ng > 1 (H_MMA_WARPS = ng * td) warp iss issues slice
+    // iss % td for the taps of group iss / td only, into its own accumulator
+    const int grp = p.ng > 1 ? iss / nj : 0, tg = ntap_total / p.ng;
+    const int tbeg = (p.ng > 1 && grp >= p.ng) ? ntap_total : grp * tg;          // warps beyond ng * td issue nothing
+    const int jbeg = p.ng > 1 ? iss % nj : iss, jstep = p.ng > 1 ? nj : H_MMA_WARPS;
     const uint32_t jmask = (1u << nj) - 1u;
     uint32_t bs = 0, bphase = 0;             // B ring slot / parity
     uint32_t buf = 0, acc_use = 0;           // accumulator buffer, number of uses so far
@@ -251,6 +262,10 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           }
           waited |= jmask << dzr;
           if (trace) tw_plane += clock64() - tp0;
+          if (p.ng > 1 && (t < tbeg || t >= tbeg + tg)) {          // another group's tap (resident weights: slot = (t, kc))
+            bs += (uint32_t)p.nkc;
+            if (bs >= (uint32_t)p.nb) bs -= (uint32_t)p.nb;
+          } else
           for (int kc = 0; kc < p.nkc; ++kc) {
             const long long tb0 = trace ? clock64() : 0;
             mbar_wait(&b_full[bs], p.b_resident ? 0u : bphase);
@@ -258,10 +273,10 @@ __global__ void __launch_bounds__(H_THREADS, 1)
             tcgen05_fence_after();
             if (leader) {
               const uint32_t b_lo = b_lo0 + bs * b_step;
-              const uint32_t first = (t | kc) ? 1u : 0u;
-              for (int j = iss; j < nj; j += H_MMA_WARPS) {
+              const uint32_t first = ((t - tbeg) | kc) ? 1u : 0u;
+              for (int j = jbeg; j < nj; j += jstep) {
                 int r = ring0 + j + (int)dzr; if (r >= p.np) r -= p.np;
-                const uint32_t aj = plane_lo0 + (uint32_t)(r * p.nkc + kc) * plane_step + tap16, dj = acc0 + j * p.Cout_w;
+                const uint32_t aj = plane_lo0 + (uint32_t)(r * p.nkc + kc) * plane_step + tap16, dj = acc0 + (grp * nj + j) * p.Cout_w;
                 umma_bf16_lohi(dj, aj, a_hi, b_lo, b_hi, idesc, first);
 #pragma unroll
                 for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dj, aj + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);
@@ -365,6 +380,12 @@ __global__ void __launch_bounds__(H_THREADS, 1)
           }
           float v[16];
           tmem_ld16(tmem_base + buf * p.acc_stride + j * p.Cout_w + c0 + ((uint32_t)(q * 32) << 16), v);
+          for (int g = 1; g < p.ng; ++g) {      // partial sums of the other tap groups, fixed order
+            float u[16];
+            tmem_ld16(tmem_base + buf * p.acc_stride + (g * p.td + j) * p.Cout_w + c0 + ((uint32_t)(q * 32) << 16), u);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += u[e];
+          }
           if (!valid_xy) continue;
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {          // 16 B shared loads: the epilogue competes with the UMMA operand fetch
@@ -588,7 +609,15 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
   if (nb >= nbt) { nb = nbt; P.b_resident = 1; }
   else if (nb > 8) nb = 8;
   P.nb = nb;
-  P.nbuf = (2 * td * d->Cout_w <= 512) ? 2 : 1;
+  P.ng = 1;
+  if (P.b_resident && d->nphase == 1) {
+    int ng = 1;
+    while (2 * ng * td <= H_MMA_WARPS && d->ntaps % (2 * ng) == 0 && 2 * ng * td * d->Cout_w <= 256) ng *= 2;
+    const char* f = getenv("OFSV_RING_NG");            // A/B hook: 1 disables the tap-group split
+    if (f && atoi(f) >= 1 && atoi(f) < ng) ng = atoi(f);
+    P.ng = ng;
+  }
+  P.nbuf = (2 * P.ng * td * d->Cout_w <= 512) ? 2 : 1;
   P.acc_stride = 256;
   const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
   OFSV_REQUIRE(total < (1ll << 31), "ofsv_conv_halo(ring): too many super-tiles");
