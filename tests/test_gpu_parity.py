@@ -443,6 +443,25 @@ def test_model3d_full_size_batch_invariance():
     assert float(mk2.min()) >= 0.0 and float(mk2.max()) <= 1.0 and bool(torch.isfinite(fl2[2]).all())
 
 
+@pytest.mark.parametrize("size,batch", [(64, 5), (128, 3)])
+def test_model3d_small_volume_batch_invariance(size, batch):
+    """Same property at sizes where the conv engine picks different super-tile depths / kernels for different batch sizes
+    (the wave count enters the choice): the numerics must not depend on that choice."""
+    from opticalflowscivis_b200 import synth
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    a, _, b = synth.droplet3d_u8(batch, size, seed=77)
+    d0, d1 = torch.from_numpy(a).to(_dev()).float() / 255.0, torch.from_numpy(b).to(_dev()).float() / 255.0
+    mgB, flB, mkB = m.inference(d0, d1)
+    mgB, flB, mkB = mgB.clone(), [f.clone() for f in flB], mkB.clone()
+    for i in (0, batch - 1):
+        mg1, fl1, mk1 = m.inference(d0[i:i + 1], d1[i:i + 1])
+        assert torch.equal(mg1[0], mgB[i]) and torch.equal(mk1[0], mkB[i])
+        assert all(torch.equal(fl1[k][0], flB[k][i]) for k in range(3))
+
+
 def test_u8_to_f32_and_streamed_interpolator():
     """The data edge: ofsv_u8_to_f32 == x.float()/255 bit for bit; StreamedInterpolator == plain inference on each pair."""
     from opticalflowscivis_b200 import ops, synth
