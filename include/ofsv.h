@@ -104,6 +104,19 @@ int ofsv_pack_block_input(const float* img0, const float* img1, const float* war
  * the reference loaders' `/ 255.`: Datasets/read_data.py, Flow-3D/load_datasets.py), so only bytes cross PCIe. */
 int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream);
 
+/* Evaluation metrics on the device, float64 like the numpy reference, reduced in a fixed order.
+ * `partials` is caller-provided scratch of N * OFSV_METRIC_BLOCKS doubles; `out` receives N doubles.
+ *   ofsv_sq_err_f64: out[n] = sum_i (((a[n][i] - b[n][i]) * scale)^2) over `count` elements per sample, all in fp64:
+ *     MSE = out/count feeds `calculate_psnr` (error.py:27-34, scale = 255 for [0,1] data) and
+ *     `-10*log10(mean((gt-pred)^2))` (Flow-3D/train.py:385-388, scale = 1).
+ *   ofsv_ssim2d_f64: out[n] = mean SSIM map of the N image pairs x[n], y[n] ([H][W] fp32 planes) with the 11x11 Gaussian
+ *     window (sigma 1.5) over the 'valid' region and C1 = (0.01 L)^2, C2 = (0.03 L)^2, L = data_range (error.py:36-56). */
+#define OFSV_METRIC_BLOCKS 64
+int ofsv_sq_err_f64(const float* a, const float* b, double* partials, double* out, int N, int64_t count, float scale,
+                    void* stream);
+int ofsv_ssim2d_f64(const float* x, const float* y, double* partials, double* out, int N, int H, int W, double data_range,
+                    void* stream);
+
 #define OFSV_MAX_TAPS 64
 /* One convolution layer in "tap" form.  For every phase ph, every virtual output position o = (oz,oy,ox) in
  * [0,Do)x[0,Ho)x[0,Wo):

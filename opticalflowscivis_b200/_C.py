@@ -46,6 +46,8 @@ _SIGS = {
     "ofsv_upsample_flow_ac_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warping_no_div_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ofsv_u8_to_f32": (_I, [_P, _P, _L, _F, _P]),
+    "ofsv_sq_err_f64": (_I, [_P, _P, _P, _P, _I, _L, _F, _P]),
+    "ofsv_ssim2d_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, ctypes.c_double, _P]),
     "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 9 + [_P]),
     "ofsv_conv_simt": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),

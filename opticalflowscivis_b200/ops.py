@@ -343,5 +343,44 @@ def u8_to_f32(src: torch.Tensor, div: float = 255.0) -> torch.Tensor:
     return dst
 
 
+METRIC_BLOCKS = 64
+
+
+def _metric_args(a: torch.Tensor, b: torch.Tensor, what: str):
+    if not (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.is_cuda and b.is_cuda):
+        raise TypeError(f"{what}: expected CUDA tensors (there is no CPU path)")
+    if a.shape != b.shape:
+        raise ValueError(f"{what}: Input images must have the same dimensions.")
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32 tensors")
+    return a.contiguous(), b.contiguous()
+
+
+def sq_err_sums(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """Per-sample sum of ((a - b) * scale)^2 over all but the first dimension -> float64 [N] (deterministic)."""
+    a, b = _metric_args(a, b, "sq_err_sums")
+    n = a.shape[0] if a.dim() > 0 else 1
+    count = a.numel() // max(n, 1)
+    out = torch.empty(n, dtype=torch.float64, device=a.device)
+    part = torch.empty(max(n, 1) * METRIC_BLOCKS, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device), _span("sq_err"):
+        _C.check(_C.lib().ofsv_sq_err_f64(_p(a), _p(b), _p(part), _p(out), n, count, float(scale), _stream()))
+    return out
+
+
+def ssim2d_means(x: torch.Tensor, y: torch.Tensor, data_range: float = 255.0) -> torch.Tensor:
+    """Mean SSIM (11x11 Gaussian window, sigma 1.5, valid region) of every [H][W] plane pair of x, y [..., H, W] -> float64."""
+    x, y = _metric_args(x, y, "ssim2d_means")
+    if x.dim() < 2:
+        raise ValueError("ssim2d_means: Wrong input image dimensions.")
+    H, W = int(x.shape[-2]), int(x.shape[-1])
+    n = x.numel() // (H * W)
+    out = torch.empty(n, dtype=torch.float64, device=x.device)
+    part = torch.empty(max(n, 1) * METRIC_BLOCKS, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device), _span("ssim2d"):
+        _C.check(_C.lib().ofsv_ssim2d_f64(_p(x), _p(y), _p(part), _p(out), n, H, W, float(data_range), _stream()))
+    return out.reshape(x.shape[:-2])
+
+
 def launch_count() -> int:
     return int(_C.lib().ofsv_launch_count())

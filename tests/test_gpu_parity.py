@@ -607,3 +607,50 @@ def test_model3d_fused_equals_unfused():
     m.flownet.fuse_output_stage = False
     d = m.inference(img0.to(_dev()), img1.to(_dev()), scale_list=[2, 4, 1])
     assert float((c[0] - d[0]).abs().max()) <= 1e-5
+
+
+def test_metrics_vs_oracle_and_reference_fixture():
+    """Device PSNR / SSIM (ofsv_sq_err_f64, ofsv_ssim2d_f64 behind metrics.calculate_*) vs the numpy oracle and vs the values
+    the reference's error.py produced for the committed fixture; float64 sums, tolerance 1e-9 relative."""
+    from opticalflowscivis_b200 import metrics, ops
+    from oracle import metrics_ref as mr
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for tag in "abcd":
+        i1, i2 = z[f"{tag}_img1"], z[f"{tag}_img2"]
+        t1, t2 = torch.from_numpy(i1).to(_dev()), torch.from_numpy(i2).to(_dev())
+        p, q = metrics.calculate_psnr(t1, t2), metrics.calculate_ssim(t1, t2)
+        assert abs(p - float(z[f"{tag}_psnr"])) <= 1e-9 * float(z[f"{tag}_psnr"]), (tag, p)
+        assert abs(q - float(z[f"{tag}_ssim"])) <= 1e-9, (tag, q)
+    t1 = torch.from_numpy(z["a_img1"]).to(_dev())
+    assert metrics.calculate_psnr(t1, t1) == float("inf")
+    with pytest.raises(ValueError):
+        metrics.calculate_ssim(t1, torch.from_numpy(z["b_img1"]).to(_dev()))
+    # batched, per-sample, [0,1] volumes (the validation loop of Flow-3D/train.py:385-388), ragged element count
+    g = torch.Generator().manual_seed(5)
+    gt, pred = torch.rand(3, 1, 9, 10, 11, generator=g), torch.rand(3, 1, 9, 10, 11, generator=g)
+    got = metrics.psnr_per_sample(pred.to(_dev()), gt.to(_dev()))
+    for j in range(3):
+        assert abs(got[j] - mr.psnr_train(pred[j].numpy(), gt[j].numpy())) <= 1e-9
+    # determinism: the reduction order is fixed
+    a, b = torch.rand(2, 1, 64, 64, 64, generator=g).to(_dev()), torch.rand(2, 1, 64, 64, 64, generator=g).to(_dev())
+    assert torch.equal(ops.sq_err_sums(a, b), ops.sq_err_sums(a, b))
+    # sequence metrics (error.py:78-103): only the interpolated members (i % factor != 0) are scored
+    seq1 = [torch.from_numpy(z["a_img1"]).to(_dev()), torch.from_numpy(z["a_img2"]).to(_dev()), torch.from_numpy(z["a_img1"]).to(_dev())]
+    seq2 = [torch.from_numpy(z["a_img1"]).to(_dev()), torch.from_numpy(z["a_img1"]).to(_dev()), torch.from_numpy(z["a_img1"]).to(_dev())]
+    pm, sm = metrics.calculate_metrics(seq1, seq2, 2)
+    assert abs(pm - float(z["a_psnr"])) <= 1e-9 * pm and abs(sm - float(z["a_ssim"])) <= 1e-9
+
+
+def test_recursive_interpolation_on_device():
+    """interp.interpolate_recursive (Flow-3D/inference_img.py:88-97) around the real 3-D model: 2^k + 1 members, end members
+    untouched, every new member equals a direct inference of its neighbours."""
+    from opticalflowscivis_b200 import interp, synth
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    a, _, b = synth.droplet3d_u8(1, 32, seed=3)
+    d0, d1 = torch.from_numpy(a).to(_dev()).float() / 255.0, torch.from_numpy(b).to(_dev()).float() / 255.0
+    seq = interp.interpolate_recursive(m, d0, d1, exp=2)
+    assert len(seq) == 5 and seq[0] is d0 and seq[4] is d1
+    assert torch.equal(seq[2], m.inference(d0, d1)[0]) and torch.equal(seq[1], m.inference(d0, seq[2])[0])

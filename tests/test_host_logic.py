@@ -153,6 +153,10 @@ def test_validation_errors_launch_nothing():
     assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, 0, null) == _C.EINVAL
     assert L.ofsv_block_stage_3d(*([null] * 11), 1, 16, 16, 16, 3, 0, 0, 0, null) == _C.EINVAL
     assert L.ofsv_u8_to_f32(null, null, 16, 255.0, null) == _C.EINVAL
+    assert L.ofsv_sq_err_f64(null, null, null, null, 1, 16, 1.0, null) == _C.EINVAL
+    assert L.ofsv_ssim2d_f64(null, null, null, null, 1, 10, 32, 255.0, null) == _C.EINVAL      # smaller than the 11x11 window
+    assert b"11x11" in L.ofsv_last_error()
+    assert L.ofsv_sq_err_f64(null, null, null, null, 0, 16, 1.0, null) == _C.OK
     d = _C.ConvDesc()
     assert L.ofsv_conv_simt(ctypes.byref(d), null, null, null, null, null, null, null) == _C.EINVAL
     with pytest.raises(RuntimeError):
@@ -163,6 +167,28 @@ def test_validation_errors_launch_nothing():
     assert L.ofsv_blend_f32(null, null, null, null, 0, null) == _C.OK
 
 
+def test_interpolation_drivers_mirror_reference_loops():
+    """interp.py vs Flow-2D/inference_img.py:64-97 with a stand-in model whose `inference` averages its inputs: the recursive
+    driver must return the 2^exp + 1 uniformly spaced members, the ratio driver must bisect to the requested time."""
+    from opticalflowscivis_b200 import interp
+
+    class Lerp:
+        calls = 0
+
+        def inference(self, a, b):
+            Lerp.calls += 1
+            return ((a + b) / 2,)
+
+    a, b = torch.zeros(1, 1, 4, 4), torch.ones(1, 1, 4, 4)
+    seq = interp.interpolate_recursive(Lerp(), a, b, exp=3)
+    assert len(seq) == 9 and Lerp.calls == 7
+    assert all(torch.allclose(x, torch.full_like(x, i / 8)) for i, x in enumerate(seq))
+    Lerp.calls = 0
+    out = interp.interpolate_ratio(Lerp(), a, b, ratio=0.3, rthreshold=0.02, rmaxcycles=8)
+    assert len(out) == 3 and abs(float(out[1].mean()) - 0.3) <= 0.01 + 1e-6 and Lerp.calls <= 8
+    assert interp.interpolate_ratio(Lerp(), a, b, ratio=0.005)[1] is a and interp.interpolate_ratio(Lerp(), a, b, ratio=0.995)[1] is b
+
+
 def test_cpu_tensors_are_rejected():
     from opticalflowscivis_b200 import ops
     from opticalflowscivis_b200.upflow import CorrelationFunction
@@ -170,6 +196,10 @@ def test_cpu_tensors_are_rejected():
         ops.warp2d(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4))
     with pytest.raises(TypeError):
         ops.warp3d(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4))
+    with pytest.raises(TypeError):
+        ops.sq_err_sums(torch.zeros(1, 16), torch.zeros(1, 16))
+    with pytest.raises(TypeError):
+        ops.ssim2d_means(torch.zeros(16, 16), torch.zeros(16, 16))
     with pytest.raises(TypeError):
         CorrelationFunction.apply(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 4, 1, 4, 1, 1, 1)
     with pytest.raises(NotImplementedError):

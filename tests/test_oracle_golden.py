@@ -97,3 +97,20 @@ def test_resize_identities():
     sel = (sel[:, :, :, 1::4] + sel[:, :, :, 2::4]) / 2
     sel = (sel[..., 1::4] + sel[..., 2::4]) / 2
     assert torch.allclose(quarter, sel, atol=1e-6)
+
+
+def test_metrics_golden():
+    """oracle/metrics_ref.py vs the reference's own error.py (fixture written by tests/golden/make_metrics_golden.py, which
+    ran calculate_psnr / calculate_ssim of /root/reference/error.py with cv2)."""
+    from oracle import metrics_ref as mr
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for tag in "abcd":
+        img1, img2 = z[f"{tag}_img1"], z[f"{tag}_img2"]
+        assert abs(mr.calculate_psnr(img1, img2) - float(z[f"{tag}_psnr"])) <= 1e-12 * float(z[f"{tag}_psnr"])
+        assert abs(mr.calculate_ssim(img1, img2) - float(z[f"{tag}_ssim"])) <= 1e-10
+    assert mr.calculate_psnr(z["a_img1"], z["a_img1"]) == float("inf")
+    with pytest.raises(ValueError):
+        mr.calculate_ssim(z["a_img1"], z["b_img1"])
+    # the training-loop form on [0,1] data is the same quantity on another scale (Flow-3D/train.py:385)
+    p01 = mr.psnr_train(z["a_img1"] / 255.0, z["a_img2"] / 255.0)
+    assert abs(p01 - float(z["a_psnr"])) <= 1e-5
