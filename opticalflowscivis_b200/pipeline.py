@@ -12,9 +12,40 @@ No arithmetic happens here: the uint8 -> fp32 `/255` conversion is the reference
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, Iterator, Optional, Tuple
+import os
+from typing import Callable, Iterable, Iterator, Optional, Sequence, Tuple
 
 import torch
+
+
+def read_raw_volume(path: str, shape: Sequence[int] = (256, 256, 256), out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One time step of the droplet ensemble: a headerless uint8 file, x fastest (`README.md:24-25`), read exactly like
+    `np.fromfile(path, dtype='uint8').resize(256, 256, 256)` (`Datasets/read_data.py:116-119`) but straight into PINNED host
+    memory, shaped (1, 1, *shape) for `StreamedInterpolator`.  A short file is zero-padded like ndarray.resize does, a longer
+    one is truncated."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if out is None:
+        out = torch.zeros((1, 1) + tuple(int(d) for d in shape), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            out = out.pin_memory()
+    elif out.dtype != torch.uint8 or out.numel() != n or not out.is_contiguous():
+        raise ValueError("read_raw_volume: `out` must be a contiguous uint8 tensor of the requested size")
+    view = memoryview(out.view(-1).numpy())
+    with open(path, "rb") as f:
+        got = f.readinto(view)
+    if got < n:
+        out.view(-1)[got:] = 0
+    return out
+
+
+def raw_pairs(paths: Sequence[str], shape: Sequence[int] = (256, 256, 256), stride: int = 2) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    """(volume[i], volume[i + stride]) pairs of a sorted file list — the inputs whose middle time step the model
+    reconstructs (`Flow-3D/load_datasets.py`: every other member is held out) — as pinned uint8 tensors."""
+    paths = sorted(paths, key=os.path.basename)
+    for i in range(0, len(paths) - stride, stride):
+        yield read_raw_volume(paths[i], shape), read_raw_volume(paths[i + stride], shape)
 
 
 class StreamedInterpolator:

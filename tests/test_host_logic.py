@@ -189,6 +189,36 @@ def test_interpolation_drivers_mirror_reference_loops():
     assert interp.interpolate_ratio(Lerp(), a, b, ratio=0.005)[1] is a and interp.interpolate_ratio(Lerp(), a, b, ratio=0.995)[1] is b
 
 
+def test_raw_volume_reader_matches_reference_loader(tmp_path):
+    """pipeline.read_raw_volume == np.fromfile(...).resize(...) of Datasets/read_data.py:116-119 (x fastest, uint8), incl. the
+    zero padding of a short file; raw_pairs yields (i, i + 2) members of the sorted list."""
+    import numpy as np
+    from opticalflowscivis_b200 import pipeline
+    rng = np.random.RandomState(0)
+    shape = (6, 8, 10)
+    files = []
+    for k in range(5):
+        v = rng.randint(0, 256, size=shape).astype(np.uint8)
+        f = tmp_path / f"drop_{k:04d}.raw"
+        v.tofile(f)
+        files.append(str(f))
+    ref = np.fromfile(files[1], dtype="uint8")
+    ref.resize(*shape)
+    got = pipeline.read_raw_volume(files[1], shape)
+    assert got.shape == (1, 1) + shape and got.dtype == torch.uint8 and np.array_equal(got[0, 0].numpy(), ref)
+    short = tmp_path / "short.raw"
+    ref[:3].tofile(short)
+    ref2 = np.fromfile(short, dtype="uint8")
+    ref2.resize(*shape)
+    assert np.array_equal(pipeline.read_raw_volume(str(short), shape)[0, 0].numpy(), ref2)
+    pairs = list(pipeline.raw_pairs(list(reversed(files)), shape))
+    assert len(pairs) == 2
+    assert np.array_equal(pairs[1][0][0, 0].numpy(), np.fromfile(files[2], dtype="uint8").reshape(shape))
+    assert np.array_equal(pairs[1][1][0, 0].numpy(), np.fromfile(files[4], dtype="uint8").reshape(shape))
+    with pytest.raises(ValueError):
+        pipeline.read_raw_volume(files[0], shape, out=torch.zeros(5, dtype=torch.uint8))
+
+
 def test_cpu_tensors_are_rejected():
     from opticalflowscivis_b200 import ops
     from opticalflowscivis_b200.upflow import CorrelationFunction
