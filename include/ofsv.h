@@ -52,6 +52,17 @@ int ofsv_warp2d_f32(const float* src, const float* flow, const float* lin_x, con
 int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
                     float* out, int N, int C, int D, int H, int W, int ref_mode, void* stream);
 
+/* ---- backward of a1 / a2: what autograd runs under warp() in the reference's training step (Flow-2D/model/RIFE.py:80-336,
+ * Flow-3D/model/RIFE.py:81-275 through Flow-{2D,3D}/model/warplayer.py:26 / :37) = ATen grid_sampler_{2,3}d_backward (bilinear,
+ * border, align_corners=True, incl. the zero gradient of clipped coordinates) followed by the backward of
+ * `flow / ((S-1)/2)`.  gout has the shape of out.  gsrc (shape of src; zero-filled by the call, then accumulated with
+ * red.global.add) and gflow (shape of flow) may each be NULL = not wanted; src may be NULL when gflow is NULL. */
+int ofsv_warp2d_bwd_f32(const float* src, const float* flow, const float* gout, const float* lin_x, const float* lin_y,
+                        float* gsrc, float* gflow, int N, int C, int H, int W, int ref_mode, void* stream);
+int ofsv_warp3d_bwd_f32(const float* src, const float* flow, const float* gout, const float* lin_h, const float* lin_d,
+                        const float* lin_w, float* gsrc, float* gflow, int N, int C, int D, int H, int W, int ref_mode,
+                        void* stream);
+
 /* ---- a6 (+a1/a2 fused): sigmoid(mask) ; warp(img0, flow[:, :nd]) ; warp(img1, flow[:, nd:2nd]) ; blend.
  * Flow-2D/model/IFNet.py:189-192,240 ; Flow-3D/model/IFNet.py:186-191,242.
  * img0,img1,mask_logit (N,1,·); flow (N,2*nd,·).  Any of warped0/warped1/merged/mask_sig may be NULL (not written). */

@@ -110,29 +110,82 @@ def linspace_table(n: int, device: torch.device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ warp
-def warp2d(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
-    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
-    if x.dim() != 4 or f.dim() != 4 or f.shape[1] != 2 or f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
-        raise ValueError(f"warp2d: bad shapes {tuple(x.shape)} / {tuple(f.shape)}")
-    n, c, h, w = x.shape
+def _check_warp_shapes(x, f, nd):
+    if x.dim() != nd + 2 or f.dim() != nd + 2 or f.shape[1] != nd or f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
+        raise ValueError(f"warp{nd}d: bad shapes {tuple(x.shape)} / {tuple(f.shape)}")
+
+
+def _warp_fwd(x, f):
+    nd = x.dim() - 2
+    dev = x.device
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
-        _C.check(_C.lib().ofsv_warp2d_f32(_p(x), _p(f), _p(linspace_table(w, x.device)), _p(linspace_table(h, x.device)),
-                                          _p(out), n, c, h, w, _FLAVOR["mode"], _stream()))
+    with torch.cuda.device(dev):
+        if nd == 2:
+            n, c, h, w = x.shape
+            _C.check(_C.lib().ofsv_warp2d_f32(_p(x), _p(f), _p(linspace_table(w, dev)), _p(linspace_table(h, dev)),
+                                              _p(out), n, c, h, w, _FLAVOR["mode"], _stream()))
+        else:
+            n, c, d, h, w = x.shape
+            with _span("warp3d"):
+                _C.check(_C.lib().ofsv_warp3d_f32(_p(x), _p(f), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
+                                                  _p(linspace_table(w, dev)), _p(out), n, c, d, h, w, _FLAVOR["mode"], _stream()))
     return out
+
+
+def warp_bwd(tenInput, tenFlow, grad_out, need_input_grad=True, need_flow_grad=True):
+    """Backward of `warp` (ofsv_warp{2,3}d_bwd_f32): (grad_input, grad_flow), either None when not asked for.
+    = ATen grid_sampler backward (bilinear / border / align_corners, zero gradient where the coordinate was clipped)
+    chained with the backward of flow / ((S-1)/2) — what autograd runs under Flow-*/model/warplayer.py:26 / :37."""
+    x, f, go = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow"), _cuda_f32(grad_out, "grad_out")
+    nd = x.dim() - 2
+    _check_warp_shapes(x, f, nd)
+    if go.shape != x.shape:
+        raise ValueError(f"warp_bwd: grad_out {tuple(go.shape)} does not match the output shape {tuple(x.shape)}")
+    dev = x.device
+    gx = torch.empty_like(x) if need_input_grad else None       # zero-filled by the library
+    gf = torch.empty_like(f) if need_flow_grad else None
+    with torch.cuda.device(dev), _span("warp_bwd"):
+        if nd == 2:
+            n, c, h, w = x.shape
+            _C.check(_C.lib().ofsv_warp2d_bwd_f32(_p(x), _p(f), _p(go), _p(linspace_table(w, dev)), _p(linspace_table(h, dev)),
+                                                  _p(gx), _p(gf), n, c, h, w, _FLAVOR["mode"], _stream()))
+        else:
+            n, c, d, h, w = x.shape
+            _C.check(_C.lib().ofsv_warp3d_bwd_f32(_p(x), _p(f), _p(go), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
+                                                  _p(linspace_table(w, dev)), _p(gx), _p(gf), n, c, d, h, w,
+                                                  _FLAVOR["mode"], _stream()))
+    return gx, gf
+
+
+class _WarpFn(torch.autograd.Function):
+    """autograd node of warp(): the reference's warp is differentiable in both arguments (it is a grid_sample)."""
+
+    @staticmethod
+    def forward(ctx, x, f):
+        ctx.save_for_backward(x, f)
+        return _warp_fwd(x, f)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, f = ctx.saved_tensors
+        gx, gf = warp_bwd(x, f, grad_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gx, gf
+
+
+def _warp(tenInput, tenFlow, nd):
+    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
+    _check_warp_shapes(x, f, nd)
+    if torch.is_grad_enabled() and (x.requires_grad or f.requires_grad):
+        return _WarpFn.apply(x, f)
+    return _warp_fwd(x, f)
+
+
+def warp2d(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
+    return _warp(tenInput, tenFlow, 2)
 
 
 def warp3d(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
-    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
-    if x.dim() != 5 or f.dim() != 5 or f.shape[1] != 3 or f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
-        raise ValueError(f"warp3d: bad shapes {tuple(x.shape)} / {tuple(f.shape)}")
-    n, c, d, h, w = x.shape
-    out = torch.empty_like(x)
-    dev = x.device
-    with torch.cuda.device(dev), _span("warp3d"):
-        _C.check(_C.lib().ofsv_warp3d_f32(_p(x), _p(f), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
-                                          _p(linspace_table(w, dev)), _p(out), n, c, d, h, w, _FLAVOR["mode"], _stream()))
-    return out
+    return _warp(tenInput, tenFlow, 3)
 
 
 def warp_blend(img0, img1, flow, mask_logit, want_warped=True, want_merged=True, want_mask=True):

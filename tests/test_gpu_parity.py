@@ -654,3 +654,91 @@ def test_recursive_interpolation_on_device():
     seq = interp.interpolate_recursive(m, d0, d1, exp=2)
     assert len(seq) == 5 and seq[0] is d0 and seq[4] is d1
     assert torch.equal(seq[2], m.inference(d0, d1)[0]) and torch.equal(seq[1], m.inference(d0, seq[2])[0])
+
+
+# ------------------------------------------------------------------------------------------------- warp backward (f.1)
+BWD_RTOL = 1e-5       # relative to the largest gradient of the case (fp32 sums in another order + atomic scatter)
+
+
+def _bwd_close(got, ref, what):
+    # grad_src is a scatter-SUM: where thousands of clipped samples pile onto one border voxel ("edge" / "far" cases) the
+    # fp32 sum depends on the order (the reference's own sequential CPU sum is 1e-5 off the fp64 value), hence 5e-5 there
+    tol = (5e-5 if "gsrc" in what else BWD_RTOL) * max(1.0, float(np.abs(ref).max()))
+    d = float(np.abs(_np(got) - ref).max())
+    assert d <= tol, (what, d, tol)
+    return d
+
+
+def test_warp_backward_golden_fixtures():
+    """ofsv_warp{2,3}d_bwd_f32 through autograd of the drop-in warp() vs autograd through the reference's warp."""
+    from opticalflowscivis_b200.flow2d.model.warplayer import warp as warp2
+    from opticalflowscivis_b200.flow3d.model.warplayer import warp as warp3
+    z = np.load(os.path.join(G, "warp_bwd.npz"))
+    keys = sorted({k.rsplit("_", 1)[0] for k in z.files})
+    assert len(keys) == 16
+    for k in keys:
+        src, flow, gout = (torch.from_numpy(z[f"{k}_{s}"]).to(_dev()) for s in ("src", "flow", "gout"))
+        a, b = src.clone().requires_grad_(), flow.clone().requires_grad_()
+        out = (warp2 if flow.shape[1] == 2 else warp3)(a, b)
+        out.backward(gout)
+        _bwd_close(a.grad, z[f"{k}_gsrc"], k + " gsrc")
+        _bwd_close(b.grad, z[f"{k}_gflow"], k + " gflow")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56), (1, 1, 160, 224), (2, 16, 30, 50), (1, 2, 20, 36, 52), (1, 1, 33, 31, 35), (2, 1, 64, 64, 64)])
+def test_warp_backward_vs_autograd_oracle(shape):
+    from opticalflowscivis_b200 import ops
+    from oracle import ops_ref
+    nd = len(shape) - 2
+    g = torch.Generator().manual_seed(11 + len(shape))
+    src = torch.rand(shape, generator=g)
+    flow = torch.randn((shape[0], nd) + shape[2:], generator=g) * 3
+    gout = torch.randn(shape, generator=g)
+    a, b = src.clone().requires_grad_(), flow.clone().requires_grad_()
+    (ops_ref.warp2d_ref if nd == 2 else ops_ref.warp3d_ref)(a, b).backward(gout)
+    gx, gf = ops.warp_bwd(src.to(_dev()), flow.to(_dev()), gout.to(_dev()))
+    _bwd_close(gx, a.grad.numpy(), "gsrc")
+    _bwd_close(gf, b.grad.numpy(), "gflow")
+    # either gradient alone (the other pointer NULL)
+    gx2, none = ops.warp_bwd(src.to(_dev()), flow.to(_dev()), gout.to(_dev()), True, False)
+    assert none is None
+    _bwd_close(gx2, a.grad.numpy(), "gsrc only")
+    none, gf2 = ops.warp_bwd(src.to(_dev()), flow.to(_dev()), gout.to(_dev()), False, True)
+    assert none is None and torch.equal(gf2, gf)
+
+
+def test_warp_backward_full_size_properties():
+    """256^3 (BASELINE cfg 4 size): the trilinear weights of a voxel sum to 1, so sum(grad_src) == sum(grad_out); a flow that
+    pushes every sample out of the volume has zero flow gradient; zero flow on a cube routes grad_out through the axis rotation."""
+    from opticalflowscivis_b200 import ops
+    S = 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.rand((1, 1, S, S, S), device=_dev(), generator=g)
+    gout = torch.rand((1, 1, S, S, S), device=_dev(), generator=g)
+    flow = torch.randn((1, 3, S, S, S), device=_dev(), generator=g) * 2
+    gx, gf = ops.warp_bwd(src, flow, gout)
+    assert abs(float(gx.double().sum()) / float(gout.double().sum()) - 1.0) < 1e-6
+    assert torch.isfinite(gf).all()
+    gx, gf = ops.warp_bwd(src, torch.full_like(flow, 1e4), gout)
+    assert float(gf.abs().max()) == 0.0       # (all 16.7 M samples pile onto one corner voxel: no fp32 sum check here)
+    gx, _ = ops.warp_bwd(src, torch.zeros_like(flow), gout, True, False)
+    # forward: out[d,h,w] = src[w,d,h]  =>  gsrc[z,y,x] = gout[y,x,z]
+    # (the fp32 linspace -> coordinate round trip is off an integer by up to an ulp of 255 = 1.5e-5: that much weight leaks)
+    assert float((gx - gout.permute(0, 1, 4, 2, 3)).abs().max()) <= 1e-4
+
+
+def test_warp_backward_edges():
+    from opticalflowscivis_b200 import ops
+    dev = _dev()
+    # empty batch / zero channels
+    gx, gf = ops.warp_bwd(torch.empty(0, 1, 8, 8, device=dev), torch.empty(0, 2, 8, 8, device=dev), torch.empty(0, 1, 8, 8, device=dev))
+    assert gx.shape == (0, 1, 8, 8) and gf.shape == (0, 2, 8, 8)
+    gx, gf = ops.warp_bwd(torch.empty(2, 0, 4, 6, 8, device=dev), torch.zeros(2, 3, 4, 6, 8, device=dev), torch.empty(2, 0, 4, 6, 8, device=dev))
+    assert gx.numel() == 0 and float(gf.abs().max()) == 0.0
+    with pytest.raises(TypeError):
+        ops.warp_bwd(torch.zeros(1, 1, 8, 8), torch.zeros(1, 2, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(ValueError):
+        ops.warp_bwd(torch.zeros(1, 1, 8, 8, device=dev), torch.zeros(1, 2, 8, 8, device=dev), torch.zeros(1, 2, 8, 8, device=dev))
+    # no grad requested -> plain forward, no autograd node
+    x = torch.rand(1, 1, 8, 8, device=dev)
+    assert not ops.warp2d(x, torch.zeros(1, 2, 8, 8, device=dev)).requires_grad

@@ -114,3 +114,24 @@ def test_metrics_golden():
     # the training-loop form on [0,1] data is the same quantity on another scale (Flow-3D/train.py:385)
     p01 = mr.psnr_train(z["a_img1"] / 255.0, z["a_img2"] / 255.0)
     assert abs(p01 - float(z["a_psnr"])) <= 1e-5
+
+
+def test_warp_backward_golden():
+    """Backward of warp (autograd under Flow-*/model/warplayer.py): torch-autograd oracle and the numpy restatement
+    both replay the vectors tests/golden/make_warp_bwd_golden.py took from autograd through the reference's warp."""
+    from oracle.warp_bwd_ref import warp_bwd
+    z = np.load(os.path.join(G, "warp_bwd.npz"))
+    n = 0
+    for name, (src, flow, gout, gsrc, gflow) in _cases(z, ("src", "flow", "gout", "gsrc", "gflow")):
+        nd = flow.shape[1]
+        a, b = torch.from_numpy(src).requires_grad_(), torch.from_numpy(flow).requires_grad_()
+        (ops_ref.warp2d_ref if nd == 2 else ops_ref.warp3d_ref)(a, b).backward(torch.from_numpy(gout))
+        assert np.abs(a.grad.numpy() - gsrc).max() <= 1e-5 * max(1.0, np.abs(gsrc).max()), name
+        assert np.abs(b.grad.numpy() - gflow).max() <= 1e-5 * max(1.0, np.abs(gflow).max()), name
+        gs, gf = warp_bwd(src, flow, gout)
+        assert np.abs(gs - gsrc).max() <= 1e-5 * max(1.0, np.abs(gsrc).max()), name
+        assert np.abs(gf - gflow).max() <= 1e-5 * max(1.0, np.abs(gflow).max()), name
+        if "far" in name or "edge" in name:      # clipped coordinates carry no flow gradient
+            assert (gflow == 0).mean() > (0.9 if "edge" in name else 0.5), name
+        n += 1
+    assert n == 16
