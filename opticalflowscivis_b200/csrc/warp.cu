@@ -129,7 +129,7 @@ template <bool VEC, bool FMA>
 __global__ void __launch_bounds__(32 * W3_WARPS, OFSV_W3_MINB)
     warp3d_kernel(const float* __restrict__ src, const float* __restrict__ flow, const float* __restrict__ lin_h,
                   const float* __restrict__ lin_d, const float* __restrict__ lin_w, float* __restrict__ out,
-                  const Warp3dParams P, const long long ntasks) {
+                  const Warp3dParams P, const uint32_t ntasks) {
   extern __shared__ __align__(16) float w3_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* sf = w3_smem + wid * (W3_SMEM_PER_WARP / 4);     // [2][3][32][W3_ROW]
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(32 * W3_WARPS, OFSV_W3_MINB)
   const int64_t V = (int64_t)D * HW;
   const int hblocks = (H + 31) >> 5;
   const int ntw = (W + W3_WT - 1) / W3_WT;
-  const long long stride = (long long)gridDim.x * W3_WARPS;
+  const uint32_t stride = gridDim.x * W3_WARPS;      // task ids are 32-bit (host check): the decode is plain 32-bit division
   struct Task { int n, d, h0, w0; };
-  auto decode = [&](long long id) {
+  auto decode = [&](uint32_t id) {
     Task k;
     k.w0 = (int)(id % ntw) * W3_WT; id /= ntw;
     k.h0 = (int)(id % hblocks) << 5; id /= hblocks;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(32 * W3_WARPS, OFSV_W3_MINB)
     return k;
   };
   // async copy of the flow tile of task `id` (3 planes x 32 rows x 16 floats) into stage st: row = i*8 + lane/4, chunk = lane%4
-  auto issue = [&](long long id, int st) {
+  auto issue = [&](uint32_t id, int st) {
     if (id < ntasks) {
       const Task k = decode(id);
       const float* fl = flow + (int64_t)k.n * 3 * V + (int64_t)k.d * HW;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(32 * W3_WARPS, OFSV_W3_MINB)
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  long long task = (long long)blockIdx.x * W3_WARPS + wid;
+  uint32_t task = blockIdx.x * W3_WARPS + wid;
   issue(task, 0);
   for (int it = 0; task < ntasks; task += stride, ++it) {
     const int st = it & 1;
@@ -321,8 +321,10 @@ extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float*
   const Warp3dParams P = make_warp3d_params(N, C, D, H, W, ref_mode);
   const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long ntasks = (long long)N * D * cdiv(H, 32) * cdiv(W, W3_WT);
-  const int64_t ctas = cdiv(ntasks, W3_WARPS);
+  const long long ntasks64 = (long long)N * D * cdiv(H, 32) * cdiv(W, W3_WT);
+  OFSV_REQUIRE(ntasks64 < (1ll << 31) - 148 * 64, "ofsv_warp3d_f32: too many tiles for 32-bit task ids");
+  const uint32_t ntasks = (uint32_t)ntasks64;
+  const int64_t ctas = cdiv(ntasks64, W3_WARPS);
   const int grid = (int)(ctas < 148 * OFSV_W3_MINB ? ctas : 148 * OFSV_W3_MINB);      // OFSV_W3_MINB CTAs of 4 warps resident per SM, persistent over the task list
   const int smem = W3_WARPS * W3_SMEM_PER_WARP;
   static bool attr_done = false;

@@ -5,8 +5,10 @@
 namespace ofsv {
 
 struct Trilin {
-  int base;            // z0*HW + y0*W + x0
-  int dx, dy, dz;      // element offset of the +1 neighbour along each source axis, 0 when it lies outside the volume
+  // unsigned 32-bit ELEMENT indices: a tap address is then one IMAD.WIDE.U32 (index * 4 + base pointer) instead of a
+  // sign-extended 64-bit add + LEA pair per tap (a quarter of the gather kernels' instructions before)
+  uint32_t base;       // z0*HW + y0*W + x0
+  uint32_t dx, dy, dz; // element offset of the +1 neighbour along each source axis, 0 when it lies outside the volume
   float ex, wx, ey, wy, ez, wz;
 };
 
@@ -27,10 +29,10 @@ __device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, flo
   // A +1 neighbour outside the volume only occurs when the clipped coordinate sits exactly on the last sample, where its
   // weight (wx / wy / wz) is exactly 0: ATen skips the tap, here it re-reads the in-range sample with weight 0.  That keeps
   // the 8 taps branch-free so that all gathers of a voxel are in flight together (one memory round trip, not four).
-  t.dx = x0 + 1 <= W - 1 ? 1 : 0;
-  t.dy = y0 + 1 <= H - 1 ? W : 0;
-  t.dz = z0 + 1 <= D - 1 ? H * W : 0;
-  t.base = (z0 * H + y0) * W + x0;
+  t.dx = x0 + 1 <= W - 1 ? 1u : 0u;
+  t.dy = y0 + 1 <= H - 1 ? (uint32_t)W : 0u;
+  t.dz = z0 + 1 <= D - 1 ? (uint32_t)(H * W) : 0u;
+  t.base = (uint32_t)((z0 * H + y0) * W + x0);
   return t;
 }
 
@@ -43,11 +45,10 @@ struct Taps8 {
   float v[8];
 };
 __device__ __forceinline__ Taps8 trilin_gather(const float* __restrict__ p, const Trilin& t) {
-  const float* q = p + t.base;
+  const uint32_t i0 = t.base, i1 = i0 + t.dx, i2 = i0 + t.dy, i3 = i2 + t.dx;
   Taps8 r;
-  r.v[0] = __ldg(q); r.v[1] = __ldg(q + t.dx); r.v[2] = __ldg(q + t.dy); r.v[3] = __ldg(q + t.dy + t.dx);
-  q += t.dz;
-  r.v[4] = __ldg(q); r.v[5] = __ldg(q + t.dx); r.v[6] = __ldg(q + t.dy); r.v[7] = __ldg(q + t.dy + t.dx);
+  r.v[0] = __ldg(p + i0); r.v[1] = __ldg(p + i1); r.v[2] = __ldg(p + i2); r.v[3] = __ldg(p + i3);
+  r.v[4] = __ldg(p + (i0 + t.dz)); r.v[5] = __ldg(p + (i1 + t.dz)); r.v[6] = __ldg(p + (i2 + t.dz)); r.v[7] = __ldg(p + (i3 + t.dz));
   return r;
 }
 // ATen grid_sampler_3d corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse; weights = product of 3 distances, left to right.
