@@ -52,6 +52,12 @@ int ofsv_warp2d_f32(const float* src, const float* flow, const float* lin_x, con
 int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
                     float* out, int N, int C, int D, int H, int W, int ref_mode, void* stream);
 
+/* Same contract as ofsv_warp3d_f32, always on the global-gather kernel (ofsv_warp3d_f32 picks the TMA slab kernel of
+ * csrc/warp3d_slab.cu on cubic volumes with S % 32 == 0; the two are bit-identical — this entry exists so that tests and
+ * benchmarks can run both). */
+int ofsv_warp3d_gather_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
+                           float* out, int N, int C, int D, int H, int W, int ref_mode, void* stream);
+
 /* ---- backward of a1 / a2: what autograd runs under warp() in the reference's training step (Flow-2D/model/RIFE.py:80-336,
  * Flow-3D/model/RIFE.py:81-275 through Flow-{2D,3D}/model/warplayer.py:26 / :37) = ATen grid_sampler_{2,3}d_backward (bilinear,
  * border, align_corners=True, incl. the zero gradient of clipped coordinates) followed by the backward of

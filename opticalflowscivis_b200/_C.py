@@ -38,6 +38,7 @@ _SIGS = {
     "ofsv_launch_count": (_L, []),
     "ofsv_warp2d_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ofsv_warp3d_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ofsv_warp3d_gather_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warp2d_bwd_f32": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),
     "ofsv_warp3d_bwd_f32": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warp_blend_2d_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),

@@ -310,14 +310,22 @@ extern "C" int ofsv_warp_blend_2d_f32(const float* img0, const float* img1, cons
   return check_launch("warp_blend_2d_kernel");
 }
 
-extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d,
-                               const float* lin_w, float* out, int N, int C, int D, int H, int W, int ref_mode,
-                               void* stream) {
+namespace ofsv {
+int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w, float* out,
+                    int N, int C, int D, int H, int W, int ref_mode, cudaStream_t st);   // warp3d_slab.cu
+}
+// engine: 0 = pick (the TMA slab kernel on cubic volumes it supports, else the global-gather kernel), 1 = global gather only
+static int warp3d_dispatch(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
+                           float* out, int N, int C, int D, int H, int W, int ref_mode, void* stream, int engine) {
   OFSV_REQUIRE(N >= 0 && C >= 0 && D >= 1 && H >= 1 && W >= 1, "ofsv_warp3d_f32: bad shape");
   if ((int64_t)N * C == 0) return OFSV_OK;   // empty batch
   OFSV_REQUIRE(src && flow && lin_h && lin_d && lin_w && out, "ofsv_warp3d_f32: null pointer");
   OFSV_REQUIRE((int64_t)D * H * W < (1ll << 31), "ofsv_warp3d_f32: volume too large for 32-bit voxel offsets");
   OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warp3d_f32: bad ref_mode %d", ref_mode);
+  if (engine == 0) {
+    const int rc = warp3d_slab_try(src, flow, lin_h, lin_d, lin_w, out, N, C, D, H, W, ref_mode, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : OFSV_OK;
+  }
   const Warp3dParams P = make_warp3d_params(N, C, D, H, W, ref_mode);
   const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
   cudaStream_t st = (cudaStream_t)stream;
@@ -340,6 +348,17 @@ extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float*
   else     { if (ref_mode == OFSV_REF_CUDA) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
   return check_launch("warp3d_kernel");
+}
+
+extern "C" int ofsv_warp3d_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d,
+                               const float* lin_w, float* out, int N, int C, int D, int H, int W, int ref_mode,
+                               void* stream) {
+  return warp3d_dispatch(src, flow, lin_h, lin_d, lin_w, out, N, C, D, H, W, ref_mode, stream, 0);
+}
+extern "C" int ofsv_warp3d_gather_f32(const float* src, const float* flow, const float* lin_h, const float* lin_d,
+                                      const float* lin_w, float* out, int N, int C, int D, int H, int W, int ref_mode,
+                                      void* stream) {
+  return warp3d_dispatch(src, flow, lin_h, lin_d, lin_w, out, N, C, D, H, W, ref_mode, stream, 1);
 }
 
 extern "C" int ofsv_warp_blend_3d_f32(const float* img0, const float* img1, const float* flow, const float* mask_logit,

@@ -1,0 +1,244 @@
+// a2 on cubic volumes: 3-D warp with the SOURCE staged in shared memory by TMA (the north-star design for the gather
+// kernels).  The generic kernel in warp.cu gathers straight from global memory: 8 LDG per voxel, each with a 64-bit address
+// (a quarter of its instructions) and 10+ sectors per request on realistic flows (L1 data pipe at 67 %).  Here
+//
+//   * the reference warp rotates axes: output (d,h,w) samples source (z,y,x) ~ (w,d,h) + flow.  A CTA owns a
+//     32(h) x 32(w) output column and WALKS ALONG d; what it needs of the source for plane d is the y-slab
+//     src[z in w0-5 .. w0+38][y = d-5 .. d+6][x in h0-8 .. h0+39] — as d advances, one new 44 x 48 slab per plane enters a
+//     16-slab ring (slot = y & 15).  Slabs arrive by ONE cp.async.bulk.tensor each (4-D box {48,1,44,1}, out-of-volume
+//     elements zero-filled = the weight-0 neighbour of a border-clipped sample), two planes ahead of their use;
+//   * the flow tile of a plane (3 x 32 x 32 floats) arrives by TMA too, SWIZZLE_128B so that lane = h reads its four
+//     consecutive w values with one conflict-free LDS.128 per channel;
+//   * a tap is an LDS with an immediate offset from one of two 32-bit bases (slab y0, slab y0+1): 8 LDS + ~10 address
+//     instructions per voxel instead of 8 LDG + ~40;
+//   * a voxel whose cell leaves the staged window (|flow| beyond ~5 voxels) takes the global gather of warp.cu, per lane —
+//     correctness never depends on the window;
+//   * results cross a swizzled shared tile and leave as fully coalesced 16 B stores along w.
+//
+// Coordinates, weights and the summation order are the shared helpers of warp_device.cuh: results are bit-identical to the
+// generic kernel (tests/test_gpu_parity.py::test_warp3d_slab_equals_generic) and to the C oracle.
+#include "tc_common.cuh"
+#include "warp_device.cuh"
+
+namespace ofsv {
+
+constexpr int SL_TH = 32, SL_TW = 32;          // output tile (h, w)
+constexpr int SL_MY = 5;                       // planes of the y window below d (live slabs of a plane pair: d-5 .. d+7)
+constexpr int SL_NS = 16;                      // ring slots
+constexpr int SL_XLO = 8, SL_NX = 48;          // x window [h0-8, h0+40)
+constexpr int SL_ZLO = 5, SL_NZ = 44;          // z window [w0-5, w0+39)
+constexpr int SL_SLAB = SL_NZ * SL_NX * 4;     // 8448 B (multiple of 128)
+constexpr int SL_FTILE = SL_TH * SL_TW * 4;    // 4096 B per (plane, channel)
+constexpr int SL_FSTAGE = 2 * 3 * SL_FTILE;    // two planes x three channels
+constexpr int SL_OUT = 2 * SL_FTILE;           // two planes of results
+constexpr int SL_THREADS = 512;
+constexpr int SL_SMEM = SL_NS * SL_SLAB + 2 * SL_FSTAGE + 2 * SL_OUT + 64 + 1024;   // + barriers + alignment slack
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct SlabParams {
+  int N, C, S;        // cubic: D = H = W = S
+  int ref_mode;
+  int dz;             // planes per task (even)
+  uint32_t ntasks;
+  float hs[6];
+};
+
+template <bool FMA>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+    warp3d_slab_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_flow,
+                       const float* __restrict__ src, const float* __restrict__ lin_h, const float* __restrict__ lin_d,
+                       const float* __restrict__ lin_w, float* __restrict__ out, const SlabParams P) {
+  extern __shared__ uint8_t sl_raw[];
+  const uint32_t s_base = (smem_u32(sl_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t s_flow = s_base;                                         // [2 stages][2 planes][3 ch][32 h][32 w] swizzled
+  const uint32_t s_out = s_flow + 2 * SL_FSTAGE;                          // [2 buffers][2 planes][32 h][32 w] swizzled
+  const uint32_t s_slab = s_out + 2 * SL_OUT;                             // [16 slots][44 z][48 x]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sl_raw + (s_slab + SL_NS * SL_SLAB - smem_u32(sl_raw)));   // full[2]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int pl = wid >> 3, q = wid & 7;                                   // plane of the pair, 4-voxel column group
+  const int S = P.S;
+  const int64_t V = (int64_t)S * S * S;
+  const int nt = S / 32, nchunk = S / P.dz;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t g = 0;                                                         // pair-iteration counter across tasks: stage = g & 1
+  for (uint32_t task = blockIdx.x; task < P.ntasks; task += gridDim.x) {
+    // task -> (volume nc, d chunk, h tile, w tile); w tile fastest: concurrent CTAs read neighbouring flow rows / source slabs
+    uint32_t r = task;
+    const int tw = r % nt; r /= nt;
+    const int th = r % nt; r /= nt;
+    const int ck = r % nchunk;
+    const int nc = r / nchunk;
+    const int n = nc / P.C;
+    const int h0 = th * 32, w0 = tw * 32, d0 = ck * P.dz;
+    const int xorg = h0 - SL_XLO, zorg = w0 - SL_ZLO;
+    const float* sp = src + (int64_t)nc * V;
+    float* op = out + (int64_t)nc * V;
+
+    auto load_pair = [&](int d, uint32_t gi, int y_first, int y_last) {   // one thread: flow of planes d, d+1 + slabs y_first..y_last
+      uint64_t* bar = &bars[gi & 1];
+      mbar_expect_tx(bar, (uint32_t)(SL_FSTAGE + (y_last - y_first + 1) * SL_SLAB));
+      const uint32_t fs = s_flow + (gi & 1) * SL_FSTAGE;
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tma_load_4d(&tm_flow, bar, fs + (p * 3 + c) * SL_FTILE, w0, h0, d + p, n * 3 + c);
+      for (int y = y_first; y <= y_last; ++y) tma_load_4d(&tm_src, bar, s_slab + (uint32_t)(y & (SL_NS - 1)) * SL_SLAB, xorg, y, zorg, nc);
+    };
+
+    __syncthreads();                       // every thread is done with the previous task's slabs / flow stages
+    if (tid == 0) load_pair(d0, g, d0 - SL_MY, d0 + SL_MY + 2);
+
+    const int h = h0 + lane;
+    const float lh = __ldg(lin_h + h);
+    for (int it = 0; it < P.dz / 2; ++it, ++g) {
+      const int dc = d0 + 2 * it;          // planes dc, dc + 1
+      __syncthreads();                     // pair it-1 fully computed: its results are in s_out, its oldest two slabs are dead
+      if (tid == 0 && it + 1 < P.dz / 2) load_pair(dc + 2, g + 1, dc + SL_MY + 3, dc + SL_MY + 4);
+      if (it > 0) {                        // coalesced stores of the previous pair
+        const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
+        const int p = tid >> 8, row = (tid >> 3) & 31, c = tid & 7;
+        const float4 v = lds_f32x4(ob + p * SL_FTILE + row * 128 + ((c ^ (row & 7)) << 4));
+        stg_stream4(op + ((int64_t)(dc - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+      }
+      mbar_wait(&bars[g & 1], (g >> 1) & 1);
+
+      const int d = dc + pl;
+      const float ld = __ldg(lin_d + d);
+      const uint32_t fa = s_flow + (g & 1) * SL_FSTAGE + pl * 3 * SL_FTILE + lane * 128 + ((q ^ (lane & 7)) << 4);
+      const float4 F0 = lds_f32x4(fa), F1 = lds_f32x4(fa + SL_FTILE), F2 = lds_f32x4(fa + 2 * SL_FTILE);
+      const float4 LW = __ldg(reinterpret_cast<const float4*>(lin_w + w0 + q * 4));
+      const float f0[4] = {F0.x, F0.y, F0.z, F0.w}, f1[4] = {F1.x, F1.y, F1.z, F1.w}, f2[4] = {F2.x, F2.y, F2.z, F2.w};
+      const float lw[4] = {LW.x, LW.y, LW.z, LW.w};
+      float res[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        TrilinCell cell[2];
+        Taps8 tp[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = half * 2 + j;
+          cell[j] = trilin_cell(f0[k], f1[k], f2[k], lh, ld, lw[k], S, S, S, P.hs, P.ref_mode);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const TrilinCell& c = cell[j];
+          const uint32_t xr = (uint32_t)(c.x0 - xorg), zr = (uint32_t)(c.z0 - zorg), yr = (uint32_t)(c.y0 - (dc - SL_MY));
+          if (xr <= (uint32_t)(SL_NX - 2) && zr <= (uint32_t)(SL_NZ - 2) && yr <= (uint32_t)(2 * SL_MY + 1)) {
+            const uint32_t in = (zr * SL_NX + xr) * 4;
+            const uint32_t a0 = s_slab + (uint32_t)(c.y0 & (SL_NS - 1)) * SL_SLAB + in;
+            const uint32_t a1 = s_slab + (uint32_t)((c.y0 + 1) & (SL_NS - 1)) * SL_SLAB + in;
+            tp[j].v[0] = lds_f32(a0); tp[j].v[1] = lds_f32(a0 + 4);
+            tp[j].v[2] = lds_f32(a1); tp[j].v[3] = lds_f32(a1 + 4);
+            tp[j].v[4] = lds_f32(a0 + SL_NX * 4); tp[j].v[5] = lds_f32(a0 + SL_NX * 4 + 4);
+            tp[j].v[6] = lds_f32(a1 + SL_NX * 4); tp[j].v[7] = lds_f32(a1 + SL_NX * 4 + 4);
+          } else {
+            tp[j] = trilin_gather(sp, trilin_from_cell(c, S, S, S));      // cell outside the staged window
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          Trilin t;
+          t.ex = cell[j].ex; t.wx = cell[j].wx; t.ey = cell[j].ey; t.wy = cell[j].wy; t.ez = cell[j].ez; t.wz = cell[j].wz;
+          t.base = t.dx = t.dy = t.dz = 0;
+          res[half * 2 + j] = trilin_reduce<FMA>(tp[j], t);
+        }
+      }
+      sts_f32x4(s_out + (g & 1) * SL_OUT + pl * SL_FTILE + lane * 128 + ((q ^ (lane & 7)) << 4),
+                make_float4(res[0], res[1], res[2], res[3]));
+    }
+    __syncthreads();
+    {                                      // last pair of the task
+      const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
+      const int p = tid >> 8, row = (tid >> 3) & 31, c = tid & 7;
+      const float4 v = lds_f32x4(ob + p * SL_FTILE + row * 128 + ((c ^ (row & 7)) << 4));
+      stg_stream4(op + ((int64_t)(d0 + P.dz - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+    }
+  }
+}
+
+// returns 1 when the slab kernel was launched, 0 when the shape is not eligible (caller falls back), < 0 on error
+int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w, float* out, int N, int C, int D, int H, int W,
+                    int ref_mode, cudaStream_t st) {
+  if (!(D == H && H == W && W % 32 == 0 && W >= 32 && W <= 1024)) return 0;
+  if (!aligned16(src) || !aligned16(flow) || !aligned16(out) || !aligned16(lin_w)) return 0;
+  if ((int64_t)N * C > (1 << 20) || (int64_t)N * 3 > (1 << 20)) return 0;
+  PFN_encodeTiled encode = get_tensor_map_encoder();
+  if (!encode) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
+  const int S = W;
+  CUtensorMap tm_src, tm_flow;
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)N * C};
+    const cuuint64_t gstr[3] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4, (cuuint64_t)S * S * S * 4};
+    const cuuint32_t box[4] = {SL_NX, 1, SL_NZ, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tm_src, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(src), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled(src) failed (%d)", (int)r); return OFSV_ECUDA; }
+  }
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)N * 3};
+    const cuuint64_t gstr[3] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4, (cuuint64_t)S * S * S * 4};
+    const cuuint32_t box[4] = {SL_TW, SL_TH, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tm_flow, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(flow), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled(flow) failed (%d)", (int)r); return OFSV_ECUDA; }
+  }
+  SlabParams P;
+  P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode;
+  const Warp3dParams wp = make_warp3d_params(N, C, D, H, W, ref_mode);
+  for (int i = 0; i < 6; ++i) P.hs[i] = wp.hs[i];
+  const int64_t tiles = (int64_t)N * C * (S / 32) * (S / 32);
+  int dz = 16;                                    // longer walks amortise the 13-slab prologue; keep >= 6 tasks per SM
+  for (int cand : {64, 32}) {
+    if (S % cand == 0 && tiles * (S / cand) >= 6 * 148) { dz = cand; break; }
+  }
+  if (S % dz != 0) dz = S % 16 == 0 ? 16 : 0;
+  if (dz == 0) return 0;
+  P.dz = dz;
+  const int64_t ntasks = tiles * (S / dz);
+  if (ntasks >= (1ll << 31)) return 0;
+  P.ntasks = (uint32_t)ntasks;
+  const int grid = (int)(ntasks < 148 ? ntasks : 148);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(warp3d_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(warp3d_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("ofsv_warp3d_f32: cudaFuncSetAttribute failed"); return OFSV_ECUDA; }
+    attr_done = true;
+  }
+  if (ref_mode == OFSV_REF_CUDA) warp3d_slab_kernel<true><<<grid, SL_THREADS, SL_SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
+  else warp3d_slab_kernel<false><<<grid, SL_THREADS, SL_SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
+  const int rc = check_launch("warp3d_slab_kernel");
+  return rc == OFSV_OK ? 1 : rc;
+}
+
+}  // namespace ofsv

@@ -13,27 +13,41 @@ struct Trilin {
 };
 
 // (f0,f1,f2) = flow channels; lh/ld/lw = linspace entries of THIS output voxel's (h,d,w).
-__device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
-                                               int W, const float* hs, int ref_mode) {
+// Integer cell (x0,y0,z0) of the sample in the source volume + the six 1-D weights, op for op like the reference.
+struct TrilinCell {
+  int x0, y0, z0;
+  float ex, wx, ey, wy, ez, wz;
+};
+__device__ __forceinline__ TrilinCell trilin_cell(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
+                                                  int W, const float* hs, int ref_mode) {
   const float g0 = __fadd_rn(lh, norm_flow(f0, hs[0], hs[3], ref_mode));  // sampled along the W axis
   const float g1 = __fadd_rn(ld, norm_flow(f1, hs[1], hs[4], ref_mode));  // along H
   const float g2 = __fadd_rn(lw, norm_flow(f2, hs[2], hs[5], ref_mode));  // along D
   const float ix = unnorm_clip_ac(g0, (float)(W - 1)), iy = unnorm_clip_ac(g1, (float)(H - 1)),
               iz = unnorm_clip_ac(g2, (float)(D - 1));
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-  Trilin t;
+  TrilinCell t;
   t.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix); t.wx = __fsub_rn(ix, fx);
   t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy); t.wy = __fsub_rn(iy, fy);
   t.ez = __fsub_rn(__fadd_rn(fz, 1.0f), iz); t.wz = __fsub_rn(iz, fz);
-  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  t.x0 = (int)fx; t.y0 = (int)fy; t.z0 = (int)fz;
+  return t;
+}
+__device__ __forceinline__ Trilin trilin_from_cell(const TrilinCell& c, int D, int H, int W) {
+  Trilin t;
+  t.ex = c.ex; t.wx = c.wx; t.ey = c.ey; t.wy = c.wy; t.ez = c.ez; t.wz = c.wz;
   // A +1 neighbour outside the volume only occurs when the clipped coordinate sits exactly on the last sample, where its
   // weight (wx / wy / wz) is exactly 0: ATen skips the tap, here it re-reads the in-range sample with weight 0.  That keeps
   // the 8 taps branch-free so that all gathers of a voxel are in flight together (one memory round trip, not four).
-  t.dx = x0 + 1 <= W - 1 ? 1u : 0u;
-  t.dy = y0 + 1 <= H - 1 ? (uint32_t)W : 0u;
-  t.dz = z0 + 1 <= D - 1 ? (uint32_t)(H * W) : 0u;
-  t.base = (uint32_t)((z0 * H + y0) * W + x0);
+  t.dx = c.x0 + 1 <= W - 1 ? 1u : 0u;
+  t.dy = c.y0 + 1 <= H - 1 ? (uint32_t)W : 0u;
+  t.dz = c.z0 + 1 <= D - 1 ? (uint32_t)(H * W) : 0u;
+  t.base = (uint32_t)((c.z0 * H + c.y0) * W + c.x0);
   return t;
+}
+__device__ __forceinline__ Trilin trilin_setup(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
+                                               int W, const float* hs, int ref_mode) {
+  return trilin_from_cell(trilin_cell(f0, f1, f2, lh, ld, lw, D, H, W, hs, ref_mode), D, H, W);
 }
 
 template <bool FMA>

@@ -132,6 +132,20 @@ def _warp_fwd(x, f):
     return out
 
 
+def warp3d_gather(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor:
+    """warp3d on the global-gather kernel only (ofsv_warp3d_gather_f32); `warp3d` itself picks the TMA slab kernel on cubic
+    volumes.  Bit-identical results; for tests and benchmarks."""
+    x, f = _cuda_f32(tenInput, "tenInput"), _cuda_f32(tenFlow, "tenFlow")
+    _check_warp_shapes(x, f, 3)
+    n, c, d, h, w = x.shape
+    dev = x.device
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().ofsv_warp3d_gather_f32(_p(x), _p(f), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
+                                                 _p(linspace_table(w, dev)), _p(out), n, c, d, h, w, _FLAVOR["mode"], _stream()))
+    return out
+
+
 def warp_bwd(tenInput, tenFlow, grad_out, need_input_grad=True, need_flow_grad=True):
     """Backward of `warp` (ofsv_warp{2,3}d_bwd_f32): (grad_input, grad_flow), either None when not asked for.
     = ATen grid_sampler backward (bilinear / border / align_corners, zero gradient where the coordinate was clipped)

@@ -23,7 +23,14 @@ for kind in ("smooth", "zero", "noise"):
         ops.warp3d(src, f)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"warp3d {n}x{s}^3 {kind:6s}: {ms*1e3:8.1f} us  {20.0 * n * s**3 / ms / 1e6:8.1f} GB/s (20 B/voxel)")
+    for _ in range(3):
+        ops.warp3d_gather(src, f)
+    e0.record()
+    for _ in range(20):
+        ops.warp3d_gather(src, f)
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / 20
+    print(f"warp3d {n}x{s}^3 {kind:6s}: {ms*1e3:8.1f} us  {20.0 * n * s**3 / ms / 1e6:8.1f} GB/s (20 B/voxel)   [global-gather kernel: {ms2*1e3:8.1f} us]")
     del f
 # reference point: plain copy moving the same number of bytes
 x = torch.empty(n * 5 * s**3 // 2, device="cuda"); y = torch.empty_like(x)

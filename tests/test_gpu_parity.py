@@ -742,3 +742,57 @@ def test_warp_backward_edges():
     # no grad requested -> plain forward, no autograd node
     x = torch.rand(1, 1, 8, 8, device=dev)
     assert not ops.warp2d(x, torch.zeros(1, 2, 8, 8, device=dev)).requires_grad
+
+
+# ------------------------------------------------------------------------------------------------- warp3d slab kernel
+@pytest.mark.parametrize("shape", [(1, 1, 32, 32, 32), (2, 2, 64, 64, 64), (1, 1, 96, 96, 96), (4, 1, 128, 128, 128)])
+@pytest.mark.parametrize("kind", ["smooth", "rand3", "rand8", "far", "zero", "edge", "shift6"])
+def test_warp3d_slab_equals_generic(shape, kind):
+    """The TMA slab kernel (cubic volumes) and the global-gather kernel share the coordinate / weight / summation code:
+    outputs must be bit-identical for every flow, including cells that leave the staged window (per-lane fallback)."""
+    from opticalflowscivis_b200 import ops
+    n, c, s = shape[0], shape[1], shape[2]
+    g = torch.Generator().manual_seed(21 + s)
+    src = torch.rand(shape, generator=g).to(_dev())
+    fs = (n, 3, s, s, s)
+    if kind == "smooth":
+        f = torch.nn.functional.interpolate(torch.randn((n, 3, s // 8, s // 8, s // 8), generator=g) * 2, size=(s, s, s), mode="trilinear")
+    elif kind == "rand3":
+        f = torch.randn(fs, generator=g) * 3
+    elif kind == "rand8":
+        f = torch.randn(fs, generator=g) * 8
+    elif kind == "far":
+        f = torch.randn(fs, generator=g) * 500
+    elif kind == "zero":
+        f = torch.zeros(fs)
+    elif kind == "edge":
+        f = torch.full(fs, float(s))
+    else:
+        f = torch.full(fs, 6.0) + torch.rand(fs, generator=g) * 0.5
+    f = f.contiguous().to(_dev())
+    a = ops.warp3d(src, f)
+    b = ops.warp3d_gather(src, f)
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
+def test_warp3d_slab_vs_c_oracle():
+    from opticalflowscivis_b200 import ops
+    from oracle import c_oracle as co
+    g = torch.Generator().manual_seed(8)
+    src = torch.rand((1, 2, 64, 64, 64), generator=g)
+    flow = torch.randn((1, 3, 64, 64, 64), generator=g) * 2.5
+    got = _np(ops.warp3d(src.to(_dev()), flow.to(_dev())))
+    ref = co.warp3d(src.numpy(), flow.numpy())
+    assert np.abs(got - ref).max() <= WARP_TOL
+
+
+def test_warp3d_slab_full_size_determinism():
+    """256^3 (BASELINE cfg 4 size): slab == gather bit for bit, and repeated launches are identical."""
+    from opticalflowscivis_b200 import ops
+    s = 256
+    g = torch.Generator(device="cuda").manual_seed(4)
+    src = torch.rand((1, 1, s, s, s), device=_dev(), generator=g)
+    f = torch.nn.functional.interpolate(torch.randn((1, 3, 32, 32, 32), device=_dev(), generator=g) * 2, size=(s, s, s), mode="trilinear").contiguous()
+    a = ops.warp3d(src, f)
+    assert torch.equal(a, ops.warp3d_gather(src, f))
+    assert torch.equal(a, ops.warp3d(src, f))
