@@ -57,7 +57,7 @@ __device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
 struct SlabParams {
   int N, C, S;        // cubic: D = H = W = S
   int ref_mode;
-  int dz;             // planes per task (even)
+  int nchunk;         // d chunks per tile column; chunk k covers planes [2*floor(k*(S/2)/nchunk), 2*floor((k+1)*(S/2)/nchunk))
   uint32_t ntasks;
   float hs[6];
 };
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
   const int pl = wid >> 3, q = wid & 7;                                   // plane of the pair, 4-voxel column group
   const int S = P.S;
   const int64_t V = (int64_t)S * S * S;
-  const int nt = S / 32, nchunk = S / P.dz;
+  const int nt = S / 32, nchunk = P.nchunk;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
     const int ck = r % nchunk;
     const int nc = r / nchunk;
     const int n = nc / P.C;
-    const int h0 = th * 32, w0 = tw * 32, d0 = ck * P.dz;
+    const int h0 = th * 32, w0 = tw * 32;
+    const int d0 = 2 * ((ck * (S / 2)) / nchunk), npair = ((ck + 1) * (S / 2)) / nchunk - d0 / 2;
     const int xorg = h0 - SL_XLO, zorg = w0 - SL_ZLO;
     const float* sp = src + (int64_t)nc * V;
     float* op = out + (int64_t)nc * V;
@@ -116,10 +117,13 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
 
     const int h = h0 + lane;
     const float lh = __ldg(lin_h + h);
-    for (int it = 0; it < P.dz / 2; ++it, ++g) {
+    const float4 LW = __ldg(reinterpret_cast<const float4*>(lin_w + w0 + q * 4));
+    for (int it = 0; it < npair; ++it, ++g) {
       const int dc = d0 + 2 * it;          // planes dc, dc + 1
+      const int d = dc + pl;
+      const float ld = __ldg(lin_d + d);   // issued before the barrier / stores / TMA wait so that its latency hides there
       __syncthreads();                     // pair it-1 fully computed: its results are in s_out, its oldest two slabs are dead
-      if (tid == 0 && it + 1 < P.dz / 2) load_pair(dc + 2, g + 1, dc + SL_MY + 3, dc + SL_MY + 4);
+      if (tid == 0 && it + 1 < npair) load_pair(dc + 2, g + 1, dc + SL_MY + 3, dc + SL_MY + 4);
       if (it > 0) {                        // coalesced stores of the previous pair
         const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
         const int p = tid >> 8, row = (tid >> 3) & 31, c = tid & 7;
@@ -128,11 +132,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
       }
       mbar_wait(&bars[g & 1], (g >> 1) & 1);
 
-      const int d = dc + pl;
-      const float ld = __ldg(lin_d + d);
       const uint32_t fa = s_flow + (g & 1) * SL_FSTAGE + pl * 3 * SL_FTILE + lane * 128 + ((q ^ (lane & 7)) << 4);
       const float4 F0 = lds_f32x4(fa), F1 = lds_f32x4(fa + SL_FTILE), F2 = lds_f32x4(fa + 2 * SL_FTILE);
-      const float4 LW = __ldg(reinterpret_cast<const float4*>(lin_w + w0 + q * 4));
       const float f0[4] = {F0.x, F0.y, F0.z, F0.w}, f1[4] = {F1.x, F1.y, F1.z, F1.w}, f2[4] = {F2.x, F2.y, F2.z, F2.w};
       const float lw[4] = {LW.x, LW.y, LW.z, LW.w};
       float res[4];
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
       const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
       const int p = tid >> 8, row = (tid >> 3) & 31, c = tid & 7;
       const float4 v = lds_f32x4(ob + p * SL_FTILE + row * 128 + ((c ^ (row & 7)) << 4));
-      stg_stream4(op + ((int64_t)(d0 + P.dz - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+      stg_stream4(op + ((int64_t)(d0 + 2 * npair - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
     }
   }
 }
@@ -217,14 +218,17 @@ int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, con
   const Warp3dParams wp = make_warp3d_params(N, C, D, H, W, ref_mode);
   for (int i = 0; i < 6; ++i) P.hs[i] = wp.hs[i];
   const int64_t tiles = (int64_t)N * C * (S / 32) * (S / 32);
-  int dz = 16;                                    // longer walks amortise the 13-slab prologue; keep >= 6 tasks per SM
-  for (int cand : {64, 32}) {
-    if (S % cand == 0 && tiles * (S / cand) >= 6 * 148) { dz = cand; break; }
+  // d chunks per tile column: every task pays a prologue (13 slabs before its first plane pair, ~6 plane times) and the last
+  // round of the persistent grid may be partly empty — minimise rounds x (planes per task + prologue)
+  int nchunk = 1;
+  double best = 1e30;
+  for (int k = 1; k <= S / 4; ++k) {
+    const int64_t rounds = cdiv(tiles * k, 148);
+    const double cost = (double)rounds * (2.0 * (double)cdiv(S / 2, k) + 6.0);
+    if (cost < best) { best = cost; nchunk = k; }
   }
-  if (S % dz != 0) dz = S % 16 == 0 ? 16 : 0;
-  if (dz == 0) return 0;
-  P.dz = dz;
-  const int64_t ntasks = tiles * (S / dz);
+  P.nchunk = nchunk;
+  const int64_t ntasks = tiles * nchunk;
   if (ntasks >= (1ll << 31)) return 0;
   P.ntasks = (uint32_t)ntasks;
   const int grid = (int)(ntasks < 148 ? ntasks : 148);
