@@ -18,6 +18,9 @@ struct TrilinCell {
   int x0, y0, z0;
   float ex, wx, ey, wy, ez, wz;
 };
+// MAGIC: floor through the 2^23 trick instead of FRND + F2I (identical results).  One instruction more per axis but none on
+// the quarter-rate conversion unit: 2 % faster in the latency-bound slab kernel, 4-5 % slower in the issue-bound kernels.
+template <bool MAGIC = false>
 __device__ __forceinline__ TrilinCell trilin_cell(float f0, float f1, float f2, float lh, float ld, float lw, int D, int H,
                                                   int W, const float* hs, int ref_mode) {
   const float g0 = __fadd_rn(lh, norm_flow(f0, hs[0], hs[3], ref_mode));  // sampled along the W axis
@@ -25,12 +28,23 @@ __device__ __forceinline__ TrilinCell trilin_cell(float f0, float f1, float f2, 
   const float g2 = __fadd_rn(lw, norm_flow(f2, hs[2], hs[5], ref_mode));  // along D
   const float ix = unnorm_clip_ac(g0, (float)(W - 1)), iy = unnorm_clip_ac(g1, (float)(H - 1)),
               iz = unnorm_clip_ac(g2, (float)(D - 1));
-  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  float fx, fy, fz;
+  int xi, yi, zi;
+  if (MAGIC) {
+  // floor of a clipped coordinate 0 <= v <= S-1 < 2^22 without the quarter-rate conversion unit (FRND + F2I per axis): adding
+  // 2^23 with round-down leaves 2^23 + floor(v) exactly (the ulp there is 1), whose low mantissa bits are the integer
+    const float tx = __fadd_rd(ix, 8388608.0f), ty = __fadd_rd(iy, 8388608.0f), tz = __fadd_rd(iz, 8388608.0f);
+    fx = __fsub_rn(tx, 8388608.0f); fy = __fsub_rn(ty, 8388608.0f); fz = __fsub_rn(tz, 8388608.0f);
+    xi = __float_as_int(tx) - 0x4B000000; yi = __float_as_int(ty) - 0x4B000000; zi = __float_as_int(tz) - 0x4B000000;
+  } else {
+    fx = floorf(ix); fy = floorf(iy); fz = floorf(iz);
+    xi = (int)fx; yi = (int)fy; zi = (int)fz;
+  }
   TrilinCell t;
   t.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix); t.wx = __fsub_rn(ix, fx);
   t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy); t.wy = __fsub_rn(iy, fy);
   t.ez = __fsub_rn(__fadd_rn(fz, 1.0f), iz); t.wz = __fsub_rn(iz, fz);
-  t.x0 = (int)fx; t.y0 = (int)fy; t.z0 = (int)fz;
+  t.x0 = xi; t.y0 = yi; t.z0 = zi;
   return t;
 }
 __device__ __forceinline__ Trilin trilin_from_cell(const TrilinCell& c, int D, int H, int W) {
