@@ -34,7 +34,7 @@ constexpr int SL_G = OFSV_SLAB_G;               // voxels of a thread whose coor
 constexpr int SL_ZLO = 5;                      // z window starts at w0-5
 // Tile width TW (voxels along w): 32 -> 512 threads, 197 KB, one CTA per SM; 16 -> 256 threads, 111 KB, TWO CTAs per SM whose
 // barrier / TMA waits overlap each other's arithmetic (the source window per output voxel grows from 2.06x to 2.44x).
-template <int TW>
+template <int TW, int VPT = 4>
 struct SlabCfg {
   // TMA pipeline depth PF (plane pairs in flight ahead of the one being computed) and y margin MY: a pair at planes (d, d+1)
   // reads slabs d-MY .. d+MY+2, the loads of pair +PF overwrite slots of slabs <= d+2PF+MY+2-16, so 2PF + 2MY < 14.  With one
@@ -48,7 +48,8 @@ struct SlabCfg {
   static constexpr int FTILE = SL_TH * TW * 4;               // bytes per (plane, channel)
   static constexpr int FSTAGE = 2 * 3 * FTILE;               // two planes x three channels
   static constexpr int OUT = 2 * FTILE;                      // two planes of results
-  static constexpr int QG = TW / 4;                          // 4-voxel column groups per plane
+  static constexpr int QG = TW / VPT;                        // column groups (warps) per plane, VPT voxels per thread
+  static constexpr int CPR = TW / 4;                         // 16 B chunks per tile row
   static constexpr int THREADS = 2 * QG * 32;
   static constexpr int ROWB = TW * 4;                        // bytes per tile row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr int SMEM = SL_NS * SLAB + NST * FSTAGE + 2 * OUT + 64 + 1024;   // + barriers + alignment slack
@@ -73,6 +74,14 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -82,15 +91,16 @@ struct SlabParams {
   int ref_mode;
   int nchunk;         // d chunks per tile column; chunk k covers planes [2*floor(k*(S/2)/nchunk), 2*floor((k+1)*(S/2)/nchunk))
   uint32_t ntasks;
+  int dbg_skip;       // OFSV_SLAB_DBG_SKIP=1 (probe): no arithmetic, out = flow channel 0 — the kernel's pure data-movement time
   float hs[6];
 };
 
-template <int TW, bool FMA>
-__global__ void __launch_bounds__(SlabCfg<TW>::THREADS, TW == 32 ? 1 : 2)
+template <int TW, int VPT, bool FMA>
+__global__ void __launch_bounds__(SlabCfg<TW, VPT>::THREADS, (TW == 32 || VPT == 2) ? 1 : 2)
     warp3d_slab_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_flow,
                        const float* __restrict__ src, const float* __restrict__ lin_h, const float* __restrict__ lin_d,
                        const float* __restrict__ lin_w, float* __restrict__ out, const SlabParams P) {
-  using K = SlabCfg<TW>;
+  using K = SlabCfg<TW, VPT>;
   constexpr int SL_NZ = K::NZ, SL_SLAB = K::SLAB, SL_FTILE = K::FTILE, SL_FSTAGE = K::FSTAGE, SL_OUT = K::OUT;
   constexpr int SL_MY = K::MY, PF = K::PF, NST = K::NST;
   extern __shared__ uint8_t sl_raw[];
@@ -145,7 +155,9 @@ __global__ void __launch_bounds__(SlabCfg<TW>::THREADS, TW == 32 ? 1 : 2)
 
     const int h = h0 + lane;
     const float lh = __ldg(lin_h + h);
-    const float4 LW = __ldg(reinterpret_cast<const float4*>(lin_w + w0 + q * 4));
+    float lw[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) lw[k] = __ldg(lin_w + w0 + q * VPT + k);
     for (int it = 0; it < npair; ++it, ++g) {
       const int dc = d0 + 2 * it;          // planes dc, dc + 1
       const int d = dc + pl;
@@ -154,19 +166,33 @@ __global__ void __launch_bounds__(SlabCfg<TW>::THREADS, TW == 32 ? 1 : 2)
       if (tid == 0 && it + PF < npair) load_pair(dc + 2 * PF, g + PF, dc + 2 * PF + SL_MY + 1, dc + 2 * PF + SL_MY + 2);
       if (it > 0) {                        // coalesced stores of the previous pair
         const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
-        const int p = tid / (K::THREADS / 2), row = (tid / K::QG) & 31, c = tid % K::QG;
-        const float4 v = lds_f32x4(ob + p * SL_FTILE + row * K::ROWB + ((c ^ K::swz(row)) << 4));
-        stg_stream4(op + ((int64_t)(dc - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+        const int p = tid / (K::THREADS / 2), tp = tid % (K::THREADS / 2), row = tp / K::CPR, c = tp % K::CPR;
+        if (tp < 32 * K::CPR) {
+          const float4 v = lds_f32x4(ob + p * SL_FTILE + row * K::ROWB + ((c ^ K::swz(row)) << 4));
+          stg_stream4(op + ((int64_t)(dc - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+        }
       }
       mbar_wait(&bars[g % NST], (g / NST) & 1);
 
-      const uint32_t fa = s_flow + (g % NST) * SL_FSTAGE + pl * 3 * SL_FTILE + lane * K::ROWB + ((q ^ K::swz(lane)) << 4);
-      const float4 F0 = lds_f32x4(fa), F1 = lds_f32x4(fa + SL_FTILE), F2 = lds_f32x4(fa + 2 * SL_FTILE);
-      const float f0[4] = {F0.x, F0.y, F0.z, F0.w}, f1[4] = {F1.x, F1.y, F1.z, F1.w}, f2[4] = {F2.x, F2.y, F2.z, F2.w};
-      const float lw[4] = {LW.x, LW.y, LW.z, LW.w};
-      float res[4];
+      // this thread's VPT consecutive w values of the three flow channels: 16 B chunk (q*VPT/4) ^ swz(row), VPT*4 B inside it
+      const uint32_t toff = lane * K::ROWB + ((((q * VPT) >> 2) ^ K::swz(lane)) << 4) + ((q * VPT) & 3) * 4;
+      const uint32_t fa = s_flow + (g % NST) * SL_FSTAGE + pl * 3 * SL_FTILE + toff;
+      float f0[VPT], f1[VPT], f2[VPT];
+      if (VPT == 4) {
+        const float4 F0 = lds_f32x4(fa), F1 = lds_f32x4(fa + SL_FTILE), F2 = lds_f32x4(fa + 2 * SL_FTILE);
+        f0[0] = F0.x; f0[1] = F0.y; f0[VPT - 2] = F0.z; f0[VPT - 1] = F0.w;
+        f1[0] = F1.x; f1[1] = F1.y; f1[VPT - 2] = F1.z; f1[VPT - 1] = F1.w;
+        f2[0] = F2.x; f2[1] = F2.y; f2[VPT - 2] = F2.z; f2[VPT - 1] = F2.w;
+      } else {
+        const float2 F0 = lds_f32x2(fa), F1 = lds_f32x2(fa + SL_FTILE), F2 = lds_f32x2(fa + 2 * SL_FTILE);
+        f0[0] = F0.x; f0[1] = F0.y; f1[0] = F1.x; f1[1] = F1.y; f2[0] = F2.x; f2[1] = F2.y;
+      }
+      float res[VPT];
 #pragma unroll
-      for (int half = 0; half < 4 / SL_G; ++half) {
+      for (int k = 0; k < VPT; ++k) res[k] = f0[k];
+      if (!P.dbg_skip)
+#pragma unroll
+      for (int half = 0; half < VPT / SL_G; ++half) {
         TrilinCell cell[SL_G];
         Taps8 tp[SL_G];
 #pragma unroll
@@ -198,24 +224,26 @@ __global__ void __launch_bounds__(SlabCfg<TW>::THREADS, TW == 32 ? 1 : 2)
           res[half * SL_G + j] = trilin_reduce<FMA>(tp[j], t);
         }
       }
-      sts_f32x4(s_out + (g & 1) * SL_OUT + pl * SL_FTILE + lane * K::ROWB + ((q ^ K::swz(lane)) << 4),
-                make_float4(res[0], res[1], res[2], res[3]));
+      if (VPT == 4) sts_f32x4(s_out + (g & 1) * SL_OUT + pl * SL_FTILE + toff, make_float4(res[0], res[1], res[VPT - 2], res[VPT - 1]));
+      else sts_f32x2(s_out + (g & 1) * SL_OUT + pl * SL_FTILE + toff, make_float2(res[0], res[1]));
     }
     __syncthreads();
     {                                      // last pair of the task
       const uint32_t ob = s_out + ((g - 1) & 1) * SL_OUT;
-      const int p = tid / (K::THREADS / 2), row = (tid / K::QG) & 31, c = tid % K::QG;
-      const float4 v = lds_f32x4(ob + p * SL_FTILE + row * K::ROWB + ((c ^ K::swz(row)) << 4));
-      stg_stream4(op + ((int64_t)(d0 + 2 * npair - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+      const int p = tid / (K::THREADS / 2), tp = tid % (K::THREADS / 2), row = tp / K::CPR, c = tp % K::CPR;
+      if (tp < 32 * K::CPR) {
+        const float4 v = lds_f32x4(ob + p * SL_FTILE + row * K::ROWB + ((c ^ K::swz(row)) << 4));
+        stg_stream4(op + ((int64_t)(d0 + 2 * npair - 2 + p) * S + (h0 + row)) * S + w0 + c * 4, v);
+      }
     }
   }
 }
 
 // returns 1 when the slab kernel was launched, 0 when the shape is not eligible (caller falls back), < 0 on error
-template <int TW>
+template <int TW, int VPT>
 static int warp3d_slab_launch(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
                               float* out, int N, int C, int S, int ref_mode, cudaStream_t st) {
-  using K = SlabCfg<TW>;
+  using K = SlabCfg<TW, VPT>;
   PFN_encodeTiled encode = get_tensor_map_encoder();
   if (!encode) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
   CUtensorMap tm_src, tm_flow;
@@ -241,10 +269,11 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
   }
   SlabParams P;
   P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode;
+  { const char* e = getenv("OFSV_SLAB_DBG_SKIP"); P.dbg_skip = e ? atoi(e) : 0; }
   const Warp3dParams wp = make_warp3d_params(N, C, S, S, S, ref_mode);
   for (int i = 0; i < 6; ++i) P.hs[i] = wp.hs[i];
   const int64_t tiles = (int64_t)N * C * (S / 32) * (S / TW);
-  const int slots = 148 * (TW == 32 ? 1 : 2);      // resident CTAs of the persistent grid
+  const int slots = 148 * ((TW == 32 || VPT == 2) ? 1 : 2);      // resident CTAs of the persistent grid
   // d chunks per tile column: every task pays a prologue (13 slabs before its first plane pair, ~6 plane times) and the last
   // round of the persistent grid may be partly empty — minimise rounds x (planes per task + prologue)
   int nchunk = 1;
@@ -261,15 +290,15 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
   const int grid = (int)(ntasks < slots ? ntasks : slots);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e1 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    cudaError_t e2 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, VPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("ofsv_warp3d_f32: cudaFuncSetAttribute failed"); return OFSV_ECUDA; }
     attr_done = true;
   }
   if (ref_mode == OFSV_REF_CUDA)
-    warp3d_slab_kernel<TW, true><<<grid, K::THREADS, K::SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
+    warp3d_slab_kernel<TW, VPT, true><<<grid, K::THREADS, K::SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
   else
-    warp3d_slab_kernel<TW, false><<<grid, K::THREADS, K::SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
+    warp3d_slab_kernel<TW, VPT, false><<<grid, K::THREADS, K::SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
   const int rc = check_launch("warp3d_slab_kernel");
   return rc == OFSV_OK ? 1 : rc;
 }
@@ -284,8 +313,9 @@ int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, con
   if ((int64_t)N * C > (1 << 20) || (int64_t)N * 3 > (1 << 20)) return 0;
   const char* e = getenv("OFSV_SLAB_TW");          // A/B switch for tests/bench_warp.py
   const int tw = e ? atoi(e) : OFSV_SLAB_TW;
-  if (tw == 32) return warp3d_slab_launch<32>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
-  return warp3d_slab_launch<16>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
+  if (tw == 32) return warp3d_slab_launch<32, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
+  if (tw == 322) return warp3d_slab_launch<32, 2>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);   // 1024 threads, 2 voxels each
+  return warp3d_slab_launch<16, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
 }
 
 }  // namespace ofsv

@@ -1,10 +1,13 @@
-"""Micro-benchmark of the standalone warp kernels (a1/a2): GB/s on algorithmic bytes.  usage: bench_warp.py [size=256] [n=1]"""
+"""Micro-benchmark of the standalone warp kernels (a1/a2): GB/s on algorithmic bytes.  usage: bench_warp.py [size=256] [n=1] [flavor=cpu|cuda]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opticalflowscivis_b200 import ops, synth
 s = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if len(sys.argv) > 3:
+    ops.set_reference_flavor(sys.argv[3])
+print('reference flavour:', ops.reference_flavor())
 a, _, b = synth.droplet3d_u8(n, s)
 src = torch.from_numpy(a).cuda().float() / 255
 g = torch.Generator().manual_seed(7)
