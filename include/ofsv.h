@@ -99,6 +99,17 @@ int ofsv_upsample_flow_ac_f32(const float* in, float* out, int B, int h_in, int 
 int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode,
                             void* stream);
 
+/* ---- backward of a10 / a11 (autograd of UPFlow's training step, BASELINE cfg 5, runs through both).
+ * ofsv_upsample_flow_ac_bwd_f32: gin (B,2,h_in,w_in) = upsample_bilinear2d_backward(gout (B,2,h_out,w_out)) with the
+ *   (w/w_, h/h_) factors of pwc_modules.py:83-88; gin is zero-filled by the call.
+ * ofsv_warping_no_div_bwd_f32: grid_sampler_2d_backward (zeros padding, align_corners=False) times the constant validity
+ *   mask, chained with the backward of `2*v/max(S-1,1) - 1` (pwc_modules.py:198-199).  gsrc (zero-filled by the call) and
+ *   gflow may each be NULL; src may be NULL when gflow is NULL. */
+int ofsv_upsample_flow_ac_bwd_f32(const float* gout, float* gin, int B, int h_in, int w_in, int h_out, int w_out, int if_rate,
+                                  void* stream);
+int ofsv_warping_no_div_bwd_f32(const float* src, const float* flow, const float* gout, float* gsrc, float* gflow, int B,
+                                int C, int H, int W, int ref_mode, void* stream);
+
 /* =====================================================================================================
  * IFBlock / IFNet engine (a3, a4, a5) — Flow-2D/model/IFNet.py:16-27,34-122,144-276 ; Flow-3D/model/IFNet.py.
  * Activations are channels-last: [N][D][H][W][Cs] with Cs the channel count rounded up to a multiple of 16

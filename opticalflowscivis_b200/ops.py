@@ -278,10 +278,7 @@ def corr81_bwd(f1, f2, gout):
     return g1, g2
 
 
-def upsample_flow_ac(flow, h, w, if_rate=True):
-    flow = _cuda_f32(flow, "inputs")
-    if flow.dim() != 4 or flow.shape[1] != 2:
-        raise ValueError("upsample_flow_ac: expected (B,2,h,w)")
+def _upsample_flow_ac_fwd(flow, h, w, if_rate):
     b, _, h_, w_ = flow.shape
     out = torch.empty(b, 2, h, w, device=flow.device, dtype=torch.float32)
     with torch.cuda.device(flow.device):
@@ -289,15 +286,79 @@ def upsample_flow_ac(flow, h, w, if_rate=True):
     return out
 
 
-def warping_no_div(x, flow):
-    x, flow = _cuda_f32(x, "x"), _cuda_f32(flow, "flow")
-    if x.dim() != 4 or flow.shape != (x.shape[0], 2, x.shape[2], x.shape[3]):
-        raise ValueError("warping_no_div: bad shapes")
+def upsample_flow_ac_bwd(grad_out, h_in, w_in, if_rate=True):
+    """Backward of upsample2d_flow_as (ofsv_upsample_flow_ac_bwd_f32): grad wrt the (B,2,h_in,w_in) input."""
+    go = _cuda_f32(grad_out, "grad_out")
+    if go.dim() != 4 or go.shape[1] != 2:
+        raise ValueError("upsample_flow_ac_bwd: expected (B,2,h,w)")
+    b, _, h, w = go.shape
+    gin = torch.empty(b, 2, h_in, w_in, device=go.device, dtype=torch.float32)     # zero-filled by the library
+    with torch.cuda.device(go.device):
+        _C.check(_C.lib().ofsv_upsample_flow_ac_bwd_f32(_p(go), _p(gin), b, h_in, w_in, h, w, int(if_rate), _stream()))
+    return gin
+
+
+class _UpsampleFlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, h, w, if_rate):
+        ctx.meta = (flow.shape[2], flow.shape[3], if_rate)
+        return _upsample_flow_ac_fwd(flow, h, w, if_rate)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h_, w_, if_rate = ctx.meta
+        return upsample_flow_ac_bwd(grad_out, h_, w_, if_rate), None, None, None
+
+
+def upsample_flow_ac(flow, h, w, if_rate=True):
+    flow = _cuda_f32(flow, "inputs")
+    if flow.dim() != 4 or flow.shape[1] != 2:
+        raise ValueError("upsample_flow_ac: expected (B,2,h,w)")
+    if torch.is_grad_enabled() and flow.requires_grad:
+        return _UpsampleFlowFn.apply(flow, h, w, if_rate)
+    return _upsample_flow_ac_fwd(flow, h, w, if_rate)
+
+
+def _warping_no_div_fwd(x, flow):
     b, c, h, w = x.shape
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         _C.check(_C.lib().ofsv_warping_no_div_f32(_p(x), _p(flow), _p(out), b, c, h, w, _FLAVOR["mode"], _stream()))
     return out
+
+
+def warping_no_div_bwd(x, flow, grad_out, need_input_grad=True, need_flow_grad=True):
+    """Backward of WarpingLayer_no_div (ofsv_warping_no_div_bwd_f32): (grad_x, grad_flow), either None when not asked for."""
+    x, flow, go = _cuda_f32(x, "x"), _cuda_f32(flow, "flow"), _cuda_f32(grad_out, "grad_out")
+    if x.dim() != 4 or flow.shape != (x.shape[0], 2, x.shape[2], x.shape[3]) or go.shape != x.shape:
+        raise ValueError("warping_no_div_bwd: bad shapes")
+    b, c, h, w = x.shape
+    gx = torch.empty_like(x) if need_input_grad else None          # zero-filled by the library
+    gf = torch.empty_like(flow) if need_flow_grad else None
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().ofsv_warping_no_div_bwd_f32(_p(x), _p(flow), _p(go), _p(gx), _p(gf), b, c, h, w, _FLAVOR["mode"], _stream()))
+    return gx, gf
+
+
+class _WarpingNoDivFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow):
+        ctx.save_for_backward(x, flow)
+        return _warping_no_div_fwd(x, flow)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, flow = ctx.saved_tensors
+        return warping_no_div_bwd(x, flow, grad_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+def warping_no_div(x, flow):
+    x, flow = _cuda_f32(x, "x"), _cuda_f32(flow, "flow")
+    if x.dim() != 4 or flow.shape != (x.shape[0], 2, x.shape[2], x.shape[3]):
+        raise ValueError("warping_no_div: bad shapes")
+    if torch.is_grad_enabled() and (x.requires_grad or flow.requires_grad):
+        return _WarpingNoDivFn.apply(x, flow)
+    return _warping_no_div_fwd(x, flow)
 
 
 # ------------------------------------------------------------------------------------------------ IFNet engine pieces

@@ -796,3 +796,62 @@ def test_warp3d_slab_full_size_determinism():
     a = ops.warp3d(src, f)
     assert torch.equal(a, ops.warp3d_gather(src, f))
     assert torch.equal(a, ops.warp3d(src, f))
+
+
+# ------------------------------------------------------------------------------------------------- a10 / a11 backward
+def test_upflow_backward_golden_fixtures():
+    """ofsv_upsample_flow_ac_bwd_f32 / ofsv_warping_no_div_bwd_f32 through autograd of the drop-in modules vs autograd
+    through the reference's pwc_modules (tests/golden/upflow_bwd.npz)."""
+    from opticalflowscivis_b200.upflow import WarpingLayer_no_div, upsample2d_flow_as
+    z = np.load(os.path.join(G, "upflow_bwd.npz"))
+    wl = WarpingLayer_no_div()
+    for i in range(4):
+        fl, go = (torch.from_numpy(z[f"ups{i}_{s}"]).to(_dev()) for s in ("in", "gout"))
+        a = fl.clone().requires_grad_()
+        upsample2d_flow_as(a, torch.empty(go.shape[0], 1, go.shape[2], go.shape[3], device=_dev()), mode="bilinear", if_rate=True).backward(go)
+        _bwd_close(a.grad, z[f"ups{i}_gin"], f"ups{i} gin")
+        x, f, go = (torch.from_numpy(z[f"wnd{i}_{s}"]).to(_dev()) for s in ("x", "flow", "gout"))
+        a, b = x.clone().requires_grad_(), f.clone().requires_grad_()
+        wl(a, b).backward(go)
+        _bwd_close(a.grad, z[f"wnd{i}_gx"], f"wnd{i} gsrc")
+        _bwd_close(b.grad, z[f"wnd{i}_gflow"], f"wnd{i} gflow")
+
+
+@pytest.mark.parametrize("chw", [(196, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104), (32, 64, 208)])
+def test_warping_no_div_backward_pyramid_shapes(chw):
+    """The five pyramid levels of a 256x832 KITTI crop (SURVEY a8 shapes), B = 2, against autograd through the oracle."""
+    from opticalflowscivis_b200 import ops
+    from oracle import ops_ref
+    c, h, w = chw
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(2, c, h, w, generator=g)
+    fl = torch.randn(2, 2, h, w, generator=g) * 2.5
+    go = torch.randn(2, c, h, w, generator=g)
+    a, b = x.clone().requires_grad_(), fl.clone().requires_grad_()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ops_ref.warping_layer_no_div_ref(a, b).backward(go)
+    gx, gf = ops.warping_no_div_bwd(x.to(_dev()), fl.to(_dev()), go.to(_dev()))
+    _bwd_close(gx, a.grad.numpy(), "gsrc")
+    _bwd_close(gf, b.grad.numpy(), "gflow")
+    gx2, none = ops.warping_no_div_bwd(x.to(_dev()), fl.to(_dev()), go.to(_dev()), True, False)
+    assert none is None
+    _bwd_close(gx2, a.grad.numpy(), "gsrc only")
+
+
+def test_upsample_flow_backward_full_chain():
+    """(64,208) -> (256,832), the final up-sampling of the reference's forward (upflow.py:608-609), B = 8; plus the linearity
+    property sum(gin) == sum(gout * scale) (bilinear weights of an output pixel sum to 1)."""
+    from opticalflowscivis_b200 import ops
+    from oracle import ops_ref
+    g = torch.Generator().manual_seed(12)
+    fl = torch.randn(8, 2, 64, 208, generator=g)
+    go = torch.randn(8, 2, 256, 832, generator=g)
+    a = fl.clone().requires_grad_()
+    ops_ref.upsample2d_flow_as_ref(a, 256, 832).backward(go)
+    gin = ops.upsample_flow_ac_bwd(go.to(_dev()), 64, 208, True)
+    _bwd_close(gin, a.grad.numpy(), "gin")
+    want = float((go.double()[:, 0] * (832 / 208)).sum() + (go.double()[:, 1] * (256 / 64)).sum())
+    assert abs(float(gin.double().sum()) - want) <= 1e-6 * float(go.double().abs().sum()) * 4
+    # empty batch
+    assert ops.upsample_flow_ac_bwd(torch.empty(0, 2, 8, 8, device=_dev()), 4, 4).shape == (0, 2, 4, 4)

@@ -135,3 +135,21 @@ def test_warp_backward_golden():
             assert (gflow == 0).mean() > (0.9 if "edge" in name else 0.5), name
         n += 1
     assert n == 16
+
+
+def test_upflow_backward_golden():
+    """Backward of a10 / a11: autograd through the oracle restatements replays the vectors taken from autograd through the
+    reference's pwc_modules (tests/golden/make_upflow_bwd_golden.py)."""
+    z = np.load(os.path.join(G, "upflow_bwd.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(4):
+            fl, go, gin = (torch.from_numpy(z[f"ups{i}_{s}"]) for s in ("in", "gout", "gin"))
+            a = fl.clone().requires_grad_()
+            ops_ref.upsample2d_flow_as_ref(a, go.shape[2], go.shape[3]).backward(go)
+            assert (a.grad - gin).abs().max() <= 1e-5 * max(1.0, float(gin.abs().max()))
+            x, f, go, gx, gf = (torch.from_numpy(z[f"wnd{i}_{s}"]) for s in ("x", "flow", "gout", "gx", "gflow"))
+            a, b = x.clone().requires_grad_(), f.clone().requires_grad_()
+            ops_ref.warping_layer_no_div_ref(a, b).backward(go)
+            assert (a.grad - gx).abs().max() <= 1e-5 * max(1.0, float(gx.abs().max()))
+            assert (b.grad - gf).abs().max() <= 1e-5 * max(1.0, float(gf.abs().max()))
