@@ -45,7 +45,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     warping_no_div_bwd_kernel(const float* __restrict__ src, const float* __restrict__ flow, const float* __restrict__ gout,
                               float* __restrict__ gsrc, float* __restrict__ gflow, int B, int C, int H, int W, float dw, float dh,
-                              float rdw, float rdh, int ref_mode) {
+                              float rdw, float rdh, int ref_mode, int c_per) {
+  // blockIdx.y = channel chunk (see warping_no_div_kernel); with more than one chunk the flow gradient is accumulated into the
+  // zero-filled gflow with red.add
+  const int c_begin = blockIdx.y * c_per, c_end = min(C, c_begin + c_per);
+  const bool split = gridDim.y > 1;
   const int64_t HW = (int64_t)H * W, total = (int64_t)B * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(256)
     const bool valid = msum >= 1.0f;          // the mask is a constant of the graph ((mask >= 1).float())
     float gix = 0.0f, giy = 0.0f;
     if (valid) {
-      for (int c = 0; c < C; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int64_t pl = ((int64_t)b * C + c) * HW;
         const float g = ldg_stream(gout + pl + r);
         if (gsrc) {
@@ -99,8 +103,12 @@ __global__ void __launch_bounds__(256)
       float fx = gix * (0.5f * (float)W), fy = giy * (0.5f * (float)H);
       fx = ref_mode == OFSV_REF_CUDA ? fx * rdw : __fdiv_rn(fx, dw);
       fy = ref_mode == OFSV_REF_CUDA ? fy * rdh : __fdiv_rn(fy, dh);
-      gflow[((int64_t)b * 2 + 0) * HW + r] = 2.0f * fx;
-      gflow[((int64_t)b * 2 + 1) * HW + r] = 2.0f * fy;
+      if (split) {
+        if (valid) { red_add_f32(gflow + ((int64_t)b * 2 + 0) * HW + r, 2.0f * fx); red_add_f32(gflow + ((int64_t)b * 2 + 1) * HW + r, 2.0f * fy); }
+      } else {
+        gflow[((int64_t)b * 2 + 0) * HW + r] = 2.0f * fx;
+        gflow[((int64_t)b * 2 + 1) * HW + r] = 2.0f * fy;
+      }
     }
   }
 }
@@ -145,7 +153,16 @@ extern "C" int ofsv_warping_no_div_bwd_f32(const float* src, const float* flow, 
     if (e != cudaSuccess) { set_error("ofsv_warping_no_div_bwd_f32: memset: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
   }
   const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
-  warping_no_div_bwd_kernel<<<grid_1d_bwd((int64_t)B * H * W), 256, 0, st>>>(
-      src, flow, gout, gsrc, gflow, B, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode);
+  const int gx = grid_1d_bwd((int64_t)B * H * W);
+  int nsplit = (int)(cdiv(148 * 8, gx));
+  nsplit = nsplit < 1 ? 1 : (nsplit > cdiv(C, 4) ? (int)cdiv(C, 4) : nsplit);
+  const int c_per = (int)cdiv(C, nsplit);
+  const unsigned gy = (unsigned)cdiv(C, c_per);
+  if (gflow && gy > 1) {
+    cudaError_t e = cudaMemsetAsync(gflow, 0, sizeof(float) * (size_t)B * 2 * H * W, st);
+    if (e != cudaSuccess) { set_error("ofsv_warping_no_div_bwd_f32: memset: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
+  }
+  warping_no_div_bwd_kernel<<<dim3((unsigned)gx, gy), 256, 0, st>>>(
+      src, flow, gout, gsrc, gflow, B, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode, c_per);
   return check_launch("warping_no_div_bwd_kernel");
 }
