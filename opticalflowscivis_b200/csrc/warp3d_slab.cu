@@ -283,6 +283,7 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
     const double cost = (double)rounds * (2.0 * (double)cdiv(S / 2, k) + 6.0);
     if (cost < best) { best = cost; nchunk = k; }
   }
+  { const char* e = getenv("OFSV_SLAB_NCHUNK"); if (e && atoi(e) >= 1 && atoi(e) <= S / 4) nchunk = atoi(e); }   // calibration of the cost model
   P.nchunk = nchunk;
   const int64_t ntasks = tiles * nchunk;
   if (ntasks >= (1ll << 31)) return 0;

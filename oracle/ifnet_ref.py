@@ -69,10 +69,11 @@ class IFNetRef(nn.Module):
         self.block1 = IFBlockRef(nd, 5 + fl, c1)
         self.block2 = IFBlockRef(nd, 5 + fl, c2)
         self.block_tea = IFBlockRef(nd, 6 + fl, 64)    # training only; kept for state_dict parity
+        self.warp_fn = None                            # tests may inject another `warp(tenInput, tenFlow)` (e.g. the CUDA drop-in)
 
     def forward(self, x, scale=(4, 2, 1), timestep=0.5):   # timestep is ignored by the reference (fact 5)
         nd = self.nd
-        warp = warp2d_ref if nd == 2 else warp3d_ref
+        warp = self.warp_fn or (warp2d_ref if nd == 2 else warp3d_ref)
         img0, img1 = x[:, :1], x[:, 1:2]
         flow_list, mask_list, merged = [], [], []
         w0, w1, flow, mask = img0, img1, None, None

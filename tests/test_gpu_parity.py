@@ -855,3 +855,53 @@ def test_upsample_flow_backward_full_chain():
     assert abs(float(gin.double().sum()) - want) <= 1e-6 * float(go.double().abs().sum()) * 4
     # empty batch
     assert ops.upsample_flow_ac_bwd(torch.empty(0, 2, 8, 8, device=_dev()), 4, 4).shape == (0, 2, 4, 4)
+
+
+@pytest.mark.parametrize("nd,shape", [(2, (2, 1, 64, 96)), (3, (1, 1, 32, 32, 48))])
+def test_differentiable_warp_inside_reference_ifnet(nd, shape):
+    """Row f.1 in context: the reference-structured IFNet (oracle restatement, CUDA eager convs) trained through OUR
+    differentiable warp() must produce the same loss and the same parameter gradients as through torch's grid_sample — the
+    situation of a maintainer who only swaps model/warplayer.py and keeps training (Model.update)."""
+    import opticalflowscivis_b200 as o
+    from opticalflowscivis_b200.flow2d.model.warplayer import warp as warp2
+    from opticalflowscivis_b200.flow3d.model.warplayer import warp as warp3
+    from oracle.ifnet_ref import IFNetRef
+    o.set_reference_flavor("cuda")              # the comparison partner is the reference in CUDA eager
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False     # fp32 convolutions on both sides: TF32 rounding would amplify the 1-ulp
+    torch.manual_seed(1234)                     # differences of the two warp backward sums through the network
+    net = IFNetRef(nd).to(_dev())
+    g = torch.Generator().manual_seed(5)
+    img0 = torch.rand(shape, generator=g)
+    img1 = (torch.roll(img0, shifts=2, dims=-1) * 0.9 + 0.05)
+    gt = (0.5 * (img0 + img1)).to(_dev())
+    x = torch.cat((img0, img1), 1).to(_dev())
+
+    def run(warp_fn):
+        net.warp_fn = warp_fn
+        net.zero_grad(set_to_none=True)
+        flow, mask, merged = net(x, (4, 2, 1))
+        loss = sum(((m - gt) ** 2).mean() for m in merged) + 1e-3 * sum(f.abs().mean() for f in flow)
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+        return float(loss), grads
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loss_ref, g_ref = run(None)
+        _, g_ref2 = run(None)                    # run-to-run noise floor of the CUDA-eager side (cuDNN wgrad / scatter atomics)
+        loss_ours, g_ours = run(warp2 if nd == 2 else warp3)
+    torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(loss_ref - loss_ours) <= 1e-6 * max(1.0, abs(loss_ref)), (loss_ref, loss_ours)
+    assert g_ref.keys() == g_ours.keys() and len(g_ref) >= 80
+    worst = floor = 0.0
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max())
+        if scale == 0.0:
+            assert float(g_ours[k].abs().max()) == 0.0, k
+            continue
+        worst = max(worst, float((g_ref[k] - g_ours[k]).abs().max()) / scale)
+        floor = max(floor, float((g_ref[k] - g_ref2[k]).abs().max()) / scale)
+    print(f"IFNet{nd}D parameter gradients through ofsv warp vs grid_sample: worst relative difference {worst:.2e} "
+          f"(reference run-to-run: {floor:.2e})")
+    assert worst <= max(2e-3, 5 * floor), (worst, floor)
