@@ -905,3 +905,36 @@ def test_differentiable_warp_inside_reference_ifnet(nd, shape):
     print(f"IFNet{nd}D parameter gradients through ofsv warp vs grid_sample: worst relative difference {worst:.2e} "
           f"(reference run-to-run: {floor:.2e})")
     assert worst <= max(2e-3, 5 * floor), (worst, floor)
+
+
+@pytest.mark.parametrize("nd,shape", [(2, (2, 1, 160, 224)), (3, (1, 1, 64, 64, 64))])
+def test_model_inference_cuda_graph_mode(nd, shape):
+    """Model.enable_cuda_graphs(): replayed inference is bit-identical to the eager call, follows new inputs, is re-captured
+    after a parameter update, and keeps the no-CPU-path error behaviour."""
+    from opticalflowscivis_b200.rife import Model2D, Model3D
+    torch.manual_seed(1234)
+    model = (Model2D if nd == 2 else Model3D)(local_rank=0)
+    model.eval()
+    g = torch.Generator().manual_seed(3)
+    pick = (lambda r: r[0][2]) if nd == 2 else (lambda r: r[0])
+
+    def pair():
+        a = torch.rand(shape, generator=g)
+        return a.to(_dev()), (torch.roll(a, 2, -1) * 0.9 + 0.05).to(_dev())
+
+    (a0, b0), (a1, b1) = pair(), pair()
+    e0 = [t.clone() for t in (pick(model.inference(a0, b0)), model.inference(a0, b0)[1][2])]
+    e1 = pick(model.inference(a1, b1)).clone()
+    model.enable_cuda_graphs()
+    r0 = model.inference(a0, b0)
+    assert torch.equal(pick(r0), e0[0]) and torch.equal(r0[1][2], e0[1])
+    assert torch.equal(pick(model.inference(a1, b1)), e1)           # same graph, new inputs
+    assert torch.equal(pick(model.inference(a0, b0)), e0[0])
+    with pytest.raises(TypeError):
+        model.inference(a0.cpu(), b0)
+    with torch.no_grad():                                           # parameter update -> graphs dropped, weights re-packed
+        model.flownet.block2.conv0[0][0].weight.mul_(1.5)
+    r2 = pick(model.inference(a0, b0)).clone()
+    model.enable_cuda_graphs(False)
+    assert torch.equal(r2, pick(model.inference(a0, b0)))
+    assert not torch.equal(r2, e0[0])
