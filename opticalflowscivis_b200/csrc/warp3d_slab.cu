@@ -91,7 +91,8 @@ struct SlabParams {
   int ref_mode;
   int nchunk;         // d chunks per tile column; chunk k covers planes [2*floor(k*(S/2)/nchunk), 2*floor((k+1)*(S/2)/nchunk))
   uint32_t ntasks;
-  int dbg_skip;       // OFSV_SLAB_DBG_SKIP=1 (probe): no arithmetic, out = flow channel 0 — the kernel's pure data-movement time
+  int dbg_skip;       // probe builds only (-DOFSV_SLAB_PROBE + OFSV_SLAB_DBG_SKIP=1): no arithmetic, out = flow channel 0 — the
+                      // kernel's pure data-movement time (212-222 us for 4 x 256^3); always 0 in the shipped library
   float hs[6];
 };
 
@@ -190,7 +191,9 @@ __global__ void __launch_bounds__(SlabCfg<TW, VPT>::THREADS, (TW == 32 || VPT ==
       float res[VPT];
 #pragma unroll
       for (int k = 0; k < VPT; ++k) res[k] = f0[k];
+#ifdef OFSV_SLAB_PROBE
       if (!P.dbg_skip)
+#endif
 #pragma unroll
       for (int half = 0; half < VPT / SL_G; ++half) {
         TrilinCell cell[SL_G];
@@ -269,7 +272,10 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
   }
   SlabParams P;
   P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode;
+  P.dbg_skip = 0;
+#ifdef OFSV_SLAB_PROBE
   { const char* e = getenv("OFSV_SLAB_DBG_SKIP"); P.dbg_skip = e ? atoi(e) : 0; }
+#endif
   const Warp3dParams wp = make_warp3d_params(N, C, S, S, S, ref_mode);
   for (int i = 0; i < 6; ++i) P.hs[i] = wp.hs[i];
   const int64_t tiles = (int64_t)N * C * (S / 32) * (S / TW);
