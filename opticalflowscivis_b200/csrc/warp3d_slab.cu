@@ -91,6 +91,7 @@ struct SlabParams {
   int ref_mode;
   int nchunk;         // d chunks per tile column; chunk k covers planes [2*floor(k*(S/2)/nchunk), 2*floor((k+1)*(S/2)/nchunk))
   uint32_t ntasks;
+  int flow_nc, flow_c0;   // the flow tensor has flow_nc channels per sample, this warp uses channels flow_c0 .. flow_c0+2
   int dbg_skip;       // probe builds only (-DOFSV_SLAB_PROBE + OFSV_SLAB_DBG_SKIP=1): no arithmetic, out = flow channel 0 — the
                       // kernel's pure data-movement time (212-222 us for 4 x 256^3); always 0 in the shipped library
   float hs[6];
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(SlabCfg<TW, VPT>::THREADS, (TW == 32 || VPT ==
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tma_load_4d(&tm_flow, bar, fs + (p * 3 + c) * SL_FTILE, w0, h0, d + p, n * 3 + c);
+        for (int c = 0; c < 3; ++c) tma_load_4d(&tm_flow, bar, fs + (p * 3 + c) * SL_FTILE, w0, h0, d + p, n * P.flow_nc + P.flow_c0 + c);
       for (int y = y_first; y <= y_last; ++y) tma_load_4d(&tm_src, bar, s_slab + (uint32_t)(y & (SL_NS - 1)) * SL_SLAB, xorg, y, zorg, nc);
     };
 
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(SlabCfg<TW, VPT>::THREADS, (TW == 32 || VPT ==
 // returns 1 when the slab kernel was launched, 0 when the shape is not eligible (caller falls back), < 0 on error
 template <int TW, int VPT>
 static int warp3d_slab_launch(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w,
-                              float* out, int N, int C, int S, int ref_mode, cudaStream_t st) {
+                              float* out, int N, int C, int S, int ref_mode, int flow_nc, int flow_c0, cudaStream_t st) {
   using K = SlabCfg<TW, VPT>;
   PFN_encodeTiled encode = get_tensor_map_encoder();
   if (!encode) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
@@ -261,7 +262,7 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
     if (r != CUDA_SUCCESS) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled(src) failed (%d)", (int)r); return OFSV_ECUDA; }
   }
   {
-    const cuuint64_t gdim[4] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)N * 3};
+    const cuuint64_t gdim[4] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)N * flow_nc};
     const cuuint64_t gstr[3] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4, (cuuint64_t)S * S * S * 4};
     const cuuint32_t box[4] = {(cuuint32_t)TW, SL_TH, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -271,7 +272,7 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
     if (r != CUDA_SUCCESS) { set_error("ofsv_warp3d_f32: cuTensorMapEncodeTiled(flow) failed (%d)", (int)r); return OFSV_ECUDA; }
   }
   SlabParams P;
-  P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode;
+  P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode; P.flow_nc = flow_nc; P.flow_c0 = flow_c0;
   P.dbg_skip = 0;
 #ifdef OFSV_SLAB_PROBE
   { const char* e = getenv("OFSV_SLAB_DBG_SKIP"); P.dbg_skip = e ? atoi(e) : 0; }
@@ -314,15 +315,15 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
 #define OFSV_SLAB_TW 16
 #endif
 int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w, float* out,
-                    int N, int C, int D, int H, int W, int ref_mode, cudaStream_t st) {
+                    int N, int C, int D, int H, int W, int ref_mode, cudaStream_t st, int flow_nc, int flow_c0) {
   if (!(D == H && H == W && W % 32 == 0 && W >= 32 && W <= 1024)) return 0;
   if (!aligned16(src) || !aligned16(flow) || !aligned16(out) || !aligned16(lin_w)) return 0;
-  if ((int64_t)N * C > (1 << 20) || (int64_t)N * 3 > (1 << 20)) return 0;
+  if ((int64_t)N * C > (1 << 20) || (int64_t)N * flow_nc > (1 << 20)) return 0;
   const char* e = getenv("OFSV_SLAB_TW");          // A/B switch for tests/bench_warp.py
   const int tw = e ? atoi(e) : OFSV_SLAB_TW;
-  if (tw == 32) return warp3d_slab_launch<32, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
-  if (tw == 322) return warp3d_slab_launch<32, 2>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);   // 1024 threads, 2 voxels each
-  return warp3d_slab_launch<16, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, st);
+  if (tw == 32) return warp3d_slab_launch<32, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);
+  if (tw == 322) return warp3d_slab_launch<32, 2>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);   // 1024 threads, 2 voxels each
+  return warp3d_slab_launch<16, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);
 }
 
 }  // namespace ofsv

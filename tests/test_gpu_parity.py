@@ -938,3 +938,25 @@ def test_model_inference_cuda_graph_mode(nd, shape):
     model.enable_cuda_graphs(False)
     assert torch.equal(r2, pick(model.inference(a0, b0)))
     assert not torch.equal(r2, e0[0])
+
+
+@pytest.mark.parametrize("n,s", [(1, 32), (2, 64), (1, 96)])
+def test_warp_blend_3d_cubic_equals_unfused_chain(n, s):
+    """On cubic volumes ofsv_warp_blend_3d_f32 runs two slab warps (flow channels 0-2 / 3-5 of the 6-channel tensor) + a
+    blend pass: must equal warp3d_gather + sigmoid/blend of the individually verified kernels bit for bit, with and without
+    the optional outputs."""
+    from opticalflowscivis_b200 import ops
+    g = torch.Generator().manual_seed(31 + s)
+    img0, img1 = torch.rand((n, 1, s, s, s), generator=g).to(_dev()), torch.rand((n, 1, s, s, s), generator=g).to(_dev())
+    flow = (torch.randn((n, 6, s, s, s), generator=g) * 3).to(_dev())
+    m = torch.randn((n, 1, s, s, s), generator=g).to(_dev())
+    w0, w1, mg, ms = ops.warp_blend(img0, img1, flow, m)
+    r0 = ops.warp3d_gather(img0, flow[:, :3].contiguous())
+    r1 = ops.warp3d_gather(img1, flow[:, 3:].contiguous())
+    assert torch.equal(w0, r0) and torch.equal(w1, r1)
+    assert torch.equal(mg, ops.blend(r0, r1, m))
+    assert float((ms - torch.sigmoid(m)).abs().max()) <= 1e-6
+    none0, none1, mg2, none2 = ops.warp_blend(img0, img1, flow, m, want_warped=False, want_mask=False)
+    assert none0 is None and none1 is None and none2 is None and torch.equal(mg2, mg)
+    w0b, w1b, none3, none4 = ops.warp_blend(img0, img1, flow, None, want_merged=False, want_mask=False)
+    assert none3 is None and none4 is None and torch.equal(w0b, r0) and torch.equal(w1b, r1)
