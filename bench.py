@@ -295,9 +295,10 @@ def run_ours(args, rank, world, local_rank):
     # HBM roofline of the standalone warp kernel: (nd flow + 1 src + 1 out) * 4 B = 20 B/voxel in 3-D, 16 B/px in 2-D
     warp_bytes = (nd + 2) * 4 * vox * pairs
     warp_gbs = warp_bytes / (warp_ms / 1e3) / 1e9
-    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/r01p_ncu_full_warp3d_slab_256.csv:
-    # dram__bytes_read 268.5 MB + write 52.3 MB per 256^3 volume), scaled to this launch's volume count
-    warp_traffic = (268.5e6 + 52.3e6) * pairs if (nd == 3 and tuple(sp) == (256, 256, 256)) else None
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/r01q_ncu_full_warp3d_slab_4x256.csv:
+    # dram__bytes_read 1118.0 MB + write 254.1 MB for a 4 x 256^3 launch = 279.5 + 63.5 MB per volume; algorithmic 335.5 MB),
+    # scaled to this launch's volume count
+    warp_traffic = (279.5e6 + 63.5e6) * pairs if (nd == 3 and tuple(sp) == (256, 256, 256)) else None
     slab = nd == 3 and sp[0] == sp[1] == sp[2] and sp[0] % 32 == 0      # ofsv_warp3d_f32 picks the TMA slab kernel on such volumes
     roofline_warp = {"kernel": "warp3d_slab_kernel" if slab else "warp%dd_kernel" % nd, "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": warp_gbs / peaks["hbm_gbs"], "traffic": warp_traffic, "peak_source": peaks["src"],
