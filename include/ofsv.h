@@ -110,6 +110,16 @@ int ofsv_upsample_flow_ac_bwd_f32(const float* gout, float* gin, int B, int h_in
 int ofsv_warping_no_div_bwd_f32(const float* src, const float* flow, const float* gout, float* gsrc, float* gflow, int B,
                                 int C, int H, int W, int ref_mode, void* stream);
 
+/* ---- training tier: the optimizer step of Model.update — torch.optim.AdamW(lr=1e-6, weight_decay=1e-3),
+ * Flow-2D/model/RIFE.py:26,317 ; Flow-3D/model/RIFE.py:29,259 — for EVERY parameter tensor in one launch.
+ * `tensors`: device array of ntensors records {float* p; const float* g; float* m; float* v; int64_t n} (40 bytes each);
+ * `chunks`: device array of nchunks (tensor index, chunk index) int32 pairs covering every tensor in 4096-element chunks.
+ * step >= 1 is the step count AFTER this update (bias corrections 1 - beta^step); grad_scale multiplies the gradients
+ * (1/world after a SUM allreduce). */
+#define OFSV_ADAMW_CHUNK 4096
+int ofsv_adamw_step_f32(const void* tensors, const void* chunks, int ntensors, int nchunks, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* =====================================================================================================
  * IFBlock / IFNet engine (a3, a4, a5) — Flow-2D/model/IFNet.py:16-27,34-122,144-276 ; Flow-3D/model/IFNet.py.
  * Activations are channels-last: [N][D][H][W][Cs] with Cs the channel count rounded up to a multiple of 16

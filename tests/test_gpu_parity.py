@@ -960,3 +960,49 @@ def test_warp_blend_3d_cubic_equals_unfused_chain(n, s):
     assert none0 is None and none1 is None and none2 is None and torch.equal(mg2, mg)
     w0b, w1b, none3, none4 = ops.warp_blend(img0, img1, flow, None, want_merged=False, want_mask=False)
     assert none3 is None and none4 is None and torch.equal(w0b, r0) and torch.equal(w1b, r1)
+
+
+# ------------------------------------------------------------------------------------------------- fused AdamW (f.1)
+def test_fused_adamw_golden_and_torch():
+    """ofsv_adamw_step_f32 (one launch for all tensors) vs the golden vectors of torch.optim.AdamW as the reference drives it
+    (lr set every step, weight_decay 1e-3), and vs torch.optim.AdamW on the GPU for the IFNet parameter set."""
+    from opticalflowscivis_b200.optim import FusedAdamW, GradientBucket
+    z = np.load(os.path.join(G, "adamw.npz"))
+    params = [torch.nn.Parameter(torch.from_numpy(z[f"p0_{i}"]).to(_dev())) for i in range(5)]
+    opt = FusedAdamW(params, lr=1e-6, weight_decay=1e-3)
+    for t, lr in enumerate(z["lrs"], start=1):
+        for pg in opt.param_groups:                          # Flow-3D/model/RIFE.py:86-87
+            pg["lr"] = float(lr)
+        for i, p in enumerate(params):
+            p.grad = torch.from_numpy(z[f"g{t}_{i}"]).to(_dev())
+        opt.step()
+        for i, p in enumerate(params):
+            ref = z[f"p{t}_{i}"]
+            assert np.abs(_np(p) - ref).max() <= 1e-6 * max(1e-30, np.abs(ref).max()), (t, i)
+    # the whole 3-D IFNet parameter set (36 MB), gradients living in one flat bucket, 3 steps, against torch's own optimizer
+    from oracle.ifnet_ref import IFNetRef
+    torch.manual_seed(1234)
+    a, b = IFNetRef(3).to(_dev()), IFNetRef(3).to(_dev())
+    b.load_state_dict(a.state_dict())
+    ref_opt = torch.optim.AdamW(a.parameters(), lr=1e-6, weight_decay=1e-3)
+    bucket = GradientBucket(b.parameters())
+    mine = FusedAdamW(b.parameters(), lr=1e-6, weight_decay=1e-3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n0 = None
+    for t in range(3):
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            gr = torch.randn(pa.shape, device=_dev(), generator=g)
+            pa.grad = gr.clone()
+            pb.grad.copy_(gr)                              # stays a view of the bucket
+        for pg in list(ref_opt.param_groups) + list(mine.param_groups):
+            pg["lr"] = 3e-4 * (t + 1)
+        ref_opt.step()
+        from opticalflowscivis_b200 import ops
+        n0 = ops.launch_count()
+        mine.step()
+        assert ops.launch_count() - n0 == 1               # one launch for ~150 tensors
+    with torch.no_grad():
+        worst = max(float((pa - pb).abs().max()) / max(1e-30, float(pa.abs().max())) for pa, pb in zip(a.parameters(), b.parameters()))
+    assert worst <= 2e-6, worst
+    with pytest.raises(TypeError):
+        FusedAdamW([torch.nn.Parameter(torch.zeros(3))])

@@ -284,3 +284,49 @@ def test_batch_sharding_world2_gloo():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
     assert all(r[3] == 5 and r[4] == 11.0 for r in res)
+
+
+def _gloo_grad_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from opticalflowscivis_b200.optim import GradientBucket, allreduce_gradients
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.PReLU(7), torch.nn.Linear(7, 3))
+    bucket = GradientBucket(net.parameters())
+    x = torch.full((4, 5), float(rank + 1))
+    net(x).sum().backward()                              # autograd accumulates INTO the bucket views
+    local = bucket.flat.clone()
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
+    scale = allreduce_gradients(bucket)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.allclose(bucket.flat, sum(gathered)) and scale == 1.0 / world and bucket.flat.numel() == sum(p.numel() for p in net.parameters())
+    q.put((rank, bool(ok), float(bucket.flat.abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_world2_gloo():
+    """Training-tier collective (SURVEY §8e): the gradients of all parameters are ONE flat bucket, summed by one all_reduce;
+    the 1/world average is returned as the optimizer's grad_scale.  Two gloo ranks on CPU."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res) and res[0][2] == res[1][2] and res[0][2] > 0
+    # no process group: no-op, scale 1
+    import torch
+    from opticalflowscivis_b200.optim import GradientBucket, allreduce_gradients
+    b = GradientBucket(torch.nn.Linear(2, 2).parameters())
+    assert allreduce_gradients(b) == 1.0

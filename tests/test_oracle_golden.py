@@ -153,3 +153,16 @@ def test_upflow_backward_golden():
             ops_ref.warping_layer_no_div_ref(a, b).backward(go)
             assert (a.grad - gx).abs().max() <= 1e-5 * max(1.0, float(gx.abs().max()))
             assert (b.grad - gf).abs().max() <= 1e-5 * max(1.0, float(gf.abs().max()))
+
+
+def test_adamw_golden():
+    """Optimizer step of the training loop: the numpy restatement replays torch.optim.AdamW as driven by the reference
+    (tests/golden/make_adamw_golden.py)."""
+    from oracle.adamw_ref import adamw_step
+    z = np.load(os.path.join(G, "adamw.npz"))
+    lrs = z["lrs"]
+    for i in range(5):
+        p, m, v = z[f"p0_{i}"], np.zeros_like(z[f"p0_{i}"]), np.zeros_like(z[f"p0_{i}"])
+        for t, lr in enumerate(lrs, start=1):
+            p, m, v = adamw_step(p, z[f"g{t}_{i}"], m, v, t, float(lr))
+            assert np.abs(p - z[f"p{t}_{i}"]).max() <= 1e-6 * max(1e-30, np.abs(z[f"p{t}_{i}"]).max()), (i, t)
