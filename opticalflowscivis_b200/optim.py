@@ -20,7 +20,9 @@ CHUNK = 4096
 
 
 class FusedAdamW:
-    def __init__(self, params, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3):
+    def __init__(self, params, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3, bucket=None):
+        """`bucket`: the GradientBucket holding these parameters' gradients, if any — the per-step validation of 160 gradient
+        tensors (≈ 80 µs of Python, twice the kernel) then reduces to checking that the bucket views are still in place."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FusedAdamW: no parameters")
@@ -37,6 +39,7 @@ class FusedAdamW:
         self.step_count = 0
         self._table = None
         self._table_key = None
+        self._bucket = bucket
 
     def zero_grad(self, set_to_none: bool = False):
         for p in self.params:
@@ -65,13 +68,14 @@ class FusedAdamW:
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0):
-        for p in self.params:
+        fast = self._bucket is not None and self._table is not None and self._bucket.intact()
+        for p in (() if fast else self.params):
             if p.grad is None:
                 raise RuntimeError("FusedAdamW.step: every parameter needs a gradient (the reference's IFNet always produces one)")
             if not p.grad.is_contiguous() or p.grad.dtype != torch.float32:
                 raise TypeError("FusedAdamW: gradients must be contiguous float32")
         g = self.param_groups[0]
-        t, c = self._tables()
+        t, c = self._table if fast else self._tables()
         self.step_count += 1
         with torch.cuda.device(self.device):
             _C.check(_C.lib().ofsv_adamw_step_f32(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(c.data_ptr()), t.shape[0], c.shape[0],
@@ -97,6 +101,13 @@ class GradientBucket:
 
     def zero(self):
         self.flat.zero_()
+
+    def intact(self) -> bool:
+        """True while every `p.grad` is still the view handed out at construction (zero_grad(set_to_none=True) or an
+        optimizer that re-assigns .grad would break that).  Cheap: first / last parameter only."""
+        a, b = self.params[0], self.params[-1]
+        return (a.grad is not None and b.grad is not None and a.grad.data_ptr() == self.flat.data_ptr()
+                and b.grad.data_ptr() == self.flat.data_ptr() + 4 * (self.flat.numel() - b.numel()))
 
 
 def allreduce_gradients(bucket: GradientBucket, group=None) -> float:

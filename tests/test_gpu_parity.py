@@ -986,7 +986,7 @@ def test_fused_adamw_golden_and_torch():
     b.load_state_dict(a.state_dict())
     ref_opt = torch.optim.AdamW(a.parameters(), lr=1e-6, weight_decay=1e-3)
     bucket = GradientBucket(b.parameters())
-    mine = FusedAdamW(b.parameters(), lr=1e-6, weight_decay=1e-3)
+    mine = FusedAdamW(b.parameters(), lr=1e-6, weight_decay=1e-3, bucket=bucket)
     g = torch.Generator(device="cuda").manual_seed(9)
     n0 = None
     for t in range(3):
