@@ -142,6 +142,10 @@ int ofsv_pack_block_input(const float* img0, const float* img1, const float* war
  * the reference loaders' `/ 255.`: Datasets/read_data.py, Flow-3D/load_datasets.py), so only bytes cross PCIe. */
 int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream);
 
+/* ... and back: dst[i] = (uint8)clamp(src[i] * mul, 0, 255), truncated toward zero — the reference's export
+ * `(img * 255).byte()` (Flow-3D/inference_img.py:105) done before the download. */
+int ofsv_f32_to_u8(const float* src, uint8_t* dst, int64_t n, float mul, void* stream);
+
 /* Evaluation metrics on the device, float64 like the numpy reference, reduced in a fixed order.
  * `partials` is caller-provided scratch of N * OFSV_METRIC_BLOCKS doubles; `out` receives N doubles.
  *   ofsv_sq_err_f64: out[n] = sum_i (((a[n][i] - b[n][i]) * scale)^2) over `count` elements per sample, all in fp64:

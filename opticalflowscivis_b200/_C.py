@@ -52,6 +52,7 @@ _SIGS = {
     "ofsv_warping_no_div_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ofsv_adamw_step_f32": (_I, [_P, _P, _I, _I, _F, _F, _F, _F, _F, _I, _F, _P]),
     "ofsv_u8_to_f32": (_I, [_P, _P, _L, _F, _P]),
+    "ofsv_f32_to_u8": (_I, [_P, _P, _L, _F, _P]),
     "ofsv_sq_err_f64": (_I, [_P, _P, _P, _P, _I, _L, _F, _P]),
     "ofsv_ssim2d_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, ctypes.c_double, _P]),
     "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 9 + [_P]),

@@ -188,6 +188,28 @@ static inline int grid_1d(int64_t total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// fp32 volume -> uint8: (uint8)(x * mul) with the product clamped to [0, 255] and truncated toward zero — the reference's
+// export `(img * 255).byte()` (Flow-3D/inference_img.py:105, Flow-2D/inference_img.py) done BEFORE the download, so that an
+// interpolated byte volume crosses PCIe as bytes.  16 voxels per thread.
+__global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n, float mul) {
+  const int64_t nv = n >> 4;
+  auto q = [mul](float x) -> uint32_t { return (uint32_t)fminf(fmaxf(__fmul_rn(x, mul), 0.0f), 255.0f); };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4* in = reinterpret_cast<const float4*>(src) + i * 4;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 v = __ldg(in + k);
+      w[k] = q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 15)) {
+    const int64_t i = (nv << 4) + threadIdx.x;
+    dst[i] = (uint8_t)q(src[i]);
+  }
+}
+
 }  // namespace ofsv
 
 using namespace ofsv;
@@ -244,4 +266,13 @@ extern "C" int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float d
   OFSV_REQUIRE(aligned16(src) && aligned16(dst), "ofsv_u8_to_f32: pointers must be 16-byte aligned");
   u8_to_f32_kernel<<<grid_1d(cdiv(n, 16)), 256, 0, (cudaStream_t)stream>>>(src, dst, n, div);
   return check_launch("u8_to_f32_kernel");
+}
+
+extern "C" int ofsv_f32_to_u8(const float* src, uint8_t* dst, int64_t n, float mul, void* stream) {
+  OFSV_REQUIRE(n >= 0, "ofsv_f32_to_u8: negative size");
+  if (n == 0) return OFSV_OK;
+  OFSV_REQUIRE(src && dst, "ofsv_f32_to_u8: null pointer");
+  OFSV_REQUIRE(aligned16(src) && aligned16(dst), "ofsv_f32_to_u8: pointers must be 16-byte aligned");
+  f32_to_u8_kernel<<<grid_1d(cdiv(n, 16)), 256, 0, (cudaStream_t)stream>>>(src, dst, n, mul);
+  return check_launch("f32_to_u8_kernel");
 }

@@ -479,6 +479,16 @@ def u8_to_f32(src: torch.Tensor, div: float = 255.0) -> torch.Tensor:
 METRIC_BLOCKS = 64
 
 
+def f32_to_u8(src: torch.Tensor, mul: float = 255.0) -> torch.Tensor:
+    """(src * mul).byte() with the product clamped to [0, 255] (ofsv_f32_to_u8): the reference's export
+    `(img * 255).byte()` (Flow-3D/inference_img.py:105) on the device, so that byte volumes are downloaded as bytes."""
+    x = _cuda_f32(src, "src")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().ofsv_f32_to_u8(_p(x), _p(out), x.numel(), float(mul), _stream()))
+    return out
+
+
 def _metric_args(a: torch.Tensor, b: torch.Tensor, what: str):
     if not (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.is_cuda and b.is_cuda):
         raise TypeError(f"{what}: expected CUDA tensors (there is no CPU path)")

@@ -58,8 +58,12 @@ class StreamedInterpolator:
     """
 
     def __init__(self, model, device: Optional[torch.device] = None, to_float: Optional[Callable] = None,
-                 select: Optional[Callable] = None, depth: int = 2):
+                 select: Optional[Callable] = None, depth: int = 2, out_u8: bool = False):
+        """out_u8: download the result as bytes, `(merged * 255).byte()` computed on the device — the reference's own export
+        (Flow-3D/inference_img.py:105) — instead of fp32: a quarter of the D2H bytes.  Off by default (fp32 like
+        `Model.inference`)."""
         self.model = model
+        self.out_u8 = out_u8
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         from . import ops
         self.to_float = to_float or (lambda t: ops.u8_to_f32(t, 255.0) if t.dtype == torch.uint8 else t)
@@ -83,6 +87,7 @@ class StreamedInterpolator:
         """pairs: iterable of (img0, img1) PINNED host tensors of one fixed shape/dtype; outs: optional iterable of pinned
         host tensors receiving the results (allocated on demand otherwise).  Yields the host results in order; a yielded
         tensor is complete (its download has been synchronised) when it is handed out."""
+        from . import ops
         comp = torch.cuda.current_stream(self.dev)
         outs_it = iter(outs) if outs is not None else None
         pending = []
@@ -99,6 +104,8 @@ class StreamedInterpolator:
             comp.wait_event(sl["up"])
             x0, x1 = self.to_float(sl["x0"]), self.to_float(sl["x1"])
             res = self.select(self.model.inference(x0, x1))
+            if self.out_u8:
+                res = ops.f32_to_u8(res, 255.0)
             sl["free"].record(comp)                            # (a pass-through to_float hands the slot itself to the model)
             ev = torch.cuda.Event()
             ev.record(comp)

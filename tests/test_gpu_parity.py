@@ -1006,3 +1006,27 @@ def test_fused_adamw_golden_and_torch():
     assert worst <= 2e-6, worst
     with pytest.raises(TypeError):
         FusedAdamW([torch.nn.Parameter(torch.zeros(3))])
+
+
+def test_f32_to_u8_export_and_streamed_u8_output():
+    """ofsv_f32_to_u8 == the reference's export `(img * 255).byte()` (Flow-3D/inference_img.py:105) on [0,1] data, clamps
+    outside it; StreamedInterpolator(out_u8=True) downloads exactly the bytes of the fp32 result."""
+    from opticalflowscivis_b200 import ops
+    from opticalflowscivis_b200.pipeline import StreamedInterpolator
+    from opticalflowscivis_b200.rife import Model3D
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(100003, generator=g).to(_dev())
+    assert torch.equal(ops.f32_to_u8(x), (x * 255).byte())
+    y = torch.tensor([-1.0, 0.0, 0.999999, 1.0, 2.0, float("nan")], device=_dev())
+    assert ops.f32_to_u8(y)[:5].tolist() == [0, 0, 254, 255, 255]
+    assert ops.f32_to_u8(torch.empty(0, device=_dev())).numel() == 0
+    torch.manual_seed(1234)
+    model = Model3D(local_rank=0)
+    model.eval()
+    a = (torch.rand((1, 1, 32, 32, 32), generator=g) > 0.5).to(torch.uint8).mul_(255).pin_memory()
+    b = torch.roll(a, 2, -1).contiguous().pin_memory()
+    f = list(StreamedInterpolator(model, _dev()).run([(a, b)] * 3))
+    u = list(StreamedInterpolator(model, _dev(), out_u8=True).run([(a, b)] * 3))
+    assert len(u) == 3 and u[0].dtype == torch.uint8
+    for ff, uu in zip(f, u):
+        assert torch.equal(uu, (ff.clamp(0, 1) * 255).byte())
