@@ -202,11 +202,41 @@ int ofsv_conv_simt(const ofsv_conv_desc* d, const void* x, const float* w, const
 int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
                  const void* residual, void* y, void* stream);
 
-/* Same contract as ofsv_conv_tc for the stride-1 layers (3^d convs, ConvTranspose phases: every tap offset in {-1,0,1}):
- * each input halo plane is loaded into shared memory once per super-tile and every tap is a shifted UMMA descriptor;
- * persistent CTAs, double-buffered TMEM accumulators.  Returns OFSV_ENOSUP (nothing launched) for other layers. */
+/* Same contract as ofsv_conv_tc for the stride-1 layers (3^d convs, ConvTranspose phases, depth-to-space heads, the
+ * space-to-depth conv0 layers: every tap offset in {-1,0,1}): each input halo plane is loaded into shared memory once per
+ * super-tile and every tap is a shifted UMMA descriptor; output slices that read the same plane are STACKED along N of one
+ * tcgen05.mma (csrc/conv_stack.cu); persistent CTAs, double-buffered TMEM accumulators, TMA-store epilogue.
+ * `w` must be in the layout ofsv_conv_halo_weight_layout(d) names.  Returns OFSV_ENOSUP (nothing launched) for other layers. */
 int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void* w, const float* bias, const float* prelu,
                    const void* residual, void* y, void* stream);
+
+/* Weight re-packing (SURVEY.md section 8b `ofsv_pack_*`): ONE launch per layer and parameter version.
+ *   w_tap : fp32 [nphase*ntaps][Cin_s][Cout_w] (the layout ofsv_conv_simt consumes)
+ *   w_out : bf16, nphase*ntaps*Cin_s*Cout_w elements, K-major [Cout_w][KC] blocks in
+ *     OFSV_WL_TAP   : [nphase][ntaps][Cin_s/KC] order, KC = largest of 64/32/16 dividing Cin_s (ofsv_conv_tc, the plane-ring kernel)
+ *     OFSV_WL_STACK : [pass][in-plane tap offset (dy,dx)][Cin_s/KC][slot = (phase asc, dz desc)] order, KC = 32 or 16: the
+ *                     slots of one in-plane offset are consecutive rows, so ONE MMA reads the weights of every output slice
+ *                     that shares an input plane (csrc/conv_stack.cu).
+ * Only nd, nphase, ntaps, tap_off, Cin_s, Cout_w of the descriptor are read (no shapes): a layer is packed once.
+ * ofsv_conv_halo_weight_layout: which of the two ofsv_conv_halo expects for this descriptor (>= 0), or a negative error. */
+#define OFSV_WL_TAP 0
+#define OFSV_WL_STACK 1
+int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_tap, void* w_out, int layout, void* stream);
+int ofsv_conv_halo_weight_layout(const ofsv_conv_desc* d);
+
+/* One-line description of the launch configuration ofsv_conv_halo would pick for `d` (kernel, super-tile depth, ring depths,
+ * epilogue mode, shared memory, modelled tensor-pipe fraction of the MMA list); host only, nothing is launched. */
+int ofsv_conv_halo_describe(const ofsv_conv_desc* d, char* buf, int buflen);
+
+/* Host-only self-check of the stacked kernel's MMA list for super-tile depth td (runs without a GPU): every (phase, tap,
+ * output slice) term covered exactly once, first-touch flags consistent, runs contiguous.  Optionally returns the number of
+ * MMAs-per-K-step and the modelled tensor cycles of one super-tile. */
+int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* nops_out, double* mma_cycles_out);
+
+/* Process-wide tuning / A-B switches between EQUIVALENT code paths (every setting computes the same results; there are no
+ * environment variables in the launch path).  Keys: "stack_epilogue" (-1 auto, 0 = per-thread stores instead of the TMA-store
+ * epilogue), "stack_td" (0 auto, 1|2|4 = super-tile depth when feasible), "warp_slab" (1 default, 0 = gather kernel only). */
+int ofsv_set_tuning(const char* key, int value);
 
 /* IFBlock output stage: flow/mask deltas at block resolution -> full resolution (IFNet.py:115-116 / :118-119,
  * F.interpolate(.., scale) and flow*scale), then flow += flow_d ; mask += mask_d (IFNet.py:177-178 / :169-170).

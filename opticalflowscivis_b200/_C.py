@@ -11,6 +11,7 @@ OK, EINVAL, ECUDA, ENOSUP = 0, -1, -2, -3
 REF_CPU, REF_CUDA = 0, 1
 F32, BF16 = 0, 1
 MAX_TAPS = 64
+WL_TAP, WL_STACK = 0, 1
 
 
 class ConvDesc(ctypes.Structure):
@@ -59,6 +60,11 @@ _SIGS = {
     "ofsv_conv_simt": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_halo": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "ofsv_conv_pack_weights": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _I, _P]),
+    "ofsv_conv_halo_weight_layout": (_I, [ctypes.POINTER(ConvDesc)]),
+    "ofsv_conv_stack_selfcheck": (_I, [ctypes.POINTER(ConvDesc), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
+    "ofsv_conv_halo_describe": (_I, [ctypes.POINTER(ConvDesc), ctypes.c_char_p, _I]),
+    "ofsv_set_tuning": (_I, [ctypes.c_char_p, _I]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 8 + [_P]),
 }

@@ -53,7 +53,7 @@ extern "C" int ofsv_adamw_step_f32(const void* tensors, const void* chunks, int 
   OFSV_REQUIRE(tensors && chunks, "ofsv_adamw_step_f32: null pointer");
   // bias corrections in double like the python scalars of torch.optim.adamw._single_tensor_adamw
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  const int grid = nchunks < 148 * 8 ? nchunks : 148 * 8;
+  const int grid = nchunks < device_num_sms() * 8 ? nchunks : device_num_sms() * 8;
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamWTensor*>(tensors), reinterpret_cast<const int2*>(chunks),
                                                       nchunks, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
   return check_launch("adamw_kernel");

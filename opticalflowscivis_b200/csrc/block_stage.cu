@@ -357,12 +357,8 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : OFSV_BS_MINB) 
 template <int SH, int SN, bool S2D, bool FMA>
 static int launch_stage(const StagePtrs& q, const Warp3dParams& P, dim3 grid, cudaStream_t st) {
   constexpr int smem = bs_smem_bytes(SH, SN);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(block_stage_3d_kernel<SH, SN, S2D, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("ofsv_block_stage_3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dyn_smem(attr_done, block_stage_3d_kernel<SH, SN, S2D, FMA>, smem, "ofsv_block_stage_3d")) return e;
   block_stage_3d_kernel<SH, SN, S2D, FMA><<<grid, 256, smem, st>>>(q, P);
   return OFSV_OK;
 }

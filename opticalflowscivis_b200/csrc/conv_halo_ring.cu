@@ -53,7 +53,7 @@ struct RingParams {
   int tiles_w, tiles_h, tiles_d;     // super-tile grid per sample
   int nb, plane_stride, b_stride;    // B ring depth, smem strides (bytes, multiples of 1024)
   int nbuf, acc_stride;              // TMEM accumulator double buffering
-  int has_prelu, has_residual, out_f32, shuffle, dbg_flags;
+  int has_prelu, has_residual, out_f32, shuffle;
   int nd, out_s2d;
   int dzspan;                        // dzmax - dzmin
   int sliding;                       // 1: z-fastest contiguous tile runs with shared boundary planes and early plane release
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(H_THREADS, 1)
         mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 128);   // long waits: sleep between polls
         tcgen05_fence_after();
         const long long te1 = clock64();
-        for (int it = half; it < ((p.dbg_flags & 1) ? 0 : nitems); it += 2) {
+        for (int it = half; it < nitems; it += 2) {
           const int j = it / nch, c0 = (it - j * nch) << 4;
           const uint4 rcur0 = rnext[0], rcur1 = rnext[1];
           float4 fcur[4];
@@ -462,41 +462,10 @@ __global__ void __launch_bounds__(H_THREADS, 1)
 template <int KC>
 static int launch_halo_ring(const RingParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
                        const float* prelu, const void* residual, void* y, int grid, size_t smem, cudaStream_t st) {
-  long long* dbg = nullptr;
-  const char* trace_path = getenv("OFSV_HALO_TRACE");
-  if (trace_path) { cudaMalloc(&dbg, 16 * 16 * 8); cudaMemset(dbg, 0, 16 * 16 * 8); }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_ring_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("ofsv_conv_halo(ring): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
-    attr_done = true;
-  }
-  conv_halo_ring_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y, dbg);
-  const int rc = check_launch("conv_halo_ring_kernel");
-  if (trace_path) {   // debug only: synchronous dump of CTA 0's timeline
-    static long long h[256];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    cudaFree(dbg);
-    if (FILE* f = fopen(trace_path, "a")) {
-      fprintf(f, "launch N=%d Cout_w=%d td=%d nphase=%d ntaps=%d tiles=%dx%dx%d grid=%d nb=%d nbuf=%d\n", P.N, P.Cout_w, P.td, P.nphase, P.ntaps, P.tiles_w, P.tiles_h, P.tiles_d, grid, P.nb, P.nbuf);
-      const long long t0 = h[0];
-      for (int i = 0; i < 16 && h[i * 16 + 3]; ++i)
-        fprintf(f, "  st %2d: prod wait_planes_empty [%lld..%lld]  mma [%lld..%lld] wait plane %lld b %lld acc %lld | epi(pass %d) wait_full [%lld..%lld] done %lld\n", i, h[i * 16] - t0, h[i * 16 + 1] - t0, h[i * 16 + 2] - t0, h[i * 16 + 3] - t0, h[i * 16 + 4], h[i * 16 + 5], h[i * 16 + 6], i, h[i * 16 + 8] - t0, h[i * 16 + 9] - t0, h[i * 16 + 10] - t0);
-      fclose(f);
-    }
-  }
-  return rc;
-}
-
-static int ring_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dyn_smem(attr_done, conv_halo_ring_kernel<KC>, 227 * 1024, "ofsv_conv_halo(ring)")) return e;
+  conv_halo_ring_kernel<KC><<<grid, H_THREADS, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y, nullptr);
+  return check_launch("conv_halo_ring_kernel");
 }
 
 }  // namespace ofsv
@@ -552,15 +521,13 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
   P.tiles_w = (int)cdiv(d->Wo, HT_W); P.tiles_h = (int)cdiv(d->Ho, HT_H);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
   P.shuffle = d->out_shuffle; P.nd = d->nd; P.out_s2d = d->out_s2d;
-  { const char* f = getenv("OFSV_HALO_DBGFLAGS"); P.dbg_flags = f ? atoi(f) : 0; }   // bring-up switches (1 = skip epilogue work)
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
-  const int sms = ring_num_sms();
+  const int sms = device_num_sms();
   const size_t smem_cap = 227 * 1024 - 2048;
   const size_t bar_bytes = (2 * H_MAX_PLANES + 2 * H_MAX_BSTAGES + 4) * 8 + 32 + 2 * 128 * 4 + OFSV_MAX_TAPS * 4;
   // TD: as many output slices per B-tile load as fit (TMEM columns, shared memory) while keeping >= 2 waves of super-tiles
   int td = 0;
-  const char* force = getenv("OFSV_HALO_TD");   // test hook: force the super-tile depth (1, 2 or 4) when it fits
-  const int forced = force ? atoi(force) : 0;
+  const int forced = 0;
   for (int cand = 4; cand >= 1; cand >>= 1) {
     if (forced && cand != forced && cand > 1) continue;
     if (d->Do % cand) continue;                       // the plane ring assumes full super-tiles along z
@@ -587,8 +554,7 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
   {  // the plane ring pays off where a super-tile has little tensor work per loaded plane (few taps, several channel chunks);
      // layers with a long tap loop hide their plane loads anyway and measured ~10 % slower with it on B200
     const int mmas = d->nphase * d->ntaps * P.nkc * (KC / 16) * td;
-    const char* f = getenv("OFSV_HALO_SLIDING");
-    P.sliding = f ? atoi(f) : (mmas <= 256 ? 1 : 0);
+    P.sliding = mmas <= 256 ? 1 : 0;
   }
   if (d->nphase == 1 && P.sliding) {
     for (int q = 0; q < td; ++q) {
@@ -614,8 +580,7 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
   // batch size through the wave count): exactly two groups, and only for layers whose accumulators fit at every TD <= 4.
   // (A pair then gives bit-identical results alone and inside any batch — tests/test_gpu_parity.py, batch invariance.)
   if (P.b_resident && d->nphase == 1 && d->ntaps % 2 == 0 && 2 * 4 * d->Cout_w <= 256 && 2 * td <= H_MMA_WARPS) {
-    const char* f = getenv("OFSV_RING_NG");            // A/B hook: 1 disables the tap-group split
-    P.ng = (f && atoi(f) == 1) ? 1 : 2;
+    P.ng = 2;
   }
   P.nbuf = (2 * P.ng * td * d->Cout_w <= 512) ? 2 : 1;
   P.acc_stride = 256;

@@ -155,12 +155,8 @@ static int launch_tc(const TcParams& P, const CUtensorMap& tmA, const CUtensorMa
                      const void* residual, void* y, dim3 grid, cudaStream_t st) {
   const int b_bytes = (P.Cout_w * KC * 2 + 1023) & ~1023;
   const size_t smem = 1024 + (size_t)P.stages * (TC_M * KC * 2 + b_bytes) + (2 * TC_MAX_STAGES + 1) * 8 + 16;
-  static bool attr_done = false;   // per-template-instance
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) { set_error("ofsv_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // per template instance, one bit per device
+  if (int e = ensure_dyn_smem(attr_done, conv_tc_kernel<KC>, 200 * 1024, "ofsv_conv_tc")) return e;
   conv_tc_kernel<KC><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
   return check_launch("conv_tc_kernel");
 }

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restric
 
 static inline int grid_1d(int64_t total) {
   int64_t b = cdiv(total, 256);
-  const int64_t cap = 148 * 32;
+  const int64_t cap = device_num_sms() * 32;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 

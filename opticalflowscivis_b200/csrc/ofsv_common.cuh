@@ -45,6 +45,23 @@ __host__ __device__ inline int64_t s2d_row(int nd, int n, int z, int y, int x, i
   return ((((int64_t)n * Dc + (z1 >> 1)) * Hc + (y1 >> 1)) * Wc + (x1 >> 1)) * 8 + (((z1 & 1) << 2) | ((y1 & 1) << 1) | (x1 & 1));
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember per kernel which device
+// ordinals have it (one bit each; devices >= 64 re-set it on every launch) instead of a per-process flag, so that a second
+// GPU used from the same process gets it too and concurrent host threads never race on a plain bool.
+template <typename K>
+inline int ensure_dyn_smem(std::atomic<uint64_t>& done, K kernel, int bytes, const char* who) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("%s: cudaGetDevice: %s", who, cudaGetErrorString(e)); return OFSV_ECUDA; }
+  const uint64_t bit = dev < 64 ? (1ull << dev) : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return OFSV_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(%d B of dynamic shared memory): %s", who, bytes, cudaGetErrorString(e)); return OFSV_ECUDA; }
+  done.fetch_or(bit, std::memory_order_release);
+  return OFSV_OK;
+}
+int device_num_sms();   // api.cu: SM count of the CURRENT device (cached per device ordinal)
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -14,7 +14,7 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 }
 static inline int grid_1d_bwd(int64_t total) {
   int64_t b = cdiv(total, 256);
-  const int64_t cap = 148 * 16;
+  const int64_t cap = device_num_sms() * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -154,7 +154,7 @@ extern "C" int ofsv_warping_no_div_bwd_f32(const float* src, const float* flow, 
   }
   const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
   const int gx = grid_1d_bwd((int64_t)B * H * W);
-  int nsplit = (int)(cdiv(148 * 8, gx));
+  int nsplit = (int)(cdiv(device_num_sms() * 8, gx));
   nsplit = nsplit < 1 ? 1 : (nsplit > cdiv(C, 4) ? (int)cdiv(C, 4) : nsplit);
   const int c_per = (int)cdiv(C, nsplit);
   const unsigned gy = (unsigned)cdiv(C, c_per);

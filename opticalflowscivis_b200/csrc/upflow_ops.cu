@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256)
 
 static inline int grid_1d(int64_t total) {
   int64_t b = cdiv(total, 256);
-  const int64_t cap = 148 * 16;
+  const int64_t cap = device_num_sms() * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -299,14 +299,11 @@ extern "C" int ofsv_corr81_bwd_f32(const float* f1, const float* f2, const float
   if (B == 0) return OFSV_OK;
   OFSV_REQUIRE(f1 && f2 && gout && g1 && g2, "ofsv_corr81_bwd_f32: null pointer");
   OFSV_REQUIRE(B <= 65535 && cdiv(H, BTH) <= 65535, "ofsv_corr81_bwd_f32: batch / height exceed the grid");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(corr81_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_BWD_SMEM);
-    cudaFuncSetAttribute(corr81_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_BWD_SMEM);
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_a{0}, attr_b{0};
+  if (int e = ensure_dyn_smem(attr_a, corr81_bwd_kernel<false>, CORR_BWD_SMEM, "ofsv_corr81_bwd_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_b, corr81_bwd_kernel<true>, CORR_BWD_SMEM, "ofsv_corr81_bwd_f32")) return e;
   const int tiles_x = (int)cdiv(W, BTW), tiles_y = (int)cdiv(H, BTH);
-  int nsplit = (int)cdiv(2 * 148, (int64_t)tiles_x * tiles_y * B);          // aim at two CTAs per SM
+  int nsplit = (int)cdiv(2 * device_num_sms(), (int64_t)tiles_x * tiles_y * B);          // aim at two CTAs per SM
   const int max_split = (int)cdiv(C, BCC);
   nsplit = nsplit < 1 ? 1 : (nsplit > max_split ? max_split : nsplit);
   const int c_per_cta = (int)cdiv(cdiv(C, nsplit), BCC) * BCC;
@@ -339,7 +336,7 @@ extern "C" int ofsv_warping_no_div_f32(const float* src, const float* flow, floa
   OFSV_REQUIRE(src && flow && out, "ofsv_warping_no_div_f32: null pointer");
   const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
   const int gx = grid_1d((int64_t)B * H * W);
-  int nsplit = (int)(cdiv(148 * 8, gx));                 // aim at >= 8 CTAs per SM; at least 4 channels per thread
+  int nsplit = (int)(cdiv(device_num_sms() * 8, gx));                 // aim at >= 8 CTAs per SM; at least 4 channels per thread
   nsplit = nsplit < 1 ? 1 : (nsplit > cdiv(C, 4) ? (int)cdiv(C, 4) : nsplit);
   const int c_per = (int)cdiv(C, nsplit);
   warping_no_div_kernel<<<dim3((unsigned)gx, (unsigned)cdiv(C, c_per)), 256, 0, (cudaStream_t)stream>>>(

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ w0
 
 static inline int grid_1d(int64_t total) {
   int64_t b = cdiv(total, 256);
-  const int64_t cap = 148 * 16;
+  const int64_t cap = device_num_sms() * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -334,16 +334,13 @@ static int warp3d_dispatch(const float* src, const float* flow, const float* lin
   OFSV_REQUIRE(ntasks64 < (1ll << 31) - 148 * 64, "ofsv_warp3d_f32: too many tiles for 32-bit task ids");
   const uint32_t ntasks = (uint32_t)ntasks64;
   const int64_t ctas = cdiv(ntasks64, W3_WARPS);
-  const int grid = (int)(ctas < 148 * OFSV_W3_MINB ? ctas : 148 * OFSV_W3_MINB);      // OFSV_W3_MINB CTAs of 4 warps resident per SM, persistent over the task list
+  const int grid = (int)(ctas < device_num_sms() * OFSV_W3_MINB ? ctas : device_num_sms() * OFSV_W3_MINB);      // OFSV_W3_MINB CTAs of 4 warps resident per SM, persistent over the task list
   const int smem = W3_WARPS * W3_SMEM_PER_WARP;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(warp3d_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(warp3d_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(warp3d_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(warp3d_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done[4];
+  if (int e = ensure_dyn_smem(attr_done[0], warp3d_kernel<true, true>, smem, "ofsv_warp3d_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_done[1], warp3d_kernel<true, false>, smem, "ofsv_warp3d_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_done[2], warp3d_kernel<false, true>, smem, "ofsv_warp3d_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_done[3], warp3d_kernel<false, false>, smem, "ofsv_warp3d_f32")) return e;
 #define LAUNCH(V, F) warp3d_kernel<V, F><<<grid, 32 * W3_WARPS, smem, st>>>(src, flow, lin_h, lin_d, lin_w, out, P, ntasks)
   if (vec) { if (ref_mode == OFSV_REF_CUDA) LAUNCH(true, true); else LAUNCH(true, false); }
   else     { if (ref_mode == OFSV_REF_CUDA) LAUNCH(false, true); else LAUNCH(false, false); }

@@ -275,12 +275,12 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
   P.N = N; P.C = C; P.S = S; P.ref_mode = ref_mode; P.flow_nc = flow_nc; P.flow_c0 = flow_c0;
   P.dbg_skip = 0;
 #ifdef OFSV_SLAB_PROBE
-  { const char* e = getenv("OFSV_SLAB_DBG_SKIP"); P.dbg_skip = e ? atoi(e) : 0; }
+  { const char* e = getenv("OFSV_SLAB_DBG_SKIP"); P.dbg_skip = e ? atoi(e) : 0; }   // probe builds only, never in the shipped library
 #endif
   const Warp3dParams wp = make_warp3d_params(N, C, S, S, S, ref_mode);
   for (int i = 0; i < 6; ++i) P.hs[i] = wp.hs[i];
   const int64_t tiles = (int64_t)N * C * (S / 32) * (S / TW);
-  const int slots = 148 * ((TW == 32 || VPT == 2) ? 1 : 2);      // resident CTAs of the persistent grid
+  const int slots = device_num_sms() * ((TW == 32 || VPT == 2) ? 1 : 2);      // resident CTAs of the persistent grid
   // d chunks per tile column: every task pays a prologue (13 slabs before its first plane pair, ~6 plane times) and the last
   // round of the persistent grid may be partly empty — minimise rounds x (planes per task + prologue)
   int nchunk = 1;
@@ -290,19 +290,14 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
     const double cost = (double)rounds * (2.0 * (double)cdiv(S / 2, k) + 6.0);
     if (cost < best) { best = cost; nchunk = k; }
   }
-  { const char* e = getenv("OFSV_SLAB_NCHUNK"); if (e && atoi(e) >= 1 && atoi(e) <= S / 4) nchunk = atoi(e); }   // calibration of the cost model
   P.nchunk = nchunk;
   const int64_t ntasks = tiles * nchunk;
   if (ntasks >= (1ll << 31)) return 0;
   P.ntasks = (uint32_t)ntasks;
   const int grid = (int)(ntasks < slots ? ntasks : slots);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e1 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    cudaError_t e2 = cudaFuncSetAttribute(warp3d_slab_kernel<TW, VPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("ofsv_warp3d_f32: cudaFuncSetAttribute failed"); return OFSV_ECUDA; }
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_a{0}, attr_b{0};
+  if (int e = ensure_dyn_smem(attr_a, warp3d_slab_kernel<TW, VPT, true>, K::SMEM, "ofsv_warp3d_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_b, warp3d_slab_kernel<TW, VPT, false>, K::SMEM, "ofsv_warp3d_f32")) return e;
   if (ref_mode == OFSV_REF_CUDA)
     warp3d_slab_kernel<TW, VPT, true><<<grid, K::THREADS, K::SMEM, st>>>(tm_src, tm_flow, src, lin_h, lin_d, lin_w, out, P);
   else
@@ -314,15 +309,14 @@ static int warp3d_slab_launch(const float* src, const float* flow, const float* 
 #ifndef OFSV_SLAB_TW
 #define OFSV_SLAB_TW 16
 #endif
+std::atomic<int> g_warp_slab{1};
 int warp3d_slab_try(const float* src, const float* flow, const float* lin_h, const float* lin_d, const float* lin_w, float* out,
                     int N, int C, int D, int H, int W, int ref_mode, cudaStream_t st, int flow_nc, int flow_c0) {
   if (!(D == H && H == W && W % 32 == 0 && W >= 32 && W <= 1024)) return 0;
   if (!aligned16(src) || !aligned16(flow) || !aligned16(out) || !aligned16(lin_w)) return 0;
   if ((int64_t)N * C > (1 << 20) || (int64_t)N * flow_nc > (1 << 20)) return 0;
-  const char* e = getenv("OFSV_SLAB_TW");          // A/B switch for tests/bench_warp.py
-  const int tw = e ? atoi(e) : OFSV_SLAB_TW;
-  if (tw == 32) return warp3d_slab_launch<32, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);
-  if (tw == 322) return warp3d_slab_launch<32, 2>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);   // 1024 threads, 2 voxels each
+  if (!g_warp_slab.load(std::memory_order_relaxed)) return 0;      // ofsv_set_tuning("warp_slab", 0): gather kernel only
+  if (OFSV_SLAB_TW == 32) return warp3d_slab_launch<32, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);
   return warp3d_slab_launch<16, 4>(src, flow, lin_h, lin_d, lin_w, out, N, C, W, ref_mode, flow_nc, flow_c0, st);
 }
 

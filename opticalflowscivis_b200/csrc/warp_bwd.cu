@@ -189,7 +189,7 @@ extern "C" int ofsv_warp2d_bwd_f32(const float* src, const float* flow, const fl
     if (e != cudaSuccess) { set_error("ofsv_warp2d_bwd_f32: memset: %s", cudaGetErrorString(e)); return OFSV_ECUDA; }
   }
   int64_t b = cdiv((int64_t)N * H * W, 256);
-  const int64_t cap = 148 * 16;
+  const int64_t cap = device_num_sms() * 16;
   const int grid = (int)(b < cap ? b : cap);
   warp2d_bwd_kernel<<<grid, 256, 0, st>>>(src, flow, gout, lin_x, lin_y, gsrc, gflow, N, C, H, W, ref_mode);
   return check_launch("warp2d_bwd_kernel");

@@ -83,10 +83,7 @@ class _Layer:
         w = torch.zeros(len(taps), self.cin_s, self.cout_w, device=dev, dtype=torch.float32)
         w[:, :cin, :cout] = w_tap
         self.w_simt = w.contiguous()
-        kc = 64 if self.cin_s % 64 == 0 else (32 if self.cin_s % 32 == 0 else 16)
-        self.kc = kc
-        self.w_tc = (w.view(len(taps), self.cin_s // kc, kc, self.cout_w).permute(0, 1, 3, 2)
-                     .contiguous().to(torch.bfloat16))
+        self._packed = {}                  # weight layout -> bf16 blocks, packed by the library on first use (one launch)
         self.bias = torch.zeros(self.cout_w, device=dev, dtype=torch.float32)
         self.bias[:cout] = bias
         self.prelu = None
@@ -95,6 +92,31 @@ class _Layer:
             self.prelu[:cout] = prelu
         self.out_f32, self.residual, self.shuffle = out_f32, residual, shuffle
         self.in_s2d = self.out_s2d = False
+
+    def _structure_desc(self):
+        """Descriptor carrying only what the weight layouts depend on (taps, Cin_s, Cout_w) — no shapes."""
+        d = _C.ConvDesc()
+        d.nd, d.Cin_s, d.Cout_w, d.Cout_s = self.nd, self.cin_s, self.cout_w, self.cout_s
+        d.nphase, d.ntaps = self.nphase, self.ntaps
+        for i, t in enumerate(self.taps):
+            d.tap_off[i][0], d.tap_off[i][1], d.tap_off[i][2], d.tap_off[i][3] = t[0], t[1], t[2], 0
+        return d
+
+    def _pack(self, layout):
+        w = self._packed.get(layout)
+        if w is None:
+            w = self._packed[layout] = ops.conv_pack_weights(self._structure_desc(), self.w_simt, layout)
+        return w
+
+    @property
+    def w_tc(self):
+        """bf16 [nphase][ntaps][Cin_s/KC][Cout_w][KC] blocks (ofsv_conv_tc, the plane-ring kernel)."""
+        return self._pack(_C.WL_TAP)
+
+    @property
+    def w_halo(self):
+        """The layout ofsv_conv_halo wants for this layer (stacked slots for the 3^d convs / ConvT / heads)."""
+        return self._pack(ops.conv_halo_weight_layout(self._structure_desc()))
 
     def out_shape(self, n, osp):
         """Physical shape of the output tensor for logical output dims osp = (D,H,W)."""
@@ -317,7 +339,7 @@ class IFBlock(nn.Module):
             if eng == "tc" and USE_HALO and lay.in_stride == 1 and not getattr(lay, "no_halo", False):
                 # stride-1 layers: halo-reuse kernel; layers it cannot hold in shared memory use the per-tap kernel
                 try:
-                    ops.conv(d, x, lay.w_tc, lay.bias, lay.prelu, res, y, "halo")
+                    ops.conv(d, x, lay.w_halo, lay.bias, lay.prelu, res, y, "halo")
                     eng = None
                 except NotImplementedError:
                     if lay.in_s2d:

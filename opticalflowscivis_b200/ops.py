@@ -457,6 +457,28 @@ def state_views(fm):
     return fm[..., :6].permute(0, 4, 1, 2, 3), fm[..., 6:7].permute(0, 4, 1, 2, 3)
 
 
+def conv_pack_weights(desc: "_C.ConvDesc", w_tap: torch.Tensor, layout: int) -> torch.Tensor:
+    """fp32 tap-form weights [T][Cin_s][Cout_w] -> the bf16 K-major blocks of `layout` (_C.WL_TAP | _C.WL_STACK) in ONE launch
+    (ofsv_conv_pack_weights).  Only the layer structure of `desc` is read (taps, Cin_s, Cout_w)."""
+    w = _cuda_f32(w_tap, "w_tap")
+    out = torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().ofsv_conv_pack_weights(ctypes.byref(desc), _p(w), _p(out), int(layout), _stream()))
+    return out
+
+
+def conv_halo_weight_layout(desc: "_C.ConvDesc") -> int:
+    rc = _C.lib().ofsv_conv_halo_weight_layout(ctypes.byref(desc))
+    if rc < 0:
+        _C.check(rc)
+    return rc
+
+
+def set_tuning(key: str, value: int) -> None:
+    """Process-wide A/B switch between equivalent code paths of the library (ofsv_set_tuning)."""
+    _C.check(_C.lib().ofsv_set_tuning(key.encode(), int(value)))
+
+
 def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
     L = _C.lib()
     fn = {"tc": L.ofsv_conv_tc, "halo": L.ofsv_conv_halo, "simt": L.ofsv_conv_simt}[engine]

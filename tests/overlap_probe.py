@@ -16,7 +16,7 @@ fm = torch.randn(n, 256, 256, 256, 8, device=dev)
 img0, img1 = torch.rand(n, 1, 256, 256, 256, device=dev), torch.rand(n, 1, 256, 256, 256, device=dev)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 def convs(k=20):
-    for _ in range(k): ops.conv(d, x, lay.w_tc, lay.bias, lay.prelu, None, y, "halo")
+    for _ in range(k): ops.conv(d, x, lay.w_halo, lay.bias, lay.prelu, None, y, "halo")
 def stages(k=3):
     for _ in range(k): ops.block_stage_3d(None, fm, img0, img1, 0, 0, True, True)
 def timed(fn):

@@ -326,6 +326,61 @@ def test_conv_engines_vs_tap_evaluator(nd, engine, dtype):
         assert err <= tol * max(1.0, scale_), (li, err, scale_)
 
 
+@pytest.mark.parametrize("nd,c", [(3, 64), (3, 128), (2, 64), (2, 96)])
+def test_stacked_halo_engine_vs_tap_evaluator(nd, c):
+    """csrc/conv_stack.cu (stacked-N tcgen05 kernel) on every stride-1 layer type of a block — 3^d conv, 3^d conv + residual,
+    merged ConvT (P = 2 passes), depth-to-space heads with and without the fp32 state residual — on ragged grids (tiles that
+    overhang in h / w, a depth that is not a multiple of the super-tile depth), against the CPU tap evaluator; and bit-identical
+    results across super-tile depths (what makes batch sharding exact) and across the two epilogues (TMA store / per-thread)."""
+    from opticalflowscivis_b200 import _C, ifnet, ops
+    from tap_eval import run_layer
+    torch.manual_seed(21)
+    cin = 5 + 2 * nd
+    blk = ifnet.IFBlock(nd, cin, c)
+    for p in blk.parameters():
+        if p.dim() == 1 and float(p.data.std()) == 0:
+            p.data.uniform_(0.05, 0.5)       # non-trivial PReLU slopes
+    blk_dev = ifnet.IFBlock(nd, cin, c).to(_dev())
+    blk_dev.load_state_dict(blk.state_dict())
+    Lc, Ld = list(blk.layers()), list(blk_dev.layers())
+    Lc.append(blk._heads_shuffle); Ld.append(blk_dev._heads_shuffle)
+    sp = (1, 20, 28) if nd == 2 else (6, 20, 12)
+    try:
+        for li in (2, 3, 10, 12, 13):
+            with_state = li == 13
+            lc, ld = Lc[min(li, 12)], Ld[min(li, 12)]
+            xin = (torch.randn((2,) + sp + (lc.cin_s,)) * 0.5).bfloat16().float()
+            d, osp = lc.desc(2, sp, _C.BF16)
+            res = None
+            if lc.residual:
+                res = (torch.randn((2,) + osp + (lc.cout_s,)) * 0.5).bfloat16().float()
+            if with_state:
+                res = torch.randn((2,) + osp + (8,)) * 2.0
+                d.has_residual = 1
+            ref = run_layer(lc, xin, res)
+            odt = torch.float32 if lc.out_f32 else torch.bfloat16
+            outs = {}
+            for td in ((0, 1, 2, 4) if nd == 3 else (0,)):
+                for epi in (-1, 0):
+                    ops.set_tuning("stack_td", td)
+                    ops.set_tuning("stack_epilogue", epi)
+                    y = torch.full((2,) + osp + (lc.cout_s,), 7.0, device=_dev(), dtype=odt)
+                    rdev = None if res is None else res.to(_dev()).to(torch.float32 if with_state else torch.bfloat16)
+                    ops.conv(d, xin.to(_dev()).bfloat16(), ld.w_halo, ld.bias, ld.prelu, rdev, y, "halo")
+                    torch.cuda.synchronize()
+                    outs[(td, epi)] = y.float().cpu()
+            got = outs[(0, -1)]
+            if nd == 2:
+                got = got.view(ref.shape)
+            err, scale_ = float((got - ref).abs().max()), float(ref.abs().max())
+            assert err <= 3e-2 * max(1.0, scale_), (nd, c, li, err, scale_)
+            for k, v in outs.items():
+                assert torch.equal(v, outs[(0, -1)]), (nd, c, li, k, float((v - outs[(0, -1)]).abs().max()))
+    finally:
+        ops.set_tuning("stack_td", 0)
+        ops.set_tuning("stack_epilogue", -1)
+
+
 def _psnr(a, b):
     mse = float(((a - b) ** 2).mean())
     return 10 * np.log10(1.0 / max(mse, 1e-20))
@@ -571,7 +626,7 @@ def test_conv0_space_to_depth_on_halo_engine(nd):
     r0 = run_layer(blk._s2d0, xs)
     d0, osp0 = blk_dev._s2d0.desc(2, sp, _C.BF16)
     y0 = torch.zeros(blk_dev._s2d0.out_shape(2, osp0), device=_dev(), dtype=torch.bfloat16)
-    ops.conv(d0, xs.to(_dev()).to(torch.bfloat16), blk_dev._s2d0.w_tc, blk_dev._s2d0.bias, blk_dev._s2d0.prelu, None, y0, "halo")
+    ops.conv(d0, xs.to(_dev()).to(torch.bfloat16), blk_dev._s2d0.w_halo, blk_dev._s2d0.bias, blk_dev._s2d0.prelu, None, y0, "halo")
     want0 = ifnet.s2d_shift_pack(r0, nd)
     got0 = y0.float().cpu().view(want0.shape)
     assert float((got0 - want0).abs().max()) <= 3e-2 * max(1.0, float(want0.abs().max()))
@@ -579,7 +634,7 @@ def test_conv0_space_to_depth_on_halo_engine(nd):
     assert float(got0[border].abs().max()) <= 3e-2          # padding sub-cells untouched (zero)
     d1, osp1 = blk_dev._s2d1.desc(2, osp0, _C.BF16)
     y1 = torch.empty(blk_dev._s2d1.out_shape(2, osp1), device=_dev(), dtype=torch.bfloat16)
-    ops.conv(d1, y0, blk_dev._s2d1.w_tc, blk_dev._s2d1.bias, blk_dev._s2d1.prelu, None, y1, "halo")
+    ops.conv(d1, y0, blk_dev._s2d1.w_halo, blk_dev._s2d1.bias, blk_dev._s2d1.prelu, None, y1, "halo")
     r1 = run_layer(blk._s2d1, got0)
     got1 = y1.float().cpu().view(r1.shape)
     assert float((got1 - r1).abs().max()) <= 3e-2 * max(1.0, float(r1.abs().max()))

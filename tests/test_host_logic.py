@@ -330,3 +330,44 @@ def test_gradient_bucket_allreduce_world2_gloo():
     from opticalflowscivis_b200.optim import GradientBucket, allreduce_gradients
     b = GradientBucket(torch.nn.Linear(2, 2).parameters())
     assert allreduce_gradients(b) == 1.0
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_stacked_conv_op_lists_cover_every_term_once(nd):
+    """csrc/conv_stack.cu builds its MMA list on the host: every (phase, tap, output slice) term must appear exactly once, the
+    first MMA into a TMEM column block must be the one that overwrites, and every run must be contiguous in weight rows and
+    columns.  ofsv_conv_stack_selfcheck replays the list with the launch code's own plan functions (no GPU needed); the
+    modelled tensor cycles per output slice must not get worse with a deeper super-tile (the point of stacking along N)."""
+    L = _C.lib()
+    for c, cin in ((128, 2), (96 if nd == 2 else 64, 5 + 2 * nd), (64, 5 + 2 * nd)):
+        torch.manual_seed(3)
+        blk = ifnet.IFBlock(nd, cin, c)
+        layers = list(blk.layers()) + [blk._heads_shuffle]
+        for li, lay in enumerate(layers):
+            if lay.in_stride != 1:
+                continue
+            d = lay._structure_desc()
+            layout = L.ofsv_conv_halo_weight_layout(ctypes.byref(d))
+            assert layout in (_C.WL_TAP, _C.WL_STACK)
+            if layout != _C.WL_STACK:
+                continue
+            per_slice = {}
+            for td in ((1, 2, 4) if nd == 3 else (1,)):
+                nops, cyc = ctypes.c_int(0), ctypes.c_double(0.0)
+                rc = L.ofsv_conv_stack_selfcheck(ctypes.byref(d), td, ctypes.byref(nops), ctypes.byref(cyc))
+                if rc == _C.ENOSUP:
+                    continue
+                assert rc == 0, (nd, c, li, td, L.ofsv_last_error().decode())
+                assert nops.value >= 1
+                per_slice[td] = cyc.value / td
+            assert per_slice, (nd, c, li)
+            tds = sorted(per_slice)
+            for a, b in zip(tds, tds[1:]):
+                assert per_slice[b] <= per_slice[a] * 1.001, (nd, c, li, per_slice)
+    # the point of the design: a 64 -> 64 3^3 conv at TD = 4 needs < 0.75 of the port-bound per-slice MMA time at TD = 1
+    blk = ifnet.IFBlock(3, 11, 64)
+    d = blk.layers()[2]._structure_desc()
+    c1, c4 = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    assert L.ofsv_conv_stack_selfcheck(ctypes.byref(d), 1, None, ctypes.byref(c1)) == 0
+    assert L.ofsv_conv_stack_selfcheck(ctypes.byref(d), 4, None, ctypes.byref(c4)) == 0
+    assert c4.value / 4 < 0.75 * c1.value, (c1.value, c4.value)
