@@ -190,6 +190,8 @@ typedef struct ofsv_conv_desc {
                                        * tensor whose border sub-cells the caller keeps zero.  A Conv(k<=4, s=2, p=1) over the
                                        * logical tensor is then a stride-1 conv with tap offsets in {0,1}^nd over 2^nd*Cout_s
                                        * channels: kernel index k = 2*offset + sub-cell. */
+  int32_t out_shuffle_hfast;          /* with out_shuffle (fp32 output): write the depth-to-space tensor H-FASTEST, [N][2Do][2Wo][2Ho][8]
+                                       * (= OFSV_STATE_DWH8 of ofsv_block_stage_3d; the residual state is read in the same layout) */
 } ofsv_conv_desc;
 
 /* SIMT (CUDA-core, fp32 accumulate) engine: exact-order validation path and small-channel layers.
@@ -253,11 +255,20 @@ int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, co
  * head [N][D/sh][H/sh][W/sh][8] fp32; fm_prev NULL for block0; merged / mask_sig (N,1,D,H,W) optional;
  * scale_next in {0: no packed output, 1, 2}: pack_out = the next block's conv0 input, bf16 [N][D/sn][H/sn][W/sn][16], or with
  * pack_s2d = 1 its shifted space-to-depth form (ofsv_conv_desc.out_s2d) so that conv0 (k=4,s=2,p=1) runs as a stride-1
- * conv on ofsv_conv_halo. */
+ * conv on ofsv_conv_halo.
+ *
+ * state_layout: how head / fm_prev / fm_out are stored.
+ *   OFSV_STATE_DHW8 : [N][D][H][W][8]  (W fastest; csrc/block_stage.cu: state tiles staged through shared memory)
+ *   OFSV_STATE_DWH8 : [N][D][W][H][8]  (H fastest; csrc/block_stage_hfast.cu).  The reference warp rotates axes, so its gathers are
+ *                     only coalesced with lanes along H; with H as the state's fastest spatial axis one thread owns one voxel for
+ *                     the whole stage and reads / writes its 32 B of state with single 256-bit coalesced accesses.  The depth-to-
+ *                     space head conv writes this layout when ofsv_conv_desc.out_shuffle_hfast is set. */
+#define OFSV_STATE_DHW8 0
+#define OFSV_STATE_DWH8 1
 int ofsv_block_stage_3d(const float* head, const float* fm_prev, const float* img0, const float* img1, const float* lin_h,
                         const float* lin_d, const float* lin_w, float* fm_out, float* merged, float* mask_sig,
                         void* pack_out, int N, int D, int H, int W, int scale_head, int scale_next, int pack_s2d,
-                        int ref_mode, void* stream);
+                        int ref_mode, int state_layout, void* stream);
 
 #ifdef __cplusplus
 }

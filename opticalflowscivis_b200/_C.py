@@ -12,6 +12,7 @@ REF_CPU, REF_CUDA = 0, 1
 F32, BF16 = 0, 1
 MAX_TAPS = 64
 WL_TAP, WL_STACK = 0, 1
+STATE_DHW8, STATE_DWH8 = 0, 1
 
 
 class ConvDesc(ctypes.Structure):
@@ -29,6 +30,7 @@ class ConvDesc(ctypes.Structure):
         ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
         ("out_shuffle", ctypes.c_int32),
         ("out_s2d", ctypes.c_int32),
+        ("out_shuffle_hfast", ctypes.c_int32),
     ]
 
 
@@ -66,7 +68,7 @@ _SIGS = {
     "ofsv_conv_halo_describe": (_I, [ctypes.POINTER(ConvDesc), ctypes.c_char_p, _I]),
     "ofsv_set_tuning": (_I, [ctypes.c_char_p, _I]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 8 + [_P]),
+    "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 9 + [_P]),
 }
 EXPORTS = tuple(_SIGS)
 

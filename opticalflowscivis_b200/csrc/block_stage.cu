@@ -363,6 +363,11 @@ static int launch_stage(const StagePtrs& q, const Warp3dParams& P, dim3 grid, cu
   return OFSV_OK;
 }
 
+// block_stage_hfast.cu: the same stage on the H-fastest state layout
+int block_stage_hfast(const float* head, const float* fm_prev, const float* img0, const float* img1, const float* lin_h,
+                      const float* lin_d, const float* lin_w, float* fm_out, float* merged, float* mask_sig, void* pack_out, int N,
+                      int D, int H, int W, int scale_head, int scale_next, int pack_s2d, int ref_mode, cudaStream_t st);
+
 }  // namespace ofsv
 
 using namespace ofsv;
@@ -370,7 +375,8 @@ using namespace ofsv;
 extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, const float* img0, const float* img1,
                                    const float* lin_h, const float* lin_d, const float* lin_w, float* fm_out, float* merged,
                                    float* mask_sig, void* pack_out, int N, int D, int H, int W, int scale_head,
-                                   int scale_next, int pack_s2d, int ref_mode, void* stream) {
+                                   int scale_next, int pack_s2d, int ref_mode, int state_layout, void* stream) {
+  OFSV_REQUIRE(state_layout == OFSV_STATE_DHW8 || state_layout == OFSV_STATE_DWH8, "ofsv_block_stage_3d: bad state_layout");
   OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < (1ll << 28), "ofsv_block_stage_3d: bad shape (D*H*W must be < 2^28)");
   OFSV_REQUIRE(scale_head == 0 || scale_head == 1 || scale_head == 2 || scale_head == 4, "ofsv_block_stage_3d: scale_head %d not in {0,1,2,4}", scale_head);
   OFSV_REQUIRE(scale_next == 0 || scale_next == 1 || scale_next == 2, "ofsv_block_stage_3d: scale_next %d not in {0,1,2}", scale_next);
@@ -386,6 +392,9 @@ extern "C" int ofsv_block_stage_3d(const float* head, const float* fm_prev, cons
   OFSV_REQUIRE((scale_next == 0) == (pack_out == nullptr), "ofsv_block_stage_3d: pack_out must be given iff scale_next != 0");
   OFSV_REQUIRE((!head || aligned16(head)) && (!fm_out || aligned16(fm_out)) && (!fm_prev || aligned16(fm_prev)) && (!pack_out || aligned16(pack_out)),
                "ofsv_block_stage_3d: head / fm / pack_out must be 16-byte aligned");
+  if (state_layout == OFSV_STATE_DWH8)
+    return block_stage_hfast(head, fm_prev, img0, img1, lin_h, lin_d, lin_w, fm_out, merged, mask_sig, pack_out, N, D, H, W, scale_head,
+                             scale_next, pack_s2d, ref_mode, (cudaStream_t)stream);
   const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
   const dim3 grid((unsigned)cdiv(W, BS_W), (unsigned)cdiv(H, BS_H), (unsigned)(N * cdiv(D, BS_DZ)));
   if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }

@@ -485,6 +485,7 @@ int ofsv::conv_halo_ring(const ofsv_conv_desc* d, const void* x, const void* w, 
                "ofsv_conv_halo(ring): pointers must be 16-byte aligned");
   if (d->in_dtype != OFSV_BF16) { set_error("ofsv_conv_halo(ring): activations must be bf16"); return OFSV_ENOSUP; }
   if (d->in_stride != 1) { set_error("ofsv_conv_halo(ring): in_stride must be 1"); return OFSV_ENOSUP; }
+  if (d->out_shuffle_hfast) { set_error("ofsv_conv_halo(ring): H-fastest depth-to-space output is implemented by the stacked kernel only"); return OFSV_ENOSUP; }
   if (d->Cout_w > 128) { set_error("ofsv_conv_halo(ring): Cout_w=%d > 128", d->Cout_w); return OFSV_ENOSUP; }
   if (d->has_residual && d->out_dtype != OFSV_BF16 && !d->out_shuffle) { set_error("ofsv_conv_halo(ring): residual needs a bf16 output"); return OFSV_ENOSUP; }
   if (d->has_residual && d->out_shuffle && d->out_dtype != OFSV_F32) { set_error("ofsv_conv_halo(ring): depth-to-space residual (flow/mask state) is fp32"); return OFSV_ENOSUP; }

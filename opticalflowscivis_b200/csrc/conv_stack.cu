@@ -163,10 +163,15 @@ struct SkParams {
   int tiles_w, tiles_h, tiles_d;
   int nb, plane_stride, b_stride, stg_stride, stg_rowb;
   int nbuf, acc_stride;
-  int has_prelu, has_residual, out_f32, shuffle, out_s2d, epi_mode;
+  int has_prelu, has_residual, out_f32, shuffle, out_s2d, epi_mode, hfast, probe;
   uint16_t group_first[SK_MAX_PASS + 1];
   SkGroupRec groups[SK_MAX_GROUPS];
-  uint32_t ops[SK_MAX_OPS][2];   // [0] = A offset inside a plane (>>4) | plane q << 16 ; [1] = B offset (>>4) | col/8 << 13 | N/16 << 20 | fresh << 26
+  // MMA list, READY TO USE: the single issuing thread runs a dependent chain of uniform-datapath instructions per MMA (one warp
+  // cannot hide their latency: ~25 field extractions / multiplies per op cost ~200 cycles against ~130 of tensor work), so every
+  // field is a whole 32-bit word — per op the issuer does three independent adds.
+  //   [0] A descriptor offset ((plane q, chunk 0) + in-plane tap, >> 4)   [1] B descriptor offset inside the stage (>> 4)
+  //   [2] TMEM column offset | fresh << 16                               [3] instruction descriptor (N of this run)
+  uint32_t ops[SK_MAX_OPS][4];
 };
 struct SkOutMaps { CUtensorMap m[8]; };
 
@@ -249,6 +254,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
             for (int g = p.group_first[pass]; g < p.group_first[pass + 1]; ++g, ++bcount) {
               const SkGroupRec gr = p.groups[g];
               if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[bs], bphase ^ 1u, 64);
+#ifdef OFSV_STACK_PROBE
+              if ((p.probe & 1) && st != (int)blockIdx.x) { mbar_expect_tx(&b_full[bs], 0); if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; } continue; }
+#endif
               mbar_expect_tx(&b_full[bs], gr.nslots * slot_bytes);
               const int row = (int)gr.row0 + kc * gr.nslots * p.Cout_w;
               for (int s = 0; s < gr.nslots; ++s)
@@ -272,6 +280,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
           if (use > 0) mbar_wait(&plane_empty[set * p.nkc + kc], (use - 1) & 1u, 64);   // previous user's MMAs have read them
           for (int q = 0; q < p.np; ++q) {
             const int idx = (set * p.np + q) * p.nkc + kc;
+#ifdef OFSV_STACK_PROBE
+            if ((p.probe & 2) && it > 0) { mbar_expect_tx(&plane_full[idx], 0); continue; }
+#endif
             mbar_expect_tx(&plane_full[idx], SK_HP_ROWS * ROWB);
             tma_load_5d(&tmA, &plane_full[idx], sP + (size_t)idx * p.plane_stride, kc * KC, tx * SK_HT_W - 1, ty * SK_HT_H - 1,
                         tz * p.td + p.dzmin + q, n);
@@ -282,7 +293,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
   } else if (warp == 1) {
     // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
     const uint32_t leader = elect_one_sync();
-    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a_hi = kmajor_desc_hi<KC>(SK_HP_W * ROWB);      // 8-row groups of A are 10 halo rows apart
     const uint32_t b_hi = kmajor_desc_hi<KC>(8 * ROWB);
     const uint32_t plane_lo0 = kmajor_desc_lo(smem_u32(sP)), plane_step = (uint32_t)p.plane_stride >> 4;
@@ -305,15 +315,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
             tcgen05_fence_after();
             if (leader) {
               const uint32_t b_lo = b_lo0 + bs * b_step;
-              uint32_t w0 = p.ops[gr.op_begin][0], w1 = p.ops[gr.op_begin][1];
+              const uint32_t fresh_ok = kc == 0 ? 1u : 0u;
+#ifdef OFSV_STACK_PROBE
+              if (!(p.probe & 8))
+#endif
+#pragma unroll 2
               for (int i = 0; i < gr.nops; ++i) {
-                const uint32_t c0 = w0, c1 = w1;
-                if (i + 1 < gr.nops) { w0 = p.ops[gr.op_begin + i + 1][0]; w1 = p.ops[gr.op_begin + i + 1][1]; }
-                const uint32_t a = a_kc + (c0 >> 16) * (uint32_t)p.nkc * plane_step + (c0 & 0xFFFFu);
-                const uint32_t b = b_lo + (c1 & 0x1FFFu);
-                const uint32_t dcol = acc0 + ((c1 >> 13) & 0x7Fu) * 8u;
-                const uint32_t idesc = idesc0 | (((c1 >> 20) & 0x3Fu) << 18);       // N >> 3 = 2 * (N / 16) at bit 17
-                const uint32_t acc = (kc == 0 && ((c1 >> 26) & 1u)) ? 0u : 1u;
+                const uint32_t* o = p.ops[gr.op_begin + i];
+                const uint32_t a = a_kc + o[0], b = b_lo + o[1], w2 = o[2], idesc = o[3];
+                const uint32_t dcol = acc0 + (w2 & 0xFFFFu);
+                const uint32_t acc = (fresh_ok & (w2 >> 16)) ^ 1u;
                 umma_bf16_lohi(dcol, a, a_hi, b, b_hi, idesc, acc);
 #pragma unroll
                 for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dcol, a + 2 * k, a_hi, b + 2 * k, b_hi, idesc, 1u);
@@ -363,6 +374,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
         const uint32_t acc0 = tmem_base + buf * p.acc_stride + lane_tm;
         mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 128);
         tcgen05_fence_after();
+#ifdef OFSV_STACK_PROBE
+        if (!(p.probe & 4))
+#endif
         for (int blk = half; blk < nblk; blk += 2) {
           const int pp = blk / p.td, j = blk - pp * p.td;
           if (j >= nj) continue;
@@ -432,7 +446,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
             // ---- fp32 depth-to-space heads: columns [parity (z,y,x)][8 ch]; this warp's 4 x 8 rows cover 8 (y) x 16 (x) x nz output
             //      voxels = one {32 floats, 4, 8, 1} box per z parity of the [N][Dy][Hy][Wy/4][32] view of the state tensor
             auto shuf_off = [&](int par) -> int64_t {
-              return ((((int64_t)n * p.Dy + oz * (p.nd == 3 ? 2 : 1) + ((par >> 2) & 1)) * p.Hy + oy * 2 + ((par >> 1) & 1)) * p.Wy + ox * 2 + (par & 1)) * 8;
+              const int zz = oz * (p.nd == 3 ? 2 : 1) + ((par >> 2) & 1), yy = oy * 2 + ((par >> 1) & 1), xx = ox * 2 + (par & 1);
+              if (p.hfast) return ((((int64_t)n * p.Dy + zz) * p.Wy + xx) * p.Hy + yy) * 8;       // [N][D][W][H][8]
+              return ((((int64_t)n * p.Dy + zz) * p.Hy + yy) * p.Wy + xx) * 8;
             };
             float4 fn[4];
             auto load_state = [&](int c) {
@@ -471,17 +487,32 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
                 __syncwarp();
                 store_pending = false;
               }
-              const uint32_t R = (uint32_t)(((2 * (lane >> 3) + cy) << 2) + (rx >> 1));
-              const uint32_t rowa = stg + R * 128u, sw = R & 7u, u0 = (uint32_t)(rx & 1) * 4u;
-              sk_sts128(rowa + (((u0 + 0) ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-              sk_sts128(rowa + (((u0 + 1) ^ sw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
-              sk_sts128(rowa + (((u0 + 2) ^ sw) << 4), __float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
-              sk_sts128(rowa + (((u0 + 3) ^ sw) << 4), __float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+              if (!p.hfast) {
+                const uint32_t R = (uint32_t)(((2 * (lane >> 3) + cy) << 2) + (rx >> 1));
+                const uint32_t rowa = stg + R * 128u, sw = R & 7u, u0 = (uint32_t)(rx & 1) * 4u;
+                sk_sts128(rowa + (((u0 + 0) ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                sk_sts128(rowa + (((u0 + 1) ^ sw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                sk_sts128(rowa + (((u0 + 2) ^ sw) << 4), __float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
+                sk_sts128(rowa + (((u0 + 3) ^ sw) << 4), __float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+              } else {
+                // H-fastest state [N][D][W][H/4][32 floats]: box {32, 2 (quarters of the warp's 8 y'), 16 (x'), 1}; staged row
+                // R = x' * 2 + (y' >> 2), this voxel's 8 floats = units (y' & 3) * 2 + {0, 1}; x parity 0 / 1 are different rows
+                const uint32_t yl = (uint32_t)(2 * (lane >> 3) + cy), u0 = (yl & 3u) * 2u;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const uint32_t R = (uint32_t)(2 * rx + e) * 2u + (yl >> 2);
+                  const uint32_t rowa = stg + R * 128u, sw = R & 7u;
+                  sk_sts128(rowa + (((u0 + 0) ^ sw) << 4), __float_as_uint(v[8 * e]), __float_as_uint(v[8 * e + 1]), __float_as_uint(v[8 * e + 2]), __float_as_uint(v[8 * e + 3]));
+                  sk_sts128(rowa + (((u0 + 1) ^ sw) << 4), __float_as_uint(v[8 * e + 4]), __float_as_uint(v[8 * e + 5]), __float_as_uint(v[8 * e + 6]), __float_as_uint(v[8 * e + 7]));
+                }
+              }
               if (cy == 1) {
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  tma_store_5d(&tmO.m[0], stg, 0, tx * (SK_HT_W / 2), 2 * (ty * SK_HT_H + 4 * qq), p.nd == 3 ? 2 * oz + cz : 0, n);
+                  const int zc = p.nd == 3 ? 2 * oz + cz : 0;
+                  if (!p.hfast) tma_store_5d(&tmO.m[0], stg, 0, tx * (SK_HT_W / 2), 2 * (ty * SK_HT_H + 4 * qq), zc, n);
+                  else tma_store_5d(&tmO.m[0], stg, 0, ty * (SK_HT_H / 2) + 2 * qq, tx * (2 * SK_HT_W), zc, n);
                   tma_store_commit();
                 }
                 store_pending = true;
@@ -494,7 +525,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
               return ((((int64_t)n * p.Dy + oz * p.out_stride + pz) * p.Hy + oy * p.out_stride + py) * p.Wy + ox * p.out_stride + px) * p.Cout_s;
             };
             auto shuf_off = [&](int par) -> int64_t {
-              return ((((int64_t)n * p.Dy + oz * (p.nd == 3 ? 2 : 1) + ((par >> 2) & 1)) * p.Hy + oy * 2 + ((par >> 1) & 1)) * p.Wy + ox * 2 + (par & 1)) * p.Cout_s;
+              const int zz = oz * (p.nd == 3 ? 2 : 1) + ((par >> 2) & 1), yy = oy * 2 + ((par >> 1) & 1), xx = ox * 2 + (par & 1);
+              if (p.hfast) return ((((int64_t)n * p.Dy + zz) * p.Wy + xx) * p.Hy + yy) * p.Cout_s;
+              return ((((int64_t)n * p.Dy + zz) * p.Hy + yy) * p.Wy + xx) * p.Cout_s;
             };
             for (int c = 0; c < nch; ++c) {
               const int c0 = c << 4;
@@ -596,7 +629,7 @@ static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkC
   // epilogue candidates: the TMA-store form of this layer type (if it has one), then per-thread stores
   int epis[2], nepi = 0;
   if (g_stack_epi.load(std::memory_order_relaxed) != 0) {
-    if (d->out_shuffle && d->out_dtype == OFSV_F32 && d->Wy % 4 == 0 && !d->has_prelu) epis[nepi++] = SK_EPI_TMA_SHUF;
+    if (d->out_shuffle && d->out_dtype == OFSV_F32 && (d->out_shuffle_hfast ? d->Hy : d->Wy) % 4 == 0 && !d->has_prelu) epis[nepi++] = SK_EPI_TMA_SHUF;
     else if (!d->out_shuffle && !d->out_s2d && d->out_dtype == OFSV_BF16 && (d->Cout_s * 2) % 32 == 0 && d->Cout_w == d->Cout_s) epis[nepi++] = SK_EPI_TMA_ROWS;
   }
   epis[nepi++] = SK_EPI_DIRECT;
@@ -801,6 +834,10 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     set_error("ofsv_conv_halo: bad space-to-depth output configuration");
     return OFSV_EINVAL;
   }
+  if (d->out_shuffle_hfast && (!d->out_shuffle || d->out_dtype != OFSV_F32)) {
+    set_error("ofsv_conv_halo: out_shuffle_hfast needs the fp32 depth-to-space output");
+    return OFSV_EINVAL;
+  }
   for (int i = 0; i < d->nphase * d->ntaps; ++i) {
     const int8_t* o = d->tap_off[i];
     if (o[0] < -1 || o[0] > 1 || o[1] < -1 || o[1] > 1 || o[2] < -1 || o[2] > 1) {
@@ -828,7 +865,10 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   P.nb = cfg.nb; P.plane_stride = cfg.plane_stride; P.b_stride = cfg.b_stride; P.stg_stride = cfg.stg_stride; P.stg_rowb = cfg.stg_rowb;
   P.nbuf = cfg.nbuf; P.acc_stride = 256;
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
-  P.shuffle = d->out_shuffle; P.out_s2d = d->out_s2d; P.epi_mode = cfg.epi_mode;
+  P.shuffle = d->out_shuffle; P.out_s2d = d->out_s2d; P.epi_mode = cfg.epi_mode; P.hfast = d->out_shuffle_hfast;
+#ifdef OFSV_STACK_PROBE   // probe builds only (tests/ab_build.sh): timing experiments that produce WRONG results; never in the shipped library
+  { const char* e = getenv("OFSV_STACK_PROBE_BITS"); P.probe = e ? atoi(e) : 0; }
+#endif
   {
     SkOp ops[SK_MAX_OPS];
     int op_first[SK_MAX_GROUPS + 1];
@@ -841,14 +881,16 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
       P.groups[g].nops = (uint8_t)(op_first[g + 1] - op_first[g]);
       P.groups[g].nslots = (uint8_t)pl.g[g].nslots;
     }
+    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);   // fp32 accumulate, bf16 x bf16, K-major, M = 128
     for (int i = 0; i < nops; ++i) {
       const SkOp& o = ops[i];
       const uint32_t a_off = (uint32_t)(((o.oy + 1) * SK_HP_W + (o.ox + 1)) * ROWB) >> 4;
-      const uint32_t b_off = (uint32_t)(o.slot0 * d->Cout_w * ROWB) >> 4;
-      const uint32_t col8 = (uint32_t)(o.col0 * d->Cout_w) >> 3, n16 = (uint32_t)(o.nsl * d->Cout_w) >> 4;
-      OFSV_REQUIRE(b_off < 0x2000u && col8 < 0x80u && n16 <= 16u, "ofsv_conv_halo: internal error (op encoding)");
-      P.ops[i][0] = a_off | ((uint32_t)o.q << 16);
-      P.ops[i][1] = b_off | (col8 << 13) | (n16 << 20) | ((uint32_t)(o.fresh ? 1 : 0) << 26);
+      const uint32_t ncols = (uint32_t)(o.nsl * d->Cout_w);
+      P.ops[i][0] = a_off + (uint32_t)o.q * (uint32_t)pl.nkc * ((uint32_t)cfg.plane_stride >> 4);
+      P.ops[i][1] = (uint32_t)(o.slot0 * d->Cout_w * ROWB) >> 4;
+      P.ops[i][2] = (uint32_t)(o.col0 * d->Cout_w) | ((uint32_t)(o.fresh ? 1 : 0) << 16);
+      P.ops[i][3] = idesc0 | ((ncols >> 3) << 17);
+      OFSV_REQUIRE(ncols <= 256 && o.col0 * d->Cout_w + ncols <= 512, "ofsv_conv_halo: internal error (op encoding)");
     }
   }
   const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
@@ -897,9 +939,12 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     }
   } else if (cfg.epi_mode == SK_EPI_TMA_SHUF) {
     // state tensor [N][Dy][Hy][Wy][8] fp32 viewed as [N][Dy][Hy][Wy/4][32 floats]
-    const cuuint64_t gdim[5] = {32, (cuuint64_t)(d->Wy / 4), (cuuint64_t)d->Hy, (cuuint64_t)d->Dy, (cuuint64_t)d->N};
-    const cuuint64_t gstr[4] = {128, (cuuint64_t)d->Wy * 32, (cuuint64_t)d->Wy * 32 * d->Hy, (cuuint64_t)d->Wy * 32 * d->Hy * d->Dy};
-    const cuuint32_t box[5] = {32, 4, 8, 1, 1};
+    // ... or, H-fastest, [N][Dy][Wy][Hy][8] viewed as [N][Dy][Wy][Hy/4][32 floats]
+    const bool hf = d->out_shuffle_hfast != 0;
+    const cuuint64_t row = (cuuint64_t)(hf ? d->Hy : d->Wy) * 32, plane = row * (hf ? d->Wy : d->Hy);
+    const cuuint64_t gdim[5] = {32, (cuuint64_t)((hf ? d->Hy : d->Wy) / 4), (cuuint64_t)(hf ? d->Wy : d->Hy), (cuuint64_t)d->Dy, (cuuint64_t)d->N};
+    const cuuint64_t gstr[4] = {128, row, plane, plane * d->Dy};
+    const cuuint32_t box[5] = {32, (cuuint32_t)(hf ? 2 : 4), (cuuint32_t)(hf ? 16 : 8), 1, 1};
     CUresult r = encode(&tmO.m[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled(state) failed with %d", (int)r); return OFSV_ECUDA; }

@@ -157,6 +157,7 @@ class _Layer:
         d.out_dtype = _C.F32 if self.out_f32 else act_dtype
         d.out_shuffle = self.shuffle
         d.out_s2d = int(self.out_s2d)
+        d.out_shuffle_hfast = 0
         return d, osp
 
 
@@ -310,10 +311,11 @@ class IFBlock(nn.Module):
         """True when the final heads run as the depth-to-space conv whose epilogue can do `fm = fm_prev + head`."""
         return engine == "tc" and USE_HALO and USE_SHUFFLE_HEADS
 
-    def run(self, xin, n, in_sp, act_dtype, engine, s2d_in=False, state_prev=None):
+    def run(self, xin, n, in_sp, act_dtype, engine, s2d_in=False, state_prev=None, hfast=False):
         """xin: packed channels-last block input [N][in_sp][16] (or its shifted space-to-depth form when s2d_in).
         Returns head [N][in_sp][8] fp32 — or, with `state_prev` ([N][in_sp][8] fp32 flow/mask state, scale-1 block only),
-        the accumulated state state_prev + head written by the head conv's epilogue."""
+        the accumulated state state_prev + head written by the head conv's epilogue.  hfast (3-D depth-to-space heads only):
+        head / state are H-fastest, [N][D][W][H][8] (ofsv_conv_desc.out_shuffle_hfast)."""
         L = self.layers()
         tdt = torch.float32 if act_dtype == _C.F32 else torch.bfloat16
         x, sp, skip = xin, in_sp, None
@@ -331,7 +333,12 @@ class IFBlock(nn.Module):
                     raise RuntimeError("state accumulation needs the depth-to-space head conv")
                 d.has_residual = 1
             odt = torch.float32 if lay.out_f32 else tdt
-            if lay.out_s2d:
+            if li == 11 and hfast:
+                if not lay.shuffle or self.nd != 3:
+                    raise RuntimeError("the H-fastest state layout needs the 3-D depth-to-space head conv")
+                d.out_shuffle_hfast = 1
+                y = torch.empty((n, osp[0], osp[2], osp[1], lay.cout_s), device=x.device, dtype=odt)
+            elif lay.out_s2d:
                 y = ops.workspace(("conv0", id(self)), lay.out_shape(n, osp), odt, x.device)
             else:
                 y = torch.empty(lay.out_shape(n, osp), device=x.device, dtype=odt)
@@ -374,6 +381,7 @@ class IFNet(nn.Module):
         self.only_last = False
         self.fuse_state_accumulate = True # scale-1 block: `flow += flow_d, mask += mask_d` inside the head conv's epilogue
         self.fuse_output_stage = True     # 3-D bf16: ofsv_block_stage_3d instead of head_upsample_add + warp_blend + pack
+        self.state_hfast = True           # fused stage on the H-fastest state layout [N][D][W][H][8] (csrc/block_stage_hfast.cu)
 
     def set_precision(self, precision: str, engine: str = "auto"):
         """precision 'bf16' (tensor-core operands, fp32 accumulate; flow/mask accumulators and heads in fp32) or
@@ -435,17 +443,18 @@ class IFNet(nn.Module):
             in_sp = tuple(v // s for v in sp)
             # scale-1 block on the halo engine: the head conv's epilogue accumulates the state (fm = fm_prev + head)
             acc_state = fused and s == 1 and fm is not None and self.fuse_state_accumulate and blk.can_accumulate_state(eng)
+            hfast = fused and self.state_hfast and blk.can_accumulate_state(eng)
             head = blk.run(xin, n, ((1,) + in_sp) if nd == 2 else in_sp, act, eng, s2d_in=s2d,
-                           state_prev=fm if acc_state else None)
+                           state_prev=fm if acc_state else None, hfast=hfast)
             xin = None
             if fused:
                 # one pass over the channels-last state: resize + accumulate + warp x2 (+ blend) (+ the next block's input)
                 s_next = 0 if last else (scales[i + 1] if scales[i + 1] in (1, 2) else 0)
                 if acc_state:
-                    fm, mg, ms, xin = ops.block_stage_3d(None, head, img0, img1, 0, s_next, want_out, want_out, pack_s2d=s2d)
+                    fm, mg, ms, xin = ops.block_stage_3d(None, head, img0, img1, 0, s_next, want_out, want_out, pack_s2d=s2d, hfast=hfast)
                 else:
-                    fm, mg, ms, xin = ops.block_stage_3d(head, fm, img0, img1, s, s_next, want_out, want_out, pack_s2d=s2d)
-                flow, mask = ops.state_views(fm)
+                    fm, mg, ms, xin = ops.block_stage_3d(head, fm, img0, img1, s, s_next, want_out, want_out, pack_s2d=s2d, hfast=hfast)
+                flow, mask = ops.state_views(fm, hfast)
                 if not last and xin is None:          # next scale not fusable (4): fall back to the separate builder
                     flow, mask = flow.contiguous(), mask.contiguous()
                     w0, w1, _, _ = ops.warp_blend(img0, img1, flow, None, want_merged=False, want_mask=False)

@@ -421,20 +421,26 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
     return flow, mask
 
 
-def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merged, want_mask, pack_s2d=False, key="xin"):
-    """Fused 3-D block output stage on the channels-last state (ofsv_block_stage_3d).  head [N][D/sh][H/sh][W/sh][8] fp32,
-    fm_prev [N][D][H][W][8] fp32 or None.  scale_head = 0: fm_prev already holds the accumulated state (the head conv's
-    epilogue added the head), only warp / blend / pack run.  Returns (fm, merged|None, mask_sig|None, next_block_input|None)."""
+def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merged, want_mask, pack_s2d=False, key="xin", hfast=False):
+    """Fused 3-D block output stage on the channels-last state (ofsv_block_stage_3d).  State layout: [N,D,H,W,8] fp32, or with
+    `hfast` the H-fastest [N,D,W,H,8] (_C.STATE_DWH8) that csrc/block_stage_hfast.cu works on; `head` is the block's head at
+    1/scale_head resolution in the same layout, fm_prev the previous state or None.  scale_head = 0: fm_prev already holds the
+    accumulated state (the head conv's epilogue added the head), only warp / blend / pack run.
+    Returns (fm, merged|None, mask_sig|None, next_block_input|None)."""
     n, _, d, h, w = img0.shape
     dev = img0.device
+    st_shape = (n, d, w, h, 8) if hfast else (n, d, h, w, 8)
     if scale_head == 0:
         if head is not None or fm_prev is None:
             raise ValueError("block_stage_3d: scale_head = 0 takes the already accumulated state in fm_prev and no head")
-    elif head.dtype != torch.float32 or head.shape[-1] != 8 or not head.is_contiguous():
-        raise ValueError("block_stage_3d: head must be a contiguous fp32 [...,8] tensor")
-    if fm_prev is not None and (fm_prev.shape != (n, d, h, w, 8) or fm_prev.dtype != torch.float32 or not fm_prev.is_contiguous()):
-        raise ValueError("block_stage_3d: fm_prev must be a contiguous fp32 [N,D,H,W,8] tensor")
-    fm = torch.empty((n, d, h, w, 8), device=dev, dtype=torch.float32) if scale_head else None
+    else:
+        s = scale_head
+        hd_shape = (n, d // s, w // s, h // s, 8) if hfast else (n, d // s, h // s, w // s, 8)
+        if head.dtype != torch.float32 or tuple(head.shape) != hd_shape or not head.is_contiguous():
+            raise ValueError(f"block_stage_3d: head must be a contiguous fp32 {hd_shape} tensor, got {tuple(head.shape)}")
+    if fm_prev is not None and (tuple(fm_prev.shape) != st_shape or fm_prev.dtype != torch.float32 or not fm_prev.is_contiguous()):
+        raise ValueError(f"block_stage_3d: fm_prev must be a contiguous fp32 {st_shape} tensor")
+    fm = torch.empty(st_shape, device=dev, dtype=torch.float32) if scale_head else None
     mg = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_merged else None
     ms = torch.empty((n, 1, d, h, w), device=dev, dtype=torch.float32) if want_mask else None
     pk = None
@@ -448,13 +454,15 @@ def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merge
         _C.check(_C.lib().ofsv_block_stage_3d(_p(head), _p(fm_prev), _p(img0), _p(img1), _p(linspace_table(h, dev)),
                                               _p(linspace_table(d, dev)), _p(linspace_table(w, dev)), _p(fm), _p(mg), _p(ms),
                                               _p(pk), n, d, h, w, scale_head, scale_next, int(bool(pack_s2d) and scale_next != 0), _FLAVOR["mode"],
-                                              _stream()))
+                                              _C.STATE_DWH8 if hfast else _C.STATE_DHW8, _stream()))
     return (fm if scale_head else fm_prev), mg, ms, pk
 
 
-def state_views(fm):
-    """(flow (N,6,D,H,W), mask_logit (N,1,D,H,W)) as permuted VIEWS of the channels-last state [N,D,H,W,8]."""
-    return fm[..., :6].permute(0, 4, 1, 2, 3), fm[..., 6:7].permute(0, 4, 1, 2, 3)
+def state_views(fm, hfast=False):
+    """(flow (N,6,D,H,W), mask_logit (N,1,D,H,W)) as permuted VIEWS of the channels-last state ([N,D,H,W,8], or the H-fastest
+    [N,D,W,H,8] with `hfast`)."""
+    perm = (0, 4, 1, 3, 2) if hfast else (0, 4, 1, 2, 3)
+    return fm[..., :6].permute(*perm), fm[..., 6:7].permute(*perm)
 
 
 def conv_pack_weights(desc: "_C.ConvDesc", w_tap: torch.Tensor, layout: int) -> torch.Tensor:

@@ -362,20 +362,26 @@ def test_stacked_halo_engine_vs_tap_evaluator(nd, c):
             outs = {}
             for td in ((0, 1, 2, 4) if nd == 3 else (0,)):
                 for epi in (-1, 0):
-                    ops.set_tuning("stack_td", td)
-                    ops.set_tuning("stack_epilogue", epi)
-                    y = torch.full((2,) + osp + (lc.cout_s,), 7.0, device=_dev(), dtype=odt)
-                    rdev = None if res is None else res.to(_dev()).to(torch.float32 if with_state else torch.bfloat16)
-                    ops.conv(d, xin.to(_dev()).bfloat16(), ld.w_halo, ld.bias, ld.prelu, rdev, y, "halo")
-                    torch.cuda.synchronize()
-                    outs[(td, epi)] = y.float().cpu()
-            got = outs[(0, -1)]
+                    for hf in ((0, 1) if (lc.shuffle and nd == 3) else (0,)):      # H-fastest depth-to-space output [N][D][W][H][8]
+                        ops.set_tuning("stack_td", td)
+                        ops.set_tuning("stack_epilogue", epi)
+                        d.out_shuffle_hfast = hf
+                        y = torch.full((2,) + osp + (lc.cout_s,), 7.0, device=_dev(), dtype=odt)
+                        rdev = None if res is None else res.to(_dev()).to(torch.float32 if with_state else torch.bfloat16)
+                        if hf:
+                            y = y.permute(0, 1, 3, 2, 4).contiguous()
+                            rdev = None if rdev is None else rdev.permute(0, 1, 3, 2, 4).contiguous()
+                        ops.conv(d, xin.to(_dev()).bfloat16(), ld.w_halo, ld.bias, ld.prelu, rdev, y, "halo")
+                        torch.cuda.synchronize()
+                        outs[(td, epi, hf)] = (y.permute(0, 1, 3, 2, 4) if hf else y).float().cpu()
+            d.out_shuffle_hfast = 0
+            got = outs[(0, -1, 0)]
             if nd == 2:
                 got = got.view(ref.shape)
             err, scale_ = float((got - ref).abs().max()), float(ref.abs().max())
             assert err <= 3e-2 * max(1.0, scale_), (nd, c, li, err, scale_)
             for k, v in outs.items():
-                assert torch.equal(v, outs[(0, -1)]), (nd, c, li, k, float((v - outs[(0, -1)]).abs().max()))
+                assert torch.equal(v, outs[(0, -1, 0)]), (nd, c, li, k, float((v - outs[(0, -1, 0)]).abs().max()))
     finally:
         ops.set_tuning("stack_td", 0)
         ops.set_tuning("stack_epilogue", -1)
@@ -431,8 +437,8 @@ def test_model_inference_vs_oracle(nd, precision):
     else:
         assert merged.shape == img0.shape and len(flow) == 3 and mask.shape == img0.shape
         merged_l, r_merged_l, mask_l, r_mask_l = merged, r_merged, mask, r_mask
-    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).view(n, 2, nd, -1).sum(2).sqrt().mean()) for i in range(3)]
-    epe_max = float(((flow[2].cpu() - r_flow[2]) ** 2).view(n, 2, nd, -1).sum(2).sqrt().max())
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(n, 2, nd, -1).sum(2).sqrt().mean()) for i in range(3)]
+    epe_max = float(((flow[2].cpu() - r_flow[2]) ** 2).reshape(n, 2, nd, -1).sum(2).sqrt().max())
     d_merged = float((merged_l.cpu() - r_merged_l).abs().max())
     d_mask = float((mask_l.cpu() - r_mask_l).abs().max())
     p_ref, p_mine = _psnr(r_merged_l.numpy(), gt.numpy()), _psnr(_np(merged_l), gt.numpy())
@@ -463,7 +469,7 @@ def test_model3d_noncubic_and_small_volumes(sp, n):
     merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
     torch.cuda.synchronize()
     assert merged.shape == img0.shape and mask.shape == img0.shape and all(f.shape == (n, 6) + sp for f in flow)
-    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).view(n, 2, 3, -1).sum(2).sqrt().mean()) for i in range(3)]
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(n, 2, 3, -1).sum(2).sqrt().mean()) for i in range(3)]
     assert max(epe) <= 1e-2, epe
     assert float((merged.cpu() - r_merged).abs().max()) <= 3e-2
     # the fp32 validation engine on the same shape
@@ -569,9 +575,10 @@ def test_model_surface():
 
 @pytest.mark.parametrize("sh,sn,has_prev", [(4, 2, False), (2, 1, True), (1, 0, True), (1, 1, True), (2, 2, True), (4, 0, False)])
 @pytest.mark.parametrize("s2d", [False, True])
-def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d):
-    """ofsv_block_stage_3d (channels-last state) == head_upsample_add -> warp_blend -> pack_block_input (the unfused,
-    individually verified chain on planar tensors)."""
+@pytest.mark.parametrize("hfast", [False, True])
+def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d, hfast):
+    """ofsv_block_stage_3d (channels-last state, in both state layouts: [N,D,H,W,8] and the H-fastest [N,D,W,H,8]) ==
+    head_upsample_add -> warp_blend -> pack_block_input (the unfused, individually verified chain on planar tensors)."""
     from opticalflowscivis_b200 import _C, ops
     if s2d and sn == 0:
         pytest.skip("no packed output")
@@ -584,9 +591,10 @@ def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d):
     mprev = torch.randn((n, 1) + sp, generator=g).to(dev) if has_prev else None
     fm_prev = None
     if has_prev:
-        fm_prev = torch.cat((fprev, mprev, torch.zeros_like(mprev)), 1).permute(0, 2, 3, 4, 1).contiguous()
-    fm, mg, ms, pk = ops.block_stage_3d(head, fm_prev, img0, img1, sh, sn, True, True, pack_s2d=s2d, key="t")
-    flow, mask = ops.state_views(fm)
+        fm_prev = torch.cat((fprev, mprev, torch.zeros_like(mprev)), 1).permute((0, 2, 4, 3, 1) if hfast else (0, 2, 3, 4, 1)).contiguous()
+    head_in = head.permute(0, 1, 3, 2, 4).contiguous() if hfast else head
+    fm, mg, ms, pk = ops.block_stage_3d(head_in, fm_prev, img0, img1, sh, sn, True, True, pack_s2d=s2d, key="t", hfast=hfast)
+    flow, mask = ops.state_views(fm, hfast)
     assert flow.shape == (n, 6) + sp and mask.shape == (n, 1) + sp
     rflow, rmask = ops.head_upsample_add(head, fprev, mprev, 3, n, sp, sh)
     w0, w1, rmg, rms = ops.warp_blend(img0, img1, rflow, rmask)
@@ -600,10 +608,10 @@ def test_block_stage_fused_equals_unfused(sh, sn, has_prev, s2d):
     else:
         assert pk is None
     # outputs that are not requested are not produced
-    f2, a, b, _ = ops.block_stage_3d(head, fm_prev, img0, img1, sh, sn, False, False, pack_s2d=s2d, key="t")
+    f2, a, b, _ = ops.block_stage_3d(head_in, fm_prev, img0, img1, sh, sn, False, False, pack_s2d=s2d, key="t", hfast=hfast)
     assert a is None and b is None and torch.equal(f2, fm)
     # scale_head = 0: the state is already accumulated (head-conv epilogue did fm_prev + head); same warps / blend / pack
-    f3, mg3, ms3, pk3 = ops.block_stage_3d(None, fm, img0, img1, 0, sn, True, True, pack_s2d=s2d, key="t3")
+    f3, mg3, ms3, pk3 = ops.block_stage_3d(None, fm, img0, img1, 0, sn, True, True, pack_s2d=s2d, key="t3", hfast=hfast)
     assert f3 is fm and torch.equal(mg3, mg) and torch.equal(ms3, ms) and (pk is None or torch.equal(pk3, pk))
 
 
@@ -656,6 +664,10 @@ def test_model3d_fused_equals_unfused():
     e = m.inference(img0.to(_dev()), img1.to(_dev()))
     assert torch.equal(a[0], e[0]) and all(torch.equal(a[1][i], e[1][i]) for i in range(3))
     m.flownet.fuse_state_accumulate = True
+    m.flownet.state_hfast = False                                                   # the W-fastest state layout (block_stage.cu)
+    e2 = m.inference(img0.to(_dev()), img1.to(_dev()))
+    assert torch.equal(a[0], e2[0]) and all(torch.equal(a[1][i], e2[1][i]) for i in range(3)) and torch.equal(a[2], e2[2])
+    m.flownet.state_hfast = True
     # scale lists other than [4,2,1] (`scale=[1,1,1]` is the reference's commented alternative)
     m.flownet.fuse_output_stage = True
     c = m.inference(img0.to(_dev()), img1.to(_dev()), scale_list=[2, 4, 1])

@@ -140,7 +140,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/ofsv.h but not exported by libofsv.so"
     assert declared == set(_C.EXPORTS), declared ^ set(_C.EXPORTS)
     assert L.ofsv_version().startswith(b"ofsv")
-    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 6
+    assert ctypes.sizeof(_C.ConvDesc) == 4 * 18 + 4 * _C.MAX_TAPS + 4 * 7
 
 
 def test_validation_errors_launch_nothing():
@@ -151,7 +151,7 @@ def test_validation_errors_launch_nothing():
     assert b"null" in L.ofsv_last_error()
     assert L.ofsv_corr81_fwd_f32(null, null, null, 1, 0, 4, 4, 0.1, 0, 0, null) == _C.EINVAL
     assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, 0, null) == _C.EINVAL
-    assert L.ofsv_block_stage_3d(*([null] * 11), 1, 16, 16, 16, 3, 0, 0, 0, null) == _C.EINVAL
+    assert L.ofsv_block_stage_3d(*([null] * 11), 1, 16, 16, 16, 3, 0, 0, 0, 0, null) == _C.EINVAL
     assert L.ofsv_u8_to_f32(null, null, 16, 255.0, null) == _C.EINVAL
     assert L.ofsv_sq_err_f64(null, null, null, null, 1, 16, 1.0, null) == _C.EINVAL
     assert L.ofsv_ssim2d_f64(null, null, null, null, 1, 10, 32, 255.0, null) == _C.EINVAL      # smaller than the 11x11 window
