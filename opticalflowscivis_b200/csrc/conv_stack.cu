@@ -34,8 +34,8 @@
 namespace ofsv {
 
 constexpr int SK_HT_H = 16, SK_HT_W = 8, SK_HP_H = SK_HT_H + 2, SK_HP_W = SK_HT_W + 2, SK_HP_ROWS = SK_HP_H * SK_HP_W;
-constexpr int SK_MAX_GROUPS = 32, SK_MAX_OPS = 192, SK_MAX_SLOTS = 6, SK_MAX_PASS = 8;
-constexpr int SK_MAX_PBARS = 24, SK_MAX_KC = 4, SK_MAX_BST = 8;
+constexpr int SK_MAX_GROUPS = 32, SK_MAX_OPS = 224, SK_MAX_SLOTS = 6, SK_MAX_PASS = 8;
+constexpr int SK_MAX_PBARS = 24, SK_MAX_KC = 8, SK_MAX_RING = 8, SK_MAX_BST = 8;
 constexpr int SK_EPI_W0 = 4, SK_EPI_WARPS = 8;
 constexpr int SK_THREADS = 32 * (SK_EPI_W0 + SK_EPI_WARPS);   // warp 0 weights, 1 MMA issuer, 2 planes, 3 idle, 4..11 epilogue
 
@@ -105,46 +105,61 @@ static bool sk_make_plan(const ofsv_conv_desc* d, SkPlan* pl) {
   return true;
 }
 
-struct SkOp { uint8_t group, q, slot0, nsl, col0, fresh; int8_t oy, ox; };
+struct SkOp { uint8_t group, q, slot0, nsl, col0, fresh, issuer; int8_t oy, ox; };
 
-// MMA list for super-tile depth td: per group, per plane, greedy runs of (consecutive slots, consecutive column blocks, same
-// initialisation state).  Column block of (phase p, slice j) = p * td + j; slice j of plane q for a slot with dz = oz is
-// j = q + dzmin - oz.  Returns the number of ops or -1 when the table would overflow.
-static int sk_build_ops(const ofsv_conv_desc* d, const SkPlan& pl, int td, SkOp* ops, int* op_first /* [ngroups + 1] */) {
+constexpr int SK_NI = 2;      // MMA-issuing warps
+
+// The single thread that issues tcgen05.mma spends ~50 cycles of uniform-datapath work per op and the tensor queue it feeds is
+// shallow: with one issuer the convblocks lose a quarter of the tensor time to it and the small-N layers (N = 32 / 64 conv0)
+// run at 83 cycles per MMA against 42-48 of operand fetch.  So the column blocks of a pass are split in two halves, each owned
+// by ONE issuing warp (every accumulator still receives its MMAs from one thread, in the same order: results stay deterministic
+// and independent of the super-tile depth); runs never cross the boundary between the halves.
+static int sk_issuers(const SkPlan& pl, int td) { return pl.P * td >= 2 ? SK_NI : 1; }
+static int sk_block_issuer(const SkPlan& pl, int td, int col) { const int nblk = pl.P * td; return sk_issuers(pl, td) * col / nblk; }
+
+// MMA list for super-tile depth td: per group and issuer, per plane, greedy runs of (consecutive slots, consecutive column
+// blocks of one issuer, same initialisation state).  Column block of (phase p, slice j) = p * td + j; slice j of plane q for a
+// slot with dz = oz is j = q + dzmin - oz.  op_first[g * SK_NI + w] = first op of (group g, issuer w), ops of a group are
+// stored issuer-major.  Returns the number of ops or -1 when the table would overflow.
+static int sk_build_ops(const ofsv_conv_desc* d, const SkPlan& pl, int td, SkOp* ops, int* op_first /* [ngroups * SK_NI + 1] */) {
   const int np = td + pl.dzmax - pl.dzmin;
+  const int ni = sk_issuers(pl, td);
   int n = 0;
   for (int pass = 0; pass < pl.npass; ++pass) {
     bool init[64] = {false};
     for (int gi = pl.group_first[pass]; gi < pl.group_first[pass + 1]; ++gi) {
       const SkGroup& G = pl.g[gi];
-      op_first[gi] = n;
-      for (int q = 0; q < np; ++q) {
-        int s = 0;
-        while (s < G.nslots) {
-          const int j = q + pl.dzmin - G.slots[s].oz;
-          if (j < 0 || j >= td) { ++s; continue; }
-          const int col = G.slots[s].p * td + j;
-          const bool fresh = !init[col];
-          int len = 1;
-          while (s + len < G.nslots) {
-            const int j2 = q + pl.dzmin - G.slots[s + len].oz;
-            if (j2 < 0 || j2 >= td) break;
-            const int col2 = G.slots[s + len].p * td + j2;
-            if (col2 != col + len || (!init[col2]) != fresh || (len + 1) * d->Cout_w > 256) break;
-            ++len;
+      for (int w = 0; w < SK_NI; ++w) {
+        op_first[gi * SK_NI + w] = n;
+        if (w >= ni) continue;
+        for (int q = 0; q < np; ++q) {
+          int s = 0;
+          while (s < G.nslots) {
+            const int j = q + pl.dzmin - G.slots[s].oz;
+            const int col = G.slots[s].p * td + j;
+            if (j < 0 || j >= td || sk_block_issuer(pl, td, col) != w) { ++s; continue; }
+            const bool fresh = !init[col];
+            int len = 1;
+            while (s + len < G.nslots) {
+              const int j2 = q + pl.dzmin - G.slots[s + len].oz;
+              if (j2 < 0 || j2 >= td) break;
+              const int col2 = G.slots[s + len].p * td + j2;
+              if (col2 != col + len || sk_block_issuer(pl, td, col2) != w || (!init[col2]) != fresh || (len + 1) * d->Cout_w > 256) break;
+              ++len;
+            }
+            if (n == SK_MAX_OPS) return -1;
+            SkOp o;
+            o.group = (uint8_t)gi; o.q = (uint8_t)q; o.slot0 = (uint8_t)s; o.nsl = (uint8_t)len; o.col0 = (uint8_t)col; o.fresh = fresh;
+            o.issuer = (uint8_t)w; o.oy = (int8_t)G.oy; o.ox = (int8_t)G.ox;
+            ops[n++] = o;
+            for (int i = 0; i < len; ++i) init[col + i] = true;
+            s += len;
           }
-          if (n == SK_MAX_OPS) return -1;
-          SkOp o;
-          o.group = (uint8_t)gi; o.q = (uint8_t)q; o.slot0 = (uint8_t)s; o.nsl = (uint8_t)len; o.col0 = (uint8_t)col; o.fresh = fresh;
-          o.oy = (int8_t)G.oy; o.ox = (int8_t)G.ox;
-          ops[n++] = o;
-          for (int i = 0; i < len; ++i) init[col + i] = true;
-          s += len;
         }
       }
     }
   }
-  op_first[pl.ngroups] = n;
+  op_first[pl.ngroups * SK_NI] = n;
   return n;
 }
 
@@ -156,14 +171,14 @@ static double sk_mma_cycles(int N) {
 }
 
 // ---------------------------------------------------------------------------------------------------- device side
-struct SkGroupRec { uint32_t row0; uint16_t op_begin; uint8_t nops, nslots; };
+struct SkGroupRec { uint32_t row0; uint8_t op_begin[SK_NI], nops[SK_NI]; uint8_t nslots, pad[3]; };
 struct SkParams {
   int N, Do, Ho, Wo, Dy, Hy, Wy, Cout_s, Cout_w;
-  int out_stride, nd, nkc, td, np, dzmin, P, npass, nsets;
+  int out_stride, nd, nkc, td, np, dzmin, P, npass, nring;
   int tiles_w, tiles_h, tiles_d;
   int nb, plane_stride, b_stride, stg_stride, stg_rowb;
   int nbuf, acc_stride;
-  int has_prelu, has_residual, out_f32, shuffle, out_s2d, epi_mode, hfast, probe;
+  int has_prelu, has_residual, out_f32, shuffle, out_s2d, epi_mode, hfast, probe, b_resident, ni;
   uint16_t group_first[SK_MAX_PASS + 1];
   SkGroupRec groups[SK_MAX_GROUPS];
   // MMA list, READY TO USE: the single issuing thread runs a dependent chain of uniform-datapath instructions per MMA (one warp
@@ -171,7 +186,7 @@ struct SkParams {
   // field is a whole 32-bit word — per op the issuer does three independent adds.
   //   [0] A descriptor offset ((plane q, chunk 0) + in-plane tap, >> 4)   [1] B descriptor offset inside the stage (>> 4)
   //   [2] TMEM column offset | fresh << 16                               [3] instruction descriptor (N of this run)
-  uint32_t ops[SK_MAX_OPS][4];
+  alignas(16) uint32_t ops[SK_MAX_OPS][4];
 };
 struct SkOutMaps { CUtensorMap m[8]; };
 
@@ -201,14 +216,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROWB = KC * 2;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nplanes = p.nsets * p.np * p.nkc;
-  uint8_t* sP = smem;                                                  // [set][q][kc] halo plane chunks
+  const int nplanes = p.nring * p.np;
+  uint8_t* sP = smem;                                                  // [ring slot][q] halo plane chunks
   uint8_t* sB = sP + (size_t)nplanes * p.plane_stride;                 // [nb] weight stages
   uint8_t* sS = sB + (size_t)p.nb * p.b_stride;                        // [8 warps] epilogue staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)SK_EPI_WARPS * p.stg_stride);
-  uint64_t* plane_full = bars;                                         // [SK_MAX_PBARS]  index (set * np + q) * nkc + kc
-  uint64_t* plane_empty = plane_full + SK_MAX_PBARS;                   // [2 * SK_MAX_KC] index set * nkc + kc
-  uint64_t* b_full = plane_empty + 2 * SK_MAX_KC;                      // [SK_MAX_BST]
+  uint64_t* plane_full = bars;                                         // [SK_MAX_PBARS]  index ring slot * np + q
+  uint64_t* plane_empty = plane_full + SK_MAX_PBARS;                   // [SK_MAX_RING]   index ring slot
+  uint64_t* b_full = plane_empty + SK_MAX_RING;                        // [SK_MAX_BST]
   uint64_t* b_empty = b_full + SK_MAX_BST;                             // [SK_MAX_BST]
   uint64_t* acc_full = b_empty + SK_MAX_BST;                           // [2]
   uint64_t* acc_empty = acc_full + 2;                                  // [2]
@@ -225,9 +240,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < SK_MAX_PBARS; ++i) mbar_init(&plane_full[i], 1);
-    for (int i = 0; i < 2 * SK_MAX_KC; ++i) mbar_init(&plane_empty[i], 1);
-    for (int i = 0; i < SK_MAX_BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SK_EPI_WARPS); }
+    for (int i = 0; i < SK_MAX_RING; ++i) mbar_init(&plane_empty[i], p.ni);
+    for (int i = 0; i < SK_MAX_BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.ni); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], p.ni); mbar_init(&acc_empty[i], SK_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -248,12 +263,21 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
     if (lane == 0) {
       uint32_t bcount = 0, bs = 0, bphase = 0;
       const uint32_t slot_bytes = (uint32_t)p.Cout_w * ROWB;
+      if (p.b_resident) {
+        // the whole packed weight tensor fits next to the planes: loaded ONCE per CTA in its global order, no ring, no hand-shakes
+        // (a stage boundary costs the issuing thread ~370 cycles of barrier / commit latency — as much as the tensor work of a
+        //  2-slot stage of the 32-channel conv0 layers)
+        uint32_t nblk = 0;
+        for (int g = 0; g < ngroups_all; ++g) nblk += (uint32_t)p.groups[g].nslots * (uint32_t)p.nkc;
+        mbar_expect_tx(&b_full[0], nblk * slot_bytes);
+        for (uint32_t b = 0; b < nblk; ++b) tma_load_2d(&tmB, &b_full[0], sB + (size_t)b * slot_bytes, 0, (int)(b * (uint32_t)p.Cout_w));
+      } else
       for (int st = blockIdx.x; st < total; st += gridDim.x)
         for (int pass = 0; pass < p.npass; ++pass)
           for (int kc = 0; kc < p.nkc; ++kc)
             for (int g = p.group_first[pass]; g < p.group_first[pass + 1]; ++g, ++bcount) {
               const SkGroupRec gr = p.groups[g];
-              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[bs], bphase ^ 1u, 64);
+              if (bcount >= (uint32_t)p.nb) mbar_wait(&b_empty[bs], bphase ^ 1u, 0);
 #ifdef OFSV_STACK_PROBE
               if ((p.probe & 1) && st != (int)blockIdx.x) { mbar_expect_tx(&b_full[bs], 0); if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; } continue; }
 #endif
@@ -265,7 +289,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
             }
     }
   } else if (warp == 2) {
-    // ================= plane producer: the halo planes of (super-tile, chunk); slot set = super-tile parity =================
+    // ================= plane producer: the halo planes of chunk c = (super-tile, kc) go to ring slot c % nring =================
+    // (a slot is reused when the MMAs of the chunk nring places earlier have read it; layers with several passes keep every chunk
+    //  of a super-tile resident: nring is then a multiple of nkc and the slot is released after the last pass)
     if (lane == 0) {
       int it = 0;
       for (int st = blockIdx.x; st < total; st += gridDim.x, ++it) {
@@ -274,12 +300,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
         const int ty = r % p.tiles_h; r /= p.tiles_h;
         const int tz = r % p.tiles_d;
         const int n = r / p.tiles_d;
-        const int set = it % p.nsets;
-        const uint32_t use = (uint32_t)(it / p.nsets);
         for (int kc = 0; kc < p.nkc; ++kc) {
-          if (use > 0) mbar_wait(&plane_empty[set * p.nkc + kc], (use - 1) & 1u, 64);   // previous user's MMAs have read them
+          const uint32_t c = (uint32_t)(it * p.nkc + kc), slot = c % (uint32_t)p.nring, use = c / (uint32_t)p.nring;
+          if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1u, 0);
           for (int q = 0; q < p.np; ++q) {
-            const int idx = (set * p.np + q) * p.nkc + kc;
+            const int idx = (int)slot * p.np + q;
 #ifdef OFSV_STACK_PROBE
             if ((p.probe & 2) && it > 0) { mbar_expect_tx(&plane_full[idx], 0); continue; }
 #endif
@@ -290,8 +315,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
+  } else if (warp == 1 || (warp == 3 && p.ni > 1)) {
+    // ================= MMA issuers (warp 1: issuer 0, warp 3: issuer 1): warp-uniform control flow, one elected lane issues =========
+    const int iss = warp == 1 ? 0 : 1;
     const uint32_t leader = elect_one_sync();
     const uint32_t a_hi = kmajor_desc_hi<KC>(SK_HP_W * ROWB);      // 8-row groups of A are 10 halo rows apart
     const uint32_t b_hi = kmajor_desc_hi<KC>(8 * ROWB);
@@ -300,42 +326,52 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
     uint32_t bs = 0, bphase = 0, buf = 0, acc_use = 0;
     int it = 0;
     for (int st = blockIdx.x; st < total; st += gridDim.x, ++it) {
-      const int set = it % p.nsets;
-      const uint32_t use = (uint32_t)(it / p.nsets);
       for (int pass = 0; pass < p.npass; ++pass) {
-        if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1);
+        if (acc_use >= (uint32_t)p.nbuf) mbar_wait(&acc_empty[buf], ((acc_use / p.nbuf) - 1) & 1, 0);
         const uint32_t acc0 = tmem_base + buf * p.acc_stride;
         for (int kc = 0; kc < p.nkc; ++kc) {
+          const uint32_t c = (uint32_t)(it * p.nkc + kc), slot = c % (uint32_t)p.nring, use = c / (uint32_t)p.nring;
           if (pass == 0)                                             // first use of this chunk's planes in this super-tile
-            for (int q = 0; q < p.np; ++q) mbar_wait(&plane_full[(set * p.np + q) * p.nkc + kc], use & 1u);
-          const uint32_t a_kc = plane_lo0 + (uint32_t)(set * p.np * p.nkc + kc) * plane_step;
+            for (int q = 0; q < p.np; ++q) mbar_wait(&plane_full[(int)slot * p.np + q], use & 1u, 0);
+          const uint32_t a_kc = plane_lo0 + slot * (uint32_t)p.np * plane_step;
           for (int g = p.group_first[pass]; g < p.group_first[pass + 1]; ++g) {
             const SkGroupRec gr = p.groups[g];
-            mbar_wait(&b_full[bs], bphase);
+            if (!p.b_resident) mbar_wait(&b_full[bs], bphase, 0);
+            else if (it == 0 && pass == 0 && kc == 0 && g == 0) mbar_wait(&b_full[0], 0u, 0);
             tcgen05_fence_after();
             if (leader) {
-              const uint32_t b_lo = b_lo0 + bs * b_step;
+              const uint32_t b_lo = p.b_resident ? b_lo0 + (((uint32_t)gr.row0 + (uint32_t)(kc * gr.nslots * p.Cout_w)) * (uint32_t)ROWB >> 4)
+                                                 : b_lo0 + bs * b_step;
               const uint32_t fresh_ok = kc == 0 ? 1u : 0u;
 #ifdef OFSV_STACK_PROBE
               if (!(p.probe & 8))
 #endif
-#pragma unroll 2
-              for (int i = 0; i < gr.nops; ++i) {
-                const uint32_t* o = p.ops[gr.op_begin + i];
-                const uint32_t a = a_kc + o[0], b = b_lo + o[1], w2 = o[2], idesc = o[3];
-                const uint32_t dcol = acc0 + (w2 & 0xFFFFu);
-                const uint32_t acc = (fresh_ok & (w2 >> 16)) ^ 1u;
-                umma_bf16_lohi(dcol, a, a_hi, b, b_hi, idesc, acc);
+              {
+                // the op words come from the kernel-parameter bank (LDCU, ~100 cycles): they are fetched TWO ops ahead of their
+                // MMAs, otherwise the single issuing thread waits for a constant load per op (84 cycles per MMA measured on
+                // the N = 32 / 64 conv0 layers against 42-48 of operand fetch)
+                const int ob = gr.op_begin[iss], no = gr.nops[iss];
+                uint4 w_a = *reinterpret_cast<const uint4*>(p.ops[no > 0 ? ob : 0]);
+                uint4 w_b = *reinterpret_cast<const uint4*>(p.ops[no > 1 ? ob + 1 : 0]);
+                for (int i = 0; i < no; ++i) {
+                  const uint4 w = w_a;
+                  w_a = w_b;
+                  if (i + 2 < no) w_b = *reinterpret_cast<const uint4*>(p.ops[ob + i + 2]);
+                  const uint32_t a = a_kc + w.x, b = b_lo + w.y;
+                  const uint32_t dcol = acc0 + (w.z & 0xFFFFu);
+                  const uint32_t acc = (fresh_ok & (w.z >> 16)) ^ 1u;
+                  umma_bf16_lohi(dcol, a, a_hi, b, b_hi, w.w, acc);
 #pragma unroll
-                for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dcol, a + 2 * k, a_hi, b + 2 * k, b_hi, idesc, 1u);
+                  for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(dcol, a + 2 * k, a_hi, b + 2 * k, b_hi, w.w, 1u);
+                }
               }
-              tcgen05_commit(&b_empty[bs]);
+              if (!p.b_resident) tcgen05_commit(&b_empty[bs]);
             }
             __syncwarp();
             if (++bs == (uint32_t)p.nb) { bs = 0; bphase ^= 1u; }
           }
           if (pass == p.npass - 1) {                                 // this chunk's planes are dead: hand them to the producer
-            if (leader) tcgen05_commit(&plane_empty[set * p.nkc + kc]);
+            if (leader) tcgen05_commit(&plane_empty[slot]);
             __syncwarp();
           }
         }
@@ -372,7 +408,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
       for (int pass = 0; pass < p.npass; ++pass, ++acc_it) {
         const int buf = acc_it % p.nbuf;
         const uint32_t acc0 = tmem_base + buf * p.acc_stride + lane_tm;
-        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 128);
+        mbar_wait(&acc_full[buf], (acc_it / p.nbuf) & 1, 0);
         tcgen05_fence_after();
 #ifdef OFSV_STACK_PROBE
         if (!(p.probe & 4))
@@ -595,14 +631,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
 }
 
 // weights fp32 tap form [T][Cin_s][Cout_w] -> bf16 blocks of [Cout_w][KC]: out block b = (tap, kc) = table[b]
-struct SkPackTable { uint16_t blk[OFSV_MAX_TAPS * SK_MAX_KC]; };
+struct SkPackTable { uint16_t blk[OFSV_MAX_TAPS * SK_MAX_KC]; };   // (tap << 4) | kc
 __global__ void conv_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SkPackTable T, int nblocks,
                                          int Cin_s, int Cout_w, int KC) {
   const int per = Cout_w * KC;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)nblocks * per; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / per), e = (int)(i - (int64_t)b * per);
     const int r = e / KC, k = e - r * KC;
-    const int tap = T.blk[b] >> 2, kc = T.blk[b] & 3;
+    const int tap = T.blk[b] >> 4, kc = T.blk[b] & 15;
     out[i] = __float2bfloat16_rn(__ldg(w + ((int64_t)tap * Cin_s + kc * KC + k) * Cout_w + r));
   }
 }
@@ -612,7 +648,7 @@ static std::atomic<int> g_stack_td{0};
 extern std::atomic<int> g_warp_slab;         // warp3d_slab.cu       // 0 auto; 1 / 2 / 4 forces the super-tile depth when it is feasible
 
 struct SkConfig {
-  int td, nsets, nb, nbuf, epi_mode, stg_stride, stg_rowb, plane_stride, b_stride;
+  int td, nring, nb, nbuf, epi_mode, stg_stride, stg_rowb, plane_stride, b_stride, b_resident;
   size_t smem;
   double cost;
 };
@@ -621,7 +657,7 @@ struct SkConfig {
 static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkConfig* out) {
   const int KC = pl.KC, ROWB = KC * 2;
   const size_t smem_cap = 227 * 1024 - 1024;           // - alignment slack
-  const size_t misc = (SK_MAX_PBARS + 2 * SK_MAX_KC + 2 * SK_MAX_BST + 4) * 8 + 64 + 2 * 128 * 4;
+  const size_t misc = (SK_MAX_PBARS + SK_MAX_RING + 2 * SK_MAX_BST + 4) * 8 + 64 + 2 * 128 * 4;
   const int plane_stride = (SK_HP_ROWS * ROWB + 1023) & ~1023;
   int max_slots = 0;
   for (int g = 0; g < pl.ngroups; ++g) max_slots = pl.g[g].nslots > max_slots ? pl.g[g].nslots : max_slots;
@@ -645,18 +681,28 @@ static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkC
     if (cols > 512) continue;
     const int np = td + pl.dzmax - pl.dzmin;
     SkOp ops[SK_MAX_OPS];
-    int op_first[SK_MAX_GROUPS + 1];
+    int op_first[SK_MAX_GROUPS * SK_NI + 1];
     const int nops = sk_build_ops(d, pl, td, ops, op_first);
     if (nops < 0) continue;
-    double mma = 0.0;
-    for (int i = 0; i < nops; ++i) mma += sk_mma_cycles(ops[i].nsl * d->Cout_w);
-    mma *= pl.nkc * (KC / 16);
+    // tensor / operand-port time of all MMAs vs the issue time of the busier issuer (~50 cycles of scalar work per op)
+    double mma = 0.0, iss_t[SK_NI] = {0.0, 0.0};
+    for (int i = 0; i < nops; ++i) {
+      const double c = sk_mma_cycles(ops[i].nsl * d->Cout_w) * (KC / 16);
+      mma += c;
+      iss_t[ops[i].issuer] += c + 50.0;
+    }
+    { const double im = iss_t[0] > iss_t[1] ? iss_t[0] : iss_t[1]; mma = (mma > im ? mma : im) * pl.nkc; }
     const int64_t nst = cdiv(d->Wo, SK_HT_W) * cdiv(d->Ho, SK_HT_H) * cdiv(d->Do, td) * d->N;
+    // plane-chunk ring depth: single-pass layers stream chunks (2 slots overlap the loads of chunk c+1 with the MMAs of chunk c,
+    // more than 2 * nkc never helps); multi-pass layers need every chunk of a super-tile resident (multiples of nkc)
+    int rings[4], nrings = 0;
+    if (pl.npass == 1) { rings[nrings++] = pl.nkc >= 2 ? 2 : 2; rings[nrings++] = 1; }
+    else { rings[nrings++] = 2 * pl.nkc; rings[nrings++] = pl.nkc; }
     for (int ei = 0; ei < nepi; ++ei)
-      for (int nsets = (pl.nkc == 1 ? 2 : 1); nsets >= 1; --nsets) {
-        const int epi = epis[ei];
-        if (nsets * np * pl.nkc > SK_MAX_PBARS) continue;
-        const size_t planes = (size_t)nsets * np * pl.nkc * plane_stride;
+      for (int ri = 0; ri < nrings; ++ri) {
+        const int epi = epis[ei], nring = rings[ri];
+        if (nring > SK_MAX_RING || nring * np > SK_MAX_PBARS) continue;
+        const size_t planes = (size_t)nring * np * plane_stride;
         // staging: full rows when they fit next to >= 4 weight stages, else half rows
         int stg_rowb = 0, stg_stride = 0;
         if (epi == SK_EPI_TMA_SHUF) { stg_rowb = 128; stg_stride = 4096; }
@@ -667,19 +713,25 @@ static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkC
           stg_stride = (32 * stg_rowb + 1023) & ~1023;
         }
         const size_t fixed = planes + (size_t)SK_EPI_WARPS * stg_stride + misc;
-        if (fixed + 2 * (size_t)b_stride > smem_cap) continue;
+        const size_t w_all = (((size_t)d->nphase * d->ntaps * d->Cin_s * d->Cout_w * 2) + 1023) & ~(size_t)1023;
+        const bool resident = fixed + w_all <= smem_cap && w_all < (1u << 20);
+        if (!resident && fixed + 2 * (size_t)b_stride > smem_cap) continue;
         int nb = (int)((smem_cap - fixed) / b_stride);
         nb = nb > SK_MAX_BST ? SK_MAX_BST : nb;
         // cost model: rounds x (tensor time + exposed plane loads + a thin weight ring + scattered stores)
-        const double exposed = (pl.nkc == 1 && nsets == 1) ? (double)np * plane_stride / 30.0 : 0.0;
-        const double stall = nb < 3 ? 0.15 * mma : 0.0;
+        const bool overlapped = pl.npass == 1 ? nring >= 2 : (nring >= 2 * pl.nkc || pl.nkc >= 2);
+        const double exposed = overlapped ? 0.0 : (double)np * pl.nkc * plane_stride / 30.0;
+        // a streamed stage costs the issuing thread ~370 cycles of barrier / commit latency that resident weights do not pay
+        const double stall = resident ? 0.0 : 370.0 * pl.ngroups * pl.nkc + (nb < 3 ? 0.15 * mma : 0.0);
         const double scatter = epi == SK_EPI_DIRECT ? 0.25 * mma : 0.0;
         const double cost = (double)cdiv(nst, sms) * (mma + exposed + stall + scatter + 1500.0);
         if (!found || cost < best.cost) {
           found = true;
-          best.td = td; best.nsets = nsets; best.nb = nb; best.nbuf = cols <= 256 ? 2 : 1; best.epi_mode = epi;
+          best.td = td; best.nring = nring; best.nb = nb; best.nbuf = cols <= 256 ? 2 : 1; best.epi_mode = epi;
           best.stg_stride = stg_stride; best.stg_rowb = stg_rowb; best.plane_stride = plane_stride; best.b_stride = b_stride;
-          best.smem = fixed + (size_t)nb * b_stride + 1024; best.cost = cost;
+          best.b_resident = resident ? 1 : 0;
+          if (resident) { best.nb = 1; best.b_stride = (int)w_all; }      // the B area is the whole packed weight tensor
+          best.smem = fixed + (resident ? w_all : (size_t)nb * b_stride) + 1024; best.cost = cost;
         }
       }
     if (forced_td && td == forced_td && found) break;
@@ -688,7 +740,8 @@ static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkC
   return found;
 }
 
-static bool sk_wants_ring(const ofsv_conv_desc* d) { return d->nphase == 1 && d->ntaps <= 8; }
+static std::atomic<int> g_conv0_ring{0};     // 1: the 2^d-tap space-to-depth conv0 layers on the legacy plane-ring kernel (A/B)
+static bool sk_wants_ring(const ofsv_conv_desc* d) { return g_conv0_ring.load(std::memory_order_relaxed) != 0 && d->nphase == 1 && d->ntaps <= 8; }
 
 template <int KC>
 static int sk_launch(const SkParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const SkOutMaps& tmO, const float* bias,
@@ -708,6 +761,7 @@ extern "C" int ofsv_set_tuning(const char* key, int value) {
   if (!strcmp(key, "stack_epilogue")) { g_stack_epi.store(value); return OFSV_OK; }
   if (!strcmp(key, "stack_td")) { g_stack_td.store(value); return OFSV_OK; }
   if (!strcmp(key, "warp_slab")) { g_warp_slab.store(value); return OFSV_OK; }
+  if (!strcmp(key, "conv0_ring")) { g_conv0_ring.store(value); return OFSV_OK; }
   set_error("ofsv_set_tuning: unknown key '%s'", key);
   return OFSV_EINVAL;
 }
@@ -733,14 +787,14 @@ extern "C" int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_ta
     nkc = d->Cin_s / KC;
     OFSV_REQUIRE(nkc <= SK_MAX_KC, "ofsv_conv_pack_weights: too many channel chunks");
     for (int t = 0; t < ntap; ++t)
-      for (int kc = 0; kc < nkc; ++kc) T.blk[nblocks++] = (uint16_t)((t << 2) | kc);
+      for (int kc = 0; kc < nkc; ++kc) T.blk[nblocks++] = (uint16_t)((t << 4) | kc);
   } else {
     SkPlan pl;
     if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_pack_weights: layer has no stacked form"); return OFSV_ENOSUP; }
     KC = pl.KC; nkc = pl.nkc;
     for (int g = 0; g < pl.ngroups; ++g)
       for (int kc = 0; kc < nkc; ++kc)
-        for (int s = 0; s < pl.g[g].nslots; ++s) T.blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 2) | kc);
+        for (int s = 0; s < pl.g[g].nslots; ++s) T.blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 4) | kc);
     OFSV_REQUIRE(nblocks == ntap * nkc, "ofsv_conv_pack_weights: internal error (slot count %d != %d)", nblocks, ntap * nkc);
   }
   const int64_t total = (int64_t)nblocks * d->Cout_w * KC;
@@ -756,7 +810,7 @@ extern "C" int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* n
   SkPlan pl;
   if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_stack_selfcheck: no stacked form"); return OFSV_ENOSUP; }
   SkOp ops[SK_MAX_OPS];
-  int op_first[SK_MAX_GROUPS + 1];
+  int op_first[SK_MAX_GROUPS * SK_NI + 1];
   const int nops = sk_build_ops(d, pl, td, ops, op_first);
   if (nops < 0) { set_error("ofsv_conv_stack_selfcheck: op table overflow"); return OFSV_ENOSUP; }
   // covered[ph * ntaps + t][j]
@@ -766,7 +820,7 @@ extern "C" int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* n
   for (int pass = 0; pass < pl.npass; ++pass) {
     bool init[64] = {false};
     for (int g = pl.group_first[pass]; g < pl.group_first[pass + 1]; ++g)
-      for (int i = op_first[g]; i < op_first[g + 1]; ++i) {
+      for (int i = op_first[g * SK_NI]; i < op_first[(g + 1) * SK_NI]; ++i) {
         const SkOp& o = ops[i];
         const SkGroup& G = pl.g[g];
         OFSV_REQUIRE(o.group == g && o.nsl >= 1 && o.slot0 + o.nsl <= G.nslots && o.nsl * d->Cout_w <= 256, "selfcheck: bad op %d", i);
@@ -799,12 +853,12 @@ extern "C" int ofsv_conv_halo_describe(const ofsv_conv_desc* d, char* buf, int b
   SkConfig cfg;
   if (!sk_configure(d, pl, device_num_sms(), &cfg)) { snprintf(buf, buflen, "does-not-fit"); return OFSV_OK; }
   SkOp ops[SK_MAX_OPS];
-  int op_first[SK_MAX_GROUPS + 1];
+  int op_first[SK_MAX_GROUPS * SK_NI + 1];
   const int nops = sk_build_ops(d, pl, cfg.td, ops, op_first);
   double mma = 0.0, ideal = 0.0;
   for (int i = 0; i < nops; ++i) { mma += sk_mma_cycles(ops[i].nsl * d->Cout_w); ideal += ops[i].nsl * d->Cout_w / 2.0; }
-  snprintf(buf, buflen, "stack KC=%d nkc=%d P=%d npass=%d groups=%d td=%d nsets=%d nb=%d nbuf=%d epi=%d rowb=%d smem=%zu ops=%d tensor_frac=%.2f",
-           pl.KC, pl.nkc, pl.P, pl.npass, pl.ngroups, cfg.td, cfg.nsets, cfg.nb, cfg.nbuf, cfg.epi_mode, cfg.stg_rowb, cfg.smem, nops, ideal / mma);
+  snprintf(buf, buflen, "stack KC=%d nkc=%d P=%d npass=%d groups=%d td=%d nring=%d nb=%d%s nbuf=%d epi=%d rowb=%d smem=%zu ops=%d tensor_frac=%.2f",
+           pl.KC, pl.nkc, pl.P, pl.npass, pl.ngroups, cfg.td, cfg.nring, cfg.nb, cfg.b_resident ? "(resident)" : "", cfg.nbuf, cfg.epi_mode, cfg.stg_rowb, cfg.smem, nops, ideal / mma);
   return OFSV_OK;
 }
 
@@ -860,10 +914,10 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   memset(&P, 0, sizeof(P));
   P.N = d->N; P.Do = d->Do; P.Ho = d->Ho; P.Wo = d->Wo; P.Dy = d->Dy; P.Hy = d->Hy; P.Wy = d->Wy;
   P.Cout_s = d->Cout_s; P.Cout_w = d->Cout_w; P.out_stride = d->out_stride; P.nd = d->nd;
-  P.nkc = pl.nkc; P.td = cfg.td; P.np = cfg.td + pl.dzmax - pl.dzmin; P.dzmin = pl.dzmin; P.P = pl.P; P.npass = pl.npass; P.nsets = cfg.nsets;
+  P.nkc = pl.nkc; P.td = cfg.td; P.np = cfg.td + pl.dzmax - pl.dzmin; P.dzmin = pl.dzmin; P.P = pl.P; P.npass = pl.npass; P.nring = cfg.nring;
   P.tiles_w = (int)cdiv(d->Wo, SK_HT_W); P.tiles_h = (int)cdiv(d->Ho, SK_HT_H); P.tiles_d = (int)cdiv(d->Do, cfg.td);
   P.nb = cfg.nb; P.plane_stride = cfg.plane_stride; P.b_stride = cfg.b_stride; P.stg_stride = cfg.stg_stride; P.stg_rowb = cfg.stg_rowb;
-  P.nbuf = cfg.nbuf; P.acc_stride = 256;
+  P.nbuf = cfg.nbuf; P.acc_stride = 256; P.b_resident = cfg.b_resident; P.ni = sk_issuers(pl, cfg.td);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
   P.shuffle = d->out_shuffle; P.out_s2d = d->out_s2d; P.epi_mode = cfg.epi_mode; P.hfast = d->out_shuffle_hfast;
 #ifdef OFSV_STACK_PROBE   // probe builds only (tests/ab_build.sh): timing experiments that produce WRONG results; never in the shipped library
@@ -871,14 +925,16 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
 #endif
   {
     SkOp ops[SK_MAX_OPS];
-    int op_first[SK_MAX_GROUPS + 1];
+    int op_first[SK_MAX_GROUPS * SK_NI + 1];
     const int nops = sk_build_ops(d, pl, cfg.td, ops, op_first);
     OFSV_REQUIRE(nops > 0, "ofsv_conv_halo: internal error (op list)");
     for (int i = 0; i <= pl.npass; ++i) P.group_first[i] = (uint16_t)pl.group_first[i];
     for (int g = 0; g < pl.ngroups; ++g) {
       P.groups[g].row0 = (uint32_t)pl.g[g].row0;
-      P.groups[g].op_begin = (uint16_t)op_first[g];
-      P.groups[g].nops = (uint8_t)(op_first[g + 1] - op_first[g]);
+      for (int w = 0; w < SK_NI; ++w) {
+        P.groups[g].op_begin[w] = (uint8_t)op_first[g * SK_NI + w];
+        P.groups[g].nops[w] = (uint8_t)(op_first[g * SK_NI + w + 1] - op_first[g * SK_NI + w]);
+      }
       P.groups[g].nslots = (uint8_t)pl.g[g].nslots;
     }
     const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);   // fp32 accumulate, bf16 x bf16, K-major, M = 128
@@ -886,7 +942,7 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
       const SkOp& o = ops[i];
       const uint32_t a_off = (uint32_t)(((o.oy + 1) * SK_HP_W + (o.ox + 1)) * ROWB) >> 4;
       const uint32_t ncols = (uint32_t)(o.nsl * d->Cout_w);
-      P.ops[i][0] = a_off + (uint32_t)o.q * (uint32_t)pl.nkc * ((uint32_t)cfg.plane_stride >> 4);
+      P.ops[i][0] = a_off + (uint32_t)o.q * ((uint32_t)cfg.plane_stride >> 4);
       P.ops[i][1] = (uint32_t)(o.slot0 * d->Cout_w * ROWB) >> 4;
       P.ops[i][2] = (uint32_t)(o.col0 * d->Cout_w) | ((uint32_t)(o.fresh ? 1 : 0) << 16);
       P.ops[i][3] = idesc0 | ((ncols >> 3) << 17);

@@ -32,10 +32,13 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
 }
 // Waiting warps back off with nanosleep: at N = 64 the tensor core's operand fetch needs ~95 % of the shared-memory
 // cycles, so nine warps hammering mbarrier words in shared memory measurably slow the MMAs down.
+// (mbarrier.try_wait is itself a hardware-suspended wait with a time limit, not a poll: sleep_ns = 0 simply re-arms it.  A
+// __nanosleep between tries costs far more than its argument — the stacked conv kernel's weight ring measured a ~2.8 us
+// producer/consumer round trip with 32-64 ns back-offs, i.e. 0.35 us per stage whatever the stage size.)
 static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t sleep_ns) {
   const long long t0 = clock64();
   while (!mbar_try(addr, parity)) {
-    __nanosleep(sleep_ns);
+    if (sleep_ns) __nanosleep(sleep_ns);
     if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
   }
 }

@@ -364,10 +364,11 @@ def test_stacked_conv_op_lists_cover_every_term_once(nd):
             tds = sorted(per_slice)
             for a, b in zip(tds, tds[1:]):
                 assert per_slice[b] <= per_slice[a] * 1.001, (nd, c, li, per_slice)
-    # the point of the design: a 64 -> 64 3^3 conv at TD = 4 needs < 0.75 of the port-bound per-slice MMA time at TD = 1
+    # the point of the design: a 64 -> 64 3^3 conv at TD = 4 (two issuers, runs of N <= 128 each) needs < 0.85 of the port-bound
+    # per-slice MMA time at TD = 1
     blk = ifnet.IFBlock(3, 11, 64)
     d = blk.layers()[2]._structure_desc()
     c1, c4 = ctypes.c_double(0.0), ctypes.c_double(0.0)
     assert L.ofsv_conv_stack_selfcheck(ctypes.byref(d), 1, None, ctypes.byref(c1)) == 0
     assert L.ofsv_conv_stack_selfcheck(ctypes.byref(d), 4, None, ctypes.byref(c4)) == 0
-    assert c4.value / 4 < 0.75 * c1.value, (c1.value, c4.value)
+    assert c4.value / 4 < 0.85 * c1.value, (c1.value, c4.value)
