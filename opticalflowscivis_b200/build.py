@@ -32,28 +32,46 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link libofsv.so next to this file.  No-op when up to date."""
+    """Compile every .cu for sm_100a and link libofsv.so next to this file.  No-op when up to date.
+    Safe under torchrun: ranks serialise on a lock file, objects and the library are written under temporary names and moved into
+    place, and staleness is re-checked once the lock is held (the first rank builds, the others find it done)."""
     if not force and not _stale():
         return SO
+    import fcntl
+    import tempfile
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    objs, procs = [], []
-    for s in SOURCES:
-        o = os.path.join(objdir, s.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(o)
-    failed = False
-    for s, p in procs:
-        out, _ = p.communicate()
-        if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- nvcc {s} ---\n{out}\n")
-        failed |= p.returncode != 0
-    if failed:
-        raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    with open(os.path.join(objdir, ".lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO
+            tmpdir = tempfile.mkdtemp(prefix="obj.", dir=objdir)
+            try:
+                objs, procs = [], []
+                for s in SOURCES:
+                    o = os.path.join(tmpdir, s.replace(".cu", ".o"))
+                    cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+                    if verbose:
+                        cmd.insert(1, "-Xptxas=-v")
+                    procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+                    objs.append(o)
+                failed = False
+                for s, p in procs:
+                    out, _ = p.communicate()
+                    if p.returncode != 0 or verbose:
+                        sys.stderr.write(f"--- nvcc {s} ---\n{out}\n")
+                    failed |= p.returncode != 0
+                if failed:
+                    raise RuntimeError("nvcc failed")
+                tmp_so = os.path.join(tmpdir, "libofsv.so")
+                subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp_so, *objs,
+                                       "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+                os.replace(tmp_so, SO)
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
     return SO
 
 

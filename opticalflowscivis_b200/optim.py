@@ -82,6 +82,17 @@ class FusedAdamW:
                                                   float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                                   float(g["weight_decay"]), self.step_count, float(grad_scale),
                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # the kernel writes the parameters through raw pointers: tell torch, so that everything keyed on (data_ptr, _version)
+        # — IFBlock's packed tap-form weights, Model's captured CUDA graphs — sees a new parameter version
+        _bump_versions(self.params)
+
+
+def _bump_versions(params):
+    """Increment `p._version` of every parameter without touching its values (no kernel launch: an in-place no-op on a
+    zero-element view shares the version counter of its base)."""
+    with torch.no_grad():
+        for p in params:
+            p.view(-1)[:0].zero_()
 
 
 class GradientBucket:

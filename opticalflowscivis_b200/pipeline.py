@@ -106,6 +106,10 @@ class StreamedInterpolator:
             res = self.select(self.model.inference(x0, x1))
             if self.out_u8:
                 res = ops.f32_to_u8(res, 255.0)
+            elif getattr(self.model, "_graphs", None) is not None:
+                # graph mode: `res` is the graph's own output buffer, which the NEXT replay overwrites while this pair's download
+                # may still be reading it (record_stream cannot protect a graph-private buffer) — hand the download a copy
+                res = res.clone()
             sl["free"].record(comp)                            # (a pass-through to_float hands the slot itself to the model)
             ev = torch.cuda.Event()
             ev.record(comp)

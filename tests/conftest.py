@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: one full-size CPU oracle call (tens of seconds); still part of the default -m gpu run")
 
 
 def pytest_collection_modifyitems(config, items):

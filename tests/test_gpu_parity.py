@@ -450,6 +450,122 @@ def test_model_inference_vs_oracle(nd, precision):
     else:
         assert max(epe) <= 1e-2, epe                       # north_star: flow within 1e-2 px EPE
         assert abs(p_ref - p_mine) <= 0.05                 # frames within 0.05 dB PSNR
+        # PSNR against gt is loose with random weights (10-20 dB): also bound the frames against the reference's directly
+        assert d_merged <= 5e-3 and d_mask <= 5e-3, (d_merged, d_mask)
+        assert _psnr(_np(merged_l), r_merged_l.numpy()) >= 70.0
+
+
+def _scaled_heads_state(nd, gain):
+    """Seed-1234 reference weights with the flow heads (conv1.2) of all three blocks multiplied by `gain`: random-init heads give
+    |flow| < 1.5 px, where a bf16 error proportional to |flow| is invisible; a gain of 6-16 puts the flows of the synthetic pair at
+    several pixels / voxels, the regime of a trained network on the reference's data (droplets move 2-8 px per pair)."""
+    from oracle.ifnet_ref import ModelRef
+    torch.manual_seed(1234)
+    ref = ModelRef(nd).eval()
+    sd = ref.flownet.state_dict()
+    for b in ("block0", "block1", "block2"):
+        sd[f"{b}.conv1.2.weight"] *= gain
+        sd[f"{b}.conv1.2.bias"] *= gain
+    ref.flownet.load_state_dict(sd)
+    return ref, sd
+
+
+@pytest.mark.parametrize("nd,gain", [(3, 16.0), (2, 6.0)])
+def test_model_large_flow_regime_bf16(nd, gain):
+    """bf16 convs vs the fp32 CPU oracle when |flow| reaches several voxels (measured, tests/probe_large_flow.py: the bf16 flow
+    error is ~0.1-0.2 % of |flow| — 3-D, mean |flow| 3.2 / max 5.7 voxels: EPE 4e-3; 2-D, mean 3.8 / max 10 px: 9.5e-3 —
+    so north_star's 1e-2 px bar holds up to mean flows of ~4 px and the frame PSNR bar (0.05 dB) with a margin of 50x)."""
+    if nd == 2:
+        from opticalflowscivis_b200.flow2d.model.RIFE import Model
+        n, sp = 2, (160, 224)
+    else:
+        from opticalflowscivis_b200.flow3d.model.RIFE import Model
+        n, sp = 1, (64, 64, 64)
+    ref, sd = _scaled_heads_state(nd, gain)
+    m = Model(precision="bf16")
+    m.flownet.load_state_dict(sd)
+    m.eval()
+    img0, gt, img1 = _synthetic_pair(nd, n, sp)
+    r_merged, r_flow, r_mask = ref.inference(img0, img1)
+    merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
+    if nd == 2:
+        merged, r_merged = merged[2], r_merged[2]
+    mag = (r_flow[2] ** 2).reshape(n, 2, nd, -1).sum(2).sqrt()
+    assert float(mag.mean()) >= 2.5 and float(mag.max()) >= 5.0, (float(mag.mean()), float(mag.max()))     # the regime is reached
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(n, 2, nd, -1).sum(2).sqrt().mean()) for i in range(3)]
+    p_ref, p_mine = _psnr(r_merged.numpy(), gt.numpy()), _psnr(_np(merged), gt.numpy())
+    print(f"large-flow IFNet{nd}D gain {gain}: |flow| mean {float(mag.mean()):.2f} max {float(mag.max()):.2f}; EPE {epe}; "
+          f"PSNR(mine, ref) {_psnr(_np(merged), r_merged.numpy()):.1f} dB")
+    assert max(epe) <= 1e-2, epe                                       # north_star: 1e-2 px EPE
+    assert max(epe) <= 4e-3 * float(mag.mean()), epe                   # and relative: < 0.4 % of the mean flow magnitude
+    assert abs(p_ref - p_mine) <= 0.05                                 # north_star: 0.05 dB
+    assert _psnr(_np(merged), r_merged.numpy()) >= 60.0 and float((merged.cpu() - r_merged).abs().max()) <= 3e-2
+
+
+def test_model3d_cfg3_rect128_batch4_vs_oracle():
+    """BASELINE.json configs[2] at its full size — 3-D textured rectangle 128^3, batch 4 — against the CPU oracle (~10 s of host
+    time), bf16 convs."""
+    from oracle.ifnet_ref import ModelRef
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    ref = ModelRef(3).eval()
+    m = Model(precision="bf16")
+    m.flownet.load_state_dict(ref.flownet.state_dict())
+    m.eval()
+    n, sp = 4, (128, 128, 128)
+    img0, gt, img1 = _synthetic_pair(3, n, sp)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    r_merged, r_flow, r_mask = ref.inference(img0, img1)
+    merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(n, 2, 3, -1).sum(2).sqrt().mean()) for i in range(3)]
+    assert max(epe) <= 1e-2, epe
+    assert float((merged.cpu() - r_merged).abs().max()) <= 5e-3 and float((mask.cpu() - r_mask).abs().max()) <= 5e-3
+    assert abs(_psnr(r_merged.numpy(), gt.numpy()) - _psnr(_np(merged), gt.numpy())) <= 0.05
+
+
+def test_model2d_cfg2_droplet_batch64_vs_oracle():
+    """BASELINE.json configs[1] at its full size — 64 droplet-shaped 160x224 frames, t = 0.5 — against the CPU oracle."""
+    from oracle.ifnet_ref import ModelRef
+    from opticalflowscivis_b200 import synth
+    from opticalflowscivis_b200.flow2d.model.RIFE import Model
+    torch.manual_seed(1234)
+    ref = ModelRef(2).eval()
+    m = Model(precision="bf16")
+    m.flownet.load_state_dict(ref.flownet.state_dict())
+    m.eval()
+    a, g_, b = synth.droplet2d(64, 160, 224, seed=1234)
+    img0, gt, img1 = torch.from_numpy(a), torch.from_numpy(g_), torch.from_numpy(b)
+    r_merged, r_flow, r_mask = ref.inference(img0, img1)
+    merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
+    epe = [float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(64, 2, 2, -1).sum(2).sqrt().mean()) for i in range(3)]
+    assert max(epe) <= 1e-2, epe
+    for k in range(3):
+        assert float((merged[k].cpu() - r_merged[k]).abs().max()) <= 1e-2
+    assert abs(_psnr(r_merged[2].numpy(), gt.numpy()) - _psnr(_np(merged[2]), gt.numpy())) <= 0.05
+
+
+@pytest.mark.slow
+def test_model3d_cfg4_droplet256_pair_vs_oracle():
+    """BASELINE.json configs[3] at its full size: ONE 256^3 droplet byte-volume pair through Model.inference (bf16 convs) against
+    the CPU oracle on the same pair (one oracle call: ~10-25 s and ~6 GB of host memory)."""
+    from oracle.ifnet_ref import ModelRef
+    from opticalflowscivis_b200 import synth
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    torch.manual_seed(1234)
+    ref = ModelRef(3).eval()
+    m = Model(precision="bf16")
+    m.flownet.load_state_dict(ref.flownet.state_dict())
+    m.eval()
+    a, g_, b = synth.droplet3d_u8(1, 256, seed=1234)
+    img0, gt, img1 = (torch.from_numpy(v).float() / 255.0 for v in (a, g_, b))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    r_merged, r_flow, r_mask = ref.inference(img0, img1)
+    merged, flow, mask = m.inference(img0.to(_dev()), img1.to(_dev()))
+    for i in range(3):
+        e = float(((flow[i].cpu() - r_flow[i]) ** 2).reshape(1, 2, 3, -1).sum(2).sqrt().mean())
+        assert e <= 1e-2, (i, e)
+    assert float((merged.cpu() - r_merged).abs().max()) <= 5e-3 and float((mask.cpu() - r_mask).abs().max()) <= 5e-3
+    assert abs(_psnr(r_merged.numpy(), gt.numpy()) - _psnr(_np(merged), gt.numpy())) <= 0.05
 
 
 @pytest.mark.parametrize("sp,n", [((32, 48, 64), 2), ((16, 16, 16), 3), ((48, 32, 80), 1)])
@@ -1097,3 +1213,31 @@ def test_f32_to_u8_export_and_streamed_u8_output():
     assert len(u) == 3 and u[0].dtype == torch.uint8
     for ff, uu in zip(f, u):
         assert torch.equal(uu, (ff.clamp(0, 1) * 255).byte())
+
+
+def test_fused_adamw_step_invalidates_packed_weights():
+    """FusedAdamW writes parameters through raw pointers; the packed tap-form weights and captured CUDA graphs are
+    keyed on (data_ptr, _version), so the optimizer must bump the versions.  After a step, inference has to equal a freshly
+    constructed model holding the updated state_dict."""
+    from opticalflowscivis_b200.flow3d.model.RIFE import Model
+    from opticalflowscivis_b200.optim import FusedAdamW
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    m.enable_cuda_graphs()
+    x0, x1 = torch.rand((1, 1, 32, 32, 32), device=_dev()), torch.rand((1, 1, 32, 32, 32), device=_dev())
+    before = m.inference(x0, x1)[0].clone()
+    params = list(m.flownet.parameters())
+    v0 = [p._version for p in params]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for p in params:
+        p.grad = torch.randn(p.shape, generator=g).to(_dev())
+    opt = FusedAdamW(params, lr=5e-2, weight_decay=1e-3)         # a step large enough to move the output
+    opt.step()
+    assert all(p._version > v for p, v in zip(params, v0))
+    after = m.inference(x0, x1)[0].clone()
+    assert not torch.equal(before, after)
+    fresh = Model()
+    fresh.flownet.load_state_dict(m.flownet.state_dict())
+    fresh.eval()
+    assert torch.equal(fresh.inference(x0, x1)[0], after)
