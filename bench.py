@@ -29,7 +29,11 @@ WORKLOADS = {
     "flow3d_droplet256": (3, (256, 256, 256), 4, "Flow-3D droplet-shaped 256^3 byte volume pairs, ensemble batch-sharded"),
     "flow3d_rect128": (3, (128, 128, 128), 4, "Flow-3D IFNet on synthetic 3D textured rectangle 128^3, batch 4"),
     "flow2d_droplet": (2, (160, 224), 64, "Flow-2D droplet-shaped 160x224 monochrome, batch 64"),
+    "flow2d_rect_b1": (2, (160, 224), 1, "Flow-2D RIFE IFNet inference on synthetic textured rectangle 160x224, batch 1"),
 }
+# a separate operator-level workload (BASELINE.json configs[4]): see run_upflow_ops()
+UPFLOW_LEVELS = ((196, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104), (32, 64, 208))     # (C, H, W) of a 256x832 pair, SURVEY.md §8 a8
+UPFLOW_PARAMS = 3_354_146                                                                  # UPFlow parameter count (13.4 MB fp32)
 
 
 def ifnet_macs(nd, sp):
@@ -104,20 +108,51 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_reference_rate(nd, sp, pairs, steps, warmup):
-    """The reference's CPU path for the same workload: oracle/ifnet_ref.py (bit-identical restatement of the reference
-    modules, pinned in tests/golden) with all host threads.  Returns (pairs_per_s, seconds_per_step, threads)."""
+def _workload_inputs(workload, pairs, seed=1234):
+    """Synthetic host inputs of a workload as numpy arrays (img0, gt, img1)."""
+    from opticalflowscivis_b200 import synth
+    nd, sp, _, _ = WORKLOADS[workload]
+    if workload == "flow3d_droplet256":
+        return synth.droplet3d_u8(pairs, sp[0], seed=seed)
+    if workload == "flow3d_rect128":
+        return synth.rectangle3d(pairs, sp[0], seed=seed)
+    if workload == "flow2d_rect_b1":
+        return synth.rectangle2d(pairs, *sp, seed=seed)
+    return synth.droplet2d(pairs, *sp, seed=seed)
+
+
+def base_config(workload, pairs):
+    """`config`: printed identically by both arms (ours / --impl reference); arm-specific settings go to `impl_config`."""
+    nd, sp, _, desc = WORKLOADS[workload]
+    return {"workload": workload, "describes": desc, "spatial": list(sp), "pairs_per_gpu_per_step": pairs,
+            "weights": "random init, seed 1234",
+            "only_last": "3-D inference returns merged[2] only (Flow-3D/model/RIFE.py:75): the blends of scales 0 and 1 are skipped, "
+                         "their flows are still returned" if nd == 3 else "all three blends run (2-D returns merged[0..2])",
+            "l2": "working set per step (>1 GB) exceeds the 126 MB L2; no explicit flush" if nd == 3 else
+                  "inputs + activations of a step exceed L2 only at batch 64; no explicit flush"}
+
+
+def reference_model(nd, device="cpu"):
+    """oracle/ifnet_ref.py: the bit-exact torch restatement of the reference's Model.inference (pinned in tests/golden)."""
     import torch
     from oracle.ifnet_ref import ModelRef
-    from opticalflowscivis_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(1234)
     m = ModelRef(nd).eval()
-    if nd == 3:
-        a, _, b = synth.droplet3d_u8(pairs, sp[0])
+    m.flownet.to(device)
+    return m
+
+
+def cpu_reference_rate(workload, pairs, steps, warmup):
+    """The reference's CPU path on the SAME workload (same spatial size; `pairs` pairs per call) with all host threads.
+    Returns (pairs_per_s, seconds_per_call, threads)."""
+    import torch
+    nd = WORKLOADS[workload][0]
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = reference_model(nd)
+    a, _, b = _workload_inputs(workload, pairs)
+    if a.dtype.kind == "u":
         img0, img1 = torch.from_numpy(a).float() / 255.0, torch.from_numpy(b).float() / 255.0
     else:
-        a, _, b = synth.droplet2d(pairs, *sp)
         img0, img1 = torch.from_numpy(a), torch.from_numpy(b)
     for _ in range(warmup):
         m.inference(img0, img1)
@@ -128,46 +163,101 @@ def cpu_reference_rate(nd, sp, pairs, steps, warmup):
     return pairs / dt, dt, torch.get_num_threads()
 
 
+# pairs per CPU call: ONE real pair of the workload's size for the 3-D volumes (a 256^3 call takes 10-25 s), the whole batch in 2-D
+CPU_SAMPLE = {"flow3d_droplet256": (1, "one full 256^3 pair per call (a quarter of the 4-pair step; rate = 1 / seconds per call)"),
+              "flow3d_rect128": (1, "one full 128^3 pair per call"),
+              "flow2d_droplet": (64, "the full batch of 64 pairs of 160x224 per call"),
+              "flow2d_rect_b1": (1, "the one 160x224 pair per call")}
+
+
 def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, bit-exact against the imported reference)
+    on this box's host cores, same workload / metric / unit; every step is a bounded sample of the step (see CPU_SAMPLE)."""
     if rank != 0:
         return
+    if args.workload == "upflow_ops":
+        print(json.dumps({"impl": "reference", "unavailable": "upflow_ops is an operator-level workload without a CPU arm"}), flush=True)
+        return
     nd, sp, pairs, desc = WORKLOADS[args.workload]
-    full_vox = 1
-    for s in sp:
-        full_vox *= s
-    # bounded sample per step: a 128^3 sub-volume pair (1/8 of a 256^3 pair) for the 3-D headline workload
-    if args.workload == "flow3d_droplet256":
-        s_sp, s_pairs, frac, sample = (128, 128, 128), 1, 1.0 / 8.0, "one 128^3 sub-volume pair per step = 1/8 of a 256^3 pair"
-    elif args.workload == "flow3d_rect128":
-        s_sp, s_pairs, frac, sample = (64, 64, 64), 1, 1.0 / 8.0, "one 64^3 sub-volume pair per step = 1/8 of a 128^3 pair"
-    else:
-        s_sp, s_pairs, frac, sample = sp, 8, 8.0, "8 pairs of 160x224 per step"
-    rate, dt, threads = cpu_reference_rate(nd, s_sp, s_pairs, args.steps, min(args.warmup, 1))
-    value = frac / dt if nd == 3 else rate
+    s_pairs, sample = CPU_SAMPLE[args.workload]
+    with contextlib.redirect_stdout(sys.stderr):
+        rate, dt, threads = cpu_reference_rate(args.workload, s_pairs, args.steps, args.warmup)
     unit = "pairs/s"
     line = {
-        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "describes": desc, "spatial": list(sp), "pairs_per_gpu_per_step": pairs},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": base_config(args.workload, pairs),
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def cuda_eager_rates(workload, pairs, dev, reps=3):
+    """Context number: the reference's own modules (oracle port = same torch calls: cuDNN convs, ATen grid_sample /
+    interpolate) in eager PyTorch ON THIS GPU, one call of `pairs` pairs, strict fp32 and with TF32 allowed."""
+    import torch
+    nd = WORKLOADS[workload][0]
+    m = reference_model(nd, dev)
+    a, _, b = _workload_inputs(workload, pairs)
+    cvt = (lambda v: torch.from_numpy(v).to(dev).float() / 255.0) if a.dtype.kind == "u" else (lambda v: torch.from_numpy(v).to(dev))
+    img0, img1 = cvt(a), cvt(b)
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(2):
+                m.inference(img0, img1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                m.inference(img0, img1)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = pairs * reps / (e0.elapsed_time(e1) / 1e3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del m, img0, img1
+    torch.cuda.empty_cache()
+    return {"value_fp32": out["fp32"], "value_tf32": out["tf32"], "unit": "pairs/s", "kind": "port",
+            "what": f"oracle/ifnet_ref.ModelRef (the reference's torch calls) in eager PyTorch on this GPU, {pairs} pair(s) per call, "
+                    f"resident inputs, {reps} calls after 2 warm-ups; cudnn.allow_tf32 False / True"}
+
+
 def metric_name(workload):
     return {"flow3d_droplet256": "256^3 volume-pair interps/sec", "flow3d_rect128": "128^3 volume-pair interps/sec",
-            "flow2d_droplet": "160x224 frame-pair interps/sec"}[workload]
+            "flow2d_droplet": "160x224 frame-pair interps/sec", "flow2d_rect_b1": "160x224 frame-pair interps/sec",
+            "upflow_ops": "UPFlow flow-path operator training steps/sec"}[workload]
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _timed(fn, steps, barrier):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    fn(steps)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+# DRAM bytes per 256^3 pair from the committed `ncu --set full` capture of one inference (dram__bytes_read.sum + dram__bytes_write.sum
+# summed over the launches of a class; file named in `traffic_source`).  None until a capture of the current kernels is committed.
+NCU_TRAFFIC = {
+    "source": None, "conv_all": None, "conv_hbm_layers": None, "stage": None,
+}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from opticalflowscivis_b200 import ops, synth
+    from opticalflowscivis_b200 import ops
     from opticalflowscivis_b200.pipeline import StreamedInterpolator
     from opticalflowscivis_b200.rife import Model2D, Model3D
 
@@ -182,14 +272,15 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(1234)
     model = (Model3D if nd == 3 else Model2D)(local_rank=local_rank, precision=args.precision, engine=args.engine)
     model.eval()
+    graphs = args.workload == "flow2d_rect_b1"      # one 160x224 pair is host-enqueue-bound: replay the call from a CUDA graph
+    if graphs:
+        model.enable_cuda_graphs()
 
-    # synthetic inputs: member seed = 1234 + global pair index (SURVEY.md §8d cfg 4)
-    if nd == 3:
-        a, _, b = synth.droplet3d_u8(pairs, sp[0], seed=1234 + rank * pairs)
-    else:
-        a, _, b = synth.droplet2d(pairs, *sp, seed=1234 + rank * pairs)
-    h0, h1 = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()      # 3-D: uint8 host volumes; 2-D: fp32
-    as_f32 = (lambda t: t.float().div_(255.0)) if nd == 3 else (lambda t: t)
+    # synthetic inputs: member seed = 1234 + global pair index
+    a, _, b = _workload_inputs(args.workload, pairs, seed=1234 + rank * pairs)
+    h0, h1 = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()      # droplet volumes: uint8 on the host; others fp32
+    bytes_in = h0.dtype == torch.uint8
+    as_f32 = (lambda t: t.float().div_(255.0)) if bytes_in else (lambda t: t)
     d0, d1 = as_f32(h0.to(dev)), as_f32(h1.to(dev))
 
     def barrier():
@@ -197,193 +288,265 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        return model.inference(d0, d1)
+    def step_resident(k=1):
+        for _ in range(k):
+            model.inference(d0, d1)
 
-    for _ in range(args.warmup):
-        step_resident()
+    step_resident(args.warmup)
     barrier()
 
     # ---- timed region 1 (`value`): inputs resident in HBM, nothing but the K inference calls between the two events
     n0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            step_resident()
-        e1.record()
-        barrier()
+        ms = _timed(step_resident, args.steps, barrier)
     launches = ops.launch_count() - n0
-    ms = e0.elapsed_time(e1)
 
     # ---- profile pass (the same K steps again): CUDA events around every launch, per kernel class, on the launching stream
-    timer = ops.LaunchTimer()
-    ops.TIMER = timer
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for _ in range(args.steps):
-        step_resident()
-    e5.record()
-    torch.cuda.synchronize()
-    ops.TIMER = None
-    ms_prof = e4.elapsed_time(e5)
-    classes = timer.totals()
+    classes, layer_ms, ms_prof = {}, None, None
+    if not graphs:
+        timer = ops.LaunchTimer()
+        ops.TIMER = timer
+        ms_prof = _timed(step_resident, args.steps, barrier)
+        ops.TIMER = None
+        classes = timer.totals()
+        conv_seq = [(a_.elapsed_time(b_)) for (name, a_, b_) in timer.seq if name.startswith("conv_")]
+        if len(conv_seq) == 36 * args.steps:       # 3 blocks x 12 conv launches, fixed order: per-layer mean time over the steps
+            layer_ms = [sum(conv_seq[i::36]) / args.steps for i in range(36)]
 
     # ---- standalone warp kernel (the "warp HBM GB/s vs peak" half of the metric): a1 / a2 on the workload's shape
     g = torch.Generator(device="cpu").manual_seed(7)
     wflow = (torch.randn((pairs, nd) + tuple(max(1, s // 8) for s in sp), generator=g) * 2.0).to(dev)
     wflow = torch.nn.functional.interpolate(wflow, size=tuple(sp), mode="trilinear" if nd == 3 else "bilinear").contiguous()
     warp_fn = ops.warp3d if nd == 3 else ops.warp2d
-    for _ in range(3):
-        warp_fn(d0, wflow)
-    w0e, w1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wreps = 10
-    w0e.record()
-    for _ in range(wreps):
-        warp_fn(d0, wflow)
-    w1e.record()
-    torch.cuda.synchronize()
-    warp_ms = w0e.elapsed_time(w1e) / wreps
+
+    def warp_loop(k):
+        for _ in range(k):
+            warp_fn(d0, wflow)
+
+    warp_loop(3)
+    warp_ms = _timed(warp_loop, wreps, lambda: torch.cuda.synchronize()) / wreps
     del wflow
 
     # ---- timed region 2 (`e2e`): pinned host pairs -> H2D -> Model.inference -> D2H of the interpolated volume through the
-    #      package's streaming front end (pipeline.StreamedInterpolator: upload / compute / download on three streams)
-    streamer = StreamedInterpolator(model, dev)
-    nbuf = 3
-    out_host = [torch.empty((pairs, 1) + tuple(sp), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    #      package's streaming front end (pipeline.StreamedInterpolator: upload / compute / download on three streams).  Byte
+    #      volumes (cfg 4) are exported the way the reference's inference driver exports them, `(merged * 255).byte()` computed on
+    #      the device before the `.cpu()` (Flow-3D/inference_img.py:105): bytes in, bytes out.  `e2e_f32` is the same run with the
+    #      fp32 result downloaded instead (Flow-3D/train.py:270 evaluates on it): the conservative figure.
+    def e2e_run(out_u8):
+        st = StreamedInterpolator(model, dev, out_u8=out_u8, depth=3)
+        nbuf = 4
+        outs = [torch.empty((pairs, 1) + tuple(sp), dtype=torch.uint8 if out_u8 else torch.float32).pin_memory() for _ in range(nbuf)]
 
-    def run_e2e(k):
-        for _ in streamer.run(((h0, h1) for _ in range(k)), (out_host[i % nbuf] for i in range(k))):
-            pass
+        def run(k):
+            for _ in st.run(((h0, h1) for _ in range(k)), (outs[i % nbuf] for i in range(k))):
+                pass            # returns when the last result has landed in host memory
 
-    run_e2e(min(args.warmup, 3))
-    barrier()
-    h2d0, d2h0 = streamer.h2d_bytes, streamer.d2h_bytes
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    run_e2e(args.steps)            # returns when the last result has landed in host memory
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    h2d_step = (streamer.h2d_bytes - h2d0) // args.steps
-    d2h_step = (streamer.d2h_bytes - d2h0) // args.steps
+        run(min(args.warmup, 3))
+        h2d0, d2h0 = st.h2d_bytes, st.d2h_bytes
+        t = _timed(run, args.steps, barrier)
+        return t, (st.h2d_bytes - h2d0) // args.steps, (st.d2h_bytes - d2h0) // args.steps
 
-    # ---- the same end-to-end path with the result exported as bytes on the device, `(merged * 255).byte()` — what the
-    #      reference's inference driver does before its `.cpu()` (Flow-3D/inference_img.py:105).  Reported NEXT TO `e2e` (which
-    #      stays the fp32 download): with 8 ranks sharing one host, the 268 MB/step/rank fp32 download is what halves `e2e`.
+    ms_e2e_f32, h2d_step, d2h_f32_step = e2e_run(False)
     ms_e2e_u8 = d2h_u8_step = None
-    try:
-        streamer8 = StreamedInterpolator(model, dev, out_u8=True)
-        out_host8 = [torch.empty((pairs, 1) + tuple(sp), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
-
-        def run_e2e8(k):
-            for _ in streamer8.run(((h0, h1) for _ in range(k)), (out_host8[i % nbuf] for i in range(k))):
-                pass
-
-        run_e2e8(min(args.warmup, 3))
-        barrier()
-        d8 = streamer8.d2h_bytes
-        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e6.record()
-        run_e2e8(args.steps)
-        e7.record()
-        barrier()
-        ms_e2e_u8 = e6.elapsed_time(e7)
-        d2h_u8_step = (streamer8.d2h_bytes - d8) // args.steps
-    except Exception as e:  # noqa: BLE001  (the extra figure must never take the bench line down)
-        print(f"[bench rank {rank}] e2e_u8 skipped: {e!r}", file=sys.stderr, flush=True)
-        ms_e2e_u8 = None
+    if bytes_in:
+        ms_e2e_u8, _, d2h_u8_step = e2e_run(True)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_e2e_u8 if ms_e2e_u8 is not None else float("inf")], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e_f32, ms_e2e_u8 if ms_e2e_u8 is not None else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        ms_e2e_u8 = float(t[2]) if float(t[2]) != float("inf") else None
+        ms, ms_e2e_f32 = float(t[0]), float(t[1])
+        ms_e2e_u8 = float(t[2]) if ms_e2e_u8 is not None else None
     if rank != 0:
         return
 
     peaks = load_peaks()
     total_pairs = pairs * world * args.steps
     value = total_pairs / (ms / 1e3)
-    e2e_value = total_pairs / (ms_e2e / 1e3)
     vox = 1
     for s in sp:
         vox *= s
+
+    def e2e_entry(t_ms, d2h, export):
+        return {"value": total_pairs / (t_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": t_ms / args.steps, "export": export}
+
+    e2e_f32 = e2e_entry(ms_e2e_f32, d2h_f32_step, "fp32 merged volume (Flow-3D/train.py:270)")
+    e2e = e2e_entry(ms_e2e_u8, d2h_u8_step, "(merged*255).byte() on the device (Flow-3D/inference_img.py:105); input was uint8") if bytes_in else e2e_f32
+
     flops_pair = 2.0 * ifnet_macs(nd, sp)
-    conv_cls = [k for k in classes if k.startswith("conv_")]
-    conv_ms = sum(classes[k][1] for k in conv_cls)
-    conv_n = sum(classes[k][0] for k in conv_cls)
-    share = {k: round(v[1] / ms_prof, 4) for k, v in classes.items()}
-    dominant = max(classes, key=lambda k: classes[k][1]) if classes else None
-    # tensor roofline of the conv engine: algorithmic FLOPs of all conv launches of the profile pass / their summed time
-    conv_tf = flops_pair * pairs * args.steps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
-    roofline = {"kernel": "+".join(sorted(conv_cls)), "bound": "tensor", "achieved": conv_tf, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": (conv_tf / peaks["tf_sustained"]) if conv_tf else None, "traffic": None,
-                "peak_source": peaks["src"] + " (sustained bf16)", "launches": conv_n, "share_of_step": round(conv_ms / ms_prof, 4),
-                "algorithmic_flops_per_pair": flops_pair}
+    roofline = roofline_hbm = roofline_stage = None
+    share, dominant = {}, None
+    if classes:
+        conv_cls = [k for k in classes if k.startswith("conv_")]
+        conv_ms = sum(classes[k][1] for k in conv_cls)
+        conv_n = sum(classes[k][0] for k in conv_cls)
+        share = {k: round(v[1] / ms_prof, 4) for k, v in classes.items()}
+        dominant = max(classes, key=lambda k: classes[k][1])
+        at256 = nd == 3 and tuple(sp) == (256, 256, 256)
+        # tensor roofline of the conv engine: algorithmic FLOPs of ALL conv launches of the profile pass / their summed time, against
+        # the BURST bf16 peak (the timed region is ~0.1 s at full clock; the sustained figure was taken at a 1342 MHz median)
+        conv_tf = flops_pair * pairs * args.steps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+        roofline = {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                    "frac": (conv_tf / peaks["tf_burst"]) if conv_tf else None,
+                    "traffic": (NCU_TRAFFIC["conv_all"] * pairs) if (at256 and NCU_TRAFFIC["conv_all"]) else None,
+                    "kernel": "+".join(sorted(conv_cls)), "frac_of_sustained_peak": (conv_tf / peaks["tf_sustained"]) if conv_tf else None,
+                    "peak_source": peaks["src"] + " (burst bf16; sustained %.0f)" % peaks["tf_sustained"], "launches": conv_n,
+                    "share_of_step": round(conv_ms / ms_prof, 4), "algorithmic_flops_per_pair": flops_pair,
+                    "traffic_source": NCU_TRAFFIC["source"]}
+        if layer_ms is not None and nd == 3:
+            # block2's first conv and final heads are HBM-bound at full resolution -> also on the HBM roofline.
+            # conv0.0: reads the 16-channel bf16 block input (32 B/voxel), writes 32 channels bf16 at 1/8 of the voxels (8 B/voxel);
+            # heads: read 64 channels bf16 at 1/8 of the voxels (16 B/voxel), read + write the fp32 flow/mask state (32 + 32 B/voxel)
+            hb = (32 + 8 + 16 + 32 + 32) * vox * pairs
+            ht = layer_ms[24] + layer_ms[35]
+            roofline_hbm = {"kernel": "block2.conv0.0 + block2 heads (conv_halo)", "bound": "hbm", "achieved": hb / (ht / 1e3) / 1e9,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hb / (ht / 1e3) / 1e9 / peaks["hbm_gbs"],
+                            "traffic": (NCU_TRAFFIC["conv_hbm_layers"] * pairs) if (at256 and NCU_TRAFFIC["conv_hbm_layers"]) else None,
+                            "ms_per_step": [round(layer_ms[24], 4), round(layer_ms[35], 4)], "algorithmic_bytes_per_step": hb}
+        bs = classes.get("block_stage")
+        if bs and nd == 3:
+            per_vox = [32 + 8 + 32 / 8.0,              # block0 -> 1: write state, read imgs, pooled bf16 input of block1 (head0 is L2-resident)
+                       32 + 32 + 8 + 32 + 4,           # block1 -> 2: read + write state, imgs, full-res bf16 input of block2, head1 (32 B / 8 voxels)
+                       32 + 8 + 8]                     # final: read the state (accumulated by the head conv), imgs, write merged + mask
+            stage_bytes = sum(per_vox) * vox * pairs * args.steps
+            sg = stage_bytes / (bs[1] / 1e3) / 1e9
+            roofline_stage = {"kernel": "stage3d_hfast_kernel", "bound": "hbm", "achieved": sg, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": sg / peaks["hbm_gbs"],
+                              "traffic": (NCU_TRAFFIC["stage"] * pairs) if (at256 and NCU_TRAFFIC["stage"]) else None,
+                              "traffic_unit": "bytes per step (3 launches)", "launches": bs[0], "share_of_step": round(bs[1] / ms_prof, 4),
+                              "algorithmic_bytes_per_voxel_per_scale": per_vox}
     # HBM roofline of the standalone warp kernel: (nd flow + 1 src + 1 out) * 4 B = 20 B/voxel in 3-D, 16 B/px in 2-D
     warp_bytes = (nd + 2) * 4 * vox * pairs
     warp_gbs = warp_bytes / (warp_ms / 1e3) / 1e9
     # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/r01q_ncu_full_warp3d_slab_4x256.csv:
-    # dram__bytes_read 1118.0 MB + write 254.1 MB for a 4 x 256^3 launch = 279.5 + 63.5 MB per volume; algorithmic 335.5 MB),
-    # scaled to this launch's volume count
+    # dram__bytes_read 1118.0 MB + write 254.1 MB for a 4 x 256^3 launch = 279.5 + 63.5 MB per volume; algorithmic 335.5 MB)
     warp_traffic = (279.5e6 + 63.5e6) * pairs if (nd == 3 and tuple(sp) == (256, 256, 256)) else None
     slab = nd == 3 and sp[0] == sp[1] == sp[2] and sp[0] % 32 == 0      # ofsv_warp3d_f32 picks the TMA slab kernel on such volumes
-    roofline_warp = {"kernel": "warp3d_slab_kernel" if slab else "warp%dd_kernel" % nd, "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": warp_traffic, "peak_source": peaks["src"],
+    roofline_warp = {"kernel": "warp3d_slab_kernel" if slab else "warp%dd_kernel" % nd, "bound": "hbm", "achieved": warp_gbs,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": warp_gbs / peaks["hbm_gbs"], "traffic": warp_traffic,
                      "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": warp_ms, "timed": "standalone, 10 launches"}
-    # HBM roofline of the fused block output stage (3-D): state read/write, img gathers, merged/mask, next block's input
-    roofline_stage = None
-    bs = classes.get("block_stage")
-    if bs and nd == 3:
-        per_vox = [32 + 8 + 32 / 8.0,                  # block0 -> 1: write state, read imgs, pooled bf16 input of block1 (head0 is L2-resident)
-                   32 + 32 + 8 + 32 + 4,               # block1 -> 2: read + write state, imgs, full-res bf16 input of block2, head1 (32 B / 8 voxels)
-                   32 + 8 + 8]                         # final: read the state (accumulated by the head conv), imgs, write merged + mask
-        stage_bytes = sum(per_vox) * vox * pairs * args.steps
-        sg = stage_bytes / (bs[1] / 1e3) / 1e9
-        # ncu --set full (profiles/r01n_ncu_full_block2_flow3d_256.csv, r01n_launches_flow3d_256.csv): the three stage launches of
-        # one 256^3 pair move 1.77 GB of DRAM reads + 1.68 GB of writes (algorithmic: 3.36 GB)
-        stage_traffic = 3.45e9 * pairs if tuple(sp) == (256, 256, 256) else None
-        roofline_stage = {"kernel": "block_stage_3d_kernel", "bound": "hbm", "achieved": sg, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": sg / peaks["hbm_gbs"], "traffic": stage_traffic, "traffic_unit": "bytes per step (3 launches)",
-                          "peak_source": peaks["src"], "launches": bs[0],
-                          "share_of_step": round(bs[1] / ms_prof, 4), "algorithmic_bytes_per_voxel_per_scale": per_vox}
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
+    cpu_baseline = cuda_eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cuda_eager = cuda_eager_rates(args.workload, CPU_SAMPLE[args.workload][0], dev)
+        except Exception as e:  # noqa: BLE001  (a context figure must never take the bench line down)
+            cuda_eager = {"unavailable": repr(e)[:200]}
         with contextlib.redirect_stdout(io.StringIO()):
-            if args.workload == "flow3d_droplet256":
-                # bounded sample: a 128^3 sub-volume pair = 1/8 of the voxels (and conv FLOPs) of one 256^3 pair
-                rate, dt, thr = cpu_reference_rate(3, (128, 128, 128), 1, 2, 1)
-                rate, sample = rate / 8.0, "128^3 sub-volume pair (1/8 of a 256^3 pair) x 2 calls after 1 warm-up; rate scaled by 1/8"
-            elif args.workload == "flow3d_rect128":
-                rate, dt, thr = cpu_reference_rate(3, (128, 128, 128), 1, 2, 1)
-                sample = "one 128^3 pair x 2 calls after 1 warm-up"
-            else:
-                rate, dt, thr = cpu_reference_rate(2, sp, 64, 3, 1)
-                sample = "64 pairs of 160x224 x 3 calls after 1 warm-up"
-        cpu_baseline = {"value": rate, "unit": "pairs/s", "cores": thr, "kind": "port", "sample": sample}
+            s_pairs, sample = CPU_SAMPLE[args.workload]
+            big = args.workload == "flow3d_droplet256"
+            rate, dt, thr = cpu_reference_rate(args.workload, s_pairs, 1 if big else 2, 0 if big else 1)
+        cpu_baseline = {"value": rate, "unit": "pairs/s", "cores": thr, "kind": "port",
+                        "sample": sample + ("; 1 call, no warm-up" if big else "; 2 calls after 1 warm-up")}
 
+    cfg = base_config(args.workload, pairs)
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "describes": desc, "spatial": list(sp), "pairs_per_gpu_per_step": pairs,
-                   "precision": args.precision, "conv_engine": model.flownet._engine(),
-                   "l2": "working set per step (>1 GB) exceeds the 126 MB L2; no explicit flush",
-                   "weights": "random init, seed 1234"},
-        "clocks": clk.summary(),
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                "ms_per_step": ms_e2e / args.steps,
-                "path": "pipeline.StreamedInterpolator(model).run(pinned host pairs): H2D / Model.inference / D2H on three streams"},
-        "e2e_u8": None if ms_e2e_u8 is None else {
-            "value": total_pairs / (ms_e2e_u8 / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
-            "d2h_bytes_per_step": int(d2h_u8_step), "ms_per_step": ms_e2e_u8 / args.steps,
-            "path": "as e2e, result downloaded as (merged*255).byte() computed on the device (Flow-3D/inference_img.py:105)"},
-        "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_warp": roofline_warp, "roofline_stage": roofline_stage, "kernel_time_share": share,
-        "dominant_kernel_class": dominant, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "e2e_f32": e2e_f32 if bytes_in else None,
+        "roofline": None if roofline is None else {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
+        "roofline_stage_frac": None if roofline_stage is None else round(roofline_stage["frac"], 4),
+        "roofline_conv_hbm_frac": None if roofline_hbm is None else round(roofline_hbm["frac"], 4),
+        "roofline_warp_frac": round(roofline_warp["frac"], 4),
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "cpu_baseline": cpu_baseline, "cuda_eager": cuda_eager,
+        "config": cfg,
+        "impl_config": {"precision": args.precision, "conv_engine": model.flownet._engine(), "cuda_graphs": graphs},
+        "e2e_path": "pipeline.StreamedInterpolator(model).run(pinned host pairs): H2D / Model.inference / D2H on three streams",
+        "roofline_detail": roofline, "roofline_conv_hbm": roofline_hbm, "roofline_stage": roofline_stage, "roofline_warp": roofline_warp,
+        "kernel_time_share": share, "dominant_kernel_class": dominant,
+        "conv_layer_ms_per_step": None if layer_ms is None else [round(v, 4) for v in layer_ms],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ UPFlow operator workload
+def run_upflow_ops(args, rank, world, local_rank):
+    """BASELINE.json configs[4] at the operator level: one step = forward AND backward of the §8a UPFlow operators the package
+    implements (WarpingLayer_no_div a11, correlation cost volume + LeakyReLU a8, upsample2d_flow_as a10) on the five pyramid levels of
+    a 256x832 pair at B = 16 (8 pairs x 2 directions per GPU), then the step's one collective — a SUM all-reduce of a flat fp32
+    gradient bucket of UPFlow's size (3 354 146 parameters = 13.4 MB) over NCCL — and the fused AdamW step on it.  The estimator /
+    context convolutions of UPFlow are NOT part of it."""
+    import torch
+    import torch.distributed as dist
+
+    from opticalflowscivis_b200 import ops
+    from opticalflowscivis_b200.optim import FusedAdamW, GradientBucket, allreduce_gradients
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.pairs or 16
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    lv = []
+    for (c, h, w) in UPFLOW_LEVELS:
+        r = lambda *shape: torch.randn(*shape, generator=g).to(dev)      # noqa: E731
+        lv.append({"c": c, "h": h, "w": w, "x": r(B, c, h, w), "f2": r(B, c, h, w), "fl": r(B, 2, h, w) * 2, "go": r(B, c, h, w),
+                   "g81": r(B, 81, h, w), "gup": r(B, 2, 2 * h, 2 * w)})
+    params = [torch.nn.Parameter(torch.zeros(UPFLOW_PARAMS, device=dev))]
+    bucket = GradientBucket(params)
+    opt = FusedAdamW(params, lr=1e-4, weight_decay=1e-4, bucket=bucket)
+    bucket.flat.normal_(generator=None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = {"corr_fwd": [], "corr_bwd": [], "allreduce": []}
+
+    def timed(key, fn, on):
+        if not on:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        ev[key].append((a, b))
+        return out
+
+    def step(k=1, prof=False):
+        for _ in range(k):
+            for L in lv:
+                ops.warping_no_div(L["x"], L["fl"])
+                timed("corr_fwd", lambda: ops.corr81_fwd(L["x"], L["f2"], leaky_slope=0.1), prof)
+                ops.upsample_flow_ac(L["fl"], 2 * L["h"], 2 * L["w"])
+            for L in reversed(lv):
+                ops.upsample_flow_ac_bwd(L["gup"], L["h"], L["w"])
+                timed("corr_bwd", lambda: ops.corr81_bwd(L["x"], L["f2"], L["g81"]), prof)
+                ops.warping_no_div_bwd(L["x"], L["fl"], L["go"])
+            scale = timed("allreduce", lambda: allreduce_gradients(bucket), prof)
+            opt.step(grad_scale=scale)
+
+    step(args.warmup)
+    n0 = ops.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = _timed(step, args.steps, barrier)
+    launches = ops.launch_count() - n0 + args.steps          # + the optimizer launch per step
+    ms_prof = _timed(lambda k: step(k, True), args.steps, barrier)
+    tot = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in ev.items()}
+    if world > 1:
+        t = torch.tensor([ms, tot["allreduce"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, tot["allreduce"] = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    corr_bytes = sum((2 * c + 81) * h * w * 4 * B for (c, h, w) in UPFLOW_LEVELS)
+    gbs = corr_bytes / (tot["corr_fwd"] / 1e3) / 1e9
+    line = {
+        "metric": metric_name("upflow_ops"), "value": world * args.steps / (ms / 1e3), "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "e2e": None,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None},
+        "allreduce_ms_per_step": tot["allreduce"], "allreduce_bytes": UPFLOW_PARAMS * 4,
+        "corr_fwd_ms_per_step": tot["corr_fwd"], "corr_bwd_ms_per_step": tot["corr_bwd"],
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "config": {"workload": "upflow_ops", "describes": run_upflow_ops.__doc__.split("\n\n")[0].replace("\n    ", " "),
+                   "levels_CHW": [list(v) for v in UPFLOW_LEVELS], "batch_per_gpu": B,
+                   "roofline_kernel": "corr81_fwd, five launches, algorithmic bytes (2C+81)*H*W*4*B = %d" % corr_bytes},
     }
     print(json.dumps(line), flush=True)
 
@@ -394,21 +557,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        with contextlib.redirect_stdout(sys.stderr):
-            pass
         run_reference_arm(args, rank, world)
         return
 
@@ -421,7 +582,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "ERROR")      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_upflow_ops if args.workload == "upflow_ops" else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

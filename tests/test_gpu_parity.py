@@ -212,6 +212,23 @@ def test_corr81_golden_leaky_and_concat_slice():
         assert np.abs(_np(g1) - z[f"corr{i}_g1"]).max() <= 5e-5 and np.abs(_np(g2) - z[f"corr{i}_g2"]).max() <= 5e-5
 
 
+def test_corr_pytorch_module_surface():
+    """UPFlow/utils/pytorch_correlation.py:10-50: `Corr_pyTorch(pad, k, md, s1, s2)(f1, f2)` — the module UPFlow builds at
+    upflow.py:359-361 and calls at :643-645 — against the golden vectors generated from the reference's own Corr_pyTorch."""
+    from opticalflowscivis_b200.upflow.utils.pytorch_correlation import Corr_pyTorch
+    z = np.load(os.path.join(G, "upflow_ops.npz"))
+    mod = Corr_pyTorch(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    for i in range(3):
+        f1 = torch.from_numpy(z[f"corr{i}_f1"]).to(_dev()).requires_grad_()
+        f2 = torch.from_numpy(z[f"corr{i}_f2"]).to(_dev()).requires_grad_()
+        out = mod(f1, f2)
+        assert np.abs(_np(out) - z[f"corr{i}_out"]).max() <= 5e-6
+        out.backward(torch.from_numpy(z[f"corr{i}_gout"]).to(_dev()))
+        assert np.abs(_np(f1.grad) - z[f"corr{i}_g1"]).max() <= 5e-5 and np.abs(_np(f2.grad) - z[f"corr{i}_g2"]).max() <= 5e-5
+    with pytest.raises(AssertionError):
+        Corr_pyTorch(pad_size=4, max_displacement=3)
+
+
 def test_upsample_flow_and_warping_layer():
     warnings.simplefilter("ignore")
     from opticalflowscivis_b200.upflow import WarpingLayer_no_div, upsample2d_flow_as
