@@ -20,35 +20,93 @@
 
 namespace ofsv {
 
-constexpr int HF_H = 32, HF_W = 8, HF_DZ = 8;
-#ifndef OFSV_HF_HEAD_MODE
-#define OFSV_HF_HEAD_MODE 0      // 0: both x-lerped coarse rows re-loaded every plane; 1: kept across planes that share a coarse z tap
-#endif
-#ifndef OFSV_HF_OWN_PREFETCH
-#define OFSV_HF_OWN_PREFETCH 1   // 1: the voxel's own image values are loaded one plane ahead
-#endif
+constexpr int HF_H = 32, HF_W = 8;
 
 struct V8 { float v[8]; };
 __device__ __forceinline__ V8 ldg256(const float* p) {
   V8 r;
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ V8 ldg256_stream(const float* p) {
+  V8 r;
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 v;
+#if OFSV_HF_STREAM
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#else
+  v = __ldg(reinterpret_cast<const float2*>(p));
+#endif
+  return v;
+}
 __device__ __forceinline__ void stg256(float* p, const V8& r) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
-               "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
-               : "memory");
+               "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]));
 }
 __device__ __forceinline__ void stg256_b32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
                                            uint32_t h) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
-               : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h));
 }
 __device__ __forceinline__ uint32_t hf_pack2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Pure (non-volatile, no memory clobber) read-only loads: the compiler may hoist them over the kernel's stores — none of which is
+// ever read back by the kernel — so that the gathers of the next voxel overlap the arithmetic and the stores of the current one.
+__device__ __forceinline__ float hf_ldg(const float* p) {
+  float v;
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ Taps8 hf_gather(const float* p, const Trilin& t) {
+  const uint32_t i0 = t.base, i1 = i0 + t.dx, i2 = i0 + t.dy, i3 = i2 + t.dx;
+  Taps8 r;
+  r.v[0] = hf_ldg(p + i0); r.v[1] = hf_ldg(p + i1); r.v[2] = hf_ldg(p + i2); r.v[3] = hf_ldg(p + i3);
+  r.v[4] = hf_ldg(p + (i0 + t.dz)); r.v[5] = hf_ldg(p + (i1 + t.dz)); r.v[6] = hf_ldg(p + (i2 + t.dz)); r.v[7] = hf_ldg(p + (i3 + t.dz));
+  return r;
+}
+__device__ __forceinline__ void hf_st2(float* p, float2 v) {
+  asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y));
+}
+
+// U consecutive floats (U = 2, 4, 8) as one 8 / 16 / 32-byte access
+template <int U>
+struct VecF { float v[U]; };
+template <int U>
+__device__ __forceinline__ VecF<U> ldg_vec(const float* p) {
+  VecF<U> r;
+  if (U == 8) {
+    const V8 t = ldg256_stream(p);
+#pragma unroll
+    for (int i = 0; i < U; ++i) r.v[i] = t.v[i];
+  } else if (U == 4) {
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2 % U]), "=f"(r.v[3 % U]) : "l"(p));
+  } else {
+    const float2 t = ldg_stream2(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+template <int U>
+__device__ __forceinline__ void stg_vec(float* p, const VecF<U>& r) {
+  if (U == 8) {
+    V8 t;
+#pragma unroll
+    for (int i = 0; i < U; ++i) t.v[i] = r.v[i];
+    stg256(p, t);
+  } else if (U == 4) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2 % U]), "f"(r.v[3 % U]));
+  } else {
+    hf_st2(p, make_float2(r.v[0], r.v[1]));
+  }
 }
 
 struct HfLerp {
@@ -86,95 +144,112 @@ struct HfPtrs {
   float* fm_out; float* merged; float* mask_sig; __nv_bfloat16* pack_out;
 };
 
+// Keeps a per-sample base pointer in ONE 64-bit register pair: without it nvcc re-adds the (uniform) sample offset to every tap
+// address — IADD3 + IADD3.X + LEA + LEA.HI.X per gather instead of one IMAD.WIDE.U32 (48 of the final stage's 344 instructions).
+template <typename T>
+__device__ __forceinline__ T* hf_pin(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // SH: scale of the head (1, 2, 4), or 0 = fm_prev already holds the accumulated state (nothing is added, fm_out not written).
 // SN: 0 = no packed output, 1 = next block at full resolution, 2 = at half resolution (2x2x2 mean).
-template <int SH, int SN, bool S2D, bool FMA>
-__global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : 3) stage3d_hfast_kernel(const HfPtrs q, const Warp3dParams P) {
-  __shared__ float s_out[2][2][HF_H][HF_W + 1];                     // [buffer][merged | mask][h][w]
-  __shared__ float s_pool[SN == 2 ? 22 : 1][HF_H][HF_W + 1];        // [plane parity * 11 + channel][h][w]
+//
+// Work distribution.  A CTA owns a 32 (h) x 8 (w) column of HF_DZ = 16 planes; warp q owns the plane pair (2q, 2q+1) and a THREAD
+// owns the 8 consecutive w of its (d, h): everything that is laid out [D][H][W] — the voxel's own image values going into the next
+// block's input, merged, sigmoid(mask) — is then ONE 256-bit access per lane per plane (a full 32 B sector) instead of 8 scalar
+// accesses spread over 8 warps, each of which costs an L1 wavefront per lane (the first version of this kernel spent 64 of its
+// ~160 L1 wavefronts per 32 voxels on the own-image loads and needed a shared tile + block barrier per plane for the planar
+// outputs: ncu l1tex throughput 83-86 % on the two up-sampling stages).  Walking along w also walks through consecutive source
+// planes of the axis-rotating warp (z ~ w), whose z+1 taps are the next voxel's z taps.  The 2x2x2 mean of SN == 2 never leaves the
+// warp: the w pair is two consecutive iterations, the h pair the neighbouring lane (one shuffle per channel), the d pair the warp's
+// second plane.  No shared memory, no barrier.
+#ifndef OFSV_HF_U_UP
+#define OFSV_HF_U_UP 8        // columns of a thread processed as one unrolled group (stages that write a state / a packed input)
+#endif
+#ifndef OFSV_HF_U_FIN
+#define OFSV_HF_U_FIN 8       // same, final stage (state in, merged + mask out)
+#endif
+#ifndef OFSV_HF_PP
+#define OFSV_HF_PP 2          // planes per warp
+#endif
+#ifndef OFSV_HF_MINB_UP
+#define OFSV_HF_MINB_UP 2     // resident CTAs per SM the register allocation aims at: stages that write a state / a packed input ...
+#endif
+#ifndef OFSV_HF_MINB_POOL
+#define OFSV_HF_MINB_POOL 2   // ... the stage with the 2x2x2 mean ...
+#endif
+#ifndef OFSV_HF_MINB_FIN
+#define OFSV_HF_MINB_FIN 3    // ... and the final stage (state in, merged + mask out)
+#endif
+#ifndef OFSV_HF_STREAM
+#define OFSV_HF_STREAM 1      // 1: streaming loads (previous state, own image values) do not allocate in L1, which is left to the gathers
+#endif
+constexpr int HF_PP = OFSV_HF_PP;
+constexpr int HF_DZ = 8 * HF_PP;   // planes per CTA: 8 warps x HF_PP
+struct HfVox {
+  V8 st;          // flow 0..5, mask logit, 0
+  float a, b;     // warped img0 / img1
+};
 
+template <int SH, int SN, bool S2D, bool FMA>
+__global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? OFSV_HF_MINB_FIN : (SN == 2 ? OFSV_HF_MINB_POOL : OFSV_HF_MINB_UP)) stage3d_hfast_kernel(const HfPtrs q, const Warp3dParams P) {
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int V = D * HW;                                             // < 2^28 (host check)
   const int nzb = (D + HF_DZ - 1) / HF_DZ;
   const int n = blockIdx.z / nzb, dbeg = (blockIdx.z - n * nzb) * HF_DZ;
-  const int nplanes = min(HF_DZ, D - dbeg);
-  const int h0 = blockIdx.y * HF_H, w0 = blockIdx.x * HF_W;
-  const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;
-  const int h = h0 + lane, w = w0 + wl;
-  const bool ok = h < H && w < W;
-  const int hc = min(h, H - 1), wc = min(w, W - 1);                 // clamped: out-of-tile lanes compute on a valid voxel and store nothing
-  const int rP = tid >> 3, cP = tid & 7;                            // planar-output mapping: 8 consecutive threads = one tile row
-  const bool okP = (h0 + rP) < H && (w0 + cP) < W;
+  const int h0 = blockIdx.y * HF_H, w0 = blockIdx.x * HF_W;         // W % 8 == 0 (host check): the 8 columns of a thread all exist
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const int h = h0 + lane;
+  const bool okh = h < H;
+  const int hc = min(h, H - 1);                                     // clamped: out-of-tile lanes compute on a valid voxel and store nothing
   constexpr int SHD = SH > 1 ? SH : 1;
+  constexpr int NROWS = SH > 1 ? HF_H / SHD + 2 : 0;                // coarse head rows a 32-row tile can touch
   const int Dh = D / SHD, Hh = H / SHD, Wh = W / SHD;
-  const float* hb = SH ? q.head + (int64_t)n * Dh * Hh * Wh * 8 : nullptr;
-  const float* fprev = q.fm_prev ? q.fm_prev + (int64_t)n * V * 8 : nullptr;
-  float* fout = SH ? q.fm_out + (int64_t)n * V * 8 : nullptr;
-  const float* i0p = q.img0 + (int64_t)n * V;
-  const float* i1p = q.img1 + (int64_t)n * V;
+  const float* hb = SH ? hf_pin(q.head + (int64_t)n * Dh * Hh * Wh * 8) : nullptr;
+  const float* fprev = q.fm_prev ? hf_pin(q.fm_prev + (int64_t)n * V * 8) : nullptr;
+  float* fout = SH ? hf_pin(q.fm_out + (int64_t)n * V * 8) : nullptr;
+  const float* i0p = hf_pin(q.img0 + (int64_t)n * V);
+  const float* i1p = hf_pin(q.img1 + (int64_t)n * V);
   const bool has_prev = fprev != nullptr;
   const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
-  const float lh = __ldg(q.lin_h + hc), lw = __ldg(q.lin_w + wc);
-  // in-plane element offset of this thread's voxel in the [W][H] state planes and the [H][W] image planes
-  const int so = wc * H + hc;
+  const float lh = __ldg(q.lin_h + hc);
+  const int d0 = dbeg + HF_PP * wq;                                 // this warp's plane group
+  if (d0 >= D) return;                                              // warp-uniform; nothing below synchronises across warps
 
-  // up-sampled head: per-axis taps.  w (x) and d (z) taps are warp-uniform; the h (y) taps are per lane.  Lane L also OWNS coarse
-  // row hb0 + L of the tile: it evaluates the x lerp of that row for both z taps, the fine lanes pick rows (y0 - hb0, y1 - hb0).
-  HfLerp Ly{0, 0, 0.f, 0.f}, Lx{0, 0, 0.f, 0.f};
+  // up-sampled head: per-axis taps.  w (x) and d (z) taps are warp-uniform; the h (y) taps are per lane.  Lane L < NROWS also OWNS
+  // coarse row hb0 + L of the tile: it evaluates the x lerp of that row for both z taps, the fine lanes pick rows (y0 - hb0, y1 - hb0).
+  HfLerp Ly{0, 0, 0.f, 0.f};
   int hb0 = 0, own = 0;
   if (SH > 1) {
     const float rs = 1.0f / (float)SHD;
     Ly = hf_up_index(hc, Hh, rs);
-    Lx = hf_up_index(wc, Wh, rs);
     hb0 = hf_up_index(h0, Hh, rs).i0;
     own = min(hb0 + lane, Hh - 1);
   }
+  const int s0 = Ly.i0 - hb0, s1 = Ly.i1 - hb0;                     // owner lanes of this lane's two coarse rows (< NROWS)
 
-  V8 pv;                                                            // previous state of the plane being processed (prefetched)
-  if (has_prev) pv = ldg256(fprev + ((int64_t)dbeg * HW + so) * 8);
-  // own image values (channels 0, 1 of the next block's input): lanes along h read 32 different lines per request; moving them
-  // through a coalescing shared tile needs a block barrier per plane, which measured slower (568 vs 485 us per 256^3 pair for the
-  // middle stage) than the direct loads issued one plane ahead
-  const int io = hc * W + wc;
-#if OFSV_HF_OWN_PREFETCH
-  float pi0 = 0.f, pi1 = 0.f;
-  if (SN != 0) { pi0 = __ldg(i0p + dbeg * HW + io); pi1 = __ldg(i1p + dbeg * HW + io); }
-#endif
-  // x-lerped coarse head rows of the two z taps, kept across planes (consecutive planes share one or both coarse z taps)
-  V8 a0, a1;
-  int cz0 = -1, cz1 = -1;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a0.v[i] = 0.f; a1.v[i] = 0.f; }
-
-  for (int it = 0; it < nplanes; ++it) {
-    const int d = dbeg + it;
-    const float ld = __ldg(q.lin_d + d);
-    V8 st;                                                          // flow 0..5, mask logit, 0
-    V8 cur = pv;
-    if (has_prev && it + 1 < nplanes) pv = ldg256(fprev + ((int64_t)(d + 1) * HW + so) * 8);
+  // one voxel (d, hc, w): state update + the two warps.  `cur` = its previous state (prefetched by the caller).
+  auto voxel = [&](int d, int w, float ld, const HfLerp& Lz, const V8& cur) -> HfVox {
+    HfVox o;
+    const int so = w * H + hc;
+    const float lw = hf_ldg(q.lin_w + w);
     if (SH != 0) {
       V8 hv;
       if (SH == 1) {
         hv = ldg256(hb + ((int64_t)d * HW + so) * 8);
       } else {
-        const HfLerp Lz = hf_up_index(d, Dh, 1.0f / (float)SHD);
-        const int c0 = Lx.i0 * Hh + own, c1 = Lx.i1 * Hh + own;
-        // x lerp of coarse row `own` for the two z taps (ATen order: x, then y, then z); warp-uniform reuse across planes
-        auto xrow = [&](int z) -> V8 {
-          const int64_t r = ((int64_t)z * Wh) * Hh;
-          return hf_lerp8(ldg256(hb + (r + c0) * 8), Lx.l0, ldg256(hb + (r + c1) * 8), Lx.l1);
-        };
-#if OFSV_HF_HEAD_MODE == 0
-        a0 = xrow(Lz.i0);                                          // every lane loads (rows beyond the tile's 32/SH + 2 are never read)
-        a1 = xrow(Lz.i1);
-#else
-        if (Lz.i0 != cz0 || Lz.i1 != cz1) {                         // warp-uniform: consecutive planes share one or both coarse z taps
-          if (Lz.i0 == cz1) a0 = a1; else a0 = xrow(Lz.i0);
-          if (Lz.i1 == Lz.i0) a1 = a0; else a1 = xrow(Lz.i1);
-          cz0 = Lz.i0; cz1 = Lz.i1;
+        const HfLerp Lx = hf_up_index(w, Wh, 1.0f / (float)SHD);
+        V8 a0, a1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0.v[i] = 0.f; a1.v[i] = 0.f; }
+        if (lane < NROWS) {
+          // x lerp of coarse row `own` for the two z taps (ATen order: x, then y, then z)
+          const int c0 = Lx.i0 * Hh + own, c1 = Lx.i1 * Hh + own;
+          const int r0 = Lz.i0 * Wh * Hh, r1 = Lz.i1 * Wh * Hh;
+          a0 = hf_lerp8(ldg256(hb + (int64_t)(r0 + c0) * 8), Lx.l0, ldg256(hb + (int64_t)(r0 + c1) * 8), Lx.l1);
+          a1 = hf_lerp8(ldg256(hb + (int64_t)(r1 + c0) * 8), Lx.l0, ldg256(hb + (int64_t)(r1 + c1) * 8), Lx.l1);
         }
-#endif
-        const int s0 = Ly.i0 - hb0, s1 = Ly.i1 - hb0;              // owner lanes of this lane's two coarse rows (< 32/SH + 2)
         const V8 b0 = hf_lerp8(hf_shfl8(a0, s0), Ly.l0, hf_shfl8(a0, s1), Ly.l1);
         const V8 b1 = hf_lerp8(hf_shfl8(a1, s0), Ly.l0, hf_shfl8(a1, s1), Ly.l1);
         hv = hf_lerp8(b0, Lz.l0, b1, Lz.l1);
@@ -182,30 +257,234 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : 3) stage3d_hfa
       const float sh = (float)SHD;
       if (has_prev) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) st.v[i] = __fadd_rn(cur.v[i], __fmul_rn(hv.v[i], sh));
-        st.v[6] = __fadd_rn(cur.v[6], hv.v[6]);
+        for (int i = 0; i < 6; ++i) o.st.v[i] = __fadd_rn(cur.v[i], __fmul_rn(hv.v[i], sh));
+        o.st.v[6] = __fadd_rn(cur.v[6], hv.v[6]);
       } else {                                                      // block 0: flow = flow_d exactly
 #pragma unroll
-        for (int i = 0; i < 6; ++i) st.v[i] = __fmul_rn(hv.v[i], sh);
-        st.v[6] = hv.v[6];
+        for (int i = 0; i < 6; ++i) o.st.v[i] = __fmul_rn(hv.v[i], sh);
+        o.st.v[6] = hv.v[6];
       }
-      st.v[7] = 0.0f;
-      if (ok) stg256(fout + ((int64_t)d * HW + so) * 8, st);
+      o.st.v[7] = 0.0f;
+      if (okh) stg256(fout + ((int64_t)d * HW + so) * 8, o.st);
     } else {
-      st = cur;
+      o.st = cur;
     }
-    // ---------------- warps / blend
+    const Trilin t0 = trilin_setup(o.st.v[0], o.st.v[1], o.st.v[2], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+    const Trilin t1 = trilin_setup(o.st.v[3], o.st.v[4], o.st.v[5], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
+    const Taps8 g0 = hf_gather(i0p, t0), g1 = hf_gather(i1p, t1);       // 16 independent loads in flight
+    o.a = trilin_reduce<FMA>(g0, t0);
+    o.b = trilin_reduce<FMA>(g1, t1);
+    return o;
+  };
+  auto state_at = [&](int d, int w) -> V8 {
+    const float* p = fprev + ((int64_t)d * HW + w * H + hc) * 8;
+    return OFSV_HF_STREAM ? ldg256_stream(p) : ldg256(p);
+  };
+  auto blend = [&](const HfVox& o, float& mg, float& ms) {
+    ms = sigmoidf_ref(o.st.v[6]);
+    mg = __fadd_rn(__fmul_rn(o.a, ms), __fmul_rn(o.b, __fsub_rn(1.0f, ms)));
+  };
+
+  if (SN != 2) {
+    // ------------------------------------------------------------------ plane by plane, U columns of the thread as one unrolled group
+    constexpr int U = (SH == 0 && SN == 0) ? OFSV_HF_U_FIN : OFSV_HF_U_UP;
+    V8 pv;
+    if (has_prev) pv = state_at(d0, w0);
+#pragma unroll 1
+    for (int p = 0; p < HF_PP; ++p) {
+      const int d = d0 + p;                                         // D % HF_PP == 0 (host check)
+      const float ld = __ldg(q.lin_d + d);
+      const HfLerp Lz = SH > 1 ? hf_up_index(d, Dh, 1.0f / (float)SHD) : HfLerp{0, 0, 0.f, 0.f};
+#pragma unroll 1
+      for (int kc = 0; kc < HF_W; kc += U) {
+        const int64_t prow = (int64_t)d * HW + hc * W + w0 + kc;    // U of this thread's voxels in the [D][H][W] planes (4U-byte aligned)
+        VecF<U> o0, o1, mg, ms;
+        if (SN == 1) { o0 = ldg_vec<U>(i0p + prow); o1 = ldg_vec<U>(i1p + prow); }
+#pragma unroll
+        for (int ku = 0; ku < U; ++ku) {
+          const int k = kc + ku, w = w0 + k;
+          const V8 cur = pv;
+          const bool more = k + 1 < HF_W || p + 1 < HF_PP;
+          if (has_prev && more) pv = (k + 1 < HF_W) ? state_at(d, w + 1) : state_at(d + 1, w0);
+          const HfVox o = voxel(d, w, ld, Lz, cur);
+          if (need_m) blend(o, mg.v[ku], ms.v[ku]);
+          if (SN == 1 && okh) {
+            int64_t ro;
+            if (S2D) ro = s2d_row(3, n, d, h, w, D, H, W) * 16;
+            else ro = ((((int64_t)n * D + d) * H + h) * W + w) * 16;
+            stg256_b32(q.pack_out + ro, hf_pack2(o0.v[ku], o1.v[ku]), hf_pack2(o.a, o.b), hf_pack2(o.st.v[6], o.st.v[0]),
+                       hf_pack2(o.st.v[1], o.st.v[2]), hf_pack2(o.st.v[3], o.st.v[4]), hf_pack2(o.st.v[5], 0.0f), 0u, 0u);
+          }
+        }
+        if (need_m && okh) {
+          if (q.merged) stg_vec<U>(q.merged + (int64_t)n * V + prow, mg);
+          if (q.mask_sig) stg_vec<U>(q.mask_sig + (int64_t)n * V + prow, ms);
+        }
+      }
+    }
+    return;
+  }
+  // Order: w pair -> the PP planes of the warp -> the two columns of the pair.  Neighbouring planes and columns share source rows
+  // of the axis-rotating warp (voxel (d, w) taps rows (z, y) = (w..w+1, d..d+1)): walking w with the planes innermost touches
+  // PP + 1 new 128-byte row segments per image for PP voxels and needs only the last few iterations to still be in L1.
+  // The 2x2x2 mean of SN == 2 (== F.interpolate(., 0.5)) nests W, H, D like ATen, each level 0.5 * a + 0.5 * b, lower index first.
+  constexpr int PP = HF_PP;
+  float ldv[PP];
+  HfLerp Lzv[PP];
+#pragma unroll
+  for (int p = 0; p < PP; ++p) {
+    ldv[p] = __ldg(q.lin_d + d0 + p);
+    Lzv[p] = SH > 1 ? hf_up_index(d0 + p, Dh, 1.0f / (float)SHD) : HfLerp{0, 0, 0.f, 0.f};
+  }
+  V8 pv;
+  if (has_prev) pv = state_at(d0, w0);
+#pragma unroll 1
+  for (int kp = 0; kp < HF_W / 2; ++kp) {
+    float pd[11];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      const int d = d0 + p;                                         // D % PP == 0 (host check): every plane of the group exists
+      const int64_t prow = (int64_t)d * HW + hc * W + w0 + 2 * kp;  // this thread's column pair in the [D][H][W] planes (8 B aligned)
+      float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+      if (SN != 0) { o0 = ldg_stream2(i0p + prow); o1 = ldg_stream2(i1p + prow); }
+      float pw[11];
+      float2 mg, ms;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int w = w0 + 2 * kp + kk;
+        const V8 cur = pv;
+        const bool more = !(kk == 1 && p == PP - 1 && kp == HF_W / 2 - 1);
+        if (has_prev && more) pv = kk == 0 ? state_at(d, w + 1) : (p < PP - 1 ? state_at(d + 1, w - 1) : state_at(d0, w + 1));
+        const HfVox o = voxel(d, w, ldv[p], Lzv[p], cur);
+        if (need_m) blend(o, kk ? mg.y : mg.x, kk ? ms.y : ms.x);
+        if (SN == 1 && okh) {
+          int64_t ro;
+          if (S2D) ro = s2d_row(3, n, d, h, w, D, H, W) * 16;
+          else ro = ((((int64_t)n * D + d) * H + h) * W + w) * 16;
+          stg256_b32(q.pack_out + ro, hf_pack2(kk ? o0.y : o0.x, kk ? o1.y : o1.x), hf_pack2(o.a, o.b), hf_pack2(o.st.v[6], o.st.v[0]),
+                     hf_pack2(o.st.v[1], o.st.v[2]), hf_pack2(o.st.v[3], o.st.v[4]), hf_pack2(o.st.v[5], 0.0f), 0u, 0u);
+        }
+        if (SN == 2) {
+          const float c11[11] = {kk ? o0.y : o0.x, kk ? o1.y : o1.x, o.a, o.b, o.st.v[6], o.st.v[0], o.st.v[1], o.st.v[2], o.st.v[3],
+                                 o.st.v[4], o.st.v[5]};
+#pragma unroll
+          for (int c = 0; c < 11; ++c) pw[c] = kk == 0 ? __fmul_rn(c11[c], 0.5f) : __fadd_rn(pw[c], __fmul_rn(c11[c], 0.5f));
+        }
+      }
+      if (need_m && okh) {
+        if (q.merged) hf_st2(q.merged + (int64_t)n * V + prow, mg);
+        if (q.mask_sig) hf_st2(q.mask_sig + (int64_t)n * V + prow, ms);
+      }
+      if (SN == 2) {
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+          const float up = __shfl_down_sync(0xffffffffu, pw[c], 1); // row h + 1 (used by the even lanes only)
+          const float ph = __fadd_rn(__fmul_rn(pw[c], 0.5f), __fmul_rn(up, 0.5f));
+          if ((p & 1) == 0) pd[c] = ph;
+          else pd[c] = __fadd_rn(__fmul_rn(pd[c], 0.5f), __fmul_rn(ph, 0.5f));
+        }
+        if ((p & 1) && !(lane & 1) && okh) {
+          const int oh = h >> 1, ow = (w0 >> 1) + kp, od = d >> 1;
+#pragma unroll
+          for (int c = 5; c < 11; ++c) pd[c] = __fmul_rn(pd[c], 0.5f);             // flow channels additionally * 0.5
+          int64_t ro;
+          if (S2D) ro = s2d_row(3, n, od, oh, ow, D / 2, H / 2, W / 2) * 16;
+          else ro = ((((int64_t)n * (D / 2) + od) * (H / 2) + oh) * (W / 2) + ow) * 16;
+          stg256_b32(q.pack_out + ro, hf_pack2(pd[0], pd[1]), hf_pack2(pd[2], pd[3]), hf_pack2(pd[4], pd[5]), hf_pack2(pd[6], pd[7]),
+                     hf_pack2(pd[8], pd[9]), hf_pack2(pd[10], 0.0f), 0u, 0u);
+        }
+      }
+    }
+  }
+}
+
+// Column variant for the stages that write the next block's input at FULL resolution (SN == 1: one 32-byte packed row per voxel,
+// nothing to vectorise along w): warp q owns ONE w column of a 32 (h) x 8 (w) tile and walks HF_CDZ planes, so everything that depends
+// on w only (x taps of the head interpolation, linspace entry, plane offsets) is hoisted out of the loop.  Measured against the
+// row variant above on the block1 -> block2 stage of a 4 x 256^3 batch: 1773 us vs 1840-2150 us (any unroll / occupancy choice).
+// merged / sigmoid(mask), when requested (IFNet.forward with all three blends), go through a shared tile + one barrier per plane.
+constexpr int HF_CDZ = 8;
+template <int SH, bool S2D, bool FMA>
+__global__ void __launch_bounds__(256, 3) stage3d_hfast_cols_kernel(const HfPtrs q, const Warp3dParams P) {
+  __shared__ float s_out[2][2][HF_H][HF_W + 1];                     // [buffer][merged | mask][h][w]
+  const int H = P.H, W = P.W, D = P.D, HW = H * W;
+  const int V = D * HW;
+  const int nzb = (D + HF_CDZ - 1) / HF_CDZ;
+  const int n = blockIdx.z / nzb, dbeg = (blockIdx.z - n * nzb) * HF_CDZ;
+  const int nplanes = min(HF_CDZ, D - dbeg);
+  const int h0 = blockIdx.y * HF_H, w0 = blockIdx.x * HF_W;
+  const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;
+  const int h = h0 + lane, w = w0 + wl;                             // W % 8 == 0 (host check): w < W
+  const bool okh = h < H;
+  const int hc = min(h, H - 1);
+  const int rP = tid >> 3, cP = tid & 7;                            // planar-output mapping: 8 consecutive threads = one tile row
+  const bool okP = (h0 + rP) < H;
+  constexpr int SHD = SH > 1 ? SH : 1;
+  constexpr int NROWS = SH > 1 ? HF_H / SHD + 2 : 0;
+  const int Dh = D / SHD, Hh = H / SHD, Wh = W / SHD;
+  const float* hb = hf_pin(q.head + (int64_t)n * Dh * Hh * Wh * 8);
+  const float* fprev = q.fm_prev ? hf_pin(q.fm_prev + (int64_t)n * V * 8) : nullptr;
+  float* fout = hf_pin(q.fm_out + (int64_t)n * V * 8);
+  const float* i0p = hf_pin(q.img0 + (int64_t)n * V);
+  const float* i1p = hf_pin(q.img1 + (int64_t)n * V);
+  const bool has_prev = fprev != nullptr;
+  const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+  const float lh = __ldg(q.lin_h + hc), lw = __ldg(q.lin_w + w);
+  const int so = w * H + hc, io = hc * W + w;                       // in-plane offsets: [W][H] state planes, [H][W] image planes
+  HfLerp Ly{0, 0, 0.f, 0.f}, Lx{0, 0, 0.f, 0.f};
+  int hb0 = 0, own = 0;
+  if (SH > 1) {
+    const float rs = 1.0f / (float)SHD;
+    Ly = hf_up_index(hc, Hh, rs);
+    Lx = hf_up_index(w, Wh, rs);
+    hb0 = hf_up_index(h0, Hh, rs).i0;
+    own = min(hb0 + lane, Hh - 1);
+  }
+  const int s0 = Ly.i0 - hb0, s1 = Ly.i1 - hb0;
+  const int c0 = Lx.i0 * Hh + own, c1 = Lx.i1 * Hh + own;
+  V8 pv;
+  if (has_prev) pv = ldg256(fprev + ((int64_t)dbeg * HW + so) * 8);
+  float pi0 = hf_ldg(i0p + dbeg * HW + io), pi1 = hf_ldg(i1p + dbeg * HW + io);     // own image values, one plane ahead
+  for (int it = 0; it < nplanes; ++it) {
+    const int d = dbeg + it;
+    const float ld = __ldg(q.lin_d + d);
+    const V8 cur = pv;
+    if (has_prev && it + 1 < nplanes) pv = ldg256(fprev + ((int64_t)(d + 1) * HW + so) * 8);
+    V8 hv, st;
+    if (SH == 1) {
+      hv = ldg256(hb + ((int64_t)d * HW + so) * 8);
+    } else {
+      const HfLerp Lz = hf_up_index(d, Dh, 1.0f / (float)SHD);
+      V8 a0, a1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0.v[i] = 0.f; a1.v[i] = 0.f; }
+      if (lane < NROWS) {                                           // x lerp of coarse row `own` for the two z taps (ATen order: x, y, z)
+        const int r0 = Lz.i0 * Wh * Hh, r1 = Lz.i1 * Wh * Hh;
+        a0 = hf_lerp8(ldg256(hb + (int64_t)(r0 + c0) * 8), Lx.l0, ldg256(hb + (int64_t)(r0 + c1) * 8), Lx.l1);
+        a1 = hf_lerp8(ldg256(hb + (int64_t)(r1 + c0) * 8), Lx.l0, ldg256(hb + (int64_t)(r1 + c1) * 8), Lx.l1);
+      }
+      const V8 b0 = hf_lerp8(hf_shfl8(a0, s0), Ly.l0, hf_shfl8(a0, s1), Ly.l1);
+      const V8 b1 = hf_lerp8(hf_shfl8(a1, s0), Ly.l0, hf_shfl8(a1, s1), Ly.l1);
+      hv = hf_lerp8(b0, Lz.l0, b1, Lz.l1);
+    }
+    const float sh = (float)SHD;
+    if (has_prev) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) st.v[i] = __fadd_rn(cur.v[i], __fmul_rn(hv.v[i], sh));
+      st.v[6] = __fadd_rn(cur.v[6], hv.v[6]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) st.v[i] = __fmul_rn(hv.v[i], sh);
+      st.v[6] = hv.v[6];
+    }
+    st.v[7] = 0.0f;
+    if (okh) stg256(fout + ((int64_t)d * HW + so) * 8, st);
     const float m = st.v[6];
     const Trilin t0 = trilin_setup(st.v[0], st.v[1], st.v[2], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
     const Trilin t1 = trilin_setup(st.v[3], st.v[4], st.v[5], lh, ld, lw, D, H, W, P.hs, P.ref_mode);
-    const Taps8 g0 = trilin_gather(i0p, t0), g1 = trilin_gather(i1p, t1);     // 16 independent loads in flight
-#if OFSV_HF_OWN_PREFETCH
+    const Taps8 g0 = hf_gather(i0p, t0), g1 = hf_gather(i1p, t1);
     const float i0v = pi0, i1v = pi1;
-    if (SN != 0 && it + 1 < nplanes) { pi0 = __ldg(i0p + (d + 1) * HW + io); pi1 = __ldg(i1p + (d + 1) * HW + io); }
-#else
-    float i0v = 0.f, i1v = 0.f;
-    if (SN != 0) { i0v = __ldg(i0p + d * HW + io); i1v = __ldg(i1p + d * HW + io); }
-#endif
+    if (it + 1 < nplanes) { pi0 = hf_ldg(i0p + (d + 1) * HW + io); pi1 = hf_ldg(i1p + (d + 1) * HW + io); }
     const float a = trilin_reduce<FMA>(g0, t0), b = trilin_reduce<FMA>(g1, t1);
     const int ob = it & 1;
     if (need_m) {
@@ -213,63 +492,37 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? 4 : 3) stage3d_hfa
       s_out[ob][0][lane][wl] = __fadd_rn(__fmul_rn(a, ms), __fmul_rn(b, __fsub_rn(1.0f, ms)));
       s_out[ob][1][lane][wl] = ms;
     }
-    if (SN == 1) {
-      if (ok) {
-        int64_t ro;
-        if (S2D) ro = s2d_row(3, n, d, h, w, D, H, W) * 16;
-        else ro = ((((int64_t)n * D + d) * H + h) * W + w) * 16;
-        stg256_b32(q.pack_out + ro, hf_pack2(i0v, i1v), hf_pack2(a, b), hf_pack2(m, st.v[0]), hf_pack2(st.v[1], st.v[2]),
-                   hf_pack2(st.v[3], st.v[4]), hf_pack2(st.v[5], 0.0f), 0u, 0u);
-      }
-    } else if (SN == 2) {
-      const float c11[11] = {i0v, i1v, a, b, m, st.v[0], st.v[1], st.v[2], st.v[3], st.v[4], st.v[5]};
-#pragma unroll
-      for (int c = 0; c < 11; ++c) s_pool[(it & 1) * 11 + c][lane][wl] = c11[c];
+    if (okh) {
+      int64_t ro;
+      if (S2D) ro = s2d_row(3, n, d, h, w, D, H, W) * 16;
+      else ro = ((((int64_t)n * D + d) * H + h) * W + w) * 16;
+      stg256_b32(q.pack_out + ro, hf_pack2(i0v, i1v), hf_pack2(a, b), hf_pack2(m, st.v[0]), hf_pack2(st.v[1], st.v[2]),
+                 hf_pack2(st.v[3], st.v[4]), hf_pack2(st.v[5], 0.0f), 0u, 0u);
     }
-    if (need_m || SN == 2) __syncthreads();
-    // ---------------- planar outputs: coalesced 32 B rows
-    if (need_m && okP) {
-      const int64_t g = (int64_t)n * V + (int64_t)d * HW + (h0 + rP) * W + w0 + cP;
-      if (q.merged) q.merged[g] = s_out[ob][0][rP][cP];
-      if (q.mask_sig) q.mask_sig[g] = s_out[ob][1][rP][cP];
-    }
-    if (SN == 2 && (it & 1) && tid < 64) {
-      // 2x2x2 mean == F.interpolate(., 0.5): nested W, H, D like ATen; flow channels additionally * 0.5
-      const int ph = tid >> 2, pw = tid & 3;
-      const int oh = h0 / 2 + ph, ow = w0 / 2 + pw;
-      if (oh < H / 2 && ow < W / 2) {
-        float c11[11];
-#pragma unroll
-        for (int c = 0; c < 11; ++c) {
-          float rz[2];
-#pragma unroll
-          for (int dz = 0; dz < 2; ++dz) {
-            const float (*pl)[HF_W + 1] = s_pool[dz * 11 + c];
-            const float r0 = __fadd_rn(__fmul_rn(pl[2 * ph][2 * pw], 0.5f), __fmul_rn(pl[2 * ph][2 * pw + 1], 0.5f));
-            const float r1 = __fadd_rn(__fmul_rn(pl[2 * ph + 1][2 * pw], 0.5f), __fmul_rn(pl[2 * ph + 1][2 * pw + 1], 0.5f));
-            rz[dz] = __fadd_rn(__fmul_rn(r0, 0.5f), __fmul_rn(r1, 0.5f));
-          }
-          float r = __fadd_rn(__fmul_rn(rz[0], 0.5f), __fmul_rn(rz[1], 0.5f));
-          if (c >= 5) r = __fmul_rn(r, 0.5f);
-          c11[c] = r;
-        }
-        int64_t ro;
-        if (S2D) ro = s2d_row(3, n, d / 2, oh, ow, D / 2, H / 2, W / 2) * 16;
-        else ro = ((((int64_t)n * (D / 2) + d / 2) * (H / 2) + oh) * (W / 2) + ow) * 16;
-        stg256_b32(q.pack_out + ro, hf_pack2(c11[0], c11[1]), hf_pack2(c11[2], c11[3]), hf_pack2(c11[4], c11[5]), hf_pack2(c11[6], c11[7]),
-                   hf_pack2(c11[8], c11[9]), hf_pack2(c11[10], 0.0f), 0u, 0u);
+    if (need_m) {
+      __syncthreads();                                              // s_out is double-buffered by plane parity: one barrier per plane
+      if (okP) {
+        const int64_t g = (int64_t)n * V + (int64_t)d * HW + (h0 + rP) * W + w0 + cP;
+        if (q.merged) q.merged[g] = s_out[ob][0][rP][cP];
+        if (q.mask_sig) q.mask_sig[g] = s_out[ob][1][rP][cP];
       }
     }
-    // s_out is double-buffered (plane parity); s_pool's two plane halves are written on alternating planes and read right after
-    // the odd plane's barrier: the next write to either half happens after the NEXT plane's barrier only for s_out, so guard s_pool
-    if (SN == 2 && (it & 1)) __syncthreads();
   }
 }
 
 template <int SH, int SN, bool S2D, bool FMA>
-static int launch_hfast(const HfPtrs& q, const Warp3dParams& P, dim3 grid, cudaStream_t st) {
-  stage3d_hfast_kernel<SH, SN, S2D, FMA><<<grid, 256, 0, st>>>(q, P);
-  return check_launch("stage3d_hfast_kernel");
+static int launch_hfast(const HfPtrs& q, const Warp3dParams& P, cudaStream_t st) {
+  if constexpr (SN == 1 && SH != 0) {
+    const dim3 grid((unsigned)cdiv(P.W, HF_W), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_CDZ)));
+    if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
+    stage3d_hfast_cols_kernel<SH, S2D, FMA><<<grid, 256, 0, st>>>(q, P);
+    return check_launch("stage3d_hfast_cols_kernel");
+  } else {
+    const dim3 grid((unsigned)cdiv(P.W, HF_W), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_DZ)));
+    if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
+    stage3d_hfast_kernel<SH, SN, S2D, FMA><<<grid, 256, 0, st>>>(q, P);
+    return check_launch("stage3d_hfast_kernel");
+  }
 }
 
 int block_stage_hfast(const float* head, const float* fm_prev, const float* img0, const float* img1, const float* lin_h,
@@ -278,13 +531,15 @@ int block_stage_hfast(const float* head, const float* fm_prev, const float* img0
   OFSV_REQUIRE((!head || (reinterpret_cast<uintptr_t>(head) & 31) == 0) && (!fm_out || (reinterpret_cast<uintptr_t>(fm_out) & 31) == 0) &&
                    (!fm_prev || (reinterpret_cast<uintptr_t>(fm_prev) & 31) == 0) && (!pack_out || (reinterpret_cast<uintptr_t>(pack_out) & 31) == 0),
                "ofsv_block_stage_3d: head / fm / pack_out must be 32-byte aligned in the H-fastest state layout");
+  OFSV_REQUIRE(D % HF_PP == 0, "ofsv_block_stage_3d: the H-fastest state layout needs D %% %d == 0", HF_PP);
+  OFSV_REQUIRE(W % 8 == 0 && (reinterpret_cast<uintptr_t>(img0) & 31) == 0 && (reinterpret_cast<uintptr_t>(img1) & 31) == 0 &&
+                   (!merged || (reinterpret_cast<uintptr_t>(merged) & 31) == 0) && (!mask_sig || (reinterpret_cast<uintptr_t>(mask_sig) & 31) == 0),
+               "ofsv_block_stage_3d: the H-fastest state layout needs W %% 8 == 0 and 32-byte aligned img0 / img1 / merged / mask_sig");
   const Warp3dParams P = make_warp3d_params(N, 1, D, H, W, ref_mode);
-  const dim3 grid((unsigned)cdiv(W, HF_W), (unsigned)cdiv(H, HF_H), (unsigned)(N * cdiv(D, HF_DZ)));
-  if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
   HfPtrs q{head, fm_prev, img0, img1, lin_h, lin_d, lin_w, fm_out, merged, mask_sig, reinterpret_cast<__nv_bfloat16*>(pack_out)};
   const bool fma = ref_mode == OFSV_REF_CUDA;
   const bool s2d = pack_s2d != 0;
-#define GO3(SH, SN, S2) return fma ? launch_hfast<SH, SN, S2, true>(q, P, grid, st) : launch_hfast<SH, SN, S2, false>(q, P, grid, st)
+#define GO3(SH, SN, S2) return fma ? launch_hfast<SH, SN, S2, true>(q, P, st) : launch_hfast<SH, SN, S2, false>(q, P, st)
 #define GO(SH)                                                                                         \
   do {                                                                                                 \
     if (scale_next == 0) GO3(SH, 0, false);                                                            \
