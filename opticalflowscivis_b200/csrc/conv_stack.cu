@@ -42,7 +42,10 @@ constexpr int SK_THREADS = 32 * (SK_EPI_W0 + SK_EPI_WARPS);   // warp 0 weights,
 enum { SK_EPI_DIRECT = 0, SK_EPI_TMA_ROWS = 1, SK_EPI_TMA_SHUF = 2 };
 
 // ---------------------------------------------------------------------------------------------------- host-side plan
-struct SkSlot { int8_t p, oz; uint8_t tap; };          // phase index inside the pass, dz of the tap, ph * ntaps + t
+struct SkSlot {
+  int8_t p, oz; uint8_t tap;                           // phase index inside the pass, dz of the tap, ph * ntaps + t
+  int16_t c_lo, c_hi;                                  // columns [c_lo, c_hi) of the slot's Cout_w can be non-zero (structural zeros outside)
+};
 struct SkGroup {
   int pass, oy, ox, nslots, row0;                      // row0: first row of the group's kc = 0 block in the packed weights
   SkSlot slots[SK_MAX_SLOTS];
@@ -90,6 +93,10 @@ static bool sk_make_plan(const ofsv_conv_desc* d, SkPlan* pl) {
               if (o[0] == oz && o[1] == oy && o[2] == ox) {
                 if (G.nslots == SK_MAX_SLOTS) return false;
                 G.slots[G.nslots].p = (int8_t)p; G.slots[G.nslots].oz = (int8_t)oz; G.slots[G.nslots].tap = (uint8_t)(ph * d->ntaps + t);
+                // depth-to-space heads (out_shuffle: columns [parity (z,y,x)][8 ch], include/ofsv.h): a tap with dz = +1 only feeds the
+                // z-parity-1 half of the columns, dz = -1 only the z-parity-0 half — the rest of its weights are zero BY CONTRACT
+                G.slots[G.nslots].c_lo = (int16_t)((d->out_shuffle && d->nd == 3 && oz == 1) ? d->Cout_w / 2 : 0);
+                G.slots[G.nslots].c_hi = (int16_t)((d->out_shuffle && d->nd == 3 && oz == -1) ? d->Cout_w / 2 : d->Cout_w);
                 ++G.nslots;
               }
             }
@@ -105,7 +112,8 @@ static bool sk_make_plan(const ofsv_conv_desc* d, SkPlan* pl) {
   return true;
 }
 
-struct SkOp { uint8_t group, q, slot0, nsl, col0, fresh, issuer; int8_t oy, ox; };
+struct SkOp { uint8_t group, q, slot0, nsl, col0, fresh, issuer; int8_t oy, ox; uint8_t lo, hi; };   // lo / hi: zero columns skipped at the ends of the run
+static int sk_op_cols(const SkOp& o, int Cout_w) { return o.nsl * Cout_w - o.lo - o.hi; }
 
 constexpr int SK_NI = 2;      // MMA-issuing warps
 
@@ -151,6 +159,9 @@ static int sk_build_ops(const ofsv_conv_desc* d, const SkPlan& pl, int td, SkOp*
             SkOp o;
             o.group = (uint8_t)gi; o.q = (uint8_t)q; o.slot0 = (uint8_t)s; o.nsl = (uint8_t)len; o.col0 = (uint8_t)col; o.fresh = fresh;
             o.issuer = (uint8_t)w; o.oy = (int8_t)G.oy; o.ox = (int8_t)G.ox;
+            // structural zeros at the two ends of the run are not multiplied — unless this MMA initialises its accumulator columns
+            o.lo = fresh ? 0 : (uint8_t)G.slots[s].c_lo;
+            o.hi = fresh ? 0 : (uint8_t)(d->Cout_w - G.slots[s + len - 1].c_hi);
             ops[n++] = o;
             for (int i = 0; i < len; ++i) init[col + i] = true;
             s += len;
@@ -687,7 +698,7 @@ static bool sk_configure(const ofsv_conv_desc* d, const SkPlan& pl, int sms, SkC
     // tensor / operand-port time of all MMAs vs the issue time of the busier issuer (~50 cycles of scalar work per op)
     double mma = 0.0, iss_t[SK_NI] = {0.0, 0.0};
     for (int i = 0; i < nops; ++i) {
-      const double c = sk_mma_cycles(ops[i].nsl * d->Cout_w) * (KC / 16);
+      const double c = sk_mma_cycles(sk_op_cols(ops[i], d->Cout_w)) * (KC / 16);
       mma += c;
       iss_t[ops[i].issuer] += c + 50.0;
     }
@@ -824,16 +835,21 @@ extern "C" int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* n
         const SkOp& o = ops[i];
         const SkGroup& G = pl.g[g];
         OFSV_REQUIRE(o.group == g && o.nsl >= 1 && o.slot0 + o.nsl <= G.nslots && o.nsl * d->Cout_w <= 256, "selfcheck: bad op %d", i);
+        OFSV_REQUIRE(sk_op_cols(o, d->Cout_w) >= 16 && sk_op_cols(o, d->Cout_w) % 16 == 0 && o.lo % 16 == 0 && (!o.fresh || (o.lo == 0 && o.hi == 0)),
+                     "selfcheck: op %d trimmed to a bad column range", i);
         for (int k = 0; k < o.nsl; ++k) {
           const SkSlot& s = G.slots[o.slot0 + k];
           const int j = o.q + pl.dzmin - s.oz, col = s.p * td + j;
           OFSV_REQUIRE(j >= 0 && j < td, "selfcheck: op %d slot %d leaves the super-tile", i, k);
           OFSV_REQUIRE(col == o.col0 + k, "selfcheck: op %d columns not contiguous", i);
           OFSV_REQUIRE((!init[col]) == (o.fresh != 0), "selfcheck: op %d fresh flag inconsistent", i);
+          // the columns this op really multiplies inside slot k must include every column that can be non-zero
+          const int lo_k = k == 0 ? o.lo : 0, hi_k = k == o.nsl - 1 ? d->Cout_w - o.hi : d->Cout_w;
+          OFSV_REQUIRE(lo_k <= s.c_lo && hi_k >= s.c_hi, "selfcheck: op %d skips non-zero columns of slot %d", i, k);
           covered[s.tap][j] += 1;
         }
         for (int k = 0; k < o.nsl; ++k) init[o.col0 + k] = true;
-        cyc += sk_mma_cycles(o.nsl * d->Cout_w);
+        cyc += sk_mma_cycles(sk_op_cols(o, d->Cout_w));
       }
     for (int c = 0; c < pl.P * td; ++c) OFSV_REQUIRE(init[c], "selfcheck: column block %d of pass %d never written", c, pass);
   }
@@ -856,7 +872,7 @@ extern "C" int ofsv_conv_halo_describe(const ofsv_conv_desc* d, char* buf, int b
   int op_first[SK_MAX_GROUPS * SK_NI + 1];
   const int nops = sk_build_ops(d, pl, cfg.td, ops, op_first);
   double mma = 0.0, ideal = 0.0;
-  for (int i = 0; i < nops; ++i) { mma += sk_mma_cycles(ops[i].nsl * d->Cout_w); ideal += ops[i].nsl * d->Cout_w / 2.0; }
+  for (int i = 0; i < nops; ++i) { mma += sk_mma_cycles(sk_op_cols(ops[i], d->Cout_w)); ideal += sk_op_cols(ops[i], d->Cout_w) / 2.0; }
   snprintf(buf, buflen, "stack KC=%d nkc=%d P=%d npass=%d groups=%d td=%d nring=%d nb=%d%s nbuf=%d epi=%d rowb=%d smem=%zu ops=%d tensor_frac=%.2f",
            pl.KC, pl.nkc, pl.P, pl.npass, pl.ngroups, cfg.td, cfg.nring, cfg.nb, cfg.b_resident ? "(resident)" : "", cfg.nbuf, cfg.epi_mode, cfg.stg_rowb, cfg.smem, nops, ideal / mma);
   return OFSV_OK;
@@ -941,12 +957,12 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
     for (int i = 0; i < nops; ++i) {
       const SkOp& o = ops[i];
       const uint32_t a_off = (uint32_t)(((o.oy + 1) * SK_HP_W + (o.ox + 1)) * ROWB) >> 4;
-      const uint32_t ncols = (uint32_t)(o.nsl * d->Cout_w);
+      const uint32_t ncols = (uint32_t)sk_op_cols(o, d->Cout_w);
       P.ops[i][0] = a_off + (uint32_t)o.q * ((uint32_t)cfg.plane_stride >> 4);
-      P.ops[i][1] = (uint32_t)(o.slot0 * d->Cout_w * ROWB) >> 4;
-      P.ops[i][2] = (uint32_t)(o.col0 * d->Cout_w) | ((uint32_t)(o.fresh ? 1 : 0) << 16);
+      P.ops[i][1] = (uint32_t)((o.slot0 * d->Cout_w + o.lo) * ROWB) >> 4;      // o.lo % 8 == 0: whole 8-row swizzle atoms
+      P.ops[i][2] = (uint32_t)(o.col0 * d->Cout_w + o.lo) | ((uint32_t)(o.fresh ? 1 : 0) << 16);
       P.ops[i][3] = idesc0 | ((ncols >> 3) << 17);
-      OFSV_REQUIRE(ncols <= 256 && o.col0 * d->Cout_w + ncols <= 512, "ofsv_conv_halo: internal error (op encoding)");
+      OFSV_REQUIRE(ncols >= 16 && ncols % 16 == 0 && ncols <= 256 && o.col0 * d->Cout_w + o.lo + ncols <= 512, "ofsv_conv_halo: internal error (op encoding)");
     }
   }
   const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
