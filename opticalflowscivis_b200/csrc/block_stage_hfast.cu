@@ -404,8 +404,11 @@ __global__ void __launch_bounds__(256, (SH == 0 && SN == 0) ? OFSV_HF_MINB_FIN :
 // row variant above on the block1 -> block2 stage of a 4 x 256^3 batch: 1773 us vs 1840-2150 us (any unroll / occupancy choice).
 // merged / sigmoid(mask), when requested (IFNet.forward with all three blends), go through a shared tile + one barrier per plane.
 constexpr int HF_CDZ = 8;
+#ifndef OFSV_HF_MINB_COLS
+#define OFSV_HF_MINB_COLS 3
+#endif
 template <int SH, bool S2D, bool FMA>
-__global__ void __launch_bounds__(256, 3) stage3d_hfast_cols_kernel(const HfPtrs q, const Warp3dParams P) {
+__global__ void __launch_bounds__(256, OFSV_HF_MINB_COLS) stage3d_hfast_cols_kernel(const HfPtrs q, const Warp3dParams P) {
   __shared__ float s_out[2][2][HF_H][HF_W + 1];                     // [buffer][merged | mask][h][w]
   const int H = P.H, W = P.W, D = P.D, HW = H * W;
   const int V = D * HW;

@@ -6,6 +6,7 @@ stream.  CPU tensors raise TypeError — there is deliberately no CPU or ATen fa
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 
@@ -377,7 +378,9 @@ def workspace(key, shape, dtype, device):
     """Persistent ZERO-initialised buffer per (key, shape, dtype, device).  Used for the shifted space-to-depth tensors whose
     border sub-cells (the conv padding) must stay zero: producers only ever write the interior, so the buffer is zeroed
     once and reused by every later call on the same stream."""
-    k = (key, tuple(shape), dtype, str(device))
+    # one buffer per host thread: two threads driving models on their own streams must not share a workspace (within a thread the
+    # calls are stream-ordered; running ONE thread's calls concurrently on several streams is not supported)
+    k = (key, tuple(shape), dtype, str(device), threading.get_ident())
     t = _WS.get(k)
     if t is None:
         t = torch.zeros(shape, dtype=dtype, device=device)

@@ -1,5 +1,5 @@
 """Tiny driver for ncu captures: warm-up inferences, then ONE Model.inference inside a cudaProfilerStart/Stop range
-(run ncu with --profile-from-start off) on one synthetic pair.  usage: prof_step.py [size=256] [warmup=3] [2d]"""
+(run ncu with --profile-from-start off) on synthetic pairs.  usage: prof_step.py [size=256] [warmup=3] [2d|3d] [pairs=1]"""
 import os
 import sys
 
@@ -11,6 +11,7 @@ from opticalflowscivis_b200 import synth  # noqa: E402
 s = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 two_d = len(sys.argv) > 3 and sys.argv[3] == "2d"
+pairs = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 torch.manual_seed(1234)
 if two_d:
     from opticalflowscivis_b200.flow2d.model.RIFE import Model
@@ -18,7 +19,7 @@ if two_d:
     d0, d1 = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
 else:
     from opticalflowscivis_b200.flow3d.model.RIFE import Model
-    a, _, b = synth.droplet3d_u8(1, s)
+    a, _, b = synth.droplet3d_u8(pairs, s)
     d0, d1 = torch.from_numpy(a).cuda().float() / 255, torch.from_numpy(b).cuda().float() / 255
 m = Model()
 m.eval()
