@@ -84,9 +84,12 @@ int ofsv_blend_f32(const float* w0, const float* w1, const float* mask_logit, fl
 /* ---- a8: correlation_cuda.forward / .backward — UPFlow/model/correlation_package/correlation.py:26-27,42-43,
  * call sites UPFlow/model/upflow.py:649,652 with (pad 4, kernel 1, max_disp 4, stride1 1, stride2 1, mult 1) only.
  * f1,f2 (B,C,H,W); out (B,81,H,W) written at out + b*out_batch_stride (elements) so the caller can point it into the
- * channel-concatenated estimator input (upflow.py:657).  apply_leaky fuses LeakyReLU(leaky_slope) (upflow.py:655-656). */
+ * channel-concatenated estimator input (upflow.py:657).  apply_leaky fuses LeakyReLU(leaky_slope) (upflow.py:655-656).
+ * work: optional caller-owned scratch of ofsv_corr81_fwd_splits(B,C,H,W) * B*81*H*W floats (NULL = none): with it the channels
+ * of the coarse pyramid levels are split over CTAs (partial sums, added in a fixed order by a second launch — deterministic). */
+int ofsv_corr81_fwd_splits(int B, int C, int H, int W);
 int ofsv_corr81_fwd_f32(const float* f1, const float* f2, float* out, int B, int C, int H, int W, float leaky_slope,
-                        int apply_leaky, int64_t out_batch_stride, void* stream);
+                        int apply_leaky, int64_t out_batch_stride, float* work, void* stream);
 int ofsv_corr81_bwd_f32(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B, int C, int H,
                         int W, void* stream);
 

@@ -47,7 +47,8 @@ _SIGS = {
     "ofsv_warp_blend_2d_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "ofsv_warp_blend_3d_f32": (_I, [_P] * 11 + [_I, _I, _I, _I, _I, _P]),
     "ofsv_blend_f32": (_I, [_P, _P, _P, _P, _L, _P]),
-    "ofsv_corr81_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _L, _P]),
+    "ofsv_corr81_fwd_splits": (_I, [_I, _I, _I, _I]),
+    "ofsv_corr81_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _L, _P, _P]),
     "ofsv_corr81_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ofsv_upsample_flow_ac_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warping_no_div_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

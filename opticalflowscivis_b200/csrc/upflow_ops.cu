@@ -16,13 +16,35 @@ namespace ofsv {
 constexpr int CTW = 32, CTH = 8, CMD = 4, CC = 8;
 constexpr int CHW = CTW + 2 * CMD, CHH = CTH + 2 * CMD;
 
+__device__ __forceinline__ uint32_t up_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// cp.async with zero fill: `bytes` valid source bytes (0 = write zeros; the source pointer must still be a valid address)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Channel chunks are DOUBLE-BUFFERED with cp.async (the chunk after the one being multiplied is in flight; out-of-image elements
+// are zero-filled by the copy itself), and the channels can be SPLIT over blockIdx.z: split s of nsplit accumulates channels
+// [s*cps, (s+1)*cps) and — when nsplit > 1 — writes raw partial sums to work[s][b][81][H][W]; corr81_finalize_kernel adds the
+// splits in a fixed order, divides by C and applies the LeakyReLU.  The coarse pyramid levels (4 x 13 ... 16 x 52 at B = 16) are
+// 16-64 tiles: one CTA per tile walking 96-196 channels with a load -> barrier -> multiply -> barrier loop took 96-160 us per
+// launch for a few hundred KB; with the split every SM gets a few chunks.
+constexpr int CORR_FWD_SMEM = 2 * (CC * CHH * CHW + CC * CTH * CTW) * 4;      // 57344 B
 template <bool VEC>
-__global__ void __launch_bounds__(288)
-    corr81_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int C, int H,
-                      int W, float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
-  __shared__ __align__(16) float s2[CC][CHH][CHW];
-  __shared__ __align__(16) float s1[CC][CTH][CTW];
-  const int b = blockIdx.z, x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
+__global__ void __launch_bounds__(288, 2)
+    corr81_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, float* __restrict__ work,
+                      int B, int C, int H, int W, int nsplit, int cps, float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
+  extern __shared__ __align__(16) float cf_smem[];
+  float (*s2)[CC][CHH][CHW] = reinterpret_cast<float (*)[CC][CHH][CHW]>(cf_smem);                         // [2][CC][16][40]
+  float (*s1)[CC][CTH][CTW] = reinterpret_cast<float (*)[CC][CTH][CTW]>(cf_smem + 2 * CC * CHH * CHW);    // [2][CC][8][32]
+  const int b = blockIdx.z / nsplit, split = blockIdx.z - b * nsplit;
+  const int x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
+  const int c_beg = split * cps, c_end = min(C, c_beg + cps);
   const int tid = threadIdx.x;
   const int q = tid & 7, rp = (tid >> 3) & 3, dy = tid >> 5;       // quad, pixel-row pair, displacement row (warp-uniform)
   const int64_t HW = (int64_t)H * W;
@@ -31,14 +53,36 @@ __global__ void __launch_bounds__(288)
   // loader role: threads 0..159 own one 16 B column of the f2 halo tile (16 rows x 10 quads), threads 160..223 one of the f1
   // tile (8 rows x 8 quads); the position (and its bounds check) is fixed, only the channel pointer moves
   const bool ld2 = tid < CHH * (CHW / 4), ld1 = tid >= 160 && tid < 160 + CTH * (CTW / 4);
-  int lyy = 0, lxx = 0;
-  bool lin = false;
-  const float* lsrc = nullptr;
-  if (ld2) { lyy = tid / (CHW / 4); lxx = (tid % (CHW / 4)) * 4; const int y = y0 + lyy - CMD, x = x0 + lxx - CMD;
-             lin = y >= 0 && y < H && x >= 0 && x < W; lsrc = p2 + (int64_t)y * W + x; }
-  if (ld1) { const int t = tid - 160; lyy = t / (CTW / 4); lxx = (t % (CTW / 4)) * 4; const int y = y0 + lyy, x = x0 + lxx;
-             lin = y < H && x < W; lsrc = p1 + (int64_t)y * W + x; }
-  const int lx_glob = ld2 ? x0 + lxx - CMD : x0 + lxx;
+  int lyy = 0, lxx = 0, lx_glob = 0;
+  bool lrow = false;
+  const float* lsrc = p1;
+  if (ld2) { lyy = tid / (CHW / 4); lxx = (tid % (CHW / 4)) * 4; const int y = y0 + lyy - CMD; lx_glob = x0 + lxx - CMD;
+             lrow = y >= 0 && y < H; lsrc = p2 + (int64_t)y * W + lx_glob; }
+  if (ld1) { const int t = tid - 160; lyy = t / (CTW / 4); lxx = (t % (CTW / 4)) * 4; const int y = y0 + lyy; lx_glob = x0 + lxx;
+             lrow = y < H; lsrc = p1 + (int64_t)y * W + lx_glob; }
+  bool lok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) lok[i] = lrow && lx_glob + i >= 0 && lx_glob + i < W;
+  const bool lok16 = lok[0] && lok[3];                              // VEC: W % 4 == 0 and x0 - 4 + 4k: a quad is all in or all out
+
+  auto issue = [&](int c0, int buf) {                               // chunk [c0, c0 + CC) -> buffer buf
+    if (ld1 || ld2) {
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        const bool cin = c0 + c < c_end;
+        const float* g = lsrc + (int64_t)(c0 + c) * HW;
+        const uint32_t dst = ld2 ? up_smem_u32(&s2[buf][c][lyy][lxx]) : up_smem_u32(&s1[buf][c][lyy][lxx]);
+        if (VEC) {
+          cp_async_16(dst, (cin && lok16) ? (const void*)g : (const void*)p1, (cin && lok16) ? 16 : 0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async_4(dst + 4 * i, (cin && lok[i]) ? (const void*)(g + i) : (const void*)p1, (cin && lok[i]) ? 4 : 0);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
   float acc[2][4][9];
 #pragma unroll
   for (int j = 0; j < 2; ++j)
@@ -47,36 +91,20 @@ __global__ void __launch_bounds__(288)
 #pragma unroll
       for (int k = 0; k < 9; ++k) acc[j][i][k] = 0.0f;
 
-  for (int c0 = 0; c0 < C; c0 += CC) {
-    const int cc = min(CC, C - c0);
-    if (ld1 || ld2) {
-#pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < cc && lin) {
-          const float* g = lsrc + (int64_t)(c0 + c) * HW;
-          if (VEC) {
-            v = __ldg(reinterpret_cast<const float4*>(g));
-          } else {                      // rows not 16 B aligned (W % 4 != 0) or ragged right edge
-            v.x = __ldg(g);
-            if (lx_glob + 1 >= 0 && lx_glob + 1 < W) v.y = __ldg(g + 1);
-            if (lx_glob + 2 >= 0 && lx_glob + 2 < W) v.z = __ldg(g + 2);
-            if (lx_glob + 3 >= 0 && lx_glob + 3 < W) v.w = __ldg(g + 3);
-          }
-        }
-        if (ld2) *reinterpret_cast<float4*>(&s2[c][lyy][lxx]) = v; else *reinterpret_cast<float4*>(&s1[c][lyy][lxx]) = v;
-      }
-    }
+  issue(c_beg, 0);
+  int buf = 0;
+  for (int c0 = c_beg; c0 < c_end; c0 += CC, buf ^= 1) {
+    if (c0 + CC < c_end) { issue(c0 + CC, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
 #pragma unroll 2
     for (int c = 0; c < CC; ++c) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int r = 2 * rp + j;
-        const float4 a4 = *reinterpret_cast<const float4*>(&s1[c][r][4 * q]);
-        const float4 r0 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q]);
-        const float4 r1 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q + 4]);
-        const float4 r2 = *reinterpret_cast<const float4*>(&s2[c][r + dy][4 * q + 8]);
+        const float4 a4 = *reinterpret_cast<const float4*>(&s1[buf][c][r][4 * q]);
+        const float4 r0 = *reinterpret_cast<const float4*>(&s2[buf][c][r + dy][4 * q]);
+        const float4 r1 = *reinterpret_cast<const float4*>(&s2[buf][c][r + dy][4 * q + 4]);
+        const float4 r2 = *reinterpret_cast<const float4*>(&s2[buf][c][r + dy][4 * q + 8]);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const float row[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
@@ -85,22 +113,27 @@ __global__ void __launch_bounds__(288)
           for (int k = 0; k < 9; ++k) acc[j][i][k] = fmaf(a[i], row[i + k], acc[j][i][k]);
       }
     }
-    __syncthreads();
+    __syncthreads();                                                // buffer `buf` is refilled by the next iteration's issue
   }
   const float cf = (float)C;
+  const bool partial = nsplit > 1;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int x = x0 + 4 * q, y = y0 + 2 * rp + j;
     if (y < H && x < W) {
-      float* o = out + (int64_t)b * out_batch_stride + (int64_t)(dy * 9) * HW + (int64_t)y * W + x;
+      float* o = partial ? work + ((int64_t)(split * B + b) * 81 + dy * 9) * HW + (int64_t)y * W + x
+                         : out + (int64_t)b * out_batch_stride + (int64_t)(dy * 9) * HW + (int64_t)y * W + x;
       const bool vec = VEC && (x + 3 < W) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) && ((HW & 3) == 0);
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          v[i] = acc[j][i][k] / cf;  // torch.mean = sum / C
-          if (apply_leaky && v[i] < 0.0f) v[i] *= leaky_slope;
+          v[i] = acc[j][i][k];
+          if (!partial) {
+            v[i] = v[i] / cf;  // torch.mean = sum / C
+            if (apply_leaky && v[i] < 0.0f) v[i] *= leaky_slope;
+          }
         }
         float* ok = o + (int64_t)k * HW;
         if (vec) {
@@ -113,6 +146,32 @@ __global__ void __launch_bounds__(288)
       }
     }
   }
+}
+
+// out[b][k][p] = leaky((sum_s work[s][b][k][p]) / C), splits added in ascending order
+__global__ void corr81_finalize_kernel(const float* __restrict__ work, float* __restrict__ out, int B, int C, int64_t HW, int nsplit,
+                                       float leaky_slope, int apply_leaky, int64_t out_batch_stride) {
+  const int64_t per = 81 * HW, total = (int64_t)B * per;
+  const float cf = (float)C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per, r = i - b * per;
+    float v = __ldg(work + i);
+    for (int s = 1; s < nsplit; ++s) v += __ldg(work + (int64_t)s * total + i);
+    v = v / cf;
+    if (apply_leaky && v < 0.0f) v *= leaky_slope;
+    out[b * out_batch_stride + r] = v;
+  }
+}
+
+// channel splits of the forward kernel for this shape: enough CTAs for two per SM, at least two chunks of channels per split
+static int corr81_splits(int B, int C, int H, int W) {
+  const int64_t ctas = cdiv(W, CTW) * cdiv(H, CTH) * (int64_t)B;
+  const int64_t want = cdiv(2 * (int64_t)device_num_sms(), ctas);
+  const int64_t cap = C / (2 * CC) > 1 ? C / (2 * CC) : 1;
+  int64_t n = want < cap ? want : cap;
+  if (n < 1) n = 1;
+  if (ctas * n > 65535) n = 65535 / ctas > 1 ? 65535 / ctas : 1;
+  return (int)n;
 }
 
 // backward (what autograd derives through Corr_pyTorch):
@@ -277,20 +336,39 @@ static inline int grid_1d(int64_t total) {
 
 using namespace ofsv;
 
+extern "C" int ofsv_corr81_fwd_splits(int B, int C, int H, int W) {
+  if (B < 1 || C < 1 || H < 1 || W < 1) return 1;
+  return corr81_splits(B, C, H, W);
+}
+
 extern "C" int ofsv_corr81_fwd_f32(const float* f1, const float* f2, float* out, int B, int C, int H, int W,
-                                   float leaky_slope, int apply_leaky, int64_t out_batch_stride, void* stream) {
+                                   float leaky_slope, int apply_leaky, int64_t out_batch_stride, float* work, void* stream) {
   OFSV_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "ofsv_corr81_fwd_f32: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   if (B == 0) return OFSV_OK;
   OFSV_REQUIRE(f1 && f2 && out, "ofsv_corr81_fwd_f32: null pointer");
   OFSV_REQUIRE(out_batch_stride >= (int64_t)81 * H * W, "ofsv_corr81_fwd_f32: out_batch_stride %lld < 81*H*W",
                (long long)out_batch_stride);
-  OFSV_REQUIRE(B <= 65535, "ofsv_corr81_fwd_f32: batch %d exceeds grid.z", B);
   OFSV_REQUIRE(cdiv(H, CTH) <= 65535, "ofsv_corr81_fwd_f32: H too large");
-  const dim3 grid((unsigned)cdiv(W, CTW), (unsigned)cdiv(H, CTH), (unsigned)B);
+  // without a workspace the channels are not split (one CTA per tile walks all of them)
+  const int nsplit = work ? corr81_splits(B, C, H, W) : 1;
+  OFSV_REQUIRE((int64_t)B * nsplit <= 65535, "ofsv_corr81_fwd_f32: batch %d exceeds grid.z", B);
+  const int cps = (int)(cdiv(cdiv(C, nsplit), CC) * CC);             // channels per split, whole chunks
+  const dim3 grid((unsigned)cdiv(W, CTW), (unsigned)cdiv(H, CTH), (unsigned)(B * nsplit));
   const bool vec = (W % 4 == 0) && aligned16(f1) && aligned16(f2);
-  if (vec) corr81_fwd_kernel<true><<<grid, 288, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, leaky_slope, apply_leaky, out_batch_stride);
-  else corr81_fwd_kernel<false><<<grid, 288, 0, (cudaStream_t)stream>>>(f1, f2, out, C, H, W, leaky_slope, apply_leaky, out_batch_stride);
-  return check_launch("corr81_fwd_kernel");
+  static std::atomic<uint64_t> attr_a{0}, attr_b{0};
+  if (int e = ensure_dyn_smem(attr_a, corr81_fwd_kernel<true>, CORR_FWD_SMEM, "ofsv_corr81_fwd_f32")) return e;
+  if (int e = ensure_dyn_smem(attr_b, corr81_fwd_kernel<false>, CORR_FWD_SMEM, "ofsv_corr81_fwd_f32")) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) corr81_fwd_kernel<true><<<grid, 288, CORR_FWD_SMEM, st>>>(f1, f2, out, work, B, C, H, W, nsplit, cps, leaky_slope, apply_leaky, out_batch_stride);
+  else corr81_fwd_kernel<false><<<grid, 288, CORR_FWD_SMEM, st>>>(f1, f2, out, work, B, C, H, W, nsplit, cps, leaky_slope, apply_leaky, out_batch_stride);
+  if (int e = check_launch("corr81_fwd_kernel")) return e;
+  if (nsplit > 1) {
+    const int64_t total = (int64_t)B * 81 * H * W;
+    const int fgrid = (int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184);
+    corr81_finalize_kernel<<<fgrid, 256, 0, st>>>(work, out, B, C, (int64_t)H * W, nsplit, leaky_slope, apply_leaky, out_batch_stride);
+    return check_launch("corr81_finalize_kernel");
+  }
+  return OFSV_OK;
 }
 
 extern "C" int ofsv_corr81_bwd_f32(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B,

@@ -267,9 +267,12 @@ def corr81_fwd(f1, f2, leaky_slope=None, out=None):
             raise ValueError("corr81: `out` must be a float32 CUDA (B,>=81,H,W) tensor with dense (C,H,W) strides")
     bstride = out.stride(0) if b > 1 else 81 * h * w
     with torch.cuda.device(f1.device):
-        _C.check(_C.lib().ofsv_corr81_fwd_f32(_p(f1), _p(f2), _p(out), b, c, h, w,
-                                              float(leaky_slope or 0.0), int(leaky_slope is not None),
-                                              max(bstride, 81 * h * w), _stream()))
+        L = _C.lib()
+        ns = L.ofsv_corr81_fwd_splits(b, c, h, w)          # coarse pyramid levels: channels split over CTAs through a scratch buffer
+        work = torch.empty((ns, b, 81, h, w), device=f1.device, dtype=torch.float32) if ns > 1 else None
+        _C.check(L.ofsv_corr81_fwd_f32(_p(f1), _p(f2), _p(out), b, c, h, w,
+                                       float(leaky_slope or 0.0), int(leaky_slope is not None),
+                                       max(bstride, 81 * h * w), _p(work), _stream()))
     return out
 
 

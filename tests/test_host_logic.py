@@ -149,7 +149,7 @@ def test_validation_errors_launch_nothing():
     n0 = L.ofsv_launch_count()
     assert L.ofsv_warp3d_f32(null, null, null, null, null, null, 1, 1, 4, 4, 4, 0, null) == _C.EINVAL
     assert b"null" in L.ofsv_last_error()
-    assert L.ofsv_corr81_fwd_f32(null, null, null, 1, 0, 4, 4, 0.1, 0, 0, null) == _C.EINVAL
+    assert L.ofsv_corr81_fwd_f32(null, null, null, 1, 0, 4, 4, 0.1, 0, 0, null, null) == _C.EINVAL
     assert L.ofsv_pack_block_input(null, null, null, null, null, null, null, 0, 3, 1, 6, 8, 8, 4, 16, 0, null) == _C.EINVAL
     assert L.ofsv_block_stage_3d(*([null] * 11), 1, 16, 16, 16, 3, 0, 0, 0, 0, null) == _C.EINVAL
     assert L.ofsv_u8_to_f32(null, null, 16, 255.0, null) == _C.EINVAL
