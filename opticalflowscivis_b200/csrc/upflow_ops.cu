@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256)
   const int b = blockIdx.z, x0 = blockIdx.x * BTW, y0 = (blockIdx.y % tiles_y) * BTH;
   const int c_beg = (blockIdx.y / tiles_y) * c_per_cta, c_end = min(C, c_beg + c_per_cta);
   const int tid = threadIdx.x;
-  const int q = tid & 7, r = (tid >> 3) & 7, cs = tid >> 6;          // quad, row, channel slot (0..3)
+  const int q = tid & 7, cs = (tid >> 3) & 3, r = tid >> 5;          // quad, channel slot (0..3), row: a warp = one row
   const int64_t HW = (int64_t)H * W;
   const float* pf = feat + (int64_t)b * C * HW;
   const float* pg = gout + (int64_t)b * 81 * HW;
@@ -224,30 +224,42 @@ __global__ void __launch_bounds__(256)
       sf[c][yy][xx] = v;
     }
     __syncthreads();
+    // per displacement row: the 9 gradient quads are loaded ONCE (a warp = 8 quads x 4 channel slots of one row: the four slots
+    // read the same 128 B, one shared-memory wavefront) and feed both channels of the slot
+    float acc[BCC / 4][4];
 #pragma unroll
-    for (int ci = 0; ci < BCC / 4; ++ci) {
-      const int c = cs + 4 * ci;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < BCC / 4; ++ci) { acc[ci][0] = 0.f; acc[ci][1] = 0.f; acc[ci][2] = 0.f; acc[ci][3] = 0.f; }
 #pragma unroll 3
-      for (int dy = 0; dy < 9; ++dy) {
+    for (int dy = 0; dy < 9; ++dy) {
+      float4 g4[9];
+#pragma unroll
+      for (int dx = 0; dx < 9; ++dx) {
+        const int k = G2 ? 80 - (dy * 9 + dx) : dy * 9 + dx;
+        g4[dx] = *reinterpret_cast<const float4*>(&sg[k][r][4 * q]);
+      }
+#pragma unroll
+      for (int ci = 0; ci < BCC / 4; ++ci) {
+        const int c = cs + 4 * ci;
         const float4 r0 = *reinterpret_cast<const float4*>(&sf[c][r + dy][4 * q]);
         const float4 r1 = *reinterpret_cast<const float4*>(&sf[c][r + dy][4 * q + 4]);
         const float4 r2 = *reinterpret_cast<const float4*>(&sf[c][r + dy][4 * q + 8]);
         const float row[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
         for (int dx = 0; dx < 9; ++dx) {
-          const int k = G2 ? 80 - (dy * 9 + dx) : dy * 9 + dx;
-          const float4 g4 = *reinterpret_cast<const float4*>(&sg[k][r][4 * q]);
-          acc[0] = fmaf(g4.x, row[dx], acc[0]); acc[1] = fmaf(g4.y, row[dx + 1], acc[1]);
-          acc[2] = fmaf(g4.z, row[dx + 2], acc[2]); acc[3] = fmaf(g4.w, row[dx + 3], acc[3]);
+          acc[ci][0] = fmaf(g4[dx].x, row[dx], acc[ci][0]); acc[ci][1] = fmaf(g4[dx].y, row[dx + 1], acc[ci][1]);
+          acc[ci][2] = fmaf(g4[dx].z, row[dx + 2], acc[ci][2]); acc[ci][3] = fmaf(g4[dx].w, row[dx + 3], acc[ci][3]);
         }
       }
+    }
+#pragma unroll
+    for (int ci = 0; ci < BCC / 4; ++ci) {
+      const int c = cs + 4 * ci;
       const int x = x0 + 4 * q, y = y0 + r;
       if (c < cc && y < H) {
         float* o = po + (int64_t)(c0 + c) * HW + (int64_t)y * W + x;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (x + i < W) o[i] = acc[i] / cf;
+          if (x + i < W) o[i] = acc[ci][i] / cf;
       }
     }
   }
