@@ -259,7 +259,10 @@ def _timed(fn, steps, barrier):
 # DRAM bytes per 256^3 pair from the committed `ncu --set full` capture of one inference (dram__bytes_read.sum + dram__bytes_write.sum
 # summed over the launches of a class; file named in `traffic_source`).  None until a capture of the current kernels is committed.
 NCU_TRAFFIC = {
-    "source": None, "conv_all": None, "conv_hbm_layers": None, "stage": None,
+    "source": "profiles/r02i_ncu_full_step_1x256.csv (ncu --set full --clock-control none of one 256^3 inference; per pair, scaled by the batch)",
+    "conv_all": 3.052e9,            # the 36 conv launches (algorithmic FLOP-side traffic is not defined; weights + activations)
+    "conv_hbm_layers": 1.979e9,     # block2 conv0.0 (0.672 GB) + block2 heads (1.307 GB); algorithmic 2.013 GB
+    "stage": 3.488e9,               # the three stage launches; algorithmic 3.355 GB
 }
 
 
