@@ -763,6 +763,31 @@ static int sk_launch(const SkParams& P, const CUtensorMap& tmA, const CUtensorMa
   return check_launch("conv_stack_kernel");
 }
 
+// launch-plan cache (see ofsv_conv_halo): a few dozen distinct (layer, shape) descriptors per model
+struct SkCacheEntry { bool used; int sms, tuning; ofsv_conv_desc d; SkPlan pl; SkConfig cfg; SkParams P; };
+constexpr int SK_CACHE_N = 128;
+static SkCacheEntry* g_sk_cache = nullptr;
+static int g_sk_cache_next = 0;
+static std::mutex g_sk_cache_mu;
+static int sk_tuning_stamp() { return (g_stack_epi.load(std::memory_order_relaxed) + 2) * 16 + g_stack_td.load(std::memory_order_relaxed); }
+static bool sk_cache_get(const ofsv_conv_desc* d, int sms, SkPlan* pl, SkConfig* cfg, SkParams* P) {
+  std::lock_guard<std::mutex> lk(g_sk_cache_mu);
+  if (!g_sk_cache) return false;
+  const int stamp = sk_tuning_stamp();
+  for (int i = 0; i < SK_CACHE_N; ++i) {
+    const SkCacheEntry& e = g_sk_cache[i];
+    if (e.used && e.sms == sms && e.tuning == stamp && memcmp(&e.d, d, sizeof(*d)) == 0) { *pl = e.pl; *cfg = e.cfg; *P = e.P; return true; }
+  }
+  return false;
+}
+static void sk_cache_put(const ofsv_conv_desc* d, int sms, const SkPlan& pl, const SkConfig& cfg, const SkParams& P) {
+  std::lock_guard<std::mutex> lk(g_sk_cache_mu);
+  if (!g_sk_cache) g_sk_cache = new SkCacheEntry[SK_CACHE_N]();
+  SkCacheEntry& e = g_sk_cache[g_sk_cache_next];
+  g_sk_cache_next = (g_sk_cache_next + 1) % SK_CACHE_N;
+  e.used = true; e.sms = sms; e.tuning = sk_tuning_stamp(); e.d = *d; e.pl = pl; e.cfg = cfg; e.P = P;
+}
+
 }  // namespace ofsv
 
 using namespace ofsv;
@@ -917,16 +942,20 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
   }
   if (sk_wants_ring(d)) return conv_halo_ring(d, x, w, bias, prelu, residual, y, stream);   // 2^d-tap space-to-depth conv0 layers
 
-  SkPlan pl;
-  if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_halo: layer has no stacked form"); return OFSV_ENOSUP; }
   PFN_encodeTiled encode = get_tensor_map_encoder();
   if (!encode) { set_error("ofsv_conv_halo: cuTensorMapEncodeTiled unavailable"); return OFSV_ECUDA; }
   const int sms = device_num_sms();
+  // plan / configuration / MMA list are pure functions of (descriptor, SM count): ~15 us of host work per launch, which is what
+  // bounds the small configurations (a 160x224 frame pair is 36 conv launches of ~10 us of GPU time each) — remembered per
+  // descriptor; only the tensor maps (which hold the pointers) are built per call
+  SkPlan pl;
   SkConfig cfg;
+  SkParams P;
+  if (!sk_cache_get(d, sms, &pl, &cfg, &P)) {
+  if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_halo: layer has no stacked form"); return OFSV_ENOSUP; }
   if (!sk_configure(d, pl, sms, &cfg)) { set_error("ofsv_conv_halo: layer does not fit (Cin_s=%d Cout_w=%d)", d->Cin_s, d->Cout_w); return OFSV_ENOSUP; }
 
   const int KC = pl.KC, ROWB = KC * 2;
-  SkParams P;
   memset(&P, 0, sizeof(P));
   P.N = d->N; P.Do = d->Do; P.Ho = d->Ho; P.Wo = d->Wo; P.Dy = d->Dy; P.Hy = d->Hy; P.Wy = d->Wy;
   P.Cout_s = d->Cout_s; P.Cout_w = d->Cout_w; P.out_stride = d->out_stride; P.nd = d->nd;
@@ -965,6 +994,11 @@ extern "C" int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void
       OFSV_REQUIRE(ncols >= 16 && ncols % 16 == 0 && ncols <= 256 && o.col0 * d->Cout_w + o.lo + ncols <= 512, "ofsv_conv_halo: internal error (op encoding)");
     }
   }
+#ifndef OFSV_STACK_PROBE
+  sk_cache_put(d, sms, pl, cfg, P);
+#endif
+  }
+  const int KC = pl.KC;
   const int64_t total = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
   OFSV_REQUIRE(total < (1ll << 31), "ofsv_conv_halo: too many super-tiles");
 

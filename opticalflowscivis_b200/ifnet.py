@@ -92,6 +92,7 @@ class _Layer:
             self.prelu[:cout] = prelu
         self.out_f32, self.residual, self.shuffle = out_f32, residual, shuffle
         self.in_s2d = self.out_s2d = False
+        self._desc_cache = {}
 
     def _structure_desc(self):
         """Descriptor carrying only what the weight layouts depend on (taps, Cin_s, Cout_w) — no shapes."""
@@ -127,8 +128,15 @@ class _Layer:
             shp = [n] + list(sp) + [self.cout_s]
         return shp
 
-    def desc(self, n, in_sp, act_dtype):
-        """in_sp = LOGICAL (D,H,W) of the input (before space-to-depth); returns (ConvDesc, logical out_sp)."""
+    def desc(self, n, in_sp, act_dtype, has_residual=None, hfast=False):
+        """in_sp = LOGICAL (D,H,W) of the input (before space-to-depth); returns (ConvDesc, logical out_sp).  `has_residual`
+        overrides the layer's own flag (state accumulation in the head conv), `hfast` selects the H-fastest depth-to-space output.
+        Descriptors are cached per argument tuple (filling the tap table from Python costs ~40 us, more than the GPU time of a small
+        layer) and must be treated as read-only."""
+        key = (n, tuple(in_sp), act_dtype, has_residual, bool(hfast))
+        hit = self._desc_cache.get(key)
+        if hit is not None:
+            return hit
         d = _C.ConvDesc()
         d.nd = self.nd
         d.N, (d.Di, d.Hi, d.Wi), d.Cin_s = n, in_sp, self.cin_s
@@ -152,12 +160,14 @@ class _Layer:
         d.nphase, d.ntaps = self.nphase, self.ntaps
         for i, t in enumerate(self.taps):
             d.tap_off[i][0], d.tap_off[i][1], d.tap_off[i][2], d.tap_off[i][3] = t[0], t[1], t[2], 0
-        d.has_prelu, d.has_residual = int(self.prelu is not None), int(self.residual)
+        d.has_prelu = int(self.prelu is not None)
+        d.has_residual = int(self.residual if has_residual is None else has_residual)
         d.in_dtype = act_dtype
         d.out_dtype = _C.F32 if self.out_f32 else act_dtype
         d.out_shuffle = self.shuffle
         d.out_s2d = int(self.out_s2d)
-        d.out_shuffle_hfast = 0
+        d.out_shuffle_hfast = int(bool(hfast))
+        self._desc_cache[key] = (d, osp)
         return d, osp
 
 
@@ -327,16 +337,14 @@ class IFBlock(nn.Module):
                 lay = self._s2d0
             elif s2d_in and li == 1 and self._s2d1_ok:
                 lay = self._s2d1
-            d, osp = lay.desc(n, sp, act_dtype)
-            if li == 11 and state_prev is not None:
-                if not lay.shuffle:
-                    raise RuntimeError("state accumulation needs the depth-to-space head conv")
-                d.has_residual = 1
+            acc = li == 11 and state_prev is not None
+            if acc and not lay.shuffle:
+                raise RuntimeError("state accumulation needs the depth-to-space head conv")
+            if li == 11 and hfast and (not lay.shuffle or self.nd != 3):
+                raise RuntimeError("the H-fastest state layout needs the 3-D depth-to-space head conv")
+            d, osp = lay.desc(n, sp, act_dtype, has_residual=True if acc else None, hfast=(li == 11 and hfast))
             odt = torch.float32 if lay.out_f32 else tdt
             if li == 11 and hfast:
-                if not lay.shuffle or self.nd != 3:
-                    raise RuntimeError("the H-fastest state layout needs the 3-D depth-to-space head conv")
-                d.out_shuffle_hfast = 1
                 y = torch.empty((n, osp[0], osp[2], osp[1], lay.cout_s), device=x.device, dtype=odt)
             elif lay.out_s2d:
                 y = ops.workspace(("conv0", id(self)), lay.out_shape(n, osp), odt, x.device)

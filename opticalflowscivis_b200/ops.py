@@ -80,6 +80,14 @@ def reference_flavor() -> str:
     return "cpu" if _FLAVOR["mode"] == _C.REF_CPU else "cuda"
 
 
+def _on(dev):
+    """Device guard for a launch: a no-op when `dev` is already current (torch.cuda.device costs ~10 us per launch, more than the
+    GPU time of the small layers of a 160x224 frame pair)."""
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NOSPAN
+    return torch.cuda.device(dev)
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -120,7 +128,7 @@ def _warp_fwd(x, f):
     nd = x.dim() - 2
     dev = x.device
     out = torch.empty_like(x)
-    with torch.cuda.device(dev):
+    with _on(dev):
         if nd == 2:
             n, c, h, w = x.shape
             _C.check(_C.lib().ofsv_warp2d_f32(_p(x), _p(f), _p(linspace_table(w, dev)), _p(linspace_table(h, dev)),
@@ -141,7 +149,7 @@ def warp3d_gather(tenInput: torch.Tensor, tenFlow: torch.Tensor) -> torch.Tensor
     n, c, d, h, w = x.shape
     dev = x.device
     out = torch.empty_like(x)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _C.check(_C.lib().ofsv_warp3d_gather_f32(_p(x), _p(f), _p(linspace_table(h, dev)), _p(linspace_table(d, dev)),
                                                  _p(linspace_table(w, dev)), _p(out), n, c, d, h, w, _FLAVOR["mode"], _stream()))
     return out
@@ -159,7 +167,7 @@ def warp_bwd(tenInput, tenFlow, grad_out, need_input_grad=True, need_flow_grad=T
     dev = x.device
     gx = torch.empty_like(x) if need_input_grad else None       # zero-filled by the library
     gf = torch.empty_like(f) if need_flow_grad else None
-    with torch.cuda.device(dev), _span("warp_bwd"):
+    with _on(dev), _span("warp_bwd"):
         if nd == 2:
             n, c, h, w = x.shape
             _C.check(_C.lib().ofsv_warp2d_bwd_f32(_p(x), _p(f), _p(go), _p(linspace_table(w, dev)), _p(linspace_table(h, dev)),
@@ -225,7 +233,7 @@ def warp_blend(img0, img1, flow, mask_logit, want_warped=True, want_merged=True,
     ms = torch.empty_like(img0) if want_mask else None
     dev = img0.device
     L = _C.lib()
-    with torch.cuda.device(dev), _span("warp_blend"):
+    with _on(dev), _span("warp_blend"):
         if nd == 2:
             n, _, h, w = img0.shape
             _C.check(L.ofsv_warp_blend_2d_f32(_p(img0), _p(img1), _p(flow), _p(mask_logit if need_m else None),
@@ -246,7 +254,7 @@ def blend(w0, w1, mask_logit):
     if not (w0.shape == w1.shape == m.shape):
         raise ValueError("blend: shapes differ")
     out = torch.empty_like(w0)
-    with torch.cuda.device(w0.device):
+    with _on(w0.device):
         _C.check(_C.lib().ofsv_blend_f32(_p(w0), _p(w1), _p(m), _p(out), w0.numel(), _stream()))
     return out
 
@@ -266,7 +274,7 @@ def corr81_fwd(f1, f2, leaky_slope=None, out=None):
                 or out.shape[2:] != f1.shape[2:] or out.stride()[1:] != (h * w, w, 1)):
             raise ValueError("corr81: `out` must be a float32 CUDA (B,>=81,H,W) tensor with dense (C,H,W) strides")
     bstride = out.stride(0) if b > 1 else 81 * h * w
-    with torch.cuda.device(f1.device):
+    with _on(f1.device):
         L = _C.lib()
         ns = L.ofsv_corr81_fwd_splits(b, c, h, w)          # coarse pyramid levels: channels split over CTAs through a scratch buffer
         work = torch.empty((ns, b, 81, h, w), device=f1.device, dtype=torch.float32) if ns > 1 else None
@@ -282,7 +290,7 @@ def corr81_bwd(f1, f2, gout):
     if gout.shape != (b, 81, h, w):
         raise ValueError("corr81_bwd: grad_output shape")
     g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
-    with torch.cuda.device(f1.device):
+    with _on(f1.device):
         _C.check(_C.lib().ofsv_corr81_bwd_f32(_p(f1), _p(f2), _p(gout), _p(g1), _p(g2), b, c, h, w, _stream()))
     return g1, g2
 
@@ -290,7 +298,7 @@ def corr81_bwd(f1, f2, gout):
 def _upsample_flow_ac_fwd(flow, h, w, if_rate):
     b, _, h_, w_ = flow.shape
     out = torch.empty(b, 2, h, w, device=flow.device, dtype=torch.float32)
-    with torch.cuda.device(flow.device):
+    with _on(flow.device):
         _C.check(_C.lib().ofsv_upsample_flow_ac_f32(_p(flow), _p(out), b, h_, w_, h, w, int(if_rate), _stream()))
     return out
 
@@ -302,7 +310,7 @@ def upsample_flow_ac_bwd(grad_out, h_in, w_in, if_rate=True):
         raise ValueError("upsample_flow_ac_bwd: expected (B,2,h,w)")
     b, _, h, w = go.shape
     gin = torch.empty(b, 2, h_in, w_in, device=go.device, dtype=torch.float32)     # zero-filled by the library
-    with torch.cuda.device(go.device):
+    with _on(go.device):
         _C.check(_C.lib().ofsv_upsample_flow_ac_bwd_f32(_p(go), _p(gin), b, h_in, w_in, h, w, int(if_rate), _stream()))
     return gin
 
@@ -331,7 +339,7 @@ def upsample_flow_ac(flow, h, w, if_rate=True):
 def _warping_no_div_fwd(x, flow):
     b, c, h, w = x.shape
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _C.check(_C.lib().ofsv_warping_no_div_f32(_p(x), _p(flow), _p(out), b, c, h, w, _FLAVOR["mode"], _stream()))
     return out
 
@@ -344,7 +352,7 @@ def warping_no_div_bwd(x, flow, grad_out, need_input_grad=True, need_flow_grad=T
     b, c, h, w = x.shape
     gx = torch.empty_like(x) if need_input_grad else None          # zero-filled by the library
     gf = torch.empty_like(flow) if need_flow_grad else None
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _C.check(_C.lib().ofsv_warping_no_div_bwd_f32(_p(x), _p(flow), _p(go), _p(gx), _p(gf), b, c, h, w, _FLAVOR["mode"], _stream()))
     return gx, gf
 
@@ -410,7 +418,7 @@ def pack_block_input(img0, img1, warped0, warped1, mask, flow, scale, act_dtype,
         dst = workspace((key, scale), s2d_shape(n, osp, cs), _TDT[act_dtype], img0.device)
     else:
         dst = torch.empty([n] + osp + [cs], device=img0.device, dtype=_TDT[act_dtype])
-    with torch.cuda.device(img0.device), _span("pack_block_input"):
+    with _on(img0.device), _span("pack_block_input"):
         _C.check(_C.lib().ofsv_pack_block_input(_p(img0), _p(img1), _p(warped0), _p(warped1), _p(mask), _p(flow), _p(dst),
                                                 act_dtype, nd, n, d, h, w, scale, cs, int(s2d), _stream()))
     return dst
@@ -421,7 +429,7 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
     d, h, w = ([1] + list(sp)) if nd == 2 else list(sp)
     flow = torch.empty([n, 2 * nd] + list(sp), device=head.device, dtype=torch.float32)
     mask = torch.empty([n, 1] + list(sp), device=head.device, dtype=torch.float32)
-    with torch.cuda.device(head.device), _span("head_upsample_add"):
+    with _on(head.device), _span("head_upsample_add"):
         _C.check(_C.lib().ofsv_head_upsample_add(_p(head), head.shape[-1], _p(flow_prev), _p(mask_prev), _p(flow), _p(mask),
                                                  nd, n, d, h, w, scale, _stream()))
     return flow, mask
@@ -456,7 +464,7 @@ def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merge
             pk = workspace((key, scale_next), s2d_shape(n, osp, 16), torch.bfloat16, dev)
         else:
             pk = torch.empty([n] + osp + [16], device=dev, dtype=torch.bfloat16)
-    with torch.cuda.device(dev), _span("block_stage"):
+    with _on(dev), _span("block_stage"):
         _C.check(_C.lib().ofsv_block_stage_3d(_p(head), _p(fm_prev), _p(img0), _p(img1), _p(linspace_table(h, dev)),
                                               _p(linspace_table(d, dev)), _p(linspace_table(w, dev)), _p(fm), _p(mg), _p(ms),
                                               _p(pk), n, d, h, w, scale_head, scale_next, int(bool(pack_s2d) and scale_next != 0), _FLAVOR["mode"],
@@ -476,7 +484,7 @@ def conv_pack_weights(desc: "_C.ConvDesc", w_tap: torch.Tensor, layout: int) -> 
     (ofsv_conv_pack_weights).  Only the layer structure of `desc` is read (taps, Cin_s, Cout_w)."""
     w = _cuda_f32(w_tap, "w_tap")
     out = torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device)
-    with torch.cuda.device(w.device):
+    with _on(w.device):
         _C.check(_C.lib().ofsv_conv_pack_weights(ctypes.byref(desc), _p(w), _p(out), int(layout), _stream()))
     return out
 
@@ -496,7 +504,7 @@ def set_tuning(key: str, value: int) -> None:
 def conv(desc: "_C.ConvDesc", x, w, bias, prelu, residual, y, engine: str):
     L = _C.lib()
     fn = {"tc": L.ofsv_conv_tc, "halo": L.ofsv_conv_halo, "simt": L.ofsv_conv_simt}[engine]
-    with torch.cuda.device(x.device), _span("conv_" + engine):
+    with _on(x.device), _span("conv_" + engine):
         _C.check(fn(ctypes.byref(desc), _p(x), _p(w), _p(bias), _p(prelu), _p(residual), _p(y), _stream()))
     return y
 
@@ -507,7 +515,7 @@ def u8_to_f32(src: torch.Tensor, div: float = 255.0) -> torch.Tensor:
         raise TypeError("u8_to_f32: expected a uint8 CUDA tensor")
     src = src.contiguous()
     dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _C.check(_C.lib().ofsv_u8_to_f32(_p(src), _p(dst), src.numel(), float(div), _stream()))
     return dst
 
@@ -520,7 +528,7 @@ def f32_to_u8(src: torch.Tensor, mul: float = 255.0) -> torch.Tensor:
     `(img * 255).byte()` (Flow-3D/inference_img.py:105) on the device, so that byte volumes are downloaded as bytes."""
     x = _cuda_f32(src, "src")
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _C.check(_C.lib().ofsv_f32_to_u8(_p(x), _p(out), x.numel(), float(mul), _stream()))
     return out
 
@@ -542,7 +550,7 @@ def sq_err_sums(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.T
     count = a.numel() // max(n, 1)
     out = torch.empty(n, dtype=torch.float64, device=a.device)
     part = torch.empty(max(n, 1) * METRIC_BLOCKS, dtype=torch.float64, device=a.device)
-    with torch.cuda.device(a.device), _span("sq_err"):
+    with _on(a.device), _span("sq_err"):
         _C.check(_C.lib().ofsv_sq_err_f64(_p(a), _p(b), _p(part), _p(out), n, count, float(scale), _stream()))
     return out
 
@@ -556,7 +564,7 @@ def ssim2d_means(x: torch.Tensor, y: torch.Tensor, data_range: float = 255.0) ->
     n = x.numel() // (H * W)
     out = torch.empty(n, dtype=torch.float64, device=x.device)
     part = torch.empty(max(n, 1) * METRIC_BLOCKS, dtype=torch.float64, device=x.device)
-    with torch.cuda.device(x.device), _span("ssim2d"):
+    with _on(x.device), _span("ssim2d"):
         _C.check(_C.lib().ofsv_ssim2d_f64(_p(x), _p(y), _p(part), _p(out), n, H, W, float(data_range), _stream()))
     return out.reshape(x.shape[:-2])
 

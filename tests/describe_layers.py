@@ -18,9 +18,7 @@ for bi, (blk, sc) in enumerate(zip((net.block0, net.block1, net.block2), (4, 2, 
         layers[1] = blk._s2d1
     sp = (s // sc,) * 3
     for li, lay in enumerate(layers):
-        d, osp = lay.desc(n, sp, _C.BF16)
-        if li == 11:
-            d.out_shuffle_hfast = 1
+        d, osp = lay.desc(n, sp, _C.BF16, hfast=(li == 11))
         _C.check(L.ofsv_conv_halo_describe(ctypes.byref(d), buf, 512))
         print(f"block{bi} layer{li:2d} in {sp} Cin_s={lay.cin_s:3d} Cout_w={lay.cout_w:3d}: {buf.value.decode()}")
         sp = osp

@@ -368,6 +368,7 @@ def test_stacked_halo_engine_vs_tap_evaluator(nd, c):
             lc, ld = Lc[min(li, 12)], Ld[min(li, 12)]
             xin = (torch.randn((2,) + sp + (lc.cin_s,)) * 0.5).bfloat16().float()
             d, osp = lc.desc(2, sp, _C.BF16)
+            d = _C.ConvDesc.from_buffer_copy(d)           # descriptors are cached per layer: mutate a copy
             res = None
             if lc.residual:
                 res = (torch.randn((2,) + osp + (lc.cout_s,)) * 0.5).bfloat16().float()
