@@ -598,8 +598,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "ERROR")      # keep stdout to the one JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout to the ONE JSON line: NCCL writes its version banner to fd 1 when the communicator is created (at the first
+        # collective), so stdout points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     try:
         (run_upflow_ops if args.workload == "upflow_ops" else run_ours)(args, rank, world, local_rank)
     finally:
