@@ -513,13 +513,152 @@ __global__ void __launch_bounds__(256, OFSV_HF_MINB_COLS) stage3d_hfast_cols_ker
   }
 }
 
+// Column variant with CPT (2 or 4) ADJACENT columns per thread: the warp still walks the planes of its columns (the L1-friendly order:
+// a plane step of the CTA touches the source rows (z, y) = (w0 .. w0 + 8 CPT, d .. d + 1), half of which the previous step loaded),
+// but the voxel's own image values are ONE 8 / 16-byte load per thread and plane instead of CPT strided 4-byte loads (a lane-along-h
+// warp touches 32 lines per request either way), the CPT voxels of a plane are independent chains for the scheduler to interleave,
+// and merged / sigmoid(mask) leave as 8 / 16-byte stores without the shared tile and its barrier.
+#ifndef OFSV_HF_CPT
+#define OFSV_HF_CPT 2
+#endif
+#ifndef OFSV_HF_MINB_CPT
+#define OFSV_HF_MINB_CPT 3
+#endif
+template <int SH, int SN, bool S2D, bool FMA, int CPT>
+__global__ void __launch_bounds__(256, OFSV_HF_MINB_CPT) stage3d_hfast_colsn_kernel(const HfPtrs q, const Warp3dParams P) {
+  constexpr int TW = HF_W * CPT;
+  const int H = P.H, W = P.W, D = P.D, HW = H * W;
+  const int V = D * HW;
+  const int nzb = (D + HF_CDZ - 1) / HF_CDZ;
+  const int n = blockIdx.z / nzb, dbeg = (blockIdx.z - n * nzb) * HF_CDZ;
+  const int nplanes = min(HF_CDZ, D - dbeg);
+  const int h0 = blockIdx.y * HF_H, w0 = blockIdx.x * TW;
+  const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;
+  const int h = h0 + lane, wb = w0 + wl * CPT;                      // this thread's columns wb .. wb + CPT - 1 (W % 8 == 0: all in or all out)
+  if (wb >= W) return;                                              // warp-uniform; no block-wide synchronisation below
+  const bool okh = h < H;
+  const int hc = min(h, H - 1);
+  constexpr int SHD = SH > 1 ? SH : 1;
+  constexpr int NROWS = SH > 1 ? HF_H / SHD + 2 : 0;
+  const int Dh = D / SHD, Hh = H / SHD, Wh = W / SHD;
+  const float* hb = SH ? hf_pin(q.head + (int64_t)n * Dh * Hh * Wh * 8) : nullptr;
+  const float* fprev = q.fm_prev ? hf_pin(q.fm_prev + (int64_t)n * V * 8) : nullptr;
+  float* fout = SH ? hf_pin(q.fm_out + (int64_t)n * V * 8) : nullptr;
+  const float* i0p = hf_pin(q.img0 + (int64_t)n * V);
+  const float* i1p = hf_pin(q.img1 + (int64_t)n * V);
+  const bool has_prev = fprev != nullptr;
+  const bool need_m = q.merged != nullptr || q.mask_sig != nullptr;
+  const float lh = __ldg(q.lin_h + hc);
+  const int io = hc * W + wb;                                       // [H][W] image planes: the CPT columns are consecutive floats
+  HfLerp Ly{0, 0, 0.f, 0.f};
+  int hb0 = 0, own = 0;
+  if (SH > 1) {
+    const float rs = 1.0f / (float)SHD;
+    Ly = hf_up_index(hc, Hh, rs);
+    hb0 = hf_up_index(h0, Hh, rs).i0;
+    own = min(hb0 + lane, Hh - 1);
+  }
+  const int s0 = Ly.i0 - hb0, s1 = Ly.i1 - hb0;
+  float lw[CPT], xl0[CPT], xl1[CPT];
+  int so[CPT], c0[CPT], c1[CPT];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    lw[k] = __ldg(q.lin_w + wb + k);
+    so[k] = (wb + k) * H + hc;                                      // [W][H] state planes
+    const HfLerp Lx = SH > 1 ? hf_up_index(wb + k, Wh, 1.0f / (float)SHD) : HfLerp{0, 0, 0.f, 0.f};
+    c0[k] = Lx.i0 * Hh + own; c1[k] = Lx.i1 * Hh + own; xl0[k] = Lx.l0; xl1[k] = Lx.l1;
+  }
+  V8 pv;
+  if (has_prev) pv = ldg256(fprev + ((int64_t)dbeg * HW + so[0]) * 8);
+  VecF<CPT> pi0, pi1;                                                // own image values, one plane ahead
+  if (SN != 0) { pi0 = ldg_vec<CPT>(i0p + dbeg * HW + io); pi1 = ldg_vec<CPT>(i1p + dbeg * HW + io); }
+  for (int it = 0; it < nplanes; ++it) {
+    const int d = dbeg + it;
+    const float ld = __ldg(q.lin_d + d);
+    const HfLerp Lz = SH > 1 ? hf_up_index(d, Dh, 1.0f / (float)SHD) : HfLerp{0, 0, 0.f, 0.f};
+    const int r0 = Lz.i0 * Wh * Hh, r1 = Lz.i1 * Wh * Hh;
+    const VecF<CPT> o0 = pi0, o1 = pi1;
+    if (SN != 0 && it + 1 < nplanes) { pi0 = ldg_vec<CPT>(i0p + (d + 1) * HW + io); pi1 = ldg_vec<CPT>(i1p + (d + 1) * HW + io); }
+    VecF<CPT> mg, ms;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const V8 cur = pv;
+      const bool more = k + 1 < CPT || it + 1 < nplanes;
+      if (has_prev && more) pv = ldg256(fprev + ((int64_t)(k + 1 < CPT ? d : d + 1) * HW + so[k + 1 < CPT ? k + 1 : 0]) * 8);
+      V8 hv, st;
+      if (SH == 0) {
+        st = cur;
+      } else if (SH == 1) {
+        hv = ldg256(hb + ((int64_t)d * HW + so[k]) * 8);
+      } else {
+        V8 a0, a1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0.v[i] = 0.f; a1.v[i] = 0.f; }
+        if (lane < NROWS) {                                         // x lerp of coarse row `own` for the two z taps (ATen order: x, y, z)
+          a0 = hf_lerp8(ldg256(hb + (int64_t)(r0 + c0[k]) * 8), xl0[k], ldg256(hb + (int64_t)(r0 + c1[k]) * 8), xl1[k]);
+          a1 = hf_lerp8(ldg256(hb + (int64_t)(r1 + c0[k]) * 8), xl0[k], ldg256(hb + (int64_t)(r1 + c1[k]) * 8), xl1[k]);
+        }
+        const V8 b0 = hf_lerp8(hf_shfl8(a0, s0), Ly.l0, hf_shfl8(a0, s1), Ly.l1);
+        const V8 b1 = hf_lerp8(hf_shfl8(a1, s0), Ly.l0, hf_shfl8(a1, s1), Ly.l1);
+        hv = hf_lerp8(b0, Lz.l0, b1, Lz.l1);
+      }
+      if (SH != 0) {
+        const float sh = (float)SHD;
+        if (has_prev) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) st.v[i] = __fadd_rn(cur.v[i], __fmul_rn(hv.v[i], sh));
+          st.v[6] = __fadd_rn(cur.v[6], hv.v[6]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) st.v[i] = __fmul_rn(hv.v[i], sh);
+          st.v[6] = hv.v[6];
+        }
+        st.v[7] = 0.0f;
+        if (okh) stg256(fout + ((int64_t)d * HW + so[k]) * 8, st);
+      }
+      const float m = st.v[6];
+      const Trilin t0 = trilin_setup(st.v[0], st.v[1], st.v[2], lh, ld, lw[k], D, H, W, P.hs, P.ref_mode);
+      const Trilin t1 = trilin_setup(st.v[3], st.v[4], st.v[5], lh, ld, lw[k], D, H, W, P.hs, P.ref_mode);
+      const Taps8 g0 = hf_gather(i0p, t0), g1 = hf_gather(i1p, t1);
+      const float a = trilin_reduce<FMA>(g0, t0), b = trilin_reduce<FMA>(g1, t1);
+      if (need_m) {
+        ms.v[k] = sigmoidf_ref(m);
+        mg.v[k] = __fadd_rn(__fmul_rn(a, ms.v[k]), __fmul_rn(b, __fsub_rn(1.0f, ms.v[k])));
+      }
+      if (SN == 1 && okh) {
+        int64_t ro;
+        if (S2D) ro = s2d_row(3, n, d, h, wb + k, D, H, W) * 16;
+        else ro = ((((int64_t)n * D + d) * H + h) * W + wb + k) * 16;
+        stg256_b32(q.pack_out + ro, hf_pack2(o0.v[k], o1.v[k]), hf_pack2(a, b), hf_pack2(m, st.v[0]), hf_pack2(st.v[1], st.v[2]),
+                   hf_pack2(st.v[3], st.v[4]), hf_pack2(st.v[5], 0.0f), 0u, 0u);
+      }
+    }
+    if (need_m && okh) {
+      const int64_t g = (int64_t)n * V + (int64_t)d * HW + io;
+      if (q.merged) stg_vec<CPT>(q.merged + g, mg);
+      if (q.mask_sig) stg_vec<CPT>(q.mask_sig + g, ms);
+    }
+  }
+}
+
+#ifndef OFSV_HF_FIN_COLS
+#define OFSV_HF_FIN_COLS 0      // 1: the stages without a packed output also run the column kernel
+#endif
 template <int SH, int SN, bool S2D, bool FMA>
 static int launch_hfast(const HfPtrs& q, const Warp3dParams& P, cudaStream_t st) {
-  if constexpr (SN == 1 && SH != 0) {
-    const dim3 grid((unsigned)cdiv(P.W, HF_W), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_CDZ)));
+  if constexpr ((SN == 1 && SH != 0) || (SN == 0 && OFSV_HF_FIN_COLS)) {
+    constexpr int CPT = OFSV_HF_CPT > 1 ? OFSV_HF_CPT : 2;
+    const dim3 grid((unsigned)cdiv(P.W, HF_W * (OFSV_HF_CPT > 1 ? CPT : 1)), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_CDZ)));
     if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
-    stage3d_hfast_cols_kernel<SH, S2D, FMA><<<grid, 256, 0, st>>>(q, P);
-    return check_launch("stage3d_hfast_cols_kernel");
+    if (OFSV_HF_CPT > 1 || SN == 0) {
+      stage3d_hfast_colsn_kernel<SH, SN, S2D, FMA, CPT><<<grid, 256, 0, st>>>(q, P);
+      return check_launch("stage3d_hfast_colsn_kernel");
+    }
+    if constexpr (SN == 1) {
+      stage3d_hfast_cols_kernel<SH, S2D, FMA><<<grid, 256, 0, st>>>(q, P);
+      return check_launch("stage3d_hfast_cols_kernel");
+    }
+    return OFSV_EINVAL;
   } else {
     const dim3 grid((unsigned)cdiv(P.W, HF_W), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_DZ)));
     if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
