@@ -568,6 +568,9 @@ __global__ void __launch_bounds__(256, OFSV_HF_MINB_CPT) stage3d_hfast_colsn_ker
     const HfLerp Lx = SH > 1 ? hf_up_index(wb + k, Wh, 1.0f / (float)SHD) : HfLerp{0, 0, 0.f, 0.f};
     c0[k] = Lx.i0 * Hh + own; c1[k] = Lx.i1 * Hh + own; xl0[k] = Lx.l0; xl1[k] = Lx.l1;
   }
+  float pd[11];                                                     // SN == 2: (w, h)-pair sums of the even plane
+#pragma unroll
+  for (int c = 0; c < 11; ++c) pd[c] = 0.f;
   V8 pv;
   if (has_prev) pv = ldg256(fprev + ((int64_t)dbeg * HW + so[0]) * 8);
   VecF<CPT> pi0, pi1;                                                // own image values, one plane ahead
@@ -580,6 +583,7 @@ __global__ void __launch_bounds__(256, OFSV_HF_MINB_CPT) stage3d_hfast_colsn_ker
     const VecF<CPT> o0 = pi0, o1 = pi1;
     if (SN != 0 && it + 1 < nplanes) { pi0 = ldg_vec<CPT>(i0p + (d + 1) * HW + io); pi1 = ldg_vec<CPT>(i1p + (d + 1) * HW + io); }
     VecF<CPT> mg, ms;
+    float pw[11];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const V8 cur = pv;
@@ -625,6 +629,11 @@ __global__ void __launch_bounds__(256, OFSV_HF_MINB_CPT) stage3d_hfast_colsn_ker
         ms.v[k] = sigmoidf_ref(m);
         mg.v[k] = __fadd_rn(__fmul_rn(a, ms.v[k]), __fmul_rn(b, __fsub_rn(1.0f, ms.v[k])));
       }
+      if (SN == 2) {                                                // 2x2x2 mean, W level: CPT == 2, the pair is this thread's two columns
+        const float c11[11] = {o0.v[k], o1.v[k], a, b, m, st.v[0], st.v[1], st.v[2], st.v[3], st.v[4], st.v[5]};
+#pragma unroll
+        for (int c = 0; c < 11; ++c) pw[c] = k == 0 ? __fmul_rn(c11[c], 0.5f) : __fadd_rn(pw[c], __fmul_rn(c11[c], 0.5f));
+      }
       if (SN == 1 && okh) {
         int64_t ro;
         if (S2D) ro = s2d_row(3, n, d, h, wb + k, D, H, W) * 16;
@@ -638,19 +647,42 @@ __global__ void __launch_bounds__(256, OFSV_HF_MINB_CPT) stage3d_hfast_colsn_ker
       if (q.merged) stg_vec<CPT>(q.merged + g, mg);
       if (q.mask_sig) stg_vec<CPT>(q.mask_sig + g, ms);
     }
+    if (SN == 2) {                                                  // H level: the neighbouring lane; D level: the previous (even) plane
+      static_assert(SN != 2 || CPT == 2, "the pooled output needs the w pair in one thread");
+#pragma unroll
+      for (int c = 0; c < 11; ++c) {
+        const float up = __shfl_down_sync(0xffffffffu, pw[c], 1);
+        const float ph = __fadd_rn(__fmul_rn(pw[c], 0.5f), __fmul_rn(up, 0.5f));
+        pd[c] = (it & 1) ? __fadd_rn(__fmul_rn(pd[c], 0.5f), __fmul_rn(ph, 0.5f)) : ph;
+      }
+      if ((it & 1) && !(lane & 1) && okh) {
+        float r[11];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) r[c] = c >= 5 ? __fmul_rn(pd[c], 0.5f) : pd[c];     // flow channels additionally * 0.5
+        const int oh = h >> 1, ow = wb >> 1, od = d >> 1;
+        int64_t ro;
+        if (S2D) ro = s2d_row(3, n, od, oh, ow, D / 2, H / 2, W / 2) * 16;
+        else ro = ((((int64_t)n * (D / 2) + od) * (H / 2) + oh) * (W / 2) + ow) * 16;
+        stg256_b32(q.pack_out + ro, hf_pack2(r[0], r[1]), hf_pack2(r[2], r[3]), hf_pack2(r[4], r[5]), hf_pack2(r[6], r[7]),
+                   hf_pack2(r[8], r[9]), hf_pack2(r[10], 0.0f), 0u, 0u);
+      }
+    }
   }
 }
 
+#ifndef OFSV_HF_POOL_COLS
+#define OFSV_HF_POOL_COLS 0     // 1: the stage with the 2x2x2 mean runs the column kernel too
+#endif
 #ifndef OFSV_HF_FIN_COLS
 #define OFSV_HF_FIN_COLS 0      // 1: the stages without a packed output also run the column kernel
 #endif
 template <int SH, int SN, bool S2D, bool FMA>
 static int launch_hfast(const HfPtrs& q, const Warp3dParams& P, cudaStream_t st) {
-  if constexpr ((SN == 1 && SH != 0) || (SN == 0 && OFSV_HF_FIN_COLS)) {
+  if constexpr ((SN == 1 && SH != 0) || (SN == 0 && OFSV_HF_FIN_COLS) || (SN == 2 && OFSV_HF_POOL_COLS && OFSV_HF_CPT == 2)) {
     constexpr int CPT = OFSV_HF_CPT > 1 ? OFSV_HF_CPT : 2;
     const dim3 grid((unsigned)cdiv(P.W, HF_W * (OFSV_HF_CPT > 1 ? CPT : 1)), (unsigned)cdiv(P.H, HF_H), (unsigned)(P.N * cdiv(P.D, HF_CDZ)));
     if (grid.z > 65535u) { set_error("ofsv_block_stage_3d: N*D=%u exceeds grid.z", grid.z); return OFSV_ENOSUP; }
-    if (OFSV_HF_CPT > 1 || SN == 0) {
+    if (OFSV_HF_CPT > 1 || SN != 1) {
       stage3d_hfast_colsn_kernel<SH, SN, S2D, FMA, CPT><<<grid, 256, 0, st>>>(q, P);
       return check_launch("stage3d_hfast_colsn_kernel");
     }
