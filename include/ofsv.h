@@ -243,6 +243,27 @@ int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* nops_out, do
  * epilogue), "stack_td" (0 auto, 1|2|4 = super-tile depth when feasible), "warp_slab" (1 default, 0 = gather kernel only). */
 int ofsv_set_tuning(const char* key, int value);
 
+/* ---- training tier: backward of conv()/deconv() + PReLU — what `loss_G.backward()` runs under every layer of
+ * IFBlock (Flow-3D/model/RIFE.py:255-259, Flow-2D/model/RIFE.py:315-317 through Flow-{2D,3D}/model/IFNet.py:16-27).
+ * The input gradient of a tap-form layer is another tap-form layer (conv <-> transposed conv) and runs on ofsv_conv_halo /
+ * ofsv_conv_tc; these two entries are the rest:
+ *
+ * ofsv_prelu_bias_bwd_bf16: gy, y, gpre bf16 [P][Cs] (y = the layer's output AFTER PReLU; gpre may alias gy); slope fp32 [Cs] or
+ *   NULL (layer without activation: gpre = gy).  gpre = gy * (y > 0 ? 1 : slope); dbias[c] = sum_P gpre; dslope[c] = sum_P gy * pre
+ *   over pre < 0, pre = y / slope (requires slope > 0).  `work`: 2 * Cs * ofsv_prelu_bias_bwd_blocks() floats of scratch; the
+ *   reduction order is fixed (deterministic).
+ * ofsv_conv_wgrad_bf16: dw fp32 [nphase*ntaps][Cin_s][Cout_w] (the tap form ofsv_conv_simt consumes),
+ *     dw[ph*ntaps+t][ci][co] = sum_{n,o} x[n, o*in_stride + tap_off[ph*ntaps+t]][ci] * gy[n, o*out_stride + parity(ph)][co],
+ *   x bf16 [N][Di][Hi][Wi][Cin_s] (the layer's input), gy bf16 [N][Dy][Hy][Wy][gy_cs] (gradient w.r.t. the pre-activation,
+ *   gy_cs >= Cout_w).  Only the geometry fields of the descriptor are read.  bf16 mma.sync GEMM over the output positions, split
+ *   along K over ofsv_conv_wgrad_splits(d) CTAs per tile; `work` = splits * nphase*ntaps*Cin_s*Cout_w floats (may be NULL when
+ *   splits == 1), summed in a fixed order. */
+int ofsv_prelu_bias_bwd_blocks(void);
+int ofsv_prelu_bias_bwd_bf16(const void* gy, const void* y, const float* slope, void* gpre, float* dbias, float* dslope, float* work,
+                             int64_t P, int Cs, void* stream);
+int ofsv_conv_wgrad_splits(const ofsv_conv_desc* d);
+int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, const void* gy, int gy_cs, float* dw, float* work, void* stream);
+
 /* IFBlock output stage: flow/mask deltas at block resolution -> full resolution (IFNet.py:115-116 / :118-119,
  * F.interpolate(.., scale) and flow*scale), then flow += flow_d ; mask += mask_d (IFNet.py:177-178 / :169-170).
  * head [N][D/s][H/s][W/s][Cs] channels-last fp32 (channels 0..2nd-1 flow, 2nd mask); flow_prev/mask_prev may be NULL

@@ -68,6 +68,10 @@ _SIGS = {
     "ofsv_conv_stack_selfcheck": (_I, [ctypes.POINTER(ConvDesc), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
     "ofsv_conv_halo_describe": (_I, [ctypes.POINTER(ConvDesc), ctypes.c_char_p, _I]),
     "ofsv_set_tuning": (_I, [ctypes.c_char_p, _I]),
+    "ofsv_prelu_bias_bwd_blocks": (_I, []),
+    "ofsv_prelu_bias_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "ofsv_conv_wgrad_splits": (_I, [ctypes.POINTER(ConvDesc)]),
+    "ofsv_conv_wgrad_bf16": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _I, _P, _P, _P]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 9 + [_P]),
 }

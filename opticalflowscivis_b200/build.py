@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libofsv.so")
-SOURCES = ["api.cu", "warp.cu", "warp_bwd.cu", "warp3d_slab.cu", "upflow_ops.cu", "upflow_bwd.cu", "ifnet_glue.cu", "conv_simt.cu", "conv_tc.cu", "conv_stack.cu", "conv_halo_ring.cu", "block_stage.cu", "block_stage_hfast.cu", "metrics.cu", "adamw.cu"]
+SOURCES = ["api.cu", "warp.cu", "warp_bwd.cu", "warp3d_slab.cu", "upflow_ops.cu", "upflow_bwd.cu", "ifnet_glue.cu", "conv_simt.cu", "conv_tc.cu", "conv_stack.cu", "conv_bwd.cu", "conv_halo_ring.cu", "block_stage.cu", "block_stage_hfast.cu", "metrics.cu", "adamw.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",

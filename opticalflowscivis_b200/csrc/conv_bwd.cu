@@ -1,0 +1,385 @@
+// Backward of the conv()/deconv() + PReLU layers of IFBlock: what autograd runs under
+// `loss_G.backward()` in Model.update — Flow-3D/model/RIFE.py:255-259, Flow-2D/model/RIFE.py:315-317 through
+// Flow-{2D,3D}/model/IFNet.py:16-27 (conv = nn.Conv + nn.PReLU, deconv = nn.ConvTranspose + nn.PReLU).
+//
+//   ofsv_prelu_bias_bwd_bf16 : gradient through bias + per-channel PReLU of one layer: g_pre, d bias, d slope in one pass.
+//   ofsv_conv_wgrad_bf16     : weight gradient of a layer in the tap form of ofsv_conv_desc,
+//                                dW[ph*ntaps+t][ci][co] = sum_{n,o} x[n, o*in_stride + tap_off][ci] * g[n, o*out_stride + parity(ph)][co]
+//                              as a bf16 tensor-core GEMM whose K axis is the output positions (fp32 accumulate), split over CTAs
+//                              along K with a fixed-order second pass (deterministic, no atomics).
+// The INPUT gradient of every layer type is itself a tap-form convolution (conv <-> transposed conv with the same weights) and
+// runs on the forward engines (ofsv_conv_halo / ofsv_conv_tc) — opticalflowscivis_b200/train.py builds those descriptors.
+#include <mutex>
+
+#include "ofsv_common.cuh"
+
+namespace ofsv {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ bias + PReLU backward
+constexpr int PB_THREADS = 256;
+
+// y is the layer's output AFTER PReLU (what the forward pass kept): for slope > 0 the sign of the pre-activation is the sign of
+// y, and the pre-activation of a negative output is y / slope.  (A non-positive slope would need the pre-activation itself;
+// the reference initialises 0.25 and trains with lr ~1e-4: the host side checks slope > 0 when it re-packs the weights.)
+__global__ void __launch_bounds__(PB_THREADS) prelu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
+                                                                     const float* __restrict__ slope, __nv_bfloat16* __restrict__ gpre,
+                                                                     float* __restrict__ partial, int64_t P, int Cs) {
+  // thread = 8 consecutive channels of a row; rows strided over (thread rows, blocks)
+  const int tpr = Cs / 8;                        // threads per row
+  const int rows_per_pass = PB_THREADS / tpr;
+  const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+  float db[8], ds[8], sl[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    db[i] = ds[i] = 0.f;
+    sl[i] = slope ? slope[tc * 8 + i] : 1.f;
+  }
+  if (tr < rows_per_pass) {
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + tr; r < P; r += (int64_t)gridDim.x * rows_per_pass) {
+      const int64_t off = r * Cs + tc * 8;
+      uint4 gv = *reinterpret_cast<const uint4*>(gy + off);
+      const __nv_bfloat16* g8 = reinterpret_cast<const __nv_bfloat16*>(&gv);
+      uint4 ov;
+      __nv_bfloat16* o8 = reinterpret_cast<__nv_bfloat16*>(&ov);
+      if (slope) {
+        uint4 yv = *reinterpret_cast<const uint4*>(y + off);
+        const __nv_bfloat16* y8 = reinterpret_cast<const __nv_bfloat16*>(&yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g = __bfloat162float(g8[i]), yy = __bfloat162float(y8[i]);
+          const bool pos = yy > 0.f;
+          const float gp = pos ? g : g * sl[i];
+          db[i] += gp;
+          ds[i] += pos ? 0.f : g * (yy / sl[i]);
+          o8[i] = __float2bfloat16(gp);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          db[i] += __bfloat162float(g8[i]);
+          o8[i] = g8[i];
+        }
+      }
+      if (gpre != gy || slope) *reinterpret_cast<uint4*>(gpre + off) = ov;
+    }
+  }
+  // block reduction over the thread rows, in a fixed order
+  __shared__ float red[PB_THREADS * 16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 16 + i] = db[i];
+    red[threadIdx.x * 16 + 8 + i] = ds[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < Cs * 2) {
+    const int which = threadIdx.x / Cs, c = threadIdx.x % Cs;       // 0 = bias, 1 = slope
+    float s = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) s += red[(r * tpr + c / 8) * 16 + which * 8 + (c % 8)];
+    partial[((int64_t)blockIdx.x * 2 + which) * Cs + c] = s;
+  }
+}
+
+__global__ void prelu_bias_bwd_finalize(const float* __restrict__ partial, float* __restrict__ dbias, float* __restrict__ dslope, int nblk,
+                                        int Cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * Cs) return;
+  const int which = i / Cs, c = i % Cs;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[((int64_t)b * 2 + which) * Cs + c];
+  if (which == 0) dbias[c] = s;
+  else if (dslope) dslope[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+constexpr int WG_THREADS = 128;
+constexpr int WG_KC = 32;          // output positions per pipeline stage (two k16 MMA steps)
+
+struct WgradParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* g;
+  float* out;                      // [splits][T][Cin_s][Cout_w]
+  int N, Di, Hi, Wi, Cin_s;
+  int Do, Ho, Wo;
+  int Dy, Hy, Wy, g_cs, Cout_w;
+  int in_stride, out_stride;
+  int T, ntaps, mt, nt;            // tiles along Cin_s / Cout_w
+  int64_t K, Kper;                 // virtual output positions, positions per K split (multiple of WG_KC)
+  int8_t tap[OFSV_MAX_TAPS][4];
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Warp grid over the MT x NT tile (see the table in ofsv_conv_wgrad_bf16).
+template <int MT, int NT>
+struct WgTile {
+  static constexpr int WM = (NT == 16) ? (MT >= 64 ? 4 : (MT >= 32 ? 2 : 1)) : (MT >= 32 ? 2 : 1);
+  static constexpr int WN = (NT == 16 && MT == 16) ? 2 : 4 / WM;
+  static constexpr int WMT = MT / WM, WNT = NT / WN;     // warp tile
+  static_assert(WMT % 16 == 0 && WNT % 8 == 0, "warp tile");
+  static constexpr int XP = MT * 2 + 16, GP = NT * 2 + 16;   // row pitches in bytes (+16: ldmatrix rows fall in distinct banks)
+  static constexpr int STAGE = WG_KC * (XP + GP);
+};
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using TL = WgTile<MT, NT>;
+  __shared__ __align__(16) unsigned char smem[2 * TL::STAGE];
+  __shared__ int xrow_tab[2][WG_KC], grow_tab[2][WG_KC];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tile = blockIdx.x;
+  const int ntile = tile % p.nt; tile /= p.nt;
+  const int mtile = tile % p.mt; tile /= p.mt;
+  const int tap = tile;                                    // ph * ntaps + t
+  const int ph = tap / p.ntaps;
+  const int pz = (ph >> 2) & 1, py = (ph >> 1) & 1, px = ph & 1;
+  const int oz = p.tap[tap][0], oy = p.tap[tap][1], ox = p.tap[tap][2];
+  const int64_t k_begin = (int64_t)blockIdx.y * p.Kper;
+  const int64_t k_end = min(p.K, k_begin + p.Kper);
+  const int nchunk = (int)((k_end - k_begin + WG_KC - 1) / WG_KC);
+
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+
+  auto fill_table = [&](int chunk) {                      // threads 0..31: source rows of the positions of `chunk`
+    if (tid < WG_KC) {
+      const int64_t q = k_begin + (int64_t)chunk * WG_KC + tid;
+      int xr = -1, gr = -1;
+      if (q < k_end) {
+        int r = (int)q;
+        const int vx = r % p.Wo; r /= p.Wo;
+        const int vy = r % p.Ho; r /= p.Ho;
+        const int vz = r % p.Do; const int n = r / p.Do;
+        gr = ((n * p.Dy + vz * p.out_stride + pz) * p.Hy + vy * p.out_stride + py) * p.Wy + vx * p.out_stride + px;
+        const int iz = vz * p.in_stride + oz, iy = vy * p.in_stride + oy, ix = vx * p.in_stride + ox;
+        if (iz >= 0 && iz < p.Di && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) xr = ((n * p.Di + iz) * p.Hi + iy) * p.Wi + ix;
+        else gr = -1;                                      // the product is zero either way: skip both loads
+      }
+      xrow_tab[chunk & 1][tid] = xr;
+      grow_tab[chunk & 1][tid] = gr;
+    }
+  };
+  auto issue_loads = [&](int chunk) {
+    const uint32_t st = sbase + (chunk & 1) * TL::STAGE;
+    constexpr int XPIECES = MT / 8, GPIECES = NT / 8;
+    for (int i = tid; i < WG_KC * XPIECES; i += WG_THREADS) {
+      const int row = i / XPIECES, pc = i % XPIECES;
+      const int xr = xrow_tab[chunk & 1][row];
+      const __nv_bfloat16* src = xr >= 0 ? p.x + (int64_t)xr * p.Cin_s + mtile * MT + pc * 8 : p.x;
+      cp_async16(st + row * TL::XP + pc * 16, src, xr >= 0 ? 16 : 0);
+    }
+    for (int i = tid; i < WG_KC * GPIECES; i += WG_THREADS) {
+      const int row = i / GPIECES, pc = i % GPIECES;
+      const int gr = grow_tab[chunk & 1][row];
+      const __nv_bfloat16* src = gr >= 0 ? p.g + (int64_t)gr * p.g_cs + ntile * NT + pc * 8 : p.g;
+      cp_async16(st + WG_KC * TL::XP + row * TL::GP + pc * 16, src, gr >= 0 ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  constexpr int MI = TL::WMT / 16, NI = TL::WNT / 8;
+  float acc[MI][NI][4];
+#pragma unroll
+  for (int a = 0; a < MI; ++a)
+#pragma unroll
+    for (int b = 0; b < NI; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  const bool active = warp < TL::WM * TL::WN;
+  const int wm = warp / TL::WN, wn = warp % TL::WN;
+  const int m0 = wm * TL::WMT, n0 = wn * TL::WNT;
+
+  if (nchunk > 0) {
+    fill_table(0);
+    __syncthreads();
+    issue_loads(0);
+    if (nchunk > 1) fill_table(1);
+    for (int c = 0; c < nchunk; ++c) {
+      __syncthreads();                                     // table(c+1) visible; stage (c+1)&1 no longer read by anyone
+      if (c + 1 < nchunk) {
+        issue_loads(c + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();                                     // chunk c landed for every thread; table slot c&1 is free again
+      if (c + 2 < nchunk) fill_table(c + 2);
+      if (active) {
+        const uint32_t xs = sbase + (c & 1) * TL::STAGE, gs = xs + WG_KC * TL::XP;
+#pragma unroll
+        for (int ks = 0; ks < WG_KC / 16; ++ks) {
+          uint32_t afr[MI][4];
+          const int mat = lane >> 3, r = lane & 7;
+#pragma unroll
+          for (int a = 0; a < MI; ++a) {
+            // A = x^T: matrices (m-block, k-block) = (mat&1, mat>>1); stored [k][m] -> .trans
+            const uint32_t addr = xs + (ks * 16 + (mat >> 1) * 8 + r) * TL::XP + (m0 + a * 16 + (mat & 1) * 8) * 2;
+            ldmatrix_x4_t(addr, afr[a][0], afr[a][1], afr[a][2], afr[a][3]);
+          }
+          if constexpr (NI % 2 == 0) {
+#pragma unroll
+            for (int b = 0; b < NI; b += 2) {
+              // B = g: matrices (k-block, n-tile) = (mat&1, mat>>1); stored [k][n] -> .trans
+              uint32_t b0, b1, b2, b3;
+              const uint32_t addr = gs + (ks * 16 + (mat & 1) * 8 + r) * TL::GP + (n0 + (b + (mat >> 1)) * 8) * 2;
+              ldmatrix_x4_t(addr, b0, b1, b2, b3);
+#pragma unroll
+              for (int a = 0; a < MI; ++a) {
+                mma_bf16_16816(acc[a][b], afr[a], b0, b1);
+                mma_bf16_16816(acc[a][b + 1], afr[a], b2, b3);
+              }
+            }
+          } else {
+            static_assert(NI == 1 || NI % 2 == 0, "NI");
+            uint32_t b0, b1;
+            const uint32_t addr = gs + (ks * 16 + ((lane >> 3) & 1) * 8 + r) * TL::GP + n0 * 2;
+            ldmatrix_x2_t(addr, b0, b1);
+#pragma unroll
+            for (int a = 0; a < MI; ++a) mma_bf16_16816(acc[a][0], afr[a], b0, b1);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    float* out = p.out + (((int64_t)blockIdx.y * p.T + tap) * p.Cin_s + mtile * MT) * p.Cout_w + ntile * NT;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+      for (int b = 0; b < NI; ++b) {
+        const int row = m0 + a * 16 + g, col = n0 + b * 8 + 2 * t;
+        *reinterpret_cast<float2*>(out + (int64_t)row * p.Cout_w + col) = make_float2(acc[a][b][0], acc[a][b][1]);
+        *reinterpret_cast<float2*>(out + (int64_t)(row + 8) * p.Cout_w + col) = make_float2(acc[a][b][2], acc[a][b][3]);
+      }
+  }
+}
+
+__global__ void conv_wgrad_finalize(const float4* __restrict__ work, float4* __restrict__ dw, int64_t n4, int splits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = work[i];
+  for (int k = 1; k < splits; ++k) {
+    const float4 v = work[(int64_t)k * n4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  dw[i] = s;
+}
+
+int tile_of(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+
+int wgrad_validate(const ofsv_conv_desc* d) {
+  OFSV_REQUIRE(d != nullptr, "conv_wgrad: null descriptor");
+  OFSV_REQUIRE(d->nd == 2 || d->nd == 3, "conv_wgrad: nd must be 2 or 3");
+  OFSV_REQUIRE(d->Cin_s > 0 && d->Cin_s % 16 == 0 && d->Cout_w > 0 && d->Cout_w % 16 == 0, "conv_wgrad: Cin_s / Cout_w must be multiples of 16");
+  OFSV_REQUIRE(d->nphase >= 1 && d->ntaps >= 1 && d->nphase * d->ntaps <= OFSV_MAX_TAPS, "conv_wgrad: too many taps");
+  OFSV_REQUIRE(d->nphase == 1 || d->nphase == (1 << d->nd), "conv_wgrad: nphase must be 1 or 2^nd");
+  OFSV_REQUIRE(!d->out_shuffle && !d->out_s2d, "conv_wgrad: depth-to-space / space-to-depth outputs have no weight-gradient form (use the phase form)");
+  OFSV_REQUIRE(d->N > 0 && d->Do > 0 && d->Ho > 0 && d->Wo > 0, "conv_wgrad: empty output grid");
+  const int64_t K = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+  const int64_t xin = (int64_t)d->N * d->Di * d->Hi * d->Wi, yo = (int64_t)d->N * d->Dy * d->Hy * d->Wy;
+  OFSV_REQUIRE(K < (1ll << 31) && xin < (1ll << 31) && yo < (1ll << 31), "conv_wgrad: more than 2^31 positions");
+  const int par = d->nphase > 1 ? 1 : 0;
+  OFSV_REQUIRE((d->nd == 2 || (d->Do - 1) * d->out_stride + par < d->Dy) && (d->Ho - 1) * d->out_stride + par < d->Hy &&
+                   (d->Wo - 1) * d->out_stride + par < d->Wy,
+               "conv_wgrad: virtual output grid exceeds the output tensor");
+  return OFSV_OK;
+}
+
+int wgrad_splits(const ofsv_conv_desc* d) {
+  const int64_t K = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+  const int64_t tiles = (int64_t)d->nphase * d->ntaps * (d->Cin_s / tile_of(d->Cin_s)) * (d->Cout_w / tile_of(d->Cout_w));
+  const int64_t want = cdiv((int64_t)device_num_sms() * 8, tiles);
+  int64_t s = std::min<int64_t>(want, cdiv(K, 8 * WG_KC));
+  s = std::max<int64_t>(1, std::min<int64_t>(s, 64));
+  return (int)s;
+}
+
+template <int MT, int NT>
+void launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
+  conv_wgrad_kernel<MT, NT><<<grid, WG_THREADS, 0, st>>>(p);
+}
+
+}  // namespace
+}  // namespace ofsv
+
+using namespace ofsv;
+
+extern "C" int ofsv_prelu_bias_bwd_blocks(void) { return 2 * device_num_sms(); }
+
+extern "C" int ofsv_prelu_bias_bwd_bf16(const void* gy, const void* y, const float* slope, void* gpre, float* dbias, float* dslope,
+                                        float* work, int64_t P, int Cs, void* stream) {
+  OFSV_REQUIRE(gy && gpre && dbias && work, "prelu_bias_bwd: null pointer");
+  OFSV_REQUIRE(!slope || (y && dslope), "prelu_bias_bwd: a slope needs the layer output y and a dslope buffer");
+  OFSV_REQUIRE(P > 0 && Cs >= 8 && Cs % 8 == 0 && Cs <= 128, "prelu_bias_bwd: need P > 0 and 8 <= Cs <= 128, Cs %% 8 == 0 (got P=%lld Cs=%d)", (long long)P, Cs);
+  OFSV_REQUIRE(aligned16(gy) && aligned16(gpre) && (!y || aligned16(y)), "prelu_bias_bwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows_per_pass = PB_THREADS / (Cs / 8);
+  int nblk = (int)std::min<int64_t>(ofsv_prelu_bias_bwd_blocks(), cdiv(P, rows_per_pass));
+  prelu_bias_bwd_kernel<<<nblk, PB_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(gy), static_cast<const __nv_bfloat16*>(y), slope,
+                                                        static_cast<__nv_bfloat16*>(gpre), work, P, Cs);
+  int rc = check_launch("prelu_bias_bwd_kernel");
+  if (rc) return rc;
+  prelu_bias_bwd_finalize<<<(int)cdiv(2 * Cs, 128), 128, 0, st>>>(work, dbias, slope ? dslope : nullptr, nblk, Cs);
+  return check_launch("prelu_bias_bwd_finalize");
+}
+
+extern "C" int ofsv_conv_wgrad_splits(const ofsv_conv_desc* d) {
+  int rc = wgrad_validate(d);
+  if (rc) return rc;
+  return wgrad_splits(d);
+}
+
+extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, const void* gy, int gy_cs, float* dw, float* work, void* stream) {
+  int rc = wgrad_validate(d);
+  if (rc) return rc;
+  OFSV_REQUIRE(x && gy && dw, "conv_wgrad: null pointer");
+  OFSV_REQUIRE(gy_cs >= d->Cout_w && gy_cs % 8 == 0, "conv_wgrad: gy_cs (%d) must be a multiple of 8 and >= Cout_w (%d)", gy_cs, d->Cout_w);
+  OFSV_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(dw) && (!work || aligned16(work)), "conv_wgrad: pointers must be 16-byte aligned");
+  const int splits = wgrad_splits(d);
+  OFSV_REQUIRE(splits == 1 || work, "conv_wgrad: %d K splits need a work buffer of ofsv_conv_wgrad_splits(d) * T * Cin_s * Cout_w floats", splits);
+  WgradParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.g = static_cast<const __nv_bfloat16*>(gy);
+  p.out = splits == 1 ? dw : work;
+  p.N = d->N; p.Di = d->nd == 2 ? 1 : d->Di; p.Hi = d->Hi; p.Wi = d->Wi; p.Cin_s = d->Cin_s;
+  p.Do = d->nd == 2 ? 1 : d->Do; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.Dy = d->nd == 2 ? 1 : d->Dy; p.Hy = d->Hy; p.Wy = d->Wy; p.g_cs = gy_cs; p.Cout_w = d->Cout_w;
+  p.in_stride = d->in_stride; p.out_stride = d->out_stride;
+  p.T = d->nphase * d->ntaps; p.ntaps = d->ntaps;
+  const int MT = tile_of(d->Cin_s), NT = tile_of(d->Cout_w);
+  p.mt = d->Cin_s / MT; p.nt = d->Cout_w / NT;
+  p.K = (int64_t)p.N * p.Do * p.Ho * p.Wo;
+  p.Kper = cdiv(cdiv(p.K, splits), WG_KC) * WG_KC;
+  for (int i = 0; i < p.T; ++i)
+    for (int j = 0; j < 4; ++j) p.tap[i][j] = d->tap_off[i][j];
+  if (d->nd == 2)
+    for (int i = 0; i < p.T; ++i) p.tap[i][0] = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)(p.T * p.mt * p.nt), (unsigned)splits);
+#define OFSV_WG_CASE(M, Nn) if (MT == M && NT == Nn) launch_wgrad<M, Nn>(p, grid, st); else
+  OFSV_WG_CASE(64, 64) OFSV_WG_CASE(64, 32) OFSV_WG_CASE(64, 16) OFSV_WG_CASE(32, 64) OFSV_WG_CASE(32, 32) OFSV_WG_CASE(32, 16)
+  OFSV_WG_CASE(16, 64) OFSV_WG_CASE(16, 32) OFSV_WG_CASE(16, 16) { set_error("conv_wgrad: no tile for %d x %d", MT, NT); return OFSV_ENOSUP; }
+#undef OFSV_WG_CASE
+  rc = check_launch("conv_wgrad_kernel");
+  if (rc) return rc;
+  if (splits > 1) {
+    const int64_t n4 = (int64_t)p.T * p.Cin_s * p.Cout_w / 4;
+    conv_wgrad_finalize<<<(unsigned)cdiv(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(work), reinterpret_cast<float4*>(dw), n4, splits);
+    rc = check_launch("conv_wgrad_finalize");
+  }
+  return rc;
+}

@@ -88,8 +88,6 @@ class _ModelBase:
             torch.save(self.flownet.state_dict(), "{}/{}".format(path, model_name))
             print("saved {}".format(model_name))
 
-    def update(self, *a, **k):
-        raise NotImplementedError("Model.update (training step) is the next tier of the hot path — SURVEY.md §8(f).1")
 
     def _run(self, img0, img1, scale_list, timestep, only_last):
         for t, name in ((img0, "img0"), (img1, "img1")):
@@ -104,6 +102,12 @@ class _ModelBase:
 
 class Model2D(_ModelBase):
     ND = 2
+
+    def update(self, imgs, gt, dataset="droplet2d", learning_rate=0, mul=1, training=True, flow_gt=None):
+        """Flow-2D/model/RIFE.py:80-336 on the 1-channel dataset branch (droplet2d / vimeo2d): LapLoss student + teacher,
+        0.01 * distillation, 1e-5 * photometric, backward, AdamW (opticalflowscivis_b200/train.py)."""
+        from . import train
+        return train.update(self, imgs, gt, learning_rate, mul, training, flow_gt, dataset=dataset)
 
     def inference(self, img0, img1, scale_list=[4, 2, 1], TTA=False, timestep=0.5):
         """Flow-2D/model/RIFE.py:66-78 -> (merged[3], flow_list[3], mask_list[3]); TTA returns the flip-averaged frame."""
@@ -121,6 +125,12 @@ class Model2D(_ModelBase):
 
 class Model3D(_ModelBase):
     ND = 3
+
+    def update(self, imgs, gt, learning_rate=0, mul=1, training=True, flow_gt=None):
+        """Flow-3D/model/RIFE.py:81-275: forward with the teacher block, L1 + L1(teacher) + 0.1 * distillation, backward, AdamW
+        (opticalflowscivis_b200/train.py).  Returns (merged[2], info dict with the reference's keys)."""
+        from . import train
+        return train.update(self, imgs, gt, learning_rate, mul, training, flow_gt)
 
     def inference(self, img0, img1, scale_list=[4, 2, 1], TTA=False, timestep=0.5):
         """Flow-3D/model/RIFE.py:67-79 -> (merged[2], flow_list[3], mask_list[2]); TTA is 'not implemented' upstream."""

@@ -90,6 +90,40 @@ class IFNetRef(nn.Module):
             merged.append(w0 * mask_list[i] + w1 * (1 - mask_list[i]))
         return flow_list, mask_list, merged
 
+    def forward_train(self, x, scale=(4, 2, 1)):
+        """The `gt.shape[1] == 1` branch: student + teacher block + distillation loss.  x = cat(img0, img1, gt).
+        Flow-3D/model/IFNet.py:133-280 (teacher :206-238, mask/loss :240-276); Flow-2D/model/IFNet.py:144-276 (teacher :206-230,
+        distillation :238-248).  Returns the reference's tuple (flow_list, mask_list, merged, flow_teacher, merged_teacher,
+        loss_distill) — the caller picks mask_list[2] in 3-D (IFNet.py:280)."""
+        nd = self.nd
+        warp = self.warp_fn or (warp2d_ref if nd == 2 else warp3d_ref)
+        img0, img1, gt = x[:, :1], x[:, 1:2], x[:, 2:3]
+        flow_list, mask_list, warped = [], [], []
+        w0, w1, flow, mask = img0, img1, None, None
+        for i, blk in enumerate((self.block0, self.block1, self.block2)):
+            if flow is None:
+                flow, mask = blk(torch.cat((img0, img1), 1), None, scale[i])
+            else:
+                fd, md = blk(torch.cat((img0, img1, w0, w1, mask), 1), flow, scale[i])
+                flow, mask = flow + fd, mask + md
+            mask_list.append(torch.sigmoid(mask))
+            flow_list.append(flow)
+            w0 = warp(img0, flow[:, :nd])
+            w1 = warp(img1, flow[:, nd:2 * nd])
+            warped.append((w0, w1))
+        fd, md = self.block_tea(torch.cat((img0, img1, w0, w1, mask, gt), 1), flow, 1)
+        flow_teacher = flow + fd
+        w0t = warp(img0, flow_teacher[:, :nd])
+        w1t = warp(img1, flow_teacher[:, nd:2 * nd])
+        mask_teacher = torch.sigmoid(mask + md)
+        merged_teacher = w0t * mask_teacher + w1t * (1 - mask_teacher)
+        merged, loss_distill = [], 0
+        for i in range(3):
+            merged.append(warped[i][0] * mask_list[i] + warped[i][1] * (1 - mask_list[i]))
+            loss_mask = ((merged[i] - gt).abs().mean(1, True) > (merged_teacher - gt).abs().mean(1, True) + 0.01).float().detach()
+            loss_distill = loss_distill + (((flow_teacher.detach() - flow_list[i]) ** 2).mean(1, True) ** 0.5 * loss_mask).mean()
+        return flow_list, mask_list, merged, flow_teacher, merged_teacher, loss_distill
+
 
 class ModelRef:
     """Model.inference surface.  2D returns (merged[3], flow_list[3], mask_list[3]) (Flow-2D/model/RIFE.py:75);

@@ -1,0 +1,177 @@
+"""GPU parity tests of the training tier: the backward kernels through the C ABI against fp32 torch evaluators of
+the same contracts, one IFBlock's gradients against the oracle block, and `Model.update` against oracle/train_ref.py (pinned
+against the reference's own `update` by tests/golden/make_update_golden.py).
+
+Tolerances: the kernels take bf16 operands and accumulate in fp32, so against an fp32 evaluation of the SAME bf16-rounded operands
+they agree to summation-order noise (1e-3 relative to the tensor's largest entry); against the fp32 oracle the bf16 storage of
+activations and gradients shows up: per-tensor gradient cosine >= 0.99 (>= 0.98 for the whole net in one vector is never needed —
+the measured values are printed), losses within 2e-3 relative."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_train_host import _cl, _pad_c, prelu_bias_bwd_eval, wgrad_eval
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("cs,rows", [(16, 1000), (32, 4096), (48, 777), (64, 20000), (96, 333), (128, 5000)])
+def test_prelu_bias_bwd_kernel(cs, rows):
+    from opticalflowscivis_b200 import train
+    torch.manual_seed(cs)
+    dev = _dev()
+    gy = torch.randn(rows, cs, device=dev).bfloat16()
+    y = torch.randn(rows, cs, device=dev).bfloat16()
+    slope = torch.rand(cs, device=dev) * 0.4 + 0.05
+    gp, db, ds = train.prelu_bias_bwd(gy, y, slope)
+    gp_r, db_r, ds_r = prelu_bias_bwd_eval(gy.cpu(), y.cpu(), slope.cpu())
+    assert torch.equal(gp.cpu(), gp_r)                                   # element-wise: identical rounding
+    assert torch.allclose(db.cpu(), db_r, atol=1e-3 * rows ** 0.5, rtol=1e-4)
+    assert torch.allclose(ds.cpu(), ds_r, atol=1e-3 * rows ** 0.5 * 10, rtol=1e-4)
+    gp2, db2, ds2 = train.prelu_bias_bwd(gy, None, None)                 # layer without activation
+    assert gp2 is gy and ds2 is None
+    assert torch.allclose(db2.cpu(), gy.float().sum(0).cpu(), atol=1e-3 * rows ** 0.5, rtol=1e-4)
+    a, b, c = train.prelu_bias_bwd(gy, y, slope)                         # deterministic
+    assert torch.equal(a, gp) and torch.equal(b, db) and torch.equal(c, ds)
+
+
+def _layers(nd):
+    """(name, forward _Layer, logical input dims) for every layer family and tile shape of the training path."""
+    from opticalflowscivis_b200 import ifnet
+    out = []
+    for c in ((64, 128) if nd == 3 else (64, 96)):
+        blk = ifnet.IFBlock(nd, 5 + 2 * nd, c=c)
+        L = blk.layers()
+        s = 16
+        out += [(f"c{c}.conv0.0", L[0], s), (f"c{c}.conv0.1", L[1], s // 2), (f"c{c}.convblock", L[2], s // 4),
+                (f"c{c}.convT", L[10], s // 4), (f"c{c}.heads", L[11], s // 2)]
+    return out
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_conv_wgrad_kernel_vs_fp32_evaluator(nd):
+    from opticalflowscivis_b200 import _C, train
+    torch.manual_seed(nd)
+    dev = _dev()
+    n = 2
+    for name, lay, s in _layers(nd):
+        in_sp = ((1,) if nd == 2 else ()) + (s,) * nd
+        d, osp = lay.desc(n, in_sp, _C.BF16, has_residual=False)
+        x = torch.randn((n,) + (((1,) + (s,) * 2) if nd == 2 else (s,) * 3) + (lay.cin_s,), device=dev).bfloat16()
+        gs = 16 if lay.out_f32 else lay.cout_s
+        gy = torch.randn((n,) + tuple(osp) + (gs,), device=dev).bfloat16()
+        dw = train.conv_wgrad(d, x, gy)
+        ref = wgrad_eval(d, x.cpu(), gy.cpu())
+        scale = ref.abs().max().item()
+        err = (dw.cpu() - ref).abs().max().item()
+        assert err <= 2e-3 * scale, (name, err, scale)
+        assert torch.equal(train.conv_wgrad(d, x, gy), dw), name          # fixed-order K split: deterministic
+
+
+@pytest.mark.parametrize("nd,c", [(3, 64), (3, 128), (2, 96)])
+def test_block_function_gradients_vs_oracle_block(nd, c):
+    from opticalflowscivis_b200 import ifnet, train
+    from oracle.ifnet_ref import IFBlockRef
+    torch.manual_seed(7)
+    dev = _dev()
+    cin = 5 + 2 * nd
+    ref = IFBlockRef(nd, cin, c).to(dev)
+    blk = ifnet.IFBlock(nd, cin, c=c).to(dev)
+    blk.load_state_dict(ref.state_dict())
+    s = 32 if nd == 3 else 64
+    x = torch.randn((2, cin) + (s,) * nd, device=dev)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    head = train._BlockFn.apply(xa, train._TrainBlock(blk), *blk.parameters())
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        hr = ref.conv0(xb)
+        for i in range(4):
+            hr = getattr(ref, f"convblock{i}")(hr) + hr
+        head_ref = torch.cat((ref.conv1(hr), ref.conv2(hr)), 1)
+        g = torch.randn_like(head_ref)
+        head_ref.backward(g)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    head.backward(g)
+    assert _cos(head, head_ref) >= 0.9995
+    assert _cos(xa.grad, xb.grad) >= 0.995, _cos(xa.grad, xb.grad)
+    worst = min((_cos(p.grad, q.grad), k) for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()))
+    print("block gradient cosine, worst tensor:", worst)
+    assert worst[0] >= 0.99, worst
+    for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        r = float(p.grad.double().norm() / (q.grad.double().norm() + 1e-300))
+        assert 0.97 <= r <= 1.03, (k, r)
+
+
+@pytest.mark.parametrize("nd,n,size", [(3, 2, 64), (2, 4, 128)])
+def test_model_update_vs_oracle(nd, n, size):
+    """Three `Model.update` steps against the oracle's (fp32 eager on the same GPU, TF32 off): losses, first-step gradients,
+    parameter movement.  AdamW's first steps move every weight by ~lr * sign(gradient), so the parameter-delta check is a
+    gradient-SIGN check weighted by nothing: it is stated as a cosine over all parameters."""
+    from opticalflowscivis_b200.rife import Model2D, Model3D
+    from oracle.train_ref import TrainerRef, training_triplet
+    dev = _dev()
+    torch.manual_seed(1234)
+    orc = TrainerRef(nd)
+    orc.flownet.to(dev)
+    orc.optimG = torch.optim.AdamW(orc.flownet.parameters(), lr=1e-6, weight_decay=1e-3)
+    model = (Model3D if nd == 3 else Model2D)(local_rank=-1)
+    model.flownet.load_state_dict(orc.flownet.state_dict())
+    p0 = [p.detach().clone() for p in model.flownet.parameters()]
+    img0, img1, gt = (t.to(dev) for t in training_triplet(nd, n, size))
+    imgs = torch.cat((img0, img1), 1)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for step in range(3):
+            mg_r, ir = orc.update(imgs, gt, learning_rate=1e-4, training=True)
+            if step == 0:
+                g_ref = [p.grad.detach().clone() for p in orc.flownet.parameters()]
+            mg, info = model.update(imgs, gt, learning_rate=1e-4, training=True) if nd == 3 else \
+                model.update(imgs, gt, "droplet2d", learning_rate=1e-4, training=True)
+            if step == 0:
+                g_mine = [p.grad.detach().clone() for p in model.flownet.parameters()]
+            for key in ("loss_l1", "loss_tea", "loss_G"):
+                a, b = float(info[key]), float(ir[key])
+                assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (step, key, a, b)
+            a, b = float(info["loss_distill"]), float(ir["loss_distill"])
+            assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3), (step, "loss_distill", a, b)
+            psnr = -10 * torch.log10(((mg - mg_r.detach()) ** 2).mean()).item()
+            assert psnr >= 50.0, (step, psnr)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    names = [k for k, _ in model.flownet.named_parameters()]
+    cosines = sorted((_cos(a, b), k) for a, b, k in zip(g_mine, g_ref, names))
+    allcos = _cos(torch.cat([g.flatten() for g in g_mine]), torch.cat([g.flatten() for g in g_ref]))
+    print(f"update nd={nd}: first-step gradient cosine over all parameters {allcos:.5f}; worst tensors {cosines[:4]}")
+    assert allcos >= 0.995
+    weights = [(c, k) for c, k in cosines if k.endswith("0.weight") or k.endswith("2.weight")]
+    assert min(weights)[0] >= 0.98, min(weights)
+    d_mine = torch.cat([(p.detach() - q).flatten() for p, q in zip(model.flownet.parameters(), p0)])
+    d_ref = torch.cat([(p.detach() - q).flatten() for p, q in zip(orc.flownet.parameters(), p0)])
+    dcos = _cos(d_mine, d_ref)
+    print(f"update nd={nd}: parameter-delta cosine after 3 steps {dcos:.4f}; |delta| mine {d_mine.norm():.4e} ref {d_ref.norm():.4e}")
+    assert dcos >= 0.9
+    assert abs(float(d_mine.norm() / d_ref.norm()) - 1) <= 0.05
+    # evaluation mode: no parameter change, teacher outputs aliased to the student's (RIFE.py:260-262)
+    before = [p.detach().clone() for p in model.flownet.parameters()]
+    mg, info = model.update(imgs, gt, learning_rate=1e-4, training=False) if nd == 3 else \
+        model.update(imgs, gt, "droplet2d", learning_rate=1e-4, training=False)
+    assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.flownet.parameters()))
+    assert torch.equal(info["merged_tea"], mg)
+    # and inference sees the updated weights (packed tap forms are keyed on parameter versions)
+    out = model.inference(img0, img1)
+    assert torch.isfinite(out[0] if nd == 3 else out[0][2]).all()
