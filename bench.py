@@ -185,8 +185,9 @@ def run_reference_arm(args, rank, world):
     on this box's host cores, same workload / metric / unit; every step is a bounded sample of the step (see CPU_SAMPLE)."""
     if rank != 0:
         return
-    if args.workload == "upflow_ops":
-        print(json.dumps({"impl": "reference", "unavailable": "upflow_ops is an operator-level workload without a CPU arm"}), flush=True)
+    if args.workload in ("upflow_ops", "train3d"):
+        print(json.dumps({"impl": "reference", "unavailable": f"{args.workload} is a training-tier workload without a CPU arm "
+                          "(train3d reports the reference's eager-CUDA update as `cuda_eager_reference`)"}), flush=True)
         return
     nd, sp, pairs, desc = WORKLOADS[args.workload]
     s_pairs, sample = CPU_SAMPLE[args.workload]
@@ -570,13 +571,112 @@ def run_upflow_ops(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ training-step workload
+def run_train3d(args, rank, world, local_rank):
+    """one step = `Model.update` of the 3-D model (Flow-3D/model/RIFE.py:81-275: forward with the teacher block,
+    L1 + L1(teacher) + 0.1 distillation, backward, gradient all-reduce, AdamW) on `pairs` synthetic 64^3 (img0, img1, gt)
+    triplets per GPU — the volume size the reference trains on (Flow-3D/train.py:513-546 model names, `--batch_size` 15-30)."""
+    import torch
+    import torch.distributed as dist
+
+    from opticalflowscivis_b200 import ops
+    from opticalflowscivis_b200.rife import Model3D
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n, size = args.pairs or 8, 64
+    torch.manual_seed(1234)
+    model = Model3D(local_rank=local_rank if world > 1 else -1)
+    g = torch.Generator().manual_seed(1234 + rank)
+    base = torch.nn.functional.avg_pool3d(torch.rand((n, 1, size + 8, size + 8, size + 8), generator=g), 5, 1, 2)
+    img0 = base[:, :, 4:-4, 4:-4, 2:-6].contiguous().to(dev)
+    gt = base[:, :, 4:-4, 4:-4, 4:-4].contiguous().to(dev)
+    img1 = base[:, :, 4:-4, 4:-4, 6:-2].contiguous().to(dev)
+    imgs = torch.cat((img0, img1), 1)
+    losses = []
+    LR = 3e-6          # the reference warms up linearly from 0 to 3e-4 over 2000 steps (Flow-3D/train.py:50-54): step 20 of that ramp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k=1):
+        for _ in range(k):
+            _, info = model.update(imgs, gt, learning_rate=LR, training=True)
+            losses.append(info["loss_G"])
+
+    step(args.warmup)
+    tr = model._trainer
+    n0 = ops.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = _timed(step, args.steps, barrier)
+        launches = ops.launch_count() - n0
+        clk.keep_loaded(lambda: (step(3), torch.cuda.synchronize()))
+    tr.allreduce_events = []
+    ops.TIMER = timer = ops.LaunchTimer()                 # second, event-instrumented pass: time per kernel class
+    ms_prof = _timed(step, args.steps, barrier)
+    ops.TIMER = None
+    classes = {k: {"launches": c // args.steps, "ms_per_step": t / args.steps} for k, (c, t) in timer.totals().items()}
+    ar = sum(a.elapsed_time(b) for a, b in tr.allreduce_events) / max(1, len(tr.allreduce_events))
+    tr.allreduce_events = None
+    lossv = [float(v) for v in losses]
+    if world > 1:
+        t = torch.tensor([ms, ar], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ar = float(t[0]), float(t[1])
+    # context: the reference's own update in eager PyTorch on this GPU (oracle/train_ref.py is the pinned restatement), rank 0 only
+    eager = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle.train_ref import TrainerRef
+            torch.manual_seed(1234)
+            orc = TrainerRef(3)
+            orc.flownet.to(dev)
+            orc.optimG = torch.optim.AdamW(orc.flownet.parameters(), lr=1e-6, weight_decay=1e-3)
+            eager = {"loss_G": []}
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+                try:
+                    for _ in range(2):
+                        eager["loss_G"].append(float(orc.update(imgs, gt, learning_rate=LR, training=True)[1]["loss_G"]))
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        orc.update(imgs, gt, learning_rate=LR, training=True)
+                    torch.cuda.synchronize()
+                    eager[name + "_triplets_per_s"] = 3 * n / (time.perf_counter() - t0)
+                finally:
+                    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        except Exception as e:  # noqa: BLE001
+            eager = {"unavailable": str(e)[:200]}
+    if rank != 0:
+        return
+    nparam = sum(p.numel() for p in model.flownet.parameters())
+    macs = ifnet_macs(3, (size,) * 3)
+    line = {
+        "metric": "Flow-3D Model.update training throughput (64^3 triplets/sec)", "value": world * n * args.steps / (ms / 1e3),
+        "unit": "triplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "e2e": None,
+        "allreduce_ms_per_step": ar, "allreduce_bytes": nparam * 4, "gpu_launches": int(launches),
+        "loss_G_first_steps": lossv[:4], "loss_G_last": lossv[-1], "cuda_eager_reference": eager,
+        "kernel_classes": classes, "ms_per_step_instrumented": ms_prof / args.steps, "clocks": clk.summary(),
+        "config": {"workload": "train3d", "describes": run_train3d.__doc__.split("\n\n")[0].replace("\n    ", " "),
+                   "spatial": [size] * 3, "triplets_per_gpu_per_step": n, "student_inference_macs_per_triplet": macs,
+                   "note": "conv stacks forward/backward, warp forward/backward and AdamW run in libofsv; interpolate/cat/sigmoid/"
+                           "blend/loss glue is torch autograd"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops"])
+    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops", "train3d"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
@@ -613,7 +713,7 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     try:
-        (run_upflow_ops if args.workload == "upflow_ops" else run_ours)(args, rank, world, local_rank)
+        {"upflow_ops": run_upflow_ops, "train3d": run_train3d}.get(args.workload, run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

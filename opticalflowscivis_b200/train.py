@@ -109,7 +109,8 @@ def prelu_bias_bwd(gy, y, slope):
         dbias = torch.empty(cs, device=gy.device, dtype=torch.float32)
         dslope = torch.empty(cs, device=gy.device, dtype=torch.float32) if slope is not None else None
         gpre = torch.empty_like(gy) if slope is not None else gy
-        _C.check(L.ofsv_prelu_bias_bwd_bf16(_p(gy), _p(y), _p(slope), _p(gpre), _p(dbias), _p(dslope), _p(work), rows, cs, _stream()))
+        with ops._span("prelu_bias_bwd"):
+            _C.check(L.ofsv_prelu_bias_bwd_bf16(    _p(gy), _p(y), _p(slope), _p(gpre), _p(dbias), _p(dslope), _p(work), rows, cs, _stream()))
     return gpre, dbias, dslope
 
 
@@ -127,7 +128,8 @@ def conv_wgrad(desc, x, gy):
             _C.check(splits)
         dw = torch.empty(T, desc.Cin_s, desc.Cout_w, device=x.device, dtype=torch.float32)
         work = torch.empty(splits * n, device=x.device, dtype=torch.float32) if splits > 1 else None
-        _C.check(L.ofsv_conv_wgrad_bf16(ctypes.byref(desc), _p(x), _p(gy), gy.shape[-1], _p(dw), _p(work), _stream()))
+        with ops._span("conv_wgrad"):
+            _C.check(L.ofsv_conv_wgrad_bf16(ctypes.byref(desc), _p(x), _p(gy), gy.shape[-1], _p(dw), _p(work), _stream()))
     return dw
 
 
@@ -163,40 +165,126 @@ _PAIRS_A, _PAIRS_B = (2, 4, 6, 8), (3, 5, 7, 9)
 
 
 class _TrainBlock:
-    """Training view of an IFBlock: the forward tap-form layers of `IFBlock.layers()` (unfused: no residual in the epilogue, phase-
-    form heads) plus, per layer, the tap-form layer that computes its input gradient.  Rebuilt when a parameter changes."""
+    """Training view of an IFBlock: its 12 engine layers in unfused tap form (no residual in the epilogue, phase-form heads) and, per
+    layer, the tap-form layer that computes its input gradient.
+
+    The layers are BUILT once (`_build`: the per-tap Python loops of ifnet._pack_* / _conv_layer / _convT_phase_layer, ~100 small
+    torch launches per layer) and REFRESHED whenever a parameter changes — every training step — by `_Source` records: one
+    index_select over the flattened kernel axis plus one strided copy per parameter tensor, then the library re-packs the bf16
+    operand blocks (one launch per layer).  tests/test_train_host.py checks refresh == rebuild exactly."""
+
+    class _Source:
+        """w_simt[:, ci0:ci0+a, co0:co0+b] = W[kidx] with W = param viewed [K][a][b] (perm = the permute of (A, B, K) that gets there);
+        kidx < 0 marks a tap the kernel does not have (zero matrix)."""
+
+        def __init__(self, param, perm, kidx, ci0=0, co0=0):
+            self.param, self.perm, self.ci0, self.co0 = param, perm, ci0, co0
+            k = torch.tensor(kidx, device=param.device)
+            self.valid = None if bool((k >= 0).all()) else (k >= 0).float().view(-1, 1, 1)
+            self.kidx = k.clamp(min=0)
+
+        def apply(self, w_simt):
+            p = self.param.detach()
+            wk = p.reshape(p.shape[0], p.shape[1], -1).permute(*self.perm).index_select(0, self.kidx)
+            if self.valid is not None:
+                wk = wk * self.valid
+            w_simt[:, self.ci0:self.ci0 + wk.shape[1], self.co0:self.co0 + wk.shape[2]] = wk
 
     def __init__(self, blk: IFBlock):
         self.blk = blk
         self.key = None
         self.names = [k for k, _ in blk.named_parameters()]
+        self.fwd = None
 
-    def refresh(self):
+    def _build(self):
+        """Structure + initial weights through the reference (slow) packing functions; returns (fwd, dgrad) layer lists."""
+        from .ifnet import _pack_conv, _pack_convT
         blk = self.blk
-        key = blk._key()
-        if key == self.key:
-            return
-        nd, c = blk.nd, blk.c
-        self.fwd = blk.layers()
+        nd, c, nf = blk.nd, blk.c, 2 * blk.nd
         k0 = blk.conv0[0][0].k
-        dg = []
-        w = blk.conv0[0][0].weight.detach().float()
-        dg.append(_convT_phase_layer(nd, w, k0, 16))                                     # conv0.0: c/2 -> block input (16 stored)
-        w = blk.conv0[1][0].weight.detach().float()
-        dg.append(_convT_phase_layer(nd, w, k0, _rup(c // 2, 16)))                       # conv0.1: c -> c/2
+        fwd = [_pack_conv(blk.conv0[0][0], blk.conv0[0][1]), _pack_conv(blk.conv0[1][0], blk.conv0[1][1])]
+        for i in range(4):
+            cb = getattr(blk, f"convblock{i}")
+            fwd += [_pack_conv(cb[0][0], cb[0][1]), _pack_conv(cb[1][0], cb[1][1])]
+        wm = torch.cat([blk.conv1[0].weight, blk.conv2[0].weight], 1).detach().float()   # merged ConvT [c][c][4..]
+        fwd.append(_pack_convT(nd, wm, torch.cat([blk.conv1[0].bias, blk.conv2[0].bias]).detach().float(),
+                               torch.cat([blk.conv1[1].weight, blk.conv2[1].weight]).detach().float(), c, False))
+        wh = torch.zeros((c, nf + 1) + (4,) * nd, device=wm.device)                      # block-diagonal heads
+        wh[: c // 2, :nf] = blk.conv1[2].weight.detach().float()
+        wh[c // 2:, nf:] = blk.conv2[2].weight.detach().float()
+        fwd.append(_pack_convT(nd, wh, torch.cat([blk.conv1[2].bias, blk.conv2[2].bias]).detach().float(), None, 8, True))
+        dg = [_convT_phase_layer(nd, blk.conv0[0][0].weight.detach().float(), k0, 16),   # conv0.0: c/2 -> block input (16 stored)
+              _convT_phase_layer(nd, blk.conv0[1][0].weight.detach().float(), k0, _rup(c // 2, 16))]   # conv0.1: c -> c/2
         for i in range(4):
             cb = getattr(blk, f"convblock{i}")
             for j in range(2):
                 dg.append(_conv_layer(nd, cb[j][0].weight.detach().float(), 3, 1, 1, _rup(c, 16), mirror=True))
-        wm = torch.cat([blk.conv1[0].weight, blk.conv2[0].weight], 1).detach().float()   # merged ConvT [c][c][4..]
         dg.append(_conv_layer(nd, wm, 4, 2, 1, _rup(c, 16)))                             # as Conv weight [Cout = c in][Cin = c merged out]
-        nf = 2 * nd
-        wh = torch.zeros((c, 16) + (4,) * nd, device=wm.device)                          # block-diagonal heads, 16 stored gradient channels
-        wh[: c // 2, :nf] = blk.conv1[2].weight.detach().float()
-        wh[c // 2:, nf:nf + 1] = blk.conv2[2].weight.detach().float()
-        dg.append(_conv_layer(nd, wh, 4, 2, 1, _rup(c, 16)))
-        self.dgrad = dg
-        self.kinv = torch.tensor(_convT_kflat(nd), device=wm.device).argsort()
+        wh16 = torch.zeros((c, 16) + (4,) * nd, device=wm.device)                        # 16 stored gradient channels
+        wh16[:, :nf + 1] = wh
+        dg.append(_conv_layer(nd, wh16, 4, 2, 1, _rup(c, 16)))
+        return fwd, dg
+
+    def _sources(self):
+        """Per layer: ([weight sources], [(bias param, offset)], [(prelu param, offset)]) for fwd, [weight sources] for dgrad."""
+        blk = self.blk
+        nd, c, nf, h = blk.nd, blk.c, 2 * blk.nd, blk.c // 2
+        S = _TrainBlock._Source
+        k0 = blk.conv0[0][0].k
+        ident = lambda k: list(range(k ** nd))                                           # noqa: E731
+        ct = _convT_kflat(nd)
+        # Conv(k0, 2, 1) input gradient: phase-form taps of ConvTranspose(k0, 2, 1), None -> -1
+        ctk = []
+        for par in itertools.product((0, 1), repeat=nd):
+            for choice in itertools.product((0, 1), repeat=nd):
+                ks = [_CT_TAPS[k0][par[a]][choice[a]][0] for a in range(nd)]
+                f = -1
+                if all(v is not None for v in ks):
+                    f = 0
+                    for v in ks:
+                        f = f * k0 + v
+                ctk.append(f)
+        AB, BA = (2, 0, 1), (2, 1, 0)                                                    # param (A,B,K) -> [K][A][B] / [K][B][A]
+        fw, dg = [], []
+        for li in (0, 1):
+            m, pr = blk.conv0[li][0], blk.conv0[li][1]
+            fw.append(([S(m.weight, BA, ident(k0))], [(m.bias, 0)], [(pr.weight, 0)]))
+            dg.append([S(m.weight, AB, ctk)])
+        for i in range(4):
+            cb = getattr(blk, f"convblock{i}")
+            for j in range(2):
+                fw.append(([S(cb[j][0].weight, BA, ident(3))], [(cb[j][0].bias, 0)], [(cb[j][1].weight, 0)]))
+                dg.append([S(cb[j][0].weight, AB, ident(3))])
+        fw.append(([S(blk.conv1[0].weight, AB, ct), S(blk.conv2[0].weight, AB, ct, co0=h)],
+                   [(blk.conv1[0].bias, 0), (blk.conv2[0].bias, h)], [(blk.conv1[1].weight, 0), (blk.conv2[1].weight, h)]))
+        dg.append([S(blk.conv1[0].weight, BA, ident(4)), S(blk.conv2[0].weight, BA, ident(4), ci0=h)])
+        fw.append(([S(blk.conv1[2].weight, AB, ct), S(blk.conv2[2].weight, AB, ct, ci0=h, co0=nf)],
+                   [(blk.conv1[2].bias, 0), (blk.conv2[2].bias, nf)], []))
+        dg.append([S(blk.conv1[2].weight, BA, ident(4)), S(blk.conv2[2].weight, BA, ident(4), ci0=nf, co0=h)])
+        return fw, dg
+
+    def refresh(self):
+        key = self.blk._key()
+        if key == self.key:
+            return
+        with torch.no_grad():
+            if self.fwd is None:
+                self.fwd, self.dgrad = self._build()
+                self.src_fwd, self.src_dgrad = self._sources()
+                self.kinv = torch.tensor(_convT_kflat(self.blk.nd), device=self.fwd[0].w_simt.device).argsort()
+            else:
+                for lay, (ws, bs, ps) in zip(self.fwd, self.src_fwd):
+                    for sct in ws:
+                        sct.apply(lay.w_simt)
+                    for b, off in bs:
+                        lay.bias[off:off + b.numel()] = b.detach()
+                    for pw, off in ps:
+                        lay.prelu[off:off + pw.numel()] = pw.detach()
+                    lay._packed.clear()
+                for lay, ws in zip(self.dgrad, self.src_dgrad):
+                    for sct in ws:
+                        sct.apply(lay.w_simt)
+                    lay._packed.clear()
         self.key = key
 
     # -- tap-form weight gradients back to the reference's parameter tensors
@@ -436,6 +524,7 @@ class Trainer:
         self.bucket = GradientBucket(self.params)
         self.optimG = FusedAdamW(self.params, lr=1e-6, weight_decay=1e-3, bucket=self.bucket)   # RIFE.py:29 / :26
         self.distributed = local_rank != -1
+        self.allreduce_events = None      # bench.py: a list collects (start, stop) CUDA events around the gradient all-reduce
         self._slopes = [p for k, p in net.named_parameters() if p.dim() == 1 and k.endswith(".1.weight")]
 
     def check_slopes(self):
@@ -450,7 +539,14 @@ class Trainer:
         from .optim import allreduce_gradients
         self.bucket.zero()                                   # optimG.zero_grad()
         loss_G.backward()
+        ev = self.allreduce_events
+        if ev is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         scale = allreduce_gradients(self.bucket) if self.distributed else 1.0
+        if ev is not None:
+            b.record()
+            ev.append((a, b))
         self.optimG.step(grad_scale=scale)
         with torch.no_grad():
             self._min_slope = torch.cat([p.view(-1) for p in self._slopes]).min()
@@ -467,8 +563,10 @@ def update(model, imgs, gt, learning_rate=0, mul=1, training=True, flow_gt=None,
         raise NotImplementedError("2-D update: only the 1-channel dataset branch (droplet2d / vimeo2d) is provided; the "
                                   "data+flow-channel datasets of RIFE.py:86-103 are outside the hot path")
     for t, name in ((imgs, "imgs"), (gt, "gt")):
-        if not t.is_cuda:
+        if not torch.is_tensor(t) or not t.is_cuda:
             raise TypeError(f"{name}: expected a CUDA tensor (no CPU path)")
+    if net.precision != "bf16":
+        raise NotImplementedError("the training step runs on the bf16 tensor-core engine only (Model(precision='bf16'))")
     tr = getattr(model, "_trainer", None)
     if tr is None:
         tr = model._trainer = Trainer(net, model.local_rank)

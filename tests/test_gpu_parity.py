@@ -696,8 +696,13 @@ def test_model_surface():
         m2.inference(torch.rand((1, 1, 30, 48), device=_dev()), torch.rand((1, 1, 30, 48), device=_dev()))
     with pytest.raises(TypeError):
         m2.inference(torch.rand(1, 1, 32, 48), torch.rand(1, 1, 32, 48))
-    with pytest.raises(NotImplementedError):
-        m2.update(None, None, None)
+    t = torch.rand((1, 1, 32, 48), device=_dev())
+    with pytest.raises(NotImplementedError):       # the training step runs on the bf16 engine only (tests/test_gpu_train.py)
+        m2.update(torch.cat((t, t), 1), t, "droplet2d", learning_rate=1e-6)
+    with pytest.raises(NotImplementedError):       # the data+flow-channel datasets of Flow-2D/model/RIFE.py:86-103
+        m2.update(torch.cat((t, t), 1), t, "cylinder2d", learning_rate=1e-6)
+    with pytest.raises(TypeError):                 # no CPU path
+        m2.update(torch.cat((t, t), 1).cpu(), t.cpu(), "droplet2d")
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         m3.save_model("flownet.pkl", td)

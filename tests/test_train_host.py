@@ -237,3 +237,24 @@ def test_oracle_update_replays_reference_golden(nd, n, size):
     sd = tr.flownet.state_dict()
     dn = np.array([(sd[k] - p0[k]).double().norm().item() for k in names])
     assert np.allclose(dn, gold[f"nd{nd}_deltanorm"], rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.parametrize("nd,c", [(3, 64), (2, 96)])
+def test_train_block_refresh_equals_rebuild(nd, c):
+    """The per-step weight refresh (index_select + strided copy per parameter) gives exactly the tap-form tensors of a fresh build."""
+    torch.manual_seed(5)
+    blk = ifnet.IFBlock(nd, 6 + 2 * nd, c=c)
+    tb = train._TrainBlock(blk)
+    tb.refresh()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    tb.refresh()
+    fresh = train._TrainBlock(blk)
+    fresh.refresh()
+    for kind in ("fwd", "dgrad"):
+        for li, (a, b) in enumerate(zip(getattr(tb, kind), getattr(fresh, kind))):
+            assert torch.equal(a.w_simt, b.w_simt), (kind, li)
+            assert torch.equal(a.bias, b.bias), (kind, li)
+            assert (a.prelu is None) == (b.prelu is None) and (a.prelu is None or torch.equal(a.prelu, b.prelu)), (kind, li)
+            assert a.taps == b.taps and not a._packed
