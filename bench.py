@@ -587,6 +587,7 @@ def run_train3d(args, rank, world, local_rank):
     n, size = args.pairs or 8, 64
     torch.manual_seed(1234)
     model = Model3D(local_rank=local_rank if world > 1 else -1)
+    model.enable_training_graph(not args.no_train_graph)
     g = torch.Generator().manual_seed(1234 + rank)
     base = torch.nn.functional.avg_pool3d(torch.rand((n, 1, size + 8, size + 8, size + 8), generator=g), 5, 1, 2)
     img0 = base[:, :, 4:-4, 4:-4, 2:-6].contiguous().to(dev)
@@ -614,7 +615,13 @@ def run_train3d(args, rank, world, local_rank):
         launches = ops.launch_count() - n0
         clk.keep_loaded(lambda: (step(3), torch.cuda.synchronize()))
     tr.allreduce_events = []
-    ops.TIMER = timer = ops.LaunchTimer()                 # second, event-instrumented pass: time per kernel class
+    # second pass, eager and event-instrumented: time per kernel class (and the eager step time next to the graphed one)
+    model.enable_training_graph(False)
+    step(2)
+    n0 = ops.launch_count()
+    ms_eager = _timed(step, args.steps, barrier)
+    launches = ops.launch_count() - n0                    # the graph replays exactly these launches (counted where Python issues them)
+    ops.TIMER = timer = ops.LaunchTimer()
     ms_prof = _timed(step, args.steps, barrier)
     ops.TIMER = None
     classes = {k: {"launches": c // args.steps, "ms_per_step": t / args.steps} for k, (c, t) in timer.totals().items()}
@@ -661,7 +668,7 @@ def run_train3d(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "e2e": None,
         "allreduce_ms_per_step": ar, "allreduce_bytes": nparam * 4, "gpu_launches": int(launches),
         "loss_G_first_steps": lossv[:4], "loss_G_last": lossv[-1], "cuda_eager_reference": eager,
-        "kernel_classes": classes, "ms_per_step_instrumented": ms_prof / args.steps, "clocks": clk.summary(),
+        "kernel_classes": classes, "ms_per_step_eager": ms_eager / args.steps, "train_graph": not args.no_train_graph, "clocks": clk.summary(),
         "config": {"workload": "train3d", "describes": run_train3d.__doc__.split("\n\n")[0].replace("\n    ", " "),
                    "spatial": [size] * 3, "triplets_per_gpu_per_step": n, "student_inference_macs_per_triplet": macs,
                    "note": "conv stacks forward/backward, warp forward/backward and AdamW run in libofsv; interpolate/cat/sigmoid/"
@@ -681,6 +688,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-graph", action="store_true", help="train3d: enqueue every launch of the step from Python instead of replaying forward + backward from a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

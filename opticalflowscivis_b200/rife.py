@@ -33,6 +33,12 @@ class _ModelBase:
         self._graphs = {} if on else None
         return self
 
+    def enable_training_graph(self, on=True):
+        """Replay forward + backward of `update` from a CUDA graph captured per input shape (train.Trainer.forward_backward_graphed).
+        Same numerics; the returned `merged` / info tensors are then the graph's buffers, overwritten by the next `update`."""
+        self._train_graph = bool(on)
+        return self
+
     def _param_signature(self):
         return tuple(p._version for p in self.flownet.parameters()) + tuple(p.data_ptr() for p in self.flownet.parameters())
 

@@ -526,6 +526,7 @@ class Trainer:
         self.distributed = local_rank != -1
         self.allreduce_events = None      # bench.py: a list collects (start, stop) CUDA events around the gradient all-reduce
         self._slopes = [p for k, p in net.named_parameters() if p.dim() == 1 and k.endswith(".1.weight")]
+        self.graphs = None                # {(shapes): (CUDAGraph, static imgs, static gt, static outputs)} when graph mode is on
 
     def check_slopes(self):
         """ofsv_prelu_bias_bwd_bf16 recovers the pre-activation sign from the layer output, which needs PReLU slopes > 0 (the
@@ -535,10 +536,46 @@ class Trainer:
         if m is not None and not (m.item() > 0):
             raise RuntimeError("a PReLU slope became <= 0: the fused bias/PReLU backward of the bf16 training path needs positive slopes")
 
-    def step(self, loss_G):
-        from .optim import allreduce_gradients
+    def forward_backward(self, imgs, gt, device_guard=False):
+        """zero_grad + forward + losses + backward (everything of the step before the gradient exchange)."""
         self.bucket.zero()                                   # optimG.zero_grad()
-        loss_G.backward()
+        with torch.enable_grad():
+            loss_G, info, merged2 = forward_losses(self.net, imgs, gt, device_guard)
+            loss_G.backward()
+        return merged2.detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in info.items() if k != "_flow2"}
+
+    def forward_backward_graphed(self, imgs, gt):
+        """The same work replayed from a CUDA graph captured per input shape: a step is ~400 libofsv launches plus ~300 small torch
+        launches, and at the reference's training sizes (64^3, 128^2 ...) the GPU finishes them faster than Python can enqueue
+        them.  The graph contains the per-step weight refresh, so it stays valid while the optimizer updates the parameters in
+        place; inputs are copied into the graph's buffers and the returned tensors are the graph's outputs, overwritten by the next
+        step (the small loss scalars are cloned).  The gradient all-reduce and the optimizer stay outside the graph: the learning
+        rate changes every step (RIFE.py:86-87)."""
+        key = (tuple(imgs.shape), tuple(gt.shape), imgs.device.index)
+        ent = self.graphs.get(key)
+        if ent is None:
+            s_imgs, s_gt = imgs.detach().clone().contiguous(), gt.detach().clone().contiguous()
+            cur = torch.cuda.current_stream(imgs.device)
+            side = torch.cuda.Stream(device=imgs.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                     # warm-up off the capture: workspaces, kernel attributes, engine choice
+                for _ in range(2):
+                    self.forward_backward(s_imgs, s_gt, device_guard=True)
+            cur.wait_stream(side)
+            for tb in self.net._train_blocks:                 # the capture must contain the weight refresh
+                tb.key = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.forward_backward(s_imgs, s_gt, device_guard=True)
+            ent = self.graphs[key] = (g, s_imgs, s_gt, out)
+        g, s_imgs, s_gt, (merged2, info) = ent
+        s_imgs.copy_(imgs)
+        s_gt.copy_(gt)
+        g.replay()
+        return merged2, {k: (v.clone() if torch.is_tensor(v) and v.dim() == 0 else v) for k, v in info.items()}
+
+    def exchange_and_step(self):
+        from .optim import allreduce_gradients
         ev = self.allreduce_events
         if ev is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -552,11 +589,43 @@ class Trainer:
             self._min_slope = torch.cat([p.view(-1) for p in self._slopes]).min()
 
 
+def forward_losses(net, imgs, gt, device_guard=False):
+    """Forward with the teacher block and the losses of `update`.  device_guard: replace the 2-D path's host-side
+    `isnan(loss_distill) or loss_distill > 10` test (RIFE.py:295) by the same selection on the device (needed under CUDA-graph
+    capture; when it triggers, the reference drops the term from the graph while this form multiplies its gradient by zero)."""
+    nd = net.nd
+    img0, img1 = imgs[:, :1], imgs[:, 1:2]
+    flow, mask, merged, flow_teacher, merged_teacher, loss_distill = ifnet_forward_train(net, torch.cat((imgs, gt), 1), (4, 2, 1))
+    if nd == 3:
+        loss_l1 = F.l1_loss(merged[2], gt)
+        loss_tea = F.l1_loss(merged_teacher, gt)
+        loss_G = loss_l1 * 1 + loss_tea * 1 + loss_distill * 0.1
+        info = {"loss_l1": loss_l1, "loss_tea": loss_tea, "loss_distill": loss_distill, "loss_G": loss_G}
+    else:
+        mask = mask[2]
+        loss_l1 = lap_loss(merged[2], gt).mean()
+        loss_tea = lap_loss(merged_teacher, gt).mean()
+        with torch.no_grad():
+            l1_reg = sum(torch.norm(p, 1) for k, p in net.state_dict().items() if "block2" in k or "block_tea" in k)
+        loss_photo = (_photometric_term(flow[2][:, 2:4], merged[2], img0) + _photometric_term(flow[2][:, :2], merged[2], img1)) / 2
+        if device_guard:
+            loss_distill = torch.where(torch.isnan(loss_distill) | (loss_distill > 10.), torch.zeros_like(loss_distill), loss_distill)
+        elif math.isnan(loss_distill) or loss_distill > 10.:              # host read, as in the reference (RIFE.py:295)
+            loss_distill = torch.zeros((), device=imgs.device)
+        loss_G = loss_l1 * 1 + loss_tea * 1 + loss_distill * 0.01 + l1_reg * 1e-6 + loss_photo * 1e-5
+        info = {"loss_l1": loss_l1 * 1, "loss_tea": loss_tea * 1, "loss_distill": loss_distill * 0.01, "l1_reg": l1_reg * 1e-6,
+                "loss_photo": loss_photo * 1e-5, "loss_flow": torch.zeros(()) * 0, "loss_G": loss_G}
+    info.update({"merged_tea": merged_teacher, "mask": mask, "mask_tea": mask, "flow": flow[2] if nd == 3 else flow[2][:, :2],
+                 "flow_tea": flow_teacher, "_flow2": flow[2]})
+    return loss_G, info, merged[2]
+
+
 def update(model, imgs, gt, learning_rate=0, mul=1, training=True, flow_gt=None, dataset=None):
     """`Model.update` of both packages.  3-D (Flow-3D/model/RIFE.py:81-275): loss_G = L1(merged[2], gt) + L1(merged_teacher, gt)
     + 0.1 * loss_distill.  2-D (Flow-2D/model/RIFE.py:80-336), 1-channel datasets (`droplet2d`, `vimeo2d`): LapLoss student and
     teacher, 0.01 * distillation (zeroed when NaN or > 10), 1e-6 * |w|_1 of block2 / block_tea (a constant for autograd: the
-    reference reads it through state_dict()), 1e-5 * photometric loss.  Returns (merged[2], info dict with the reference's keys)."""
+    reference reads it through state_dict()), 1e-5 * photometric loss.  Returns (merged[2], info dict with the reference's keys).
+    `model.enable_training_graph()` replays forward + backward from a CUDA graph (see Trainer.forward_backward_graphed)."""
     net = model.flownet
     nd = net.nd
     if nd == 2 and dataset not in (None, "droplet2d", "vimeo2d"):
@@ -573,31 +642,15 @@ def update(model, imgs, gt, learning_rate=0, mul=1, training=True, flow_gt=None,
     for g in tr.optimG.param_groups:
         g["lr"] = learning_rate
     tr.check_slopes()
-    img0, img1 = imgs[:, :1], imgs[:, 1:2]
     model.train() if training else model.eval()
-    with torch.enable_grad() if training else torch.no_grad():
-        flow, mask, merged, flow_teacher, merged_teacher, loss_distill = ifnet_forward_train(net, torch.cat((imgs, gt), 1), (4, 2, 1))
-        if nd == 3:
-            loss_l1 = F.l1_loss(merged[2], gt)
-            loss_tea = F.l1_loss(merged_teacher, gt)
-            loss_G = loss_l1 * 1 + loss_tea * 1 + loss_distill * 0.1
-            info = {"loss_l1": loss_l1, "loss_tea": loss_tea, "loss_distill": loss_distill, "loss_G": loss_G}
-        else:
-            mask = mask[2]
-            loss_l1 = lap_loss(merged[2], gt).mean()
-            loss_tea = lap_loss(merged_teacher, gt).mean()
-            with torch.no_grad():
-                l1_reg = sum(torch.norm(p, 1) for k, p in net.state_dict().items() if "block2" in k or "block_tea" in k)
-            loss_photo = (_photometric_term(flow[2][:, 2:4], merged[2], img0) + _photometric_term(flow[2][:, :2], merged[2], img1)) / 2
-            if math.isnan(loss_distill) or loss_distill > 10.:               # host read, as in the reference (RIFE.py:295)
-                loss_distill = torch.zeros((), device=imgs.device)
-            loss_G = loss_l1 * 1 + loss_tea * 1 + loss_distill * 0.01 + l1_reg * 1e-6 + loss_photo * 1e-5
-            info = {"loss_l1": loss_l1 * 1, "loss_tea": loss_tea * 1, "loss_distill": loss_distill * 0.01, "l1_reg": l1_reg * 1e-6,
-                    "loss_photo": loss_photo * 1e-5, "loss_flow": torch.zeros(()) * 0, "loss_G": loss_G}
-    if training:
-        tr.step(loss_G)
-    else:
-        flow_teacher, merged_teacher = flow[2], merged[2]
-    info.update({"merged_tea": merged_teacher, "mask": mask, "mask_tea": mask, "flow": flow[2] if nd == 3 else flow[2][:, :2],
-                 "flow_tea": flow_teacher})
-    return merged[2].detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in info.items()}
+    if not training:
+        with torch.no_grad():
+            _, info, merged2 = forward_losses(net, imgs, gt)
+        info["flow_tea"], info["merged_tea"] = info.pop("_flow2"), merged2       # RIFE.py:260-262 / :319-321
+        return merged2, info
+    want_graph = getattr(model, "_train_graph", False)
+    if want_graph and tr.graphs is None:
+        tr.graphs = {}
+    merged2, info = tr.forward_backward_graphed(imgs, gt) if want_graph else tr.forward_backward(imgs, gt)
+    tr.exchange_and_step()
+    return merged2, info

@@ -175,3 +175,32 @@ def test_model_update_vs_oracle(nd, n, size):
     # and inference sees the updated weights (packed tap forms are keyed on parameter versions)
     out = model.inference(img0, img1)
     assert torch.isfinite(out[0] if nd == 3 else out[0][2]).all()
+
+
+@pytest.mark.parametrize("nd,n,size", [(3, 1, 64), (2, 2, 64)])
+def test_model_update_graph_mode_equals_eager(nd, n, size):
+    """`enable_training_graph()` replays the same kernels: losses and parameters follow the eager run (not bit-for-bit: the warp
+    backward accumulates with red.global.add in whatever order the SMs get there)."""
+    from opticalflowscivis_b200.rife import Model2D, Model3D
+    from oracle.train_ref import training_triplet
+    dev = _dev()
+    torch.manual_seed(1234)
+    M = Model3D if nd == 3 else Model2D
+    a, b = M(local_rank=-1), M(local_rank=-1)
+    b.flownet.load_state_dict(a.flownet.state_dict())
+    b.enable_training_graph()
+    img0, img1, gt = (t.to(dev) for t in training_triplet(nd, n, size))
+    imgs = torch.cat((img0, img1), 1)
+    for step in range(4):
+        lr = 1e-4 * (step + 1)                      # the learning rate changes every step (RIFE.py:86-87) — outside the graph
+        args = (imgs, gt) if nd == 3 else (imgs, gt, "droplet2d")
+        _, ia = a.update(*args, learning_rate=lr, training=True)
+        mg, ib = b.update(*args, learning_rate=lr, training=True)
+        for key in ("loss_l1", "loss_tea", "loss_distill", "loss_G"):
+            x, y = float(ia[key]), float(ib[key])
+            assert abs(x - y) <= (5e-3 if key == "loss_distill" else 5e-4) * max(abs(x), 1e-3), (step, key, x, y)
+    da = torch.cat([p.detach().flatten() for p in a.flownet.parameters()])
+    db = torch.cat([p.detach().flatten() for p in b.flownet.parameters()])
+    assert _cos(da, db) >= 0.999999
+    assert (da - db).abs().max().item() <= 2.5e-3      # a sign flip of a ~zero gradient moves a weight by 2 * lr per step
+    assert len(b._trainer.graphs) == 1
