@@ -8,6 +8,9 @@ class IFBlock(_g.IFBlock):
         super().__init__(2, in_planes, c)
 
 
+refine = False      # Flow-2D/model/IFNet.py:32 — module-level switch of the reference (read at construction)
+
+
 class IFNet(_g.IFNet):
     def __init__(self, precision="bf16", engine="auto"):
-        super().__init__(2, precision=precision, engine=engine)
+        super().__init__(2, precision=precision, engine=engine, refine=refine)

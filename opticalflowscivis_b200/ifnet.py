@@ -376,15 +376,23 @@ class IFNet(nn.Module):
 
     WIDTHS = {2: (128, 96, 64), 3: (128, 64, 64)}
 
-    def __init__(self, nd: int, precision: str = "bf16", engine: str = "auto"):
+    def __init__(self, nd: int, precision: str = "bf16", engine: str = "auto", refine: bool = False):
         super().__init__()
         self.nd = nd
+        self.refine = bool(refine)
         c0, c1, c2 = self.WIDTHS[nd]
         nf = 2 * nd
         self.block0 = IFBlock(nd, 2, c=c0)
         self.block1 = IFBlock(nd, 5 + nf, c=c1)
         self.block2 = IFBlock(nd, 5 + nf, c=c2)
         self.block_tea = IFBlock(nd, 6 + nf, c=64)      # teacher: training only (§8f), kept for state_dict parity
+        if self.refine:                                 # Flow-2D/model/IFNet.py:140-142 (commented out in Flow-3D/model/IFNet.py:130-131)
+            if nd != 2:
+                raise NotImplementedError("refine=True exists for the 2-D IFNet only: Flow-3D/model/refine.py keeps the upstream RGB "
+                                          "channel counts (3 / 17 / 3) and its use in Flow-3D/model/IFNet.py:274-279 is commented out")
+            from .refine import Contextnet, Unet
+            self.contextnet = Contextnet(nd)
+            self.unet = Unet(nd)
         self.set_precision(precision, engine)
         self.only_last = False
         self.fuse_state_accumulate = True # scale-1 block: `flow += flow_d, mask += mask_d` inside the head conv's epilogue
@@ -472,4 +480,9 @@ class IFNet(nn.Module):
             flow_list.append(flow)
             mask_list.append(ms)
             merged.append(mg)
+        if self.refine:
+            if act != _C.BF16:
+                raise NotImplementedError("the refinement nets run on the bf16 tensor-core engine only")
+            from .refine import refine_merged
+            merged[2] = refine_merged(self, img0, img1, w0, w1, mask, flow, merged[2])
         return flow_list, (mask_list if nd == 2 else mask_list[2]), merged, None, None, 0

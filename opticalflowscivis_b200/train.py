@@ -461,10 +461,24 @@ def ifnet_forward_train(net: IFNet, x, scale=(4, 2, 1)):
 
 
 # ------------------------------------------------------------------------------------------------ 2-D losses (Flow-2D/model)
+_CONST = {}
+
+
+def _const(key, device, make):
+    """Small constant tensors are built once per device (a host-to-device copy is not allowed inside CUDA-graph capture)."""
+    k = (key, str(device))
+    t = _CONST.get(k)
+    if t is None:
+        t = _CONST[k] = make().to(device)
+    return t
+
+
 def _gauss_kernel(channels, device):
     """Flow-2D/model/laplacian.py:10-19."""
-    k = torch.tensor([1., 4., 6., 4., 1.], device=device)
-    return (torch.outer(k, k) / 256.).repeat(channels, 1, 1, 1)
+    def make():
+        k = torch.tensor([1., 4., 6., 4., 1.])
+        return (torch.outer(k, k) / 256.).repeat(channels, 1, 1, 1)
+    return _const(("gauss", channels), device, make)
 
 
 def _conv_gauss(img, kernel):
@@ -504,9 +518,11 @@ def _photometric_term(flow, merged, frame):
     """Flow-2D/model/RIFE.py:245-282: backwrd_warp (grid_sample with zeros padding / align_corners=False on a (2/w, 2/h) grid) of
     `merged` by `flow`, Charbonnier distance to `frame`, summed over pixels / 3 / batch."""
     b, _, h, w = flow.shape
-    yy, xx = torch.meshgrid(torch.arange(h, device=flow.device), torch.arange(w, device=flow.device), indexing="ij")
-    grid = flow.permute(0, 2, 3, 1) + torch.stack((xx, yy), -1).float().unsqueeze(0)
-    grid = grid * torch.tensor([2 / w, 2 / h], device=flow.device) - 1
+    def base():
+        yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        return torch.stack((xx, yy), -1).float().unsqueeze(0)
+    grid = flow.permute(0, 2, 3, 1) + _const(("photo_grid", h, w), flow.device, base)
+    grid = grid * _const(("photo_factor", h, w), flow.device, lambda: torch.tensor([2 / w, 2 / h])) - 1
     # loss glue with weight 1e-5, not on the inference path: ATen's sampler (zeros padding, align_corners=False) is used as is
     warped = F.grid_sample(merged, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
     p = _charbonnier(warped - frame)

@@ -204,3 +204,80 @@ def test_model_update_graph_mode_equals_eager(nd, n, size):
     assert _cos(da, db) >= 0.999999
     assert (da - db).abs().max().item() <= 2.5e-3      # a sign flip of a ~zero gradient moves a weight by 2 * lr per step
     assert len(b._trainer.graphs) == 1
+
+
+# ------------------------------------------------------------------------------------------------ refinement nets (§8 f.3)
+@pytest.mark.parametrize("nd,sp", [(2, (64, 96)), (2, (160, 224)), (3, (32, 32, 48))])
+def test_refine_nets_vs_oracle(nd, sp):
+    """Contextnet / Unet on the bf16 engines against the fp32 oracle (pinned bit-exact against Flow-{2D,3D}/model/refine.py)."""
+    from opticalflowscivis_b200 import refine
+    from oracle.refine_ref import ContextnetRef, UnetRef
+    dev = _dev()
+    torch.manual_seed(77)
+    oc, ou = ContextnetRef(nd).to(dev), UnetRef(nd).to(dev)
+    mc, mu = refine.Contextnet(nd).to(dev), refine.Unet(nd).to(dev)
+    mc.load_state_dict(oc.state_dict())
+    mu.load_state_dict(ou.state_dict())
+    g = torch.Generator().manual_seed(5)
+    cin = 1 if nd == 2 else 3
+    x = torch.rand((2, cin) + sp, generator=g).to(dev)
+    flow = (torch.randn((2, nd) + sp, generator=g) * 2).to(dev)
+    parts = torch.rand((2, 9 if nd == 2 else 17) + sp, generator=g).to(dev)
+    args = (parts[:, :cin], parts[:, cin:2 * cin], parts[:, 2 * cin:3 * cin], parts[:, 3 * cin:4 * cin], parts[:, 4 * cin:4 * cin + 1],
+            parts[:, 4 * cin + 1:])
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fo, fo1 = oc(x, flow), oc(x.flip(0), flow)
+            yo = ou(*args, fo, fo1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    fm, fm1 = mc(x, flow), mc(x.flip(0), flow)
+    for i, (a, b) in enumerate(zip(fm, fo)):
+        assert a.shape == b.shape
+        rel = float((a - b).norm() / (b.norm() + 1e-12))
+        assert rel <= 1.5e-2, (i, rel)                       # bf16 activations through 2 (i + 1) conv layers
+    ym = mu(*args, fm, fm1)
+    assert ym.shape == yo.shape
+    err = float((ym - yo).abs().max())
+    print(f"refine nd={nd} {sp}: Unet output max-abs {err:.2e}")
+    assert err <= 1e-2, err                                   # sigmoid output in [0,1]
+
+
+def test_ifnet2d_refine_switch_vs_oracle():
+    """`refine = True` (Flow-2D/model/IFNet.py:32,255-273): merged[2] = clamp(merged[2] + unet(...) * 2 - 1, 0, 1)."""
+    import importlib
+    mod = importlib.import_module("opticalflowscivis_b200.flow2d.model.IFNet")
+    from oracle.ifnet_ref import IFNetRef
+    from oracle.ops_ref import warp2d_ref
+    from oracle.refine_ref import ContextnetRef, UnetRef, refine_merged_ref
+    dev = _dev()
+    torch.manual_seed(1234)
+    onet, oc, ou = IFNetRef(2).to(dev), ContextnetRef(2).to(dev), UnetRef(2).to(dev)
+    mod.refine = True
+    try:
+        net = mod.IFNet().to(dev)
+    finally:
+        mod.refine = False
+    sd = dict(onet.state_dict())
+    sd.update({"contextnet." + k: v for k, v in oc.state_dict().items()})
+    sd.update({"unet." + k: v for k, v in ou.state_dict().items()})
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((2, 2, 64, 96), generator=g).to(dev)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fo, mo, mgo = onet(x, (4, 2, 1))
+            w0, w1 = warp2d_ref(x[:, :1], fo[2][:, :2]), warp2d_ref(x[:, 1:2], fo[2][:, 2:4])
+            ref = refine_merged_ref(oc, ou, x[:, :1], x[:, 1:2], w0, w1, torch.logit(mo[2]), fo[2], mgo[2])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    flow, mask, merged, *_ = net(x, (4, 2, 1))
+    err = float((merged[2] - ref).abs().max())
+    psnr = -10 * float(torch.log10(((merged[2] - ref) ** 2).mean()))
+    print(f"IFNet2D refine=True: merged[2] max-abs {err:.2e}, PSNR {psnr:.1f} dB vs the fp32 oracle")
+    assert err <= 3e-2 and psnr >= 45.0
+    assert float((merged[2] - mgo[2]).abs().max()) > 0.01      # the refinement did change the frame (0.034 with this init)

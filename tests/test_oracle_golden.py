@@ -166,3 +166,25 @@ def test_adamw_golden():
         for t, lr in enumerate(lrs, start=1):
             p, m, v = adamw_step(p, z[f"g{t}_{i}"], m, v, t, float(lr))
             assert np.abs(p - z[f"p{t}_{i}"]).max() <= 1e-6 * max(1e-30, np.abs(z[f"p{t}_{i}"]).max()), (i, t)
+
+
+@pytest.mark.parametrize("nd,sp", [(2, (32, 48)), (3, (16, 16, 32))])
+def test_refine_oracle_replays_reference_golden(nd, sp):
+    """oracle/refine_ref.py from the generator's seeds reproduces the sums recorded while it was bit-exact against the reference."""
+    from oracle.refine_ref import ContextnetRef, UnetRef
+    gold = np.load(os.path.join(G, "refine.npz"))
+    torch.manual_seed(77)
+    oc, ou = ContextnetRef(nd), UnetRef(nd)
+    g = torch.Generator().manual_seed(5)
+    cin = 1 if nd == 2 else 3
+    x = torch.rand((2, cin) + sp, generator=g)
+    flow = torch.randn((2, nd) + sp, generator=g) * 2
+    with torch.no_grad():
+        fo = oc(x, flow)
+        parts = torch.rand((2, 9 if nd == 2 else 17) + sp, generator=g)
+        args = (parts[:, :cin], parts[:, cin:2 * cin], parts[:, 2 * cin:3 * cin], parts[:, 3 * cin:4 * cin], parts[:, 4 * cin:4 * cin + 1],
+                parts[:, 4 * cin + 1:])
+        yo = ou(*args, fo, oc(x.flip(0), flow))
+    assert np.allclose([float(f.double().sum()) for f in fo], gold[f"nd{nd}_ctx_sum"], rtol=1e-5, atol=1e-3)
+    assert abs(float(yo.double().sum()) - float(gold[f"nd{nd}_unet_sum"])) <= 1e-5 * abs(float(gold[f"nd{nd}_unet_sum"]))
+    assert np.allclose(yo.flatten()[:16].numpy(), gold[f"nd{nd}_unet_head"], atol=1e-6)
