@@ -102,6 +102,20 @@ int ofsv_upsample_flow_ac_f32(const float* in, float* out, int B, int h_in, int 
 int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode,
                             void* stream);
 
+/* tools.torch_warp(x, flo) — UPFlow/utils/tools.py:1317-1361: the sampling of WarpingLayer_no_div WITHOUT the validity mask (used by
+ * the occlusion check, tools.py:592-630, and by sgu_model, upflow.py:86). */
+int ofsv_torch_warp_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode, void* stream);
+
+/* ---- f.2: producer of the cost-volume inputs of one pyramid level — UPFlow/model/upflow.py:621-640:
+ *   out_warp  = normalize(WarpingLayer_no_div(f_src, flow))      (flow NULL = level 0: no warp)
+ *   out_plain = normalize(f_plain)
+ * with network_tools.normalize_features(normalize = center = True, moments_across_channels = moments_across_images = False)
+ * (upflow.py:95-138; the configuration of scripts/simple_train.py:321-329 and test.py:116-118): per (sample, channel) plane
+ * (f - mean) / sqrt(var_unbiased + 1e-16).  All tensors (B,C,H,W) fp32, flow (B,2,H,W).  One launch; planes are staged in shared
+ * memory (H*W*4 <= 200 KB, else OFSV_ENOSUP). */
+int ofsv_feature_norm_pair_f32(const float* f_plain, const float* f_src, const float* flow, float* out_plain, float* out_warp, int B,
+                               int C, int H, int W, int ref_mode, void* stream);
+
 /* ---- backward of a10 / a11 (autograd of UPFlow's training step, BASELINE cfg 5, runs through both).
  * ofsv_upsample_flow_ac_bwd_f32: gin (B,2,h_in,w_in) = upsample_bilinear2d_backward(gout (B,2,h_out,w_out)) with the
  *   (w/w_, h/h_) factors of pwc_modules.py:83-88; gin is zero-filled by the call.

@@ -52,6 +52,8 @@ _SIGS = {
     "ofsv_corr81_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ofsv_upsample_flow_ac_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warping_no_div_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ofsv_torch_warp_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ofsv_feature_norm_pair_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ofsv_upsample_flow_ac_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_warping_no_div_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ofsv_adamw_step_f32": (_I, [_P, _P, _I, _I, _F, _F, _F, _F, _F, _I, _F, _P]),

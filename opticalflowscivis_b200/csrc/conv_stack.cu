@@ -642,14 +642,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
 }
 
 // weights fp32 tap form [T][Cin_s][Cout_w] -> bf16 blocks of [Cout_w][KC]: out block b = (tap, kc) = table[b]
-struct SkPackTable { uint16_t blk[OFSV_MAX_TAPS * SK_MAX_KC]; };   // (tap << 4) | kc
+struct SkPackTable { uint16_t blk[OFSV_MAX_TAPS * SK_MAX_KC]; };   // (tap << 6) | kc
 __global__ void conv_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SkPackTable T, int nblocks,
                                          int Cin_s, int Cout_w, int KC) {
   const int per = Cout_w * KC;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)nblocks * per; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / per), e = (int)(i - (int64_t)b * per);
     const int r = e / KC, k = e - r * KC;
-    const int tap = T.blk[b] >> 4, kc = T.blk[b] & 15;
+    const int tap = T.blk[b] >> 6, kc = T.blk[b] & 63;
     out[i] = __float2bfloat16_rn(__ldg(w + ((int64_t)tap * Cin_s + kc * KC + k) * Cout_w + r));
   }
 }
@@ -821,16 +821,18 @@ extern "C" int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_ta
   if (layout == OFSV_WL_TAP) {
     KC = d->Cin_s % 64 == 0 ? 64 : (d->Cin_s % 32 == 0 ? 32 : 16);
     nkc = d->Cin_s / KC;
-    OFSV_REQUIRE(nkc <= SK_MAX_KC, "ofsv_conv_pack_weights: too many channel chunks");
+    // the table packs (tap << 6) | kc into 16 bits and holds OFSV_MAX_TAPS * SK_MAX_KC entries: the per-tap kernel itself has no limit
+    // on Cin_s (UPFlow's dense estimator reaches 576 channels = 9 chunks of 64 with 9 taps)
+    OFSV_REQUIRE(nkc <= 64 && ntap * nkc <= OFSV_MAX_TAPS * SK_MAX_KC, "ofsv_conv_pack_weights: too many channel chunks (%d taps x %d chunks)", ntap, nkc);
     for (int t = 0; t < ntap; ++t)
-      for (int kc = 0; kc < nkc; ++kc) T.blk[nblocks++] = (uint16_t)((t << 4) | kc);
+      for (int kc = 0; kc < nkc; ++kc) T.blk[nblocks++] = (uint16_t)((t << 6) | kc);
   } else {
     SkPlan pl;
     if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_pack_weights: layer has no stacked form"); return OFSV_ENOSUP; }
     KC = pl.KC; nkc = pl.nkc;
     for (int g = 0; g < pl.ngroups; ++g)
       for (int kc = 0; kc < nkc; ++kc)
-        for (int s = 0; s < pl.g[g].nslots; ++s) T.blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 4) | kc);
+        for (int s = 0; s < pl.g[g].nslots; ++s) T.blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 6) | kc);
     OFSV_REQUIRE(nblocks == ntap * nkc, "ofsv_conv_pack_weights: internal error (slot count %d != %d)", nblocks, ntap * nkc);
   }
   const int64_t total = (int64_t)nblocks * d->Cout_w * KC;

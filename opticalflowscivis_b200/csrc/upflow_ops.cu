@@ -296,9 +296,48 @@ __global__ void __launch_bounds__(256)
 // corner weights >= 1).  The >= 1 test is decided by the last bit of fp32 arithmetic, so the op order (including the
 // one contracted FMA in ATen's unnormalize) is replicated exactly — see oracle/ofsv_oracle.c.
 // ----------------------------------------------------------------------------------------------------
+// Sampling position, corner weights, in-bounds flags and the >= 1 validity of one output pixel (shared by the kernels below).
+struct NoDivTaps {
+  float nw, ne, sw, se, valid;
+  int x0, y0;
+  bool in00, in01, in10, in11;
+};
+__device__ __forceinline__ NoDivTaps nodiv_taps(int x, int y, float fx, float fy, int H, int W, float dw, float dh, float rdw, float rdh,
+                                                int ref_mode) {
+  NoDivTaps t;
+  const float vx = __fadd_rn((float)x, fx), vy = __fadd_rn((float)y, fy);
+  float gx, gy;
+  if (ref_mode == OFSV_REF_CUDA) {
+    gx = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vx), rdw), 1.0f);
+    gy = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vy), rdh), 1.0f);
+  } else {
+    gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vx), dw), 1.0f);
+    gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vy), dh), 1.0f);
+  }
+  const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), (float)W, -1.0f), 0.5f);
+  const float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), (float)H, -1.0f), 0.5f);
+  const float xw = floorf(ix), yn = floorf(iy);
+  const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.0f, w), n = __fsub_rn(iy, yn), s = __fsub_rn(1.0f, n);
+  t.nw = __fmul_rn(s, e); t.ne = __fmul_rn(s, w); t.sw = __fmul_rn(n, e); t.se = __fmul_rn(n, w);
+  const float xc = fminf(fmaxf(xw, -2.0f), (float)W + 1.0f), yc = fminf(fmaxf(yn, -2.0f), (float)H + 1.0f);
+  t.x0 = (int)xc; t.y0 = (int)yc;
+  const int x1 = t.x0 + 1, y1 = t.y0 + 1;
+  const bool ix0 = t.x0 >= 0 && t.x0 < W, ix1 = x1 >= 0 && x1 < W, iy0 = t.y0 >= 0 && t.y0 < H, iy1 = y1 >= 0 && y1 < H;
+  t.in00 = ix0 && iy0; t.in01 = ix1 && iy0; t.in10 = ix0 && iy1; t.in11 = ix1 && iy1;
+  const float msum = __fadd_rn(__fadd_rn(__fadd_rn(t.in00 ? t.nw : 0.0f, t.in01 ? t.ne : 0.0f), t.in10 ? t.sw : 0.0f), t.in11 ? t.se : 0.0f);
+  t.valid = msum >= 1.0f ? 1.0f : 0.0f;
+  return t;
+}
+__device__ __forceinline__ float nodiv_sample(const NoDivTaps& t, const float* __restrict__ p, int W) {
+  const float p00 = t.in00 ? __ldg(p + (int64_t)t.y0 * W + t.x0) : 0.0f, p01 = t.in01 ? __ldg(p + (int64_t)t.y0 * W + t.x0 + 1) : 0.0f;
+  const float p10 = t.in10 ? __ldg(p + (int64_t)(t.y0 + 1) * W + t.x0) : 0.0f, p11 = t.in11 ? __ldg(p + (int64_t)(t.y0 + 1) * W + t.x0 + 1) : 0.0f;
+  return __fmaf_rn(p11, t.se, __fmaf_rn(p10, t.sw, __fmaf_rn(p01, t.ne, __fmul_rn(p00, t.nw))));
+}
+
+// apply_mask = 1: WarpingLayer_no_div; 0: tools.torch_warp (UPFlow/utils/tools.py:1317-1361), the same sampling without the mask
 __global__ void __launch_bounds__(256)
     warping_no_div_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out, int B,
-                          int C, int H, int W, float dw, float dh, float rdw, float rdh, int ref_mode, int c_per) {
+                          int C, int H, int W, float dw, float dh, float rdw, float rdh, int ref_mode, int c_per, int apply_mask) {
   // blockIdx.y = channel chunk: the coarse pyramid levels have few pixels and many channels (4 x 13 x 196), one thread per
   // pixel looping over all channels left the GPU empty (43 us for 160 KB)
   const int c_begin = blockIdx.y * c_per, c_end = min(C, c_begin + c_per);
@@ -307,35 +346,69 @@ __global__ void __launch_bounds__(256)
     const int b = (int)(i / HW);
     const int r = (int)(i - (int64_t)b * HW);
     const int y = r / W, x = r - y * W;
-    const float vx = __fadd_rn((float)x, ldg_stream(flow + ((int64_t)b * 2 + 0) * HW + r));
-    const float vy = __fadd_rn((float)y, ldg_stream(flow + ((int64_t)b * 2 + 1) * HW + r));
-    float gx, gy;
-    if (ref_mode == OFSV_REF_CUDA) {
-      gx = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vx), rdw), 1.0f);
-      gy = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, vy), rdh), 1.0f);
-    } else {
-      gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vx), dw), 1.0f);
-      gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vy), dh), 1.0f);
-    }
-    const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), (float)W, -1.0f), 0.5f);
-    const float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), (float)H, -1.0f), 0.5f);
-    const float xw = floorf(ix), yn = floorf(iy);
-    const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.0f, w), n = __fsub_rn(iy, yn), s = __fsub_rn(1.0f, n);
-    const float nw = __fmul_rn(s, e), ne = __fmul_rn(s, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
-    const float xc = fminf(fmaxf(xw, -2.0f), (float)W + 1.0f), yc = fminf(fmaxf(yn, -2.0f), (float)H + 1.0f);
-    const int x0 = (int)xc, y0 = (int)yc, x1 = x0 + 1, y1 = y0 + 1;
-    const bool ix0 = x0 >= 0 && x0 < W, ix1 = x1 >= 0 && x1 < W, iy0 = y0 >= 0 && y0 < H, iy1 = y1 >= 0 && y1 < H;
-    const bool in00 = ix0 && iy0, in01 = ix1 && iy0, in10 = ix0 && iy1, in11 = ix1 && iy1;
-    const float msum = __fadd_rn(__fadd_rn(__fadd_rn(in00 ? nw : 0.0f, in01 ? ne : 0.0f), in10 ? sw : 0.0f), in11 ? se : 0.0f);
-    const float valid = msum >= 1.0f ? 1.0f : 0.0f;
+    const NoDivTaps t = nodiv_taps(x, y, ldg_stream(flow + ((int64_t)b * 2 + 0) * HW + r), ldg_stream(flow + ((int64_t)b * 2 + 1) * HW + r), H, W,
+                                   dw, dh, rdw, rdh, ref_mode);
+    const float valid = apply_mask ? t.valid : 1.0f;
     for (int c = c_begin; c < c_end; ++c) {
-      const float* p = src + ((int64_t)b * C + c) * HW;
-      const float p00 = in00 ? __ldg(p + (int64_t)y0 * W + x0) : 0.0f, p01 = in01 ? __ldg(p + (int64_t)y0 * W + x1) : 0.0f;
-      const float p10 = in10 ? __ldg(p + (int64_t)y1 * W + x0) : 0.0f, p11 = in11 ? __ldg(p + (int64_t)y1 * W + x1) : 0.0f;
-      const float v = __fmaf_rn(p11, se, __fmaf_rn(p10, sw, __fmaf_rn(p01, ne, __fmul_rn(p00, nw))));
-      out[((int64_t)b * C + c) * HW + r] = __fmul_rn(v, valid);
+      const float v = nodiv_sample(t, src + ((int64_t)b * C + c) * HW, W);
+      out[((int64_t)b * C + c) * HW + r] = apply_mask ? __fmul_rn(v, valid) : v;
     }
   }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Producer of the cost-volume inputs of one pyramid level (UPFlow/model/upflow.py:621-640): feature_2_warp =
+// WarpingLayer_no_div(feature_2, flow) followed by network_tools.normalize_features((feature_1, feature_2_warp), normalize = center
+// = True, moments_across_channels = moments_across_images = False) (upflow.py:95-138): per (sample, channel) plane
+//   out = (f - mean(f)) / sqrt(var_unbiased(f) + 1e-16).
+// One CTA per (tensor, sample, channel): the plane (warped on the fly for the second tensor) is staged in shared memory, so the
+// source is read once and the three passes (mean, centred sum of squares, normalise) never touch HBM again.
+// ----------------------------------------------------------------------------------------------------
+constexpr int FN_THREADS = 256;
+__device__ __forceinline__ float fn_block_sum(float v, float* red) {
+  // fixed-order reduction: lanes by shuffle, warps by one thread
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();                                   // `red` may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < FN_THREADS / 32; ++w) s += red[w];
+  return s;
+}
+__global__ void __launch_bounds__(FN_THREADS)
+    feature_norm_pair_kernel(const float* __restrict__ f_plain, const float* __restrict__ f_src, const float* __restrict__ flow,
+                             float* __restrict__ out_plain, float* __restrict__ out_warp, int C, int H, int W, float dw, float dh,
+                             float rdw, float rdh, int ref_mode) {
+  extern __shared__ float plane[];
+  __shared__ float red[FN_THREADS / 32];
+  const int c = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
+  const int HW = H * W;
+  const float* src = (which == 0 ? f_plain : f_src) + ((int64_t)b * C + c) * HW;
+  float* out = (which == 0 ? out_plain : out_warp) + ((int64_t)b * C + c) * HW;
+  const bool warp = which == 1 && flow != nullptr;
+  float sum = 0.f;
+  for (int r = threadIdx.x; r < HW; r += FN_THREADS) {
+    float v;
+    if (warp) {
+      const int y = r / W, x = r - y * W;
+      const NoDivTaps t = nodiv_taps(x, y, __ldg(flow + ((int64_t)b * 2 + 0) * HW + r), __ldg(flow + ((int64_t)b * 2 + 1) * HW + r), H, W, dw, dh,
+                                     rdw, rdh, ref_mode);
+      v = __fmul_rn(nodiv_sample(t, src, W), t.valid);
+    } else {
+      v = __ldg(src + r);
+    }
+    plane[r] = v;
+    sum += v;
+  }
+  const float mean = fn_block_sum(sum, red) / (float)HW;
+  float ss = 0.f;
+  for (int r = threadIdx.x; r < HW; r += FN_THREADS) {
+    const float d = plane[r] - mean;
+    ss += d * d;
+  }
+  const float var = fn_block_sum(ss, red) / (float)(HW - 1);     // torch.var: unbiased
+  const float sd = sqrtf(var + 1e-16f);
+  for (int r = threadIdx.x; r < HW; r += FN_THREADS) out[r] = __fdiv_rn(__fsub_rn(plane[r], mean), sd);
 }
 
 static inline int grid_1d(int64_t total) {
@@ -418,18 +491,48 @@ extern "C" int ofsv_upsample_flow_ac_f32(const float* in, float* out, int B, int
   return check_launch("upsample_flow_ac_kernel");
 }
 
-extern "C" int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W,
-                                       int ref_mode, void* stream) {
-  OFSV_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && (int64_t)H * W < (1ll << 31), "ofsv_warping_no_div_f32: bad shape");
-  OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_warping_no_div_f32: bad ref_mode");
+static int warping_no_div_launch(const char* who, const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode,
+                                 int apply_mask, void* stream) {
+  OFSV_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && (int64_t)H * W < (1ll << 31), "%s: bad shape", who);
+  OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "%s: bad ref_mode", who);
   if ((int64_t)B * C == 0) return OFSV_OK;
-  OFSV_REQUIRE(src && flow && out, "ofsv_warping_no_div_f32: null pointer");
+  OFSV_REQUIRE(src && flow && out, "%s: null pointer", who);
   const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
   const int gx = grid_1d((int64_t)B * H * W);
   int nsplit = (int)(cdiv(device_num_sms() * 8, gx));                 // aim at >= 8 CTAs per SM; at least 4 channels per thread
   nsplit = nsplit < 1 ? 1 : (nsplit > cdiv(C, 4) ? (int)cdiv(C, 4) : nsplit);
   const int c_per = (int)cdiv(C, nsplit);
   warping_no_div_kernel<<<dim3((unsigned)gx, (unsigned)cdiv(C, c_per)), 256, 0, (cudaStream_t)stream>>>(
-      src, flow, out, B, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode, c_per);
+      src, flow, out, B, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode, c_per, apply_mask);
   return check_launch("warping_no_div_kernel");
+}
+
+extern "C" int ofsv_warping_no_div_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W,
+                                       int ref_mode, void* stream) {
+  return warping_no_div_launch("ofsv_warping_no_div_f32", src, flow, out, B, C, H, W, ref_mode, 1, stream);
+}
+
+extern "C" int ofsv_torch_warp_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int ref_mode,
+                                   void* stream) {
+  return warping_no_div_launch("ofsv_torch_warp_f32", src, flow, out, B, C, H, W, ref_mode, 0, stream);
+}
+
+extern "C" int ofsv_feature_norm_pair_f32(const float* f_plain, const float* f_src, const float* flow, float* out_plain, float* out_warp,
+                                          int B, int C, int H, int W, int ref_mode, void* stream) {
+  OFSV_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1 && (int64_t)H * W >= 2, "ofsv_feature_norm_pair_f32: bad shape (a plane needs >= 2 pixels)");
+  OFSV_REQUIRE(ref_mode == OFSV_REF_CPU || ref_mode == OFSV_REF_CUDA, "ofsv_feature_norm_pair_f32: bad ref_mode");
+  if ((int64_t)B * C == 0) return OFSV_OK;
+  OFSV_REQUIRE(f_plain && f_src && out_plain && out_warp, "ofsv_feature_norm_pair_f32: null pointer");
+  OFSV_REQUIRE(B <= 65535, "ofsv_feature_norm_pair_f32: B > 65535");
+  const int64_t bytes = (int64_t)H * W * 4;
+  if (bytes > 200 * 1024) {
+    set_error("ofsv_feature_norm_pair_f32: a %d x %d plane does not fit the 200 KB shared-memory staging (pyramid levels of UPFlow are <= 64 x 208)", H, W);
+    return OFSV_ENOSUP;
+  }
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dyn_smem(attr_done, feature_norm_pair_kernel, 200 * 1024, "ofsv_feature_norm_pair_f32")) return e;
+  const int dw = W - 1 > 1 ? W - 1 : 1, dh = H - 1 > 1 ? H - 1 : 1;
+  feature_norm_pair_kernel<<<dim3((unsigned)C, (unsigned)B, 2), FN_THREADS, (size_t)bytes, (cudaStream_t)stream>>>(
+      f_plain, f_src, flow, out_plain, out_warp, C, H, W, (float)dw, (float)dh, (float)(1.0 / (double)dw), (float)(1.0 / (double)dh), ref_mode);
+  return check_launch("feature_norm_pair_kernel");
 }

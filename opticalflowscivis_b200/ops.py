@@ -378,6 +378,36 @@ def warping_no_div(x, flow):
     return _warping_no_div_fwd(x, flow)
 
 
+def torch_warp(x, flow):
+    """tools.torch_warp (UPFlow/utils/tools.py:1317-1361): WarpingLayer_no_div's sampling without the validity mask (forward only)."""
+    x, flow = _cuda_f32(x, "x"), _cuda_f32(flow, "flow")
+    if x.dim() != 4 or flow.shape != (x.shape[0], 2, x.shape[2], x.shape[3]):
+        raise ValueError("torch_warp: bad shapes")
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    with _on(x.device), _span("torch_warp"):
+        _C.check(_C.lib().ofsv_torch_warp_f32(_p(x), _p(flow), _p(out), b, c, h, w, _FLAVOR["mode"], _stream()))
+    return out
+
+
+def feature_norm_pair(f_plain, f_src, flow=None):
+    """(normalize(f_plain), normalize(WarpingLayer_no_div(f_src, flow))) in one launch (ofsv_feature_norm_pair_f32) — the producer of
+    the cost-volume inputs, UPFlow/model/upflow.py:621-640 with the per-(sample, channel) moments of simple_train.py:321-329.
+    flow None = pyramid level 0 (no warp)."""
+    f_plain, f_src = _cuda_f32(f_plain, "f_plain"), _cuda_f32(f_src, "f_src")
+    if f_plain.dim() != 4 or f_src.shape != f_plain.shape:
+        raise ValueError("feature_norm_pair: bad shapes")
+    b, c, h, w = f_plain.shape
+    if flow is not None:
+        flow = _cuda_f32(flow, "flow")
+        if flow.shape != (b, 2, h, w):
+            raise ValueError("feature_norm_pair: bad flow shape")
+    o0, o1 = torch.empty_like(f_plain), torch.empty_like(f_src)
+    with _on(f_plain.device), _span("feature_norm_pair"):
+        _C.check(_C.lib().ofsv_feature_norm_pair_f32(_p(f_plain), _p(f_src), _p(flow), _p(o0), _p(o1), b, c, h, w, _FLAVOR["mode"], _stream()))
+    return o0, o1
+
+
 # ------------------------------------------------------------------------------------------------ IFNet engine pieces
 _TDT = {_C.F32: torch.float32, _C.BF16: torch.bfloat16}
 
