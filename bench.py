@@ -185,8 +185,8 @@ def run_reference_arm(args, rank, world):
     on this box's host cores, same workload / metric / unit; every step is a bounded sample of the step (see CPU_SAMPLE)."""
     if rank != 0:
         return
-    if args.workload in ("upflow_ops", "train3d"):
-        print(json.dumps({"impl": "reference", "unavailable": f"{args.workload} is a training-tier workload without a CPU arm "
+    if args.workload in ("upflow_ops", "train3d", "upflow_net"):
+        print(json.dumps({"impl": "reference", "unavailable": f"{args.workload} is a next-tier workload (SURVEY.md §8f) without a CPU arm "
                           "(train3d reports the reference's eager-CUDA update as `cuda_eager_reference`)"}), flush=True)
         return
     nd, sp, pairs, desc = WORKLOADS[args.workload]
@@ -571,6 +571,65 @@ def run_upflow_ops(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ UPFlow network workload
+def run_upflow_net(args, rank, world, local_rank):
+    """one step = `UPFlow_net.forward_2_frame_v3` (UPFlow/model/upflow.py:580-665: feature pyramid, five decode
+    levels x two directions with warp + feature normalisation + 81-channel correlation + dense estimator + dilated context net) on
+    `pairs` synthetic 256x832 image pairs per GPU (BASELINE.json configs[4] shapes), inference, random MSRA-scale weights."""
+    import torch
+    import torch.distributed as dist
+
+    from opticalflowscivis_b200 import ops
+    from opticalflowscivis_b200.upflow.net import UPFlowNet
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    b = args.pairs or 8
+    torch.manual_seed(1234)
+    net = UPFlowNet().to(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    base = torch.nn.functional.avg_pool2d(torch.rand((b, 3, 256 + 16, 832 + 16), generator=g), 7, 1, 3)
+    base = (base - base.mean()) / base.std() * 0.2
+    im1, im2 = base[:, :, 8:-8, 8:-8].contiguous().to(dev), base[:, :, 8:-8, 2:-14].contiguous().to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k=1):
+        for _ in range(k):
+            net.forward_2_frame_v3(im1, im2)
+
+    step(args.warmup)
+    n0 = ops.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = _timed(step, args.steps, barrier)
+        launches = ops.launch_count() - n0
+        clk.keep_loaded(lambda: (step(5), torch.cuda.synchronize()))
+    ops.TIMER = timer = ops.LaunchTimer()
+    ms_prof = _timed(step, args.steps, barrier)
+    ops.TIMER = None
+    classes = {k: {"launches": c // args.steps, "ms_per_step": t / args.steps} for k, (c, t) in timer.totals().items()}
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank != 0:
+        return
+    line = {
+        "metric": "UPFlow 256x832 flow pairs/sec (forward_2_frame_v3, both directions)", "value": world * b * args.steps / (ms / 1e3),
+        "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "e2e": None,
+        "gpu_launches": int(launches), "kernel_classes": classes, "ms_per_step_instrumented": ms_prof / args.steps, "clocks": clk.summary(),
+        "config": {"workload": "upflow_net", "describes": run_upflow_net.__doc__.split("\n\n")[0].replace("\n    ", " "),
+                   "spatial": [256, 832], "pairs_per_gpu_per_step": b,
+                   "note": "convolutions on the tcgen05 engines (bf16), correlation / warps / normalisation / flow resizes in fp32 "
+                           "libofsv kernels; layout changes and concatenations are torch copies; eager enqueue (no CUDA graph)"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ training-step workload
 def run_train3d(args, rank, world, local_rank):
     """one step = `Model.update` of the 3-D model (Flow-3D/model/RIFE.py:81-275: forward with the teacher block,
@@ -683,7 +742,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops", "train3d"])
+    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops", "train3d", "upflow_net"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
@@ -721,7 +780,7 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     try:
-        {"upflow_ops": run_upflow_ops, "train3d": run_train3d}.get(args.workload, run_ours)(args, rank, world, local_rank)
+        {"upflow_ops": run_upflow_ops, "train3d": run_train3d, "upflow_net": run_upflow_net}.get(args.workload, run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
