@@ -268,6 +268,158 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
   }
 }
 
+// ---- tap-group variant -------------------------------------------------------------------------------------------------------
+// For layers with many taps and small channel tiles (conv0.0: 64 taps of 16 x 32, the heads: 8 x 8 taps of 64 x 16) the kernel above
+// spends its time re-loading the gradient rows and synchronising once per tap.  Here a CTA owns TG = 4 * TPW taps of one phase:
+// the 32 gradient rows of a position chunk are loaded ONCE and their B fragments reused for every tap, each warp accumulates the
+// full MT x NT tile of its TPW taps (A fragments from that tap's shifted input rows), and the position -> (n, z, y, x) divisions
+// are done once per row and shared by the taps.
+template <int MT, int NT, int TPW>
+struct WgTg {
+  static constexpr int TG = 4 * TPW;
+  static constexpr int XP = MT * 2 + 16, GP = NT * 2 + 16;
+  static constexpr int STAGE = WG_KC * GP + TG * WG_KC * XP;
+  static constexpr int MI = MT / 16, NI = NT / 8;
+  static_assert(TPW * MI * NI * 4 <= 64, "accumulator registers");
+};
+
+template <int MT, int NT, int TPW>
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tg_kernel(const __grid_constant__ WgradParams p, int ngroups) {
+  using TL = WgTg<MT, NT, TPW>;
+  constexpr int TG = TL::TG, MI = TL::MI, NI = TL::NI;
+  extern __shared__ __align__(16) unsigned char dsmem[];
+  __shared__ int xrow_tab[2][TG][WG_KC], grow_tab[2][WG_KC];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tile = blockIdx.x;
+  const int ntile = tile % p.nt; tile /= p.nt;
+  const int mtile = tile % p.mt; tile /= p.mt;
+  const int grp = tile % ngroups, ph = tile / ngroups;
+  const int tap0 = grp * TG;                               // first tap (within the phase) of this CTA
+  const int ntap = min(TG, p.ntaps - tap0);
+  const int pz = (ph >> 2) & 1, py = (ph >> 1) & 1, px = ph & 1;
+  const int64_t k_begin = (int64_t)blockIdx.y * p.Kper;
+  const int64_t k_end = min(p.K, k_begin + p.Kper);
+  const int nchunk = (int)((k_end - k_begin + WG_KC - 1) / WG_KC);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dsmem);
+
+  auto fill_table = [&](int chunk) {                      // thread = (row, tap quarter): one position decomposition, TPW taps
+    const int row = tid & 31, tq = tid >> 5;
+    const int64_t q = k_begin + (int64_t)chunk * WG_KC + row;
+    int n = 0, vz = 0, vy = 0, vx = 0;
+    const bool live = q < k_end;
+    if (live) {
+      int r = (int)q;
+      vx = r % p.Wo; r /= p.Wo;
+      vy = r % p.Ho; r /= p.Ho;
+      vz = r % p.Do; n = r / p.Do;
+    }
+    if (tq == 0)
+      grow_tab[chunk & 1][row] = live ? ((n * p.Dy + vz * p.out_stride + pz) * p.Hy + vy * p.out_stride + py) * p.Wy + vx * p.out_stride + px : -1;
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) {
+      const int tl = tq + 4 * j;
+      int xr = -1;
+      if (live && tl < ntap) {
+        const int8_t* o = p.tap[ph * p.ntaps + tap0 + tl];
+        const int iz = vz * p.in_stride + o[0], iy = vy * p.in_stride + o[1], ix = vx * p.in_stride + o[2];
+        if (iz >= 0 && iz < p.Di && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) xr = ((n * p.Di + iz) * p.Hi + iy) * p.Wi + ix;
+      }
+      xrow_tab[chunk & 1][tl][row] = xr;
+    }
+  };
+  auto issue_loads = [&](int chunk) {
+    const uint32_t st = sbase + (chunk & 1) * TL::STAGE;
+    constexpr int XPIECES = MT / 8, GPIECES = NT / 8;
+    for (int i = tid; i < WG_KC * GPIECES; i += WG_THREADS) {
+      const int row = i / GPIECES, pc = i % GPIECES;
+      const int gr = grow_tab[chunk & 1][row];
+      const __nv_bfloat16* src = gr >= 0 ? p.g + (int64_t)gr * p.g_cs + ntile * NT + pc * 8 : p.g;
+      cp_async16(st + row * TL::GP + pc * 16, src, gr >= 0 ? 16 : 0);
+    }
+    const uint32_t xs = st + WG_KC * TL::GP;
+    for (int i = tid; i < ntap * WG_KC * XPIECES; i += WG_THREADS) {
+      const int tl = i / (WG_KC * XPIECES), rem = i % (WG_KC * XPIECES);
+      const int row = rem / XPIECES, pc = rem % XPIECES;
+      const int xr = xrow_tab[chunk & 1][tl][row];
+      const __nv_bfloat16* src = xr >= 0 ? p.x + (int64_t)xr * p.Cin_s + mtile * MT + pc * 8 : p.x;
+      cp_async16(xs + (tl * WG_KC + row) * TL::XP + pc * 16, src, xr >= 0 ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[TPW][MI][NI][4];
+#pragma unroll
+  for (int j = 0; j < TPW; ++j)
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+      for (int b = 0; b < NI; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][a][b][c] = 0.f;
+
+  if (nchunk > 0) {
+    fill_table(0);
+    __syncthreads();
+    issue_loads(0);
+    if (nchunk > 1) fill_table(1);
+    for (int c = 0; c < nchunk; ++c) {
+      __syncthreads();
+      if (c + 1 < nchunk) {
+        issue_loads(c + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      if (c + 2 < nchunk) fill_table(c + 2);
+      const uint32_t gs = sbase + (c & 1) * TL::STAGE, xs0 = gs + WG_KC * TL::GP;
+      const int mat = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < WG_KC / 16; ++ks) {
+        uint32_t bfr[NI][2];
+        if constexpr (NI % 2 == 0) {
+#pragma unroll
+          for (int b = 0; b < NI; b += 2)
+            ldmatrix_x4_t(gs + (ks * 16 + (mat & 1) * 8 + r) * TL::GP + ((b + (mat >> 1)) * 8) * 2, bfr[b][0], bfr[b][1], bfr[b + 1][0], bfr[b + 1][1]);
+        } else {
+          ldmatrix_x2_t(gs + (ks * 16 + (mat & 1) * 8 + r) * TL::GP, bfr[0][0], bfr[0][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          const int tl = warp + 4 * j;
+          if (tl < ntap) {                                 // warp-uniform
+            const uint32_t xs = xs0 + tl * WG_KC * TL::XP;
+#pragma unroll
+            for (int a = 0; a < MI; ++a) {
+              uint32_t afr[4];
+              ldmatrix_x4_t(xs + (ks * 16 + (mat >> 1) * 8 + r) * TL::XP + (a * 16 + (mat & 1) * 8) * 2, afr[0], afr[1], afr[2], afr[3]);
+#pragma unroll
+              for (int b = 0; b < NI; ++b) mma_bf16_16816(acc[j][a][b], afr, bfr[b][0], bfr[b][1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < TPW; ++j) {
+    const int tl = warp + 4 * j;
+    if (tl >= ntap) continue;
+    const int tap = ph * p.ntaps + tap0 + tl;
+    float* out = p.out + (((int64_t)blockIdx.y * p.T + tap) * p.Cin_s + mtile * MT) * p.Cout_w + ntile * NT;
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+      for (int b = 0; b < NI; ++b) {
+        const int row = a * 16 + g, col = b * 8 + 2 * t;
+        *reinterpret_cast<float2*>(out + (int64_t)row * p.Cout_w + col) = make_float2(acc[j][a][b][0], acc[j][a][b][1]);
+        *reinterpret_cast<float2*>(out + (int64_t)(row + 8) * p.Cout_w + col) = make_float2(acc[j][a][b][2], acc[j][a][b][3]);
+      }
+  }
+}
+
 __global__ void conv_wgrad_finalize(const float4* __restrict__ work, float4* __restrict__ dw, int64_t n4, int splits) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -299,18 +451,42 @@ int wgrad_validate(const ofsv_conv_desc* d) {
   return OFSV_OK;
 }
 
-int wgrad_splits(const ofsv_conv_desc* d) {
+// Taps per warp of the tap-group kernel for an MT x NT tile (0 = use the per-tap kernel): 64 accumulator registers per thread.
+int tg_tpw(int MT, int NT) {
+  const int per_tap = (MT / 16) * (NT / 8) * 4;
+  return per_tap > 64 ? 0 : (64 / per_tap > 4 ? 4 : 64 / per_tap);
+}
+struct WgPlan { int MT, NT, tpw, ngroups, splits; int64_t tiles; };
+WgPlan wgrad_plan(const ofsv_conv_desc* d) {
+  WgPlan pl;
+  pl.MT = tile_of(d->Cin_s); pl.NT = tile_of(d->Cout_w);
+  pl.tpw = d->ntaps >= 4 ? tg_tpw(pl.MT, pl.NT) : 0;
+  const int64_t mn = (int64_t)(d->Cin_s / pl.MT) * (d->Cout_w / pl.NT);
+  if (pl.tpw) {
+    pl.ngroups = (int)cdiv(d->ntaps, 4 * pl.tpw);
+    pl.tiles = (int64_t)d->nphase * pl.ngroups * mn;
+  } else {
+    pl.ngroups = 0;
+    pl.tiles = (int64_t)d->nphase * d->ntaps * mn;
+  }
   const int64_t K = (int64_t)d->N * d->Do * d->Ho * d->Wo;
-  const int64_t tiles = (int64_t)d->nphase * d->ntaps * (d->Cin_s / tile_of(d->Cin_s)) * (d->Cout_w / tile_of(d->Cout_w));
-  const int64_t want = cdiv((int64_t)device_num_sms() * 8, tiles);
+  const int64_t want = cdiv((int64_t)device_num_sms() * (pl.tpw ? 4 : 8), pl.tiles);
   int64_t s = std::min<int64_t>(want, cdiv(K, 8 * WG_KC));
-  s = std::max<int64_t>(1, std::min<int64_t>(s, 64));
-  return (int)s;
+  pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+  return pl;
 }
 
 template <int MT, int NT>
 void launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
   conv_wgrad_kernel<MT, NT><<<grid, WG_THREADS, 0, st>>>(p);
+}
+template <int MT, int NT, int TPW>
+int launch_wgrad_tg(const WgradParams& p, dim3 grid, int ngroups, cudaStream_t st) {
+  static std::atomic<uint64_t> attr_done{0};
+  constexpr int smem = 2 * WgTg<MT, NT, TPW>::STAGE;
+  if (int e = ensure_dyn_smem(attr_done, conv_wgrad_tg_kernel<MT, NT, TPW>, smem, "ofsv_conv_wgrad_bf16")) return e;
+  conv_wgrad_tg_kernel<MT, NT, TPW><<<grid, WG_THREADS, smem, st>>>(p, ngroups);
+  return OFSV_OK;
 }
 
 }  // namespace
@@ -340,7 +516,7 @@ extern "C" int ofsv_prelu_bias_bwd_bf16(const void* gy, const void* y, const flo
 extern "C" int ofsv_conv_wgrad_splits(const ofsv_conv_desc* d) {
   int rc = wgrad_validate(d);
   if (rc) return rc;
-  return wgrad_splits(d);
+  return wgrad_plan(d).splits;
 }
 
 extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, const void* gy, int gy_cs, float* dw, float* work, void* stream) {
@@ -349,7 +525,8 @@ extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, cons
   OFSV_REQUIRE(x && gy && dw, "conv_wgrad: null pointer");
   OFSV_REQUIRE(gy_cs >= d->Cout_w && gy_cs % 8 == 0, "conv_wgrad: gy_cs (%d) must be a multiple of 8 and >= Cout_w (%d)", gy_cs, d->Cout_w);
   OFSV_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(dw) && (!work || aligned16(work)), "conv_wgrad: pointers must be 16-byte aligned");
-  const int splits = wgrad_splits(d);
+  const WgPlan pl = wgrad_plan(d);
+  const int splits = pl.splits;
   OFSV_REQUIRE(splits == 1 || work, "conv_wgrad: %d K splits need a work buffer of ofsv_conv_wgrad_splits(d) * T * Cin_s * Cout_w floats", splits);
   WgradParams p;
   p.x = static_cast<const __nv_bfloat16*>(x);
@@ -360,7 +537,7 @@ extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, cons
   p.Dy = d->nd == 2 ? 1 : d->Dy; p.Hy = d->Hy; p.Wy = d->Wy; p.g_cs = gy_cs; p.Cout_w = d->Cout_w;
   p.in_stride = d->in_stride; p.out_stride = d->out_stride;
   p.T = d->nphase * d->ntaps; p.ntaps = d->ntaps;
-  const int MT = tile_of(d->Cin_s), NT = tile_of(d->Cout_w);
+  const int MT = pl.MT, NT = pl.NT;
   p.mt = d->Cin_s / MT; p.nt = d->Cout_w / NT;
   p.K = (int64_t)p.N * p.Do * p.Ho * p.Wo;
   p.Kper = cdiv(cdiv(p.K, splits), WG_KC) * WG_KC;
@@ -369,11 +546,20 @@ extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, cons
   if (d->nd == 2)
     for (int i = 0; i < p.T; ++i) p.tap[i][0] = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid((unsigned)(p.T * p.mt * p.nt), (unsigned)splits);
+  dim3 grid((unsigned)pl.tiles, (unsigned)splits);
+  if (pl.tpw) {
+    int e = OFSV_ENOSUP;
+#define OFSV_TG_CASE(M, Nn, TP) if (MT == M && NT == Nn && pl.tpw == TP) e = launch_wgrad_tg<M, Nn, TP>(p, grid, pl.ngroups, st); else
+    OFSV_TG_CASE(64, 32, 1) OFSV_TG_CASE(64, 16, 2) OFSV_TG_CASE(32, 64, 1) OFSV_TG_CASE(32, 32, 2) OFSV_TG_CASE(32, 16, 4)
+    OFSV_TG_CASE(16, 64, 2) OFSV_TG_CASE(16, 32, 4) OFSV_TG_CASE(16, 16, 4) { set_error("conv_wgrad: no tap-group kernel for %d x %d x %d", MT, NT, pl.tpw); }
+#undef OFSV_TG_CASE
+    if (e) return e;
+  } else {
 #define OFSV_WG_CASE(M, Nn) if (MT == M && NT == Nn) launch_wgrad<M, Nn>(p, grid, st); else
-  OFSV_WG_CASE(64, 64) OFSV_WG_CASE(64, 32) OFSV_WG_CASE(64, 16) OFSV_WG_CASE(32, 64) OFSV_WG_CASE(32, 32) OFSV_WG_CASE(32, 16)
-  OFSV_WG_CASE(16, 64) OFSV_WG_CASE(16, 32) OFSV_WG_CASE(16, 16) { set_error("conv_wgrad: no tile for %d x %d", MT, NT); return OFSV_ENOSUP; }
+    OFSV_WG_CASE(64, 64) OFSV_WG_CASE(64, 32) OFSV_WG_CASE(64, 16) OFSV_WG_CASE(32, 64) OFSV_WG_CASE(32, 32) OFSV_WG_CASE(32, 16)
+    OFSV_WG_CASE(16, 64) OFSV_WG_CASE(16, 32) OFSV_WG_CASE(16, 16) { set_error("conv_wgrad: no tile for %d x %d", MT, NT); return OFSV_ENOSUP; }
 #undef OFSV_WG_CASE
+  }
   rc = check_launch("conv_wgrad_kernel");
   if (rc) return rc;
   if (splits > 1) {
