@@ -272,6 +272,20 @@ int ofsv_set_tuning(const char* key, int value);
  *   gy_cs >= Cout_w).  Only the geometry fields of the descriptor are read.  bf16 mma.sync GEMM over the output positions, split
  *   along K over ofsv_conv_wgrad_splits(d) CTAs per tile; `work` = splits * nphase*ntaps*Cin_s*Cout_w floats (may be NULL when
  *   splits == 1), summed in a fixed order. */
+/* Per-step refresh of the fp32 tap-form weights (and padded bias / slope vectors) of many layers from the reference's parameter
+ * tensors in ONE launch (the optimizer changes every parameter every step; opticalflowscivis_b200/train.py).  `recs_dev` is a DEVICE
+ * array of records:
+ *   kind 0: dst[(t*Cin_s + ci0 + i)*Cout_w + co0 + o] = kidx[t] >= 0 ? src[(a*B + b)*K + kidx[t]] : 0 for t < T, with the parameter
+ *           viewed [A][B][K] (K = kernel volume) and (i, o) = (a, b) (swap = 0: ConvTranspose weights forward, Conv weights as the
+ *           matrices of an input-gradient layer) or (b, a) (swap = 1);
+ *   kind 1: dst[i] = src[i], i < n. */
+typedef struct ofsv_refresh_rec {
+  const float* src;
+  float* dst;
+  int32_t kind, A, B, K, swap, T, Cin_s, Cout_w, ci0, co0, n, pad_;
+  int16_t kidx[OFSV_MAX_TAPS];
+} ofsv_refresh_rec;
+int ofsv_conv_refresh_tapform(const ofsv_refresh_rec* recs_dev, int nrec, void* stream);
 int ofsv_prelu_bias_bwd_blocks(void);
 int ofsv_prelu_bias_bwd_bf16(const void* gy, const void* y, const float* slope, void* gpre, float* dbias, float* dslope, float* work,
                              int64_t P, int Cs, void* stream);

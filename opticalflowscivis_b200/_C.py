@@ -34,6 +34,14 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class RefreshRec(ctypes.Structure):
+    """Mirror of `ofsv_refresh_rec` (include/ofsv.h)."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p),
+                ("kind", ctypes.c_int32), ("A", ctypes.c_int32), ("B", ctypes.c_int32), ("K", ctypes.c_int32), ("swap", ctypes.c_int32),
+                ("T", ctypes.c_int32), ("Cin_s", ctypes.c_int32), ("Cout_w", ctypes.c_int32), ("ci0", ctypes.c_int32), ("co0", ctypes.c_int32),
+                ("n", ctypes.c_int32), ("pad_", ctypes.c_int32), ("kidx", ctypes.c_int16 * MAX_TAPS)]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGS = {
     "ofsv_version": (ctypes.c_char_p, []),
@@ -70,6 +78,7 @@ _SIGS = {
     "ofsv_conv_stack_selfcheck": (_I, [ctypes.POINTER(ConvDesc), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
     "ofsv_conv_halo_describe": (_I, [ctypes.POINTER(ConvDesc), ctypes.c_char_p, _I]),
     "ofsv_set_tuning": (_I, [ctypes.c_char_p, _I]),
+    "ofsv_conv_refresh_tapform": (_I, [_P, _I, _P]),
     "ofsv_prelu_bias_bwd_blocks": (_I, []),
     "ofsv_prelu_bias_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "ofsv_conv_wgrad_splits": (_I, [ctypes.POINTER(ConvDesc)]),

@@ -80,15 +80,19 @@ __global__ void __launch_bounds__(PB_THREADS) prelu_bias_bwd_kernel(const __nv_b
   }
 }
 
+// one warp per output (bias | slope, channel): lanes stride over the per-CTA partials, then a fixed shuffle tree (deterministic)
 __global__ void prelu_bias_bwd_finalize(const float* __restrict__ partial, float* __restrict__ dbias, float* __restrict__ dslope, int nblk,
                                         int Cs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= 2 * Cs) return;
   const int which = i / Cs, c = i % Cs;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[((int64_t)b * 2 + which) * Cs + c];
-  if (which == 0) dbias[c] = s;
-  else if (dslope) dslope[c] = s;
+  for (int b = lane; b < nblk; b += 32) s += partial[((int64_t)b * 2 + which) * Cs + c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (which == 0) dbias[c] = s;
+    else if (dslope) dslope[c] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -492,7 +496,38 @@ int launch_wgrad_tg(const WgradParams& p, dim3 grid, int ngroups, cudaStream_t s
 }  // namespace
 }  // namespace ofsv
 
+namespace ofsv {
+namespace {
+// ------------------------------------------------------------------------------------------------ per-step weight refresh
+__global__ void __launch_bounds__(256) conv_refresh_kernel(const ofsv_refresh_rec* __restrict__ recs) {
+  const ofsv_refresh_rec& r = recs[blockIdx.y];
+  if (r.kind == 1) {                                      // vector copy (bias, PReLU slopes)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += gridDim.x * blockDim.x) r.dst[i] = r.src[i];
+    return;
+  }
+  const int cin = r.swap ? r.B : r.A, cout = r.swap ? r.A : r.B;
+  const int64_t total = (int64_t)r.T * cin * cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(e % cout);
+    const int64_t q = e / cout;
+    const int i = (int)(q % cin), t = (int)(q / cin);
+    const int k = r.kidx[t];
+    const int a = r.swap ? o : i, b = r.swap ? i : o;
+    r.dst[((int64_t)t * r.Cin_s + r.ci0 + i) * r.Cout_w + r.co0 + o] = k >= 0 ? __ldg(r.src + ((int64_t)a * r.B + b) * r.K + k) : 0.f;
+  }
+}
+}  // namespace
+}  // namespace ofsv
+
 using namespace ofsv;
+
+extern "C" int ofsv_conv_refresh_tapform(const ofsv_refresh_rec* recs_dev, int nrec, void* stream) {
+  OFSV_REQUIRE(nrec >= 0 && nrec <= 65535, "ofsv_conv_refresh_tapform: bad record count");
+  if (nrec == 0) return OFSV_OK;
+  OFSV_REQUIRE(recs_dev != nullptr && (reinterpret_cast<uintptr_t>(recs_dev) & 7u) == 0, "ofsv_conv_refresh_tapform: null / misaligned record table");
+  conv_refresh_kernel<<<dim3(32, (unsigned)nrec), 256, 0, static_cast<cudaStream_t>(stream)>>>(recs_dev);
+  return check_launch("conv_refresh_kernel");
+}
 
 extern "C" int ofsv_prelu_bias_bwd_blocks(void) { return 2 * device_num_sms(); }
 
@@ -509,7 +544,7 @@ extern "C" int ofsv_prelu_bias_bwd_bf16(const void* gy, const void* y, const flo
                                                         static_cast<__nv_bfloat16*>(gpre), work, P, Cs);
   int rc = check_launch("prelu_bias_bwd_kernel");
   if (rc) return rc;
-  prelu_bias_bwd_finalize<<<(int)cdiv(2 * Cs, 128), 128, 0, st>>>(work, dbias, slope ? dslope : nullptr, nblk, Cs);
+  prelu_bias_bwd_finalize<<<(int)cdiv(2 * Cs * 32, 256), 256, 0, st>>>(work, dbias, slope ? dslope : nullptr, nblk, Cs);
   return check_launch("prelu_bias_bwd_finalize");
 }
 

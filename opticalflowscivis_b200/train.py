@@ -179,6 +179,7 @@ class _TrainBlock:
 
         def __init__(self, param, perm, kidx, ci0=0, co0=0):
             self.param, self.perm, self.ci0, self.co0 = param, perm, ci0, co0
+            self.raw_kidx = list(kidx)
             k = torch.tensor(kidx, device=param.device)
             self.valid = None if bool((k >= 0).all()) else (k >= 0).float().view(-1, 1, 1)
             self.kidx = k.clamp(min=0)
@@ -263,6 +264,41 @@ class _TrainBlock:
         dg.append([S(blk.conv1[2].weight, BA, ident(4)), S(blk.conv2[2].weight, BA, ident(4), ci0=nf, co0=h)])
         return fw, dg
 
+    def _record_table(self):
+        """Device table of ofsv_refresh_rec: every weight source and bias / slope vector of the 24 layers, for ONE refresh launch."""
+        recs = []
+
+        def weight(lay, sct):
+            r = _C.RefreshRec()
+            p = sct.param
+            r.src, r.dst, r.kind = p.data_ptr(), lay.w_simt.data_ptr(), 0
+            r.A, r.B, r.K = p.shape[0], p.shape[1], p[0, 0].numel()
+            r.swap = 0 if tuple(sct.perm) == (2, 0, 1) else 1
+            r.T, r.Cin_s, r.Cout_w = lay.w_simt.shape
+            r.ci0, r.co0 = sct.ci0, sct.co0
+            for i, k in enumerate(sct.raw_kidx):
+                r.kidx[i] = k
+            recs.append(r)
+
+        def vector(dst, off, p):
+            r = _C.RefreshRec()
+            r.src, r.dst, r.kind, r.n = p.data_ptr(), dst.data_ptr() + 4 * off, 1, p.numel()
+            recs.append(r)
+
+        for lay, (ws, bs, ps) in zip(self.fwd, self.src_fwd):
+            for sct in ws:
+                weight(lay, sct)
+            for b, off in bs:
+                vector(lay.bias, off, b)
+            for pw, off in ps:
+                vector(lay.prelu, off, pw)
+        for lay, ws in zip(self.dgrad, self.src_dgrad):
+            for sct in ws:
+                weight(lay, sct)
+        raw = b"".join(bytes(r) for r in recs)
+        dev = self.fwd[0].w_simt.device
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev), len(recs)
+
     def refresh(self):
         key = self.blk._key()
         if key == self.key:
@@ -272,7 +308,19 @@ class _TrainBlock:
                 self.fwd, self.dgrad = self._build()
                 self.src_fwd, self.src_dgrad = self._sources()
                 self.kinv = torch.tensor(_convT_kflat(self.blk.nd), device=self.fwd[0].w_simt.device).argsort()
-            else:
+                self._table, self._table_ptrs = None, None
+                if self.fwd[0].w_simt.is_cuda:          # built here, outside any CUDA-graph capture (it is a host-to-device copy)
+                    self._table, self._table_ptrs = self._record_table(), tuple(p.data_ptr() for p in self.blk.parameters())
+            elif self.fwd[0].w_simt.is_cuda:
+                ptrs = tuple(p.data_ptr() for p in self.blk.parameters())
+                if self._table is None or self._table_ptrs != ptrs:         # parameters moved (load_state_dict keeps them, .to() may not)
+                    self._table, self._table_ptrs = self._record_table(), ptrs
+                tab, n = self._table
+                with ops._on(tab.device), ops._span("conv_refresh"):
+                    _C.check(_C.lib().ofsv_conv_refresh_tapform(_p(tab), n, _stream()))
+                for lay in self.fwd + self.dgrad:
+                    lay._packed.clear()
+            else:                                                           # tests/test_train_host.py: the same refresh with torch ops
                 for lay, (ws, bs, ps) in zip(self.fwd, self.src_fwd):
                     for sct in ws:
                         sct.apply(lay.w_simt)

@@ -345,3 +345,25 @@ def test_upflow_net_vs_reference_record(tag, sgu):
     assert of.shape == (1, 1, 128, 192) and float(of.min()) >= 0 and float(of.max()) <= 1
     rf, rb = ur.occ_check_ref(ff.cpu(), fb.cpu())
     assert float((of.cpu() - rf).abs().mean()) <= 2e-3           # thresholded: a few pixels may sit on the threshold
+
+
+@pytest.mark.parametrize("nd,c", [(3, 64), (3, 128), (2, 96)])
+def test_train_block_refresh_kernel_equals_rebuild(nd, c):
+    """ofsv_conv_refresh_tapform (one launch for the 24 layers of a block) == the tap forms of a fresh build, exactly."""
+    from opticalflowscivis_b200 import ifnet, train
+    torch.manual_seed(5)
+    blk = ifnet.IFBlock(nd, 6 + 2 * nd, c=c).to(_dev())
+    tb = train._TrainBlock(blk)
+    tb.refresh()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    tb.refresh()
+    assert tb._table is not None
+    fresh = train._TrainBlock(blk)
+    fresh.refresh()
+    for kind in ("fwd", "dgrad"):
+        for li, (a, b) in enumerate(zip(getattr(tb, kind), getattr(fresh, kind))):
+            assert torch.equal(a.w_simt, b.w_simt), (kind, li)
+            assert torch.equal(a.bias, b.bias), (kind, li)
+            assert (a.prelu is None) == (b.prelu is None) and (a.prelu is None or torch.equal(a.prelu, b.prelu)), (kind, li)
