@@ -135,14 +135,16 @@ struct WgTile {
   static constexpr int WMT = MT / WM, WNT = NT / WN;     // warp tile
   static_assert(WMT % 16 == 0 && WNT % 8 == 0, "warp tile");
   static constexpr int XP = MT * 2 + 16, GP = NT * 2 + 16;   // row pitches in bytes (+16: ldmatrix rows fall in distinct banks)
-  static constexpr int STAGE = WG_KC * (XP + GP);
+  static constexpr int KC = 64;                               // positions per pipeline stage (four k16 MMA steps)
+  static constexpr int STAGE = KC * (XP + GP);
 };
 
 template <int MT, int NT>
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   using TL = WgTile<MT, NT>;
   __shared__ __align__(16) unsigned char smem[2 * TL::STAGE];
-  __shared__ int xrow_tab[2][WG_KC], grow_tab[2][WG_KC];
+  constexpr int KC = TL::KC;
+  __shared__ int xrow_tab[2][KC], grow_tab[2][KC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int tile = blockIdx.x;
@@ -154,13 +156,13 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
   const int oz = p.tap[tap][0], oy = p.tap[tap][1], ox = p.tap[tap][2];
   const int64_t k_begin = (int64_t)blockIdx.y * p.Kper;
   const int64_t k_end = min(p.K, k_begin + p.Kper);
-  const int nchunk = (int)((k_end - k_begin + WG_KC - 1) / WG_KC);
+  const int nchunk = (int)((k_end - k_begin + KC - 1) / KC);
 
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 
   auto fill_table = [&](int chunk) {                      // threads 0..31: source rows of the positions of `chunk`
-    if (tid < WG_KC) {
-      const int64_t q = k_begin + (int64_t)chunk * WG_KC + tid;
+    if (tid < KC) {
+      const int64_t q = k_begin + (int64_t)chunk * KC + tid;
       int xr = -1, gr = -1;
       if (q < k_end) {
         int r = (int)q;
@@ -179,17 +181,17 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
   auto issue_loads = [&](int chunk) {
     const uint32_t st = sbase + (chunk & 1) * TL::STAGE;
     constexpr int XPIECES = MT / 8, GPIECES = NT / 8;
-    for (int i = tid; i < WG_KC * XPIECES; i += WG_THREADS) {
+    for (int i = tid; i < KC * XPIECES; i += WG_THREADS) {
       const int row = i / XPIECES, pc = i % XPIECES;
       const int xr = xrow_tab[chunk & 1][row];
       const __nv_bfloat16* src = xr >= 0 ? p.x + (int64_t)xr * p.Cin_s + mtile * MT + pc * 8 : p.x;
       cp_async16(st + row * TL::XP + pc * 16, src, xr >= 0 ? 16 : 0);
     }
-    for (int i = tid; i < WG_KC * GPIECES; i += WG_THREADS) {
+    for (int i = tid; i < KC * GPIECES; i += WG_THREADS) {
       const int row = i / GPIECES, pc = i % GPIECES;
       const int gr = grow_tab[chunk & 1][row];
       const __nv_bfloat16* src = gr >= 0 ? p.g + (int64_t)gr * p.g_cs + ntile * NT + pc * 8 : p.g;
-      cp_async16(st + WG_KC * TL::XP + row * TL::GP + pc * 16, src, gr >= 0 ? 16 : 0);
+      cp_async16(st + KC * TL::XP + row * TL::GP + pc * 16, src, gr >= 0 ? 16 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -222,9 +224,9 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
       __syncthreads();                                     // chunk c landed for every thread; table slot c&1 is free again
       if (c + 2 < nchunk) fill_table(c + 2);
       if (active) {
-        const uint32_t xs = sbase + (c & 1) * TL::STAGE, gs = xs + WG_KC * TL::XP;
+        const uint32_t xs = sbase + (c & 1) * TL::STAGE, gs = xs + KC * TL::XP;
 #pragma unroll
-        for (int ks = 0; ks < WG_KC / 16; ++ks) {
+        for (int ks = 0; ks < KC / 16; ++ks) {
           uint32_t afr[MI][4];
           const int mat = lane >> 3, r = lane & 7;
 #pragma unroll
@@ -575,7 +577,7 @@ extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, cons
   const int MT = pl.MT, NT = pl.NT;
   p.mt = d->Cin_s / MT; p.nt = d->Cout_w / NT;
   p.K = (int64_t)p.N * p.Do * p.Ho * p.Wo;
-  p.Kper = cdiv(cdiv(p.K, splits), WG_KC) * WG_KC;
+  p.Kper = cdiv(cdiv(p.K, splits), 64) * 64;              // a multiple of both kernels' chunk sizes
   for (int i = 0; i < p.T; ++i)
     for (int j = 0; j < 4; ++j) p.tap[i][j] = d->tap_off[i][j];
   if (d->nd == 2)

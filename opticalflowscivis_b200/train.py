@@ -110,7 +110,7 @@ def prelu_bias_bwd(gy, y, slope):
         dslope = torch.empty(cs, device=gy.device, dtype=torch.float32) if slope is not None else None
         gpre = torch.empty_like(gy) if slope is not None else gy
         with ops._span("prelu_bias_bwd"):
-            _C.check(L.ofsv_prelu_bias_bwd_bf16(    _p(gy), _p(y), _p(slope), _p(gpre), _p(dbias), _p(dslope), _p(work), rows, cs, _stream()))
+            _C.check(L.ofsv_prelu_bias_bwd_bf16(_p(gy), _p(y), _p(slope), _p(gpre), _p(dbias), _p(dslope), _p(work), rows, cs, _stream()))
     return gpre, dbias, dslope
 
 
@@ -169,9 +169,10 @@ class _TrainBlock:
     layer, the tap-form layer that computes its input gradient.
 
     The layers are BUILT once (`_build`: the per-tap Python loops of ifnet._pack_* / _conv_layer / _convT_phase_layer, ~100 small
-    torch launches per layer) and REFRESHED whenever a parameter changes — every training step — by `_Source` records: one
-    index_select over the flattened kernel axis plus one strided copy per parameter tensor, then the library re-packs the bf16
-    operand blocks (one launch per layer).  tests/test_train_host.py checks refresh == rebuild exactly."""
+    torch launches per layer) and REFRESHED whenever a parameter changes — every training step — from `_Source` records (which
+    parameter tensor, in which orientation and tap order, lands where in a layer's tap form): ONE ofsv_conv_refresh_tapform launch
+    for the 24 layers of the block, then the library re-packs the bf16 operand blocks (one launch per layer).  On CPU tensors (the
+    wiring tests) the same records are applied with torch ops.  tests check refresh == rebuild exactly for both."""
 
     class _Source:
         """w_simt[:, ci0:ci0+a, co0:co0+b] = W[kidx] with W = param viewed [K][a][b] (perm = the permute of (A, B, K) that gets there);
