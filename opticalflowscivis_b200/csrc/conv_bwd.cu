@@ -9,9 +9,13 @@
 //                              along K with a fixed-order second pass (deterministic, no atomics).
 // The INPUT gradient of every layer type is itself a tap-form convolution (conv <-> transposed conv with the same weights) and
 // runs on the forward engines (ofsv_conv_halo / ofsv_conv_tc) — opticalflowscivis_b200/train.py builds those descriptors.
-#include <mutex>
+#include <algorithm>
+#include <cstring>
+
+#include <cuda.h>
 
 #include "ofsv_common.cuh"
+#include "tc_common.cuh"
 
 namespace ofsv {
 namespace {
@@ -426,6 +430,141 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tg_kernel(const __grid_
   }
 }
 
+// ---- brick-window variant ----------------------------------------------------------------------------------------------------
+// The two kernels above load the input row of every (position, tap) separately: 64 taps read the input 64 times (2.1 GB of L2 -> SM
+// traffic for the heads of a 64^3 block, 0.53 ms).  Here a CTA owns a 16 x 16 channel tile for ALL taps and walks BRICKS of 4 x 4 x 4
+// (2-D: 8 x 8) output positions: the input WINDOW a brick can touch (6^3 rows for a 3^3 / transposed layer, 10^3 for a 4^3 stride-2
+// conv) and the brick's gradient rows are staged in shared memory once, and every tap's A fragment is an ldmatrix whose eight row
+// addresses are window rows — window row = (position part) + (tap part), both linear, so a tap costs one add per fragment.  The
+// eight warps split the taps (<= 8 each: 64 accumulator registers), double-buffered windows, fixed-order K split as above.
+// Measured on the layers of one 8 x 64^3 step (tests/bench_wgrad.py, profiles/r02x_bench_wgrad.txt): the windows cut the L2 -> SM
+// bytes 6-17x, but with 16-channel tiles every window row is a 32-byte request and the kernel is bound by the REQUEST rate of the
+// TMA unit (and of cp.async before it: the same times): heads 458 us vs 535 us for the tap-group kernel, conv0.0 246 vs 232, the
+// 64-channel layers 1.7-2.6x slower.  Policy: -1 (default) = only where it wins (Cout_w == 16 and >= 32 taps: the heads);
+// ofsv_set_tuning("wgrad_brick", 1 | 0) forces it on (wherever the windows fit) / off.
+std::atomic<int> g_wgrad_brick{-1};
+constexpr int WB_THREADS = 256, WB_PITCH = 32;    // window rows are the 16 channels of the tile: dense, as TMA writes them
+
+struct WbParams {
+  float* out;
+  int N, Cin_s, Cout_w;
+  int s, os, T, ntaps, mt, nt;
+  int lby, lbx, bz, by, bx;         // brick dims (bz * by * bx == 64) and log2 of by, bx
+  int nbz, nby, nbx, nbricks;       // bricks per axis, N * nbz * nby * nbx
+  int ominz, ominy, ominx;          // smallest tap offset per axis
+  int wz, wy, wx, gz, gy, gx;       // window dims (rows) of the input and of the gradient
+  int8_t tap[OFSV_MAX_TAPS][4];
+};
+
+__global__ void __launch_bounds__(WB_THREADS) conv_wgrad_brick_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                                                                       const __grid_constant__ WbParams p) {
+  extern __shared__ __align__(128) unsigned char wsmem[];
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntile = blockIdx.x % p.nt, mtile = blockIdx.x / p.nt;
+  const int xrows = p.wz * p.wy * p.wx, grows = p.gz * p.gy * p.gx;
+  const int xbytes = (xrows * WB_PITCH + 127) & ~127;                 // TMA destinations are 128-byte aligned
+  const int stage_bytes = xbytes + ((grows * WB_PITCH + 127) & ~127);
+  const uint32_t sbase = (smem_u32(wsmem) + 127u) & ~127u;
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // one thread issues the two window loads of a brick: a 5-D box each, out-of-volume rows zero-filled by the TMA unit
+  auto issue = [&](int brick, int st) {
+    int r = brick;
+    const int bxi = r % p.nbx; r /= p.nbx;
+    const int byi = r % p.nby; r /= p.nby;
+    const int bzi = r % p.nbz; const int n = r / p.nbz;
+    const uint32_t xs = sbase + st * stage_bytes, gs = xs + xbytes;
+    mbar_expect_tx(&full[st], (uint32_t)((xrows + grows) * WB_PITCH));
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(xs),
+                 "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full[st])), "r"(mtile * 16), "r"(p.s * bxi * p.bx + p.ominx),
+                 "r"(p.s * byi * p.by + p.ominy), "r"(p.s * bzi * p.bz + p.ominz), "r"(n)
+                 : "memory");
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(gs),
+                 "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&full[st])), "r"(ntile * 16), "r"(p.os * bxi * p.bx), "r"(p.os * byi * p.by),
+                 "r"(p.os * bzi * p.bz), "r"(n)
+                 : "memory");
+  };
+
+  // per-lane position parts of the fragment row addresses, for the four k16 steps of a brick (64 positions)
+  const int mat = lane >> 3, r8 = lane & 7;
+  uint32_t a_pos[4], b_pos[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int pa = ks * 16 + (mat >> 1) * 8 + r8;          // A: matrices (m-block, k-block) = (mat & 1, mat >> 1)
+    const int az = pa >> (p.lby + p.lbx), ay = (pa >> p.lbx) & (p.by - 1), ax = pa & (p.bx - 1);
+    a_pos[ks] = (uint32_t)(((p.s * az) * p.wy + p.s * ay) * p.wx + p.s * ax) * WB_PITCH + (mat & 1) * 16;
+    const int pb = ks * 16 + (mat & 1) * 8 + r8;           // B: matrices (k-block, n8-tile) = (mat & 1, mat >> 1)
+    const int bz_ = pb >> (p.lby + p.lbx), by_ = (pb >> p.lbx) & (p.by - 1), bx_ = pb & (p.bx - 1);
+    b_pos[ks] = (uint32_t)(((p.os * bz_) * p.gy + p.os * by_) * p.gx + p.os * bx_) * WB_PITCH + (mat >> 1) * 16;
+  }
+  // this warp's taps: tap = warp + 8 j; tap parts of the addresses
+  uint32_t a_tap[8], b_tap[8];
+  int ntw = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int tap = warp + 8 * j;
+    a_tap[j] = b_tap[j] = 0;
+    if (tap < p.T) {
+      ntw = j + 1;
+      const int ph = tap / p.ntaps;
+      a_tap[j] = (uint32_t)(((p.tap[tap][0] - p.ominz) * p.wy + (p.tap[tap][1] - p.ominy)) * p.wx + (p.tap[tap][2] - p.ominx)) * WB_PITCH;
+      b_tap[j] = (uint32_t)((((ph >> 2) & 1) * p.gy + ((ph >> 1) & 1)) * p.gx + (ph & 1)) * WB_PITCH;
+    }
+  }
+  float acc[8][2][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][b][c] = 0.f;
+
+  int brick = blockIdx.y, it = 0;
+  if (tid == 0 && brick < p.nbricks) issue(brick, 0);
+  for (; brick < p.nbricks; brick += gridDim.y, ++it) {
+    const int st = it & 1;
+    if (tid == 0 && brick + (int)gridDim.y < p.nbricks) issue(brick + gridDim.y, st ^ 1);   // stage st^1 was released by the barrier below
+    mbar_wait(&full[st], (uint32_t)(it >> 1) & 1u);
+    const uint32_t xs = sbase + st * stage_bytes, gs = xs + xbytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < ntw) {                                        // warp-uniform
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t afr[4], b0, b1, b2, b3;
+          ldmatrix_x4_t(xs + a_pos[ks] + a_tap[j], afr[0], afr[1], afr[2], afr[3]);
+          ldmatrix_x4_t(gs + b_pos[ks] + b_tap[j], b0, b1, b2, b3);
+          mma_bf16_16816(acc[j][0], afr, b0, b1);
+          mma_bf16_16816(acc[j][1], afr, b2, b3);
+        }
+      }
+    }
+    __syncthreads();                                        // every warp is done with stage st before it is loaded again
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int tap = warp + 8 * j;
+    if (tap >= p.T) continue;
+    float* out = p.out + (((int64_t)blockIdx.y * p.T + tap) * p.Cin_s + mtile * 16) * p.Cout_w + ntile * 16;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int col = b * 8 + 2 * t;
+      *reinterpret_cast<float2*>(out + (int64_t)g * p.Cout_w + col) = make_float2(acc[j][b][0], acc[j][b][1]);
+      *reinterpret_cast<float2*>(out + (int64_t)(g + 8) * p.Cout_w + col) = make_float2(acc[j][b][2], acc[j][b][3]);
+    }
+  }
+}
+
 __global__ void conv_wgrad_finalize(const float4* __restrict__ work, float4* __restrict__ dw, int64_t n4, int splits) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -462,9 +601,50 @@ int tg_tpw(int MT, int NT) {
   const int per_tap = (MT / 16) * (NT / 8) * 4;
   return per_tap > 64 ? 0 : (64 / per_tap > 4 ? 4 : 64 / per_tap);
 }
-struct WgPlan { int MT, NT, tpw, ngroups, splits; int64_t tiles; };
+struct WgPlan { int MT, NT, tpw, ngroups, splits; int64_t tiles; bool brick; WbParams wb; size_t wb_smem; };
+// Brick-window kernel: any layer with >= 4 taps whose windows fit shared memory (all layers of the IFBlocks do).
+bool wgrad_brick_plan(const ofsv_conv_desc* d, WbParams* w, size_t* smem) {
+  const int T = d->nphase * d->ntaps;
+  if (d->ntaps < 4 || T > OFSV_MAX_TAPS) return false;
+  int omin[3] = {127, 127, 127}, omax[3] = {-127, -127, -127};
+  for (int i = 0; i < T; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const int o = (d->nd == 2 && a == 0) ? 0 : d->tap_off[i][a];
+      omin[a] = std::min(omin[a], o); omax[a] = std::max(omax[a], o);
+    }
+  memset(w, 0, sizeof(*w));
+  w->s = d->in_stride; w->os = d->out_stride; w->T = T; w->ntaps = d->ntaps;
+  if (d->nd == 3) { w->bz = 4; w->by = 4; w->bx = 4; w->lby = 2; w->lbx = 2; }
+  else { w->bz = 1; w->by = 8; w->bx = 8; w->lby = 3; w->lbx = 3; }
+  const int Do = d->nd == 2 ? 1 : d->Do;
+  w->nbz = (int)cdiv(Do, w->bz); w->nby = (int)cdiv(d->Ho, w->by); w->nbx = (int)cdiv(d->Wo, w->bx);
+  const int64_t nb = (int64_t)d->N * w->nbz * w->nby * w->nbx;
+  if (nb >= (1ll << 31)) return false;
+  w->nbricks = (int)nb;
+  w->ominz = omin[0]; w->ominy = omin[1]; w->ominx = omin[2];
+  w->wz = w->s * (w->bz - 1) + omax[0] - omin[0] + 1;
+  w->wy = w->s * (w->by - 1) + omax[1] - omin[1] + 1;
+  w->wx = w->s * (w->bx - 1) + omax[2] - omin[2] + 1;
+  const int span = d->nphase > 1 ? w->os : 1;
+  w->gz = d->nd == 2 ? 1 : w->os * (w->bz - 1) + span;
+  w->gy = w->os * (w->by - 1) + span;
+  w->gx = w->os * (w->bx - 1) + span;
+  const size_t xb = ((size_t)w->wz * w->wy * w->wx * WB_PITCH + 127) & ~(size_t)127, gb = ((size_t)w->gz * w->gy * w->gx * WB_PITCH + 127) & ~(size_t)127;
+  *smem = 2 * (xb + gb) + 128;                             // + alignment slack
+  return *smem <= 200 * 1024 && w->wx <= 256 && w->wy <= 256 && w->wz <= 256 && w->gx <= 256 && w->gy <= 256 && w->gz <= 256;
+}
 WgPlan wgrad_plan(const ofsv_conv_desc* d) {
   WgPlan pl;
+  const int64_t K = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+  const int mode = g_wgrad_brick.load(std::memory_order_relaxed);
+  pl.brick = (mode > 0 || (mode < 0 && d->Cout_w == 16 && d->nphase * d->ntaps >= 32)) && wgrad_brick_plan(d, &pl.wb, &pl.wb_smem);
+  if (pl.brick) {
+    pl.MT = pl.NT = 16; pl.tpw = 0; pl.ngroups = 0;
+    pl.tiles = (int64_t)(d->Cin_s / 16) * (d->Cout_w / 16);
+    const int64_t want = cdiv((int64_t)device_num_sms() * 2, pl.tiles);
+    pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, pl.wb.nbricks), 64));
+    return pl;
+  }
   pl.MT = tile_of(d->Cin_s); pl.NT = tile_of(d->Cout_w);
   pl.tpw = d->ntaps >= 4 ? tg_tpw(pl.MT, pl.NT) : 0;
   const int64_t mn = (int64_t)(d->Cin_s / pl.MT) * (d->Cout_w / pl.NT);
@@ -475,7 +655,6 @@ WgPlan wgrad_plan(const ofsv_conv_desc* d) {
     pl.ngroups = 0;
     pl.tiles = (int64_t)d->nphase * d->ntaps * mn;
   }
-  const int64_t K = (int64_t)d->N * d->Do * d->Ho * d->Wo;
   const int64_t want = cdiv((int64_t)device_num_sms() * (pl.tpw ? 4 : 8), pl.tiles);
   int64_t s = std::min<int64_t>(want, cdiv(K, 8 * WG_KC));
   pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
@@ -496,6 +675,7 @@ int launch_wgrad_tg(const WgradParams& p, dim3 grid, int ngroups, cudaStream_t s
 }
 
 }  // namespace
+void ofsv_set_wgrad_brick(int v) { g_wgrad_brick.store(v, std::memory_order_relaxed); }
 }  // namespace ofsv
 
 namespace ofsv {
@@ -562,9 +742,52 @@ extern "C" int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, cons
   OFSV_REQUIRE(x && gy && dw, "conv_wgrad: null pointer");
   OFSV_REQUIRE(gy_cs >= d->Cout_w && gy_cs % 8 == 0, "conv_wgrad: gy_cs (%d) must be a multiple of 8 and >= Cout_w (%d)", gy_cs, d->Cout_w);
   OFSV_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(dw) && (!work || aligned16(work)), "conv_wgrad: pointers must be 16-byte aligned");
-  const WgPlan pl = wgrad_plan(d);
+  WgPlan pl = wgrad_plan(d);
   const int splits = pl.splits;
   OFSV_REQUIRE(splits == 1 || work, "conv_wgrad: %d K splits need a work buffer of ofsv_conv_wgrad_splits(d) * T * Cin_s * Cout_w floats", splits);
+  if (pl.brick) {
+    WbParams& w = pl.wb;
+    w.out = splits == 1 ? dw : work;
+    w.N = d->N; w.Cin_s = d->Cin_s; w.Cout_w = d->Cout_w;
+    w.mt = d->Cin_s / 16; w.nt = d->Cout_w / 16;
+    for (int i = 0; i < w.T; ++i) {
+      for (int j = 0; j < 4; ++j) w.tap[i][j] = d->tap_off[i][j];
+      if (d->nd == 2) w.tap[i][0] = 0;
+    }
+    PFN_encodeTiled encode = get_tensor_map_encoder();
+    if (!encode) { set_error("ofsv_conv_wgrad_bf16: cuTensorMapEncodeTiled unavailable (driver too old?)"); return OFSV_ECUDA; }
+    CUtensorMap tmX, tmG;
+    {
+      const int Di = d->nd == 2 ? 1 : d->Di, Dy = d->nd == 2 ? 1 : d->Dy;
+      const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      const cuuint64_t xdim[5] = {(cuuint64_t)d->Cin_s, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)Di, (cuuint64_t)d->N};
+      const cuuint64_t xstr[4] = {(cuuint64_t)d->Cin_s * 2, (cuuint64_t)d->Wi * d->Cin_s * 2, (cuuint64_t)d->Hi * d->Wi * d->Cin_s * 2,
+                                  (cuuint64_t)Di * d->Hi * d->Wi * d->Cin_s * 2};
+      const cuuint32_t xbox[5] = {16, (cuuint32_t)w.wx, (cuuint32_t)w.wy, (cuuint32_t)w.wz, 1};
+      CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xdim, xstr, xbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("ofsv_conv_wgrad_bf16: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return OFSV_ECUDA; }
+      const cuuint64_t gdim[5] = {(cuuint64_t)gy_cs, (cuuint64_t)d->Wy, (cuuint64_t)d->Hy, (cuuint64_t)Dy, (cuuint64_t)d->N};
+      const cuuint64_t gstr[4] = {(cuuint64_t)gy_cs * 2, (cuuint64_t)d->Wy * gy_cs * 2, (cuuint64_t)d->Hy * d->Wy * gy_cs * 2,
+                                  (cuuint64_t)Dy * d->Hy * d->Wy * gy_cs * 2};
+      const cuuint32_t gbox[5] = {16, (cuuint32_t)w.gx, (cuuint32_t)w.gy, (cuuint32_t)w.gz, 1};
+      r = encode(&tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(gy), gdim, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("ofsv_conv_wgrad_bf16: cuTensorMapEncodeTiled(gy) failed with %d", (int)r); return OFSV_ECUDA; }
+    }
+    static std::atomic<uint64_t> attr_done{0};
+    if (int e = ensure_dyn_smem(attr_done, conv_wgrad_brick_kernel, 200 * 1024, "ofsv_conv_wgrad_bf16")) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    conv_wgrad_brick_kernel<<<dim3((unsigned)pl.tiles, (unsigned)splits), WB_THREADS, pl.wb_smem, st>>>(tmX, tmG, w);
+    rc = check_launch("conv_wgrad_brick_kernel");
+    if (rc) return rc;
+    if (splits > 1) {
+      const int64_t n4 = (int64_t)w.T * w.Cin_s * w.Cout_w / 4;
+      conv_wgrad_finalize<<<(unsigned)cdiv(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(work), reinterpret_cast<float4*>(dw), n4, splits);
+      rc = check_launch("conv_wgrad_finalize");
+    }
+    return rc;
+  }
   WgradParams p;
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.g = static_cast<const __nv_bfloat16*>(gy);

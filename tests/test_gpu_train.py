@@ -55,18 +55,29 @@ def _layers(nd):
     for c in ((64, 128) if nd == 3 else (64, 96)):
         blk = ifnet.IFBlock(nd, 5 + 2 * nd, c=c)
         L = blk.layers()
-        s = 16
+        s = 24 if c == 64 else 16          # 24: grids of 12 / 6 positions per axis = partial bricks of the brick-window kernel
         out += [(f"c{c}.conv0.0", L[0], s), (f"c{c}.conv0.1", L[1], s // 2), (f"c{c}.convblock", L[2], s // 4),
                 (f"c{c}.convT", L[10], s // 4), (f"c{c}.heads", L[11], s // 2)]
     return out
 
 
+@pytest.mark.parametrize("brick", [1, 0])
 @pytest.mark.parametrize("nd", [2, 3])
-def test_conv_wgrad_kernel_vs_fp32_evaluator(nd):
-    from opticalflowscivis_b200 import _C, train
+def test_conv_wgrad_kernel_vs_fp32_evaluator(nd, brick):
+    """brick = 1: the brick-window kernel wherever its windows fit; 0: the per-tap / tap-group kernels (ofsv_set_tuning('wgrad_brick', v);
+    the default policy -1 mixes them per layer and is what every other test runs)."""
+    from opticalflowscivis_b200 import _C, ops, train
     torch.manual_seed(nd)
     dev = _dev()
     n = 2
+    ops.set_tuning("wgrad_brick", brick)
+    try:
+        _wgrad_cases(nd, n, dev, _C, train)
+    finally:
+        ops.set_tuning("wgrad_brick", -1)
+
+
+def _wgrad_cases(nd, n, dev, _C, train):
     for name, lay, s in _layers(nd):
         in_sp = ((1,) if nd == 2 else ()) + (s,) * nd
         d, osp = lay.desc(n, in_sp, _C.BF16, has_residual=False)
