@@ -252,8 +252,47 @@ class UPFlowNet(nn.Module):
         flow_fine = self.context_networks.run(ctx_in, ctx_map, n, (1, h, w))
         return flow_up, flow_res + flow_fine
 
+    def enable_cuda_graphs(self, on=True):
+        """Replay `forward_2_frame_v3` from a CUDA graph captured per input shape: a call is ~520 libofsv launches plus the torch
+        layout copies, more host time than GPU time at 256 x 832.  Same numerics; the inputs are copied into graph-owned buffers
+        and the returned tensors are the graph's outputs, overwritten by the next call with the same shape (clone what you keep).
+        Graphs are dropped when a parameter changes."""
+        self._graphs = {} if on else None
+        return self
+
     @torch.no_grad()
     def forward_2_frame_v3(self, x1_raw, x2_raw, if_loss=False):
+        graphs = getattr(self, "_graphs", None)
+        if graphs is None:
+            return self._forward_2_frame_v3(x1_raw, x2_raw)
+        x1_raw, x2_raw = ops._cuda_f32(x1_raw, "x1_raw"), ops._cuda_f32(x2_raw, "x2_raw")
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if graphs.get("sig") != sig:
+            graphs.clear()
+            graphs["sig"] = sig
+        key = (tuple(x1_raw.shape), x1_raw.device.index)
+        ent = graphs.get(key)
+        if ent is None:
+            a, b = x1_raw.clone(), x2_raw.clone()
+            cur = torch.cuda.current_stream(a.device)
+            side = torch.cuda.Stream(device=a.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                   # warm-up off the capture: packed weights, engine choice, kernel attributes
+                for _ in range(2):
+                    self._forward_2_frame_v3(a, b)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_2_frame_v3(a, b)
+            ent = graphs[key] = (g, a, b, out)
+        g, a, b, out = ent
+        a.copy_(x1_raw)
+        b.copy_(x2_raw)
+        g.replay()
+        return out
+
+    @torch.no_grad()
+    def _forward_2_frame_v3(self, x1_raw, x2_raw):
         x1_raw, x2_raw = ops._cuda_f32(x1_raw, "x1_raw"), ops._cuda_f32(x2_raw, "x2_raw")
         if x1_raw.dim() != 4 or x1_raw.shape[1] != 3 or x2_raw.shape != x1_raw.shape:
             raise ValueError(f"UPFlowNet: expected two (B,3,H,W) images, got {tuple(x1_raw.shape)} / {tuple(x2_raw.shape)}")

@@ -352,6 +352,12 @@ def test_upflow_net_vs_reference_record(tag, sgu):
     err = float(np.abs(ff[:, :, ::4, ::4].cpu().numpy() - ref).mean())
     print(f"UPFlowNet ({tag}) free-running: mean |flow error| {err:.3e} px at mean |flow| {float(np.abs(ref).mean()):.3f} px")
     assert err <= 0.1 * float(np.abs(ref).mean())
+    if not sgu:                                                  # CUDA-graph replay: same kernels, same results
+        net.enable_cuda_graphs()
+        for _ in range(2):
+            gf, gb, gflows = net.forward_2_frame_v3(im1, im2)
+        assert torch.equal(gf, ff) and torch.equal(gb, fb) and torch.equal(gflows[0][0], flows[0][0])
+        net.enable_cuda_graphs(False)
     of, ob = unet.occ_check(ff, fb)
     assert of.shape == (1, 1, 128, 192) and float(of.min()) >= 0 and float(of.max()) <= 1
     rf, rb = ur.occ_check_ref(ff.cpu(), fb.cpu())
