@@ -19,36 +19,33 @@ from .ifnet_ref import IFNetRef
 
 # ------------------------------------------------------------------------------------------------ Flow-2D/model/laplacian.py
 def _gauss_kernel(channels, device):
-    k = torch.tensor([[1., 4., 6., 4., 1], [4., 16., 24., 16., 4.], [6., 24., 36., 24., 6.], [4., 16., 24., 16., 4.], [1., 4., 6., 4., 1.]])
-    k /= 256.
-    return k.repeat(channels, 1, 1, 1).to(device)
+    """laplacian.py:10-19: the 5x5 binomial kernel [1 4 6 4 1] (x) [1 4 6 4 1] / 256, one copy per channel (depth-wise)."""
+    b = torch.tensor([1., 4., 6., 4., 1.])
+    return (torch.outer(b, b) / 256.).repeat(channels, 1, 1, 1).to(device)
 
 
 def _conv_gauss(img, kernel):
-    img = F.pad(img, (2, 2, 2, 2), mode="reflect")
-    return F.conv2d(img, kernel, groups=img.shape[1])
+    """laplacian.py:33-36: reflect-pad by 2, depth-wise 5x5 convolution."""
+    return F.conv2d(F.pad(img, (2, 2, 2, 2), mode="reflect"), kernel, groups=img.shape[1])
 
 
 def _upsample(x):
-    dev = x.device
-    cc = torch.cat([x, torch.zeros(x.shape[0], x.shape[1], x.shape[2], x.shape[3], device=dev)], dim=3)
-    cc = cc.view(x.shape[0], x.shape[1], x.shape[2] * 2, x.shape[3])
-    cc = cc.permute(0, 1, 3, 2)
-    cc = torch.cat([cc, torch.zeros(x.shape[0], x.shape[1], x.shape[3], x.shape[2] * 2, device=dev)], dim=3)
-    cc = cc.view(x.shape[0], x.shape[1], x.shape[3] * 2, x.shape[2] * 2)
-    x_up = cc.permute(0, 1, 3, 2)
-    return _conv_gauss(x_up, 4 * _gauss_kernel(x.shape[1], dev))
+    """laplacian.py:24-31 builds the zero-interleaved 2x image with two cat/view/permute round trips; the result is x at the even
+    (row, column) positions and zeros elsewhere, then 4 * Gaussian."""
+    n, c, h, w = x.shape
+    up = x.new_zeros((n, c, 2 * h, 2 * w))
+    up[:, :, ::2, ::2] = x
+    return _conv_gauss(up, 4 * _gauss_kernel(c, x.device))
 
 
 def _laplacian_pyramid(img, kernel, max_levels):
+    """laplacian.py:38-57: level = current - upsample(downsample(blur(current))), cropped to the common size; next = the down-sample."""
     current, pyr = img, []
     for _ in range(max_levels):
-        filtered = _conv_gauss(current, kernel)
-        down = filtered[:, :, ::2, ::2]
+        down = _conv_gauss(current, kernel)[:, :, ::2, ::2]
         up = _upsample(down)
         h, w = min(current.shape[2], up.shape[2]), min(current.shape[3], up.shape[3])
-        current, up = current[:, :, :h, :w], up[:, :, :h, :w]
-        pyr.append(current - up)
+        pyr.append(current[:, :, :h, :w] - up[:, :, :h, :w])
         current = down
     return pyr
 
