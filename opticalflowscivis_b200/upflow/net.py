@@ -15,8 +15,6 @@ Parameter containers with the reference's `state_dict()` keys (`feature_pyramid_
 """
 from __future__ import annotations
 
-import types
-
 import torch
 import torch.nn as nn
 

@@ -6,15 +6,13 @@ Tolerances: the kernels take bf16 operands and accumulate in fp32, so against an
 they agree to summation-order noise (1e-3 relative to the tensor's largest entry); against the fp32 oracle the bf16 storage of
 activations and gradients shows up: per-tensor gradient cosine >= 0.99 (>= 0.98 for the whole net in one vector is never needed —
 the measured values are printed), losses within 2e-3 relative."""
-import ctypes
 import os
 
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
-from test_train_host import _cl, _pad_c, prelu_bias_bwd_eval, wgrad_eval
+from test_train_host import prelu_bias_bwd_eval, wgrad_eval
 
 pytestmark = pytest.mark.gpu
 
