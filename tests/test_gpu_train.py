@@ -382,3 +382,40 @@ def test_train_block_refresh_kernel_equals_rebuild(nd, c):
             assert torch.equal(a.w_simt, b.w_simt), (kind, li)
             assert torch.equal(a.bias, b.bias), (kind, li)
             assert (a.prelu is None) == (b.prelu is None) and (a.prelu is None or torch.equal(a.prelu, b.prelu)), (kind, li)
+
+
+@pytest.mark.parametrize("nd,sp", [(3, (32, 48, 64)), (2, (96, 160))])
+def test_training_gradients_noncubic_vs_oracle(nd, sp):
+    """Forward with the teacher block + backward on a non-cubic volume / non-square frame (the 3-D warp then runs on the gather
+    kernel, the weight-gradient bricks and tiles are partial along some axes): first-step gradients against the fp32 oracle's."""
+    from opticalflowscivis_b200 import ifnet, train
+    from oracle.ifnet_ref import IFNetRef
+    dev = _dev()
+    torch.manual_seed(1234)
+    ref = IFNetRef(nd).to(dev)
+    net = ifnet.IFNet(nd).to(dev)
+    net.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(3)
+    base = torch.rand((2, 1) + tuple(s + 8 for s in sp), generator=g)
+    pool = torch.nn.functional.avg_pool3d if nd == 3 else torch.nn.functional.avg_pool2d
+    base = pool(base, 5, 1, 2).to(dev)
+    crop = lambda o: base[(slice(None), slice(None)) + tuple(slice(4, 4 + s) for s in sp[:-1]) + (slice(o, o + sp[-1]),)].contiguous()  # noqa: E731
+    x = torch.cat((crop(2), crop(6), crop(4)), 1)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        fr, mr, mgr, ftr, mtr, ldr = ref.forward_train(x)
+        loss_r = (mgr[2] - x[:, 2:3]).abs().mean() + (mtr - x[:, 2:3]).abs().mean() + 0.1 * ldr
+        loss_r.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    flow, mask, merged, flow_t, merged_t, ld = train.ifnet_forward_train(net, x)
+    loss = (merged[2] - x[:, 2:3]).abs().mean() + (merged_t - x[:, 2:3]).abs().mean() + 0.1 * ld
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_r.detach())) <= 2e-3 * abs(float(loss_r.detach()))
+    ga = torch.cat([p.grad.flatten() for p in net.parameters()])
+    gb = torch.cat([p.grad.flatten() for p in ref.parameters()])
+    c = _cos(ga, gb)
+    worst = min((_cos(p.grad, q.grad), k) for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()) if k.endswith("0.weight") or k.endswith("2.weight"))
+    print(f"non-cubic {sp}: gradient cosine {c:.5f}, worst weight tensor {worst}")
+    assert c >= 0.999 and worst[0] >= 0.98
