@@ -155,6 +155,14 @@ int ofsv_pack_block_input(const float* img0, const float* img1, const float* war
 /* s2d = 1: dst is the shifted space-to-depth tensor [N][Dn/2+1][Hn/2+1][Wn/2+1][2^nd][Cs] of the resized grid
  * (Dn,Hn,Wn) = (D,H,W)/scale (see ofsv_conv_desc.out_s2d); only interior sub-cells are written. */
 
+/* Layout changes between the reference's fp32 NC(D)HW tensors and the engine's channels-last bf16 activations, P = D*H*W pixels:
+ *   ofsv_pack_nhwc_bf16 : dst [N][P][Cs] bf16 = the channel concatenation of 1..4 sources [N][channels[i]][P] fp32 (host arrays of
+ *                         device pointers / channel counts), zero-padded to Cs — torch.cat + pad + cast in one pass, e.g. the
+ *                         estimator input torch.cat([corr, x_1x1, flow], 1) of UPFlow/model/upflow.py:657;
+ *   ofsv_unpack_nhwc_f32: dst [N][C][P] fp32 = the first C channels of src [N][P][Cs] bf16. */
+int ofsv_pack_nhwc_bf16(const float* const* srcs, const int* channels, int nsrc, void* dst, int N, int64_t P, int Cs, void* stream);
+int ofsv_unpack_nhwc_f32(const void* src, float* dst, int N, int64_t P, int Cs, int C, void* stream);
+
 /* Data edge: uint8 volume -> fp32, dst[i] = (float)src[i] / div with IEEE division (div = 255 reproduces
  * the reference loaders' `/ 255.`: Datasets/read_data.py, Flow-3D/load_datasets.py), so only bytes cross PCIe. */
 int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream);

@@ -69,6 +69,8 @@ _SIGS = {
     "ofsv_f32_to_u8": (_I, [_P, _P, _L, _F, _P]),
     "ofsv_sq_err_f64": (_I, [_P, _P, _P, _P, _I, _L, _F, _P]),
     "ofsv_ssim2d_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, ctypes.c_double, _P]),
+    "ofsv_pack_nhwc_bf16": (_I, [_P, _P, _I, _P, _I, _L, _I, _P]),
+    "ofsv_unpack_nhwc_f32": (_I, [_P, _P, _I, _L, _I, _I, _P]),
     "ofsv_pack_block_input": (_I, [_P] * 7 + [_I] * 9 + [_P]),
     "ofsv_conv_simt": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),

@@ -259,6 +259,94 @@ extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* fl
   return check_launch("head_upsample_add_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------ layout changes
+// NC(P) fp32 (P = product of the spatial dims) <-> channels-last bf16 [N][P][Cs], through a 32-pixel x 64-channel shared tile so that
+// both sides move 128-byte segments.  pack concatenates up to four sources along the channel axis (torch.cat + zero padding + cast
+// of the estimator input torch.cat([corr, x_1x1, flow], 1), UPFlow/model/upflow.py:657, in one pass) and zero-fills the padding.
+namespace ofsv {
+struct NhwcSrc { const float* p[4]; int c[4]; int nsrc; };
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const NhwcSrc S, __nv_bfloat16* __restrict__ dst, int64_t P, int Cs) {
+  __shared__ float tile[32][65];
+  const int n = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty: 8 channel rows per pass
+  for (int c0 = 0; c0 < Cs; c0 += 64) {
+    const int ncc = min(64, Cs - c0);
+    for (int cc = ty; cc < ncc; cc += 8) {
+      const int c = c0 + cc;
+      float v = 0.f;
+      if (p0 + tx < P) {
+        int base = 0;
+        for (int s = 0; s < S.nsrc; ++s) {
+          if (c >= base && c < base + S.c[s]) v = __ldg(S.p[s] + ((int64_t)n * S.c[s] + (c - base)) * P + p0 + tx);
+          base += S.c[s];
+        }
+      }
+      tile[tx][cc] = v;
+    }
+    __syncthreads();
+    // 32 pixels x 64 channels -> rows of 128 bytes: thread = (pixel, 8-channel group)
+    const int px = threadIdx.x >> 3, g8 = threadIdx.x & 7;
+    if (p0 + px < P && c0 + g8 * 8 < Cs) {
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(tile[px][g8 * 8 + 2 * i], tile[px][g8 * 8 + 2 * i + 1]);
+      *reinterpret_cast<uint4*>(dst + ((int64_t)n * P + p0 + px) * Cs + c0 + g8 * 8) = o;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t P, int Cs, int C) {
+  __shared__ float tile[32][65];
+  const int n = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int px = threadIdx.x >> 3, g8 = threadIdx.x & 7;
+    if (p0 + px < P && c0 + g8 * 8 < Cs) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + ((int64_t)n * P + p0 + px) * Cs + c0 + g8 * 8);
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(v2[i]);
+        tile[px][g8 * 8 + 2 * i] = f.x;
+        tile[px][g8 * 8 + 2 * i + 1] = f.y;
+      }
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 64; cc += 8) {
+      const int c = c0 + cc;
+      if (c < C && p0 + tx < P) dst[((int64_t)n * C + c) * P + p0 + tx] = tile[tx][cc];
+    }
+    __syncthreads();
+  }
+}
+}  // namespace ofsv
+
+extern "C" int ofsv_pack_nhwc_bf16(const float* const* srcs, const int* channels, int nsrc, void* dst, int N, int64_t P, int Cs, void* stream) {
+  OFSV_REQUIRE(srcs && channels && nsrc >= 1 && nsrc <= 4, "ofsv_pack_nhwc_bf16: 1..4 sources");
+  OFSV_REQUIRE(N >= 0 && N <= 65535 && P >= 0 && Cs >= 8 && Cs % 8 == 0, "ofsv_pack_nhwc_bf16: bad shape");
+  ofsv::NhwcSrc S;
+  int total = 0;
+  for (int i = 0; i < 4; ++i) { S.p[i] = i < nsrc ? srcs[i] : nullptr; S.c[i] = i < nsrc ? channels[i] : 0; total += S.c[i]; }
+  S.nsrc = nsrc;
+  OFSV_REQUIRE(total <= Cs, "ofsv_pack_nhwc_bf16: %d source channels do not fit Cs = %d", total, Cs);
+  if ((int64_t)N * P == 0) return OFSV_OK;
+  for (int i = 0; i < nsrc; ++i) OFSV_REQUIRE(srcs[i] != nullptr && channels[i] > 0, "ofsv_pack_nhwc_bf16: null / empty source %d", i);
+  OFSV_REQUIRE(dst && aligned16(dst), "ofsv_pack_nhwc_bf16: dst must be 16-byte aligned");
+  ofsv::pack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(S, static_cast<__nv_bfloat16*>(dst), P, Cs);
+  return check_launch("pack_nhwc_kernel");
+}
+
+extern "C" int ofsv_unpack_nhwc_f32(const void* src, float* dst, int N, int64_t P, int Cs, int C, void* stream) {
+  OFSV_REQUIRE(N >= 0 && N <= 65535 && P >= 0 && Cs >= 8 && Cs % 8 == 0 && C >= 1 && C <= Cs, "ofsv_unpack_nhwc_f32: bad shape");
+  if ((int64_t)N * P == 0) return OFSV_OK;
+  OFSV_REQUIRE(src && dst && aligned16(src), "ofsv_unpack_nhwc_f32: null / misaligned pointer");
+  ofsv::unpack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), dst, P, Cs, C);
+  return check_launch("unpack_nhwc_kernel");
+}
+
 extern "C" int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream) {
   OFSV_REQUIRE(n >= 0 && div != 0.0f, "ofsv_u8_to_f32: bad arguments");
   if (n == 0) return OFSV_OK;

@@ -438,6 +438,35 @@ def s2d_shape(n, sp, c):
     return [n] + [v // 2 + 1 for v in sp] + [(2 ** len(sp)) * c]
 
 
+def pack_nhwc(srcs, cs):
+    """Channel concatenation of 1..4 fp32 (N,C_i,*sp) CUDA tensors -> channels-last bf16 [N][D][H][W][cs] (D = 1 for 2-D inputs),
+    zero-padded channels, in one launch (ofsv_pack_nhwc_bf16)."""
+    srcs = [_cuda_f32(t, "pack_nhwc source") for t in srcs]
+    n, sp = srcs[0].shape[0], tuple(srcs[0].shape[2:])
+    if not 1 <= len(srcs) <= 4 or any(t.shape[0] != n or tuple(t.shape[2:]) != sp for t in srcs):
+        raise ValueError("pack_nhwc: 1..4 tensors with equal batch and spatial dims")
+    pix = 1
+    for v in sp:
+        pix *= v
+    out = torch.empty((n,) + ((1,) + sp if len(sp) == 2 else sp) + (cs,), device=srcs[0].device, dtype=torch.bfloat16)
+    ptrs = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+    chans = (ctypes.c_int * len(srcs))(*[t.shape[1] for t in srcs])
+    with _on(out.device), _span("pack_nhwc"):
+        _C.check(_C.lib().ofsv_pack_nhwc_bf16(ptrs, chans, len(srcs), _p(out), n, pix, cs, _stream()))
+    return out
+
+
+def unpack_nhwc(y, c, nd):
+    """Channels-last bf16 [N][D][H][W][Cs] (D = 1 for nd = 2) -> fp32 (N,c,*sp) with the first c channels (ofsv_unpack_nhwc_f32)."""
+    if not (y.is_cuda and y.dtype == torch.bfloat16 and y.is_contiguous() and y.dim() == 5):
+        raise TypeError("unpack_nhwc: expected a contiguous CUDA bf16 [N][D][H][W][Cs] tensor (no CPU path)")
+    n, d, h, w, cs = y.shape
+    out = torch.empty((n, c) + ((h, w) if nd == 2 else (d, h, w)), device=y.device, dtype=torch.float32)
+    with _on(y.device), _span("unpack_nhwc"):
+        _C.check(_C.lib().ofsv_unpack_nhwc_f32(_p(y), _p(out), n, d * h * w, cs, c, _stream()))
+    return out
+
+
 def pack_block_input(img0, img1, warped0, warped1, mask, flow, scale, act_dtype, cs=16, s2d=False, key="xin"):
     nd = img0.dim() - 2
     n = img0.shape[0]

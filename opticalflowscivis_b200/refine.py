@@ -34,18 +34,19 @@ def run_tap_layer(lay, x, n, in_sp):
 
 
 def _to_cl(x, nd, cs):
-    """fp32 (N,C,*sp) -> bf16 channels-last [N][D][H][W][cs], zero-padded channels."""
-    n, c = x.shape[:2]
-    sp = tuple(x.shape[2:])
-    out = torch.zeros((n,) + ((1,) if nd == 2 else ()) + sp + (cs,), device=x.device, dtype=torch.bfloat16)
-    (out[:, 0] if nd == 2 else out)[..., :c] = x.permute(0, 2, 3, 1) if nd == 2 else x.permute(0, 2, 3, 4, 1)
-    return out
+    """fp32 (N,C,*sp) tensor — or a list of up to four, concatenated along the channels — -> bf16 channels-last [N][D][H][W][cs]
+    with zero-padded channels, one launch (ofsv_pack_nhwc_bf16)."""
+    return ops.pack_nhwc(list(x) if isinstance(x, (list, tuple)) else [x], cs)
 
 
 def _from_cl(y, c, nd):
+    """channels-last [N][D][H][W][Cs] -> fp32 (N,c,*sp): bf16 activations through ofsv_unpack_nhwc_f32; the fp32 outputs of the
+    linear heads (8 stored channels) are a strided view made contiguous."""
+    if y.dtype == torch.bfloat16:
+        return ops.unpack_nhwc(y, c, nd)
     if nd == 2:
-        return y[:, 0, :, :, :c].permute(0, 3, 1, 2).float().contiguous()
-    return y[..., :c].permute(0, 4, 1, 2, 3).float().contiguous()
+        return y[:, 0, :, :, :c].permute(0, 3, 1, 2).contiguous()
+    return y[..., :c].permute(0, 4, 1, 2, 3).contiguous()
 
 
 def _conv_layers(m, prelu):

@@ -144,20 +144,17 @@ def _run_layer(lay, d, x, res, y):
 
 
 def _to_cl16(x, nd):
-    """fp32 (N,C,*sp) -> bf16 channels-last [N][D][H][W][16] (D = 1 in 2-D), zero-padded channels."""
-    n, c = x.shape[:2]
-    sp = tuple(x.shape[2:])
-    out = torch.zeros((n,) + ((1,) if nd == 2 else ()) + sp + (16,), device=x.device, dtype=_ACT_DTYPE)
-    src = x.permute(0, 2, 3, 1) if nd == 2 else x.permute(0, 2, 3, 4, 1)
-    (out[:, 0] if nd == 2 else out)[..., :c] = src
-    return out
+    """fp32 (N,C,*sp) -> bf16 channels-last [N][D][H][W][16] (D = 1 in 2-D), zero-padded channels (ofsv_pack_nhwc_bf16)."""
+    return ops.pack_nhwc([x], 16)
 
 
 def _from_cl(y, c, nd):
-    """channels-last [N][D][H][W][Cs] -> fp32 (N,c,*sp) contiguous."""
-    if nd == 2:
-        return y[:, 0, :, :, :c].permute(0, 3, 1, 2).float().contiguous()
-    return y[..., :c].permute(0, 4, 1, 2, 3).float().contiguous()
+    """channels-last [N][D][H][W][Cs] bf16 / fp32 -> fp32 (N,c,*sp) contiguous."""
+    if y.dtype == torch.bfloat16:
+        return ops.unpack_nhwc(y, c, nd)
+    if nd == 2:                                    # the fp32 head tensor (8 stored channels)
+        return y[:, 0, :, :, :c].permute(0, 3, 1, 2).contiguous()
+    return y[..., :c].permute(0, 4, 1, 2, 3).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------ one IFBlock = one autograd node

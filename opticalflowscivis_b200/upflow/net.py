@@ -190,8 +190,8 @@ class SguModel(_Net):
         if (h, w) != (hf, wf):
             flow_init = ops.upsample_flow_ac(flow_init, hf, wf)
         f2w = ops.warping_no_div(feature_2, flow_init)
-        x = torch.cat((feature_1, f2w), 1)
-        _, _, x_out = self.dense_estimator_mask.run(_to_cl(x, 2, _rup(x.shape[1], 16)), n, (1, hf, wf))
+        x_cl = _to_cl([feature_1, f2w], 2, _rup(feature_1.shape[1] + f2w.shape[1], 16))
+        _, _, x_out = self.dense_estimator_mask.run(x_cl, n, (1, hf, wf))
         inter_flow, inter_mask = x_out[:, :2].contiguous(), torch.sigmoid(x_out[:, 2:3])
         if output_level_flow is not None:
             H, W = output_level_flow.shape[2:]
@@ -242,8 +242,8 @@ class UPFlowNet(nn.Module):
         else:
             f1, f2w = feat, (ops.warping_no_div(other, flow_up) if level > 0 else other)
         corr = ops.corr81_fwd(f1, f2w, leaky_slope=0.1)
-        x = torch.cat((corr, feat_1x1, flow_up), 1)
-        x5, x5_map, flow_res = self.flow_estimators.run(_to_cl(x, 2, _rup(x.shape[1], 16)), n, (1, h, w))
+        x_cl = _to_cl([corr, feat_1x1, flow_up], 2, _rup(corr.shape[1] + feat_1x1.shape[1] + 2, 16))    # upflow.py:657, one launch
+        x5, x5_map, flow_res = self.flow_estimators.run(x_cl, n, (1, h, w))
         flow_ = flow_up + flow_res
         ctx_in = torch.cat((x5, _to_cl(flow_, 2, 16)), -1)
         ctx_map = x5_map + [x5.shape[-1], x5.shape[-1] + 1]

@@ -419,3 +419,25 @@ def test_training_gradients_noncubic_vs_oracle(nd, sp):
     worst = min((_cos(p.grad, q.grad), k) for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()) if k.endswith("0.weight") or k.endswith("2.weight"))
     print(f"non-cubic {sp}: gradient cosine {c:.5f}, worst weight tensor {worst}")
     assert c >= 0.999 and worst[0] >= 0.98
+
+
+@pytest.mark.parametrize("shape,chans,cs", [((2, 37, 45), (81, 32, 2), 128), ((1, 5, 6, 7), (11,), 16), ((3, 64, 208), (196,), 208),
+                                            ((2, 8, 8), (7, 9, 3, 5), 32), ((1, 16, 16, 16), (64,), 64)])
+def test_pack_unpack_nhwc_kernels(shape, chans, cs):
+    """ofsv_pack_nhwc_bf16 (channel concatenation + zero padding + cast, one launch) and ofsv_unpack_nhwc_f32 against torch."""
+    from opticalflowscivis_b200 import ops
+    dev = _dev()
+    torch.manual_seed(sum(chans))
+    n, sp = shape[0], shape[1:]
+    nd = len(sp)
+    srcs = [torch.randn((n, c) + sp, device=dev) for c in chans]
+    got = ops.pack_nhwc(srcs, cs)
+    cat = torch.cat(srcs, 1)
+    ref = torch.zeros((n,) + ((1,) + sp if nd == 2 else sp) + (cs,), device=dev, dtype=torch.bfloat16)
+    (ref[:, 0] if nd == 2 else ref)[..., :cat.shape[1]] = cat.permute(0, 2, 3, 1) if nd == 2 else cat.permute(0, 2, 3, 4, 1)
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    c = cat.shape[1]
+    back = ops.unpack_nhwc(got, c, nd)
+    assert back.shape == cat.shape and torch.equal(back, cat.bfloat16().float())
+    with pytest.raises(TypeError):
+        ops.pack_nhwc([srcs[0].cpu()], cs)

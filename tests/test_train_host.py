@@ -78,9 +78,24 @@ def _run_layer_eval(lay, d, x, res, y):
     return y
 
 
+def _to_cl16_eval(x, nd):
+    n, c = x.shape[:2]
+    out = torch.zeros((n,) + ((1,) if nd == 2 else ()) + tuple(x.shape[2:]) + (16,))
+    (out[:, 0] if nd == 2 else out)[..., :c] = x.permute(0, 2, 3, 1) if nd == 2 else x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def _from_cl_eval(y, c, nd):
+    if nd == 2:
+        return y[:, 0, :, :, :c].permute(0, 3, 1, 2).float().contiguous()
+    return y[..., :c].permute(0, 4, 1, 2, 3).float().contiguous()
+
+
 @pytest.fixture
 def cpu_engine(monkeypatch):
     monkeypatch.setattr(train, "_require_cuda", lambda t, name: t)
+    monkeypatch.setattr(train, "_to_cl16", _to_cl16_eval)
+    monkeypatch.setattr(train, "_from_cl", _from_cl_eval)
     monkeypatch.setattr(train, "_ACT_DTYPE", torch.float32)
     monkeypatch.setattr(train, "_run_layer", _run_layer_eval)
     monkeypatch.setattr(train, "conv_wgrad", wgrad_eval)

@@ -21,7 +21,13 @@ def _run_tap_layer_eval(lay, x, n, in_sp):
     return run_layer(lay, x.float()), osp
 
 
+def _from_cl_f32(y, c, nd):
+    return y[:, 0, :, :, :c].permute(0, 3, 1, 2).float().contiguous()
+
+
 def _to_cl_f32(x, nd, cs):
+    if isinstance(x, (list, tuple)):
+        x = torch.cat(list(x), 1)
     n, c = x.shape[:2]
     out = torch.zeros((n, 1) + tuple(x.shape[2:]) + (cs,))
     out[:, 0, :, :, :c] = x.permute(0, 2, 3, 1)
@@ -32,6 +38,7 @@ def _to_cl_f32(x, nd, cs):
 def cpu_engine(monkeypatch):
     monkeypatch.setattr(unet, "run_tap_layer", _run_tap_layer_eval)
     monkeypatch.setattr(unet, "_to_cl", _to_cl_f32)
+    monkeypatch.setattr(unet, "_from_cl", _from_cl_f32)
     monkeypatch.setattr(unet.ops, "_cuda_f32", lambda t, name: t.float())
     monkeypatch.setattr(unet.ops, "upsample_flow_ac", lambda f, h, w, if_rate=True: ops_ref.upsample2d_flow_as_ref(f, h, w, if_rate))
     monkeypatch.setattr(unet.ops, "warping_no_div", ops_ref.warping_layer_no_div_ref)
