@@ -301,6 +301,8 @@ class _TrainBlock:
         key = self.blk._key()
         if key == self.key:
             return
+        if self.fwd is not None and self.fwd[0].w_simt.device != next(self.blk.parameters()).device:
+            self.fwd = None                                  # the module was moved to another device: build there from scratch
         with torch.no_grad():
             if self.fwd is None:
                 self.fwd, self.dgrad = self._build()
