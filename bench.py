@@ -185,7 +185,7 @@ def run_reference_arm(args, rank, world):
     on this box's host cores, same workload / metric / unit; every step is a bounded sample of the step (see CPU_SAMPLE)."""
     if rank != 0:
         return
-    if args.workload in ("upflow_ops", "train3d", "upflow_net"):
+    if args.workload in ("upflow_ops", "train3d", "train2d", "upflow_net"):
         print(json.dumps({"impl": "reference", "unavailable": f"{args.workload} is a next-tier workload (SURVEY.md §8f) without a CPU arm "
                           "(train3d reports the reference's eager-CUDA update as `cuda_eager_reference`)"}), flush=True)
         return
@@ -638,27 +638,30 @@ def run_upflow_net(args, rank, world, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------ training-step workload
-def run_train3d(args, rank, world, local_rank):
-    """one step = `Model.update` of the 3-D model (Flow-3D/model/RIFE.py:81-275: forward with the teacher block,
-    L1 + L1(teacher) + 0.1 distillation, backward, gradient all-reduce, AdamW) on `pairs` synthetic 64^3 (img0, img1, gt)
-    triplets per GPU — the volume size the reference trains on (Flow-3D/train.py:513-546 model names, `--batch_size` 15-30)."""
+def run_train(args, rank, world, local_rank):
+    """one step = `Model.update` (forward with the teacher block, losses, backward, gradient all-reduce, AdamW).
+    train3d: the 3-D model (Flow-3D/model/RIFE.py:81-275, L1 + L1(teacher) + 0.1 distillation) on `pairs` synthetic 64^3 (img0, img1,
+    gt) triplets per GPU — the volume size the reference trains on (Flow-3D/train.py:513-546 model names, `--batch_size` 15-30).
+    train2d: the 2-D model (Flow-2D/model/RIFE.py:80-336, LapLoss + 0.01 distillation + 1e-5 photometric) on 160x224 triplets."""
     import torch
     import torch.distributed as dist
 
     from opticalflowscivis_b200 import ops
-    from opticalflowscivis_b200.rife import Model3D
+    from opticalflowscivis_b200.rife import Model2D, Model3D
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    n, size = args.pairs or 8, 64
+    nd = 3 if args.workload == "train3d" else 2
+    sp = (64, 64, 64) if nd == 3 else (160, 224)
+    n = args.pairs or (8 if nd == 3 else 16)
     torch.manual_seed(1234)
-    model = Model3D(local_rank=local_rank if world > 1 else -1)
+    model = (Model3D if nd == 3 else Model2D)(local_rank=local_rank if world > 1 else -1)
     model.enable_training_graph(not args.no_train_graph)
     g = torch.Generator().manual_seed(1234 + rank)
-    base = torch.nn.functional.avg_pool3d(torch.rand((n, 1, size + 8, size + 8, size + 8), generator=g), 5, 1, 2)
-    img0 = base[:, :, 4:-4, 4:-4, 2:-6].contiguous().to(dev)
-    gt = base[:, :, 4:-4, 4:-4, 4:-4].contiguous().to(dev)
-    img1 = base[:, :, 4:-4, 4:-4, 6:-2].contiguous().to(dev)
+    pool = torch.nn.functional.avg_pool3d if nd == 3 else torch.nn.functional.avg_pool2d
+    base = pool(torch.rand((n, 1) + tuple(v + 8 for v in sp), generator=g), 5, 1, 2)
+    crop = lambda o: base[(slice(None), slice(None)) + tuple(slice(4, 4 + v) for v in sp[:-1]) + (slice(o, o + sp[-1]),)].contiguous().to(dev)  # noqa: E731
+    img0, gt, img1 = crop(2), crop(4), crop(6)
     imgs = torch.cat((img0, img1), 1)
     losses = []
     LR = 3e-6          # the reference warms up linearly from 0 to 3e-4 over 2000 steps (Flow-3D/train.py:50-54): step 20 of that ramp
@@ -670,7 +673,8 @@ def run_train3d(args, rank, world, local_rank):
 
     def step(k=1):
         for _ in range(k):
-            _, info = model.update(imgs, gt, learning_rate=LR, training=True)
+            _, info = model.update(imgs, gt, learning_rate=LR, training=True) if nd == 3 else \
+                model.update(imgs, gt, "droplet2d", learning_rate=LR, training=True)
             losses.append(info["loss_G"])
 
     step(args.warmup)
@@ -704,7 +708,7 @@ def run_train3d(args, rank, world, local_rank):
         try:
             from oracle.train_ref import TrainerRef
             torch.manual_seed(1234)
-            orc = TrainerRef(3)
+            orc = TrainerRef(nd)
             orc.flownet.to(dev)
             orc.optimG = torch.optim.AdamW(orc.flownet.parameters(), lr=1e-6, weight_decay=1e-3)
             eager = {"loss_G": []}
@@ -727,16 +731,17 @@ def run_train3d(args, rank, world, local_rank):
     if rank != 0:
         return
     nparam = sum(p.numel() for p in model.flownet.parameters())
-    macs = ifnet_macs(3, (size,) * 3)
+    macs = ifnet_macs(nd, sp)
     line = {
-        "metric": "Flow-3D Model.update training throughput (64^3 triplets/sec)", "value": world * n * args.steps / (ms / 1e3),
+        "metric": ("Flow-3D Model.update training throughput (64^3 triplets/sec)" if nd == 3 else
+                   "Flow-2D Model.update training throughput (160x224 triplets/sec)"), "value": world * n * args.steps / (ms / 1e3),
         "unit": "triplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "e2e": None,
         "allreduce_ms_per_step": ar, "allreduce_bytes": nparam * 4, "gpu_launches": int(launches),
         "loss_G_first_steps": lossv[:4], "loss_G_last": lossv[-1], "cuda_eager_reference": eager,
         "kernel_classes": classes, "ms_per_step_eager": ms_eager / args.steps, "train_graph": not args.no_train_graph, "clocks": clk.summary(),
-        "config": {"workload": "train3d", "describes": run_train3d.__doc__.split("\n\n")[0].replace("\n    ", " "),
-                   "spatial": [size] * 3, "triplets_per_gpu_per_step": n, "student_inference_macs_per_triplet": macs,
+        "config": {"workload": args.workload, "describes": run_train.__doc__.replace("\n    ", " "),
+                   "spatial": list(sp), "triplets_per_gpu_per_step": n, "student_inference_macs_per_triplet": macs,
                    "note": "conv stacks forward/backward, warp forward/backward and AdamW run in libofsv; interpolate/cat/sigmoid/"
                            "blend/loss glue is torch autograd"},
     }
@@ -749,7 +754,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops", "train3d", "upflow_net"])
+    ap.add_argument("--workload", default="flow3d_droplet256", choices=list(WORKLOADS) + ["upflow_ops", "train3d", "train2d", "upflow_net"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
@@ -787,7 +792,7 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     try:
-        {"upflow_ops": run_upflow_ops, "train3d": run_train3d, "upflow_net": run_upflow_net}.get(args.workload, run_ours)(args, rank, world, local_rank)
+        {"upflow_ops": run_upflow_ops, "train3d": run_train, "train2d": run_train, "upflow_net": run_upflow_net}.get(args.workload, run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

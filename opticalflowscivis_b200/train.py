@@ -674,8 +674,10 @@ def forward_losses(net, imgs, gt, device_guard=False):
         loss_photo = (_photometric_term(flow[2][:, 2:4], merged[2], img0) + _photometric_term(flow[2][:, :2], merged[2], img1)) / 2
         if device_guard:
             loss_distill = torch.where(torch.isnan(loss_distill) | (loss_distill > 10.), torch.zeros_like(loss_distill), loss_distill)
-        elif math.isnan(loss_distill) or loss_distill > 10.:              # host read, as in the reference (RIFE.py:295)
-            loss_distill = torch.zeros((), device=imgs.device)
+        else:
+            ld = float(loss_distill.detach())                              # host read, as in the reference (RIFE.py:295)
+            if math.isnan(ld) or ld > 10.:
+                loss_distill = torch.zeros((), device=imgs.device)
         loss_G = loss_l1 * 1 + loss_tea * 1 + loss_distill * 0.01 + l1_reg * 1e-6 + loss_photo * 1e-5
         info = {"loss_l1": loss_l1 * 1, "loss_tea": loss_tea * 1, "loss_distill": loss_distill * 0.01, "l1_reg": l1_reg * 1e-6,
                 "loss_photo": loss_photo * 1e-5, "loss_flow": torch.zeros(()) * 0, "loss_G": loss_G}
