@@ -308,6 +308,18 @@ int ofsv_conv_wgrad_bf16(const ofsv_conv_desc* d, const void* x, const void* gy,
 int ofsv_head_upsample_add(const float* head, int Cs, const float* flow_prev, const float* mask_prev, float* flow_out,
                            float* mask_out, int nd, int N, int D, int H, int W, int scale, void* stream);
 
+/* Backward of ofsv_head_upsample_add and ofsv_pack_block_input for the training step (autograd of
+ * IFNet.py:84-93,115-119 / :82-90,118-119 under Model.update).
+ *   ofsv_head_upsample_add_bwd: ghead [N][D/s][H/s][W/s][8] fp32 = adjoint of the trilinear / bilinear up-sampling applied to
+ *     (gflow (N,2nd,.) * s, gmask (N,1,.)); the gradients w.r.t. flow_prev / mask_prev are gflow / gmask themselves.  Gather form,
+ *     deterministic.
+ *   ofsv_pack_block_input_bwd: gx [N][D/s][H/s][W/s][16] bf16 (plain layout, Cs = 16) -> gradients of warped0, warped1, mask (N,1,.)
+ *     and flow (N,2nd,.) fp32; img0 / img1 take none. */
+int ofsv_head_upsample_add_bwd(const float* gflow, const float* gmask, float* ghead, int nd, int N, int D, int H, int W, int scale,
+                               void* stream);
+int ofsv_pack_block_input_bwd(const void* gx, float* gw0, float* gw1, float* gmask, float* gflow, int nd, int N, int D, int H, int W,
+                              int scale, void* stream);
+
 /* Fused 3-D IFBlock output stage: ofsv_head_upsample_add + ofsv_warp_blend_3d_f32 (+ the next block's
  * ofsv_pack_block_input) in one pass over the full-resolution voxels — Flow-3D/model/IFNet.py:118-119 (resize, *scale),
  * :169-170 (flow/mask accumulate), :186-191 (sigmoid, warp x2), :242 (blend), :82-90,166 (next block's resized concat).

@@ -85,6 +85,8 @@ _SIGS = {
     "ofsv_prelu_bias_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "ofsv_conv_wgrad_splits": (_I, [ctypes.POINTER(ConvDesc)]),
     "ofsv_conv_wgrad_bf16": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _I, _P, _P, _P]),
+    "ofsv_head_upsample_add_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ofsv_pack_block_input_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_head_upsample_add": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ofsv_block_stage_3d": (_I, [_P] * 11 + [_I] * 9 + [_P]),
 }

@@ -3,6 +3,8 @@
 // Both follow ATen's upsample_{bi,tri}linear (align_corners=False) index/weight arithmetic:
 //   src = rscale*(dst+0.5)-0.5 (clamped at 0), i0 = min(floor(src), n-1), i1 = i0 + (i0 < n-1), l1 = src-i0, l0 = 1-l1,
 //   value = nested  t0*l0 + t1*l1  with W innermost (SURVEY.md Appendix A "Resize identities").
+#include <algorithm>
+
 #include "ofsv_common.cuh"
 
 namespace ofsv {
@@ -163,6 +165,98 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- backward of the two stages above (training tier) ----------------------------------------------------
+// head_upsample_add: flow_out = flow_prev + s * up_s(head[0..NF)), mask_out = mask_prev + up_s(head[NF]).  The gradient w.r.t. the
+// previous flow / mask is the incoming gradient itself; w.r.t. the head it is the ADJOINT of the trilinear up-sampling, evaluated
+// as a gather (deterministic): coarse cell c collects every fine position whose two taps (up_index — the forward's own index /
+// weight function) include c.  One thread per coarse cell, all NF + 1 channels.
+template <int ND>
+__global__ void __launch_bounds__(128)
+    head_upsample_add_bwd_kernel(const float* __restrict__ gflow, const float* __restrict__ gmask, float* __restrict__ ghead, int N, int D,
+                                 int H, int W, int s) {
+  constexpr int NF = 2 * ND, NC = NF + 1;
+  const int Dh = ND == 3 ? D / s : 1, Hh = H / s, Wh = W / s;
+  const int64_t V = (int64_t)D * H * W, Vh = (int64_t)Dh * Hh * Wh, total = (int64_t)N * Vh;
+  const float rscale = 1.0f / (float)s, fs = (float)s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Vh);
+    int r = (int)(i - (int64_t)n * Vh);
+    const int cx = r % Wh; r /= Wh;
+    const int cy = r % Hh;
+    const int cz = r / Hh;
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+    auto weight = [&](int j, int c, int n_in) -> float {
+      if (s == 1) return j == c ? 1.f : 0.f;
+      const Lerp L = up_index(j, n_in, rscale);
+      return (L.i0 == c ? L.l0 : 0.f) + (L.i1 == c ? L.l1 : 0.f);       // both taps on c at the clamped far edge: l0 + l1 = 1
+    };
+    const int z_lo = ND == 3 ? max(0, s * cz - s) : 0, z_hi = ND == 3 ? min(D, s * cz + 2 * s) : 1;
+    for (int z = z_lo; z < z_hi; ++z) {
+      const float wz = ND == 3 ? weight(z, cz, Dh) : 1.f;
+      if (wz == 0.f) continue;
+      for (int y = max(0, s * cy - s); y < min(H, s * cy + 2 * s); ++y) {
+        const float wy = weight(y, cy, Hh);
+        if (wy == 0.f) continue;
+        for (int x = max(0, s * cx - s); x < min(W, s * cx + 2 * s); ++x) {
+          const float wx = weight(x, cx, Wh);
+          if (wx == 0.f) continue;
+          const float w = wz * wy * wx;
+          const int64_t o = ((int64_t)z * H + y) * W + x;
+#pragma unroll
+          for (int c = 0; c < NF; ++c) acc[c] = fmaf(w, __ldg(gflow + ((int64_t)n * NF + c) * V + o), acc[c]);
+          acc[NF] = fmaf(w, __ldg(gmask + (int64_t)n * V + o), acc[NF]);
+        }
+      }
+    }
+    float out[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] = c < NF ? acc[c] * fs : (c == NF ? acc[NF] : 0.f);
+    float4* po = reinterpret_cast<float4*>(ghead + i * 8);
+    po[0] = make_float4(out[0], out[1], out[2], out[3]);
+    po[1] = make_float4(out[4], out[5], out[6], out[7]);
+  }
+}
+
+// pack_block_input: channel c of the packed row = resize_{1/s}(source c) (flow channels additionally / s); the resize is the mean of
+// the 2^nd samples at offsets {s/2 - 1, s/2} of each s-cell, so a fine voxel receives gx[cell] / 2^nd if it is
+// one of them and nothing otherwise.  One thread per fine voxel; img0 / img1 (and a teacher's gt) take no gradient.
+template <int ND>
+__global__ void __launch_bounds__(256)
+    pack_block_input_bwd_kernel(const __nv_bfloat16* __restrict__ gx, float* __restrict__ gw0, float* __restrict__ gw1, float* __restrict__ gmask,
+                                float* __restrict__ gflow, int N, int D, int H, int W, int s) {
+  constexpr int NF = 2 * ND;
+  const int Do = ND == 3 ? D / s : 1, Ho = H / s, Wo = W / s;
+  const int64_t V = (int64_t)D * H * W, total = (int64_t)N * V;
+  const float wgt = s == 1 ? 1.0f : (ND == 3 ? 0.125f : 0.25f), inv_s = 1.0f / (float)s;
+  const int lo = s / 2 - 1, hi = s / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const int64_t r = i - (int64_t)n * V;
+    const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((int64_t)W * H));
+    auto inside = [&](int j) { const int o = j % s; return s == 1 || o == lo || o == hi; };
+    float v[3 + NF];
+#pragma unroll
+    for (int c = 0; c < 3 + NF; ++c) v[c] = 0.f;
+    if (inside(x) && inside(y) && (ND == 2 || inside(z))) {
+      const int64_t cell = (((int64_t)n * Do + (ND == 3 ? z / s : 0)) * Ho + y / s) * Wo + x / s;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(gx + cell * 16)), b = __ldg(reinterpret_cast<const uint4*>(gx + cell * 16) + 1);
+      const __nv_bfloat16* ha = reinterpret_cast<const __nv_bfloat16*>(&a);
+      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&b);
+      float row[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { row[c] = __bfloat162float(ha[c]); row[8 + c] = __bfloat162float(hb[c]); }
+      v[0] = row[2] * wgt; v[1] = row[3] * wgt; v[2] = row[4] * wgt;
+#pragma unroll
+      for (int c = 0; c < NF; ++c) v[3 + c] = row[5 + c] * wgt * inv_s;
+    }
+    gw0[i] = v[0]; gw1[i] = v[1]; gmask[i] = v[2];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) gflow[((int64_t)n * NF + c) * V + r] = v[3 + c];
+  }
+}
+
 // uint8 volume -> fp32 in [0,1]: float(x) / 255.0f (true division, what the reference loaders compute on the host:
 // Datasets/read_data.py, Flow-3D/load_datasets.py).  16 voxels per thread: one 16 B load, four 16 B stores.
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n, float div) {
@@ -265,11 +359,14 @@ extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* fl
 // of the estimator input torch.cat([corr, x_1x1, flow], 1), UPFlow/model/upflow.py:657, in one pass) and zero-fills the padding.
 namespace ofsv {
 struct NhwcSrc { const float* p[4]; int c[4]; int nsrc; };
-__global__ void __launch_bounds__(256) pack_nhwc_kernel(const NhwcSrc S, __nv_bfloat16* __restrict__ dst, int64_t P, int Cs) {
+constexpr int NHWC_TILES = 8;
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const NhwcSrc S, __nv_bfloat16* __restrict__ dst, int64_t P, int Cs, int tiles) {
   __shared__ float tile[32][65];
   const int n = blockIdx.y;
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty: 8 channel rows per pass
+  for (int t = 0; t < tiles; ++t) {                             // a CTA walks `tiles` consecutive 32-pixel tiles (8 on large tensors)
+  const int64_t p0 = ((int64_t)blockIdx.x * tiles + t) * 32;
+  if (p0 >= P) break;
   for (int c0 = 0; c0 < Cs; c0 += 64) {
     const int ncc = min(64, Cs - c0);
     for (int cc = ty; cc < ncc; cc += 8) {
@@ -296,12 +393,15 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const NhwcSrc S, __nv_bf
     }
     __syncthreads();
   }
+  }
 }
-__global__ void __launch_bounds__(256) unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t P, int Cs, int C) {
+__global__ void __launch_bounds__(256) unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t P, int Cs, int C, int tiles) {
   __shared__ float tile[32][65];
   const int n = blockIdx.y;
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = 0; t < tiles; ++t) {
+  const int64_t p0 = ((int64_t)blockIdx.x * tiles + t) * 32;
+  if (p0 >= P) break;
   for (int c0 = 0; c0 < C; c0 += 64) {
     const int px = threadIdx.x >> 3, g8 = threadIdx.x & 7;
     if (p0 + px < P && c0 + g8 * 8 < Cs) {
@@ -321,6 +421,7 @@ __global__ void __launch_bounds__(256) unpack_nhwc_kernel(const __nv_bfloat16* _
     }
     __syncthreads();
   }
+  }
 }
 }  // namespace ofsv
 
@@ -335,7 +436,8 @@ extern "C" int ofsv_pack_nhwc_bf16(const float* const* srcs, const int* channels
   if ((int64_t)N * P == 0) return OFSV_OK;
   for (int i = 0; i < nsrc; ++i) OFSV_REQUIRE(srcs[i] != nullptr && channels[i] > 0, "ofsv_pack_nhwc_bf16: null / empty source %d", i);
   OFSV_REQUIRE(dst && aligned16(dst), "ofsv_pack_nhwc_bf16: dst must be 16-byte aligned");
-  ofsv::pack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(S, static_cast<__nv_bfloat16*>(dst), P, Cs);
+  const int tiles = (int64_t)N * P >= (1 << 20) ? ofsv::NHWC_TILES : 1;
+  ofsv::pack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32 * tiles), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(S, static_cast<__nv_bfloat16*>(dst), P, Cs, tiles);
   return check_launch("pack_nhwc_kernel");
 }
 
@@ -343,8 +445,40 @@ extern "C" int ofsv_unpack_nhwc_f32(const void* src, float* dst, int N, int64_t 
   OFSV_REQUIRE(N >= 0 && N <= 65535 && P >= 0 && Cs >= 8 && Cs % 8 == 0 && C >= 1 && C <= Cs, "ofsv_unpack_nhwc_f32: bad shape");
   if ((int64_t)N * P == 0) return OFSV_OK;
   OFSV_REQUIRE(src && dst && aligned16(src), "ofsv_unpack_nhwc_f32: null / misaligned pointer");
-  ofsv::unpack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), dst, P, Cs, C);
+  const int tiles = (int64_t)N * P >= (1 << 20) ? ofsv::NHWC_TILES : 1;
+  ofsv::unpack_nhwc_kernel<<<dim3((unsigned)cdiv(P, 32 * tiles), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), dst, P, Cs, C, tiles);
   return check_launch("unpack_nhwc_kernel");
+}
+
+extern "C" int ofsv_head_upsample_add_bwd(const float* gflow, const float* gmask, float* ghead, int nd, int N, int D, int H, int W, int scale,
+                                          void* stream) {
+  OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_head_upsample_add_bwd: nd must be 2 or 3");
+  OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_head_upsample_add_bwd: scale must be 1, 2 or 4");
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
+               "ofsv_head_upsample_add_bwd: spatial dims must be multiples of scale");
+  if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(gflow && gmask && ghead && aligned16(ghead), "ofsv_head_upsample_add_bwd: null / misaligned pointer");
+  const int64_t cells = (int64_t)N * (nd == 3 ? D / scale : 1) * (H / scale) * (W / scale);
+  const int g = (int)std::min<int64_t>(cdiv(cells, 128), (int64_t)device_num_sms() * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nd == 2) head_upsample_add_bwd_kernel<2><<<g, 128, 0, st>>>(gflow, gmask, ghead, N, D, H, W, scale);
+  else head_upsample_add_bwd_kernel<3><<<g, 128, 0, st>>>(gflow, gmask, ghead, N, D, H, W, scale);
+  return check_launch("head_upsample_add_bwd_kernel");
+}
+
+extern "C" int ofsv_pack_block_input_bwd(const void* gx, float* gw0, float* gw1, float* gmask, float* gflow, int nd, int N, int D, int H, int W,
+                                         int scale, void* stream) {
+  OFSV_REQUIRE(nd == 2 || nd == 3, "ofsv_pack_block_input_bwd: nd must be 2 or 3");
+  OFSV_REQUIRE(scale == 1 || scale == 2 || scale == 4, "ofsv_pack_block_input_bwd: scale must be 1, 2 or 4");
+  OFSV_REQUIRE(N >= 0 && D >= 1 && H >= 1 && W >= 1 && (nd == 2 ? D == 1 : D % scale == 0) && H % scale == 0 && W % scale == 0,
+               "ofsv_pack_block_input_bwd: spatial dims must be multiples of scale");
+  if (N == 0) return OFSV_OK;
+  OFSV_REQUIRE(gx && gw0 && gw1 && gmask && gflow && aligned16(gx), "ofsv_pack_block_input_bwd: null / misaligned pointer");
+  const int g = grid_1d((int64_t)N * D * H * W);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nd == 2) pack_block_input_bwd_kernel<2><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gx), gw0, gw1, gmask, gflow, N, D, H, W, scale);
+  else pack_block_input_bwd_kernel<3><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gx), gw0, gw1, gmask, gflow, N, D, H, W, scale);
+  return check_launch("pack_block_input_bwd_kernel");
 }
 
 extern "C" int ofsv_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float div, void* stream) {

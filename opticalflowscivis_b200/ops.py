@@ -494,6 +494,32 @@ def head_upsample_add(head, flow_prev, mask_prev, nd, n, sp, scale):
     return flow, mask
 
 
+def head_upsample_add_bwd(gflow, gmask, nd, scale):
+    """Gradient of head_upsample_add w.r.t. the head: channels-last fp32 [N][D/s][H/s][W/s][8] (ofsv_head_upsample_add_bwd)."""
+    gflow, gmask = _cuda_f32(gflow, "gflow"), _cuda_f32(gmask, "gmask")
+    n = gflow.shape[0]
+    sp = tuple(gflow.shape[2:])
+    d, h, w = ((1,) + sp) if nd == 2 else sp
+    out = torch.empty((n, (d // scale) if nd == 3 else 1, h // scale, w // scale, 8), device=gflow.device, dtype=torch.float32)
+    with _on(gflow.device), _span("head_upsample_add_bwd"):
+        _C.check(_C.lib().ofsv_head_upsample_add_bwd(_p(gflow), _p(gmask), _p(out), nd, n, d, h, w, scale, _stream()))
+    return out
+
+
+def pack_block_input_bwd(gx, nd, sp, scale):
+    """Gradients of pack_block_input (plain layout, Cs = 16) w.r.t. (warped0, warped1, mask, flow) (ofsv_pack_block_input_bwd)."""
+    if not (gx.is_cuda and gx.dtype == torch.bfloat16 and gx.is_contiguous() and gx.shape[-1] == 16):
+        raise TypeError("pack_block_input_bwd: expected a contiguous CUDA bf16 [...][16] tensor (no CPU path)")
+    n = gx.shape[0]
+    d, h, w = ((1,) + tuple(sp)) if nd == 2 else tuple(sp)
+    g0 = torch.empty((n, 1) + tuple(sp), device=gx.device, dtype=torch.float32)
+    g1, gm = torch.empty_like(g0), torch.empty_like(g0)
+    gf = torch.empty((n, 2 * nd) + tuple(sp), device=gx.device, dtype=torch.float32)
+    with _on(gx.device), _span("pack_block_input_bwd"):
+        _C.check(_C.lib().ofsv_pack_block_input_bwd(_p(gx), _p(g0), _p(g1), _p(gm), _p(gf), nd, n, d, h, w, scale, _stream()))
+    return g0, g1, gm, gf
+
+
 def block_stage_3d(head, fm_prev, img0, img1, scale_head, scale_next, want_merged, want_mask, pack_s2d=False, key="xin", hfast=False):
     """Fused 3-D block output stage on the channels-last state (ofsv_block_stage_3d).  State layout: [N,D,H,W,8] fp32, or with
     `hfast` the H-fastest [N,D,W,H,8] (_C.STATE_DWH8) that csrc/block_stage_hfast.cu works on; `head` is the block's head at

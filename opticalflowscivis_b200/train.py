@@ -12,8 +12,10 @@ What runs where
   * warp forward / backward: ofsv_warp{2,3}d_f32 / ofsv_warp{2,3}d_bwd_f32 behind `ops.warp2d / warp3d` (autograd Functions);
   * optimizer: `optim.FusedAdamW` on a flat `GradientBucket`, one all-reduce of the bucket when a process group is up (the
     reference wraps the net in DDP when local_rank != -1: RIFE.py:31-32);
-  * the glue between those (F.interpolate of the block inputs / heads, cat, sigmoid, blend, the loss reductions) is plain torch
-    autograd on fp32 NC(D)HW tensors — a few dozen element-wise launches per step, none of them a convolution or a sampler.
+  * the student blocks' input packing (resize 1/s of the concatenation, flow / s) and head up-sampling + accumulate are libofsv
+    autograd nodes as well (ofsv_pack_block_input[_bwd], ofsv_head_upsample_add[_bwd]); what is left between the nodes (sigmoid,
+    blend, the loss reductions, the teacher block's resize-free concat) is plain torch autograd on fp32 NC(D)HW tensors — element-wise
+    launches, none of them a convolution or a sampler.
 There is no CPU path: everything raises on CPU tensors like the rest of the package.
 """
 from __future__ import annotations
@@ -351,16 +353,18 @@ class _BlockFn(torch.autograd.Function):
     the up-resize).  Flow-3D/model/IFNet.py:91-116 / Flow-2D/model/IFNet.py:95-113 (conv0, convblock0-3 with skips, conv1, conv2)."""
 
     @staticmethod
-    def forward(ctx, x, tb, *params):
+    def forward(ctx, x, tb, cl_io, *params):
+        """cl_io = False: x fp32 (N, Cin, *sp), returns the head fp32 (N, 2nd+1, *sp).  cl_io = True: x is the packed block input itself
+        (bf16 channels-last [N][D][H][W][16], ofsv_pack_block_input) and the head comes back as the engine wrote it (fp32
+        channels-last [N][D][H][W][8]) — no layout copies on either side."""
         _require_cuda(x, "IFBlock training forward")
         blk = tb.blk
         nd = blk.nd
         tb.refresh()
         n = x.shape[0]
-        sp = tuple(x.shape[2:])
-        sp3 = ((1,) + sp) if nd == 2 else sp
+        sp3 = tuple(x.shape[1:4]) if cl_io else (((1,) + tuple(x.shape[2:])) if nd == 2 else tuple(x.shape[2:]))
         with ops._on(x.device):
-            a = _to_cl16(x.detach(), nd)
+            a = x.detach() if cl_io else _to_cl16(x.detach(), nd)
             xs, ys, descs = [], [], []
             cur, cur_sp, skip = a, sp3, None
             for li, lay in enumerate(tb.fwd):
@@ -374,11 +378,11 @@ class _BlockFn(torch.autograd.Function):
                     skip = cur
                 cur = (y + skip) if li in _PAIRS_B else y
                 cur_sp = osp
-            head = _from_cl(ys[-1], 2 * nd + 1, nd)
+            head = ys[-1] if cl_io else _from_cl(ys[-1], 2 * nd + 1, nd)
         ctx.tb, ctx.xs, ctx.ys, ctx.descs, ctx.nd, ctx.n = tb, xs, ys, descs, nd, n
-        ctx.cin = x.shape[1]
+        ctx.cin = 16 if cl_io else x.shape[1]
         ctx.need_x = x.requires_grad
-        ctx.in_sp = sp3
+        ctx.in_sp, ctx.cl_io = sp3, cl_io
         return head
 
     @staticmethod
@@ -404,10 +408,14 @@ class _BlockFn(torch.autograd.Function):
         with ops._on(dev):
             g_head = g_head.contiguous()
             # heads (merged block-diagonal ConvT c -> 2nd+1, no activation): bias gradient is a plain sum
-            red = (0,) + tuple(range(2, 2 + nd))
-            db = g_head.sum(red)
+            if ctx.cl_io:                                     # fp32 channels-last [N][D][H][W][8] -> bf16 [..][16]
+                db = g_head.reshape(-1, 8).sum(0)
+                g = torch.zeros(g_head.shape[:-1] + (16,), device=dev, dtype=_ACT_DTYPE)
+                g[..., :8] = g_head
+            else:
+                db = g_head.sum((0,) + tuple(range(2, 2 + nd)))
+                g = _to_cl16(g_head, nd)
             grads["conv1.2.bias"], grads["conv2.2.bias"] = db[:nf], db[nf:nf + 1]
-            g = _to_cl16(g_head, nd)
             dw = tb.convT_weight_grad(conv_wgrad(descs[11], xs[11], g), c, nf + 1)
             grads["conv1.2.weight"], grads["conv2.2.weight"] = dw[: c // 2, :nf], dw[c // 2:, nf:nf + 1]
             g = dgrad(11, g, sp_of(g))
@@ -440,8 +448,8 @@ class _BlockFn(torch.autograd.Function):
                 grads[f"conv0.{li}.0.weight"] = tb.conv_weight_grad(conv_wgrad(descs[li], xs[li], gp), m)
                 if li == 1 or ctx.need_x:
                     g = dgrad(li, gp, sp_of(gp))
-            gx = _from_cl(g, ctx.cin, nd) if ctx.need_x else None
-        return (gx, None) + tuple(grads[k].contiguous() for k in tb.names)
+            gx = (g if ctx.cl_io else _from_cl(g, ctx.cin, nd)) if ctx.need_x else None
+        return (gx, None, None) + tuple(grads[k].contiguous() for k in tb.names)
 
 
 def _warp_fn(nd):
@@ -457,11 +465,51 @@ def block_train(tb: _TrainBlock, x, flow, scale):
     if flow is not None:
         flow = F.interpolate(flow, scale_factor=1. / scale, mode=mode, align_corners=False) * 1. / scale
         x = torch.cat((x, flow), 1)
-    head = _BlockFn.apply(x, tb, *tb.blk.parameters())
+    head = _BlockFn.apply(x, tb, False, *tb.blk.parameters())
     nf = 2 * nd
     flow_d = F.interpolate(head[:, :nf], scale_factor=scale, mode=mode, align_corners=False, recompute_scale_factor=False) * scale
     mask_d = F.interpolate(head[:, nf:nf + 1], scale_factor=scale, mode=mode, align_corners=False, recompute_scale_factor=False)
     return flow_d, mask_d
+
+
+def _pack_input(img0, img1, w0, w1, mask, flow, scale):
+    """ofsv_pack_block_input in the plain layout, always 5-D: [N][D][H][W][16] with D = 1 for frames."""
+    xin = ops.pack_block_input(img0, img1, w0, w1, mask, flow, scale, _C.BF16)
+    return xin.unsqueeze(1) if img0.dim() == 4 else xin
+
+
+class _PackInputFn(torch.autograd.Function):
+    """xin = ofsv_pack_block_input(img0, img1, warped0, warped1, mask, flow; scale): resize 1/s of the concatenation with the flow / s
+    (IFNet.py:84-93 / :82-90 + the cat of :174 / :166), bf16 channels-last [N][D][H][W][16]; backward: ofsv_pack_block_input_bwd."""
+
+    @staticmethod
+    def forward(ctx, img0, img1, w0, w1, mask, flow, scale):
+        ctx.scale, ctx.nd, ctx.sp = scale, img0.dim() - 2, tuple(img0.shape[2:])
+        return _pack_input(img0, img1, w0.contiguous(), w1.contiguous(), mask.contiguous(), flow.contiguous(), scale)
+
+    @staticmethod
+    def backward(ctx, gx):
+        g0, g1, gm, gf = ops.pack_block_input_bwd(gx.contiguous(), ctx.nd, ctx.sp, ctx.scale)
+        return None, None, g0, g1, gm, gf, None
+
+
+class _HeadUpFn(torch.autograd.Function):
+    """(flow, mask) = (flow_prev + s * up_s(head[:2nd]), mask_prev + up_s(head[2nd])) — IFNet.py:115-119,177-178 / :118-119,169-170 — on
+    the fp32 channels-last head (ofsv_head_upsample_add); backward: ofsv_head_upsample_add_bwd (+ identity to the previous state)."""
+
+    @staticmethod
+    def forward(ctx, head, flow_prev, mask_prev, scale, nd, sp):
+        ctx.scale, ctx.nd, ctx.has_prev = scale, nd, flow_prev is not None
+        fp = flow_prev.contiguous() if flow_prev is not None else None
+        mp = mask_prev.contiguous() if mask_prev is not None else None
+        flow, mask = ops.head_upsample_add(head, fp, mp, nd, head.shape[0], sp, scale)
+        return flow, mask
+
+    @staticmethod
+    def backward(ctx, gflow, gmask):
+        gflow, gmask = gflow.contiguous(), gmask.contiguous()
+        ghead = ops.head_upsample_add_bwd(gflow, gmask, ctx.nd, ctx.scale)
+        return ghead, (gflow if ctx.has_prev else None), (gmask if ctx.has_prev else None), None, None, None
 
 
 def ifnet_forward_train(net: IFNet, x, scale=(4, 2, 1)):
@@ -483,8 +531,18 @@ def ifnet_forward_train(net: IFNet, x, scale=(4, 2, 1)):
     img0, img1, gt = x[:, :1].contiguous(), x[:, 1:2].contiguous(), x[:, 2:3].contiguous()
     flow_list, mask_list, warped = [], [], []
     w0, w1, flow, mask = img0, img1, None, None
+    fused = x.is_cuda          # student blocks: input packing and head up-sampling + accumulate as libofsv nodes (no torch resizes)
+    sp = tuple(x.shape[2:])
     for i in range(3):
-        if flow is None:
+        if fused:
+            s = int(scale[i])
+            if flow is None:
+                xin = _pack_input(img0, img1, None, None, None, None, s)
+            else:
+                xin = _PackInputFn.apply(img0, img1, w0, w1, mask, flow, s)
+            head = _BlockFn.apply(xin, tbs[i], True, *tbs[i].blk.parameters())
+            flow, mask = _HeadUpFn.apply(head, flow, mask, s, nd, sp)
+        elif flow is None:
             flow, mask = block_train(tbs[i], torch.cat((img0, img1), 1), None, scale[i])
         else:
             fd, md = block_train(tbs[i], torch.cat((img0, img1, w0, w1, mask), 1), flow, scale[i])

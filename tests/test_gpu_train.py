@@ -103,7 +103,7 @@ def test_block_function_gradients_vs_oracle_block(nd, c):
     s = 32 if nd == 3 else 64
     x = torch.randn((2, cin) + (s,) * nd, device=dev)
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    head = train._BlockFn.apply(xa, train._TrainBlock(blk), *blk.parameters())
+    head = train._BlockFn.apply(xa, train._TrainBlock(blk), False, *blk.parameters())
     old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
@@ -441,3 +441,58 @@ def test_pack_unpack_nhwc_kernels(shape, chans, cs):
     assert back.shape == cat.shape and torch.equal(back, cat.bfloat16().float())
     with pytest.raises(TypeError):
         ops.pack_nhwc([srcs[0].cpu()], cs)
+
+
+@pytest.mark.parametrize("nd,sp,scale", [(3, (16, 32, 48), 4), (3, (16, 16, 32), 2), (3, (8, 16, 16), 1), (2, (64, 96), 4), (2, (32, 48), 2),
+                                         (2, (16, 32), 1)])
+def test_pack_input_and_head_upsample_backward_vs_autograd(nd, sp, scale):
+    """ofsv_pack_block_input_bwd / ofsv_head_upsample_add_bwd against torch autograd through the reference's own expressions
+    (F.interpolate(x, 1/s), F.interpolate(flow, 1/s) / s, cat — IFNet.py:84-93 / :82-90; F.interpolate(head, s) * s + prev — :115-119)."""
+    import torch.nn.functional as F
+    from opticalflowscivis_b200 import _C, ops, train
+    dev = _dev()
+    torch.manual_seed(nd * 10 + scale)
+    mode = "bilinear" if nd == 2 else "trilinear"
+    n, nf = 2, 2 * nd
+    img0, img1 = torch.rand((n, 1) + sp, device=dev), torch.rand((n, 1) + sp, device=dev)
+    leaves = [torch.randn((n, c) + sp, device=dev, requires_grad=True) for c in (1, 1, 1, nf)]      # w0, w1, mask, flow
+    # pack: ours
+    xin = train._PackInputFn.apply(img0, img1, *leaves, scale)
+    g = torch.randn(xin.shape, device=dev).bfloat16()
+    g[..., 5 + nf:] = 0
+    xin.backward(g)
+    mine = [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    # pack: reference expression
+    x = torch.cat((img0, img1, leaves[0], leaves[1], leaves[2]), 1)
+    fl = leaves[3]
+    if scale != 1:
+        x = F.interpolate(x, scale_factor=1. / scale, mode=mode, align_corners=False)
+    fl = F.interpolate(fl, scale_factor=1. / scale, mode=mode, align_corners=False) * 1. / scale
+    ref_in = torch.cat((x, fl), 1)
+    gref = g[..., :5 + nf].float()
+    gref = gref[:, 0].permute(0, 3, 1, 2) if nd == 2 else gref.permute(0, 4, 1, 2, 3)
+    ref_in.backward(gref)
+    got_fwd = xin[..., :5 + nf].float()
+    got_fwd = got_fwd[:, 0].permute(0, 3, 1, 2) if nd == 2 else got_fwd.permute(0, 4, 1, 2, 3)
+    assert float((got_fwd - ref_in.detach()).abs().max()) <= 2e-2          # bf16 storage of the packed input
+    for a, t in zip(mine, leaves):
+        assert float((a - t.grad).abs().max()) <= 1e-5 * max(1.0, float(t.grad.abs().max()))
+    # head up-sampling + accumulate
+    hsp = tuple(v // scale for v in sp)
+    head = torch.randn((n, 1 if nd == 2 else hsp[0]) + (hsp if nd == 2 else hsp[1:]) + (8,), device=dev, requires_grad=True)
+    fprev, mprev = torch.randn((n, nf) + sp, device=dev, requires_grad=True), torch.randn((n, 1) + sp, device=dev, requires_grad=True)
+    flow, mask = train._HeadUpFn.apply(head, fprev, mprev, scale, nd, sp)
+    gf, gm = torch.randn_like(flow), torch.randn_like(mask)
+    torch.autograd.backward((flow, mask), (gf, gm))
+    gh, gfp, gmp = head.grad.clone(), fprev.grad.clone(), mprev.grad.clone()
+    head.grad = fprev.grad = mprev.grad = None
+    hn = head[:, 0].permute(0, 3, 1, 2) if nd == 2 else head.permute(0, 4, 1, 2, 3)
+    flow_r = fprev + F.interpolate(hn[:, :nf], scale_factor=scale, mode=mode, align_corners=False, recompute_scale_factor=False) * scale
+    mask_r = mprev + F.interpolate(hn[:, nf:nf + 1], scale_factor=scale, mode=mode, align_corners=False, recompute_scale_factor=False)
+    assert float((flow - flow_r).abs().max()) <= 1e-5 * max(1.0, float(flow_r.abs().max()))
+    torch.autograd.backward((flow_r, mask_r), (gf, gm))
+    assert float((gh[..., :nf + 1] - head.grad[..., :nf + 1]).abs().max()) <= 2e-5 * max(1.0, float(head.grad.abs().max()))
+    assert float(gh[..., nf + 1:].abs().max()) == 0.0
+    assert torch.equal(gfp, fprev.grad) and torch.equal(gmp, mprev.grad)

@@ -183,7 +183,7 @@ def test_block_function_gradients_match_oracle_block(nd, cpu_engine):
     x = torch.randn((2, cin) + (s,) * nd)
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     tb = train._TrainBlock(blk)
-    head = train._BlockFn.apply(xa, tb, *blk.parameters())
+    head = train._BlockFn.apply(xa, tb, False, *blk.parameters())
     hr = ref.conv0(xb)
     for i in range(4):
         hr = getattr(ref, f"convblock{i}")(hr) + hr
