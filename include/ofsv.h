@@ -251,6 +251,18 @@ int ofsv_conv_halo(const ofsv_conv_desc* d, const void* x, const void* w, const 
 int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_tap, void* w_out, int layout, void* stream);
 int ofsv_conv_halo_weight_layout(const ofsv_conv_desc* d);
 
+/* Batched re-packing for the training step (all layers of a block change every step): ofsv_conv_pack_record fills one HOST record per
+ * (layer, layout) — same arguments and result as ofsv_conv_pack_weights —, the caller uploads the array of records once and
+ * ofsv_conv_pack_weights_batched re-packs all of them in ONE launch whenever the fp32 tap forms changed. */
+typedef struct ofsv_pack_rec {
+  const float* w_tap;
+  void* w_out;
+  int32_t nblocks, Cin_s, Cout_w, KC;
+  uint16_t blk[OFSV_MAX_TAPS * 8];
+} ofsv_pack_rec;
+int ofsv_conv_pack_record(const ofsv_conv_desc* d, int layout, const float* w_tap, void* w_out, ofsv_pack_rec* rec);
+int ofsv_conv_pack_weights_batched(const ofsv_pack_rec* recs_dev, int nrec, void* stream);
+
 /* One-line description of the launch configuration ofsv_conv_halo would pick for `d` (kernel, super-tile depth, ring depths,
  * epilogue mode, shared memory, modelled tensor-pipe fraction of the MMA list); host only, nothing is launched. */
 int ofsv_conv_halo_describe(const ofsv_conv_desc* d, char* buf, int buflen);

@@ -42,6 +42,13 @@ class RefreshRec(ctypes.Structure):
                 ("n", ctypes.c_int32), ("pad_", ctypes.c_int32), ("kidx", ctypes.c_int16 * MAX_TAPS)]
 
 
+class PackRec(ctypes.Structure):
+    """Mirror of `ofsv_pack_rec` (include/ofsv.h)."""
+    _fields_ = [("w_tap", ctypes.c_void_p), ("w_out", ctypes.c_void_p),
+                ("nblocks", ctypes.c_int32), ("Cin_s", ctypes.c_int32), ("Cout_w", ctypes.c_int32), ("KC", ctypes.c_int32),
+                ("blk", ctypes.c_uint16 * (MAX_TAPS * 8))]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGS = {
     "ofsv_version": (ctypes.c_char_p, []),
@@ -76,6 +83,8 @@ _SIGS = {
     "ofsv_conv_tc": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_halo": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ofsv_conv_pack_weights": (_I, [ctypes.POINTER(ConvDesc), _P, _P, _I, _P]),
+    "ofsv_conv_pack_record": (_I, [ctypes.POINTER(ConvDesc), _I, _P, _P, ctypes.POINTER(PackRec)]),
+    "ofsv_conv_pack_weights_batched": (_I, [_P, _I, _P]),
     "ofsv_conv_halo_weight_layout": (_I, [ctypes.POINTER(ConvDesc)]),
     "ofsv_conv_stack_selfcheck": (_I, [ctypes.POINTER(ConvDesc), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
     "ofsv_conv_halo_describe": (_I, [ctypes.POINTER(ConvDesc), ctypes.c_char_p, _I]),

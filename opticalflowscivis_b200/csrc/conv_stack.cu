@@ -811,13 +811,13 @@ extern "C" int ofsv_conv_halo_weight_layout(const ofsv_conv_desc* d) {
   return sk_make_plan(d, &pl) ? OFSV_WL_STACK : OFSV_WL_TAP;
 }
 
-extern "C" int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_tap, void* w_out, int layout, void* stream) {
-  OFSV_REQUIRE(d && w_tap && w_out, "ofsv_conv_pack_weights: null pointer");
+// (tap, kc) order of the bf16 blocks of `layout` for the layer structure of `d`; returns the block count or a negative error.
+static int sk_pack_table(const ofsv_conv_desc* d, int layout, SkPackTable* T, int* KC_out) {
+  OFSV_REQUIRE(d != nullptr, "ofsv_conv_pack_weights: null descriptor");
   OFSV_REQUIRE(d->Cin_s >= 16 && d->Cin_s % 16 == 0 && d->Cout_w >= 16 && d->Cout_w % 16 == 0, "ofsv_conv_pack_weights: bad channels");
   OFSV_REQUIRE(d->nphase >= 1 && d->ntaps >= 1 && d->nphase * d->ntaps <= OFSV_MAX_TAPS, "ofsv_conv_pack_weights: nphase*ntaps out of range");
   OFSV_REQUIRE(layout == OFSV_WL_TAP || layout == OFSV_WL_STACK, "ofsv_conv_pack_weights: bad layout");
-  SkPackTable T;
-  memset(&T, 0, sizeof(T));
+  memset(T, 0, sizeof(*T));
   int KC, nkc, nblocks = 0;
   const int ntap = d->nphase * d->ntaps;
   if (layout == OFSV_WL_TAP) {
@@ -827,20 +827,65 @@ extern "C" int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_ta
     // on Cin_s (UPFlow's dense estimator reaches 576 channels = 9 chunks of 64 with 9 taps)
     OFSV_REQUIRE(nkc <= 64 && ntap * nkc <= OFSV_MAX_TAPS * SK_MAX_KC, "ofsv_conv_pack_weights: too many channel chunks (%d taps x %d chunks)", ntap, nkc);
     for (int t = 0; t < ntap; ++t)
-      for (int kc = 0; kc < nkc; ++kc) T.blk[nblocks++] = (uint16_t)((t << 6) | kc);
+      for (int kc = 0; kc < nkc; ++kc) T->blk[nblocks++] = (uint16_t)((t << 6) | kc);
   } else {
     SkPlan pl;
     if (!sk_make_plan(d, &pl)) { set_error("ofsv_conv_pack_weights: layer has no stacked form"); return OFSV_ENOSUP; }
     KC = pl.KC; nkc = pl.nkc;
     for (int g = 0; g < pl.ngroups; ++g)
       for (int kc = 0; kc < nkc; ++kc)
-        for (int s = 0; s < pl.g[g].nslots; ++s) T.blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 6) | kc);
+        for (int s = 0; s < pl.g[g].nslots; ++s) T->blk[nblocks++] = (uint16_t)((pl.g[g].slots[s].tap << 6) | kc);
     OFSV_REQUIRE(nblocks == ntap * nkc, "ofsv_conv_pack_weights: internal error (slot count %d != %d)", nblocks, ntap * nkc);
   }
+  *KC_out = KC;
+  return nblocks;
+}
+
+extern "C" int ofsv_conv_pack_weights(const ofsv_conv_desc* d, const float* w_tap, void* w_out, int layout, void* stream) {
+  OFSV_REQUIRE(d && w_tap && w_out, "ofsv_conv_pack_weights: null pointer");
+  SkPackTable T;
+  int KC = 0;
+  const int nblocks = sk_pack_table(d, layout, &T, &KC);
+  if (nblocks < 0) return nblocks;
   const int64_t total = (int64_t)nblocks * d->Cout_w * KC;
   const int grid = (int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184);
   conv_pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_tap, reinterpret_cast<__nv_bfloat16*>(w_out), T, nblocks, d->Cin_s, d->Cout_w, KC);
   return check_launch("conv_pack_weights_kernel");
+}
+
+// Batched form for the training step (every layer of a block is re-packed every step): ofsv_conv_pack_record fills one HOST record
+// per (layer, layout), the caller uploads the array once, ofsv_conv_pack_weights_batched re-packs all of them in ONE launch.
+static_assert(sizeof(ofsv_pack_rec) == 16 + 16 + sizeof(SkPackTable), "ofsv_pack_rec layout");
+__global__ void __launch_bounds__(256) conv_pack_weights_batched_kernel(const ofsv_pack_rec* __restrict__ recs) {
+  const ofsv_pack_rec& r = recs[blockIdx.y];
+  const int per = r.Cout_w * r.KC;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(r.w_out);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)r.nblocks * per; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), e = (int)(i - (int64_t)b * per);
+    const int row = e / r.KC, k = e - row * r.KC;
+    const int tap = r.blk[b] >> 6, kc = r.blk[b] & 63;
+    out[i] = __float2bfloat16_rn(__ldg(r.w_tap + ((int64_t)tap * r.Cin_s + kc * r.KC + k) * r.Cout_w + row));
+  }
+}
+
+extern "C" int ofsv_conv_pack_record(const ofsv_conv_desc* d, int layout, const float* w_tap, void* w_out, ofsv_pack_rec* rec) {
+  OFSV_REQUIRE(w_tap && w_out && rec, "ofsv_conv_pack_record: null pointer");
+  SkPackTable T;
+  int KC = 0;
+  const int nblocks = sk_pack_table(d, layout, &T, &KC);
+  if (nblocks < 0) return nblocks;
+  rec->w_tap = w_tap; rec->w_out = w_out;
+  rec->nblocks = nblocks; rec->Cin_s = d->Cin_s; rec->Cout_w = d->Cout_w; rec->KC = KC;
+  memcpy(rec->blk, T.blk, sizeof(T.blk));
+  return OFSV_OK;
+}
+
+extern "C" int ofsv_conv_pack_weights_batched(const ofsv_pack_rec* recs_dev, int nrec, void* stream) {
+  OFSV_REQUIRE(nrec >= 0 && nrec <= 65535, "ofsv_conv_pack_weights_batched: bad record count");
+  if (nrec == 0) return OFSV_OK;
+  OFSV_REQUIRE(recs_dev != nullptr && (reinterpret_cast<uintptr_t>(recs_dev) & 7u) == 0, "ofsv_conv_pack_weights_batched: null / misaligned record table");
+  conv_pack_weights_batched_kernel<<<dim3(64, (unsigned)nrec), 256, 0, (cudaStream_t)stream>>>(recs_dev);
+  return check_launch("conv_pack_weights_batched_kernel");
 }
 
 // Host-only check of the op list (no GPU): every (phase, tap, output slice) term must be covered exactly once, the first MMA

@@ -299,6 +299,28 @@ class _TrainBlock:
         dev = self.fwd[0].w_simt.device
         return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev), len(recs)
 
+    def _repack(self):
+        """bf16 operand blocks of every (layer, layout) that exists, re-packed IN PLACE by one launch (ofsv_conv_pack_weights_batched).
+        The table follows the set of packed forms (the first step creates them lazily, layer by layer, and decides halo vs per-tap
+        there); building it is a host-to-device copy, so the graph path refreshes once eagerly before it captures."""
+        layers = self.fwd + self.dgrad
+        keys = tuple(tuple(sorted(lay._packed)) for lay in layers)          # a layer that has not run yet has no packed form: the
+        if getattr(self, "_pack_table", None) is None or self._pack_keys != keys:    # engines pack it lazily, from the current tap form
+            recs = []
+            L = _C.lib()
+            for lay in layers:
+                d = lay._structure_desc()
+                for layout, w_out in sorted(lay._packed.items()):
+                    r = _C.PackRec()
+                    _C.check(L.ofsv_conv_pack_record(ctypes.byref(d), int(layout), _p(lay.w_simt), _p(w_out), ctypes.byref(r)))
+                    recs.append(r)
+            raw = b"".join(bytes(r) for r in recs) or b"\0" * 8
+            self._pack_table = (torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(layers[0].w_simt.device), len(recs))
+            self._pack_keys = keys
+        tab, n = self._pack_table
+        with ops._on(tab.device), ops._span("conv_pack_batched"):
+            _C.check(_C.lib().ofsv_conv_pack_weights_batched(_p(tab), n, _stream()))
+
     def refresh(self):
         key = self.blk._key()
         if key == self.key:
@@ -310,7 +332,7 @@ class _TrainBlock:
                 self.fwd, self.dgrad = self._build()
                 self.src_fwd, self.src_dgrad = self._sources()
                 self.kinv = torch.tensor(_convT_kflat(self.blk.nd), device=self.fwd[0].w_simt.device).argsort()
-                self._table, self._table_ptrs = None, None
+                self._table, self._table_ptrs, self._pack_table = None, None, None
                 if self.fwd[0].w_simt.is_cuda:          # built here, outside any CUDA-graph capture (it is a host-to-device copy)
                     self._table, self._table_ptrs = self._record_table(), tuple(p.data_ptr() for p in self.blk.parameters())
             elif self.fwd[0].w_simt.is_cuda:
@@ -320,8 +342,7 @@ class _TrainBlock:
                 tab, n = self._table
                 with ops._on(tab.device), ops._span("conv_refresh"):
                     _C.check(_C.lib().ofsv_conv_refresh_tapform(_p(tab), n, _stream()))
-                for lay in self.fwd + self.dgrad:
-                    lay._packed.clear()
+                self._repack()
             else:                                                           # tests/test_train_host.py: the same refresh with torch ops
                 for lay, (ws, bs, ps) in zip(self.fwd, self.src_fwd):
                     for sct in ws:
@@ -684,7 +705,10 @@ class Trainer:
                 for _ in range(2):
                     self.forward_backward(s_imgs, s_gt, device_guard=True)
             cur.wait_stream(side)
-            for tb in self.net._train_blocks:                 # the capture must contain the weight refresh
+            for tb in self.net._train_blocks:                 # tables complete (built outside the capture) ...
+                tb.key = None
+                tb.refresh()
+            for tb in self.net._train_blocks:                 # ... and the capture must contain the weight refresh
                 tb.key = None
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

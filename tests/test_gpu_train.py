@@ -496,3 +496,29 @@ def test_pack_input_and_head_upsample_backward_vs_autograd(nd, sp, scale):
     assert float((gh[..., :nf + 1] - head.grad[..., :nf + 1]).abs().max()) <= 2e-5 * max(1.0, float(head.grad.abs().max()))
     assert float(gh[..., nf + 1:].abs().max()) == 0.0
     assert torch.equal(gfp, fprev.grad) and torch.equal(gmp, mprev.grad)
+
+
+@pytest.mark.parametrize("nd,c", [(3, 64), (2, 96)])
+def test_train_block_batched_repack_equals_per_layer_pack(nd, c):
+    """After the first pass created the packed bf16 operand forms, every refresh re-packs them IN PLACE with one launch
+    (ofsv_conv_pack_weights_batched); the result must equal ofsv_conv_pack_weights of the refreshed tap forms, layer by layer."""
+    from opticalflowscivis_b200 import ifnet, ops, train
+    torch.manual_seed(9)
+    dev = _dev()
+    cin = 5 + 2 * nd
+    blk = ifnet.IFBlock(nd, cin, c=c).to(dev)
+    tb = train._TrainBlock(blk)
+    x = torch.randn((1, cin) + (32,) * nd, device=dev, requires_grad=True)
+    head = train._BlockFn.apply(x, tb, False, *blk.parameters())
+    head.backward(torch.randn_like(head))                      # every forward and input-gradient layer has run: packed forms exist
+    ptrs = {(i, k): v.data_ptr() for i, lay in enumerate(tb.fwd + tb.dgrad) for k, v in lay._packed.items()}
+    assert len(ptrs) >= 24
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    tb.refresh()
+    assert tb._pack_table is not None and tb._pack_table[1] == len(ptrs)
+    for i, lay in enumerate(tb.fwd + tb.dgrad):
+        for layout, w in lay._packed.items():
+            assert w.data_ptr() == ptrs[(i, layout)]            # in place (CUDA graphs keep pointing at it)
+            assert torch.equal(w, ops.conv_pack_weights(lay._structure_desc(), lay.w_simt, layout)), (i, layout)
