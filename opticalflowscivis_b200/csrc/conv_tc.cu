@@ -17,6 +17,7 @@
 
 namespace ofsv {
 
+std::atomic<int> g_tc_pair{-1};      // -1 auto, 0 never, 1 whenever there are two tiles (ofsv_set_tuning("tc_pair", v))
 constexpr int TC_MAX_STAGES = 16;   // pipeline depth is chosen per layer: small K chunks need more loads in flight
 constexpr int TC_M = 128;
 
@@ -28,7 +29,10 @@ struct TcParams {
   int8_t tap_off[OFSV_MAX_TAPS][4];
 };
 
-template <int KC>
+// MT = M tiles per CTA (1 or 2).  With 2, the CTA owns two consecutive tiles that SHARE every weight tile: the B operand — as many
+// bytes per K step as one A tile when Cout_w = 128 — is fetched once for two MMAs, into two accumulators (2 x Cout_w TMEM columns).
+// Layers with many tiles and large K (UPFlow's dense estimator: 1.3 MB of weights per tile) are bound by that L2 -> SM stream.
+template <int KC, int MT>
 __global__ void __launch_bounds__(192, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                    const float* __restrict__ bias, const float* __restrict__ prelu, const void* __restrict__ residual,
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(192, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   const int S = p.stages;
-  uint8_t* sB = smem + S * A_BYTES;
+  uint8_t* sB = smem + S * MT * A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + TC_MAX_STAGES;
@@ -48,16 +52,23 @@ __global__ void __launch_bounds__(192, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ph = blockIdx.z;
-  // tile -> (n, tz, ty, tx)
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_w; tile /= p.tiles_w;
-  const int ty = tile % p.tiles_h; tile /= p.tiles_h;
-  const int tz = tile % p.tiles_d;
-  const int n = tile / p.tiles_d;
-  const int ox0 = tx * p.tw, oy0 = ty * p.th, oz0 = tz * p.td;
+  // tile -> (n, tz, ty, tx); the CTA's tiles are MT * blockIdx.x + m
+  int tn[MT], ox0[MT], oy0[MT], oz0[MT];
+  const int ntiles = p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  const int nmt = min(MT, ntiles - (int)blockIdx.x * MT);      // live tiles of this CTA (the last CTA may own one)
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    int tile = min((int)blockIdx.x * MT + m, ntiles - 1);
+    const int tx = tile % p.tiles_w; tile /= p.tiles_w;
+    const int ty = tile % p.tiles_h; tile /= p.tiles_h;
+    const int tz = tile % p.tiles_d;
+    tn[m] = tile / p.tiles_d;
+    ox0[m] = tx * p.tw; oy0[m] = ty * p.th; oz0[m] = tz * p.td;
+  }
   const int kiters = p.ntaps * p.nkc;
-  uint32_t ncols = 32;
-  while ((int)ncols < p.Cout_w) ncols <<= 1;
+  uint32_t ncol1 = 32;
+  while ((int)ncol1 < p.Cout_w) ncol1 <<= 1;
+  const uint32_t ncols = ncol1 * MT;                           // power of two: MT is 1 or 2
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -78,15 +89,18 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 0) {
     // ================= TMA producer (one lane) =================
     if (lane == 0) {
-      const uint32_t tx_bytes = A_BYTES + p.Cout_w * KC * 2;
+      const uint32_t tx_bytes = nmt * A_BYTES + p.Cout_w * KC * 2;
       for (int it = 0; it < kiters; ++it) {
         const int s = it % S;
         if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
         const int t = it / p.nkc, kc = it - t * p.nkc;
         const int8_t* off = p.tap_off[ph * p.ntaps + t];
         mbar_expect_tx(&full[s], tx_bytes);
-        tma_load_5d(&tmA, &full[s], sA + s * A_BYTES, kc * KC, ox0 * p.in_stride + off[2], oy0 * p.in_stride + off[1],
-                    oz0 * p.in_stride + off[0], n);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          if (m < nmt)
+            tma_load_5d(&tmA, &full[s], sA + (s * MT + m) * A_BYTES, kc * KC, ox0[m] * p.in_stride + off[2], oy0[m] * p.in_stride + off[1],
+                        oz0[m] * p.in_stride + off[0], tn[m]);
         tma_load_2d(&tmB, &full[s], sB + s * b_bytes, 0, ((ph * p.ntaps + t) * p.nkc + kc) * p.Cout_w);
       }
     }
@@ -102,10 +116,15 @@ __global__ void __launch_bounds__(192, 1)
       mbar_wait(&full[s], (it / S) & 1);
       tcgen05_fence_after();
       if (leader) {
-        const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4), b_lo = b_lo0 + s * (b_bytes >> 4);
-        umma_bf16_lohi(tmem_base, a_lo, d_hi, b_lo, d_hi, idesc, it > 0 ? 1u : 0u);
+        const uint32_t b_lo = b_lo0 + s * (b_bytes >> 4);
 #pragma unroll
-        for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, 1u);
+        for (int m = 0; m < MT; ++m) {
+          if (m >= nmt) break;
+          const uint32_t a_lo = a_lo0 + (s * MT + m) * (A_BYTES >> 4), acc = tmem_base + m * ncol1;
+          umma_bf16_lohi(acc, a_lo, d_hi, b_lo, d_hi, idesc, it > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 1; k < KC / 16; ++k) umma_bf16_lohi(acc, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, 1u);
+        }
         tcgen05_commit(&empty[s]);          // frees the smem slot when these MMAs have read it
       }
       __syncwarp();
@@ -117,17 +136,21 @@ __global__ void __launch_bounds__(192, 1)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int rx = row % p.tw, ry = (row / p.tw) % p.th, rz = row / (p.tw * p.th);
-    const int ox = ox0 + rx, oy = oy0 + ry, oz = oz0 + rz;
-    const bool valid = ox < p.Wo && oy < p.Ho && oz < p.Do;
-    const int yz = oz * p.out_stride + ((ph >> 2) & 1), yy = oy * p.out_stride + ((ph >> 1) & 1), yx = ox * p.out_stride + (ph & 1);
-    const int64_t yo = ((((int64_t)n * p.Dy + yz) * p.Hy + yy) * p.Wy + yx) * p.Cout_s;
     mbar_wait(accum_full, 0);
     tcgen05_fence_after();
-    for (int c0 = 0; c0 < p.Cout_w; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!valid) continue;
-      epilogue_store16(v, c0, yo, p.Cout_s, p.has_prelu, p.has_residual, p.out_f32, bias, prelu, residual, y);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m >= nmt) break;
+      const int ox = ox0[m] + rx, oy = oy0[m] + ry, oz = oz0[m] + rz;
+      const bool valid = ox < p.Wo && oy < p.Ho && oz < p.Do;
+      const int yz = oz * p.out_stride + ((ph >> 2) & 1), yy = oy * p.out_stride + ((ph >> 1) & 1), yx = ox * p.out_stride + (ph & 1);
+      const int64_t yo = ((((int64_t)tn[m] * p.Dy + yz) * p.Hy + yy) * p.Wy + yx) * p.Cout_s;
+      for (int c0 = 0; c0 < p.Cout_w; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * ncol1 + c0), v);
+        if (!valid) continue;
+        epilogue_store16(v, c0, yo, p.Cout_s, p.has_prelu, p.has_residual, p.out_f32, bias, prelu, residual, y);
+      }
     }
   }
   tcgen05_fence_before();
@@ -150,14 +173,14 @@ PFN_encodeTiled get_tensor_map_encoder() {
   return fn;
 }
 
-template <int KC>
+template <int KC, int MT>
 static int launch_tc(const TcParams& P, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* prelu,
                      const void* residual, void* y, dim3 grid, cudaStream_t st) {
   const int b_bytes = (P.Cout_w * KC * 2 + 1023) & ~1023;
-  const size_t smem = 1024 + (size_t)P.stages * (TC_M * KC * 2 + b_bytes) + (2 * TC_MAX_STAGES + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)P.stages * (MT * TC_M * KC * 2 + b_bytes) + (2 * TC_MAX_STAGES + 1) * 8 + 16;
   static std::atomic<uint64_t> attr_done{0};   // per template instance, one bit per device
-  if (int e = ensure_dyn_smem(attr_done, conv_tc_kernel<KC>, 200 * 1024, "ofsv_conv_tc")) return e;
-  conv_tc_kernel<KC><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
+  if (int e = ensure_dyn_smem(attr_done, conv_tc_kernel<KC, MT>, 200 * 1024, "ofsv_conv_tc")) return e;
+  conv_tc_kernel<KC, MT><<<grid, 192, smem, st>>>(tmA, tmB, P, bias, prelu, residual, y);
   return check_launch("conv_tc_kernel");
 }
 
@@ -221,9 +244,18 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
   }
-  const dim3 grid((unsigned)ntiles, 1, (unsigned)d->nphase);
+  // two tiles per CTA when there are enough tiles to keep every SM busy with pairs and the K loop is long enough for the shared
+  // weight stream to matter (ofsv_set_tuning("tc_pair", 0 | 1) forces it off / on where it fits)
+  const int pair_mode = g_tc_pair.load(std::memory_order_relaxed);
+  const bool pair = pair_mode != 0 && ntiles >= 2 && (pair_mode > 0 || (ntiles >= 4 * (int64_t)device_num_sms() && d->ntaps * P.nkc >= 8));
+  const dim3 grid((unsigned)(pair ? cdiv(ntiles, 2) : ntiles), 1, (unsigned)d->nphase);
   cudaStream_t st = (cudaStream_t)stream;
-  if (KC == 64) return launch_tc<64>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
-  if (KC == 32) return launch_tc<32>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
-  return launch_tc<16>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  if (pair) {
+    if (KC == 64) return launch_tc<64, 2>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+    if (KC == 32) return launch_tc<32, 2>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+    return launch_tc<16, 2>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  }
+  if (KC == 64) return launch_tc<64, 1>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  if (KC == 32) return launch_tc<32, 1>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
+  return launch_tc<16, 1>(P, tmA, tmB, bias, prelu, residual, y, grid, st);
 }

@@ -522,3 +522,29 @@ def test_train_block_batched_repack_equals_per_layer_pack(nd, c):
         for layout, w in lay._packed.items():
             assert w.data_ptr() == ptrs[(i, layout)]            # in place (CUDA graphs keep pointing at it)
             assert torch.equal(w, ops.conv_pack_weights(lay._structure_desc(), lay.w_simt, layout)), (i, layout)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_conv_tc_paired_tiles_equal_single_tiles(nd):
+    """ofsv_conv_tc with two output tiles per CTA sharing every weight tile (ofsv_set_tuning('tc_pair', 1)) computes the same MMAs in
+    the same order per tile: bit-identical to the one-tile form on every layer family, odd tile counts and ragged edges included."""
+    from opticalflowscivis_b200 import _C, ifnet, ops
+    torch.manual_seed(21 + nd)
+    dev = _dev()
+    blk = ifnet.IFBlock(nd, 5 + 2 * nd, c=64).to(dev)
+    L = blk.layers()
+    n = 3
+    for li, s in ((0, 24), (1, 12), (2, 8), (10, 6), (11, 12)):
+        lay = L[li]
+        in_sp = ((1,) if nd == 2 else ()) + (s,) * nd
+        d, osp = lay.desc(n, in_sp, _C.BF16, has_residual=False)
+        x = torch.randn((n,) + (((1,) + (s,) * 2) if nd == 2 else (s,) * 3) + (lay.cin_s,), device=dev).bfloat16()
+        outs = []
+        for pair in (0, 1):
+            ops.set_tuning("tc_pair", pair)
+            y = torch.full((n,) + tuple(osp) + (lay.cout_s,), float("nan"), device=dev, dtype=torch.float32 if lay.out_f32 else torch.bfloat16)
+            ops.conv(d, x, lay.w_tc, lay.bias, lay.prelu, None, y, "tc")
+            outs.append(y)
+        ops.set_tuning("tc_pair", -1)
+        assert torch.isfinite(outs[1].float()).all(), li
+        assert torch.equal(outs[0], outs[1]), li
