@@ -276,7 +276,8 @@ int ofsv_conv_stack_selfcheck(const ofsv_conv_desc* d, int td, int* nops_out, do
  * environment variables in the launch path).  Keys: "stack_epilogue" (-1 auto, 0 = per-thread stores instead of the TMA-store
  * epilogue), "stack_td" (0 auto, 1|2|4 = super-tile depth when feasible), "warp_slab" (1 default, 0 = gather kernel only), "wgrad_brick" (-1 default: the
  * brick-window weight-gradient kernel where it is the fastest, 1 = wherever its windows fit, 0 = per-tap / tap-group kernels only), "tc_pair" (-1 default: ofsv_conv_tc gives a CTA two output tiles that share every weight tile
- * when the layer has many tiles and a long K loop; 0 never, 1 whenever there are two tiles). */
+ * when the layer has many tiles and a long K loop; 0 never, 1 whenever there are two tiles), "tc_stages" (0 default: ofsv_conv_tc's
+ * pipeline depth such that two CTAs fit an SM; 2..4 forces it). */
 int ofsv_set_tuning(const char* key, int value);
 
 /* ---- training tier: backward of conv()/deconv() + PReLU — what `loss_G.backward()` runs under every layer of

@@ -657,7 +657,7 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, __nv_bfloa
 static std::atomic<int> g_stack_epi{-1};     // -1 auto; 0 forces the direct epilogue (ofsv_set_tuning("stack_epilogue", v))
 static std::atomic<int> g_stack_td{0};
 void ofsv_set_wgrad_brick(int v);            // conv_bwd.cu
-extern std::atomic<int> g_tc_pair;           // conv_tc.cu
+extern std::atomic<int> g_tc_pair, g_tc_stages;   // conv_tc.cu
 extern std::atomic<int> g_warp_slab;         // warp3d_slab.cu       // 0 auto; 1 / 2 / 4 forces the super-tile depth when it is feasible
 
 struct SkConfig {
@@ -802,6 +802,7 @@ extern "C" int ofsv_set_tuning(const char* key, int value) {
   if (!strcmp(key, "conv0_ring")) { g_conv0_ring.store(value); return OFSV_OK; }
   if (!strcmp(key, "wgrad_brick")) { ofsv_set_wgrad_brick(value); return OFSV_OK; }
   if (!strcmp(key, "tc_pair")) { g_tc_pair.store(value); return OFSV_OK; }
+  if (!strcmp(key, "tc_stages")) { g_tc_stages.store(value); return OFSV_OK; }
   set_error("ofsv_set_tuning: unknown key '%s'", key);
   return OFSV_EINVAL;
 }

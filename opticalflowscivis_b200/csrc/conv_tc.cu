@@ -11,6 +11,7 @@
 //   D       = fp32 accumulator in tensor memory (128 lanes x N columns), read back with tcgen05.ld by 4 epilogue warps
 //             that fuse bias + PReLU + residual + dtype conversion and write channels-last output rows.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <algorithm>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -18,6 +19,7 @@
 namespace ofsv {
 
 std::atomic<int> g_tc_pair{-1};      // -1 auto, 0 never, 1 whenever there are two tiles (ofsv_set_tuning("tc_pair", v))
+std::atomic<int> g_tc_stages{0};     // 0 auto, 2..4 forces the pipeline depth (ofsv_set_tuning("tc_stages", v))
 constexpr int TC_MAX_STAGES = 16;   // pipeline depth is chosen per layer: small K chunks need more loads in flight
 constexpr int TC_M = 128;
 
@@ -213,12 +215,23 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
   P.tiles_w = (int)cdiv(d->Wo, P.tw); P.tiles_h = (int)cdiv(d->Ho, P.th); P.tiles_d = (int)cdiv(d->Do, P.td);
   P.has_prelu = d->has_prelu; P.has_residual = d->has_residual; P.out_f32 = d->out_dtype == OFSV_F32;
   memcpy(P.tap_off, d->tap_off, sizeof(P.tap_off));
-  {  // 4 stages: small-K layers hide TMA latency through CTA occupancy (up to ~10 CTAs/SM), measured faster than deep rings
-    const int kiters = d->ntaps * P.nkc;
-    P.stages = kiters < 4 ? kiters : 4;
-  }
   const int64_t ntiles = (int64_t)P.tiles_w * P.tiles_h * P.tiles_d * d->N;
   OFSV_REQUIRE(ntiles < (1ll << 31), "ofsv_conv_tc: too many tiles");
+  // two tiles per CTA when there are enough tiles to keep every SM busy with pairs and the K loop is long enough for the shared
+  // weight stream to matter (ofsv_set_tuning("tc_pair", 0 | 1) forces it off / on where it fits)
+  const int pair_mode = g_tc_pair.load(std::memory_order_relaxed);
+  const bool pair = pair_mode != 0 && ntiles >= 2 && (pair_mode > 0 || (ntiles >= 4 * (int64_t)device_num_sms() && d->ntaps * P.nkc >= 8));
+  {  // Pipeline depth.  The kernel is one tile (pair) per CTA, not persistent: while a CTA runs its prologue or its epilogue the tensor
+     // pipe of its SM idles unless ANOTHER CTA is resident.  Small stages get that from occupancy (4 stages, up to ~10 CTAs per SM,
+     // measured faster than deep rings); 32-48 KB stages (KC = 64 with 64-128 output channels) are cut to the depth at which two
+     // CTAs fit the 227 KB of an SM.  ofsv_set_tuning("tc_stages", 2..4) forces a depth.
+    const int kiters = d->ntaps * P.nkc;
+    const int stage_bytes = (pair ? 2 : 1) * TC_M * KC * 2 + ((d->Cout_w * KC * 2 + 1023) & ~1023);
+    int depth = g_tc_stages.load(std::memory_order_relaxed);
+    if (depth <= 0) depth = std::max(2, std::min(4, (112 * 1024 - 2048) / stage_bytes));
+    depth = std::max(1, std::min(depth, std::min(4, (200 * 1024 - 2048) / stage_bytes)));
+    P.stages = kiters < depth ? kiters : depth;
+  }
 
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB;
@@ -244,10 +257,6 @@ extern "C" int ofsv_conv_tc(const ofsv_conv_desc* d, const void* x, const void* 
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("ofsv_conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return OFSV_ECUDA; }
   }
-  // two tiles per CTA when there are enough tiles to keep every SM busy with pairs and the K loop is long enough for the shared
-  // weight stream to matter (ofsv_set_tuning("tc_pair", 0 | 1) forces it off / on where it fits)
-  const int pair_mode = g_tc_pair.load(std::memory_order_relaxed);
-  const bool pair = pair_mode != 0 && ntiles >= 2 && (pair_mode > 0 || (ntiles >= 4 * (int64_t)device_num_sms() && d->ntaps * P.nkc >= 8));
   const dim3 grid((unsigned)(pair ? cdiv(ntiles, 2) : ntiles), 1, (unsigned)d->nphase);
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) {
