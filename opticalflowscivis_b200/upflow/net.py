@@ -34,25 +34,37 @@ def _conv(cin, cout, kernel_size=3, stride=1, dilation=1, isReLU=True):
     return nn.Sequential(m)
 
 
-def _layers(m, in_map=None, cin_phys=None, out_f32=False):
+def _pad64(c):
+    """Physical width of a c-channel activation: wide ones are padded to a multiple of 64 so that the NEXT layer's K chunks are 64
+    channels (ofsv_conv_tc picks KC = 64 / 32 / 16 from Cin_s; with 16-channel chunks a 592-channel layer makes 37 tiny K steps per
+    tap: 0.53 ms for the first context layer of the finest level, `profiles/r03p_ncu_full_upflow_convs.csv`)."""
+    return _rup(c, 64) if c >= 96 else _rup(c, 16)
+
+
+def _layers(m, in_map=None, cin_phys=None, out_f32=False, cout_phys=None):
     """Tap-form layer(s) of one pwc_modules.conv: dilation as tap offsets, LeakyReLU(0.1) as a constant PReLU slope, the input
-    channels scattered to their PHYSICAL positions (in_map) when the channels-last input carries padding in the middle, and the
-    output split into <= 128-channel launches (ofsv_conv_tc's limit; FeatureExtractor's last level has 196)."""
+    channels scattered to their PHYSICAL positions (in_map; identity when only cin_phys is given: padding at the end), the output
+    zero-padded to cout_phys channels and split into <= 128-channel launches (ofsv_conv_tc's limit; FeatureExtractor's last level
+    has 196 -> 128 + 128)."""
     k, d = m.k, m.dilation
     w = m.weight.detach().float()
     cin = w.shape[1]
-    if in_map is not None:
+    if cin_phys is not None:
         wp = torch.zeros((w.shape[0], cin_phys) + tuple(w.shape[2:]), device=w.device)
-        wp[:, in_map] = w
+        wp[:, in_map if in_map is not None else list(range(cin))] = w
         w = wp
+    bias = m.bias.detach().float()
+    if cout_phys is not None and cout_phys > m.cout and not out_f32:
+        w = torch.cat((w, torch.zeros((cout_phys - m.cout,) + tuple(w.shape[1:]), device=w.device)), 0)
+        bias = torch.cat((bias, torch.zeros(cout_phys - m.cout, device=w.device)))
+    cout = w.shape[0]
     taps = [(0, (ky - (k - 1) // 2) * d, (kx - (k - 1) // 2) * d) for ky in range(k) for kx in range(k)]
     out = []
-    for lo in range(0, m.cout, 128):
-        hi = min(m.cout, lo + 128)
+    for lo in range(0, cout, 128):
+        hi = min(cout, lo + 128)
         w_tap = torch.stack([w[lo:hi, :, ky, kx].t() for ky in range(k) for kx in range(k)])        # [T][Cin][Cout]
         slope = torch.full((hi - lo,), 0.1, device=w.device) if m.leaky else None
-        lay = _Layer(2, m.stride, 1, 1, taps, w_tap, m.bias.detach().float()[lo:hi], slope, 8 if out_f32 else _rup(hi - lo, 16),
-                     out_f32=out_f32)
+        lay = _Layer(2, m.stride, 1, 1, taps, w_tap, bias[lo:hi], slope, 8 if out_f32 else _rup(hi - lo, 16), out_f32=out_f32)
         out.append(lay)
     return out
 
@@ -82,7 +94,14 @@ class FeatureExtractor(_Net):
 
     @torch.no_grad()
     def forward(self, x):
-        L = self._packed_layers(lambda: [[_layers(s[0][0]), _layers(s[1][0])] for s in self.convs])
+        def build():
+            out, cin_phys = [], 16
+            for st in self.convs:
+                cp = _pad64(st[0][0].cout)
+                out.append([_layers(st[0][0], cin_phys=cin_phys, cout_phys=cp), _layers(st[1][0], cin_phys=cp, cout_phys=cp)])
+                cin_phys = cp
+            return out
+        L = self._packed_layers(build)
         n, sp = x.shape[0], (1,) + tuple(x.shape[2:])
         a = _to_cl(x, 2, 16)
         out = []
@@ -107,19 +126,26 @@ class FlowEstimatorDense(_Net):
         self.n_channels = n
         self.conv_last = _conv(n, out_channel, isReLU=False)
 
+    def in_phys(self):
+        """Physical width of the input tensor `run` expects."""
+        return _rup(self.ch_in, 16)
+
     def _build(self):
-        # physical channels-last layout of x_i: [conv_i out | ... | conv_1 out | x (ch_in, zero-padded to a multiple of 16)]: all
-        # estimator widths are multiples of 16 except 8 (sgu), so pieces are padded individually and mapped
-        phys, logical = _rup(self.ch_in, 16), self.ch_in
+        # physical channels-last layout of x_i: [conv_i out | ... | conv_1 out | x (ch_in, zero-padded)], every piece padded on its own
+        # (to a multiple of 64 for the wide main estimator: the running totals 128, 256, 384, 512, 576, 640 then all give KC = 64) and
+        # the reference's logical input-channel order mapped onto it
+        phys = self.in_phys()
         maps = [list(range(self.ch_in))]                       # logical input channel -> physical position, per layer
-        pieces = [(self.ch_in, _rup(self.ch_in, 16))]          # (logical, physical) widths, newest first
+        pieces = [(self.ch_in, phys)]                          # (logical, physical) widths, newest first
         L = []
         for i, f in enumerate(self.f_channels):
             m = getattr(self, f"conv{i + 1}")[0]
-            L.append(_layers(m, in_map=maps[-1], cin_phys=phys))
-            pieces.insert(0, (f, _rup(f, 16)))
-            phys += _rup(f, 16)
-            logical += f
+            fp = _rup(f, 16)
+            if self.ch_in >= 96 and phys % 64 == 0:            # keep the running total a multiple of 64 (96 -> 128, the last 32 -> 64)
+                fp = _rup(f, 64) if (f >= 96 or i == len(self.f_channels) - 1) else fp
+            L.append(_layers(m, in_map=maps[-1], cin_phys=phys, cout_phys=fp))
+            pieces.insert(0, (f, fp))
+            phys += fp
             mp, off = [], 0
             for lg, ph in pieces:
                 mp += list(range(off, off + lg))
@@ -154,9 +180,10 @@ class ContextNetwork(_Net):
     @torch.no_grad()
     def run(self, x_cl, in_map, n, sp):
         def build():
-            L = [_layers(self.convs[0][0], in_map=in_map, cin_phys=x_cl.shape[-1])]
-            L += [_layers(self.convs[i][0]) for i in range(1, 6)]
-            L.append(_layers(self.convs[6][0], out_f32=True))
+            cp = [_pad64(self.convs[i][0].cout) for i in range(6)]
+            L = [_layers(self.convs[0][0], in_map=in_map, cin_phys=x_cl.shape[-1], cout_phys=cp[0])]
+            L += [_layers(self.convs[i][0], cin_phys=cp[i - 1], cout_phys=cp[i]) for i in range(1, 6)]
+            L.append(_layers(self.convs[6][0], cin_phys=cp[5], out_f32=True))
             return L
         L = self._packed_layers(build)
         x = x_cl
@@ -223,9 +250,9 @@ class UPFlowNet(nn.Module):
         net = self.conv_1x1[l]
         key = (net[0].weight.data_ptr(), net[0].weight._version, net[0].bias._version)
         if getattr(net, "_pk", None) != key:
-            net._pl, net._pk = _layers(net[0]), key
+            net._pl, net._pk = _layers(net[0], cin_phys=_pad64(net[0].cin)), key
         n, sp = x.shape[0], (1,) + tuple(x.shape[2:])
-        y, _ = _run(net._pl, _to_cl(x, 2, _rup(x.shape[1], 16)), n, sp)
+        y, _ = _run(net._pl, _to_cl(x, 2, _pad64(x.shape[1])), n, sp)
         return _from_cl(y, 32, 2)
 
     @torch.no_grad()
@@ -245,7 +272,7 @@ class UPFlowNet(nn.Module):
         x_cl = _to_cl([corr, feat_1x1, flow_up], 2, _rup(corr.shape[1] + feat_1x1.shape[1] + 2, 16))    # upflow.py:657, one launch
         x5, x5_map, flow_res = self.flow_estimators.run(x_cl, n, (1, h, w))
         flow_ = flow_up + flow_res
-        ctx_in = torch.cat((x5, _to_cl(flow_, 2, 16)), -1)
+        ctx_in = torch.cat((x5, _to_cl(flow_, 2, 64 if x5.shape[-1] % 64 == 0 else 16)), -1)     # 576 + 64 = 640 channels: KC = 64
         ctx_map = x5_map + [x5.shape[-1], x5.shape[-1] + 1]
         flow_fine = self.context_networks.run(ctx_in, ctx_map, n, (1, h, w))
         return flow_up, flow_res + flow_fine
