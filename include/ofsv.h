@@ -156,7 +156,7 @@ int ofsv_pack_block_input(const float* img0, const float* img1, const float* war
  * (Dn,Hn,Wn) = (D,H,W)/scale (see ofsv_conv_desc.out_s2d); only interior sub-cells are written. */
 
 /* Layout changes between the reference's fp32 NC(D)HW tensors and the engine's channels-last bf16 activations, P = D*H*W pixels:
- *   ofsv_pack_nhwc_bf16 : dst [N][P][Cs] bf16 = the channel concatenation of 1..4 sources [N][channels[i]][P] fp32 (host arrays of
+ *   ofsv_pack_nhwc_bf16 : dst [N][P][Cs] bf16 = the channel concatenation of 1..8 sources [N][channels[i]][P] fp32 (host arrays of
  *                         device pointers / channel counts), zero-padded to Cs — torch.cat + pad + cast in one pass, e.g. the
  *                         estimator input torch.cat([corr, x_1x1, flow], 1) of UPFlow/model/upflow.py:657;
  *   ofsv_unpack_nhwc_f32: dst [N][C][P] fp32 = the first C channels of src [N][P][Cs] bf16. */

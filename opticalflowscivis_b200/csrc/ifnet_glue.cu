@@ -356,10 +356,10 @@ extern "C" int ofsv_head_upsample_add(const float* head, int Cs, const float* fl
 
 // ------------------------------------------------------------------------------------------------ layout changes
 // NC(P) fp32 (P = product of the spatial dims) <-> channels-last bf16 [N][P][Cs], through a 32-pixel x 64-channel shared tile so that
-// both sides move 128-byte segments.  pack concatenates up to four sources along the channel axis (torch.cat + zero padding + cast
+// both sides move 128-byte segments.  pack concatenates up to eight sources along the channel axis (torch.cat + zero padding + cast
 // of the estimator input torch.cat([corr, x_1x1, flow], 1), UPFlow/model/upflow.py:657, in one pass) and zero-fills the padding.
 namespace ofsv {
-struct NhwcSrc { const float* p[4]; int c[4]; int nsrc; };
+struct NhwcSrc { const float* p[8]; int c[8]; int nsrc; };
 constexpr int NHWC_TILES = 8;
 __global__ void __launch_bounds__(256) pack_nhwc_kernel(const NhwcSrc S, __nv_bfloat16* __restrict__ dst, int64_t P, int Cs, int tiles) {
   __shared__ float tile[32][65];
@@ -427,11 +427,11 @@ __global__ void __launch_bounds__(256) unpack_nhwc_kernel(const __nv_bfloat16* _
 }  // namespace ofsv
 
 extern "C" int ofsv_pack_nhwc_bf16(const float* const* srcs, const int* channels, int nsrc, void* dst, int N, int64_t P, int Cs, void* stream) {
-  OFSV_REQUIRE(srcs && channels && nsrc >= 1 && nsrc <= 4, "ofsv_pack_nhwc_bf16: 1..4 sources");
+  OFSV_REQUIRE(srcs && channels && nsrc >= 1 && nsrc <= 8, "ofsv_pack_nhwc_bf16: 1..8 sources");
   OFSV_REQUIRE(N >= 0 && N <= 65535 && P >= 0 && Cs >= 8 && Cs % 8 == 0, "ofsv_pack_nhwc_bf16: bad shape");
   ofsv::NhwcSrc S;
   int total = 0;
-  for (int i = 0; i < 4; ++i) { S.p[i] = i < nsrc ? srcs[i] : nullptr; S.c[i] = i < nsrc ? channels[i] : 0; total += S.c[i]; }
+  for (int i = 0; i < 8; ++i) { S.p[i] = i < nsrc ? srcs[i] : nullptr; S.c[i] = i < nsrc ? channels[i] : 0; total += S.c[i]; }
   S.nsrc = nsrc;
   OFSV_REQUIRE(total <= Cs, "ofsv_pack_nhwc_bf16: %d source channels do not fit Cs = %d", total, Cs);
   if ((int64_t)N * P == 0) return OFSV_OK;

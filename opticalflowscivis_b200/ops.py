@@ -439,12 +439,12 @@ def s2d_shape(n, sp, c):
 
 
 def pack_nhwc(srcs, cs):
-    """Channel concatenation of 1..4 fp32 (N,C_i,*sp) CUDA tensors -> channels-last bf16 [N][D][H][W][cs] (D = 1 for 2-D inputs),
+    """Channel concatenation of 1..8 fp32 (N,C_i,*sp) CUDA tensors -> channels-last bf16 [N][D][H][W][cs] (D = 1 for 2-D inputs),
     zero-padded channels, in one launch (ofsv_pack_nhwc_bf16)."""
     srcs = [_cuda_f32(t, "pack_nhwc source") for t in srcs]
     n, sp = srcs[0].shape[0], tuple(srcs[0].shape[2:])
-    if not 1 <= len(srcs) <= 4 or any(t.shape[0] != n or tuple(t.shape[2:]) != sp for t in srcs):
-        raise ValueError("pack_nhwc: 1..4 tensors with equal batch and spatial dims")
+    if not 1 <= len(srcs) <= 8 or any(t.shape[0] != n or tuple(t.shape[2:]) != sp for t in srcs):
+        raise ValueError("pack_nhwc: 1..8 tensors with equal batch and spatial dims")
     pix = 1
     for v in sp:
         pix *= v

@@ -34,7 +34,7 @@ def run_tap_layer(lay, x, n, in_sp):
 
 
 def _to_cl(x, nd, cs):
-    """fp32 (N,C,*sp) tensor — or a list of up to four, concatenated along the channels — -> bf16 channels-last [N][D][H][W][cs]
+    """fp32 (N,C,*sp) tensor — or a list of up to eight, concatenated along the channels — -> bf16 channels-last [N][D][H][W][cs]
     with zero-padded channels, one launch (ofsv_pack_nhwc_bf16)."""
     return ops.pack_nhwc(list(x) if isinstance(x, (list, tuple)) else [x], cs)
 

@@ -13,9 +13,9 @@ What runs where
   * optimizer: `optim.FusedAdamW` on a flat `GradientBucket`, one all-reduce of the bucket when a process group is up (the
     reference wraps the net in DDP when local_rank != -1: RIFE.py:31-32);
   * the student blocks' input packing (resize 1/s of the concatenation, flow / s) and head up-sampling + accumulate are libofsv
-    autograd nodes as well (ofsv_pack_block_input[_bwd], ofsv_head_upsample_add[_bwd]); what is left between the nodes (sigmoid,
-    blend, the loss reductions, the teacher block's resize-free concat) is plain torch autograd on fp32 NC(D)HW tensors — element-wise
-    launches, none of them a convolution or a sampler.
+    autograd nodes as well (ofsv_pack_block_input[_bwd], ofsv_head_upsample_add[_bwd]; the teacher's concat: ofsv_pack_nhwc_bf16 /
+    ofsv_unpack_nhwc_f32); what is left between the nodes (sigmoid, blend, the loss reductions) is plain torch autograd on fp32
+    NC(D)HW tensors — element-wise launches, none of them a convolution or a sampler.
 There is no CPU path: everything raises on CPU tensors like the rest of the package.
 """
 from __future__ import annotations
@@ -514,6 +514,27 @@ class _PackInputFn(torch.autograd.Function):
         return None, None, g0, g1, gm, gf, None
 
 
+class _PackCatFn(torch.autograd.Function):
+    """The teacher block's input torch.cat((img0, img1, warped0, warped1, mask, gt, flow), 1) at scale 1 (IFNet.py:215 / :213; the
+    resizes of IFBlock.forward are identities there) as bf16 channels-last [N][D][H][W][16] in one launch (ofsv_pack_nhwc_bf16);
+    backward: ofsv_unpack_nhwc_f32 of the input gradient, split back into the sources."""
+
+    @staticmethod
+    def forward(ctx, *srcs):
+        ctx.chans = [t.shape[1] for t in srcs]
+        ctx.nd = srcs[0].dim() - 2
+        return ops.pack_nhwc([t.contiguous() for t in srcs], 16)
+
+    @staticmethod
+    def backward(ctx, gx):
+        g = ops.unpack_nhwc(gx.contiguous(), sum(ctx.chans), ctx.nd)
+        out, off = [], 0
+        for i, c in enumerate(ctx.chans):
+            out.append(g[:, off:off + c] if ctx.needs_input_grad[i] else None)
+            off += c
+        return tuple(out)
+
+
 class _HeadUpFn(torch.autograd.Function):
     """(flow, mask) = (flow_prev + s * up_s(head[:2nd]), mask_prev + up_s(head[2nd])) — IFNet.py:115-119,177-178 / :118-119,169-170 — on
     the fp32 channels-last head (ofsv_head_upsample_add); backward: ofsv_head_upsample_add_bwd (+ identity to the previous state)."""
@@ -573,11 +594,17 @@ def ifnet_forward_train(net: IFNet, x, scale=(4, 2, 1)):
         w0 = warp(img0, flow[:, :nd].contiguous())
         w1 = warp(img1, flow[:, nd:2 * nd].contiguous())
         warped.append((w0, w1))
-    fd, md = block_train(tbs[3], torch.cat((img0, img1, w0, w1, mask, gt), 1), flow, 1)
-    flow_teacher = flow + fd
+    if fused:
+        xin = _PackCatFn.apply(img0, img1, w0, w1, mask, gt, flow)
+        head = _BlockFn.apply(xin, tbs[3], True, *tbs[3].blk.parameters())
+        flow_teacher, mask_tea_logit = _HeadUpFn.apply(head, flow, mask, 1, nd, sp)
+        fd = md = None
+    else:
+        fd, md = block_train(tbs[3], torch.cat((img0, img1, w0, w1, mask, gt), 1), flow, 1)
+        flow_teacher, mask_tea_logit = flow + fd, mask + md
     w0t = warp(img0, flow_teacher[:, :nd].contiguous())
     w1t = warp(img1, flow_teacher[:, nd:2 * nd].contiguous())
-    mask_teacher = torch.sigmoid(mask + md)
+    mask_teacher = torch.sigmoid(mask_tea_logit)
     merged_teacher = w0t * mask_teacher + w1t * (1 - mask_teacher)
     merged, loss_distill = [], 0
     for i in range(3):
